@@ -1,0 +1,162 @@
+"""CPU tests pinning the oracle: (1) against golden vectors produced by executing the reference's own
+loss/matcher code (tests/golden/make_golden.py), (2) the C LSAP restatement against the installed scipy
+(the reference's real third-party arithmetic) incl. the tie known-answer table of SURVEY Appendix C,
+(3) model pieces against independent implementations (torchvision resnet50, F.multi_head_attention_forward)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import detr_oracle as O
+from oracle.lsap_oracle import lsap
+
+
+def test_cost_matrix_and_indices_vs_reference_golden(golden):
+    g = golden
+    B = g["m_logits"].shape[0]
+    for b in range(B):
+        tb, tc = torch.from_numpy(g["m_t_bbox"][b]), torch.from_numpy(g["m_t_class"][b])
+        pb, pc = torch.from_numpy(g["m_boxes"][b]), torch.from_numpy(g["m_logits"][b])
+        C, _, _ = O.cost_matrix(tb, tc, pb, pc)
+        np.testing.assert_allclose(C.numpy(), g[f"m_cost_{b}"], rtol=1e-5, atol=2e-6)
+        ti, pi, ts, ps, tbb, tcc = O.hungarian_matching(tb, tc, pb, pc)
+        assert np.array_equal(ti.numpy(), g[f"m_t_indices_{b}"])
+        assert np.array_equal(pi.numpy(), g[f"m_p_indices_{b}"])
+        assert np.array_equal(ps.numpy(), g[f"m_p_selector_{b}"])
+        assert np.array_equal(ts.numpy(), g[f"m_t_selector_{b}"])
+        np.testing.assert_array_equal(tbb.numpy(), g[f"m_tb_{b}"])
+        np.testing.assert_array_equal(tcc.numpy(), g[f"m_tc_{b}"])
+        # the C restatement on the reference's own cost matrix
+        r, c = lsap(g[f"m_cost_{b}"])
+        assert np.array_equal(r, g[f"m_p_indices_{b}"]) and np.array_equal(c, g[f"m_t_indices_{b}"])
+
+
+def test_set_criterion_vs_reference_golden(golden):
+    g = golden
+    logits, boxes = torch.from_numpy(g["l_logits"]), torch.from_numpy(g["l_boxes"])
+    out = {"pred_logits": logits[5], "pred_boxes": boxes[5],
+           "aux": [{"pred_logits": logits[i], "pred_boxes": boxes[i]} for i in range(5)]}
+    total, losses = O.get_losses(out, torch.from_numpy(g["l_t_bbox"]), torch.from_numpy(g["l_t_class"]), 91)
+    assert abs(float(total) - float(g["l_total"])) < 2e-4 * abs(float(g["l_total"]))
+    for k, v in zip(g["l_keys"], g["l_values"]):
+        assert abs(float(losses[str(k)]) - float(v)) < 1e-5 + 1e-4 * abs(float(v)), k
+    assert len(losses) == 36
+
+
+KAT = [  # SURVEY.md Appendix C (scipy 1.18.1)
+    ([[1], [1], [.5], [.5]], [2], [0]),
+    ([[1, 2], [1, 2], [.5, 3], [.5, 3]], [0, 2], [1, 0]),
+    (np.ones((6, 2)), [0, 1], [0, 1]),
+    (np.ones((3, 3)), [0, 1, 2], [0, 1, 2]),
+    ([[0, 0], [1, 1], [2, 2], [3, 3], [4, 4]], [0, 1], [0, 1]),
+    ([[3, 3], [1, 1], [1, 1], [2, 2], [5, 5]], [1, 2], [0, 1]),
+    (np.zeros((2, 5)), [0, 1], [0, 1]),
+    ([[1, np.inf], [2, 3], [np.inf, 1]], None, None),
+]
+
+
+def test_lsap_known_answers():
+    from scipy.optimize import linear_sum_assignment
+    for cost, rows, cols in KAT:
+        c = np.asarray(cost, np.float32)
+        r0, c0 = linear_sum_assignment(c)
+        r1, c1 = lsap(c)
+        assert np.array_equal(r0, r1) and np.array_equal(c0, c1)
+        if rows is not None:
+            assert list(r1) == rows and list(c1) == cols
+    r, c = lsap(np.zeros((100, 0), np.float32))
+    assert len(r) == 0 and len(c) == 0
+    with pytest.raises(ValueError):
+        lsap(np.array([[1, np.nan], [0, 1]], np.float32))
+
+
+def test_lsap_vs_scipy_random_and_ties():
+    from scipy.optimize import linear_sum_assignment
+    rs = np.random.RandomState(7)
+    for it in range(4000):
+        n = rs.randint(0, 100) if it % 2 else rs.randint(0, 30)
+        if it % 3 == 0:
+            c = rs.rand(100, n).astype(np.float32)
+        elif it % 3 == 1:
+            c = rs.randint(0, 4, (100, n)).astype(np.float32)
+        else:
+            c = (rs.randint(0, 3, (100, n)) * 0.25).astype(np.float32) - rs.randint(0, 2, (100, 1))
+        r0, c0 = linear_sum_assignment(c)
+        r1, c1 = lsap(c)
+        assert np.array_equal(r0, r1) and np.array_equal(c0, c1)
+
+
+def test_backbone_vs_torchvision():
+    tv = pytest.importorskip("torchvision")
+    m = tv.models.resnet50(weights=None).eval()
+    P = O.init_params(seed=3)
+    sd = m.state_dict()
+
+    def put(conv, name):
+        sd[conv + ".weight"] = P[name].permute(3, 2, 0, 1).contiguous()
+
+    def putbn(bn, name):
+        sd[bn + ".weight"], sd[bn + ".bias"] = P[name + "/weight"], P[name + "/bias"]
+        sd[bn + ".running_mean"], sd[bn + ".running_var"] = P[name + "/running_mean"], P[name + "/running_var"]
+    put("conv1", "backbone/conv1/kernel")
+    putbn("bn1", "backbone/bn1")
+    for li, (nb, _, _, _) in enumerate(O.RESNET_STAGES["resnet50"]):
+        for b in range(nb):
+            t, p = f"layer{li + 1}.{b}", f"backbone/layer{li + 1}/{b}"
+            for k in (1, 2, 3):
+                put(f"{t}.conv{k}", f"{p}/conv{k}/kernel")
+                putbn(f"{t}.bn{k}", f"{p}/bn{k}")
+            if b == 0:
+                put(f"{t}.downsample.0", f"{p}/downsample_0/kernel")
+                putbn(f"{t}.downsample.1", f"{p}/downsample_1")
+    m.load_state_dict(sd)
+    x = torch.randn(1, 67, 93, 3)
+    with torch.no_grad():
+        y = O.backbone_forward(P, x)
+        xt = x.permute(0, 3, 1, 2)
+        z = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(xt))))))))
+    assert y.shape == (1, 3, 3, 2048)
+    torch.testing.assert_close(y.permute(0, 3, 1, 2), z, rtol=2e-4, atol=2e-4)
+
+
+def test_backbone_shapes_800x1333_formula():
+    # spatial sizes of SURVEY 8: 800x1333 -> 400x667 -> 200x334 -> 100x167 -> 50x84 -> 25x42
+    def o(n, k, s, p):
+        return (n + 2 * p - k) // s + 1
+    h, w = o(800, 7, 2, 3), o(1333, 7, 2, 3)
+    assert (h, w) == (400, 667)
+    h, w = o(h, 3, 2, 1), o(w, 3, 2, 1)
+    assert (h, w) == (200, 334)
+    for exp in ((100, 167), (50, 84), (25, 42)):
+        h, w = o(h, 3, 2, 1), o(w, 3, 2, 1)
+        assert (h, w) == exp
+
+
+def test_mha_vs_torch_functional():
+    P = O.init_params(seed=5, num_encoder_layers=1, num_decoder_layers=1)
+    p = "transformer/encoder/layer_0/self_attn"
+    q, k, v = torch.randn(3, 11, 256), torch.randn(3, 37, 256), torch.randn(3, 37, 256)
+    a = O.mha(P, p, q, k, v)
+    b, _ = F.multi_head_attention_forward(
+        q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1), 256, 8,
+        P[p + "/in_proj_kernel"], P[p + "/in_proj_bias"], None, None, False, 0.0,
+        P[p + "/out_proj_kernel"], P[p + "/out_proj_bias"], training=False, need_weights=False)
+    torch.testing.assert_close(a, b.transpose(0, 1), rtol=1e-4, atol=1e-5)
+
+
+def test_forward_shapes_and_param_count():
+    P = O.init_params(seed=0)
+    assert sum(p.numel() for n, p in P.items() if O.param_group(n)) == 41499168   # SURVEY 8a totals
+    with torch.no_grad():
+        out = O.detr_forward(P, torch.randn(1, 64, 96, 3))
+    assert out["pred_logits"].shape == (1, 100, 92) and out["pred_boxes"].shape == (1, 100, 4)
+    assert len(out["aux"]) == 5
+
+
+def test_pos_embedding_layout():
+    pe = O.position_embedding_sine(3, 4)
+    assert pe.shape == (3, 4, 256)
+    # first 128 channels depend on the row only, last 128 on the column only (concat [pos_y, pos_x])
+    assert torch.allclose(pe[0, 0, :128], pe[0, 3, :128]) and torch.allclose(pe[0, 1, 128:], pe[2, 1, 128:])
+    y = (1.0 / (3 + 1e-6)) * 2 * np.pi
+    assert abs(float(pe[0, 0, 0]) - np.sin(y)) < 1e-6 and abs(float(pe[0, 0, 1]) - np.cos(y)) < 1e-6
