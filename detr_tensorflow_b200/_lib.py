@@ -1,0 +1,108 @@
+"""ctypes binding of libdetrb.so (C ABI declared in include/detrb.h).
+
+The shared object is built in-tree by ``build()`` (nvcc, sm_100a only) and loaded lazily.  There is no
+fallback: if the library is missing or the device is not a B200-class GPU every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint32,
+                    c_uint64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_HERE, "libdetrb.so")
+_SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu"]
+_lib = None
+
+EXPORTS = [
+    "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
+    "detrb_attn_bwd", "detrb_layernorm_fwd", "detrb_layernorm_bwd", "detrb_add_rowbcast", "detrb_add",
+    "detrb_image_to_nhwc4", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
+    "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",
+]
+
+
+def sources():
+    return [os.path.join(_CSRC, s) for s in _SOURCES if os.path.exists(os.path.join(_CSRC, s))]
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> detr_tensorflow_b200/libdetrb.so (in-tree)."""
+    srcs = sources()
+    deps = srcs + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "detrb.h"))
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return _SO
+
+
+class IgemmParams(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("W", c_void_p), ("M", c_int), ("N", c_int), ("K", c_int), ("lda", c_int), ("ldw", c_int),
+        ("batch", c_int), ("IH", c_int), ("IW", c_int), ("Cin", c_int), ("OH", c_int), ("OW", c_int),
+        ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("mode", c_int),
+        ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int), ("mask", c_void_p), ("ldm", c_int),
+        ("mask_scale", c_float), ("relu", c_int), ("sigmoid", c_int), ("drop_p", c_float), ("seed", c_uint64),
+        ("site", c_uint32), ("seed_ptr", c_void_p), ("C", c_void_p), ("ldc", c_int), ("Cf", c_void_p), ("ldcf", c_int),
+        ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int),
+    ]
+
+
+class WgradParams(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int), ("dY", c_void_p), ("ldy", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+        ("batch", c_int), ("IH", c_int), ("IW", c_int), ("Cin", c_int), ("OH", c_int), ("OW", c_int),
+        ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int),
+        ("rowscale", c_void_p), ("dW", c_void_p), ("ldw", c_int), ("dbias", c_void_p),
+    ]
+
+
+class AttnFwdParams(Structure):
+    _fields_ = [
+        ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p), ("ldq", c_int), ("ldk", c_int), ("ldv", c_int),
+        ("O", c_void_p), ("ldo", c_int), ("lse", c_void_p), ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int),
+        ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64), ("site", c_uint32), ("seed_ptr", c_void_p),
+    ]
+
+
+class AttnBwdParams(Structure):
+    _fields_ = [
+        ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p), ("O", c_void_p), ("dO", c_void_p),
+        ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldo", c_int), ("lddo", c_int),
+        ("lse", c_void_p), ("delta", c_void_p), ("dQ", c_void_p), ("dK", c_void_p), ("dV", c_void_p),
+        ("lddq", c_int), ("lddk", c_int), ("lddv", c_int), ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int),
+        ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64), ("site", c_uint32), ("seed_ptr", c_void_p),
+    ]
+
+
+def lib():
+    """Load libdetrb.so (building it first if the sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        build()
+    L = ctypes.CDLL(_SO)
+    L.detrb_last_error.restype = c_char_p
+    for name in EXPORTS:
+        getattr(L, name)         # raises AttributeError if a declared symbol is missing
+    _lib = L
+    return L
+
+
+class DetrbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise DetrbError("libdetrb error %d: %s" % (rc, lib().detrb_last_error().decode()))

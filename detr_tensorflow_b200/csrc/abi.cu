@@ -1,0 +1,28 @@
+// abi.cu -- version / error plumbing of the C ABI (include/detrb.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void detrb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int detrb_version(void) { return 100; }   // 0.1.0
+
+extern "C" const char *detrb_last_error(void) { return g_err; }
+
+extern "C" int detrb_check_device(void)
+{
+    int dev = 0;
+    DETRB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    DETRB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        DETRB_FAIL(DETRB_E_ARCH, "libdetrb is built for sm_100a only; device %d is sm_%d%d (no fallback path exists)", dev, prop.major, prop.minor);
+    return DETRB_OK;
+}

@@ -1,0 +1,442 @@
+// attention.cu -- fused multi-head attention core, forward and backward, head_dim = 32.
+//   O = dropout(softmax(Q K^T)) V   per (batch, head);  no S x S tensor ever reaches HBM.
+// Replaces transformer.py:308-345 (the reshape/transpose x4, matmul QK^T, softmax, dropout, matmul PV)
+// and its gradient.  The 32^-0.5 query scaling (transformer.py:307) is applied to the scores (p.scale).
+// Tensor path: mma.sync bf16 (flash-attention-2 style online softmax, probabilities stay in registers).
+#include "common.cuh"
+
+namespace {
+
+constexpr int DH = 32;
+constexpr int TQ = 64;             // queries per CTA (fwd / dQ), keys per CTA (dK/dV)
+constexpr int TKV = 64;            // keys (or queries) per inner tile
+constexpr int LDH = DH + 8;        // smem row stride (bf16): 80 B
+constexpr float LOG2E = 1.4426950408889634f;
+
+// cooperative 64 x 32 bf16 tile load (rows beyond `nrows` zero-filled); 128 threads, 2 chunks each
+__device__ __forceinline__ void load_tile64(bf16 *dst, const bf16 *src, int ld, int row0, int nrows, int tid)
+{
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int c = tid + i * 128;
+        int r = c >> 2, ch = c & 3;
+        bool ok = row0 + r < nrows;
+        const bf16 *s = ok ? src + (size_t)(row0 + r) * ld + ch * 8 : src;
+        cp_async16(smem_u32(dst + r * LDH + ch * 8), s, ok ? 16 : 0);
+    }
+}
+
+// A-operand fragments (16 rows x 32 dh) of warp rows [r0, r0+16) from a [rows][LDH] tile
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[2][4], const bf16 *tile, int r0, int lane)
+{
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+        int r = r0 + (lane & 15), c = kk * 16 + (lane >> 4) * 8;
+        ldmatrix_x4(a[kk][0], a[kk][1], a[kk][2], a[kk][3], smem_u32(tile + r * LDH + c));
+    }
+}
+
+// S[16 x 64] = A(16 x 32) * T^T where T is a [64][LDH] tile (rows = n index, cols = dh)
+__device__ __forceinline__ void mma_a_tileT(float (&s)[8][4], const uint32_t (&a)[2][4], const bf16 *tile, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[j][k] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            uint32_t b[2][2];
+            int r = j * 8 + (lane & 7) + ((lane >> 4) << 3);
+            int c = kk * 16 + ((lane >> 3) & 1) * 8;
+            ldmatrix_x4(b[0][0], b[0][1], b[1][0], b[1][1], smem_u32(tile + r * LDH + c));
+            mma_bf16_16816(s[j], a[kk], b[0]);
+            mma_bf16_16816(s[j + 1], a[kk], b[1]);
+        }
+}
+
+// O[16 x 32] += P(16 x 64, registers as S-layout) * T where T is a [64][LDH] tile (rows = k index, cols = dh)
+__device__ __forceinline__ void mma_p_tile(float (&o)[4][4], const float (&p)[8][4], const bf16 *tile, int lane)
+{
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+        a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+        a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+        a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+            uint32_t b[2][2];
+            int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            int c = j * 8 + (lane >> 4) * 8;
+            ldmatrix_x4_trans(b[0][0], b[0][1], b[1][0], b[1][1], smem_u32(tile + r * LDH + c));
+            mma_bf16_16816(o[j], a, b[0]);
+            mma_bf16_16816(o[j + 1], a, b[1]);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const detrb_attn_fwd_t p)
+{
+    __shared__ __align__(16) bf16 sQ[TQ * LDH];
+    __shared__ __align__(16) bf16 sK[2][TKV * LDH];
+    __shared__ __align__(16) bf16 sV[2][TKV * LDH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+    const bf16 *Q = reinterpret_cast<const bf16 *>(p.Q) + (size_t)b * p.Lq * p.ldq + h * DH;
+    const bf16 *K = reinterpret_cast<const bf16 *>(p.K) + (size_t)b * p.Lk * p.ldk + h * DH;
+    const bf16 *V = reinterpret_cast<const bf16 *>(p.V) + (size_t)b * p.Lk * p.ldv + h * DH;
+    const int nkt = (p.Lk + TKV - 1) / TKV;
+
+    load_tile64(sQ, Q, p.ldq, q0, p.Lq, tid);
+    load_tile64(sK[0], K, p.ldk, 0, p.Lk, tid);
+    load_tile64(sV[0], V, p.ldv, 0, p.Lk, tid);
+    cp_async_commit();
+
+    float o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[j][k] = 0.f;
+    float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+    uint32_t aq[2][4];
+
+    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
+    const float sl2 = p.scale * LOG2E;
+    const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+
+    for (int kt = 0; kt < nkt; kt++) {
+        if (kt + 1 < nkt) {
+            load_tile64(sK[(kt + 1) & 1], K, p.ldk, (kt + 1) * TKV, p.Lk, tid);
+            load_tile64(sV[(kt + 1) & 1], V, p.ldv, (kt + 1) * TKV, p.Lk, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (kt == 0) load_a_frags(aq, sQ, warp * 16, lane);
+
+        float s[8][4];
+        mma_a_tileT(s, aq, sK[kt & 1], lane);
+        // mask keys beyond Lk, convert to log2 domain
+        const int kbase = kt * TKV;
+        float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int key = kbase + j * 8 + t * 2 + (e & 1);
+                float v = key < p.Lk ? s[j][e] * sl2 : -INFINITY;
+                s[j][e] = v;
+                tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+            tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+        }
+        float alpha[2], mnew[2], rsum[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            mnew[r] = fmaxf(mrow[r], tmax[r]);
+            alpha[r] = exp2f(mrow[r] - mnew[r]);          // exp2(-inf) = 0 on the first tile
+            mrow[r] = mnew[r];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float pv = exp2f(s[j][e] - mnew[e >> 1]);
+                rsum[e >> 1] += pv;
+                s[j][e] = pv;
+            }
+            if (p.drop_p > 0.f) {
+                uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    bool k0, k1;
+                    dropout_keep2(dropout_bits(seed, p.site, rowbase + r * 8, pair), thresh, k0, k1);
+                    s[j][r * 2 + 0] = k0 ? s[j][r * 2 + 0] * drop_scale : 0.f;
+                    s[j][r * 2 + 1] = k1 ? s[j][r * 2 + 1] * drop_scale : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            rsum[r] += __shfl_xor_sync(0xffffffffu, rsum[r], 1);
+            rsum[r] += __shfl_xor_sync(0xffffffffu, rsum[r], 2);
+            lrow[r] = lrow[r] * alpha[r] + rsum[r];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
+            o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
+        }
+        mma_p_tile(o, s, sV[kt & 1], lane);
+        __syncthreads();
+    }
+
+    bf16 *O = reinterpret_cast<bf16 *>(p.O) + (size_t)b * p.Lq * p.ldo + h * DH;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int q = q0 + warp * 16 + g + r * 8;
+        if (q >= p.Lq) continue;
+        float inv = 1.f / lrow[r];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<uint32_t *>(O + (size_t)q * p.ldo + j * 8 + t * 2) =
+                pack_bf16x2(o[j][r * 2] * inv, o[j][r * 2 + 1] * inv);
+        if (t == 0 && p.lse)
+            p.lse[((size_t)b * p.H + h) * p.Lq + q] = (mrow[r] + log2f(lrow[r])) * (1.f / LOG2E);
+    }
+}
+
+// --------------------------------------------------------------------------------------- backward
+// delta[b,h,q] = sum_d dO[b,q,h*32+d] * O[b,q,h*32+d]
+__global__ void attn_delta_kernel(const bf16 *O, const bf16 *dO, int ldo, int lddo, float *delta,
+                                  int B, int H, int Lq)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H * Lq) return;
+    int q = idx % Lq, h = (idx / Lq) % H, b = idx / (Lq * H);
+    const uint4 *o = reinterpret_cast<const uint4 *>(O + ((size_t)b * Lq + q) * ldo + h * DH);
+    const uint4 *d = reinterpret_cast<const uint4 *>(dO + ((size_t)b * Lq + q) * lddo + h * DH);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint4 ov = o[i], dv = d[i];
+        float2 a, c;
+        a = unpack_bf16x2(ov.x); c = unpack_bf16x2(dv.x); acc += a.x * c.x + a.y * c.y;
+        a = unpack_bf16x2(ov.y); c = unpack_bf16x2(dv.y); acc += a.x * c.x + a.y * c.y;
+        a = unpack_bf16x2(ov.z); c = unpack_bf16x2(dv.z); acc += a.x * c.x + a.y * c.y;
+        a = unpack_bf16x2(ov.w); c = unpack_bf16x2(dv.w); acc += a.x * c.x + a.y * c.y;
+    }
+    delta[idx] = acc;
+}
+
+// dK, dV: CTA owns 64 keys (warp: 16), loops over query tiles; works on S^T so that P^T / dS^T come out
+// of the MMAs directly in A-operand layout.
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
+{
+    __shared__ __align__(16) bf16 sK[TQ * LDH];
+    __shared__ __align__(16) bf16 sV[TQ * LDH];
+    __shared__ __align__(16) bf16 sQ[2][TKV * LDH];
+    __shared__ __align__(16) bf16 sdO[2][TKV * LDH];
+    __shared__ float sLse[2][TKV], sDelta[2][TKV];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int k0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+    const bf16 *Q = reinterpret_cast<const bf16 *>(p.Q) + (size_t)b * p.Lq * p.ldq + h * DH;
+    const bf16 *K = reinterpret_cast<const bf16 *>(p.K) + (size_t)b * p.Lk * p.ldk + h * DH;
+    const bf16 *V = reinterpret_cast<const bf16 *>(p.V) + (size_t)b * p.Lk * p.ldv + h * DH;
+    const bf16 *dO = reinterpret_cast<const bf16 *>(p.dO) + (size_t)b * p.Lq * p.lddo + h * DH;
+    const float *lse = p.lse + ((size_t)b * p.H + h) * p.Lq;
+    const float *delta = p.delta + ((size_t)b * p.H + h) * p.Lq;
+    const int nqt = (p.Lq + TKV - 1) / TKV;
+
+    auto load_q = [&](int st, int qt) {
+        load_tile64(sQ[st], Q, p.ldq, qt * TKV, p.Lq, tid);
+        load_tile64(sdO[st], dO, p.lddo, qt * TKV, p.Lq, tid);
+        if (tid < TKV) {
+            int q = qt * TKV + tid;
+            sLse[st][tid] = q < p.Lq ? lse[q] * LOG2E : INFINITY;
+            sDelta[st][tid] = q < p.Lq ? delta[q] : 0.f;
+        }
+    };
+    load_tile64(sK, K, p.ldk, k0, p.Lk, tid);
+    load_tile64(sV, V, p.ldv, k0, p.Lk, tid);
+    load_q(0, 0);
+    cp_async_commit();
+
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { dk[j][k] = 0.f; dv[j][k] = 0.f; }
+    uint32_t ak[2][4], av[2][4];
+    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const int keyr[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
+    const float sl2 = p.scale * LOG2E;
+    const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+
+    for (int qt = 0; qt < nqt; qt++) {
+        if (qt + 1 < nqt) { load_q((qt + 1) & 1, qt + 1); cp_async_commit(); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        if (qt == 0) { load_a_frags(ak, sK, warp * 16, lane); load_a_frags(av, sV, warp * 16, lane); }
+        const int st = qt & 1;
+        float sT[8][4], dpT[8][4];
+        mma_a_tileT(sT, ak, sQ[st], lane);        // S^T[key, q]
+        mma_a_tileT(dpT, av, sdO[st], lane);      // dP^T[key, q]
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int ql = j * 8 + t * 2 + (e & 1);
+                int key = keyr[e >> 1];
+                float pv = key < p.Lk ? exp2f(sT[j][e] * sl2 - sLse[st][ql]) : 0.f;
+                float dpv = dpT[j][e];
+                float pd = pv;
+                if (p.drop_p > 0.f) {
+                    uint32_t row = (uint32_t)((b * p.H + h) * p.Lq + qt * TKV + ql);
+                    uint32_t bits = dropout_bits(seed, p.site, row, (uint32_t)(key >> 1));
+                    bool keep = ((key & 1) ? (bits >> 16) : (bits & 0xffffu)) >= thresh;
+                    pd = keep ? pv * drop_scale : 0.f;
+                    dpv = keep ? dpv * drop_scale : 0.f;
+                }
+                sT[j][e] = pd;                                   // dropped probabilities (for dV)
+                dpT[j][e] = p.scale * pv * (dpv - sDelta[st][ql]); // scale * dS^T
+            }
+        mma_p_tile(dv, sT, sdO[st], lane);        // dV += P_d^T dO
+        mma_p_tile(dk, dpT, sQ[st], lane);        // dK += dS^T Q
+        __syncthreads();
+    }
+    bf16 *dK = reinterpret_cast<bf16 *>(p.dK) + (size_t)b * p.Lk * p.lddk + h * DH;
+    bf16 *dV = reinterpret_cast<bf16 *>(p.dV) + (size_t)b * p.Lk * p.lddv + h * DH;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int key = keyr[r];
+        if (key >= p.Lk) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            *reinterpret_cast<uint32_t *>(dK + (size_t)key * p.lddk + j * 8 + t * 2) = pack_bf16x2(dk[j][r * 2], dk[j][r * 2 + 1]);
+            *reinterpret_cast<uint32_t *>(dV + (size_t)key * p.lddv + j * 8 + t * 2) = pack_bf16x2(dv[j][r * 2], dv[j][r * 2 + 1]);
+        }
+    }
+}
+
+// dQ: CTA owns 64 queries (warp: 16), loops over key tiles.
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
+{
+    __shared__ __align__(16) bf16 sQ[TQ * LDH];
+    __shared__ __align__(16) bf16 sdO[TQ * LDH];
+    __shared__ __align__(16) bf16 sK[2][TKV * LDH];
+    __shared__ __align__(16) bf16 sV[2][TKV * LDH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int q0 = blockIdx.x * TQ, h = blockIdx.y, b = blockIdx.z;
+    const bf16 *Q = reinterpret_cast<const bf16 *>(p.Q) + (size_t)b * p.Lq * p.ldq + h * DH;
+    const bf16 *K = reinterpret_cast<const bf16 *>(p.K) + (size_t)b * p.Lk * p.ldk + h * DH;
+    const bf16 *V = reinterpret_cast<const bf16 *>(p.V) + (size_t)b * p.Lk * p.ldv + h * DH;
+    const bf16 *dO = reinterpret_cast<const bf16 *>(p.dO) + (size_t)b * p.Lq * p.lddo + h * DH;
+    const int nkt = (p.Lk + TKV - 1) / TKV;
+
+    load_tile64(sQ, Q, p.ldq, q0, p.Lq, tid);
+    load_tile64(sdO, dO, p.lddo, q0, p.Lq, tid);
+    load_tile64(sK[0], K, p.ldk, 0, p.Lk, tid);
+    load_tile64(sV[0], V, p.ldv, 0, p.Lk, tid);
+    cp_async_commit();
+
+    float dq[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) dq[j][k] = 0.f;
+    uint32_t aq[2][4], ado[2][4];
+    float lrow[2], drow[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int q = q0 + warp * 16 + g + r * 8;
+        size_t idx = ((size_t)b * p.H + h) * p.Lq + q;
+        lrow[r] = q < p.Lq ? p.lse[idx] * LOG2E : INFINITY;
+        drow[r] = q < p.Lq ? p.delta[idx] : 0.f;
+    }
+    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
+    const float sl2 = p.scale * LOG2E;
+    const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+
+    for (int kt = 0; kt < nkt; kt++) {
+        if (kt + 1 < nkt) {
+            load_tile64(sK[(kt + 1) & 1], K, p.ldk, (kt + 1) * TKV, p.Lk, tid);
+            load_tile64(sV[(kt + 1) & 1], V, p.ldv, (kt + 1) * TKV, p.Lk, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else cp_async_wait<0>();
+        __syncthreads();
+        if (kt == 0) { load_a_frags(aq, sQ, warp * 16, lane); load_a_frags(ado, sdO, warp * 16, lane); }
+        float s[8][4], dp[8][4];
+        mma_a_tileT(s, aq, sK[kt & 1], lane);
+        mma_a_tileT(dp, ado, sV[kt & 1], lane);
+        const int kbase = kt * TKV;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            bool keep[4] = {true, true, true, true};
+            if (p.drop_p > 0.f) {
+                uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+                    dropout_keep2(dropout_bits(seed, p.site, rowbase + r * 8, pair), thresh, keep[r * 2], keep[r * 2 + 1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int key = kbase + j * 8 + t * 2 + (e & 1);
+                float pv = key < p.Lk ? exp2f(s[j][e] * sl2 - lrow[e >> 1]) : 0.f;
+                float dpv = keep[e] ? dp[j][e] * drop_scale : 0.f;
+                s[j][e] = p.scale * pv * (dpv - drow[e >> 1]);  // scale * dS
+            }
+        }
+        mma_p_tile(dq, s, sK[kt & 1], lane);      // dQ += dS K
+        __syncthreads();
+    }
+    bf16 *dQ = reinterpret_cast<bf16 *>(p.dQ) + (size_t)b * p.Lq * p.lddq + h * DH;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int q = q0 + warp * 16 + g + r * 8;
+        if (q >= p.Lq) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<uint32_t *>(dQ + (size_t)q * p.lddq + j * 8 + t * 2) = pack_bf16x2(dq[j][r * 2], dq[j][r * 2 + 1]);
+    }
+}
+
+}  // namespace
+
+extern "C" int detrb_attn_fwd(const detrb_attn_fwd_t *pp, detrb_stream_t stream_)
+{
+    if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_attn_fwd: null params");
+    const detrb_attn_fwd_t &p = *pp;
+    DETRB_REQUIRE(p.Q && p.K && p.V && p.O, "detrb_attn_fwd: null pointer");
+    DETRB_REQUIRE(p.B > 0 && p.H > 0 && p.Lq > 0 && p.Lk > 0, "detrb_attn_fwd: empty problem");
+    DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "detrb_attn_fwd: strides must be multiples of 8");
+    DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_attn_fwd: drop_p");
+    dim3 grid(ceil_div(p.Lq, TQ), p.H, p.B);
+    attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(p);
+    DETRB_CHECK_LAUNCH("attn_fwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_attn_bwd(const detrb_attn_bwd_t *pp, detrb_stream_t stream_)
+{
+    if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_attn_bwd: null params");
+    const detrb_attn_bwd_t &p = *pp;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DETRB_REQUIRE(p.Q && p.K && p.V && p.O && p.dO && p.lse && p.delta && p.dQ && p.dK && p.dV, "detrb_attn_bwd: null pointer");
+    DETRB_REQUIRE(p.B > 0 && p.H > 0 && p.Lq > 0 && p.Lk > 0, "detrb_attn_bwd: empty problem");
+    DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 8 == 0 && p.lddo % 8 == 0,
+                  "detrb_attn_bwd: strides must be multiples of 8");
+    int n = p.B * p.H * p.Lq;
+    attn_delta_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
+                                                            p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq);
+    DETRB_CHECK_LAUNCH("attn_delta_kernel");
+    attn_bwd_dkv_kernel<<<dim3(ceil_div(p.Lk, TQ), p.H, p.B), 128, 0, stream>>>(p);
+    DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+    attn_bwd_dq_kernel<<<dim3(ceil_div(p.Lq, TQ), p.H, p.B), 128, 0, stream>>>(p);
+    DETRB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+    return DETRB_OK;
+}

@@ -1,0 +1,105 @@
+// common.cuh -- shared device/host helpers for libdetrb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/detrb.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- host-side error plumbing
+void detrb_set_error(const char *fmt, ...);
+#define DETRB_FAIL(code, ...) do { detrb_set_error(__VA_ARGS__); return (code); } while (0)
+#define DETRB_REQUIRE(cond, ...) do { if (!(cond)) DETRB_FAIL(DETRB_E_BADARG, __VA_ARGS__); } while (0)
+#define DETRB_CHECK_LAUNCH(name) do { cudaError_t e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) DETRB_FAIL(DETRB_E_CUDA, "%s: %s", name, cudaGetErrorString(e_)); } while (0)
+#define DETRB_CUDA(call) do { cudaError_t e_ = (call); \
+    if (e_ != cudaSuccess) DETRB_FAIL(DETRB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// 16-byte (or 8-byte) async global->shared copy; src_bytes==0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" :: "n"(N));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162 *>(&u);
+    return __bfloat1622float2(v);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- counter-based dropout RNG
+// 32 random bits for the counter (site, row, pair) under `seed`: two rounds of the "lowbias32"
+// integer finaliser.  One call serves two adjacent elements (16 bits each): element (row, col)
+// uses pair = col >> 1 and the low/high half for even/odd col.  keep <=> bits16 >= thresh16,
+// thresh16 = round(p * 65536).  Forward and backward regenerate identical masks from the counter.
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint32_t site, uint32_t row, uint32_t pair) {
+    uint32_t h = lowbias32(row ^ (uint32_t)seed ^ (site * 0x9E3779B9U));
+    h = lowbias32(h ^ pair ^ (uint32_t)(seed >> 32));
+    return lowbias32(h + 0x6a09e667U + site);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
+    return (uint32_t)(p * 65536.0f + 0.5f);
+}
+// keep flags for the element pair (col even, col odd) of `pair`
+__device__ __forceinline__ void dropout_keep2(uint32_t bits, uint32_t thresh, bool &k0, bool &k1) {
+    k0 = (bits & 0xffffu) >= thresh;
+    k1 = (bits >> 16) >= thresh;
+}

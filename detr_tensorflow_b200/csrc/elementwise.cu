@@ -1,0 +1,386 @@
+// elementwise.cu -- bandwidth-bound pieces of the DETR step: LayerNorm fwd/bwd (d = 256), positional
+// add, max-pool fwd/bwd, layout conversion, column sums (bias gradients).  All NHWC / row-major bf16,
+// 16-byte vector accesses, one warp per row where a row reduction is needed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int D = 256;   // model_dim (transformer.py:8)
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+
+// ---------------------------------------------------------------- LayerNorm forward: warp per row
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf16 *y2, const bf16 *pos, int S,
+              float *mean, float *rstd, int M)
+{
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4 *>(x + (size_t)row * D + lane * 8), v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    float mu = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { float d = v[i] - mu; q += d * d; }
+    float rs = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+    float4 g0 = *reinterpret_cast<const float4 *>(gamma + lane * 8), g1 = *reinterpret_cast<const float4 *>(gamma + lane * 8 + 4);
+    float4 b0 = *reinterpret_cast<const float4 *>(beta + lane * 8), b1 = *reinterpret_cast<const float4 *>(beta + lane * 8 + 4);
+    float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = (v[i] - mu) * rs * gg[i] + bb[i];
+    uint4 packed = pack8(o);
+    *reinterpret_cast<uint4 *>(y + (size_t)row * D + lane * 8) = packed;
+    if (y2) {
+        // y2 = bf16(y) + pos : add to the ROUNDED y so that y2 == (stored y) + pos exactly like a separate add
+        float yr[8], pp[8];
+        unpack8(packed, yr);
+        unpack8(*reinterpret_cast<const uint4 *>(pos + (size_t)(row % S) * D + lane * 8), pp);
+#pragma unroll
+        for (int i = 0; i < 8; i++) yr[i] += pp[i];
+        *reinterpret_cast<uint4 *>(y2 + (size_t)row * D + lane * 8) = pack8(yr);
+    }
+    if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+}
+
+// ---------------------------------------------------------------- LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma ; dgamma += sum dy*xhat ; dbeta += sum dy
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma, const float *mean, const float *rstd,
+              bf16 *dx, bf16 *dx_drop, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr,
+              float *dgamma, float *dbeta, int M, int rows_per_block)
+{
+    const uint64_t seed = seed_in ^ ((drop_p > 0.f && seed_ptr) ? *seed_ptr : 0ull);
+    __shared__ float sg[8][D], sb[8][D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 g0 = *reinterpret_cast<const float4 *>(gamma + lane * 8), g1 = *reinterpret_cast<const float4 *>(gamma + lane * 8 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float acc_g[8], acc_b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc_g[i] = 0.f; acc_b[i] = 0.f; }
+    const uint32_t thresh = dropout_thresh16(drop_p);
+    const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(M, r_begin + rows_per_block);
+    for (int row = r_begin + warp; row < r_end; row += 8) {
+        float d[8], xv[8];
+        unpack8(*reinterpret_cast<const uint4 *>(dy + (size_t)row * D + lane * 8), d);
+        if (dy2) {
+            float d2[8];
+            unpack8(*reinterpret_cast<const uint4 *>(dy2 + (size_t)row * D + lane * 8), d2);
+#pragma unroll
+            for (int i = 0; i < 8; i++) d[i] += d2[i];
+        }
+        unpack8(*reinterpret_cast<const uint4 *>(x + (size_t)row * D + lane * 8), xv);
+        const float mu = mean[row], rs = rstd[row];
+        float s1 = 0.f, s2 = 0.f, xh[8], gv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            xh[i] = (xv[i] - mu) * rs;
+            gv[i] = d[i] * gg[i];
+            s1 += gv[i]; s2 += gv[i] * xh[i];
+            acc_g[i] += d[i] * xh[i]; acc_b[i] += d[i];
+        }
+        s1 = warp_sum(s1) * (1.f / D); s2 = warp_sum(s2) * (1.f / D);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = rs * (gv[i] - s1 - xh[i] * s2);
+        uint4 packed = pack8(o);
+        *reinterpret_cast<uint4 *>(dx + (size_t)row * D + lane * 8) = packed;
+        if (dx_drop) {
+            float od[8];
+            unpack8(packed, od);
+            if (drop_p > 0.f) {
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    bool k0, k1;
+                    dropout_keep2(dropout_bits(seed, site, (uint32_t)row, (uint32_t)((lane * 8 + i) >> 1)), thresh, k0, k1);
+                    od[i] = k0 ? od[i] * drop_scale : 0.f;
+                    od[i + 1] = k1 ? od[i + 1] * drop_scale : 0.f;
+                }
+            }
+            *reinterpret_cast<uint4 *>(dx_drop + (size_t)row * D + lane * 8) = pack8(od);
+        }
+    }
+    if (dgamma) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { sg[warp][lane * 8 + i] = acc_g[i]; sb[warp][lane * 8 + i] = acc_b[i]; }
+        __syncthreads();
+        int c = threadIdx.x;       // 256 threads == D columns
+        float a = 0.f, bsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += sg[w][c]; bsum += sb[w][c]; }
+        atomicAdd(dgamma + c, a);
+        atomicAdd(dbeta + c, bsum);
+    }
+}
+
+// ---------------------------------------------------------------- simple vector kernels
+__global__ void add_rowbcast_kernel(const uint4 *x, const uint4 *pos, uint4 *out, int64_t nvec, int64_t svec)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    float a[8], b[8];
+    unpack8(x[i], a); unpack8(pos[i % svec], b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] += b[k];
+    out[i] = pack8(a);
+}
+__global__ void add_kernel(const uint4 *x, const uint4 *y, uint4 *out, int64_t nvec)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    if (!y) { out[i] = x[i]; return; }
+    float a[8], b[8];
+    unpack8(x[i], a); unpack8(y[i], b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] += b[k];
+    out[i] = pack8(a);
+}
+__global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    float r = img[i * 3], g = img[i * 3 + 1], b = img[i * 3 + 2];
+    out[i] = make_uint2(pack_bf16x2(r, g), pack_bf16x2(b, 0.f));
+}
+__global__ void f32_to_bf16_kernel(const float *x, bf16 *y, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16(x[i]);
+}
+
+// out[n] += scale[n] * sum_m x[m, n]; block = 32 column-pairs x 8 row lanes
+__global__ void __launch_bounds__(256)
+colsum_kernel(const bf16 *x, int ldx, int M, int N, const float *scale, float *out, int rows_per_block)
+{
+    __shared__ float red[8][64];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = blockIdx.x * 64 + cx * 2;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float a0 = 0.f, a1 = 0.f;
+    if (n < N) {
+        for (int r = r0 + ry; r < r1; r += 8) {
+            float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(x + (size_t)r * ldx + n));
+            a0 += v.x; a1 += v.y;
+        }
+    }
+    red[ry][cx * 2] = a0; red[ry][cx * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        int nn = blockIdx.x * 64 + threadIdx.x;
+        if (nn < N) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) s += red[w][threadIdx.x];
+            atomicAdd(out + nn, s * (scale ? scale[nn] : 1.f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- max pool 3x3 s2 pad 1 (zero pad == -inf pad: x >= 0)
+__global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW)
+{
+    const int cv = C / 8;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * OH * OW * cv;
+    if (idx >= total) return;
+    int c8 = idx % cv; int64_t pix = idx / cv;
+    int ox = pix % OW; int oy = (pix / OW) % OH; int b = pix / ((int64_t)OW * OH);
+    float best[8]; int arg[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { best[i] = -INFINITY; arg[i] = 0; }
+    // padded positions hold 0 (ZeroPadding2D): a window of all-negative values cannot occur post-ReLU,
+    // so treating the pad as "absent" is identical; taps are scanned in row-major order, first max wins.
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++) {
+            int iy = oy * 2 - 1 + kh, ix = ox * 2 - 1 + kw;
+            if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4 *>(x + (((size_t)b * IH + iy) * IW + ix) * C + c8 * 8), v);
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = kh * 3 + kw; }
+        }
+    size_t o = (size_t)pix * C + c8 * 8;
+    *reinterpret_cast<uint4 *>(y + o) = pack8(best);
+    uint2 a;
+    a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    *reinterpret_cast<uint2 *>(argmax + o) = a;
+}
+
+// dx[b,iy,ix,c] = (x > 0) * sum over the <= 4 windows containing (iy,ix) whose argmax is this pixel
+__global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const bf16 *x, bf16 *dx,
+                                   int B, int IH, int IW, int C, int OH, int OW)
+{
+    const int cv = C / 8;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * IH * IW * cv;
+    if (idx >= total) return;
+    int c8 = idx % cv; int64_t pix = idx / cv;
+    int ix = pix % IW; int iy = (pix / IW) % IH; int b = pix / ((int64_t)IW * IH);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int kh = 0; kh < 3; kh++) {
+        int ty = iy + 1 - kh;
+        if (ty < 0 || (ty & 1)) continue;
+        int oy = ty >> 1; if (oy >= OH) continue;
+        for (int kw = 0; kw < 3; kw++) {
+            int tx = ix + 1 - kw;
+            if (tx < 0 || (tx & 1)) continue;
+            int ox = tx >> 1; if (ox >= OW) continue;
+            size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
+            uint2 a = *reinterpret_cast<const uint2 *>(argmax + o);
+            float d[8];
+            unpack8(*reinterpret_cast<const uint4 *>(dy + o), d);
+            const int tap = kh * 3 + kw;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                int ai = ((i < 4 ? a.x : a.y) >> ((i & 3) * 8)) & 0xff;
+                if (ai == tap) acc[i] += d[i];
+            }
+        }
+    }
+    float xv[8];
+    size_t xo = (size_t)pix * C + c8 * 8;
+    unpack8(*reinterpret_cast<const uint4 *>(x + xo), xv);
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (!(xv[i] > 0.f)) acc[i] = 0.f;
+    *reinterpret_cast<uint4 *>(dx + xo) = pack8(acc);
+}
+
+__global__ void dropout_mask_kernel(uint8_t *out, int M, int N, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr)
+{
+    const uint64_t seed = seed_in ^ (seed_ptr ? *seed_ptr : 0ull);
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    int m = idx / N, n = idx % N;
+    uint32_t bits = dropout_bits(seed, site, (uint32_t)m, (uint32_t)(n >> 1));
+    uint32_t v = (n & 1) ? (bits >> 16) : (bits & 0xffffu);
+    out[idx] = v >= dropout_thresh16(drop_p) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, const float *beta, detrb_bf16 *y, detrb_bf16 *y2,
+                                   const detrb_bf16 *pos, int S, float *mean, float *rstd, int M, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(x && gamma && beta && y && M > 0, "detrb_layernorm_fwd: bad args");
+    DETRB_REQUIRE(!y2 || (pos && S > 0), "detrb_layernorm_fwd: y2 needs pos and S");
+    ln_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, gamma, beta, (bf16 *)y, (bf16 *)y2,
+                                                                   (const bf16 *)pos, S, mean, rstd, M);
+    DETRB_CHECK_LAUNCH("ln_fwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, const detrb_bf16 *x, const float *gamma,
+                                   const float *mean, const float *rstd, detrb_bf16 *dx, detrb_bf16 *dx_drop,
+                                   float drop_p, uint64_t seed, uint32_t site, const uint64_t *seed_ptr,
+                                   float *dgamma, float *dbeta, int M, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(dy && x && gamma && mean && rstd && dx && M > 0, "detrb_layernorm_bwd: bad args");
+    DETRB_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "detrb_layernorm_bwd: dgamma/dbeta must both be set or both NULL");
+    int blocks = ceil_div(M, 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    int rpb = ceil_div(ceil_div(M, blocks), 8) * 8;
+    blocks = ceil_div(M, rpb);
+    ln_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, (const bf16 *)dy2, (const bf16 *)x, gamma, mean, rstd,
+                                                            (bf16 *)dx, (bf16 *)dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M, rpb);
+    DETRB_CHECK_LAUNCH("ln_bwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *out, int M, int S, int d, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(x && pos && out && M > 0 && S > 0 && d % 8 == 0, "detrb_add_rowbcast: bad args");
+    int64_t nvec = (int64_t)M * d / 8, svec = (int64_t)S * d / 8;
+    add_rowbcast_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x, (const uint4 *)pos, (uint4 *)out, nvec, svec);
+    DETRB_CHECK_LAUNCH("add_rowbcast_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *out, int64_t n, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(a && out && n > 0 && n % 8 == 0, "detrb_add: bad args");
+    int64_t nvec = n / 8;
+    add_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out, nvec);
+    DETRB_CHECK_LAUNCH("add_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(img && out && npix > 0, "detrb_image_to_nhwc4: bad args");
+    image_to_nhwc4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (uint2 *)out, npix);
+    DETRB_CHECK_LAUNCH("image_to_nhwc4_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(x && y && n > 0, "detrb_f32_to_bf16: bad args");
+    f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16 *)y, n);
+    DETRB_CHECK_LAUNCH("f32_to_bf16_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const float *scale, float *out, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(x && out && M > 0 && N > 0 && ldx % 2 == 0 && N % 2 == 0, "detrb_colsum: bad args");
+    int gy = ceil_div(M, 256);
+    if (gy > 296) gy = 296;
+    int rpb = ceil_div(M, gy);
+    gy = ceil_div(M, rpb);
+    colsum_kernel<<<dim3(ceil_div(N, 64), gy), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, ldx, M, N, scale, out, rpb);
+    DETRB_CHECK_LAUNCH("colsum_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW,
+                                 detrb_stream_t stream)
+{
+    DETRB_REQUIRE(x && y && argmax && C % 8 == 0, "detrb_maxpool_fwd: bad args");
+    DETRB_REQUIRE(OH == (IH + 2 - 3) / 2 + 1 && OW == (IW + 2 - 3) / 2 + 1, "detrb_maxpool_fwd: bad output size");
+    int64_t total = (int64_t)B * OH * OW * (C / 8);
+    maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
+    DETRB_CHECK_LAUNCH("maxpool_fwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
+                                 int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(dy && argmax && x && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
+    int64_t total = (int64_t)B * IH * IW * (C / 8);
+    maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
+                                                                                          B, IH, IW, C, OH, OW);
+    DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
+                                  const uint64_t *seed_ptr, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(out && M > 0 && N > 0, "detrb_dropout_mask: bad args");
+    int64_t total = (int64_t)M * N;
+    dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, M, N, drop_p, seed, site, seed_ptr);
+    DETRB_CHECK_LAUNCH("dropout_mask_kernel");
+    return DETRB_OK;
+}

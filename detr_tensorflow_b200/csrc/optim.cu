@@ -1,0 +1,106 @@
+// optim.cu -- optimizer step of the reference (optimizers.py:86-88,137-163): three Keras Adam optimizers
+// (beta1 .9, beta2 .999, eps 1e-7, no weight decay) with PER-VARIABLE clipnorm, as one multi-tensor pass over a
+// flat fp32 arena, plus the fp32-master -> bf16 kernel-layout weight refresh.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SLICES = 16;
+
+__global__ void adam_prologue_kernel(int32_t *steps, const uint8_t *enabled, int G, float *norms, int T)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G && enabled[i]) steps[i] += 1;
+    if (i < T) norms[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const float *grads, const int64_t *table, float *norms)
+{
+    const int t = blockIdx.x, s = blockIdx.y;
+    const int64_t off = table[2 * t], n = table[2 * t + 1];
+    const int64_t per = ((n + SLICES - 1) / SLICES + 3) & ~(int64_t)3;
+    const int64_t b = s * per, e = min(n, b + per);
+    float acc = 0.f;
+    for (int64_t i = b + threadIdx.x; i < e; i += 256) { float g = grads[off + i]; acc += g * g; }
+    acc = warp_sum(acc);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += red[w];
+        if (b < e) atomicAdd(norms + t, tot);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_update_kernel(float *params, const float *grads, float *m, float *v, const int64_t *table,
+                   const int32_t *lr_group, const float *lrs, const uint8_t *enabled, const int32_t *steps,
+                   const float *norms, float clipnorm, float beta1, float beta2, float eps)
+{
+    const int t = blockIdx.x, s = blockIdx.y;
+    const int g = lr_group[t];
+    if (!enabled[g]) return;
+    const int64_t off = table[2 * t], n = table[2 * t + 1];
+    const int64_t per = ((n + SLICES - 1) / SLICES + 3) & ~(int64_t)3;
+    const int64_t b = s * per, e = min(n, b + per);
+    const float norm = sqrtf(norms[t]);
+    const float coef = (clipnorm > 0.f && norm > clipnorm) ? clipnorm / norm : 1.f;   // tf.clip_by_norm
+    const float step = (float)steps[g];
+    const float lr_t = lrs[g] * sqrtf(1.f - powf(beta2, step)) / (1.f - powf(beta1, step));
+    for (int64_t i = b + threadIdx.x; i < e; i += 256) {
+        float gr = grads[off + i] * coef;
+        float mi = beta1 * m[off + i] + (1.f - beta1) * gr;
+        float vi = beta2 * v[off + i] + (1.f - beta2) * gr * gr;
+        m[off + i] = mi; v[off + i] = vi;
+        params[off + i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+__global__ void prep_weight_kernel(const float *master, const float *fold, int N, int taps, int Cin,
+                                   bf16 *Wf, int ldf, bf16 *Wd, int ldd)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)N * taps * Cin;
+    if (idx >= total) return;
+    int c = idx % Cin; int t = (idx / Cin) % taps; int n = idx / ((int64_t)Cin * taps);
+    float w = master[idx] * (fold ? fold[n] : 1.f);
+    bf16 wb = __float2bfloat16(w);
+    if (Wf) Wf[(size_t)n * ldf + t * Cin + c] = wb;
+    if (Wd) Wd[((size_t)c * taps + t) * ldd + n] = wb;
+}
+
+}  // namespace
+
+extern "C" int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v, const int64_t *table,
+                                   const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,
+                                   int64_t total, float clipnorm, float beta1, float beta2, float eps,
+                                   int32_t *steps, float *norms, detrb_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DETRB_REQUIRE(params && grads && m && v && table && lr_group && lrs && group_enabled && steps && norms, "detrb_adam_clipnorm: null pointer");
+    DETRB_REQUIRE(T > 0 && T <= 65535 && total > 0, "detrb_adam_clipnorm: bad sizes");
+    // groups: at most 8 (the reference has 3: backbone, transformers, nlayers)
+    adam_prologue_kernel<<<ceil_div(T > 8 ? T : 8, 256), 256, 0, stream>>>(steps, group_enabled, 8, norms, T);
+    DETRB_CHECK_LAUNCH("adam_prologue_kernel");
+    grad_sumsq_kernel<<<dim3(T, SLICES), 256, 0, stream>>>(grads, table, norms);
+    DETRB_CHECK_LAUNCH("grad_sumsq_kernel");
+    adam_update_kernel<<<dim3(T, SLICES), 256, 0, stream>>>(params, grads, m, v, table, lr_group, lrs, group_enabled, steps, norms,
+                                                           clipnorm, beta1, beta2, eps);
+    DETRB_CHECK_LAUNCH("adam_update_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_prep_weight(const float *master, const float *fold, int N, int taps, int Cin,
+                                 detrb_bf16 *Wf, int ldf, detrb_bf16 *Wd, int ldd, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(master && (Wf || Wd) && N > 0 && taps > 0 && Cin > 0, "detrb_prep_weight: bad args");
+    DETRB_REQUIRE(!Wf || ldf >= taps * Cin, "detrb_prep_weight: ldf");
+    DETRB_REQUIRE(!Wd || ldd >= N, "detrb_prep_weight: ldd");
+    int64_t total = (int64_t)N * taps * Cin;
+    prep_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(master, fold, N, taps, Cin, (bf16 *)Wf, ldf, (bf16 *)Wd, ldd);
+    DETRB_CHECK_LAUNCH("prep_weight_kernel");
+    return DETRB_OK;
+}

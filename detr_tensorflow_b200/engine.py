@@ -1,0 +1,748 @@
+"""DETR train-step engine: owns device memory (torch tensors) and drives the sm_100a kernels of libdetrb
+through the C ABI.  Pure orchestration -- every FLOP of the step runs in csrc/*.cu.
+
+Data layout in HBM
+  * activations: NHWC / [tokens, channels] row-major bf16, kept resident for the backward pass
+  * parameters : one flat fp32 arena (master weights) + same-shaped arenas for grads / Adam m / Adam v; conv
+                 kernels are stored [Cout][tap][Cin] (GEMM K-major), Linear kernels [out][in] as in the reference
+  * bf16 weight copies in kernel layouts (forward [N][K], data-gradient [Cin][tap][N]) refreshed after each
+                 optimizer step; FrozenBatchNorm2D is folded into them (scale) and into the epilogue bias (shift)
+
+Reference being replaced: detr_tf/networks/{detr,resnet_backbone,transformer,position_embeddings,custom_layers}.py,
+detr_tf/loss/{loss,hungarian_matching}.py, detr_tf/optimizers.py, detr_tf/training.py:9-25.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib, ops
+from .networks.spec import RESNET_STAGES, model_params
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+GROUPS = ("backbone", "transformers", "nlayers")
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Slot:
+    """A GEMM-able weight (conv or linear) with its optimizer views and bf16 kernel-layout copies."""
+    def __init__(self):
+        self.name = None
+        self.N = self.taps = self.Cin = self.K = 0
+        self.master = self.grad = None          # fp32 [N*K] views into the arenas
+        self.bias = self.bias_grad = None       # fp32 [N] views (trainable bias) or None
+        self.fold = None                        # fp32 [N]: FrozenBN scale folded into the weight
+        self.shift = None                       # fp32 [N]: FrozenBN shift used as epilogue bias
+        self.Wf = self.Wd = None
+        self.ldd = 0
+        self.geom = None                        # (kh, kw_real, kw_padded, stride, pad) for convs
+
+    @property
+    def epi_bias(self):
+        return self.shift if self.shift is not None else self.bias
+
+
+class Engine:
+    def __init__(self, device="cuda", backbone="resnet50", num_classes=92, num_encoder_layers=6,
+                 num_decoder_layers=6, num_queries=100, dropout=0.1, seed=0):
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        if self.device.type != "cuda" and not getattr(_lib, "_EMULATED", False):
+            raise RuntimeError("detr_tensorflow_b200 has no CPU path: a B200 (sm_100a) device is required")
+        if self.device.type == "cuda":
+            _lib.check(self.lib.detrb_check_device())
+        self.backbone_name = backbone
+        self.C = num_classes
+        self.nenc, self.ndec, self.Q = num_encoder_layers, num_decoder_layers, num_queries
+        self.d, self.H, self.dff = 256, 8, 2048
+        self.dropout = dropout
+        self.base_seed = seed
+        self.spec = model_params(num_classes, backbone, num_encoder_layers, num_decoder_layers, 256, 2048, num_queries)
+        self._build_params()
+        self.plan_key = None
+        self.sites = {}
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _build_params(self):
+        dev = self.device
+        spec = self.spec
+        self.slots = OrderedDict()          # slot name (prefix) -> Slot
+        self.vars = []                      # (ref_name, offset, numel, group, kind)
+        off = 0
+
+        def alloc(n):
+            nonlocal off
+            o = off
+            off = _round_up(off + n, 64)
+            return o
+        layout = {}
+        for group in ("backbone", "transformers"):
+            for name, p in spec.items():
+                if p.group != group:
+                    continue
+                if p.kind == "conv":
+                    kh, kw, ci, co = p.shape
+                    if name == "backbone/conv1/kernel":
+                        n = co * kh * 8 * 4          # 7 x 8(padded) taps x 4(padded) channels
+                    else:
+                        n = co * kh * kw * ci
+                else:
+                    n = 1
+                    for s in p.shape:
+                        n *= s
+                o = alloc(n)
+                layout[name] = (o, n)
+                self.vars.append((name, o, n, group, p.kind))
+        self.total = off
+        self.params = torch.zeros(self.total, dtype=F32, device=dev)
+        self.grads = torch.zeros(self.total, dtype=F32, device=dev)
+        self.adam_m = torch.zeros(self.total, dtype=F32, device=dev)
+        self.adam_v = torch.zeros(self.total, dtype=F32, device=dev)
+        self.layout = layout
+        T = len(self.vars)
+        self.T = T
+        self.table = torch.tensor([[o, n] for (_, o, n, _, _) in self.vars], dtype=torch.int64).to(dev)
+        self.lr_group = torch.tensor([GROUPS.index(g) for (_, _, _, g, _) in self.vars], dtype=torch.int32).to(dev)
+        self.lrs = torch.zeros(8, dtype=F32, device=dev)
+        self.group_enabled = torch.zeros(8, dtype=torch.uint8, device=dev)
+        self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.norms = torch.zeros(T, dtype=F32, device=dev)
+        self.group_range = {}
+        for g in ("backbone", "transformers"):
+            offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
+            self.group_range[g] = (offs[0][0], offs[-1][0] + offs[-1][1])
+
+        def view(arena, name):
+            o, n = layout[name]
+            return arena[o:o + n]
+
+        # ---- slots
+        def conv_slot(prefix, kname, bn_prefix=None, bias_name=None, stride=1, pad=0):
+            kh, kw, ci, co = spec[kname].shape
+            s = Slot()
+            s.name = prefix
+            stem = (kname == "backbone/conv1/kernel")
+            kwp, cip = (8, 4) if stem else (kw, ci)
+            s.N, s.taps, s.Cin = co, kh * kwp, cip
+            s.K = s.taps * s.Cin
+            s.master, s.grad = view(self.params, kname), view(self.grads, kname)
+            if bias_name:
+                s.bias, s.bias_grad = view(self.params, bias_name), view(self.grads, bias_name)
+            if bn_prefix:
+                s.fold = torch.ones(co, dtype=F32, device=dev)
+                s.shift = torch.zeros(co, dtype=F32, device=dev)
+                s.bn_prefix = bn_prefix
+            s.Wf = torch.zeros(co, s.K, dtype=BF16, device=dev)
+            if not stem:
+                s.ldd = _round_up(co, 32)
+                s.Wd = torch.zeros(ci, s.taps, s.ldd, dtype=BF16, device=dev)
+            s.geom = (kh, kw, kwp, stride, pad)
+            self.slots[prefix] = s
+            return s
+
+        def lin_slot(prefix, kname=None, bname=None):
+            kname = kname or prefix + "/kernel"
+            bname = bname or prefix + "/bias"
+            o_, i_ = spec[kname].shape
+            s = Slot()
+            s.name = prefix
+            s.N, s.taps, s.Cin, s.K = o_, 1, i_, i_
+            s.master, s.grad = view(self.params, kname), view(self.grads, kname)
+            s.bias, s.bias_grad = view(self.params, bname), view(self.grads, bname)
+            s.Wf = torch.zeros(o_, i_, dtype=BF16, device=dev)
+            s.ldd = _round_up(o_, 32)
+            s.Wd = torch.zeros(i_, 1, s.ldd, dtype=BF16, device=dev)
+            self.slots[prefix] = s
+            return s
+
+        conv_slot("backbone/conv1", "backbone/conv1/kernel", "backbone/bn1", stride=2, pad=3)
+        self.blocks = []
+        cin = 64
+        for li, (nb, d1, d2, stride) in enumerate(RESNET_STAGES[self.backbone_name]):
+            for b in range(nb):
+                p = f"backbone/layer{li + 1}/{b}"
+                st = stride if b == 0 else 1
+                blk = dict(prefix=p, cin=cin, d1=d1, d2=d2, stride=st, ds=(b == 0), first=(li == 0 and b == 0))
+                blk["c1"] = conv_slot(p + "/conv1", p + "/conv1/kernel", p + "/bn1")
+                blk["c2"] = conv_slot(p + "/conv2", p + "/conv2/kernel", p + "/bn2", stride=st, pad=1)
+                blk["c3"] = conv_slot(p + "/conv3", p + "/conv3/kernel", p + "/bn3")
+                if b == 0:
+                    blk["cd"] = conv_slot(p + "/downsample", p + "/downsample_0/kernel", p + "/downsample_1", stride=st)
+                self.blocks.append(blk)
+                cin = d2
+        self.c_feat = cin
+        conv_slot("input_proj", "input_proj/kernel", None, "input_proj/bias")
+
+        def mha_slots(p):
+            return dict(inp=lin_slot(p + "/in_proj", p + "/in_proj_kernel", p + "/in_proj_bias"),
+                        out=lin_slot(p + "/out_proj", p + "/out_proj_kernel", p + "/out_proj_bias"))
+
+        def ln_views(p):
+            return dict(g=view(self.params, p + "/gamma"), b=view(self.params, p + "/beta"),
+                        dg=view(self.grads, p + "/gamma"), db=view(self.grads, p + "/beta"))
+        self.enc = []
+        for l in range(self.nenc):
+            p = f"transformer/encoder/layer_{l}"
+            self.enc.append(dict(sa=mha_slots(p + "/self_attn"), l1=lin_slot(p + "/linear1"), l2=lin_slot(p + "/linear2"),
+                                 n1=ln_views(p + "/norm1"), n2=ln_views(p + "/norm2")))
+        self.dec = []
+        for l in range(self.ndec):
+            p = f"transformer/decoder/layer_{l}"
+            self.dec.append(dict(sa=mha_slots(p + "/self_attn"), ca=mha_slots(p + "/multihead_attn"),
+                                 l1=lin_slot(p + "/linear1"), l2=lin_slot(p + "/linear2"),
+                                 n1=ln_views(p + "/norm1"), n2=ln_views(p + "/norm2"), n3=ln_views(p + "/norm3")))
+        self.dec_norm = ln_views("transformer/decoder/norm")
+        self.h_cls = lin_slot("class_embed")
+        self.h_b0, self.h_b1, self.h_b2 = lin_slot("bbox_embed_0"), lin_slot("bbox_embed_1"), lin_slot("bbox_embed_2")
+        self.bn = {n: torch.zeros(p.shape, dtype=F32, device=dev) for n, p in spec.items() if p.kind.startswith("bn_")}
+        self.query_embed = torch.zeros(self.Q, self.d, dtype=F32, device=dev)
+        self.query_pos = torch.zeros(self.Q, self.d, dtype=BF16, device=dev)
+
+    def load_params(self, ref_params):
+        """ref_params: {reference name: tensor in the reference layout} (HWIO convs, [out,in] linears)."""
+        dev = self.device
+        for name, p in self.spec.items():
+            t = ref_params[name].detach().to(torch.float32).cpu()
+            assert tuple(t.shape) == p.shape, (name, tuple(t.shape), p.shape)
+            if p.kind.startswith("bn_"):
+                self.bn[name].copy_(t)
+            elif p.kind == "embed":
+                self.query_embed.copy_(t)
+            else:
+                if p.kind == "conv":
+                    kh, kw, ci, co = p.shape
+                    t = t.permute(3, 0, 1, 2).contiguous()              # [co, kh, kw, ci]
+                    if name == "backbone/conv1/kernel":
+                        tp = torch.zeros(co, kh, 8, 4)
+                        tp[:, :, :kw, :ci] = t
+                        t = tp
+                o, n = self.layout[name]
+                self.params[o:o + n].copy_(t.reshape(-1))
+        # FrozenBatchNorm2D (custom_layers.py:21-24): scale = w * rsqrt(var + eps); shift = b - mean * scale
+        for s in self.slots.values():
+            if s.fold is not None:
+                pre = s.bn_prefix
+                scale = self.bn[pre + "/weight"] * torch.rsqrt(self.bn[pre + "/running_var"] + 1e-5)
+                s.fold.copy_(scale)
+                s.shift.copy_(self.bn[pre + "/bias"] - self.bn[pre + "/running_mean"] * scale)
+        self.query_pos.copy_(self.query_embed.to(BF16))
+        self.refresh_weights()
+
+    def export_params(self):
+        out = OrderedDict()
+        for name, p in self.spec.items():
+            if p.kind.startswith("bn_"):
+                out[name] = self.bn[name].detach().cpu().clone()
+            elif p.kind == "embed":
+                out[name] = self.query_embed.detach().cpu().clone()
+            else:
+                out[name] = self._to_ref_layout(name, self.params)
+        return out
+
+    def _to_ref_layout(self, name, arena):
+        p = self.spec[name]
+        o, n = self.layout[name]
+        t = arena[o:o + n].detach().cpu().clone()
+        if p.kind == "conv":
+            kh, kw, ci, co = p.shape
+            if name == "backbone/conv1/kernel":
+                t = t.reshape(co, kh, 8, 4)[:, :, :kw, :ci]
+            else:
+                t = t.reshape(co, kh, kw, ci)
+            return t.permute(1, 2, 3, 0).contiguous()
+        return t.reshape(p.shape)
+
+    def export_grads(self):
+        return OrderedDict((name, self._to_ref_layout(name, self.grads)) for (name, _, _, _, _) in self.vars)
+
+    def refresh_weights(self):
+        """fp32 master -> bf16 kernel-layout copies (FrozenBN scale folded in)."""
+        for s in self.slots.values():
+            ops.prep_weight(s.master, s.fold, s.N, s.taps, s.Cin, s.Wf, s.K, s.Wd, s.ldd)
+            self.launches += 1
+
+    # ------------------------------------------------------------------------------------------ plan / buffers
+    def _plan(self, B, H, W):
+        key = (B, H, W)
+        if self.plan_key == key:
+            return
+        dev = self.device
+        self.plan_key = key
+        self.B = B
+
+        def o(n, k, s, p):
+            return (n + 2 * p - k) // s + 1
+        a = {}
+
+        def buf(name, *shape, dtype=BF16):
+            a[name] = torch.empty(*shape, dtype=dtype, device=dev)
+            return a[name]
+        self.a = a
+        self.H0, self.W0 = H, W
+        h1, w1 = o(H, 7, 2, 3), o(W, 7, 2, 3)
+        h2, w2 = o(h1, 3, 2, 1), o(w1, 3, 2, 1)
+        self.hw_stem, self.hw_pool = (h1, w1), (h2, w2)
+        buf("img4", B, H, W, 4)
+        buf("stem", B, h1, w1, 64)
+        buf("pool", B, h2, w2, 64)
+        buf("pool_arg", B, h2, w2, 64, dtype=torch.uint8)
+        hh, ww = h2, w2
+        max_elems = B * h1 * w1 * 64
+        for i, blk in enumerate(self.blocks):
+            st = blk["stride"]
+            ho, wo = (o(hh, 3, st, 1), o(ww, 3, st, 1)) if st > 1 else (hh, ww)
+            blk["in_hw"], blk["out_hw"] = (hh, ww), (ho, wo)
+            buf(f"b{i}_a1", B, hh, ww, blk["d1"])
+            buf(f"b{i}_a2", B, ho, wo, blk["d1"])
+            if blk["ds"]:
+                buf(f"b{i}_idn", B, ho, wo, blk["d2"])
+            buf(f"b{i}_out", B, ho, wo, blk["d2"])
+            max_elems = max(max_elems, B * hh * ww * max(blk["cin"], blk["d1"]), B * ho * wo * blk["d2"])
+            hh, ww = ho, wo
+        self.fh, self.fw = hh, ww
+        S = hh * ww
+        self.S = S
+        M, Mq, d, dff, Q = B * S, B * self.Q, self.d, self.dff, self.Q
+        self.M, self.Mq = M, Mq
+        # position embedding: input independent (all-False mask, detr.py:172) -> computed once, fp32 then bf16
+        self.pos = self._pos_embedding(hh, ww).to(dev).to(BF16).contiguous()
+        buf("src", M, d)
+        buf("srcp", M, d)
+        for l in range(self.nenc):
+            for nm, shp in (("qk", (M, 2 * d)), ("v", (M, d)), ("o", (M, d)), ("pre1", (M, d)), ("y1", (M, d)),
+                            ("h", (M, dff)), ("pre2", (M, d)), ("y2", (M, d)), ("y2p", (M, d))):
+                buf(f"e{l}_{nm}", *shp)
+            buf(f"e{l}_lse", B * self.H * S, dtype=F32)
+            for nm in ("mean1", "rstd1", "mean2", "rstd2"):
+                buf(f"e{l}_{nm}", M, dtype=F32)
+        buf("tgt0", Mq, d).zero_()
+        for l in range(self.ndec):
+            for nm, shp in (("tq", (Mq, d)), ("qk", (Mq, 2 * d)), ("v", (Mq, d)), ("o", (Mq, d)), ("pre1", (Mq, d)),
+                            ("t1", (Mq, d)), ("t1q", (Mq, d)), ("q2", (Mq, d)), ("k2", (M, d)), ("v2", (M, d)),
+                            ("o2", (Mq, d)), ("pre2", (Mq, d)), ("t2", (Mq, d)), ("h", (Mq, dff)), ("pre3", (Mq, d)),
+                            ("t3", (Mq, d))):
+                buf(f"d{l}_{nm}", *shp)
+            buf(f"d{l}_lse1", B * self.H * Q, dtype=F32)
+            buf(f"d{l}_lse2", B * self.H * Q, dtype=F32)
+            for nm in ("mean1", "rstd1", "mean2", "rstd2", "mean3", "rstd3", "meanf", "rstdf"):
+                buf(f"d{l}_{nm}", Mq, dtype=F32)
+        L = self.ndec
+        buf("hs", L * Mq, d)
+        buf("logits", L * Mq, self.C, dtype=F32)
+        buf("hb1", L * Mq, d)
+        buf("hb2", L * Mq, d)
+        buf("boxes", L * Mq, 4, dtype=F32)
+        # matcher / loss
+        P = L * B
+        buf("p_indices", P, Q, dtype=torch.int64)
+        buf("t_indices", P, Q, dtype=torch.int64)
+        buf("p_selector", P, Q, dtype=torch.uint8)
+        buf("match", P, Q, dtype=torch.int32)
+        buf("status", P, dtype=torch.int32)
+        buf("loss_sums", L, 8, dtype=F32)
+        buf("losses", L, 6, dtype=F32)
+        buf("total", 1, dtype=F32)
+        buf("t_bbox", B, 100, 4, dtype=F32)
+        buf("t_class", B, 100, 1, dtype=torch.int64)
+        buf("images", B, H, W, 3, dtype=F32)
+        self.ld_dl = _round_up(self.C, 32)
+        buf("d_logits", L * Mq, self.ld_dl)
+        buf("d_boxpre", L * Mq, 32)
+        # backward scratch
+        buf("g_hs", L * Mq, d)
+        buf("g_hb1", L * Mq, d)
+        buf("g_hb2", L * Mq, d)
+        for nm, shp in (("gq_a", (Mq, d)), ("gq_b", (Mq, d)), ("gq_c", (Mq, d)), ("gq_d", (Mq, d)), ("gq_qk", (Mq, 2 * d)),
+                        ("gq_n0", (Mq, d)), ("gq_n1", (Mq, d)), ("gm_n0", (M, d)), ("gm_n1", (M, d)),
+                        ("gq_v", (Mq, d)), ("gq_h", (Mq, dff)), ("gq_q2", (Mq, d)), ("gm_k2", (M, d)), ("gm_v2", (M, d)),
+                        ("g_mem", (M, d)), ("gm_a", (M, d)), ("gm_b", (M, d)), ("gm_c", (M, d)), ("gm_d", (M, d)),
+                        ("gm_qk", (M, 2 * d)), ("gm_v", (M, d)), ("gm_h", (M, dff))):
+            buf(nm, *shp)
+        buf("delta", B * self.H * max(S, Q), dtype=F32)
+        buf("g_x", max_elems)
+        buf("g_y", max_elems)
+        buf("g_1", max_elems)
+        buf("g_2", max_elems)
+        self.normalisers = None
+
+    def _pos_embedding(self, h, w):
+        """position_embeddings.py:23-50 with an all-False mask -> [h*w, 256] fp32 (host, once per shape)."""
+        eps, scale, npf, T = 1e-6, 2 * math.pi, 128, 10000.0
+        y = torch.arange(1, h + 1, dtype=F32).view(h, 1).expand(h, w)
+        x = torch.arange(1, w + 1, dtype=F32).view(1, w).expand(h, w)
+        y = y / (y[-1:, :] + eps) * scale
+        x = x / (x[:, -1:] + eps) * scale
+        dim_t = torch.arange(npf, dtype=F32)
+        dim_t = T ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / npf)
+        px, py = x[..., None] / dim_t, y[..., None] / dim_t
+        px = torch.stack([px[..., 0::2].sin(), px[..., 1::2].cos()], dim=3).reshape(h, w, -1)
+        py = torch.stack([py[..., 0::2].sin(), py[..., 1::2].cos()], dim=3).reshape(h, w, -1)
+        return torch.cat([py, px], dim=2).reshape(h * w, 2 * npf)
+
+    # ------------------------------------------------------------------------------------------ op helpers
+    def _site(self, name):
+        if name not in self.sites:
+            self.sites[name] = len(self.sites) + 1
+        return self.sites[name]
+
+    def _drop(self, name):
+        if self.training and self.dropout > 0:
+            return dict(drop_p=self.dropout, seed=self.base_seed, site=self._site(name), seed_ptr=self.seed_dev)
+        return {}
+
+    def _lin(self, A, W, M, N, K, ldw, out=None, ldc=None, lda=None, **kw):
+        """plain GEMM  out[M,N] = A[M,K] . W[N,K]^T (+epilogue)"""
+        self.launches += 1
+        ops.igemm(A, W, M, N, K, lda or K, ldw, ops.plain_geom(M, K), C=out, ldc=(ldc if ldc is not None else N), **kw)
+
+    def _conv_geom(self, s, B, ih, iw, oh, ow, mode=0):
+        kh, kw, kwp, stride, pad = s.geom
+        return dict(batch=B, IH=ih, IW=iw, Cin=s.Cin, OH=oh, OW=ow, KH=kh, KW=kwp, stride=stride, pad=pad, mode=mode)
+
+    def _conv_fwd(self, s, x, ihw, ohw, out, relu=True, residual=None):
+        B = self.B
+        g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
+        self.launches += 1
+        ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual, ldr=s.N,
+                  relu=relu, C=out, ldc=s.N)
+
+    def _conv_dgrad(self, s, dy, ihw, ohw, out, mask=None, residual=None):
+        """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]."""
+        B = self.B
+        kh, kw, kwp, stride, pad = s.geom
+        M = B * ihw[0] * ihw[1]
+        g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=s.ldd, OH=ihw[0], OW=ihw[1], KH=kh, KW=kwp, stride=stride, pad=pad, mode=1)
+        self.launches += 1
+        ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin, mask_scale=1.0,
+                  residual=residual, ldr=s.Cin, C=out, ldc=s.Cin)
+
+    def _conv_wgrad(self, s, x, dy, ihw, ohw):
+        B = self.B
+        g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
+        self.launches += 1
+        ops.wgrad(x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold, dbias=s.bias_grad)
+
+    def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
+        """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
+        n_rows = n_rows or s.N
+        self.launches += 2
+        ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
+                  s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:])
+
+    def _ln_fwd(self, x, n, y, mean, rstd, M, y2=None, pos=None, S=1):
+        self.launches += 1
+        ops.layernorm_fwd(x, n["g"], n["b"], y, y2, pos, S, mean, rstd, M)
+
+    def _ln_bwd(self, dy, dy2, x, n, mean, rstd, dx, dx_drop, M, drop_name=None):
+        self.launches += 1
+        d = self._drop(drop_name) if drop_name else {}
+        ops.layernorm_bwd(dy, dy2, x, n["g"], mean, rstd, dx, dx_drop, d.get("drop_p", 0.0), d.get("seed", 0),
+                          d.get("site", 0), d.get("seed_ptr"), n["dg"], n["db"], M)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, images, training=False):
+        """images: [B,H,W,3] float32 (NHWC like the reference, training.py:18).  Returns the reference's output
+        dict {'pred_logits','pred_boxes','aux'} as fp32 device tensors (detr.py:190-204)."""
+        B, H, W, _ = images.shape
+        self._plan(B, H, W)
+        self.training = bool(training)
+        a = self.a
+        if images.device != self.device or images.data_ptr() != a["images"].data_ptr():
+            a["images"].copy_(images, non_blocking=True)
+        self._forward_impl()
+        return self.outputs()
+
+    def outputs(self):
+        a, L, B, Q = self.a, self.ndec, self.B, self.Q
+        lg = a["logits"].view(L, B, Q, self.C)
+        bx = a["boxes"].view(L, B, Q, 4)
+        return {"pred_logits": lg[L - 1], "pred_boxes": bx[L - 1],
+                "aux": [{"pred_logits": lg[i], "pred_boxes": bx[i]} for i in range(L - 1)]}
+
+    def _forward_impl(self):
+        a, B = self.a, self.B
+        d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
+        scale = float(d // Hh) ** -0.5
+        # ---------------- backbone (resnet_backbone.py:20-32)
+        ops.image_to_nhwc4(a["images"], a["img4"], B * self.H0 * self.W0)
+        self.launches += 1
+        stem = self.slots["backbone/conv1"]
+        self._conv_fwd(stem, a["img4"], (self.H0, self.W0), self.hw_stem, a["stem"], relu=True)
+        ops.maxpool_fwd(a["stem"], a["pool"], a["pool_arg"], B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
+        self.launches += 1
+        x = a["pool"]
+        for i, blk in enumerate(self.blocks):
+            ihw, ohw = blk["in_hw"], blk["out_hw"]
+            self._conv_fwd(blk["c1"], x, ihw, ihw, a[f"b{i}_a1"])
+            self._conv_fwd(blk["c2"], a[f"b{i}_a1"], ihw, ohw, a[f"b{i}_a2"])
+            if blk["ds"]:
+                self._conv_fwd(blk["cd"], x, ihw, ohw, a[f"b{i}_idn"], relu=False)
+                idn = a[f"b{i}_idn"]
+            else:
+                idn = x
+            self._conv_fwd(blk["c3"], a[f"b{i}_a2"], ohw, ohw, a[f"b{i}_out"], relu=True, residual=idn)
+            x = a[f"b{i}_out"]
+        self.feat = x
+        # ---------------- input_proj (detr.py:44,175) + pos add
+        ip = self.slots["input_proj"]
+        self._lin(x, ip.Wf, M, d, ip.K, ip.K, out=a["src"], bias=ip.bias)
+        ops.add_rowbcast(a["src"], self.pos, a["srcp"], M, S, d)
+        self.launches += 1
+        # ---------------- encoder (transformer.py:157-179)
+        xin, xinp = a["src"], a["srcp"]
+        for l, E in enumerate(self.enc):
+            e = lambda n: a[f"e{l}_{n}"]
+            W = E["sa"]["inp"]
+            self._lin(xinp, W.Wf, M, 2 * d, d, d, out=e("qk"), bias=W.bias)
+            self._lin(xin, W.Wf[2 * d:], M, d, d, d, out=e("v"), bias=W.bias[2 * d:])
+            self.launches += 1
+            ops.attn_fwd(e("qk"), e("qk")[:, d:], e("v"), 2 * d, 2 * d, d, e("o"), d, e("lse"), B, Hh, S, S, scale,
+                         **self._attn_drop(f"e{l}_attn"))
+            Wo = E["sa"]["out"]
+            self._lin(e("o"), Wo.Wf, M, d, d, d, out=e("pre1"), bias=Wo.bias, residual=xin, ldr=d, **self._drop(f"e{l}_do1"))
+            self._ln_fwd(e("pre1"), E["n1"], e("y1"), e("mean1"), e("rstd1"), M)
+            self._lin(e("y1"), E["l1"].Wf, M, dff, d, d, out=e("h"), bias=E["l1"].bias, relu=True, **self._drop(f"e{l}_dh"))
+            self._lin(e("h"), E["l2"].Wf, M, d, dff, dff, out=e("pre2"), bias=E["l2"].bias, residual=e("y1"), ldr=d,
+                      **self._drop(f"e{l}_do2"))
+            self._ln_fwd(e("pre2"), E["n2"], e("y2"), e("mean2"), e("rstd2"), M, y2=e("y2p"), pos=self.pos, S=S)
+            xin, xinp = e("y2"), e("y2p")
+        mem, memp = xin, xinp
+        self.mem, self.memp = mem, memp
+        # ---------------- decoder (transformer.py:207-234, 104-133)
+        tgt = a["tgt0"]
+        for l, D in enumerate(self.dec):
+            t = lambda n: a[f"d{l}_{n}"]
+            ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d)
+            self.launches += 1
+            W = D["sa"]["inp"]
+            self._lin(t("tq"), W.Wf, Mq, 2 * d, d, d, out=t("qk"), bias=W.bias)
+            self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:])
+            self.launches += 1
+            ops.attn_fwd(t("qk"), t("qk")[:, d:], t("v"), 2 * d, 2 * d, d, t("o"), d, t("lse1"), B, Hh, Q, Q, scale,
+                         **self._attn_drop(f"d{l}_attn1"))
+            Wo = D["sa"]["out"]
+            self._lin(t("o"), Wo.Wf, Mq, d, d, d, out=t("pre1"), bias=Wo.bias, residual=tgt, ldr=d, **self._drop(f"d{l}_do1"))
+            self._ln_fwd(t("pre1"), D["n1"], t("t1"), t("mean1"), t("rstd1"), Mq, y2=t("t1q"), pos=self.query_pos, S=Q)
+            W = D["ca"]["inp"]
+            self._lin(t("t1q"), W.Wf, Mq, d, d, d, out=t("q2"), bias=W.bias)
+            self._lin(memp, W.Wf[d:], M, d, d, d, out=t("k2"), bias=W.bias[d:])
+            self._lin(mem, W.Wf[2 * d:], M, d, d, d, out=t("v2"), bias=W.bias[2 * d:])
+            self.launches += 1
+            ops.attn_fwd(t("q2"), t("k2"), t("v2"), d, d, d, t("o2"), d, t("lse2"), B, Hh, Q, S, scale,
+                         **self._attn_drop(f"d{l}_attn2"))
+            Wo = D["ca"]["out"]
+            self._lin(t("o2"), Wo.Wf, Mq, d, d, d, out=t("pre2"), bias=Wo.bias, residual=t("t1"), ldr=d, **self._drop(f"d{l}_do2"))
+            self._ln_fwd(t("pre2"), D["n2"], t("t2"), t("mean2"), t("rstd2"), Mq)
+            self._lin(t("t2"), D["l1"].Wf, Mq, dff, d, d, out=t("h"), bias=D["l1"].bias, relu=True, **self._drop(f"d{l}_dh"))
+            self._lin(t("h"), D["l2"].Wf, Mq, d, dff, dff, out=t("pre3"), bias=D["l2"].bias, residual=t("t2"), ldr=d,
+                      **self._drop(f"d{l}_do3"))
+            self._ln_fwd(t("pre3"), D["n3"], t("t3"), t("mean3"), t("rstd3"), Mq)
+            # shared final norm on every layer output (transformer.py:122-126)
+            self._ln_fwd(t("t3"), self.dec_norm, a["hs"][l * Mq:(l + 1) * Mq], t("meanf"), t("rstdf"), Mq)
+            tgt = t("t3")
+        # ---------------- heads (detr.py:185-188)
+        LM = self.ndec * Mq
+        self._lin(a["hs"], self.h_cls.Wf, LM, self.C, d, d, Cf=a["logits"], ldcf=self.C, bias=self.h_cls.bias)
+        self._lin(a["hs"], self.h_b0.Wf, LM, d, d, d, out=a["hb1"], bias=self.h_b0.bias, relu=True)
+        self._lin(a["hb1"], self.h_b1.Wf, LM, d, d, d, out=a["hb2"], bias=self.h_b1.bias, relu=True)
+        self._lin(a["hb2"], self.h_b2.Wf, LM, 4, d, d, Cf=a["boxes"], ldcf=4, bias=self.h_b2.bias, sigmoid=True)
+
+    def _attn_drop(self, name):
+        return self._drop(name)
+
+    # ------------------------------------------------------------------------------------------ loss
+    def match(self, want_cost=False):
+        """Hungarian matching of all L*B problems on device (hungarian_matching.py:163-203)."""
+        a, L, B, Q = self.a, self.ndec, self.B, self.Q
+        cost = None
+        if want_cost:
+            cost = torch.zeros(L * B, Q, 100, dtype=F32, device=self.device)
+        self.launches += 1
+        ops.matcher(a["logits"], self.C, a["boxes"], a["t_bbox"], a["t_class"], L * B, B, Q, self.C,
+                    a["p_indices"], a["t_indices"], a["p_selector"], a["match"], cost, a["status"])
+        return cost
+
+    def set_targets(self, t_bbox, t_class):
+        a = self.a
+        a["t_bbox"].copy_(t_bbox.reshape(a["t_bbox"].shape), non_blocking=True)
+        a["t_class"].copy_(t_class.reshape(a["t_class"].shape), non_blocking=True)
+
+    def loss(self, background_class, loss_scale=1.0, with_grad=True):
+        """get_losses (loss.py:22-34): matcher + set criterion for all decoder layers; fills d_logits/d_boxpre."""
+        a, L, B, Q = self.a, self.ndec, self.B, self.Q
+        self.match()
+        self.launches += 2
+        ops.set_loss(a["logits"], self.C, a["boxes"], a["t_bbox"], a["t_class"], a["match"], L, B, Q, self.C,
+                     background_class, self.normalisers, loss_scale, a["loss_sums"], a["losses"], a["total"],
+                     a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32)
+
+    def loss_dict(self):
+        """36 scalars with the reference's keys (loss.py:172-179; aux layer i -> suffix _i, main = last layer)."""
+        a, L = self.a, self.ndec
+        names = ("label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss")
+        out = OrderedDict()
+        for l in [L - 1] + list(range(L - 1)):
+            suf = "" if l == L - 1 else f"_{l}"
+            for k, n in enumerate(names):
+                out[n + suf] = a["losses"][l, k]
+        return a["total"][0], out
+
+    # ------------------------------------------------------------------------------------------ backward
+    def zero_grads(self):
+        self.grads.zero_()
+
+    def backward(self, train_backbone=True):
+        """Gradients of total_loss wrt every trainable variable, accumulated (+=) into self.grads.
+        train_backbone=False stops after the transformer (results identical for the trained groups; the reference
+        computes the dead work anyway, optimizers.py:112-115 / SURVEY appendix A.7)."""
+        a, B = self.a, self.B
+        d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
+        scale = float(d // Hh) ** -0.5
+        LM = self.ndec * Mq
+        inv_keep = 1.0 / (1.0 - self.dropout) if (self.training and self.dropout > 0) else 1.0
+        # ---------------- heads
+        self._lin_wgrad(self.h_b2, a["hb2"], a["d_boxpre"], LM, ldy=32)
+        self._lin(a["d_boxpre"], self.h_b2.Wd, LM, d, 32, 32, out=a["g_hb2"], mask=a["hb2"], ldm=d)
+        self._lin_wgrad(self.h_b1, a["hb1"], a["g_hb2"], LM)
+        self._lin(a["g_hb2"], self.h_b1.Wd, LM, d, d, d, out=a["g_hb1"], mask=a["hb1"], ldm=d)
+        self._lin_wgrad(self.h_b0, a["hs"], a["g_hb1"], LM)
+        self._lin(a["g_hb1"], self.h_b0.Wd, LM, d, d, d, out=a["g_hs"])
+        self._lin_wgrad(self.h_cls, a["hs"], a["d_logits"], LM, ldy=self.ld_dl)
+        self._lin(a["d_logits"], self.h_cls.Wd, LM, d, self.ld_dl, self.ld_dl, out=a["g_hs"], residual=a["g_hs"], ldr=d)
+        # ---------------- decoder, last layer first
+        mem, memp = self.mem, self.memp
+        g_next = None                      # gradient wrt t3 coming from layer l+1 (None for the last layer)
+        first_mem = True
+        for l in reversed(range(self.ndec)):
+            D = self.dec[l]
+            t = lambda n: a[f"d{l}_{n}"]
+            tgt = a["tgt0"] if l == 0 else a[f"d{l - 1}_t3"]
+            # final-norm branch: d t3 += LN_f'(g_hs[l])
+            self._ln_bwd(a["g_hs"][l * Mq:(l + 1) * Mq], None, t("t3"), self.dec_norm, t("meanf"), t("rstdf"), a["gq_a"], None, Mq)
+            # LN3
+            self._ln_bwd(a["gq_a"], g_next, t("pre3"), D["n3"], t("mean3"), t("rstd3"), a["gq_b"], a["gq_c"], Mq, f"d{l}_do3")
+            # FFN: pre3 = t2 + drop(h W2 + b2), h = drop(relu(t2 W1 + b1))
+            self._lin_wgrad(D["l2"], t("h"), a["gq_c"], Mq)
+            self._lin(a["gq_c"], D["l2"].Wd, Mq, dff, d, d, out=a["gq_h"], mask=t("h"), ldm=dff, mask_scale=inv_keep)
+            self._lin_wgrad(D["l1"], t("t2"), a["gq_h"], Mq)
+            self._lin(a["gq_h"], D["l1"].Wd, Mq, d, dff, dff, out=a["gq_a"], residual=a["gq_b"], ldr=d)      # d t2
+            # LN2
+            self._ln_bwd(a["gq_a"], None, t("pre2"), D["n2"], t("mean2"), t("rstd2"), a["gq_b"], a["gq_c"], Mq, f"d{l}_do2")
+            # cross attention: pre2 = t1 + drop(o2 Wo + bo)
+            Wo, W = D["ca"]["out"], D["ca"]["inp"]
+            self._lin_wgrad(Wo, t("o2"), a["gq_c"], Mq)
+            self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o2
+            self.launches += 3
+            ops.attn_bwd(t("q2"), t("k2"), t("v2"), t("o2"), a["gq_d"], d, d, d, d, d, t("lse2"), a["delta"],
+                         a["gq_q2"], a["gm_k2"], a["gm_v2"], d, d, d, B, Hh, Q, S, scale, **self._attn_drop(f"d{l}_attn2"))
+            self._lin_wgrad(W, t("t1q"), a["gq_q2"], Mq, n_off=0, n_rows=d)
+            self._lin_wgrad(W, memp, a["gm_k2"], M, n_off=d, n_rows=d)
+            self._lin_wgrad(W, mem, a["gm_v2"], M, n_off=2 * d, n_rows=d)
+            # d memory accumulates over decoder layers (memory feeds every cross attention)
+            self._lin(a["gm_k2"], W.Wd[:, :, d:], M, d, d, W.ldd, out=a["g_mem"], residual=None if first_mem else a["g_mem"], ldr=d)
+            self._lin(a["gm_v2"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=a["g_mem"], residual=a["g_mem"], ldr=d)
+            first_mem = False
+            self._lin(a["gq_q2"], W.Wd, Mq, d, d, W.ldd, out=a["gq_a"], residual=a["gq_b"], ldr=d)            # d t1
+            # LN1
+            self._ln_bwd(a["gq_a"], None, t("pre1"), D["n1"], t("mean1"), t("rstd1"), a["gq_b"], a["gq_c"], Mq, f"d{l}_do1")
+            # self attention: pre1 = tgt + drop(o Wo + bo)
+            Wo, W = D["sa"]["out"], D["sa"]["inp"]
+            self._lin_wgrad(Wo, t("o"), a["gq_c"], Mq)
+            self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o
+            self.launches += 3
+            ops.attn_bwd(t("qk"), t("qk")[:, d:], t("v"), t("o"), a["gq_d"], 2 * d, 2 * d, d, d, d, t("lse1"), a["delta"],
+                         a["gq_qk"], a["gq_qk"][:, d:], a["gq_v"], 2 * d, 2 * d, d, B, Hh, Q, Q, scale,
+                         **self._attn_drop(f"d{l}_attn1"))
+            self._lin_wgrad(W, t("tq"), a["gq_qk"], Mq, n_off=0, n_rows=2 * d)
+            self._lin_wgrad(W, tgt, a["gq_v"], Mq, n_off=2 * d, n_rows=d)
+            if l > 0:
+                # d tgt = d_pre1 + dqk.Wqk (tq = tgt + query_pos) + dv.Wv   -> gradient wrt the previous layer's t3
+                self._lin(a["gq_qk"], W.Wd, Mq, d, 2 * d, W.ldd, out=a["gq_a"], residual=a["gq_b"], ldr=d)
+                g_next = a["gq_n0"] if (l & 1) else a["gq_n1"]       # ping-pong: read by layer l-1's LN3 backward
+                self._lin(a["gq_v"], W.Wd[:, :, 2 * d:], Mq, d, d, W.ldd, out=g_next, residual=a["gq_a"], ldr=d)
+        # ---------------- encoder, last layer first.  g_mem = d y2 (last encoder layer output incl. its +pos use)
+        g_y = a["g_mem"]
+        for l in reversed(range(self.nenc)):
+            E = self.enc[l]
+            e = lambda n: a[f"e{l}_{n}"]
+            xin = a["src"] if l == 0 else a[f"e{l - 1}_y2"]
+            xinp = a["srcp"] if l == 0 else a[f"e{l - 1}_y2p"]
+            self._ln_bwd(g_y, None, e("pre2"), E["n2"], e("mean2"), e("rstd2"), a["gm_a"], a["gm_b"], M, f"e{l}_do2")
+            self._lin_wgrad(E["l2"], e("h"), a["gm_b"], M)
+            self._lin(a["gm_b"], E["l2"].Wd, M, dff, d, d, out=a["gm_h"], mask=e("h"), ldm=dff, mask_scale=inv_keep)
+            self._lin_wgrad(E["l1"], e("y1"), a["gm_h"], M)
+            self._lin(a["gm_h"], E["l1"].Wd, M, d, dff, dff, out=a["gm_c"], residual=a["gm_a"], ldr=d)        # d y1
+            self._ln_bwd(a["gm_c"], None, e("pre1"), E["n1"], e("mean1"), e("rstd1"), a["gm_a"], a["gm_b"], M, f"e{l}_do1")
+            Wo, W = E["sa"]["out"], E["sa"]["inp"]
+            self._lin_wgrad(Wo, e("o"), a["gm_b"], M)
+            self._lin(a["gm_b"], Wo.Wd, M, d, d, d, out=a["gm_c"])                                             # d o
+            self.launches += 3
+            ops.attn_bwd(e("qk"), e("qk")[:, d:], e("v"), e("o"), a["gm_c"], 2 * d, 2 * d, d, d, d, e("lse"), a["delta"],
+                         a["gm_qk"], a["gm_qk"][:, d:], a["gm_v"], 2 * d, 2 * d, d, B, Hh, S, S, scale,
+                         **self._attn_drop(f"e{l}_attn"))
+            self._lin_wgrad(W, xinp, a["gm_qk"], M, n_off=0, n_rows=2 * d)
+            self._lin_wgrad(W, xin, a["gm_v"], M, n_off=2 * d, n_rows=d)
+            # d x = d_pre1 + dqk.Wqk + dv.Wv   (xp = x + pos shares x's gradient)
+            self._lin(a["gm_qk"], W.Wd, M, d, 2 * d, W.ldd, out=a["gm_c"], residual=a["gm_a"], ldr=d)
+            g_y = a["gm_n0"] if (l & 1) else a["gm_n1"]
+            self._lin(a["gm_v"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=g_y, residual=a["gm_c"], ldr=d)
+        # ---------------- input_proj
+        ip = self.slots["input_proj"]
+        self._lin_wgrad(ip, self.feat, g_y, M)
+        if not train_backbone:
+            return
+        nb = len(self.blocks)
+        last = self.blocks[-1]
+        g_out = a["g_x"]
+        self._lin(g_y, ip.Wd, M, self.c_feat, d, ip.ldd, out=g_out, mask=self.feat, ldm=self.c_feat)
+        # ---------------- backbone, last block first
+        g_in = a["g_y"]
+        for i in reversed(range(nb)):
+            blk = self.blocks[i]
+            ihw, ohw = blk["in_hw"], blk["out_hw"]
+            x = a["pool"] if i == 0 else a[f"b{i - 1}_out"]
+            a1, a2 = a[f"b{i}_a1"], a[f"b{i}_a2"]
+            xmask = None if blk["first"] else x
+            self._conv_wgrad(blk["c3"], a2, g_out, ohw, ohw)
+            self._conv_dgrad(blk["c3"], g_out, ohw, ohw, a["g_2"], mask=a2)
+            self._conv_wgrad(blk["c2"], a1, a["g_2"], ihw, ohw)
+            self._conv_dgrad(blk["c2"], a["g_2"], ihw, ohw, a["g_1"], mask=a1)
+            self._conv_wgrad(blk["c1"], x, a["g_1"], ihw, ihw)
+            self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask=xmask, residual=None if blk["ds"] else g_out)
+            if blk["ds"]:
+                cd = blk["cd"]
+                self._conv_wgrad(cd, x, g_out, ihw, ohw)
+                st = blk["stride"]
+                Mo = B * ohw[0] * ohw[1]
+                g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=cd.ldd, OH=ohw[0], OW=ohw[1], KH=1, KW=1, stride=1, pad=0, mode=0)
+                self.launches += 1
+                ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask=xmask, ldm=cd.Cin, mask_scale=1.0,
+                          C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True)
+            g_out, g_in = g_in, g_out
+        # g_out now holds d pool
+        self.launches += 1
+        ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
+        stem = self.slots["backbone/conv1"]
+        self._conv_wgrad(stem, a["img4"], g_in, (self.H0, self.W0), self.hw_stem)
+
+    # ------------------------------------------------------------------------------------------ optimizer
+    def set_lrs(self, backbone_lr, transformers_lr, nlayers_lr=0.0):
+        self.lrs[:3] = torch.tensor([backbone_lr, transformers_lr, nlayers_lr], dtype=F32)
+
+    def set_enabled(self, backbone, transformers, nlayers=False):
+        self.group_enabled[:3] = torch.tensor([int(backbone), int(transformers), int(nlayers)], dtype=torch.uint8)
+
+    def optimizer_step(self, clipnorm):
+        """aggregate_grad_and_apply's apply branch (optimizers.py:160-163) for all enabled groups."""
+        self.launches += 3
+        ops.adam_clipnorm(self.params, self.grads, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
+                          self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
+        self.refresh_weights()

@@ -1,0 +1,146 @@
+"""Thin Python wrappers over the C ABI (include/detrb.h).  Arguments are torch tensors (device memory owners)
+and plain ints; every call is enqueued on torch's current CUDA stream.  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p, byref
+
+import torch
+
+from . import _lib
+from ._lib import AttnBwdParams, AttnFwdParams, IgemmParams, WgradParams, check
+
+
+def _stream():
+    if torch.cuda.is_available():
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(0)
+
+
+def ptr(t, offset=0):
+    """device pointer of tensor `t` (+ element offset); None -> NULL"""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr() + offset * t.element_size())
+
+
+def plain_geom(M, K):
+    return dict(batch=1, IH=1, IW=M, Cin=K, OH=1, OW=M, KH=1, KW=1, stride=1, pad=0, mode=0)
+
+
+def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mask=None, ldm=0, mask_scale=1.0,
+          relu=False, sigmoid=False, drop_p=0.0, seed=0, site=0, seed_ptr=None, C=None, ldc=0, Cf=None, ldcf=0,
+          out_stride=1, SH=0, SW=0, accumulate=False):
+    p = IgemmParams()
+    p.A, p.W = ptr(A), ptr(W)
+    p.M, p.N, p.K, p.lda, p.ldw = M, N, K, lda, ldw
+    for k, v in geom.items():
+        setattr(p, k, v)
+    p.bias, p.residual, p.ldr, p.mask, p.ldm, p.mask_scale = ptr(bias), ptr(residual), ldr, ptr(mask), ldm, mask_scale
+    p.relu, p.sigmoid, p.drop_p, p.seed, p.site, p.seed_ptr = int(relu), int(sigmoid), drop_p, seed, site, ptr(seed_ptr)
+    p.C, p.ldc, p.Cf, p.ldcf = ptr(C), ldc, ptr(Cf), ldcf
+    p.out_stride, p.SH, p.SW, p.accumulate = out_stride, SH, SW, int(accumulate)
+    check(_lib.lib().detrb_igemm(byref(p), _stream()))
+
+
+def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None):
+    p = WgradParams()
+    p.A, p.lda, p.dY, p.ldy, p.M, p.N, p.K = ptr(A), lda, ptr(dY), ldy, M, N, K
+    for k, v in geom.items():
+        if k != "mode":
+            setattr(p, k, v)
+    p.rowscale, p.dW, p.ldw, p.dbias = ptr(rowscale), ptr(dW), ldw, ptr(dbias)
+    check(_lib.lib().detrb_wgrad(byref(p), _stream()))
+
+
+def attn_fwd(Q, K, V, ldq, ldk, ldv, O, ldo, lse, B, H, Lq, Lk, scale, drop_p=0.0, seed=0, site=0, seed_ptr=None):
+    p = AttnFwdParams()
+    p.Q, p.K, p.V, p.ldq, p.ldk, p.ldv = ptr(Q), ptr(K), ptr(V), ldq, ldk, ldv
+    p.O, p.ldo, p.lse, p.B, p.H, p.Lq, p.Lk = ptr(O), ldo, ptr(lse), B, H, Lq, Lk
+    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr = scale, drop_p, seed, site, ptr(seed_ptr)
+    check(_lib.lib().detrb_attn_fwd(byref(p), _stream()))
+
+
+def attn_bwd(Q, K, V, O, dO, ldq, ldk, ldv, ldo, lddo, lse, delta, dQ, dK, dV, lddq, lddk, lddv, B, H, Lq, Lk,
+             scale, drop_p=0.0, seed=0, site=0, seed_ptr=None):
+    p = AttnBwdParams()
+    p.Q, p.K, p.V, p.O, p.dO = ptr(Q), ptr(K), ptr(V), ptr(O), ptr(dO)
+    p.ldq, p.ldk, p.ldv, p.ldo, p.lddo = ldq, ldk, ldv, ldo, lddo
+    p.lse, p.delta, p.dQ, p.dK, p.dV = ptr(lse), ptr(delta), ptr(dQ), ptr(dK), ptr(dV)
+    p.lddq, p.lddk, p.lddv, p.B, p.H, p.Lq, p.Lk = lddq, lddk, lddv, B, H, Lq, Lk
+    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr = scale, drop_p, seed, site, ptr(seed_ptr)
+    check(_lib.lib().detrb_attn_bwd(byref(p), _stream()))
+
+
+def layernorm_fwd(x, gamma, beta, y, y2, pos, S, mean, rstd, M):
+    check(_lib.lib().detrb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(y2), ptr(pos), c_int(S),
+                                         ptr(mean), ptr(rstd), c_int(M), _stream()))
+
+
+def layernorm_bwd(dy, dy2, x, gamma, mean, rstd, dx, dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M):
+    check(_lib.lib().detrb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
+                                         ptr(dx_drop), c_float(drop_p), c_uint64(seed), c_uint32(site), ptr(seed_ptr),
+                                         ptr(dgamma), ptr(dbeta), c_int(M), _stream()))
+
+
+def add_rowbcast(x, pos, out, M, S, d):
+    check(_lib.lib().detrb_add_rowbcast(ptr(x), ptr(pos), ptr(out), c_int(M), c_int(S), c_int(d), _stream()))
+
+
+def add(a, b, out, n):
+    check(_lib.lib().detrb_add(ptr(a), ptr(b), ptr(out), c_int64(n), _stream()))
+
+
+def image_to_nhwc4(img, out, npix):
+    check(_lib.lib().detrb_image_to_nhwc4(ptr(img), ptr(out), c_int64(npix), _stream()))
+
+
+def f32_to_bf16(x, y, n):
+    check(_lib.lib().detrb_f32_to_bf16(ptr(x), ptr(y), c_int64(n), _stream()))
+
+
+def colsum(x, ldx, M, N, scale, out):
+    check(_lib.lib().detrb_colsum(ptr(x), c_int(ldx), c_int(M), c_int(N), ptr(scale), ptr(out), _stream()))
+
+
+def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW):
+    check(_lib.lib().detrb_maxpool_fwd(ptr(x), ptr(y), ptr(argmax), c_int(B), c_int(IH), c_int(IW), c_int(C),
+                                       c_int(OH), c_int(OW), _stream()))
+
+
+def maxpool_bwd(dy, argmax, x, dx, B, IH, IW, C, OH, OW):
+    check(_lib.lib().detrb_maxpool_bwd(ptr(dy), ptr(argmax), ptr(x), ptr(dx), c_int(B), c_int(IH), c_int(IW), c_int(C),
+                                       c_int(OH), c_int(OW), _stream()))
+
+
+def matcher(logits, ldl, boxes, t_bbox, t_class, P, B, Q, C, p_indices, t_indices, p_selector, match, cost, status,
+            fcost_class=1.0, fcost_bbox=5.0, fcost_giou=2.0):
+    check(_lib.lib().detrb_matcher(ptr(logits), c_int(ldl), ptr(boxes), ptr(t_bbox), ptr(t_class), c_int(P), c_int(B),
+                                   c_int(Q), c_int(C), c_float(fcost_class), c_float(fcost_bbox), c_float(fcost_giou),
+                                   ptr(p_indices), ptr(t_indices), ptr(p_selector), ptr(match), ptr(cost), ptr(status),
+                                   _stream()))
+
+
+def set_loss(logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class, normalisers, loss_scale,
+             sums, losses, total, d_logits, ld_dl, d_boxpre, ld_db):
+    check(_lib.lib().detrb_set_loss(ptr(logits), c_int(ldl), ptr(boxes), ptr(t_bbox), ptr(t_class), ptr(match),
+                                    c_int(L), c_int(B), c_int(Q), c_int(C), c_int(background_class), ptr(normalisers),
+                                    c_float(loss_scale), ptr(sums), ptr(losses), ptr(total), ptr(d_logits), c_int(ld_dl),
+                                    ptr(d_boxpre), c_int(ld_db), _stream()))
+
+
+def adam_clipnorm(params, grads, m, v, table, lr_group, lrs, group_enabled, T, total, clipnorm, steps, norms,
+                  beta1=0.9, beta2=0.999, eps=1e-7):
+    check(_lib.lib().detrb_adam_clipnorm(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(table), ptr(lr_group), ptr(lrs),
+                                         ptr(group_enabled), c_int(T), c_int64(total), c_float(clipnorm), c_float(beta1),
+                                         c_float(beta2), c_float(eps), ptr(steps), ptr(norms), _stream()))
+
+
+def prep_weight(master, fold, N, taps, Cin, Wf, ldf, Wd, ldd):
+    check(_lib.lib().detrb_prep_weight(ptr(master), ptr(fold), c_int(N), c_int(taps), c_int(Cin), ptr(Wf), c_int(ldf),
+                                       ptr(Wd), c_int(ldd), _stream()))
+
+
+def dropout_mask(out, M, N, drop_p, seed, site, seed_ptr=None):
+    check(_lib.lib().detrb_dropout_mask(ptr(out), c_int(M), c_int(N), c_float(drop_p), c_uint64(seed), c_uint32(site),
+                                        ptr(seed_ptr), _stream()))

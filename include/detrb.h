@@ -1,0 +1,234 @@
+/* detrb.h -- C ABI of libdetrb.so: the B200 (sm_100a) DETR train-step hot path.
+ *
+ * The reference (Visual-Behavior/detr-tensorflow) is pure Python/TensorFlow and has no
+ * FFI / plugin interface; its boundary is the Python API (get_detr_model / get_losses /
+ * hungarian_matching / setup_optimizers / training.fit).  This header is the C ABI that
+ * sits directly under our Python mirror of that API.  Each entry point names the reference
+ * computation (file:line under detr_tf/) that it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes; every pointer is a DEVICE pointer unless noted.
+ *   - the caller owns all memory; the library never allocates or frees device memory and
+ *     keeps no pointer past the call.  All work is enqueued on `stream`; no host sync, no
+ *     allocation => every call is CUDA-graph capturable.
+ *   - return value: 0 ok, <0 error (DETRB_E_*); detrb_last_error() gives a message
+ *     (thread-local, host pointer).  No C++ exception crosses the ABI.
+ *   - activations are NHWC / row-major bf16; accumulators, losses, gradients of parameters
+ *     and optimizer state are fp32; matcher indices are int64 like the reference's.
+ *   - there is no CPU fallback: detrb_check_device() fails unless the device is CC 10.x.
+ */
+#ifndef DETRB_H
+#define DETRB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *detrb_stream_t;          /* cudaStream_t */
+typedef uint16_t detrb_bf16;           /* raw bfloat16 bits */
+
+enum {
+    DETRB_OK = 0,
+    DETRB_E_BADARG = -1,
+    DETRB_E_SHAPE = -2,
+    DETRB_E_ARCH = -3,
+    DETRB_E_CUDA = -4,
+    DETRB_E_NUMERIC = -5
+};
+
+int detrb_version(void);
+const char *detrb_last_error(void);
+/* fails (DETRB_E_ARCH) unless the current device is compute capability 10.x */
+int detrb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer:  C[M,N] = epilogue( gather(A)[M,K] * W[N,K]^T )
+ * Replaces tf Conv2D+ZeroPadding2D+FrozenBatchNorm2D+ReLU(+residual) (networks/resnet_backbone.py:
+ * 20-26, 116-136; custom_layers.py:21-24), Conv2D input_proj (detr.py:44), Linear
+ * (custom_layers.py:49-50) and every tf.matmul of the transformer (transformer.py:294-347),
+ * plus their data-gradients (tape.gradient, training.py:23).
+ *
+ *   A     : NHWC tensor [batch, IH, IW, Cin] (bf16, pixel stride lda elements).  A plain matrix
+ *           [M,K] is the case batch=1, IH=1, IW=M, KH=KW=1, Cin=K.
+ *   mode 0: forward gather   iy = oy*stride - pad + kh
+ *   mode 1: transposed gather (data gradient of a strided conv; A is dy at the conv's OUTPUT
+ *           resolution IHxIW, the GEMM rows are the conv's INPUT pixels OHxOW):
+ *           t = oy + pad - kh ; valid iff t % stride == 0 ; iy = t / stride
+ *   W     : [N, K] bf16, K = KH*KW*Cin ordered (kh, kw, c); ldw = row stride.
+ *   stem  : Cin == 4 (RGB padded to 4 channels) with KW padded to 8 (7x8 taps, K = 224).
+ *   epilogue, in this order:  acc (+bias[n]) (+residual[m,n]) (relu) (*mask: (mask[m,n]>0)*mask_scale)
+ *           (sigmoid) (dropout keep/(1-p), counter-based on (m,n))  -> C bf16 and/or Cf fp32.
+ *           With drop_p > 0 the residual is the un-dropped skip path and is added AFTER the dropout.
+ *   scatter: if out_stride > 1 the GEMM row (b,oy,ox) is written to pixel (b, oy*out_stride,
+ *           ox*out_stride) of a [batch, SH, SW, N] tensor (data gradient of a 1x1 stride-s conv).
+ *   accumulate: C += result (read-modify-write in bf16) instead of C = result.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const detrb_bf16 *A;
+    const detrb_bf16 *W;
+    int M, N, K;
+    int lda, ldw;
+    int batch, IH, IW, Cin;
+    int OH, OW;
+    int KH, KW, stride, pad;
+    int mode;
+    const float *bias;
+    const detrb_bf16 *residual; int ldr;
+    const detrb_bf16 *mask; int ldm; float mask_scale;
+    int relu, sigmoid;
+    float drop_p; uint64_t seed; uint32_t site;
+    const uint64_t *seed_ptr;    /* optional device word XOR-ed into seed (lets a captured CUDA graph draw fresh masks) */
+    detrb_bf16 *C; int ldc;
+    float *Cf; int ldcf;
+    int out_stride, SH, SW;
+    int accumulate;
+} detrb_igemm_t;
+
+int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
+
+/* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)
+ * and optionally dbias[n] += rowscale[n] * sum_m dY[m,n].
+ * gather() as in detrb_igemm mode 0 (the forward conv's own gather).  Replaces the
+ * kernel/bias gradients of tape.gradient (training.py:23, optimizers.py:115). */
+typedef struct {
+    const detrb_bf16 *A; int lda;
+    const detrb_bf16 *dY; int ldy;
+    int M, N, K;
+    int batch, IH, IW, Cin;
+    int OH, OW;
+    int KH, KW, stride, pad;
+    const float *rowscale;       /* [N] or NULL */
+    float *dW; int ldw;          /* fp32 [N, K] */
+    float *dbias;                /* fp32 [N] or NULL */
+} detrb_wgrad_t;
+
+int detrb_wgrad(const detrb_wgrad_t *p, detrb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-head attention core (transformer.py:308-345): softmax(Q K^T) V per (batch, head),
+ * head h = channels [32h, 32h+32); the 32^-0.5 query scaling (:307) is applied to the scores.
+ * Dropout (p) on the probabilities (:341) is counter-based on (seed, site, b, h, q, k).
+ * Q [B, Lq, *] bf16 with row stride ldq, K/V [B, Lk, *] (ldk, ldv); O [B, Lq, H*32] (ldo).
+ * lse [B, H, Lq] fp32 = log-sum-exp of the scores (saved for the backward).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const detrb_bf16 *Q, *K, *V; int ldq, ldk, ldv;
+    detrb_bf16 *O; int ldo;
+    float *lse;
+    int B, H, Lq, Lk;
+    float scale;                 /* scores = scale * Q K^T  (head_dim^-0.5, transformer.py:307) */
+    float drop_p; uint64_t seed; uint32_t site; const uint64_t *seed_ptr;
+} detrb_attn_fwd_t;
+int detrb_attn_fwd(const detrb_attn_fwd_t *p, detrb_stream_t stream);
+
+typedef struct {
+    const detrb_bf16 *Q, *K, *V, *O, *dO; int ldq, ldk, ldv, ldo, lddo;
+    const float *lse;
+    float *delta;                /* scratch [B, H, Lq] fp32 */
+    detrb_bf16 *dQ, *dK, *dV; int lddq, lddk, lddv;
+    int B, H, Lq, Lk;
+    float scale;
+    float drop_p; uint64_t seed; uint32_t site; const uint64_t *seed_ptr;
+} detrb_attn_bwd_t;
+int detrb_attn_bwd(const detrb_attn_bwd_t *p, detrb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNormalization(epsilon=1e-5) over the last dim d == 256 (transformer.py:151-152,200-202,22).
+ * fwd:  y = LN(x)*gamma+beta ; optional y2 = y + pos[(row % S)] (the `src + pos_encoding`
+ *       of transformer.py:161,209,217) ; saves mean/rstd.
+ * bwd:  dx = LN'(dy [+ dy2]) ; optional dx_drop = dx * keep(m,n)/(1-p) (gradient entering the
+ *       dropout'ed sub-layer branch, transformer.py:169,176) ; dgamma/dbeta fp32 atomics.
+ * ------------------------------------------------------------------------------------------ */
+int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, const float *beta,
+                        detrb_bf16 *y, detrb_bf16 *y2, const detrb_bf16 *pos, int S,
+                        float *mean, float *rstd, int M, detrb_stream_t stream);
+int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, const detrb_bf16 *x,
+                        const float *gamma, const float *mean, const float *rstd,
+                        detrb_bf16 *dx, detrb_bf16 *dx_drop, float drop_p, uint64_t seed, uint32_t site,
+                        const uint64_t *seed_ptr, float *dgamma, float *dbeta, int M, detrb_stream_t stream);
+
+/* elementwise helpers (bf16, n multiple of 8) */
+/* out[r, :] = x[r, :] + pos[r % S, :]          (transformer.py:161: source + pos_encoding) */
+int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *out,
+                       int M, int S, int d, detrb_stream_t stream);
+/* out = a + b (b may be NULL -> copy) */
+int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *out, int64_t n, detrb_stream_t stream);
+/* fp32 NHWC3 image -> bf16 NHWC4 (4th channel 0): the layout the stem kernel gathers from */
+int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_stream_t stream);
+/* fp32 -> bf16 */
+int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream);
+/* column sums: out[n] += scale[n]* sum_m x[m,n]  (bias gradients) */
+int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const float *scale, float *out,
+                 detrb_stream_t stream);
+
+/* ZeroPadding2D(1)+MaxPool2D(3,2,'valid') (resnet_backbone.py:16-17,25-26), NHWC, C%8==0.
+ * fwd stores the argmax tap (0..8) per output element; bwd routes dy to it and applies the
+ * stem ReLU mask (x > 0). */
+int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax,
+                      int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream);
+int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
+                      int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hungarian matcher (loss/hungarian_matching.py:163-203 + :27-46 -> scipy LSAP) for P = L*B
+ * independent problems (L decoder layers x B images), entirely on device.
+ *   logits [P, Q, C] fp32 (row stride ldl), boxes [P, Q, 4] fp32 cxcywh, targets in the padded
+ *   wire format of data/processing.py:35-55: t_bbox [B,100,4] f32 (row 0 = [n,0,0,0]),
+ *   t_class [B,100,1] i64.  Problem p uses image p % B.
+ * out: p_indices [P,Q] i64 (ascending query ids, first n valid, rest -1), t_indices [P,Q] i64
+ *      (target matched to p_indices[k]), p_selector [P,Q] u8, match [P,Q] i32 (target of query q
+ *      or -1), cost [P, Q, 100] fp32 (optional, may be NULL), status [P] i32 (0 ok, 1 NaN/-inf cost).
+ * Bit-exact vs scipy.optimize.linear_sum_assignment on the same fp32 cost matrix, ties included.
+ * ------------------------------------------------------------------------------------------ */
+int detrb_matcher(const float *logits, int ldl, const float *boxes,
+                  const float *t_bbox, const int64_t *t_class,
+                  int P, int B, int Q, int C,
+                  float fcost_class, float fcost_bbox, float fcost_giou,
+                  int64_t *p_indices, int64_t *t_indices, uint8_t *p_selector, int32_t *match,
+                  float *cost, int32_t *status, detrb_stream_t stream);
+
+/* Set criterion (loss/loss.py:37-179) forward + analytic backward for L layers at once.
+ *   sums [L, 8] fp32 scratch (zeroed by the call); losses [L, 6] fp32 in the order
+ *   label_cost, true_neg, true_pos, pos_accuracy, giou_loss, l1_loss; total [1] fp32 =
+ *   sum_l (1*label_cost + 2*giou_loss + 5*l1_loss) * loss_scale   (loss.py:6-19, training.py:20).
+ *   normalisers: device float[2] = {n_matched, sum_w}, the batch-level normalisers (loss.py:66-67, 82, 94);
+ *   pass the GLOBAL values under data parallelism; NULL: computed from this batch's targets.
+ *   d_logits bf16 [P*Q, ld_dl] (cols >= C zeroed), d_boxpre bf16 [P*Q, ld_db]: gradient wrt the
+ *   pre-sigmoid box head output (boxes = sigmoid(pre), detr.py:188), cols >= 4 zeroed.  NULL -> fwd only. */
+int detrb_set_loss(const float *logits, int ldl, const float *boxes,
+                   const float *t_bbox, const int64_t *t_class, const int32_t *match,
+                   int L, int B, int Q, int C, int background_class,
+                   const float *normalisers, float loss_scale,
+                   float *sums, float *losses, float *total,
+                   detrb_bf16 *d_logits, int ld_dl, detrb_bf16 *d_boxpre, int ld_db,
+                   detrb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer (optimizers.py:86-88,137-163): Keras Adam(beta1=.9, beta2=.999, eps=1e-7) with
+ * PER-VARIABLE clipnorm, over a flat fp32 parameter arena described by a tensor table.
+ *   table: T rows of {offset, numel} (int64 pairs, device); lr_group [T] i32 index into lrs [G] (device, fp32)
+ *   so that learning rates can change without re-capturing a graph (training_config.py:66-68).
+ *   group_enabled [8] u8 (config.train_<group>, optimizers.py:148), steps [8] i32: per-group Adam iteration
+ *   counters (device), incremented by the call for enabled groups.  norms [T] fp32 scratch.
+ * ------------------------------------------------------------------------------------------ */
+int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v,
+                        const int64_t *table, const int32_t *lr_group, const float *lrs,
+                        const uint8_t *group_enabled, int T, int64_t total,
+                        float clipnorm, float beta1, float beta2, float eps,
+                        int32_t *steps, float *norms, detrb_stream_t stream);
+
+/* master fp32 weight [N, taps, Cin] (+ optional per-row fold[n]) -> bf16 forward copy Wf [N, ldf]
+ * (K = taps*Cin, zero padded to ldf) and optional data-gradient copy Wd [Cin, taps, ldd] (cols>=N zero). */
+int detrb_prep_weight(const float *master, const float *fold, int N, int taps, int Cin,
+                      detrb_bf16 *Wf, int ldf, detrb_bf16 *Wd, int ldd, detrb_stream_t stream);
+
+/* debug/test helper: writes the dropout keep-mask (0/1 bytes) the kernels use for an [M,N] site */
+int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
+                       const uint64_t *seed_ptr, detrb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -390,14 +390,25 @@ def hungarian_matching(t_bbox, t_class, p_bbox, p_class, fcost_class=1, fcost_bb
 
 
 def get_detr_losses(pred_logits, pred_boxes, t_bbox, t_class, background_class, suffix="",
-                    return_indices=False):
-    """loss.py:98-179 with loss_labels :37-69 and loss_boxes :72-96 (diag of the NxN GIoU == per-pair)."""
+                    return_indices=False, match_override=None):
+    """loss.py:98-179 with loss_labels :37-69 and loss_boxes :72-96 (diag of the NxN GIoU == per-pair).
+    match_override [B,Q] (target index per query, -1 = unmatched) replaces the Hungarian step: used by tests to
+    compare gradients under an identical assignment (assignments of near-tied random-init predictions flip
+    under bf16 noise, which says nothing about the gradient arithmetic)."""
     B, Q, C = pred_logits.shape
     t_idx, p_idx, tb_all, tc_all, p_sel_all = [], [], [], [], []
     t_off = 0
     for b in range(B):
-        ti, pi, _, psel, tb, tc = hungarian_matching(t_bbox[b], t_class[b], pred_boxes[b].detach(),
-                                                      pred_logits[b].detach())
+        if match_override is not None:
+            mo = match_override[b].long()
+            n = int(t_bbox[b][0, 0])
+            pi = torch.nonzero(mo >= 0).squeeze(-1)
+            ti = mo[pi]
+            psel = mo >= 0
+            tb, tc = t_bbox[b][1:1 + n], t_class[b][1:1 + n].reshape(-1).long()
+        else:
+            ti, pi, _, psel, tb, tc = hungarian_matching(t_bbox[b], t_class[b], pred_boxes[b].detach(),
+                                                          pred_logits[b].detach())
         t_idx.append(ti + t_off)
         p_idx.append(pi + b * Q)
         tb_all.append(tb)
@@ -463,13 +474,15 @@ def get_total_loss(losses):
     return total
 
 
-def get_losses(m_outputs, t_bbox, t_class, background_class):
-    """loss.py:22-34"""
+def get_losses(m_outputs, t_bbox, t_class, background_class, match_override=None):
+    """loss.py:22-34.  match_override: optional [L,B,Q] tensor (layer order 0..L-1, main output = last)."""
+    naux = len(m_outputs.get("aux", []))
     losses = get_detr_losses(m_outputs["pred_logits"], m_outputs["pred_boxes"], t_bbox, t_class,
-                             background_class)
+                             background_class, match_override=None if match_override is None else match_override[naux])
     for a, aux in enumerate(m_outputs.get("aux", [])):
         losses.update(get_detr_losses(aux["pred_logits"], aux["pred_boxes"], t_bbox, t_class,
-                                      background_class, suffix=f"_{a}"))
+                                      background_class, suffix=f"_{a}",
+                                      match_override=None if match_override is None else match_override[a]))
     return get_total_loss(losses), losses
 
 
@@ -536,12 +549,13 @@ def adam_clipnorm_step(param, grad, m, v, step, lr, clipnorm=0.1, beta1=0.9, bet
 
 
 def train_step(P, images, t_bbox, t_class, background_class=91, backbone="resnet50",
-               num_encoder_layers=6, num_decoder_layers=6, gradient_aggregate=1, training=False):
+               num_encoder_layers=6, num_decoder_layers=6, gradient_aggregate=1, training=False,
+               match_override=None):
     """training.py:9-25: fwd -> get_losses -> /gradient_aggregate -> grads for every trainable var."""
     names = [n for n in P if param_group(n) is not None]
     Pg = OrderedDict((n, (p.clone().requires_grad_(True) if n in names else p)) for n, p in P.items())
     out = detr_forward(Pg, images, backbone, num_encoder_layers, num_decoder_layers, training=training)
-    total, log = get_losses(out, t_bbox, t_class, background_class)
+    total, log = get_losses(out, t_bbox, t_class, background_class, match_override)
     total = total / gradient_aggregate
     grads = torch.autograd.grad(total, [Pg[n] for n in names], allow_unused=True)
     return out, total.detach(), {k: v.detach() for k, v in log.items()}, dict(zip(names, grads))

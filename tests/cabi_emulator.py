@@ -1,0 +1,522 @@
+"""A pure-PyTorch (CPU) stand-in for libdetrb.so's C ABI -- TEST INFRASTRUCTURE ONLY.
+
+Purpose: exercise the Python orchestration of the engine (buffer plumbing, layer order, hand-written
+backward chain, parameter layouts, optimizer glue) against the oracle on a machine without a GPU.  Each
+function re-implements the *documented semantics* of the matching entry point of include/detrb.h on raw
+host pointers (bf16 storage, fp32 accumulate).  It says nothing about the CUDA kernels themselves -- those
+are checked against the oracle on a B200 by the `-m gpu` tests.  The product never imports this file.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from detr_tensorflow_b200 import _lib
+
+F32 = torch.float32
+
+
+class _Act:
+    """storage dtype standing in for the device's bf16 tensors; tests may switch it to float32 (together with
+    engine.BF16) to check the orchestration without rounding noise"""
+    dtype = torch.bfloat16
+
+
+def set_act_dtype(dt):
+    _Act.dtype = dt
+    import detr_tensorflow_b200.engine as E
+    E.BF16 = dt
+
+_ITEM = {torch.bfloat16: 2, F32: 4, torch.int64: 8, torch.int32: 4, torch.uint8: 1, torch.float64: 8}
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, ctypes.c_void_p):
+        return p.value or 0
+    if isinstance(p, int):
+        return p
+    return getattr(p, "value", 0) or 0
+
+
+def T(p, dtype, count):
+    """1-D tensor view of `count` elements of `dtype` at raw host address p (None if NULL)."""
+    a = _addr(p)
+    if a == 0:
+        return None
+    buf = (ctypes.c_uint8 * (count * _ITEM[dtype])).from_address(a)
+    return torch.frombuffer(buf, dtype=dtype, count=count)
+
+
+def M2(p, dtype, rows, cols, ld):
+    """[rows, cols] strided view with row stride ld"""
+    t = T(p, dtype, (rows - 1) * ld + cols)
+    return None if t is None else torch.as_strided(t, (rows, cols), (ld, 1))
+
+
+def _v(x):
+    return x.value if hasattr(x, "value") else x
+
+
+# ---------------------------------------------------------------- dropout hash (mirrors csrc/common.cuh)
+def _lowbias32(x):
+    x = x.astype(np.uint64)
+    x ^= x >> 16
+    x = (x * 0x7feb352d) & 0xffffffff
+    x ^= x >> 15
+    x = (x * 0x846ca68b) & 0xffffffff
+    x ^= x >> 16
+    return x
+
+
+def keep_mask(rows, cols, drop_p, seed, site, seed_ptr=None):
+    """bool [len(rows), len(cols)] keep mask for element (row, col)"""
+    seed = int(seed)
+    if _addr(seed_ptr):
+        seed ^= int(T(seed_ptr, torch.int64, 1)[0]) & 0xffffffffffffffff
+    r = np.asarray(rows, dtype=np.uint64)[:, None]
+    c = np.asarray(cols, dtype=np.uint64)[None, :]
+    h = _lowbias32((r ^ (seed & 0xffffffff) ^ ((site * 0x9E3779B9) & 0xffffffff)) & 0xffffffff)
+    h = _lowbias32((h ^ (c >> 1) ^ (seed >> 32)) & 0xffffffff)
+    h = _lowbias32((h + 0x6a09e667 + site) & 0xffffffff)
+    bits = np.where((c & 1) == 1, h >> 16, h & 0xffff)
+    thresh = int(drop_p * 65536.0 + 0.5)
+    return torch.from_numpy(bits >= thresh)
+
+
+# ---------------------------------------------------------------- gather
+def _gather(p_A, lda, M, K, batch, IH, IW, Cin, OH, OW, KH, KW, stride, pad, mode, stem_real_kw=None):
+    A = M2(p_A, _Act.dtype, batch * IH * IW, Cin, lda).to(F32)
+    m = torch.arange(M)
+    b = m // (OH * OW)
+    rem = m % (OH * OW)
+    oy, ox = rem // OW, rem % OW
+    cols = []
+    for kh in range(KH):
+        for kw in range(KW):
+            if mode == 0:
+                iy, ix = oy * stride - pad + kh, ox * stride - pad + kw
+                ok = torch.ones(M, dtype=torch.bool)
+            else:
+                ty, tx = oy + pad - kh, ox + pad - kw
+                ok = (ty >= 0) & (tx >= 0) & (ty % stride == 0) & (tx % stride == 0)
+                iy, ix = torch.div(ty, stride, rounding_mode="floor"), torch.div(tx, stride, rounding_mode="floor")
+            ok = ok & (iy >= 0) & (iy < IH) & (ix >= 0) & (ix < IW)
+            if stem_real_kw is not None and kw >= stem_real_kw:
+                ok = ok & False
+            idx = (b * IH + iy.clamp(0, IH - 1)) * IW + ix.clamp(0, IW - 1)
+            cols.append(A[idx] * ok[:, None].to(F32))
+    out = torch.cat(cols, dim=1)
+    assert out.shape[1] == K, (out.shape, K)
+    return out
+
+
+class FakeLib:
+    def __init__(self):
+        self.err = b""
+        self._harness = None
+
+    # -- plumbing
+    def detrb_version(self):
+        return 100
+
+    def detrb_last_error(self):
+        return self.err
+
+    def detrb_check_device(self):
+        return 0
+
+    def harness(self):
+        if self._harness is None:
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            so = os.path.join(root, "tests", "_harness_build", "libharness.so")
+            os.makedirs(os.path.dirname(so), exist_ok=True)
+            subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                                   os.path.join(root, "tests", "host_harness.c"), "-lm"])
+            self._harness = ctypes.CDLL(so)
+        return self._harness
+
+    # -- GEMM / conv
+    def detrb_igemm(self, pref, stream):
+        p = pref._obj
+        stem = p.Cin == 4
+        Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, p.mode)
+        W = M2(p.W, _Act.dtype, p.N, p.K, p.ldw).to(F32)
+        v = Ag @ W.t()
+        out_stride = max(p.out_stride, 1)
+        m = torch.arange(p.M)
+        if out_stride > 1:
+            b = m // (p.OH * p.OW)
+            rem = m % (p.OH * p.OW)
+            orow = (b * p.SH + (rem // p.OW) * out_stride) * p.SW + (rem % p.OW) * out_stride
+            nrows = p.batch * p.SH * p.SW
+        else:
+            orow, nrows = m, p.M
+        if _addr(p.bias):
+            v = v + T(p.bias, F32, p.N)
+        res = M2(p.residual, _Act.dtype, nrows, p.N, p.ldr)[orow].to(F32) if _addr(p.residual) else None
+        if res is not None and not p.drop_p > 0:
+            v = v + res
+        if p.relu:
+            v = F.relu(v)
+        if _addr(p.mask):
+            mk = M2(p.mask, _Act.dtype, nrows, p.N, p.ldm)[orow].to(F32)
+            v = torch.where(mk > 0, v * p.mask_scale, torch.zeros_like(v))
+        if p.sigmoid:
+            v = torch.sigmoid(v)
+        if p.drop_p > 0:
+            keep = keep_mask(range(p.M), range(p.N), p.drop_p, p.seed, p.site, p.seed_ptr)
+            v = torch.where(keep, v / (1 - p.drop_p), torch.zeros_like(v))
+            if res is not None:
+                v = v + res
+        if _addr(p.C):
+            C = M2(p.C, _Act.dtype, nrows, p.N, p.ldc)
+            if p.accumulate:
+                v = v + C[orow].to(F32)
+            C[orow] = v.to(_Act.dtype)
+        if _addr(p.Cf):
+            M2(p.Cf, F32, nrows, p.N, p.ldcf)[orow] = v
+        return 0
+
+    def detrb_wgrad(self, pref, stream):
+        p = pref._obj
+        stem = p.Cin == 4
+        Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, 0,
+                     stem_real_kw=7 if stem else None)
+        dY = M2(p.dY, _Act.dtype, p.M, p.N, p.ldy).to(F32)
+        g = dY.t() @ Ag
+        sc = T(p.rowscale, F32, p.N) if _addr(p.rowscale) else None
+        if sc is not None:
+            g = g * sc[:, None]
+        M2(p.dW, F32, p.N, p.K, p.ldw).add_(g)
+        if _addr(p.dbias):
+            s = dY.sum(0)
+            T(p.dbias, F32, p.N).add_(s * sc if sc is not None else s)
+        return 0
+
+    # -- attention
+    @staticmethod
+    def _attn_core(Q, K, V, p, B, H, Lq, Lk):
+        """Q [B,Lq,H*32] etc float32 -> O, lse; differentiable"""
+        q = Q.view(B, Lq, H, 32).transpose(1, 2)
+        k = K.view(B, Lk, H, 32).transpose(1, 2)
+        v = V.view(B, Lk, H, 32).transpose(1, 2)
+        s = (q @ k.transpose(-1, -2)) * p.scale
+        lse = torch.logsumexp(s, -1)
+        w = torch.softmax(s, -1)
+        if p.drop_p > 0:
+            keep = keep_mask(range(B * H * Lq), range(Lk), p.drop_p, p.seed, p.site, p.seed_ptr).view(B, H, Lq, Lk)
+            w = torch.where(keep, w / (1 - p.drop_p), torch.zeros_like(w))
+        o = (w.to(_Act.dtype).to(F32) @ v).transpose(1, 2).reshape(B, Lq, H * 32)
+        return o, lse
+
+    def detrb_attn_fwd(self, pref, stream):
+        p = pref._obj
+        B, H, Lq, Lk = p.B, p.H, p.Lq, p.Lk
+        Q = M2(p.Q, _Act.dtype, B * Lq, H * 32, p.ldq).to(F32).view(B, Lq, -1)
+        K = M2(p.K, _Act.dtype, B * Lk, H * 32, p.ldk).to(F32).view(B, Lk, -1)
+        V = M2(p.V, _Act.dtype, B * Lk, H * 32, p.ldv).to(F32).view(B, Lk, -1)
+        o, lse = self._attn_core(Q, K, V, p, B, H, Lq, Lk)
+        M2(p.O, _Act.dtype, B * Lq, H * 32, p.ldo)[:] = o.reshape(B * Lq, -1).to(_Act.dtype)
+        if _addr(p.lse):
+            T(p.lse, F32, B * H * Lq)[:] = lse.reshape(-1)
+        return 0
+
+    def detrb_attn_bwd(self, pref, stream):
+        p = pref._obj
+        B, H, Lq, Lk = p.B, p.H, p.Lq, p.Lk
+        Q = M2(p.Q, _Act.dtype, B * Lq, H * 32, p.ldq).to(F32).view(B, Lq, -1).clone().requires_grad_(True)
+        K = M2(p.K, _Act.dtype, B * Lk, H * 32, p.ldk).to(F32).view(B, Lk, -1).clone().requires_grad_(True)
+        V = M2(p.V, _Act.dtype, B * Lk, H * 32, p.ldv).to(F32).view(B, Lk, -1).clone().requires_grad_(True)
+        dO = M2(p.dO, _Act.dtype, B * Lq, H * 32, p.lddo).to(F32).view(B, Lq, -1)
+        o, _ = self._attn_core(Q, K, V, p, B, H, Lq, Lk)
+        gq, gk, gv = torch.autograd.grad(o, [Q, K, V], dO)
+        M2(p.dQ, _Act.dtype, B * Lq, H * 32, p.lddq)[:] = gq.reshape(B * Lq, -1).to(_Act.dtype)
+        M2(p.dK, _Act.dtype, B * Lk, H * 32, p.lddk)[:] = gk.reshape(B * Lk, -1).to(_Act.dtype)
+        M2(p.dV, _Act.dtype, B * Lk, H * 32, p.lddv)[:] = gv.reshape(B * Lk, -1).to(_Act.dtype)
+        return 0
+
+    # -- layer norm
+    def detrb_layernorm_fwd(self, x, gamma, beta, y, y2, pos, S, mean, rstd, M, stream):
+        S, M = _v(S), _v(M)
+        xv = M2(x, _Act.dtype, M, 256, 256).to(F32)
+        mu = xv.mean(-1, keepdim=True)
+        var = ((xv - mu) ** 2).mean(-1, keepdim=True)
+        rs = torch.rsqrt(var + 1e-5)
+        o = ((xv - mu) * rs * T(gamma, F32, 256) + T(beta, F32, 256)).to(_Act.dtype)
+        M2(y, _Act.dtype, M, 256, 256)[:] = o
+        if _addr(y2):
+            pv = M2(pos, _Act.dtype, S, 256, 256).to(F32)
+            M2(y2, _Act.dtype, M, 256, 256)[:] = (o.to(F32) + pv[torch.arange(M) % S]).to(_Act.dtype)
+        if _addr(mean):
+            T(mean, F32, M)[:] = mu[:, 0]
+        if _addr(rstd):
+            T(rstd, F32, M)[:] = rs[:, 0]
+        return 0
+
+    def detrb_layernorm_bwd(self, dy, dy2, x, gamma, mean, rstd, dx, dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta,
+                            M, stream):
+        M, drop_p, seed, site = _v(M), _v(drop_p), _v(seed), _v(site)
+        d = M2(dy, _Act.dtype, M, 256, 256).to(F32)
+        if _addr(dy2):
+            d = d + M2(dy2, _Act.dtype, M, 256, 256).to(F32)
+        xv = M2(x, _Act.dtype, M, 256, 256).to(F32)
+        mu, rs = T(mean, F32, M)[:, None], T(rstd, F32, M)[:, None]
+        g = T(gamma, F32, 256)
+        xh = (xv - mu) * rs
+        gv = d * g
+        o = rs * (gv - gv.mean(-1, keepdim=True) - xh * (gv * xh).mean(-1, keepdim=True))
+        ob = o.to(_Act.dtype)
+        M2(dx, _Act.dtype, M, 256, 256)[:] = ob
+        if _addr(dx_drop):
+            od = ob.to(F32)
+            if drop_p > 0:
+                keep = keep_mask(range(M), range(256), drop_p, seed, site, seed_ptr)
+                od = torch.where(keep, od / (1 - drop_p), torch.zeros_like(od))
+            M2(dx_drop, _Act.dtype, M, 256, 256)[:] = od.to(_Act.dtype)
+        if _addr(dgamma):
+            T(dgamma, F32, 256).add_((d * xh).sum(0))
+            T(dbeta, F32, 256).add_(d.sum(0))
+        return 0
+
+    # -- elementwise
+    def detrb_add_rowbcast(self, x, pos, out, M, S, d, stream):
+        M, S, d = _v(M), _v(S), _v(d)
+        xv = M2(x, _Act.dtype, M, d, d).to(F32)
+        pv = M2(pos, _Act.dtype, S, d, d).to(F32)
+        M2(out, _Act.dtype, M, d, d)[:] = (xv + pv[torch.arange(M) % S]).to(_Act.dtype)
+        return 0
+
+    def detrb_add(self, a, b, out, n, stream):
+        n = _v(n)
+        v = T(a, _Act.dtype, n).to(F32)
+        if _addr(b):
+            v = v + T(b, _Act.dtype, n).to(F32)
+        T(out, _Act.dtype, n)[:] = v.to(_Act.dtype)
+        return 0
+
+    def detrb_image_to_nhwc4(self, img, out, npix, stream):
+        npix = _v(npix)
+        o = M2(out, _Act.dtype, npix, 4, 4)
+        o[:, :3] = M2(img, F32, npix, 3, 3).to(_Act.dtype)
+        o[:, 3] = 0
+        return 0
+
+    def detrb_f32_to_bf16(self, x, y, n, stream):
+        n = _v(n)
+        T(y, _Act.dtype, n)[:] = T(x, F32, n).to(_Act.dtype)
+        return 0
+
+    def detrb_colsum(self, x, ldx, M, N, scale, out, stream):
+        ldx, M, N = _v(ldx), _v(M), _v(N)
+        s = M2(x, _Act.dtype, M, N, ldx).to(F32).sum(0)
+        if _addr(scale):
+            s = s * T(scale, F32, N)
+        T(out, F32, N).add_(s)
+        return 0
+
+    def detrb_maxpool_fwd(self, x, y, argmax, B, IH, IW, C, OH, OW, stream):
+        B, IH, IW, C, OH, OW = map(_v, (B, IH, IW, C, OH, OW))
+        xv = T(x, _Act.dtype, B * IH * IW * C).to(F32).view(B, IH, IW, C)
+        best = torch.full((B, OH, OW, C), -float("inf"))
+        arg = torch.zeros((B, OH, OW, C), dtype=torch.uint8)
+        oy, ox = torch.arange(OH), torch.arange(OW)
+        for kh in range(3):
+            for kw in range(3):
+                iy, ix = oy * 2 - 1 + kh, ox * 2 - 1 + kw
+                oky, okx = (iy >= 0) & (iy < IH), (ix >= 0) & (ix < IW)
+                v = xv[:, iy.clamp(0, IH - 1)][:, :, ix.clamp(0, IW - 1)]
+                ok = (oky[:, None] & okx[None, :])[None, :, :, None]
+                v = torch.where(ok, v, torch.full_like(v, -float("inf")))
+                upd = v > best
+                best = torch.where(upd, v, best)
+                arg = torch.where(upd, torch.full_like(arg, kh * 3 + kw), arg)
+        T(y, _Act.dtype, B * OH * OW * C)[:] = best.reshape(-1).to(_Act.dtype)
+        T(argmax, torch.uint8, B * OH * OW * C)[:] = arg.reshape(-1)
+        return 0
+
+    def detrb_maxpool_bwd(self, dy, argmax, x, dx, B, IH, IW, C, OH, OW, stream):
+        B, IH, IW, C, OH, OW = map(_v, (B, IH, IW, C, OH, OW))
+        d = T(dy, _Act.dtype, B * OH * OW * C).to(F32).view(B, OH, OW, C)
+        arg = T(argmax, torch.uint8, B * OH * OW * C).view(B, OH, OW, C)
+        xv = T(x, _Act.dtype, B * IH * IW * C).to(F32).view(B, IH, IW, C)
+        out = torch.zeros(B, IH, IW, C)
+        for oy in range(OH):
+            for ox in range(OW):
+                for kh in range(3):
+                    for kw in range(3):
+                        iy, ix = oy * 2 - 1 + kh, ox * 2 - 1 + kw
+                        if 0 <= iy < IH and 0 <= ix < IW:
+                            out[:, iy, ix] += d[:, oy, ox] * (arg[:, oy, ox] == kh * 3 + kw).to(F32)
+        out = out * (xv > 0).to(F32)
+        T(dx, _Act.dtype, B * IH * IW * C)[:] = out.reshape(-1).to(_Act.dtype)
+        return 0
+
+    # -- matcher / loss
+    def detrb_matcher(self, logits, ldl, boxes, t_bbox, t_class, P, B, Q, C, fc, fb, fg, p_indices, t_indices, p_selector,
+                      match, cost, status, stream):
+        ldl, P, B, Q, C, fc, fb, fg = map(_v, (ldl, P, B, Q, C, fc, fb, fg))
+        h = self.harness()
+        lg = M2(logits, F32, P * Q, C, ldl).view(P, Q, C)
+        bx = T(boxes, F32, P * Q * 4).view(P, Q, 4)
+        tb = T(t_bbox, F32, B * 400).view(B, 100, 4)
+        tc = T(t_class, torch.int64, B * 100).view(B, 100)
+        pi = T(p_indices, torch.int64, P * Q).view(P, Q)
+        ti = T(t_indices, torch.int64, P * Q).view(P, Q)
+        ps = T(p_selector, torch.uint8, P * Q).view(P, Q)
+        mt = T(match, torch.int32, P * Q).view(P, Q)
+        st = T(status, torch.int32, P)
+        co = T(cost, F32, P * Q * 100).view(P, Q, 100) if _addr(cost) else None
+        for p in range(P):
+            b = p % B
+            n = int(tb[b, 0, 0])
+            probs = torch.softmax(lg[p], -1).contiguous().numpy()
+            pb = bx[p].contiguous().numpy()
+            tbn = tb[b, 1:1 + n].contiguous().numpy()
+            tcn = tc[b, 1:1 + n].contiguous().numpy()
+            c = np.zeros((Q, max(n, 1)), np.float32)
+            if n > 0:
+                c = np.zeros((Q, n), np.float32)
+                h.h_cost_matrix(pb.ctypes.data_as(ctypes.c_void_p), probs.ctypes.data_as(ctypes.c_void_p), Q, C,
+                                tbn.ctypes.data_as(ctypes.c_void_p), tcn.ctypes.data_as(ctypes.c_void_p), n,
+                                ctypes.c_float(fc), ctypes.c_float(fb), ctypes.c_float(fg), c.ctypes.data_as(ctypes.c_void_p))
+            if co is not None and n > 0:
+                co[p, :, :n] = torch.from_numpy(c)
+            r4c = np.full(Q, -1, np.int32)
+            rc = 0
+            if n > 0:
+                costT = np.ascontiguousarray(c.T)
+                rc = h.lsap_warp_model(costT.ctypes.data_as(ctypes.c_void_p), n, Q, r4c.ctypes.data_as(ctypes.c_void_p))
+            st[p] = rc
+            mt[p] = torch.from_numpy(r4c)
+            ps[p] = torch.from_numpy((r4c >= 0).astype(np.uint8))
+            qs = np.nonzero(r4c >= 0)[0]
+            pi[p] = -1
+            ti[p] = -1
+            pi[p, :len(qs)] = torch.from_numpy(qs.astype(np.int64))
+            ti[p, :len(qs)] = torch.from_numpy(r4c[qs].astype(np.int64))
+        return 0
+
+    def detrb_set_loss(self, logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, bg, normalisers, loss_scale, sums, losses,
+                       total, d_logits, ld_dl, d_boxpre, ld_db, stream):
+        ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db = map(_v, (ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db))
+        lg = M2(logits, F32, L * B * Q, C, ldl).clone().view(L, B, Q, C).requires_grad_(True)
+        bx = T(boxes, F32, L * B * Q * 4).clone().view(L, B, Q, 4).requires_grad_(True)
+        tb = T(t_bbox, F32, B * 400).view(B, 100, 4)
+        tc = T(t_class, torch.int64, B * 100).view(B, 100)
+        mt = T(match, torch.int32, L * B * Q).view(L, B, Q).long()
+        ns = tb[:, 0, 0].clamp(0, 99)
+        if _addr(normalisers):
+            nrm = T(normalisers, F32, 2)
+            n_matched, sum_w = float(nrm[0]), float(nrm[1])
+        else:
+            n_matched = float(ns.sum())
+            sum_w = 0.1 * (B * Q - n_matched) + n_matched
+        out = T(losses, F32, L * 6).view(L, 6)
+        tot = 0
+        for l in range(L):
+            m = mt[l]
+            matched = m >= 0
+            cls = torch.where(matched, torch.gather(tc, 1, (m.clamp(min=0) + 1)), torch.full_like(m, bg))
+            w = torch.where(matched, torch.ones(B, Q), torch.full((B, Q), 0.1))
+            ce = F.cross_entropy(lg[l].reshape(B * Q, C), cls.reshape(-1), reduction="none").view(B, Q)
+            label = (ce * w).sum() / sum_w
+            am = lg[l].argmax(-1)
+            tbm = torch.gather(tb, 1, (m.clamp(min=0) + 1)[..., None].expand(B, Q, 4))
+            pbm = bx[l]
+            l1 = ((pbm - tbm).abs().sum(-1) * matched).sum() / n_matched
+
+            def xyxy(b_):
+                return torch.cat([b_[..., :2] - b_[..., 2:] / 2, b_[..., :2] + b_[..., 2:] / 2], -1).clamp(0, 1)
+            pa, ta = xyxy(pbm), xyxy(tbm)
+            inter = (torch.minimum(pa[..., 2:], ta[..., 2:]) - torch.maximum(pa[..., :2], ta[..., :2])).clamp(min=0)
+            inter = inter[..., 0] * inter[..., 1]
+            ap = (pa[..., 2] - pa[..., 0]) * (pa[..., 3] - pa[..., 1])
+            at = (ta[..., 2] - ta[..., 0]) * (ta[..., 3] - ta[..., 1])
+            uni = ap + at - inter
+            cwh = (torch.maximum(pa[..., 2:], ta[..., 2:]) - torch.minimum(pa[..., :2], ta[..., :2])).clamp(min=0)
+            area = cwh[..., 0] * cwh[..., 1]
+            giou = inter / uni - (area - uni) / area
+            gl = torch.where(matched, 1 - giou, torch.zeros_like(giou)).sum() / n_matched
+            out[l, 0] = label.detach()
+            out[l, 1] = ((am == bg) & ~matched).sum() / (~matched).sum()
+            out[l, 2] = ((am != bg) & matched).sum() / matched.sum()
+            out[l, 3] = ((am == cls) & matched).sum() / matched.sum()
+            out[l, 4] = gl.detach()
+            out[l, 5] = l1.detach()
+            tot = tot + label + 2 * gl + 5 * l1
+        tot = tot * loss_scale
+        T(total, F32, 1)[0] = tot.detach()
+        if _addr(d_logits):
+            gl_, gb_ = torch.autograd.grad(tot, [lg, bx])
+            dl = M2(d_logits, _Act.dtype, L * B * Q, ld_dl, ld_dl)
+            dl.zero_()
+            dl[:, :C] = gl_.reshape(-1, C).to(_Act.dtype)
+            db = M2(d_boxpre, _Act.dtype, L * B * Q, ld_db, ld_db)
+            db.zero_()
+            bxd = bx.detach()
+            db[:, :4] = (gb_ * bxd * (1 - bxd)).reshape(-1, 4).to(_Act.dtype)
+        return 0
+
+    # -- optimizer
+    def detrb_adam_clipnorm(self, params, grads, m, v, table, lr_group, lrs, enabled, Tn, total, clipnorm, beta1, beta2, eps,
+                            steps, norms, stream):
+        Tn, total, clipnorm, beta1, beta2, eps = map(_v, (Tn, total, clipnorm, beta1, beta2, eps))
+        P_, G_, M_, V_ = (T(x, F32, total) for x in (params, grads, m, v))
+        tab = T(table, torch.int64, 2 * Tn).view(Tn, 2)
+        grp = T(lr_group, torch.int32, Tn)
+        lr = T(lrs, F32, 8)
+        en = T(enabled, torch.uint8, 8)
+        st = T(steps, torch.int32, 8)
+        nr = T(norms, F32, Tn)
+        st += en.to(torch.int32)
+        for t in range(Tn):
+            o, n = int(tab[t, 0]), int(tab[t, 1])
+            g = G_[o:o + n]
+            nr[t] = (g * g).sum()
+            k = int(grp[t])
+            if not en[k]:
+                continue
+            norm = float(nr[t].sqrt())
+            g = g * (clipnorm / norm) if (clipnorm > 0 and norm > clipnorm) else g
+            step = float(st[k])
+            M_[o:o + n] = beta1 * M_[o:o + n] + (1 - beta1) * g
+            V_[o:o + n] = beta2 * V_[o:o + n] + (1 - beta2) * g * g
+            lr_t = float(lr[k]) * np.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
+            P_[o:o + n] -= lr_t * M_[o:o + n] / (V_[o:o + n].sqrt() + eps)
+        return 0
+
+    def detrb_prep_weight(self, master, fold, N, taps, Cin, Wf, ldf, Wd, ldd, stream):
+        N, taps, Cin, ldf, ldd = map(_v, (N, taps, Cin, ldf, ldd))
+        w = T(master, F32, N * taps * Cin).view(N, taps, Cin)
+        if _addr(fold):
+            w = w * T(fold, F32, N)[:, None, None]
+        wb = w.to(_Act.dtype)
+        if _addr(Wf):
+            M2(Wf, _Act.dtype, N, taps * Cin, ldf)[:] = wb.reshape(N, taps * Cin)
+        if _addr(Wd):
+            t = T(Wd, _Act.dtype, Cin * taps * ldd).view(Cin, taps, ldd)
+            t[:, :, :N] = wb.permute(2, 1, 0)
+        return 0
+
+    def detrb_dropout_mask(self, out, M, N, drop_p, seed, site, seed_ptr, stream):
+        M, N = _v(M), _v(N)
+        T(out, torch.uint8, M * N)[:] = keep_mask(range(M), range(N), _v(drop_p), _v(seed), _v(site), seed_ptr).reshape(-1).to(torch.uint8)
+        return 0
+
+
+def install():
+    """Route detr_tensorflow_b200's C-ABI calls to the emulator (CPU tensors stand in for device memory)."""
+    fake = FakeLib()
+    _lib._lib = fake
+    _lib._EMULATED = True
+    return fake
+
+
+def uninstall():
+    _lib._lib = None
+    _lib._EMULATED = False
