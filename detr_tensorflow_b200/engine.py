@@ -69,6 +69,7 @@ class Engine:
         self.sites = {}
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.launches = 0
+        self.acc = None
 
     # ------------------------------------------------------------------------------------------ parameters
     def _build_params(self):
@@ -740,9 +741,73 @@ class Engine:
     def set_enabled(self, backbone, transformers, nlayers=False):
         self.group_enabled[:3] = torch.tensor([int(backbone), int(transformers), int(nlayers)], dtype=torch.uint8)
 
+    def apply_group(self, name, grads_arena, clipnorm):
+        """Adam apply for ONE group (the reference applies its three optimizers one after the other,
+        training.py:53-54 -> optimizers.py:160-163)."""
+        en = torch.zeros(8, dtype=torch.uint8)
+        en[GROUPS.index(name)] = 1
+        self.group_enabled.copy_(en)
+        self.launches += 3
+        ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
+                          self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
+        self.refresh_weights()
+
+    def allreduce_grads(self):
+        """data parallel: ONE sum all-reduce over the flat gradient arena (NCCL over NVLink); no-op on one rank."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+
+    def set_global_normalisers(self, t_bbox):
+        """Under data parallelism the reference's batch-level normalisers (loss.py:66-67,82,94) must be those of the
+        GLOBAL batch: N = sum n_i over all ranks, sum_w = 0.1*(B_glob*Q - N) + N.  They depend on the labels only, so
+        one tiny all-reduce of the local target count before the step is enough."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            self.normalisers = None
+            return
+        n_local = t_bbox.reshape(-1, 100, 4)[:, 0, 0].to(self.device, torch.float32).clamp(0, 99).sum().reshape(1)
+        dist.all_reduce(n_local, op=dist.ReduceOp.SUM)
+        bq = float(dist.get_world_size() * t_bbox.shape[0] * self.Q)
+        if getattr(self, "_norm_buf", None) is None:
+            self._norm_buf = torch.zeros(2, dtype=F32, device=self.device)
+        self._norm_buf[0:1] = n_local
+        self._norm_buf[1:2] = 0.1 * (bq - n_local) + n_local
+        self.normalisers = self._norm_buf
+
     def optimizer_step(self, clipnorm):
         """aggregate_grad_and_apply's apply branch (optimizers.py:160-163) for all enabled groups."""
         self.launches += 3
         ops.adam_clipnorm(self.params, self.grads, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
                           self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
         self.refresh_weights()
+
+    # ------------------------------------------------------------------------------------------ fused fast path
+    def train_step(self, background_class, clipnorm, loss_scale=1.0, train_backbone=True):
+        """One optimizer step on the batch already resident in a['images'] / a['t_bbox'] / a['t_class']:
+        training.py:9-25 + :53-54 with no accumulation.  Launch-only (no host sync): CUDA-graph capturable."""
+        self.training = True
+        self.seed_dev.add_(1)                   # fresh dropout masks every step, also under graph replay
+        self._forward_impl()
+        self.loss(background_class, loss_scale=loss_scale, with_grad=True)
+        self.zero_grads()
+        self.backward(train_backbone=train_backbone)
+        self.allreduce_grads()
+        self.optimizer_step(clipnorm)
+
+    def capture_train_step(self, background_class, clipnorm, loss_scale=1.0, train_backbone=True, warmup=2):
+        """Capture train_step into a CUDA graph (static shapes: fixed-size images).  Returns a callable replaying it."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_step(background_class, clipnorm, loss_scale, train_backbone)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = self.launches
+        with torch.cuda.graph(graph):
+            self.train_step(background_class, clipnorm, loss_scale, train_backbone)
+        self.launches_per_step = self.launches - n0
+        self._graph = graph
+        return graph.replay

@@ -1,0 +1,57 @@
+"""get_detr_model -- mirror of detr_tf/networks/detr.py:116-204 on top of the sm_100a engine."""
+import numpy as np
+import torch
+
+from ..engine import Engine
+from .init import init_params
+
+
+def _as_device_f32(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    return x.to(device=device, dtype=torch.float32, non_blocking=True)
+
+
+class DetrModel:
+    """Callable like the Keras functional model the reference returns: model(images[B,H,W,3], training=bool) ->
+    {'pred_logits': [B,100,C], 'pred_boxes': [B,100,4], 'aux': [5 x same]} (detr.py:190-204).
+    With include_top=False the call returns the stacked decoder states hs [L,B,100,256] (detr.py:177-179)."""
+
+    def __init__(self, engine, include_top, name):
+        self.engine = engine
+        self.include_top = include_top
+        self.name = name
+
+    def __call__(self, images, training=False):
+        eng = self.engine
+        out = eng.forward(_as_device_f32(images, eng.device), training=training)
+        if self.include_top:
+            return out
+        return eng.a["hs"].view(eng.ndec, eng.B, eng.Q, eng.d)
+
+    # convenience (not in the reference): parameter I/O in the reference's layouts
+    def load_params(self, params):
+        self.engine.load_params(params)
+
+    def export_params(self):
+        return self.engine.export_params()
+
+
+def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_backbone=False, num_decoder_layers=6,
+                   num_encoder_layers=6, backbone="resnet50", device="cuda", seed=0, params=None, dropout=0.1):
+    """detr.py:116-204.  Extensions: `backbone` ("resnet50" | "resnet101": the reference ignores its own backbone
+    argument, detr.py:21,31), `device`, `seed`/`params` (synthetic or caller-provided weights in reference layouts),
+    `dropout` (transformer.py:9 default 0.1; 0 makes training-mode steps deterministic for tests)."""
+    if tf_backbone:
+        raise NotImplementedError("tf_backbone=True (keras.applications ResNet50, detr.py:146-148) is out of scope")
+    if weights is not None:
+        raise NotImplementedError("pretrained checkpoint download (networks/weights.py) is out of scope: pass params=")
+    if nb_class is not None:
+        raise NotImplementedError("fine-tuning heads (add_heads_nlayers, detr.py:94-114) are a 'next' row (SURVEY 8f N4)")
+    eng = Engine(device=device, backbone=backbone, num_classes=92, num_encoder_layers=num_encoder_layers,
+                 num_decoder_layers=num_decoder_layers, seed=seed, dropout=dropout)
+    if params is None:
+        params = init_params(seed, backbone=backbone, num_encoder_layers=num_encoder_layers,
+                             num_decoder_layers=num_decoder_layers)
+    eng.load_params(params)
+    return DetrModel(eng, include_top, "detr_finetuning" if include_top else "detr")

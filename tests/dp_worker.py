@@ -1,0 +1,47 @@
+"""worker for test_data_parallel_two_ranks_gloo (CPU, gloo, C ABI emulated)"""
+import sys
+
+import torch
+import torch.distributed as dist
+
+import cabi_emulator
+from oracle import detr_oracle as O
+
+rank, world, outdir = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+cabi_emulator.install()
+cabi_emulator.set_act_dtype(torch.float32)
+import detr_tensorflow_b200 as D  # noqa: E402
+
+NE, ND = 1, 2
+P = O.init_params(seed=1, num_encoder_layers=NE, num_decoder_layers=ND)
+img = torch.randn(2, 32, 48, 3, generator=torch.Generator().manual_seed(5))
+tb, tc = O.synthetic_targets(2, n=4, seed=5, n_range=(2, 6))
+cfg = D.TrainingConfig()
+cfg.background_class = 91
+
+
+def run(images, tbb, tcc, distributed):
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    eng = model.engine
+    eng.forward(images, training=False)
+    eng.set_targets(tbb, tcc)
+    if distributed:
+        eng.set_global_normalisers(tbb)
+    eng.zero_grads()
+    eng.loss(91)
+    eng.backward()
+    eng.allreduce_grads()
+    total, _ = eng.loss_dict()
+    return float(total), eng.export_grads()
+
+
+if rank == 0:
+    total, grads = run(img, tb, tc, False)
+    torch.save({"total": total, "grads": grads}, f"{outdir}/single.pt")
+dist.init_process_group("gloo", rank=rank, world_size=world)
+total, grads = run(img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], True)
+t = torch.tensor([total])
+dist.all_reduce(t)
+if rank == 0:
+    torch.save({"total_global": float(t), "grads": grads}, f"{outdir}/dp_rank0.pt")
+dist.destroy_process_group()

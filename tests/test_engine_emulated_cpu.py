@@ -1,0 +1,199 @@
+"""CPU tests of the host-side logic (engine orchestration, API mirror, optimizer glue, data-parallel path) with the
+C ABI replaced by tests/cabi_emulator.py.  With fp32 storage the hand-written backward chain must reproduce the
+oracle's autograd gradients to rounding error; with bf16 storage it must stay within bf16 noise on the forward."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cabi_emulator
+from oracle import detr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NE, ND = 1, 2
+
+
+@pytest.fixture()
+def emu():
+    cabi_emulator.install()
+    cabi_emulator.set_act_dtype(torch.float32)
+    yield cabi_emulator
+    cabi_emulator.set_act_dtype(torch.bfloat16)
+    cabi_emulator.uninstall()
+
+
+def _setup(B=2, H=64, W=96, n=5, seed=1):
+    P = O.init_params(seed=seed, num_encoder_layers=NE, num_decoder_layers=ND)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    tb, tc = O.synthetic_targets(B, n=n, seed=seed)
+    return P, img, tb, tc
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-20))
+
+
+def test_forward_loss_backward_match_oracle_fp32(emu):
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup()
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    out = model(img, training=False)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img, num_encoder_layers=NE, num_decoder_layers=ND)
+    assert out["pred_logits"].shape == (2, 100, 92) and out["pred_boxes"].shape == (2, 100, 4) and len(out["aux"]) == ND - 1
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 1e-4 and rel(out["pred_boxes"], ref["pred_boxes"]) < 1e-4
+    eng = model.engine
+    eng.set_targets(tb, tc)
+    eng.zero_grads()
+    eng.loss(91)
+    total, log = eng.loss_dict()
+    eng.backward()
+    match = eng.a["match"].view(ND, 2, 100)
+    _, ototal, olog, ograds = O.train_step(P, img, tb, tc, num_encoder_layers=NE, num_decoder_layers=ND, match_override=match)
+    assert abs(float(total) - float(ototal)) < 1e-4 * abs(float(ototal))
+    for k in olog:
+        assert abs(float(log[k]) - float(olog[k])) < 1e-4 + 1e-4 * abs(float(olog[k])), k
+    grads = eng.export_grads()
+    assert set(grads) == set(ograds)
+    for n_, g in grads.items():
+        ref_g = ograds[n_]
+        if float(ref_g.norm()) < 1e-6:
+            assert float(g.norm()) < 1e-5, n_
+        else:
+            assert rel(g, ref_g) < 2e-3, (n_, rel(g, ref_g))
+    # and the Hungarian assignment equals the oracle's (scipy) on the same fp32 outputs
+    for l in range(ND):
+        o_ = ref if l == ND - 1 else ref["aux"][l]
+        for b in range(2):
+            ti, pi, _, _, _, _ = O.hungarian_matching(tb[b], tc[b], o_["pred_boxes"][b], o_["pred_logits"][b])
+            exp = -torch.ones(100, dtype=torch.int32)
+            exp[pi] = ti.int()
+            assert torch.equal(exp, match[l, b])
+
+
+def test_bf16_storage_forward_noise_level(emu):
+    import detr_tensorflow_b200 as D
+    emu.set_act_dtype(torch.bfloat16)
+    P, img, tb, tc = _setup()
+    model = D.get_detr_model(D.TrainingConfig(), include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    out = model(img, training=False)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img, num_encoder_layers=NE, num_decoder_layers=ND)
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 3e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 2e-2
+
+
+def test_training_fit_adam_and_accumulation(emu):
+    """fit() over 2 micro-steps with target_batch = 2*batch_size: accumulate, then one Keras-Adam apply with
+    per-variable clipnorm; compared with the oracle's restatement of optimizers.py."""
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    P2, img2, tb2, tc2 = _setup(B=1, H=32, W=48, n=4, seed=2)
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 1, 2
+    cfg.train_backbone, cfg.train_transformers = True, True
+    cfg.backbone_lr, cfg.transformers_lr = 1e-3, 1e-2
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+    opt = D.setup_optimizers(model, cfg)
+    assert set(opt) >= {"backbone_optimizer", "transformers_optimizer", "nlayers_optimizer", "backbone_variables",
+                        "transformers_variables", "nlayers_variables"}
+    eng = model.engine
+    # the body of fit() (training.py:41-54), keeping each micro-step's assignment so that the oracle can be evaluated
+    # under the same matching (assignments of random-init predictions are unstable to 1e-6 perturbations)
+    acc = None
+    for step, (im, b_, c_) in enumerate(((img, tb, tc), (img2, tb2, tc2))):
+        m_out, total_loss, log, gsteps = D.training.run_train_step(model, im, b_, c_, opt, cfg)
+        assert set(gsteps) == {"backbone", "transformers", "nlayers"} and "backbone_lr" in log
+        match = eng.a["match"].view(ND, 1, 100).clone()
+        for name in gsteps:
+            D.optimizers.aggregate_grad_and_apply(name, opt, gsteps[name]["gradients"], step, cfg)
+        _, ototal, _, g = O.train_step(P, im, b_, c_, num_encoder_layers=NE, num_decoder_layers=ND, gradient_aggregate=2,
+                                       match_override=match)
+        assert abs(float(total_loss) - float(ototal)) < 1e-4 * abs(float(ototal))
+        acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+    assert opt["backbone_optimizer"].iterations == 1 and opt["transformers_optimizer"].iterations == 1
+    new = model.export_params()
+    for name, g in acc.items():
+        p = P[name].clone()
+        lr = cfg.backbone_lr if O.param_group(name) == "backbone" else cfg.transformers_lr
+        O.adam_clipnorm_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1, lr, 0.1)
+        # Adam's first step moves every element by ~lr * sign(g): compare the update, not the value
+        upd, ref_upd = new[name] - P[name], p - P[name]
+        if float(g.norm()) < 1e-6:
+            continue
+        assert rel(upd, ref_upd) < 5e-2, (name, rel(upd, ref_upd))
+    # frozen / ungrouped tensors untouched
+    assert torch.equal(new["query_embed/kernel"], P["query_embed/kernel"])
+    assert torch.equal(new["backbone/bn1/weight"], P["backbone/bn1/weight"])
+
+
+def test_fit_loop_runs(emu, capsys):
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 1, 2
+    cfg.train_backbone, cfg.train_transformers = True, True
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    opt = D.setup_optimizers(model, cfg)
+    D.training.fit(model, [(img, tb, tc), (img, tb, tc)], opt, cfg, 0, None)
+    D.training.eval(model, [(img, tb, tc)], cfg, None, evaluation_step=1)
+    assert cfg.global_step == 2 and opt["backbone_optimizer"].iterations == 1
+    outp = capsys.readouterr().out
+    assert "Epoch: [0]" in outp and "Validation step: [0]" in outp
+
+
+def test_group_gating(emu):
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 1, None
+    cfg.train_backbone, cfg.train_transformers = False, True
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    opt = D.setup_optimizers(model, cfg)
+    D.training.fit(model, [(img, tb, tc)], opt, cfg, 0, None)
+    new = model.export_params()
+    assert torch.equal(new["backbone/layer1/0/conv1/kernel"], P["backbone/layer1/0/conv1/kernel"])      # not applied
+    assert not torch.equal(new["class_embed/kernel"], P["class_embed/kernel"])
+    assert opt["backbone_optimizer"].iterations == 0 and opt["transformers_optimizer"].iterations == 1
+
+
+def test_standalone_losses_and_matching_api(emu, golden):
+    import detr_tensorflow_b200 as D
+    g = golden
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    logits, boxes = torch.from_numpy(g["l_logits"]), torch.from_numpy(g["l_boxes"])
+    out = {"pred_logits": logits[5], "pred_boxes": boxes[5],
+           "aux": [{"pred_logits": logits[i], "pred_boxes": boxes[i]} for i in range(5)]}
+    total, losses = D.get_losses(out, g["l_t_bbox"], g["l_t_class"], cfg)
+    assert abs(float(total) - float(g["l_total"])) < 2e-4 * float(g["l_total"])
+    assert list(losses)[:6] == ["label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss"] and len(losses) == 36
+    for k, v in zip(g["l_keys"], g["l_values"]):
+        assert abs(float(losses[str(k)]) - float(v)) < 1e-4 + 1e-4 * abs(float(v)), k
+    b = 0
+    r = D.hungarian_matching(g["m_t_bbox"][b], g["m_t_class"][b], g["m_boxes"][b], g["m_logits"][b], device="cpu")
+    assert np.array_equal(r[0].numpy(), g[f"m_t_indices_{b}"]) and np.array_equal(r[1].numpy(), g[f"m_p_indices_{b}"])
+    assert np.array_equal(r[3].numpy(), g[f"m_p_selector_{b}"]) and bool(r[2].all())
+    np.testing.assert_array_equal(r[4].numpy(), g[f"m_tb_{b}"])
+
+
+def test_data_parallel_two_ranks_gloo(tmp_path):
+    """world_size-2 gloo run of the N>1 path: each rank takes half of a global batch of 2, gradients are summed with
+    one all-reduce and the loss uses GLOBAL normalisers -> must equal the single-process global-batch gradients."""
+    script = os.path.join(ROOT, "tests", "dp_worker.py")
+    port = 29500 + (os.getpid() % 2000)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2", str(tmp_path)], env=env) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    single = torch.load(os.path.join(tmp_path, "single.pt"))
+    dp = torch.load(os.path.join(tmp_path, "dp_rank0.pt"))
+    assert abs(dp["total_global"] - single["total"]) < 1e-4 * abs(single["total"])
+    for k in single["grads"]:
+        a, b = dp["grads"][k], single["grads"][k]
+        if float(b.norm()) > 1e-6:
+            assert rel(a, b) < 2e-3, (k, rel(a, b))
