@@ -412,8 +412,15 @@ class Engine:
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
+        probe = getattr(self, "probe_name", None) == s.name          # bench.py: CUDA-event timing of one launch
+        if probe:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual, ldr=s.N,
                   relu=relu, C=out, ldc=s.N)
+        if probe:
+            e1.record()
+            self.probe_events.append((e0, e1))
 
     def _conv_dgrad(self, s, dy, ihw, ohw, out, mask=None, residual=None):
         """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]."""

@@ -17,7 +17,9 @@ def _dev(x, dtype, device):
 def _forward_loss(model, images, t_bbox, t_class, config, training, loss_scale, with_grad):
     eng = model.engine
     m_outputs = eng.forward(_dev(images, torch.float32, eng.device), training=training)
-    eng.set_targets(_dev(t_bbox, torch.float32, eng.device), _dev(t_class, torch.int64, eng.device))
+    t_bbox = _dev(t_bbox, torch.float32, eng.device)
+    eng.set_targets(t_bbox, _dev(t_class, torch.int64, eng.device))
+    eng.set_global_normalisers(t_bbox)          # data parallel: batch-level normalisers of the GLOBAL batch
     eng.loss(int(config.background_class), loss_scale=loss_scale, with_grad=with_grad)
     total, log = eng.loss_dict()
     return m_outputs, total, dict(log)
