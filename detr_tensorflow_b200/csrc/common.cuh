@@ -19,6 +19,11 @@ void detrb_set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// gemm_tc.cu (tcgen05 / TMA / TMEM path)
+bool detrb_gemm_tc_supported(const detrb_igemm_t &p);
+bool detrb_gemm_tc_enabled();
+int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);

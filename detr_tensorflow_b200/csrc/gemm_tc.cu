@@ -1,0 +1,352 @@
+// gemm_tc.cu -- Blackwell-native GEMM:  C[M,N] = epilogue( A[M,K] * W[N,K]^T ), bf16 operands, fp32 accumulation
+// in TENSOR MEMORY.  TMA (cp.async.bulk.tensor, 128B swizzle) stages the operand tiles into shared memory, a single
+// elected thread issues tcgen05.mma (cta_group::1, M=128 x N=BN x K=16 per instruction), completion is tracked with
+// mbarriers (tcgen05.commit), the epilogue warps read the accumulator with tcgen05.ld and apply the same fused epilogue as
+// igemm.cu (bias / residual / ReLU / ReLU-mask / sigmoid / dropout / bf16+fp32 stores / strided scatter-accumulate).
+//
+// Used by detrb_igemm for every *plain* GEMM of the train step (1x1 stride-1 convolutions and their data gradients,
+// input_proj, all Linear layers of the transformer and the heads) -- ~57 % of the model's FLOPs.  Gathered convolutions
+// (3x3, 7x7, strided) stay on igemm.cu until their TMA-im2col variant lands.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane
+// quarter = warp_id % 4).  BN x STAGES are sized so that 2-3 CTAs are co-resident per SM (<= 96 KB smem, <= 128 TMEM
+// columns each): one CTA's epilogue overlaps another's main loop -- the k-loops of this model are short (1..32 blocks).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TBM = 128;
+constexpr int TBK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int NTHREADS_TC = 192;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row core groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                  // version
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
+// N>>3 at bits [17,23), M>>4 at bits [24,29)   (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = TBM * TBK * 2;
+    static constexpr int B_BYTES = BN * TBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;      // barriers + slack for 1024-byte alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS_TC)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const detrb_igemm_t p)
+{
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
+    const uint32_t bar_base = smem_base + L::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+    const int nk = p.K / TBK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nk; kb++) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+                tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nk; kb++) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
+                const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + L::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TBK / 16; k++)          // advance 32 B (16 bf16) inside the 128 B swizzle row
+                    tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                tc_commit(empty_bar(stage));                // frees this smem stage when the MMAs have read it
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tmem_full_bar);                       // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+        size_t orow = m;
+        if (row_ok && p.out_stride > 1) {
+            const int ohw = p.OH * p.OW;
+            int b = m / ohw, rem = m - b * ohw;
+            int oy = rem / p.OW, ox = rem - oy * p.OW;
+            orow = ((size_t)b * p.SH + (size_t)oy * p.out_stride) * p.SW + (size_t)ox * p.out_stride;
+        }
+        const uint32_t thresh = dropout_thresh16(p.drop_p);
+        const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+        const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        bf16 *C = reinterpret_cast<bf16 *>(p.C);
+        const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
+        const bf16 *Mk = reinterpret_cast<const bf16 *>(p.mask);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc_wait_ld();
+            if (!row_ok || n0 + c0 >= p.N) continue;
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                const int n = n0 + c0 + hf * 8;
+                if (n >= p.N) continue;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hf * 8 + i]);
+                if (p.bias) {
+                    float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                float res[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) res[i] = 0.f;
+                if (R) {
+                    uint4 u = *reinterpret_cast<const uint4 *>(R + orow * p.ldr + n);
+                    float2 t;
+                    t = unpack_bf16x2(u.x); res[0] = t.x; res[1] = t.y; t = unpack_bf16x2(u.y); res[2] = t.x; res[3] = t.y;
+                    t = unpack_bf16x2(u.z); res[4] = t.x; res[5] = t.y; t = unpack_bf16x2(u.w); res[6] = t.x; res[7] = t.y;
+                }
+                if (!(p.drop_p > 0.f)) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] += res[i];
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (Mk) {
+                    uint4 u = *reinterpret_cast<const uint4 *>(Mk + orow * p.ldm + n);
+                    float mk[8]; float2 t;
+                    t = unpack_bf16x2(u.x); mk[0] = t.x; mk[1] = t.y; t = unpack_bf16x2(u.y); mk[2] = t.x; mk[3] = t.y;
+                    t = unpack_bf16x2(u.z); mk[4] = t.x; mk[5] = t.y; t = unpack_bf16x2(u.w); mk[6] = t.x; mk[7] = t.y;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
+                }
+                if (p.sigmoid) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+                }
+                if (p.drop_p > 0.f) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        bool k0, k1;
+                        dropout_keep2(dropout_bits(seed, p.site, (uint32_t)m, (uint32_t)((n + i) >> 1)), thresh, k0, k1);
+                        v[i] = (k0 ? v[i] * drop_scale : 0.f) + res[i];
+                        v[i + 1] = (k1 ? v[i + 1] * drop_scale : 0.f) + res[i + 1];
+                    }
+                }
+                if (C) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(C + orow * p.ldc + n);
+                    if (p.accumulate) {
+                        uint4 u = *dst; float2 t;
+                        t = unpack_bf16x2(u.x); v[0] += t.x; v[1] += t.y; t = unpack_bf16x2(u.y); v[2] += t.x; v[3] += t.y;
+                        t = unpack_bf16x2(u.z); v[4] += t.x; v[5] += t.y; t = unpack_bf16x2(u.w); v[6] += t.x; v[7] += t.y;
+                    }
+                    uint4 o;
+                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                    *dst = o;
+                }
+                if (p.Cf) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.Cf + orow * p.ldcf + n);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+    }
+    // ---- teardown: everyone done with TMEM -> the allocating warp frees it
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill
+bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {TBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    using L = SmemLayout<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM) ||
+        !make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN))
+        DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", p.M, p.N, p.K, p.lda, p.ldw);
+    dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
+    gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, p);
+    DETRB_CHECK_LAUNCH("gemm_tc_kernel");
+    return DETRB_OK;
+}
+
+}  // namespace
+
+// 1 if the tcgen05 path can run this problem (plain GEMM, aligned); detrb_igemm falls through to igemm.cu otherwise
+bool detrb_gemm_tc_supported(const detrb_igemm_t &p)
+{
+    if (p.mode != 0 || p.KH != 1 || p.KW != 1 || p.stride != 1 || p.pad != 0) return false;
+    if (p.Cin != p.K || p.K % TBK != 0) return false;
+    if (p.N % 8 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0) return false;
+    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15)) return false;
+    if (p.C && (p.ldc % 8 != 0 || ((uintptr_t)p.C & 15))) return false;
+    if (p.Cf && (p.ldcf % 4 != 0 || ((uintptr_t)p.Cf & 15))) return false;
+    if (p.residual && (p.ldr % 8 != 0 || ((uintptr_t)p.residual & 15))) return false;
+    if (p.mask && (p.ldm % 8 != 0 || ((uintptr_t)p.mask & 15))) return false;
+    if (p.bias && ((uintptr_t)p.bias & 15)) return false;
+    return get_encode_fn() != nullptr;
+}
+
+static int g_tc_enabled = 0;
+extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
+bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
+
+int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
+    if (p.N >= 128 && tiles128 >= 148) return launch_tc<128, 3>(p, stream);
+    return launch_tc<64, 3>(p, stream);
+}
+
+// standalone entry for tests / microbenchmarks: forces the tcgen05 path (error if unsupported)
+extern "C" int detrb_gemm_tc_force(const detrb_igemm_t *pp, int bn, detrb_stream_t stream)
+{
+    if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: null params");
+    detrb_igemm_t p = *pp;
+    if (p.out_stride < 1) p.out_stride = 1;
+    if (!detrb_gemm_tc_supported(p)) DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc_force: problem not supported by the tcgen05 path");
+    if (bn == 128) return launch_tc<128, 3>(p, (cudaStream_t)stream);
+    if (bn == 64) return launch_tc<64, 3>(p, (cudaStream_t)stream);
+    return detrb_gemm_tc(p, (cudaStream_t)stream);
+}

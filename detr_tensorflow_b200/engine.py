@@ -389,6 +389,28 @@ class Engine:
         return torch.cat([py, px], dim=2).reshape(h * w, 2 * npf)
 
     # ------------------------------------------------------------------------------------------ op helpers
+    def _mark(self, name):
+        """section boundary for profile_step(): a CUDA event on the launch stream (no-op otherwise)"""
+        marks = getattr(self, "_marks", None)
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    def profile_step(self, background_class, clipnorm, repeats=3):
+        """eager train steps with CUDA events at section boundaries -> {section: ms} (median over repeats)"""
+        import statistics
+        acc = {}
+        for _ in range(repeats):
+            self._marks = []
+            self._mark("start")
+            self.train_step(background_class, clipnorm)
+            torch.cuda.synchronize()
+            marks, self._marks = self._marks, None
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+        return {k: statistics.median(v) for k, v in acc.items()}
+
     def _site(self, name):
         if name not in self.sites:
             self.sites[name] = len(self.sites) + 1
@@ -499,6 +521,7 @@ class Engine:
             self._conv_fwd(blk["c3"], a[f"b{i}_a2"], ohw, ohw, a[f"b{i}_out"], relu=True, residual=idn)
             x = a[f"b{i}_out"]
         self.feat = x
+        self._mark("fwd_backbone")
         # ---------------- input_proj (detr.py:44,175) + pos add
         ip = self.slots["input_proj"]
         self._lin(x, ip.Wf, M, d, ip.K, ip.K, out=a["src"], bias=ip.bias)
@@ -524,6 +547,7 @@ class Engine:
             xin, xinp = e("y2"), e("y2p")
         mem, memp = xin, xinp
         self.mem, self.memp = mem, memp
+        self._mark("fwd_encoder")
         # ---------------- decoder (transformer.py:207-234, 104-133)
         tgt = a["tgt0"]
         for l, D in enumerate(self.dec):
@@ -562,6 +586,7 @@ class Engine:
         self._lin(a["hs"], self.h_b0.Wf, LM, d, d, d, out=a["hb1"], bias=self.h_b0.bias, relu=True)
         self._lin(a["hb1"], self.h_b1.Wf, LM, d, d, d, out=a["hb2"], bias=self.h_b1.bias, relu=True)
         self._lin(a["hb2"], self.h_b2.Wf, LM, 4, d, d, Cf=a["boxes"], ldcf=4, bias=self.h_b2.bias, sigmoid=True)
+        self._mark("fwd_decoder_heads")
 
     def _attn_drop(self, name):
         return self._drop(name)
@@ -591,6 +616,7 @@ class Engine:
         ops.set_loss(a["logits"], self.C, a["boxes"], a["t_bbox"], a["t_class"], a["match"], L, B, Q, self.C,
                      background_class, self.normalisers, loss_scale, a["loss_sums"], a["losses"], a["total"],
                      a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32)
+        self._mark("matcher_loss")
 
     def loss_dict(self):
         """36 scalars with the reference's keys (loss.py:172-179; aux layer i -> suffix _i, main = last layer)."""
@@ -676,6 +702,7 @@ class Engine:
                 self._lin(a["gq_qk"], W.Wd, Mq, d, 2 * d, W.ldd, out=a["gq_a"], residual=a["gq_b"], ldr=d)
                 g_next = a["gq_n0"] if (l & 1) else a["gq_n1"]       # ping-pong: read by layer l-1's LN3 backward
                 self._lin(a["gq_v"], W.Wd[:, :, 2 * d:], Mq, d, d, W.ldd, out=g_next, residual=a["gq_a"], ldr=d)
+        self._mark("bwd_heads_decoder")
         # ---------------- encoder, last layer first.  g_mem = d y2 (last encoder layer output incl. its +pos use)
         g_y = a["g_mem"]
         for l in reversed(range(self.nenc)):
@@ -702,6 +729,7 @@ class Engine:
             self._lin(a["gm_qk"], W.Wd, M, d, 2 * d, W.ldd, out=a["gm_c"], residual=a["gm_a"], ldr=d)
             g_y = a["gm_n0"] if (l & 1) else a["gm_n1"]
             self._lin(a["gm_v"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=g_y, residual=a["gm_c"], ldr=d)
+        self._mark("bwd_encoder")
         # ---------------- input_proj
         ip = self.slots["input_proj"]
         self._lin_wgrad(ip, self.feat, g_y, M)
@@ -740,6 +768,7 @@ class Engine:
         ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
         stem = self.slots["backbone/conv1"]
         self._conv_wgrad(stem, a["img4"], g_in, (self.H0, self.W0), self.hw_stem)
+        self._mark("bwd_backbone")
 
     # ------------------------------------------------------------------------------------------ optimizer
     def set_lrs(self, backbone_lr, transformers_lr, nlayers_lr=0.0):
@@ -800,7 +829,9 @@ class Engine:
         self.zero_grads()
         self.backward(train_backbone=train_backbone)
         self.allreduce_grads()
+        self._mark("allreduce")
         self.optimizer_step(clipnorm)
+        self._mark("adam_refresh")
 
     def capture_train_step(self, background_class, clipnorm, loss_scale=1.0, train_backbone=True, warmup=2):
         """Capture train_step into a CUDA graph (static shapes: fixed-size images).  Returns a callable replaying it."""

@@ -30,7 +30,7 @@ def plain_geom(M, K):
 
 def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mask=None, ldm=0, mask_scale=1.0,
           relu=False, sigmoid=False, drop_p=0.0, seed=0, site=0, seed_ptr=None, C=None, ldc=0, Cf=None, ldcf=0,
-          out_stride=1, SH=0, SW=0, accumulate=False):
+          out_stride=1, SH=0, SW=0, accumulate=False, force_tc=None):
     p = IgemmParams()
     p.A, p.W = ptr(A), ptr(W)
     p.M, p.N, p.K, p.lda, p.ldw = M, N, K, lda, ldw
@@ -40,7 +40,15 @@ def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mas
     p.relu, p.sigmoid, p.drop_p, p.seed, p.site, p.seed_ptr = int(relu), int(sigmoid), drop_p, seed, site, ptr(seed_ptr)
     p.C, p.ldc, p.Cf, p.ldcf = ptr(C), ldc, ptr(Cf), ldcf
     p.out_stride, p.SH, p.SW, p.accumulate = out_stride, SH, SW, int(accumulate)
-    check(_lib.lib().detrb_igemm(byref(p), _stream()))
+    if force_tc is not None:
+        check(_lib.lib().detrb_gemm_tc_force(byref(p), c_int(force_tc), _stream()))
+    else:
+        check(_lib.lib().detrb_igemm(byref(p), _stream()))
+
+
+def set_tc(enable):
+    """route plain GEMMs through the tcgen05/TMA/TMEM kernel (gemm_tc.cu); returns the previous setting"""
+    return _lib.lib().detrb_set_tc(c_int(int(enable)))
 
 
 def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None):

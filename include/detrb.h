@@ -87,6 +87,11 @@ typedef struct {
 } detrb_igemm_t;
 
 int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
+/* Plain GEMMs (KH=KW=1, stride 1, K % 64 == 0, 16-byte aligned operands) run on the tcgen05 / TMA / TMEM kernel
+ * (gemm_tc.cu) when enabled; everything else, and everything when disabled, runs on the mma.sync kernel (igemm.cu).
+ * detrb_set_tc returns the previous setting.  detrb_gemm_tc_force runs the tcgen05 kernel or fails (tests; bn = 64|128|0). */
+int detrb_set_tc(int enable);
+int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)
  * and optionally dbias[n] += rowscale[n] * sum_m dY[m,n].

@@ -1,0 +1,95 @@
+"""tcgen05 / TMA / TMEM GEMM (csrc/gemm_tc.cu) against a PyTorch fp32 reference and against the mma.sync kernel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from detr_tensorflow_b200 import _lib, ops as o
+    _lib.check(_lib.lib().detrb_check_device())
+    return o
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).cuda()
+
+
+def check(name, got, ref, rtol, atol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    assert int(bad.sum()) == 0, f"{name}: {int(bad.sum())}/{bad.numel()} bad, max err {float(err.max()):.4g}, " \
+                                f"rel {float((got - ref).norm() / ref.norm()):.4g}, first bad {torch.nonzero(bad)[0].tolist()}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 64, 128), (256, 128, 128, 128), (1050, 256, 256, 128),
+                                      (1050, 256, 256, 64), (4175, 64, 256, 64), (300, 2048, 256, 128), (777, 256, 2048, 128),
+                                      (100, 256, 256, 0), (8400, 512, 1024, 0), (130, 72, 64, 64)])
+def test_gemm_tc_plain(ops, M, N, K, bn):
+    A = rnd(M, K, seed=1).to(BF)
+    W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+    bias = rnd(N, seed=3)
+    C = torch.full((M, N), 7.0, dtype=BF, device="cuda")
+    Cf = torch.full((M, N), 7.0, dtype=F32, device="cuda")
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, C=C, ldc=N, Cf=Cf, ldcf=N, force_tc=bn)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    check("tc f32", Cf, ref, 1e-3, 1e-3)
+    check("tc bf16", C, ref, 1e-2, 1e-2)
+
+
+def test_gemm_tc_epilogues_match_mma_sync_kernel(ops):
+    M, N, K = 1000, 256, 192
+    A = rnd(M, 2 * K, seed=1).to(BF)[:, K:]            # strided A (lda = 2K)
+    W = rnd(3 * N, K, scale=K ** -0.5, seed=2).to(BF)[N:2 * N]
+    bias, res, mask = rnd(N, seed=3), rnd(M, N, seed=4).to(BF), rnd(M, N, seed=5).to(BF)
+    seed_dev = torch.tensor([4242], dtype=torch.int64, device="cuda")
+    cases = [dict(bias=bias, residual=res, ldr=N, relu=True), dict(bias=bias, mask=mask, ldm=N, mask_scale=1.0 / 0.9),
+             dict(bias=bias, sigmoid=True), dict(bias=bias, residual=res, ldr=N, drop_p=0.1, seed=5, site=3, seed_ptr=seed_dev),
+             dict(bias=bias, relu=True, drop_p=0.1, seed=5, site=4, seed_ptr=seed_dev)]
+    for i, kw in enumerate(cases):
+        C1, C2 = torch.zeros(M, N, dtype=BF, device="cuda"), torch.zeros(M, N, dtype=BF, device="cuda")
+        ops.igemm(A, W, M, N, K, 2 * K, K, ops.plain_geom(M, K), C=C1, ldc=N, **kw)
+        ops.igemm(A, W, M, N, K, 2 * K, K, ops.plain_geom(M, K), C=C2, ldc=N, force_tc=0, **kw)
+        torch.cuda.synchronize()
+        check(f"case {i}", C2, C1, 1e-2, 1e-2)
+    # accumulate + strided scatter (1x1 stride-2 data gradient)
+    B, oh, ow, H, Wd, cin, cout = 2, 7, 10, 13, 19, 256, 512
+    dy = rnd(B * oh * ow, cout, seed=6).to(BF)
+    wd = rnd(cin, cout, scale=cout ** -0.5, seed=7).to(BF)
+    base = rnd(B * H * Wd, cin, seed=8).to(BF)
+    xm = rnd(B * H * Wd, cin, seed=9).to(BF)
+    g = dict(batch=B, IH=oh, IW=ow, Cin=cout, OH=oh, OW=ow, KH=1, KW=1, stride=1, pad=0, mode=0)
+    outs = []
+    for tc in (None, 0):
+        dx = base.clone()
+        ops.igemm(dy, wd, B * oh * ow, cin, cout, cout, cout, g, mask=xm, ldm=cin, C=dx, ldc=cin, out_stride=2, SH=H, SW=Wd,
+                  accumulate=True, force_tc=tc)
+        outs.append(dx)
+    torch.cuda.synchronize()
+    check("scatter-accumulate", outs[1], outs[0], 1e-2, 2e-2)
+
+
+def test_engine_forward_with_tc_enabled(ops):
+    import detr_tensorflow_b200 as D
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=1)
+    img = torch.randn(2, 160, 224, 3, generator=torch.Generator().manual_seed(1))
+    cfg = D.TrainingConfig()
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0)
+    old = ops.set_tc(1)
+    try:
+        out = model(img, training=False)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_tc(old)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img)
+    rel = float((out["pred_logits"].cpu() - ref["pred_logits"]).norm() / ref["pred_logits"].norm())
+    assert rel < 5e-2, rel
