@@ -22,7 +22,13 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // gemm_tc.cu (tcgen05 / TMA / TMEM path)
 bool detrb_gemm_tc_supported(const detrb_igemm_t &p);
 bool detrb_gemm_tc_enabled();
+bool detrb_gemm_tc_conv_enabled();
+int detrb_gemm_tc_kind(const detrb_igemm_t &p);
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
+// tma_probe.cu / conv_tc.cu: im2col tensor maps
+void *detrb_get_im2col_encode();
+int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int stride, int pixels, int swizzle128);
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

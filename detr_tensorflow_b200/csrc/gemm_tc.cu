@@ -42,6 +42,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -89,9 +95,13 @@ struct SmemLayout {
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;      // barriers + slack for 1024-byte alignment
 };
 
-template <int BN, int STAGES>
+// IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
+// 3x3 / strided / transposed-stride-1); `conv_pad` is the effective padding and `flip` reverses the tap order of the
+// weight tile (data gradient of a stride-1 convolution == convolution with the flipped kernel).
+template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(NTHREADS_TC)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const detrb_igemm_t p)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const detrb_igemm_t p,
+               const int conv_pad, const int flip)
 {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -125,12 +135,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            int w0 = 0, h0 = 0, img = 0;
+            if (IM2COL) {                                   // first output pixel of this tile -> window origin in the input
+                const int ohw = p.OH * p.OW;
+                img = m0 / ohw;
+                const int rem = m0 - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                const int st = p.mode == 0 ? p.stride : 1;
+                w0 = ox * st - conv_pad; h0 = oy * st - conv_pad;
+            }
+            const int taps = p.KH * p.KW;
             for (int kb = 0; kb < nk; kb++) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
                 const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
-                tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
-                tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                if (IM2COL) {
+                    const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    const int wtap = flip ? (taps - 1 - tap) : tap;
+                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), wtap * p.Cin + c0, n0);
+                } else {
+                    tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -292,61 +319,102 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool IM2COL>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
 {
     using L = SmemLayout<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     CUtensorMap ma, mb;
-    if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM) ||
-        !make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN))
-        DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", p.M, p.N, p.K, p.lda, p.ldw);
+    int conv_pad = 0, flip = 0;
+    if (IM2COL) {
+        // forward: window origin = out*stride - pad.  transposed (stride 1): convolution of dY with the flipped kernel, pad' = K-1-pad
+        const int st = p.mode == 0 ? p.stride : 1;
+        conv_pad = p.mode == 0 ? p.pad : (p.KH - 1 - p.pad);
+        flip = p.mode == 1;
+        const int lower = -conv_pad, upper_w = conv_pad - (p.KW - 1), upper_h = conv_pad - (p.KH - 1);
+        if ((p.IW + upper_w - lower - 1) / st + 1 != p.OW || (p.IH + upper_h - lower - 1) / st + 1 != p.OH)
+            DETRB_FAIL(DETRB_E_SHAPE, "gemm_tc im2col: inconsistent conv geometry IH=%d IW=%d OH=%d OW=%d k=%dx%d s=%d p=%d", p.IH, p.IW,
+                       p.OH, p.OW, p.KH, p.KW, st, conv_pad);
+        int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, st, TBM, 1);
+        if (rc) return rc;
+    } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM)) {
+        DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
+    }
+    if (!make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN))
+        DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(W) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
-    gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, p);
+    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, p, conv_pad, flip);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
 }
 
 }  // namespace
 
-// 1 if the tcgen05 path can run this problem (plain GEMM, aligned); detrb_igemm falls through to igemm.cu otherwise
-bool detrb_gemm_tc_supported(const detrb_igemm_t &p)
+static bool aligned_epilogue(const detrb_igemm_t &p)
 {
-    if (p.mode != 0 || p.KH != 1 || p.KW != 1 || p.stride != 1 || p.pad != 0) return false;
-    if (p.Cin != p.K || p.K % TBK != 0) return false;
-    if (p.N % 8 != 0 || p.lda % 8 != 0 || p.ldw % 8 != 0) return false;
-    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.W & 15)) return false;
+    if (p.N % 8 != 0 || p.ldw % 8 != 0 || ((uintptr_t)p.W & 15)) return false;
     if (p.C && (p.ldc % 8 != 0 || ((uintptr_t)p.C & 15))) return false;
     if (p.Cf && (p.ldcf % 4 != 0 || ((uintptr_t)p.Cf & 15))) return false;
     if (p.residual && (p.ldr % 8 != 0 || ((uintptr_t)p.residual & 15))) return false;
     if (p.mask && (p.ldm % 8 != 0 || ((uintptr_t)p.mask & 15))) return false;
     if (p.bias && ((uintptr_t)p.bias & 15)) return false;
-    return get_encode_fn() != nullptr;
+    return true;
 }
+
+// 0: not supported (falls through to igemm.cu), 1: plain GEMM (2-D TMA), 2: implicit-GEMM convolution (TMA im2col)
+int detrb_gemm_tc_kind(const detrb_igemm_t &p)
+{
+    if (p.K % TBK != 0 || p.lda % 8 != 0 || ((uintptr_t)p.A & 15) || !aligned_epilogue(p)) return 0;
+    const bool plain = p.mode == 0 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && p.Cin == p.K;
+    if (plain) return get_encode_fn() != nullptr ? 1 : 0;
+    if (p.Cin % TBK != 0 || p.K != p.KH * p.KW * p.Cin) return 0;
+    if (p.mode == 1 && p.stride != 1) return 0;             // transposed gather of a strided conv stays on igemm.cu
+    if (p.KH > 16 || p.KW > 16 || p.stride > 8) return 0;
+    if ((long)p.lda * 2 * p.IW >= (1l << 40)) return 0;
+    return (get_encode_fn() != nullptr && detrb_get_im2col_encode() != nullptr) ? 2 : 0;
+}
+
+bool detrb_gemm_tc_supported(const detrb_igemm_t &p) { return detrb_gemm_tc_kind(p) != 0; }
 
 static int g_tc_enabled = 0;
 extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
 bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
 
-int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
+static int g_tc_conv_enabled = 1;
+extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }
+bool detrb_gemm_tc_conv_enabled() { return g_tc_conv_enabled != 0; }
+
+template <bool IM2COL>
+static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream)
 {
-    const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
-    if (p.N >= 128 && tiles128 >= 148) return launch_tc<128, 3>(p, stream);
-    return launch_tc<64, 3>(p, stream);
+    if (bn == 0) {
+        const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
+        bn = (p.N >= 128 && tiles128 >= 148) ? 128 : 64;
+    }
+    if (bn == 128) return launch_tc<128, 3, IM2COL>(p, stream);
+    return launch_tc<64, 3, IM2COL>(p, stream);
 }
 
-// standalone entry for tests / microbenchmarks: forces the tcgen05 path (error if unsupported)
+int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    const int kind = detrb_gemm_tc_kind(p);
+    if (kind == 1) return dispatch_tc<false>(p, 0, stream);
+    if (kind == 2) return dispatch_tc<true>(p, 0, stream);
+    DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc: unsupported problem");
+}
+
+// standalone entry for tests / microbenchmarks: forces the tcgen05 path (error if unsupported); bn = 64 | 128 | 0 (auto)
 extern "C" int detrb_gemm_tc_force(const detrb_igemm_t *pp, int bn, detrb_stream_t stream)
 {
     if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: null params");
     detrb_igemm_t p = *pp;
     if (p.out_stride < 1) p.out_stride = 1;
-    if (!detrb_gemm_tc_supported(p)) DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc_force: problem not supported by the tcgen05 path");
-    if (bn == 128) return launch_tc<128, 3>(p, (cudaStream_t)stream);
-    if (bn == 64) return launch_tc<64, 3>(p, (cudaStream_t)stream);
-    return detrb_gemm_tc(p, (cudaStream_t)stream);
+    const int kind = detrb_gemm_tc_kind(p);
+    if (kind == 0) DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc_force: problem not supported by the tcgen05 path");
+    if (bn != 0 && bn != 64 && bn != 128) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: bn must be 0, 64 or 128");
+    return kind == 1 ? dispatch_tc<false>(p, bn, (cudaStream_t)stream) : dispatch_tc<true>(p, bn, (cudaStream_t)stream);
 }

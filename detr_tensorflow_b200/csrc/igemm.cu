@@ -257,7 +257,10 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(!p.mask || p.ldm % 2 == 0, "detrb_igemm: ldm must be even");
     DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_igemm: drop_p");
     if (p.out_stride < 1) p.out_stride = 1;
-    if (detrb_gemm_tc_enabled() && detrb_gemm_tc_supported(p)) return detrb_gemm_tc(p, stream);   // tcgen05 / TMA / TMEM
+    if (detrb_gemm_tc_enabled()) {                                    // tcgen05 / TMA / TMEM
+        const int kind = detrb_gemm_tc_kind(p);
+        if (kind == 1 || (kind == 2 && detrb_gemm_tc_conv_enabled())) return detrb_gemm_tc(p, stream);
+    }
     const bool stem = (p.Cin == 4);
     if (stem) {
         DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4 && p.mode == 0,

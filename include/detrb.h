@@ -91,6 +91,7 @@ int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
  * (gemm_tc.cu) when enabled; everything else, and everything when disabled, runs on the mma.sync kernel (igemm.cu).
  * detrb_set_tc returns the previous setting.  detrb_gemm_tc_force runs the tcgen05 kernel or fails (tests; bn = 64|128|0). */
 int detrb_set_tc(int enable);
+int detrb_set_tc_conv(int enable);   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
 int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)
@@ -232,6 +233,12 @@ int detrb_prep_weight(const float *master, const float *fold, int N, int taps, i
 /* debug/test helper: writes the dropout keep-mask (0/1 bytes) the kernels use for an [M,N] site */
 int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
                        const uint64_t *seed_ptr, detrb_stream_t stream);
+
+/* test helper: one TMA im2col load (channelsPerPixel = 64, pixelsPerColumn = pixels) of NHWC bf16 x[B,H,W,C] dumped
+ * raw into out[pixels*128 + 1] (last byte: 1 if the load completed).  Pins the cuTensorMapEncodeIm2col conventions. */
+int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int lower_w, int lower_h, int upper_w,
+                           int upper_h, int stride, int pixels, int swizzle128, int c0, int w, int h, int n,
+                           int off_w, int off_h, uint8_t *out, detrb_stream_t stream);
 
 #ifdef __cplusplus
 }

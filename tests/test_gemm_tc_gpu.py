@@ -93,3 +93,49 @@ def test_engine_forward_with_tc_enabled(ops):
         ref = O.detr_forward(P, img)
     rel = float((out["pred_logits"].cpu() - ref["pred_logits"]).norm() / ref["pred_logits"].norm())
     assert rel < 5e-2, rel
+
+
+# ------------------------------------------------------------------------------------------------ TMA-im2col convolutions
+def conv_geom(B, ih, iw, cin, oh, ow, kh, kw, stride, pad, mode=0):
+    return dict(batch=B, IH=ih, IW=iw, Cin=cin, OH=oh, OW=ow, KH=kh, KW=kw, stride=stride, pad=pad, mode=mode)
+
+
+def _out(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,H,W,bn", [(64, 64, 3, 1, 1, 13, 19, 64), (128, 128, 3, 1, 1, 25, 42, 128),
+                                                           (128, 128, 3, 2, 1, 13, 19, 0), (256, 512, 1, 2, 0, 13, 19, 0),
+                                                           (256, 256, 3, 1, 1, 50, 84, 0), (64, 64, 3, 1, 1, 200, 334, 0)])
+def test_conv_tc_forward_and_dgrad(ops, cin, cout, k, stride, pad, H, W, bn):
+    B = 2
+    oh, ow = _out(H, k, stride, pad), _out(W, k, stride, pad)
+    x = rnd(B, H, W, cin, seed=1).to(BF)
+    w = rnd(cout, k, k, cin, scale=(k * k * cin) ** -0.5, seed=2).to(BF)
+    shift = rnd(cout, seed=3)
+    res = rnd(B, oh, ow, cout, seed=4).to(BF)
+    M, K = B * oh * ow, k * k * cin
+    y_tc = torch.zeros(B, oh, ow, cout, dtype=BF, device="cuda")
+    g = conv_geom(B, H, W, cin, oh, ow, k, k, stride, pad)
+    ops.igemm(x, w, M, cout, K, cin, K, g, bias=shift, residual=res, ldr=cout, relu=True, C=y_tc, ldc=cout, force_tc=bn)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias=shift, stride=stride, padding=pad)
+    ref = F.relu(ref.permute(0, 2, 3, 1) + res.float())
+    check("conv tc fwd", y_tc, ref, 1e-2, 2e-2)
+    if stride == 1:
+        # data gradient through the transposed gather (flipped taps), with the producer's ReLU mask
+        dy = rnd(B, oh, ow, cout, seed=5).to(BF)
+        wd = w.reshape(cout, k * k, cin).permute(2, 1, 0).contiguous()
+        mask = rnd(B, H, W, cin, seed=6).to(BF)
+        dx_a = torch.zeros(B, H, W, cin, dtype=BF, device="cuda")
+        dx_b = torch.zeros_like(dx_a)
+        gd = conv_geom(B, oh, ow, cout, H, W, k, k, stride, pad, mode=1)
+        ops.igemm(dy, wd, B * H * W, cin, k * k * cout, cout, k * k * cout, gd, mask=mask, ldm=cin, C=dx_a, ldc=cin)
+        ops.igemm(dy, wd, B * H * W, cin, k * k * cout, cout, k * k * cout, gd, mask=mask, ldm=cin, C=dx_b, ldc=cin, force_tc=bn)
+        torch.cuda.synchronize()
+        xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        o = F.conv2d(xt, w.float().permute(0, 3, 1, 2), stride=stride, padding=pad)
+        gx, = torch.autograd.grad(o, [xt], dy.float().permute(0, 3, 1, 2))
+        refd = gx.permute(0, 2, 3, 1) * (mask.float() > 0)
+        check("conv tc dgrad vs torch", dx_b, refd, 1e-2, 2e-2)
+        check("conv tc dgrad vs mma.sync", dx_b, dx_a, 1e-2, 2e-2)
