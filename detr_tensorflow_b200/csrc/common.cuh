@@ -25,7 +25,11 @@ bool detrb_gemm_tc_enabled();
 bool detrb_gemm_tc_conv_enabled();
 int detrb_gemm_tc_kind(const detrb_igemm_t &p);
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
-// tma_probe.cu / conv_tc.cu: im2col tensor maps
+// wgrad_tc.cu
+bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p);
+bool detrb_wgrad_tc_enabled();
+int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream);
+// tma_probe.cu: im2col tensor maps
 void *detrb_get_im2col_encode();
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
                           int upper_w, int upper_h, int stride, int pixels, int swizzle128);

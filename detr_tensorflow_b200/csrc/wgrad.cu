@@ -160,6 +160,12 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "detrb_wgrad: empty problem");
     DETRB_REQUIRE(p.M == p.batch * p.OH * p.OW, "detrb_wgrad: M=%d != batch*OH*OW", p.M);
     DETRB_REQUIRE(p.ldy >= ((p.N + 7) & ~7) && p.ldy % 8 == 0, "detrb_wgrad: ldy=%d must cover N=%d rounded to 8", p.ldy, p.N);
+    if (detrb_wgrad_tc_enabled() && detrb_wgrad_tc_supported(p)) {           // tcgen05 / TMA im2col / TMEM
+        int rc = detrb_wgrad_tc(p, stream);
+        if (rc) return rc;
+        if (p.dbias) return detrb_colsum(p.dY, p.ldy, p.M, p.N, p.rowscale, p.dbias, stream_);
+        return DETRB_OK;
+    }
     const bool stem = (p.Cin == 4);
     if (stem) DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4, "detrb_wgrad: stem geometry");
     else DETRB_REQUIRE(p.Cin % 8 == 0 && p.K == p.KH * p.KW * p.Cin && p.lda % 8 == 0, "detrb_wgrad: Cin=%d K=%d lda=%d", p.Cin, p.K, p.lda);

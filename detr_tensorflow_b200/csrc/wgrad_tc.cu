@@ -1,0 +1,207 @@
+// wgrad_tc.cu -- weight gradients on tcgen05:   dW[n, k] += rowscale[n] * sum_m dY[m, n] * gather(A)[m, k]
+//
+// The reduction runs over pixels m, i.e. over the *rows* of both operands as they sit in memory ([pixel][channel]).  TMA
+// lands [64 pixels x 64 channels] boxes (128-byte swizzle) and the UMMA descriptors declare both operands MN-major
+// (a_major = b_major = 1): no transposition anywhere.  The gathered operand uses the same TMA im2col tensor map as the forward
+// convolution (one box per 64-channel slice of one filter tap), so 1x1, 3x3, strided convolutions and Linear layers share the
+// kernel.  D = 128 (out channels) x 128 (k = tap*Cin + c) fp32 in TMEM; CTAs split the pixel range and merge with fp32 atomics.
+//
+// Replaces wgrad.cu (mma.sync) for every layer whose Cin is a multiple of 64 (everything but the 7x7 stem).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int WN = 128;                 // dW rows per CTA (output channels)  = UMMA M
+constexpr int WK = 128;                 // dW cols per CTA (tap*Cin + c)      = UMMA N
+constexpr int WP = 64;                  // pixels per pipeline stage (4 UMMAs of K = 16)
+constexpr int WSTAGES = 3;
+constexpr int BOX_BYTES = WP * 128;     // one [64 pixels x 64 channels] bf16 box
+constexpr int WSTAGE_BYTES = 4 * BOX_BYTES;
+constexpr int WSMEM = WSTAGES * WSTAGE_BYTES + 256 + 1024;
+constexpr int WTHREADS = 192;
+
+// MN-major 128B-swizzled operand: 64-element (128 B) rows, one per K index (pixel); 8-pixel swizzle atoms 1024 B apart
+// (SBO); the next 64-channel block of the MN dimension lives one box further (LBO = BOX_BYTES).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(BOX_BYTES >> 4) << 16;                   // leading byte offset: next 64-channel block
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset: next 8 pixels
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+// kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t WIDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WK >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
+
+template <bool IM2COL>
+__global__ void __launch_bounds__(WTHREADS)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, const detrb_wgrad_t p,
+                const int pix_per_split)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + WSTAGES * WSTAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (WSTAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * WSTAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * WSTAGES + 1);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * WK, n0 = blockIdx.y * WN;
+    const int m_begin = blockIdx.z * pix_per_split;
+    const int m_end = min(p.M, m_begin + pix_per_split);
+    const int nsteps = (m_end - m_begin + WP - 1) / WP;     // >= 1 by construction of the grid
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < WSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)WK) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the two 64-wide k blocks of this tile: (tap, channel offset)
+            int tap[2], cc[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int k = k0 + j * 64;
+                tap[j] = k / p.Cin; cc[j] = k - tap[j] * p.Cin;
+            }
+            const int ohw = p.OH * p.OW;
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                const int m = m_begin + st * WP;
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                mbar_expect_tx(full_bar(stage), WSTAGE_BYTES);
+                const uint32_t dst = smem_base + stage * WSTAGE_BYTES;
+                tma_load_2d(dst, &map_y, full_bar(stage), n0, m);                         // dY[m.., n0 .. n0+64)
+                tma_load_2d(dst + BOX_BYTES, &map_y, full_bar(stage), n0 + 64, m);
+                if (IM2COL) {
+                    const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                    const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int kh = tap[j] / p.KW, kw = tap[j] - kh * p.KW;
+                        tma_load_im2col(dst + (2 + j) * BOX_BYTES, &map_x, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    }
+                } else {
+                    tma_load_2d(dst + 2 * BOX_BYTES, &map_x, full_bar(stage), k0, m);
+                    tma_load_2d(dst + 3 * BOX_BYTES, &map_x, full_bar(stage), k0 + 64, m);
+                }
+                if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t base = smem_base + stage * WSTAGE_BYTES;
+                const uint64_t da = make_desc_mn(base), db = make_desc_mn(base + 2 * BOX_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < WP / 16; ks++)      // 16 pixels = 2 swizzle atoms = 2048 B further down the box
+                    tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
+                tc_commit(empty_bar(stage));
+                if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+        const bool row_ok = n < p.N;
+        const float sc = (row_ok && p.rowscale) ? p.rowscale[n] : 1.f;
+        float *drow = p.dW + (size_t)(row_ok ? n : 0) * p.ldw;
+#pragma unroll 1
+        for (int c0 = 0; c0 < WK; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc_wait_ld();
+            if (!row_ok) continue;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k = k0 + c0 + i;
+                if (k < p.K) atomicAdd(drow + k, __uint_as_float(r[i]) * sc);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)WK) : "memory");
+    }
+}
+
+}  // namespace
+
+bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
+{
+    if (p.Cin % 64 != 0 || p.K != p.KH * p.KW * p.Cin) return false;
+    if (p.lda % 8 != 0 || p.ldy % 8 != 0 || ((uintptr_t)p.A & 15) || ((uintptr_t)p.dY & 15)) return false;
+    if (p.KH > 16 || p.KW > 16 || p.stride > 8) return false;
+    return detrb_get_im2col_encode() != nullptr;
+}
+
+int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
+{
+    const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
+    CUtensorMap my, mx;
+    if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64))
+        DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for dY failed (M=%d N=%d ldy=%d)", p.M, p.N, p.ldy);
+    if (plain) {
+        if (!detrb_make_tiled_map(&mx, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64))
+            DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for A failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
+    } else {
+        const int lower = -p.pad, upper_w = p.pad - (p.KW - 1), upper_h = p.pad - (p.KH - 1);
+        if ((p.IW + upper_w - lower - 1) / p.stride + 1 != p.OW || (p.IH + upper_h - lower - 1) / p.stride + 1 != p.OH)
+            DETRB_FAIL(DETRB_E_SHAPE, "wgrad_tc: inconsistent conv geometry");
+        int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP, 1);
+        if (rc) return rc;
+    }
+    const int tiles = ceil_div(p.K, WK) * ceil_div(p.N, WN);
+    int splits = ceil_div(148 * 4, tiles);
+    const int max_splits = ceil_div(p.M, WP * 4);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int pix_per_split = ceil_div(ceil_div(p.M, splits), WP) * WP;
+    splits = ceil_div(p.M, pix_per_split);
+    static bool configured = false;
+    if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        configured = true;
+    }
+    dim3 grid(ceil_div(p.K, WK), ceil_div(p.N, WN), splits);
+    if (plain) wgrad_tc_kernel<false><<<grid, WTHREADS, WSMEM, stream>>>(my, mx, p, pix_per_split);
+    else       wgrad_tc_kernel<true><<<grid, WTHREADS, WSMEM, stream>>>(my, mx, p, pix_per_split);
+    DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
+    return DETRB_OK;
+}
+
+static int g_wgrad_tc_enabled = 0;
+extern "C" int detrb_set_tc_wgrad(int enable) { int old = g_wgrad_tc_enabled; g_wgrad_tc_enabled = enable; return old; }
+bool detrb_wgrad_tc_enabled() { return g_wgrad_tc_enabled != 0; }
+
+// test entry: force the tcgen05 weight-gradient kernel (no bias gradient)
+extern "C" int detrb_wgrad_tc_force(const detrb_wgrad_t *pp, detrb_stream_t stream)
+{
+    if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_wgrad_tc_force: null params");
+    if (!detrb_wgrad_tc_supported(*pp)) DETRB_FAIL(DETRB_E_SHAPE, "detrb_wgrad_tc_force: problem not supported");
+    return detrb_wgrad_tc(*pp, (cudaStream_t)stream);
+}

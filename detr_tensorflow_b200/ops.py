@@ -51,14 +51,25 @@ def set_tc(enable):
     return _lib.lib().detrb_set_tc(c_int(int(enable)))
 
 
-def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None):
+def set_tc_wgrad(enable):
+    return _lib.lib().detrb_set_tc_wgrad(c_int(int(enable)))
+
+
+def set_tc_conv(enable):
+    return _lib.lib().detrb_set_tc_conv(c_int(int(enable)))
+
+
+def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None, force_tc=False):
     p = WgradParams()
     p.A, p.lda, p.dY, p.ldy, p.M, p.N, p.K = ptr(A), lda, ptr(dY), ldy, M, N, K
     for k, v in geom.items():
         if k != "mode":
             setattr(p, k, v)
     p.rowscale, p.dW, p.ldw, p.dbias = ptr(rowscale), ptr(dW), ldw, ptr(dbias)
-    check(_lib.lib().detrb_wgrad(byref(p), _stream()))
+    if force_tc:
+        check(_lib.lib().detrb_wgrad_tc_force(byref(p), _stream()))
+    else:
+        check(_lib.lib().detrb_wgrad(byref(p), _stream()))
 
 
 def attn_fwd(Q, K, V, ldq, ldk, ldv, O, ldo, lse, B, H, Lq, Lk, scale, drop_p=0.0, seed=0, site=0, seed_ptr=None):

@@ -111,6 +111,9 @@ typedef struct {
 } detrb_wgrad_t;
 
 int detrb_wgrad(const detrb_wgrad_t *p, detrb_stream_t stream);
+/* tcgen05 weight-gradient kernel (wgrad_tc.cu; MN-major operands straight from TMA): switch + forced entry for tests */
+int detrb_set_tc_wgrad(int enable);
+int detrb_wgrad_tc_force(const detrb_wgrad_t *p, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-head attention core (transformer.py:308-345): softmax(Q K^T) V per (batch, head),

@@ -63,7 +63,8 @@ def sections(tc):
         tb[b, 1:21, :2] = torch.rand(20, 2, generator=g) * 0.8 + 0.1
         tb[b, 1:21, 2:] = torch.rand(20, 2, generator=g) * 0.48 + 0.02
         tc_[b, 1:21, 0] = torch.randint(0, 91, (20,), generator=g)
-    old = ops.set_tc(tc)
+    old = ops.set_tc(1 if tc else 0)
+    oldw = ops.set_tc_wgrad(1 if tc >= 2 else 0)
     try:
         eng.forward(img, training=True)
         eng.set_targets(tb, tc_)
@@ -75,6 +76,7 @@ def sections(tc):
         res["loss"] = float(eng.a["total"][0])
     finally:
         ops.set_tc(old)
+        ops.set_tc_wgrad(oldw)
     print(json.dumps({"tc": tc, "sections_ms": {k: round(v, 3) for k, v in res.items()}}), flush=True)
     del model, eng
     torch.cuda.empty_cache()
@@ -85,5 +87,8 @@ if __name__ == "__main__":
     if what in ("all", "gemm"):
         gemm_sweep()
     if what in ("all", "sections"):
-        sections(0)
-        sections(1)
+        for mode in (0, 1, 2):
+            try:
+                sections(mode)
+            except Exception as e:      # noqa
+                print(json.dumps({"tc": mode, "error": str(e)[:300]}), flush=True)

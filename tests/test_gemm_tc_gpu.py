@@ -139,3 +139,32 @@ def test_conv_tc_forward_and_dgrad(ops, cin, cout, k, stride, pad, H, W, bn):
         refd = gx.permute(0, 2, 3, 1) * (mask.float() > 0)
         check("conv tc dgrad vs torch", dx_b, refd, 1e-2, 2e-2)
         check("conv tc dgrad vs mma.sync", dx_b, dx_a, 1e-2, 2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 weight gradient
+@pytest.mark.parametrize("cin,cout,k,stride,pad,H,W", [(64, 64, 1, 1, 0, 13, 19), (64, 64, 3, 1, 1, 13, 19), (128, 128, 3, 2, 1, 13, 19),
+                                                       (256, 512, 1, 2, 0, 13, 19), (64, 256, 1, 1, 0, 9, 11), (256, 256, 3, 1, 1, 50, 84),
+                                                       (256, 92, 1, 1, 0, 30, 40), (2048, 256, 1, 1, 0, 25, 42)])
+def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
+    B = 2
+    oh, ow = _out(H, k, stride, pad), _out(W, k, stride, pad)
+    M, K = B * oh * ow, k * k * cin
+    x = rnd(B, H, W, cin, seed=1).to(BF)
+    ldy = (cout + 7) // 8 * 8
+    dy = torch.zeros(M, ldy, dtype=BF, device="cuda")
+    dy[:, :cout] = rnd(M, cout, seed=2).to(BF)
+    scale = rnd(cout, seed=3).abs() + 0.5
+    g = conv_geom(B, H, W, cin, oh, ow, k, k, stride, pad)
+    dW_a = torch.zeros(cout, K, dtype=F32, device="cuda")
+    dW_b = torch.zeros(cout, K, dtype=F32, device="cuda")
+    ops.wgrad(x, cin, dy, ldy, M, cout, K, g, dW_a, K, rowscale=scale)
+    ops.wgrad(x, cin, dy, ldy, M, cout, K, g, dW_b, K, rowscale=scale, force_tc=True)
+    torch.cuda.synchronize()
+    xt = x.float().permute(0, 3, 1, 2)
+    wt = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
+    o = F.conv2d(xt, wt, stride=stride, padding=pad)
+    gw, = torch.autograd.grad(o, [wt], dy[:, :cout].float().view(B, oh, ow, cout).permute(0, 3, 1, 2))
+    ref = gw.permute(0, 2, 3, 1).reshape(cout, K) * scale[:, None]
+    tol = 1e-2 * float(ref.abs().max())
+    check("wgrad tc vs torch", dW_b, ref, 1e-2, tol)
+    check("wgrad tc vs mma.sync", dW_b, dW_a, 1e-2, tol)
