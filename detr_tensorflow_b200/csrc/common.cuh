@@ -28,6 +28,7 @@ int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
 // wgrad_tc.cu
 bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p);
 bool detrb_wgrad_tc_enabled();
+bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p);
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream);
 // tma_probe.cu: im2col tensor maps
 void *detrb_get_im2col_encode();

@@ -50,8 +50,9 @@ struct SmemLayout {
 // weight tile (data gradient of a stride-1 convolution == convolution with the flipped kernel).
 template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(NTHREADS_TC)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const detrb_igemm_t p,
-               const int conv_pad, const int flip)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+               const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const int conv_pad, const int flip, const int tma_epi)
 {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -61,6 +62,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+    const uint32_t epi_bar = bar_base + 8u * (2 * STAGES + 2);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,6 +72,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
+        mbar_init(epi_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -148,6 +151,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t thresh = dropout_thresh16(p.drop_p);
         const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        if (tma_epi) {
+            // ---------- coalesced epilogue: residual / mask tiles arrive by TMA, the bf16 result leaves by TMA store.
+            // The pipeline stages are free once tmem_full fired: reuse them as [128 x 64] staging tiles (128B swizzle).
+            const uint32_t bufR = smem_base, bufM = smem_base + 16384, bufO = smem_base + 32768;
+            const bool leader = (warp == 2 && lane == 0);
+            const int row = q * 32 + lane;                    // row inside the tile == TMEM lane
+            const uint32_t row_off = (uint32_t)row * 128u;
+            const uint32_t sw = (uint32_t)(row & 7);          // 16-byte chunk c of a row lives at chunk c ^ (row % 8)
+            uint32_t parity = 0;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 64; cb++) {
+                const int nb = n0 + cb * 64;
+                if (nb >= p.N) break;                         // uniform across the CTA
+                const bool have_in = (p.residual != nullptr) || (p.mask != nullptr);
+                if (have_in) {
+                    if (leader) {
+                        mbar_expect_tx(epi_bar, ((p.residual ? 1u : 0u) + (p.mask ? 1u : 0u)) * 16384u);
+                        if (p.residual) tma_load_2d(bufR, &map_r, epi_bar, nb, m0);
+                        if (p.mask) tma_load_2d(bufM, &map_m, epi_bar, nb, m0);
+                    }
+                    mbar_wait(epi_bar, parity);
+                    parity ^= 1;
+                }
+#pragma unroll
+                for (int c16 = 0; c16 < 4; c16++) {
+                    uint32_t r[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 64 + c16 * 16), r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        const int n = nb + c16 * 16 + hf * 8;
+                        const uint32_t chunk = (uint32_t)(c16 * 2 + hf);
+                        const uint32_t soff = row_off + ((chunk ^ sw) << 4);
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hf * 8 + i]);
+                        if (p.bias && n < p.N) {
+                            float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        }
+                        float res[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) res[i] = 0.f;
+                        if (p.residual) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(bufR + soff));
+                            float2 t;
+                            t = unpack_bf16x2(u.x); res[0] = t.x; res[1] = t.y; t = unpack_bf16x2(u.y); res[2] = t.x; res[3] = t.y;
+                            t = unpack_bf16x2(u.z); res[4] = t.x; res[5] = t.y; t = unpack_bf16x2(u.w); res[6] = t.x; res[7] = t.y;
+                        }
+                        if (!(p.drop_p > 0.f)) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[i] += res[i];
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (p.mask) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(bufM + soff));
+                            float mk[8]; float2 t;
+                            t = unpack_bf16x2(u.x); mk[0] = t.x; mk[1] = t.y; t = unpack_bf16x2(u.y); mk[2] = t.x; mk[3] = t.y;
+                            t = unpack_bf16x2(u.z); mk[4] = t.x; mk[5] = t.y; t = unpack_bf16x2(u.w); mk[6] = t.x; mk[7] = t.y;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
+                        }
+                        if (p.sigmoid) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+                        }
+                        if (p.drop_p > 0.f) {
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                bool k0, k1;
+                                dropout_keep2(dropout_bits(seed, p.site, (uint32_t)m, (uint32_t)((n + i) >> 1)), thresh, k0, k1);
+                                v[i] = (k0 ? v[i] * drop_scale : 0.f) + res[i];
+                                v[i + 1] = (k1 ? v[i + 1] * drop_scale : 0.f) + res[i + 1];
+                            }
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(bufO + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to TMA
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 :: "l"(&map_c), "r"(bufO), "r"(nb), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // bufO may be overwritten afterwards
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
         bf16 *C = reinterpret_cast<bf16 *>(p.C);
         const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
         const bf16 *Mk = reinterpret_cast<const bf16 *>(p.mask);
@@ -224,6 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
+        }   // direct-store epilogue
     }
     // ---- teardown: everyone done with TMEM -> the allocating warp frees it
     tc_fence_before();
@@ -269,6 +370,8 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
     return r == CUDA_SUCCESS;
 }
 
+static int g_tma_epilogue = 1;
+
 template <int BN, int STAGES, bool IM2COL>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
 {
@@ -296,8 +399,17 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
     }
     if (!make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN))
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(W) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
+    // coalesced TMA epilogue whenever the output is a plain bf16 tile (no fp32 copy, scatter or read-modify-write)
+    CUtensorMap mc = ma, mr = ma, mm = ma;
+    int tma_epi = (p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue) ? 1 : 0;
+    if (tma_epi) {
+        bool ok = make_map(&mc, p.C, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc, TBM);
+        if (ok && p.residual) ok = make_map(&mr, p.residual, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldr, TBM);
+        if (ok && p.mask) ok = make_map(&mm, p.mask, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldm, TBM);
+        if (!ok) tma_epi = 0;
+    }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
-    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, p, conv_pad, flip);
+    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, conv_pad, flip, tma_epi);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
 }
@@ -340,6 +452,7 @@ static int g_tc_enabled = 1;      // validated on B200 (tests/test_gemm_tc_gpu.p
 extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
 bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
 
+extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
 static int g_tc_conv_enabled = 1;
 extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }
 bool detrb_gemm_tc_conv_enabled() { return g_tc_conv_enabled != 0; }

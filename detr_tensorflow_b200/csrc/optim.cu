@@ -72,7 +72,52 @@ __global__ void prep_weight_kernel(const float *master, const float *fold, int N
     if (Wd) Wd[((size_t)c * taps + t) * ldd + n] = wb;
 }
 
+// multi-tensor weight refresh: one launch for all layers.  Work item = 32x32 (n, c) tile of one filter tap of one weight;
+// the tile is read coalesced along c, written coalesced to Wf (along c) and, through a shared-memory transpose, to Wd (along n).
+__global__ void __launch_bounds__(256)
+prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
+{
+    __shared__ float tile[32][33];
+    const int t = blockIdx.x;
+    int lo = 0, hi = nslots - 1;                       // last slot whose tile_begin <= t
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const detrb_prep_desc_t d = descs[lo];
+    const int local = t - d.tile_begin;
+    const int ct = (d.Cin + 31) / 32, nt = (d.N + 31) / 32;
+    const int ci = local % ct, ni = (local / ct) % nt, tap = local / (ct * nt);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = ci * 32 + tx;
+    for (int r = ty; r < 32; r += 8) {
+        const int n = ni * 32 + r;
+        float w = 0.f;
+        if (n < d.N && c < d.Cin) {
+            w = d.master[((size_t)n * d.taps + tap) * d.Cin + c] * (d.fold ? d.fold[n] : 1.f);
+            if (d.Wf) reinterpret_cast<bf16 *>(d.Wf)[(size_t)n * d.ldf + tap * d.Cin + c] = __float2bfloat16(w);
+        }
+        tile[r][tx] = w;
+    }
+    if (!d.Wd) return;
+    __syncthreads();
+    const int n = ni * 32 + tx;
+    for (int r = ty; r < 32; r += 8) {
+        const int cc = ci * 32 + r;
+        if (cc < d.Cin && n < d.N)
+            reinterpret_cast<bf16 *>(d.Wd)[((size_t)cc * d.taps + tap) * d.ldd + n] = __float2bfloat16(tile[tx][r]);
+    }
+}
+
 }  // namespace
+
+extern "C" int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(descs && nslots > 0 && total_tiles > 0, "detrb_prep_weights_multi: bad args");
+    prep_weights_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(descs, nslots);
+    DETRB_CHECK_LAUNCH("prep_weights_multi_kernel");
+    return DETRB_OK;
+}
 
 extern "C" int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v, const int64_t *table,
                                    const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,

@@ -158,6 +158,9 @@ bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
     return detrb_get_im2col_encode() != nullptr;
 }
 
+// small token counts (transformer: M = 800 / 8400) are latency bound and faster on the mma.sync split kernel
+bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p) { return p.M >= 16384; }
+
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {
     const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
@@ -194,7 +197,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     return DETRB_OK;
 }
 
-static int g_wgrad_tc_enabled = 0;
+static int g_wgrad_tc_enabled = 1;     // validated on B200 (tests/test_gemm_tc_gpu.py::test_wgrad_tc)
 extern "C" int detrb_set_tc_wgrad(int enable) { int old = g_wgrad_tc_enabled; g_wgrad_tc_enabled = enable; return old; }
 bool detrb_wgrad_tc_enabled() { return g_wgrad_tc_enabled != 0; }
 

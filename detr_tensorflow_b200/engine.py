@@ -265,10 +265,29 @@ class Engine:
         return OrderedDict((name, self._to_ref_layout(name, self.grads)) for (name, _, _, _, _) in self.vars)
 
     def refresh_weights(self):
-        """fp32 master -> bf16 kernel-layout copies (FrozenBN scale folded in)."""
-        for s in self.slots.values():
-            ops.prep_weight(s.master, s.fold, s.N, s.taps, s.Cin, s.Wf, s.K, s.Wd, s.ldd)
+        """fp32 master -> bf16 kernel-layout copies (FrozenBN scale folded in): ONE multi-tensor launch."""
+        if getattr(self, "_prep_table", None) is None:
+            import ctypes
+            import numpy as np
+            n = len(self.slots)
+            arr = (_lib.PrepDesc * n)()
+            begin = 0
+            for i, s in enumerate(self.slots.values()):
+                d = arr[i]
+                d.master, d.fold = s.master.data_ptr(), (s.fold.data_ptr() if s.fold is not None else None)
+                d.Wf, d.Wd = s.Wf.data_ptr(), (s.Wd.data_ptr() if s.Wd is not None else None)
+                d.N, d.taps, d.Cin, d.ldf, d.ldd, d.tile_begin = s.N, s.taps, s.Cin, s.K, s.ldd, begin
+                begin += s.taps * ((s.N + 31) // 32) * ((s.Cin + 31) // 32)
+            raw = np.frombuffer(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr)), dtype=np.uint8).copy()
+            self._prep_table = torch.from_numpy(raw).to(self.device)
+            self._prep_n, self._prep_tiles = n, begin
+        if hasattr(self.lib, "detrb_prep_weights_multi"):
+            ops.prep_weights_multi(self._prep_table, self._prep_n, self._prep_tiles)
             self.launches += 1
+        else:
+            for s in self.slots.values():
+                ops.prep_weight(s.master, s.fold, s.N, s.taps, s.Cin, s.Wf, s.K, s.Wd, s.ldd)
+                self.launches += 1
 
     # ------------------------------------------------------------------------------------------ plan / buffers
     def _plan(self, B, H, W):

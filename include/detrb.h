@@ -91,7 +91,8 @@ int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
  * (gemm_tc.cu) when enabled; everything else, and everything when disabled, runs on the mma.sync kernel (igemm.cu).
  * detrb_set_tc returns the previous setting.  detrb_gemm_tc_force runs the tcgen05 kernel or fails (tests; bn = 64|128|0). */
 int detrb_set_tc(int enable);
-int detrb_set_tc_conv(int enable);   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
+int detrb_set_tc_conv(int enable);
+int detrb_set_tc_tma_epilogue(int enable);   /* coalesced TMA-load/TMA-store epilogue of the tcgen05 kernel (default on) */   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
 int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)
@@ -232,6 +233,15 @@ int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v,
  * (K = taps*Cin, zero padded to ldf) and optional data-gradient copy Wd [Cin, taps, ldd] (cols>=N zero). */
 int detrb_prep_weight(const float *master, const float *fold, int N, int taps, int Cin,
                       detrb_bf16 *Wf, int ldf, detrb_bf16 *Wd, int ldd, detrb_stream_t stream);
+
+/* The same refresh for ALL weights in one launch.  descs: DEVICE array of nslots descriptors (device pointers inside);
+ * tile_begin = exclusive prefix sum of taps * ceil(N/32) * ceil(Cin/32) over the slots; total_tiles = the full sum. */
+typedef struct {
+    const float *master; const float *fold;
+    detrb_bf16 *Wf; detrb_bf16 *Wd;
+    int N, taps, Cin, ldf, ldd, tile_begin;
+} detrb_prep_desc_t;
+int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream);
 
 /* debug/test helper: writes the dropout keep-mask (0/1 bytes) the kernels use for an [M,N] site */
 int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,

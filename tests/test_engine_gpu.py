@@ -129,3 +129,22 @@ def test_training_mode_steps_graph_and_dropout(D, setup):
     assert all(l == l and l < 1e4 for l in losses), losses
     assert int(eng.steps[0]) >= 3 and float((eng.params - before).abs().max()) > 0
     assert eng.launches_per_step > 100
+
+
+def test_multi_tensor_weight_refresh(D, setup):
+    """the single-launch refresh (prep_weights_multi) must produce exactly the per-layer layouts"""
+    O, P, img, tb, tc, cfg, model = setup
+    eng = model.engine
+    eng.refresh_weights()
+    torch.cuda.synchronize()
+    for name in ("backbone/conv1", "backbone/layer1/0/conv2", "backbone/layer3/0/downsample", "input_proj", "class_embed",
+                 "bbox_embed_2", "transformer/encoder/layer_0/self_attn/in_proj", "transformer/decoder/layer_5/linear2"):
+        s = eng.slots[name]
+        w = s.master.view(s.N, s.taps, s.Cin)
+        if s.fold is not None:
+            w = w * s.fold[:, None, None]
+        wb = w.to(torch.bfloat16)
+        assert torch.equal(s.Wf.view(s.N, s.taps, s.Cin), wb), name
+        if s.Wd is not None:
+            assert torch.equal(s.Wd[:, :, :s.N], wb.permute(2, 1, 0)), name
+            assert float(s.Wd[:, :, s.N:].float().abs().max()) == 0 if s.ldd > s.N else True

@@ -44,6 +44,28 @@ def test_gemm_tc_plain(ops, M, N, K, bn):
     check("tc bf16", C, ref, 1e-2, 1e-2)
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (1050, 256, 256, 128), (4175, 64, 256, 64), (130, 72, 64, 64), (8400, 2048, 256, 0),
+                                      (777, 256, 2048, 0)])
+def test_gemm_tc_tma_epilogue(ops, M, N, K, bn):
+    """bf16-only output -> TMA-store epilogue with TMA-loaded residual and mask tiles"""
+    A = rnd(M, K, seed=1).to(BF)
+    W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+    bias, res, mask = rnd(N, seed=3), rnd(M, N, seed=4).to(BF), rnd(M, N, seed=5).to(BF)
+    base = A.float() @ W.float().t() + bias
+    C = torch.full((M + 3, N), 7.0, dtype=BF, device="cuda")          # 3 guard rows: the store must clip at M
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, residual=res, ldr=N, relu=True, C=C, ldc=N, force_tc=bn)
+    torch.cuda.synchronize()
+    check("tma epi res+relu", C[:M], F.relu(base + res.float()), 1e-2, 1e-2)
+    assert float((C[M:].float() - 7.0).abs().max()) == 0
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, residual=res, ldr=N, mask=mask, ldm=N, mask_scale=1.5, C=C, ldc=N,
+              force_tc=bn)
+    torch.cuda.synchronize()
+    check("tma epi res+mask", C[:M], torch.where(mask.float() > 0, (base + res.float()) * 1.5, torch.zeros_like(base)), 1e-2, 1e-2)
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), C=C, ldc=N, force_tc=bn)
+    torch.cuda.synchronize()
+    check("tma epi plain", C[:M], A.float() @ W.float().t(), 1e-2, 1e-2)
+
+
 def test_gemm_tc_epilogues_match_mma_sync_kernel(ops):
     M, N, K = 1000, 256, 192
     A = rnd(M, 2 * K, seed=1).to(BF)[:, K:]            # strided A (lda = 2K)
