@@ -72,6 +72,62 @@ __global__ void prep_weight_kernel(const float *master, const float *fold, int N
     if (Wd) Wd[((size_t)c * taps + t) * ldd + n] = wb;
 }
 
+// ---- chunked variants: uniform work items {tensor, start, len} (len <= 8192, start 16-byte aligned) and float4 accesses
+__global__ void __launch_bounds__(256)
+chunk_sumsq_kernel(const float *grads, const int32_t *chunks, float *norms)
+{
+    const int t = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
+    const float4 *g4 = reinterpret_cast<const float4 *>(grads + start);
+    float acc = 0.f;
+    const int n4 = len >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) { float4 g = g4[i]; acc += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w; }
+    for (int i = (n4 << 2) + threadIdx.x; i < len; i += 256) { float g = grads[start + i]; acc += g * g; }
+    acc = warp_sum(acc);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += red[w];
+        atomicAdd(norms + t, tot);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+chunk_adam_kernel(float *params, const float *grads, float *m, float *v, const int32_t *chunks, const int32_t *lr_group,
+                  const float *lrs, const uint8_t *enabled, const int32_t *steps, const float *norms,
+                  float clipnorm, float beta1, float beta2, float eps)
+{
+    const int t = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
+    const int g = lr_group[t];
+    if (!enabled[g]) return;
+    const float norm = sqrtf(norms[t]);
+    const float coef = (clipnorm > 0.f && norm > clipnorm) ? clipnorm / norm : 1.f;
+    const float step = (float)steps[g];
+    const float lr_t = lrs[g] * sqrtf(1.f - powf(beta2, step)) / (1.f - powf(beta1, step));
+    const float ob1 = 1.f - beta1, ob2 = 1.f - beta2;
+    float4 *p4 = reinterpret_cast<float4 *>(params + start), *m4 = reinterpret_cast<float4 *>(m + start), *v4 = reinterpret_cast<float4 *>(v + start);
+    const float4 *g4 = reinterpret_cast<const float4 *>(grads + start);
+    const int n4 = len >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+        float4 gr = g4[i], mi = m4[i], vi = v4[i], pi = p4[i];
+        gr.x *= coef; gr.y *= coef; gr.z *= coef; gr.w *= coef;
+        mi.x = beta1 * mi.x + ob1 * gr.x; mi.y = beta1 * mi.y + ob1 * gr.y; mi.z = beta1 * mi.z + ob1 * gr.z; mi.w = beta1 * mi.w + ob1 * gr.w;
+        vi.x = beta2 * vi.x + ob2 * gr.x * gr.x; vi.y = beta2 * vi.y + ob2 * gr.y * gr.y;
+        vi.z = beta2 * vi.z + ob2 * gr.z * gr.z; vi.w = beta2 * vi.w + ob2 * gr.w * gr.w;
+        pi.x -= lr_t * mi.x / (sqrtf(vi.x) + eps); pi.y -= lr_t * mi.y / (sqrtf(vi.y) + eps);
+        pi.z -= lr_t * mi.z / (sqrtf(vi.z) + eps); pi.w -= lr_t * mi.w / (sqrtf(vi.w) + eps);
+        m4[i] = mi; v4[i] = vi; p4[i] = pi;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < len; i += 256) {
+        float gr = grads[start + i] * coef;
+        float mi = beta1 * m[start + i] + ob1 * gr, vi = beta2 * v[start + i] + ob2 * gr * gr;
+        m[start + i] = mi; v[start + i] = vi;
+        params[start + i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
 // multi-tensor weight refresh: one launch for all layers.  Work item = 32x32 (n, c) tile of one filter tap of one weight;
 // the tile is read coalesced along c, written coalesced to Wf (along c) and, through a shared-memory transpose, to Wd (along n).
 __global__ void __launch_bounds__(256)
@@ -135,6 +191,24 @@ extern "C" int detrb_adam_clipnorm(float *params, const float *grads, float *m, 
     adam_update_kernel<<<dim3(T, SLICES), 256, 0, stream>>>(params, grads, m, v, table, lr_group, lrs, group_enabled, steps, norms,
                                                            clipnorm, beta1, beta2, eps);
     DETRB_CHECK_LAUNCH("adam_update_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_adam_clipnorm_chunked(float *params, const float *grads, float *m, float *v, const int32_t *chunks, int nchunks,
+                                           const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,
+                                           float clipnorm, float beta1, float beta2, float eps, int32_t *steps, float *norms,
+                                           detrb_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DETRB_REQUIRE(params && grads && m && v && chunks && lr_group && lrs && group_enabled && steps && norms, "detrb_adam_clipnorm_chunked: null pointer");
+    DETRB_REQUIRE(T > 0 && nchunks > 0, "detrb_adam_clipnorm_chunked: bad sizes");
+    adam_prologue_kernel<<<ceil_div(T > 8 ? T : 8, 256), 256, 0, stream>>>(steps, group_enabled, 8, norms, T);
+    DETRB_CHECK_LAUNCH("adam_prologue_kernel");
+    chunk_sumsq_kernel<<<nchunks, 256, 0, stream>>>(grads, chunks, norms);
+    DETRB_CHECK_LAUNCH("chunk_sumsq_kernel");
+    chunk_adam_kernel<<<nchunks, 256, 0, stream>>>(params, grads, m, v, chunks, lr_group, lrs, group_enabled, steps, norms,
+                                                   clipnorm, beta1, beta2, eps);
+    DETRB_CHECK_LAUNCH("chunk_adam_kernel");
     return DETRB_OK;
 }
 

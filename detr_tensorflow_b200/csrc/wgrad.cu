@@ -92,6 +92,8 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int k = 0; k < 4; k++) acc[i][j][k] = 0.f;
+    const bool do_bias = p.dbias != nullptr && blockIdx.x == 0 && tid < TN;     // one k-tile column of CTAs owns the bias
+    float bias_acc = 0.f;
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
@@ -108,6 +110,10 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
         }
         const bf16 *y_s = sY + (step % STAGES) * BP * LDT;
         const bf16 *a_s = sA + (step % STAGES) * BP * LDT;
+        if (do_bias) {                                    // bias gradient = column sums of dY: free ride on the staged tile
+#pragma unroll 8
+            for (int pix = 0; pix < BP; pix++) bias_acc += __bfloat162float(y_s[pix * LDT + tid]);
+        }
 #pragma unroll
         for (int kk = 0; kk < BP / 16; kk++) {
             uint32_t af[4][4], bfr[4][2];
@@ -132,6 +138,7 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
     }
     cp_async_wait<0>();
 
+    if (do_bias && n0 + tid < p.N) atomicAdd(p.dbias + n0 + tid, bias_acc * (p.rowscale ? p.rowscale[n0 + tid] : 1.f));
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -188,6 +195,5 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     if (stem) wgrad_kernel<true><<<grid, NTHREADS, smem, stream>>>(p, pix_per_split);
     else      wgrad_kernel<false><<<grid, NTHREADS, smem, stream>>>(p, pix_per_split);
     DETRB_CHECK_LAUNCH("wgrad_kernel");
-    if (p.dbias) return detrb_colsum(p.dY, p.ldy, p.M, p.N, p.rowscale, p.dbias, stream_);
-    return DETRB_OK;
+    return DETRB_OK;                                       // bias gradient fused (column sums of the staged dY tiles)
 }

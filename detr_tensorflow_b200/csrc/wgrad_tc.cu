@@ -159,7 +159,11 @@ bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 }
 
 // small token counts (transformer: M = 800 / 8400) are latency bound and faster on the mma.sync split kernel
-bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p) { return p.M >= 16384; }
+bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
+{
+    // large pixel counts (backbone) or large weight matrices (layer4 convs at M = 8400); small transformer linears stay on mma.sync
+    return p.M >= 16384 || (p.M >= 4096 && (long)p.N * p.K >= (1l << 20));
+}
 
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {

@@ -116,6 +116,10 @@ class Engine:
         self.group_enabled = torch.zeros(8, dtype=torch.uint8, device=dev)
         self.steps = torch.zeros(8, dtype=torch.int32, device=dev)
         self.norms = torch.zeros(T, dtype=F32, device=dev)
+        CH = 8192
+        chunks = [[t, o + c, min(CH, n - c)] for t, (_, o, n, _, _) in enumerate(self.vars) for c in range(0, n, CH)]
+        self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        self.nchunks = len(chunks)
         self.group_range = {}
         for g in ("backbone", "transformers"):
             offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
@@ -482,7 +486,7 @@ class Engine:
     def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
         """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
         n_rows = n_rows or s.N
-        self.launches += 2
+        self.launches += 1
         ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
                   s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:])
 
@@ -803,9 +807,16 @@ class Engine:
         en[GROUPS.index(name)] = 1
         self.group_enabled.copy_(en)
         self.launches += 3
-        ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
-                          self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
+        self._adam(grads_arena, clipnorm)
         self.refresh_weights()
+
+    def _adam(self, grads_arena, clipnorm):
+        if hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
+            ops.adam_clipnorm_chunked(self.params, grads_arena, self.adam_m, self.adam_v, self.chunks, self.nchunks, self.lr_group,
+                                      self.lrs, self.group_enabled, self.T, clipnorm, self.steps, self.norms)
+        else:
+            ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
+                              self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
 
     def allreduce_grads(self):
         """data parallel: ONE sum all-reduce over the flat gradient arena (NCCL over NVLink); no-op on one rank."""
@@ -833,8 +844,7 @@ class Engine:
     def optimizer_step(self, clipnorm):
         """aggregate_grad_and_apply's apply branch (optimizers.py:160-163) for all enabled groups."""
         self.launches += 3
-        ops.adam_clipnorm(self.params, self.grads, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
-                          self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
+        self._adam(self.grads, clipnorm)
         self.refresh_weights()
 
     # ------------------------------------------------------------------------------------------ fused fast path

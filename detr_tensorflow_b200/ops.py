@@ -167,3 +167,10 @@ def dropout_mask(out, M, N, drop_p, seed, site, seed_ptr=None):
 
 def prep_weights_multi(descs_dev, nslots, total_tiles):
     check(_lib.lib().detrb_prep_weights_multi(ptr(descs_dev), c_int(nslots), c_int(total_tiles), _stream()))
+
+
+def adam_clipnorm_chunked(params, grads, m, v, chunks, nchunks, lr_group, lrs, group_enabled, T, clipnorm, steps, norms,
+                          beta1=0.9, beta2=0.999, eps=1e-7):
+    check(_lib.lib().detrb_adam_clipnorm_chunked(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(chunks), c_int(nchunks), ptr(lr_group),
+                                                 ptr(lrs), ptr(group_enabled), c_int(T), c_float(clipnorm), c_float(beta1), c_float(beta2),
+                                                 c_float(eps), ptr(steps), ptr(norms), _stream()))

@@ -229,6 +229,13 @@ int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v,
                         float clipnorm, float beta1, float beta2, float eps,
                         int32_t *steps, float *norms, detrb_stream_t stream);
 
+/* Same step over uniform work items: chunks = DEVICE int32 [nchunks][3] = {table row, start offset in the arena (multiple of 4),
+ * length <= 8192}; tensors are cut into chunks by the host once.  float4 accesses, balanced blocks. */
+int detrb_adam_clipnorm_chunked(float *params, const float *grads, float *m, float *v, const int32_t *chunks, int nchunks,
+                                const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,
+                                float clipnorm, float beta1, float beta2, float eps, int32_t *steps, float *norms,
+                                detrb_stream_t stream);
+
 /* master fp32 weight [N, taps, Cin] (+ optional per-row fold[n]) -> bf16 forward copy Wf [N, ldf]
  * (K = taps*Cin, zero padded to ldf) and optional data-gradient copy Wd [Cin, taps, ldd] (cols>=N zero). */
 int detrb_prep_weight(const float *master, const float *fold, int N, int taps, int Cin,

@@ -477,6 +477,17 @@ def test_adam_clipnorm_and_prep_weight(ops):
     for t, (o, n) in enumerate(zip(offs, sizes)):
         close(f"adam tensor {t}", p_d[o:o + n], ref_p[t], 1e-5, 1e-6)
     close("norms", norms.cpu().sqrt(), torch.stack([G[o:o + n].norm() for o, n in zip(offs, sizes)]), 1e-4, 1e-6)
+    # chunked / vectorised variant must give the same result
+    CH = 8192
+    chunks = torch.tensor([[t, o + c, min(CH, n - c)] for t, (o, n) in enumerate(zip(offs, sizes)) for c in range(0, n, CH)], dtype=torch.int32)
+    p2, m2, v2 = dev(P.clone()), torch.zeros(total, device="cuda"), torch.zeros(total, device="cuda")
+    steps2, norms2 = torch.zeros(8, dtype=torch.int32, device="cuda"), torch.zeros(len(sizes), device="cuda")
+    for step in (1, 2, 3):
+        ops.adam_clipnorm_chunked(p2, g_d, m2, v2, dev(chunks), chunks.shape[0], dev(grp), dev(lrs), dev(en), len(sizes), 0.1, steps2, norms2)
+    torch.cuda.synchronize()
+    close("chunked adam params", p2, p_d, 1e-6, 1e-7)
+    close("chunked adam v", v2, v_d, 1e-5, 1e-12)
+    assert steps2.cpu()[:3].tolist() == [3, 3, 0]
     # prep_weight
     N, taps, Cin = 96, 9, 64
     master = dev(rnd(N, taps, Cin, seed=4))
