@@ -335,6 +335,324 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ================================================================================================ persistent variant
+// One CTA per SM loops over output tiles; every latency is overlapped across tiles:
+//   warp 0   TMA producer for the A / W stages (4-deep ring that runs ahead across tile boundaries)
+//   warp 1   MMA issuer; accumulators ping-pong between two TMEM buffers (tmem_full / tmem_empty barriers)
+//   warp 2   TMEM allocator
+//   warp 3   TMA producer for the residual / mask tiles of the NEXT epilogue (resid_full / resid_empty barriers)
+//   warps 4-7  epilogue: tcgen05.ld -> fused math -> swizzled smem staging (double buffered) -> TMA store
+// The memory-bound layers of the backbone (K = 64..256: one to four k-blocks per tile) are limited by per-CTA latency chains
+// in the one-tile-per-CTA kernel above; here the TMA queue never drains between tiles.
+constexpr int PSTAGES = 4;
+constexpr int NTHREADS_P = 256;
+
+template <int BN>
+struct PLayout {
+    static constexpr int A_BYTES = TBM * TBK * 2;
+    static constexpr int B_BYTES = BN * TBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NCH = BN / 64;                                   // 64-column chunks per tile
+    static constexpr int RBUF = PSTAGES * STAGE_BYTES;                    // residual tile  [NCH][128 x 64]
+    static constexpr int MBUF = RBUF + NCH * 16384;                       // mask tile
+    static constexpr int OBUF = MBUF + NCH * 16384;                       // output staging, 2 x [128 x 64]
+    static constexpr int BAR_OFF = OBUF + 2 * 16384;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y; t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y; t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+// fused epilogue arithmetic on 8 consecutive columns n..n+7 of row m (same order as igemm.cu)
+__device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], const float (&mk)[8], bool has_mask,
+                                          const detrb_igemm_t &p, int m, int n, uint64_t seed, uint32_t thresh, float drop_scale)
+{
+    if (p.bias) {
+        float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (!(p.drop_p > 0.f)) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] += res[i];
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (has_mask) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
+    }
+    if (p.sigmoid) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
+    }
+    if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            bool k0, k1;
+            dropout_keep2(dropout_bits(seed, p.site, (uint32_t)m, (uint32_t)((n + i) >> 1)), thresh, k0, k1);
+            v[i] = (k0 ? v[i] * drop_scale : 0.f) + res[i];
+            v[i + 1] = (k1 ? v[i + 1] * drop_scale : 0.f) + res[i + 1];
+        }
+    }
+}
+
+template <int BN, bool IM2COL>
+__global__ void __launch_bounds__(NTHREADS_P, 1)
+gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+                const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const int conv_pad, const int flip,
+                const int tma_epi, const int n_tiles_n, const int n_tiles)
+{
+    using L = PLayout<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + L::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (PSTAGES + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (2 * PSTAGES + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * PSTAGES + 2 + a); };
+    const uint32_t resid_full = bar_base + 8u * (2 * PSTAGES + 4);
+    const uint32_t resid_empty = bar_base + 8u * (2 * PSTAGES + 5);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * PSTAGES + 6);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = p.K / TBK;
+    const bool have_in = tma_epi && (p.residual != nullptr || p.mask != nullptr);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < PSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+        mbar_init(resid_full, 1);
+        mbar_init(resid_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== A / W producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const int taps = p.KH * p.KW;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
+                int w0 = 0, h0 = 0, img = 0;
+                if (IM2COL) {
+                    const int ohw = p.OH * p.OW;
+                    img = m0 / ohw;
+                    const int rem = m0 - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                    const int st = p.mode == 0 ? p.stride : 1;
+                    w0 = ox * st - conv_pad; h0 = oy * st - conv_pad;
+                }
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                    const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+                    if (IM2COL) {
+                        const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
+                        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                        tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                        const int wtap = flip ? (taps - 1 - tap) : tap;
+                        tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), wtap * p.Cin + c0, n0);
+                    } else {
+                        tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                        tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                    }
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                mbar_wait(tmem_empty(acc), ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
+                    const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + L::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; k++)
+                        tc_mma_f16(d_addr, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    tc_commit(empty_bar(stage));
+                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full(acc));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== residual / mask producer =====================
+        if (lane == 0 && have_in) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
+                mbar_wait(resid_empty, (it & 1) ^ 1);
+                int nch = 0;
+                for (int cb = 0; cb < L::NCH; cb++) if (n0 + cb * 64 < p.N) nch++;
+                mbar_expect_tx(resid_full, (uint32_t)nch * 16384u * ((p.residual ? 1u : 0u) + (p.mask ? 1u : 0u)));
+                for (int cb = 0; cb < nch; cb++) {
+                    if (p.residual) tma_load_2d(smem_base + L::RBUF + cb * 16384, &map_r, resid_full, n0 + cb * 64, m0);
+                    if (p.mask) tma_load_2d(smem_base + L::MBUF + cb * 16384, &map_m, resid_full, n0 + cb * 64, m0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const bool leader = (warp == 4 && lane == 0);
+        const uint32_t thresh = dropout_thresh16(p.drop_p);
+        const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+        const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        bf16 *C = reinterpret_cast<bf16 *>(p.C);
+        const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
+        const bf16 *Mk = reinterpret_cast<const bf16 *>(p.mask);
+        int it = 0, ob = 0;                                    // ob: output staging buffer toggle
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
+            const int acc = it & 1;
+            const int m = m0 + row;
+            const bool row_ok = m < p.M;
+            mbar_wait(tmem_full(acc), (it >> 1) & 1);
+            tc_fence_after();
+            if (have_in) mbar_wait(resid_full, it & 1);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            if (tma_epi) {
+#pragma unroll 1
+                for (int cb = 0; cb < L::NCH; cb++) {
+                    const int nb = n0 + cb * 64;
+                    if (nb >= p.N) break;
+                    const uint32_t obuf = smem_base + L::OBUF + ob * 16384;
+                    // the TMA store that last read this staging buffer (two chunks ago) must have finished reading it
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int c16 = 0; c16 < 4; c16++) {
+                        uint32_t r[16];
+                        tc_ld16(t_addr + (uint32_t)(cb * 64 + c16 * 16), r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) {
+                            const int n = nb + c16 * 16 + hf * 8;
+                            const uint32_t soff = row_off + (((uint32_t)(c16 * 2 + hf) ^ sw) << 4);
+                            float v[8], res[8], mk[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) { v[i] = __uint_as_float(r[hf * 8 + i]); res[i] = 0.f; mk[i] = 1.f; }
+                            if (p.residual) {
+                                uint4 u;
+                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                             : "r"(smem_base + L::RBUF + cb * 16384 + soff));
+                                unpack8(u, res);
+                            }
+                            if (p.mask) {
+                                uint4 u;
+                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                             : "r"(smem_base + L::MBUF + cb * 16384 + soff));
+                                unpack8(u, mk);
+                            }
+                            if (n < p.N) epi_math8(v, res, mk, p.mask != nullptr, p, m, n, seed, thresh, drop_scale);
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(obuf + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (leader) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     :: "l"(&map_c), "r"(obuf), "r"(nb), "r"(m0) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ob ^= 1;
+                }
+            } else {
+                // direct stores (fp32 copy, strided scatter, read-modify-write): rare, small launches
+                size_t orow = m;
+                if (row_ok && p.out_stride > 1) {
+                    const int ohw = p.OH * p.OW;
+                    int b = m / ohw, rem = m - b * ohw;
+                    int oy = rem / p.OW, ox = rem - oy * p.OW;
+                    orow = ((size_t)b * p.SH + (size_t)oy * p.out_stride) * p.SW + (size_t)ox * p.out_stride;
+                }
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t r[16];
+                    tc_ld16(t_addr + (uint32_t)c0, r);
+                    tc_wait_ld();
+                    if (!row_ok || n0 + c0 >= p.N) continue;
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        const int n = n0 + c0 + hf * 8;
+                        if (n >= p.N) continue;
+                        float v[8], res[8], mk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { v[i] = __uint_as_float(r[hf * 8 + i]); res[i] = 0.f; mk[i] = 1.f; }
+                        if (R) unpack8(*reinterpret_cast<const uint4 *>(R + orow * p.ldr + n), res);
+                        if (Mk) unpack8(*reinterpret_cast<const uint4 *>(Mk + orow * p.ldm + n), mk);
+                        epi_math8(v, res, mk, Mk != nullptr, p, m, n, seed, thresh, drop_scale);
+                        if (C) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(C + orow * p.ldc + n);
+                            if (p.accumulate) {
+                                float old[8];
+                                unpack8(*dst, old);
+#pragma unroll
+                                for (int i = 0; i < 8; i++) v[i] += old[i];
+                            }
+                            uint4 o;
+                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                            *dst = o;
+                        }
+                        if (p.Cf) {
+                            float4 *dst = reinterpret_cast<float4 *>(p.Cf + orow * p.ldcf + n);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        }
+                    }
+                }
+            }
+            // this warp is done with the accumulator and with the residual / mask tile of this output tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(tmem_empty(acc));
+                if (have_in) mbar_arrive(resid_empty);
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -371,6 +689,7 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
 }
 
 static int g_tma_epilogue = 1;
+static int g_tc_persistent = 0;
 
 template <int BN, int STAGES, bool IM2COL>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
@@ -408,6 +727,23 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
         if (ok && p.mask) ok = make_map(&mm, p.mask, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldm, TBM);
         if (!ok) tma_epi = 0;
     }
+    if (g_tc_persistent) {
+        using PL = PLayout<BN>;
+        static bool pconfigured = false;
+        static int num_sms = 148;
+        if (!pconfigured) {
+            DETRB_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            pconfigured = true;
+        }
+        const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
+        const int grid_p = ntiles < num_sms ? ntiles : num_sms;
+        gemm_tcp_kernel<BN, IM2COL><<<grid_p, NTHREADS_P, PL::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, conv_pad, flip, tma_epi, ntn, ntiles);
+        DETRB_CHECK_LAUNCH("gemm_tcp_kernel");
+        return DETRB_OK;
+    }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
     gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, conv_pad, flip, tma_epi);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
@@ -437,7 +773,7 @@ static bool aligned_epilogue(const detrb_igemm_t &p)
 int detrb_gemm_tc_kind(const detrb_igemm_t &p)
 {
     if (p.K % TBK != 0 || p.lda % 8 != 0 || ((uintptr_t)p.A & 15) || !aligned_epilogue(p)) return 0;
-    const bool plain = p.mode == 0 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && p.Cin == p.K;
+    const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && p.Cin == p.K;   // mode 0 and 1 coincide
     if (plain) return get_encode_fn() != nullptr ? 1 : 0;
     if (p.Cin % TBK != 0 || p.K != p.KH * p.KW * p.Cin) return 0;
     if (p.mode == 1 && p.stride != 1) return 0;             // transposed gather of a strided conv stays on igemm.cu
@@ -452,6 +788,7 @@ static int g_tc_enabled = 1;      // validated on B200 (tests/test_gemm_tc_gpu.p
 extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
 bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
 
+extern "C" int detrb_set_tc_persistent(int enable) { int old = g_tc_persistent; g_tc_persistent = enable; return old; }
 extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
 static int g_tc_conv_enabled = 1;
 extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }

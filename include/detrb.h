@@ -92,7 +92,8 @@ int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
  * detrb_set_tc returns the previous setting.  detrb_gemm_tc_force runs the tcgen05 kernel or fails (tests; bn = 64|128|0). */
 int detrb_set_tc(int enable);
 int detrb_set_tc_conv(int enable);
-int detrb_set_tc_tma_epilogue(int enable);   /* coalesced TMA-load/TMA-store epilogue of the tcgen05 kernel (default on) */   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
+int detrb_set_tc_tma_epilogue(int enable);
+int detrb_set_tc_persistent(int enable);     /* persistent tile loop (one CTA per SM, epilogue overlapped with the next main loop) */   /* coalesced TMA-load/TMA-store epilogue of the tcgen05 kernel (default on) */   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
 int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)

@@ -34,14 +34,16 @@ def gemm_sweep():
         A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         Wt = torch.randn(N, K, device="cuda").to(torch.bfloat16)
         C = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        R = torch.randn(M, N, device="cuda").to(torch.bfloat16)
         bias = torch.zeros(N, device="cuda")
         row = {"M": M, "N": N, "K": K}
-        for name, tc in (("mma_sync", None), ("tcgen05", 0)):
+        for name, tc in (("tc_1tile", 0), ("tc_persist", 0)):
+            ops.set_tc_persistent(1 if name == "tc_persist" else 0)
             try:
-                us = time_fn(lambda: ops.igemm(A, Wt, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, force_tc=tc))
+                us = time_fn(lambda: ops.igemm(A, Wt, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, residual=R, ldr=N, C=C, ldc=N, force_tc=tc))
                 row[name + "_us"] = round(us, 1)
                 row[name + "_tflops"] = round(2.0 * M * N * K / us / 1e6, 1)
-                row[name + "_gbs"] = round((M * K + N * K + M * N) * 2 / us / 1e3, 0)
+                row[name + "_gbs"] = round((M * K + N * K + 2 * M * N) * 2 / us / 1e3, 0)
             except Exception as e:      # noqa
                 row[name + "_err"] = str(e)[:100]
         out.append(row)
@@ -65,6 +67,7 @@ def sections(tc):
         tc_[b, 1:21, 0] = torch.randint(0, 91, (20,), generator=g)
     old = ops.set_tc(1 if tc else 0)
     oldw = ops.set_tc_wgrad(1 if tc >= 2 else 0)
+    oldp = ops.set_tc_persistent(1 if tc >= 3 else 0)
     try:
         eng.forward(img, training=True)
         eng.set_targets(tb, tc_)
@@ -77,6 +80,7 @@ def sections(tc):
     finally:
         ops.set_tc(old)
         ops.set_tc_wgrad(oldw)
+        ops.set_tc_persistent(oldp)
     print(json.dumps({"tc": tc, "sections_ms": {k: round(v, 3) for k, v in res.items()}}), flush=True)
     del model, eng
     torch.cuda.empty_cache()
@@ -87,7 +91,7 @@ if __name__ == "__main__":
     if what in ("all", "gemm"):
         gemm_sweep()
     if what in ("all", "sections"):
-        for mode in (0, 1, 2):
+        for mode in (2, 3):
             try:
                 sections(mode)
             except Exception as e:      # noqa

@@ -7,13 +7,15 @@ pytestmark = pytest.mark.gpu
 BF, F32 = torch.bfloat16, torch.float32
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=["one-tile-per-CTA", "persistent"])
+def ops(request):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from detr_tensorflow_b200 import _lib, ops as o
     _lib.check(_lib.lib().detrb_check_device())
-    return o
+    old = o.set_tc_persistent(1 if request.param == "persistent" else 0)
+    yield o
+    o.set_tc_persistent(old)
 
 
 def rnd(*shape, scale=1.0, seed=0):
