@@ -36,6 +36,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// convolution side-band for the IM2COL kernels: effective padding and, per im2col tap, the weight tap to pair it with
+// (identity: forward; reversed: stride-1 data gradient; sparse: one parity class of a stride-2 data gradient)
+struct ConvAux { int pad; int wtap[16]; };
+
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int A_BYTES = TBM * TBK * 2;
@@ -46,13 +50,12 @@ struct SmemLayout {
 };
 
 // IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
-// 3x3 / strided / transposed-stride-1); `conv_pad` is the effective padding and `flip` reverses the tap order of the
-// weight tile (data gradient of a stride-1 convolution == convolution with the flipped kernel).
+// 3x3 / strided / transposed); `aux` carries the effective padding and the im2col-tap -> weight-tap map.
 template <int BN, int STAGES, bool IM2COL>
 __global__ void __launch_bounds__(NTHREADS_TC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const int conv_pad, const int flip, const int tma_epi)
+               const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux, const int tma_epi)
 {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -94,9 +97,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 img = m0 / ohw;
                 const int rem = m0 - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                 const int st = p.mode == 0 ? p.stride : 1;
-                w0 = ox * st - conv_pad; h0 = oy * st - conv_pad;
+                w0 = ox * st - aux.pad; h0 = oy * st - aux.pad;
             }
-            const int taps = p.KH * p.KW;
             for (int kb = 0; kb < nk; kb++) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
@@ -105,8 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
                     tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
-                    const int wtap = flip ? (taps - 1 - tap) : tap;
-                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), wtap * p.Cin + c0, n0);
+                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
                 } else {
                     tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
                     tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
@@ -246,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the reads
         } else {
         bf16 *C = reinterpret_cast<bf16 *>(p.C);
         const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
@@ -407,7 +408,7 @@ template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-                const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const int conv_pad, const int flip,
+                const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux,
                 const int tma_epi, const int n_tiles_n, const int n_tiles)
 {
     using L = PLayout<BN>;
@@ -447,7 +448,6 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ===================== A / W producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const int taps = p.KH * p.KW;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
                 int w0 = 0, h0 = 0, img = 0;
@@ -456,7 +456,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     img = m0 / ohw;
                     const int rem = m0 - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                     const int st = p.mode == 0 ? p.stride : 1;
-                    w0 = ox * st - conv_pad; h0 = oy * st - conv_pad;
+                    w0 = ox * st - aux.pad; h0 = oy * st - aux.pad;
                 }
                 for (int kb = 0; kb < nk; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -466,8 +466,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
                         const int kh = tap / p.KW, kw = tap - kh * p.KW;
                         tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
-                        const int wtap = flip ? (taps - 1 - tap) : tap;
-                        tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), wtap * p.Cin + c0, n0);
+                        tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
                     } else {
                         tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
                         tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
@@ -691,8 +690,10 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
 static int g_tma_epilogue = 1;
 static int g_tc_persistent = 0;
 
+struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
+
 template <int BN, int STAGES, bool IM2COL>
-int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
+int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
     using L = SmemLayout<BN, STAGES>;
     static bool configured = false;
@@ -701,22 +702,33 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
         configured = true;
     }
     CUtensorMap ma, mb;
-    int conv_pad = 0, flip = 0;
+    ConvAux aux;
+    aux.pad = 0;
+    for (int i = 0; i < 16; i++) aux.wtap[i] = i;
+    uint64_t w_cols = (uint64_t)p.K;                        // columns of the weight matrix the W tensor map spans
     if (IM2COL) {
-        // forward: window origin = out*stride - pad.  transposed (stride 1): convolution of dY with the flipped kernel, pad' = K-1-pad
         const int st = p.mode == 0 ? p.stride : 1;
-        conv_pad = p.mode == 0 ? p.pad : (p.KH - 1 - p.pad);
-        flip = p.mode == 1;
-        const int lower = -conv_pad, upper_w = conv_pad - (p.KW - 1), upper_h = conv_pad - (p.KH - 1);
-        if ((p.IW + upper_w - lower - 1) / st + 1 != p.OW || (p.IH + upper_h - lower - 1) / st + 1 != p.OH)
+        int lower_w, lower_h, upper_w, upper_h;
+        if (cls) {
+            // one parity class of a stride-2 data gradient: plain window walk over dY (pad 0), sparse tap map (see below)
+            aux = cls->aux;
+            lower_w = lower_h = 0; upper_w = cls->upper_w; upper_h = cls->upper_h;
+            w_cols = (uint64_t)cls->w_cols;
+        } else {
+            // forward: window origin = out*stride - pad.  transposed (stride 1): convolution of dY with the flipped kernel, pad' = K-1-pad
+            aux.pad = p.mode == 0 ? p.pad : (p.KH - 1 - p.pad);
+            if (p.mode == 1) for (int i = 0; i < p.KH * p.KW; i++) aux.wtap[i] = p.KH * p.KW - 1 - i;
+            lower_w = lower_h = -aux.pad; upper_w = aux.pad - (p.KW - 1); upper_h = aux.pad - (p.KH - 1);
+        }
+        if ((p.IW + upper_w - lower_w - 1) / st + 1 != p.OW || (p.IH + upper_h - lower_h - 1) / st + 1 != p.OH)
             DETRB_FAIL(DETRB_E_SHAPE, "gemm_tc im2col: inconsistent conv geometry IH=%d IW=%d OH=%d OW=%d k=%dx%d s=%d p=%d", p.IH, p.IW,
-                       p.OH, p.OW, p.KH, p.KW, st, conv_pad);
-        int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, st, TBM, 1);
+                       p.OH, p.OW, p.KH, p.KW, st, aux.pad);
+        int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM, 1);
         if (rc) return rc;
     } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM)) {
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     }
-    if (!make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN))
+    if (!make_map(&mb, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN))
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(W) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
     // coalesced TMA epilogue whenever the output is a plain bf16 tile (no fp32 copy, scatter or read-modify-write)
     CUtensorMap mc = ma, mr = ma, mm = ma;
@@ -740,12 +752,12 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream)
         }
         const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        gemm_tcp_kernel<BN, IM2COL><<<grid_p, NTHREADS_P, PL::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, conv_pad, flip, tma_epi, ntn, ntiles);
+        gemm_tcp_kernel<BN, IM2COL><<<grid_p, NTHREADS_P, PL::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, aux, tma_epi, ntn, ntiles);
         DETRB_CHECK_LAUNCH("gemm_tcp_kernel");
         return DETRB_OK;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
-    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, conv_pad, flip, tma_epi);
+    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, aux, tma_epi);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
 }
@@ -776,7 +788,11 @@ int detrb_gemm_tc_kind(const detrb_igemm_t &p)
     const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && p.Cin == p.K;   // mode 0 and 1 coincide
     if (plain) return get_encode_fn() != nullptr ? 1 : 0;
     if (p.Cin % TBK != 0 || p.K != p.KH * p.KW * p.Cin) return 0;
-    if (p.mode == 1 && p.stride != 1) return 0;             // transposed gather of a strided conv stays on igemm.cu
+    if (p.mode == 1 && p.stride != 1) {                     // 3x3 / stride 2 / pad 1: four parity-class sub-convolutions
+        if (p.stride == 2 && p.KH == 3 && p.KW == 3 && p.pad == 1 && p.out_stride <= 1 && !p.accumulate && !p.Cf &&
+            get_encode_fn() != nullptr && detrb_get_im2col_encode() != nullptr) return 3;
+        return 0;
+    }
     if (p.KH > 16 || p.KW > 16 || p.stride > 8) return 0;
     if ((long)p.lda * 2 * p.IW >= (1l << 40)) return 0;
     return (get_encode_fn() != nullptr && detrb_get_im2col_encode() != nullptr) ? 2 : 0;
@@ -795,14 +811,49 @@ extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc
 bool detrb_gemm_tc_conv_enabled() { return g_tc_conv_enabled != 0; }
 
 template <bool IM2COL>
-static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream)
+static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
     if (bn == 0) {
         const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
         bn = (p.N >= 128 && tiles128 >= 148) ? 128 : 64;
     }
-    if (bn == 128) return launch_tc<128, 3, IM2COL>(p, stream);
-    return launch_tc<64, 3, IM2COL>(p, stream);
+    // short k-loops (K <= 256) are latency bound: 2 stages -> 64 / 48 KB of smem -> 3-4 co-resident CTAs per SM hide each other
+    const bool shallow = (p.K / TBK) <= 4 && !g_tc_persistent;
+    if (bn == 128) return shallow ? launch_tc<128, 2, IM2COL>(p, stream, cls) : launch_tc<128, 3, IM2COL>(p, stream, cls);
+    return shallow ? launch_tc<64, 2, IM2COL>(p, stream, cls) : launch_tc<64, 3, IM2COL>(p, stream, cls);
+}
+
+// Data gradient of a 3x3 / stride-2 / pad-1 convolution as four dense stride-1 sub-convolutions over dY, one per output
+// parity class (py, px): pixel (2a+py, 2b+px) only sees the taps kh with (py + 1 - kh) even -- {1} for py = 0, {2, 0} for
+// py = 1 (dY rows a, a+1) -- so no multiply-by-zero work is issued (the generic transposed gather wastes 75 %).
+static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    static const int kmap[2][2] = {{1, -1}, {2, 0}};       // [parity][window offset] -> original tap index along that axis
+    for (int py = 0; py < 2; py++)
+        for (int px = 0; px < 2; px++) {
+            const int ny = 1 + py, nx = 1 + px;
+            const int A = (p.OH - py + 1) / 2, Bc = (p.OW - px + 1) / 2;       // rows / cols of this class in the dX grid
+            if (A <= 0 || Bc <= 0) continue;
+            detrb_igemm_t q = p;
+            q.mode = 0; q.stride = 1; q.pad = 0; q.KH = ny; q.KW = nx;
+            q.OH = A; q.OW = Bc; q.M = p.batch * A * Bc; q.K = ny * nx * p.Cin;
+            q.out_stride = 2; q.SH = p.OH; q.SW = p.OW;
+            const size_t off = (size_t)py * p.OW + px;                         // first pixel of the class
+            if (q.C) q.C = q.C + off * q.ldc;
+            if (q.Cf) q.Cf = q.Cf + off * q.ldcf;
+            if (q.mask) q.mask = q.mask + off * q.ldm;
+            if (q.residual) q.residual = q.residual + off * q.ldr;
+            ConvClass cls;
+            cls.aux.pad = 0;
+            for (int i = 0; i < 16; i++) cls.aux.wtap[i] = 0;
+            for (int ty = 0; ty < ny; ty++)
+                for (int tx = 0; tx < nx; tx++) cls.aux.wtap[ty * nx + tx] = kmap[py][ty] * 3 + kmap[px][tx];
+            cls.upper_h = A - p.IH; cls.upper_w = Bc - p.IW;
+            cls.w_cols = p.K;
+            int rc = dispatch_tc<true>(q, 0, stream, &cls);
+            if (rc) return rc;
+        }
+    return DETRB_OK;
 }
 
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
@@ -810,6 +861,7 @@ int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
     const int kind = detrb_gemm_tc_kind(p);
     if (kind == 1) return dispatch_tc<false>(p, 0, stream);
     if (kind == 2) return dispatch_tc<true>(p, 0, stream);
+    if (kind == 3) return strided_dgrad_tc(p, stream);
     DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc: unsupported problem");
 }
 
@@ -822,5 +874,6 @@ extern "C" int detrb_gemm_tc_force(const detrb_igemm_t *pp, int bn, detrb_stream
     const int kind = detrb_gemm_tc_kind(p);
     if (kind == 0) DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc_force: problem not supported by the tcgen05 path");
     if (bn != 0 && bn != 64 && bn != 128) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: bn must be 0, 64 or 128");
+    if (kind == 3) return strided_dgrad_tc(p, (cudaStream_t)stream);
     return kind == 1 ? dispatch_tc<false>(p, bn, (cudaStream_t)stream) : dispatch_tc<true>(p, bn, (cudaStream_t)stream);
 }

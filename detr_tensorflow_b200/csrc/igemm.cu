@@ -259,7 +259,7 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
     if (p.out_stride < 1) p.out_stride = 1;
     if (detrb_gemm_tc_enabled()) {                                    // tcgen05 / TMA / TMEM
         const int kind = detrb_gemm_tc_kind(p);
-        if (kind == 1 || (kind == 2 && detrb_gemm_tc_conv_enabled())) return detrb_gemm_tc(p, stream);
+        if (kind == 1 || (kind >= 2 && detrb_gemm_tc_conv_enabled())) return detrb_gemm_tc(p, stream);
     }
     const bool stem = (p.Cin == 4);
     if (stem) {

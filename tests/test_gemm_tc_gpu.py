@@ -129,7 +129,7 @@ def _out(n, k, s, p):
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,pad,H,W,bn", [(64, 64, 3, 1, 1, 13, 19, 64), (128, 128, 3, 1, 1, 25, 42, 128),
-                                                           (128, 128, 3, 2, 1, 13, 19, 0), (256, 512, 1, 2, 0, 13, 19, 0),
+                                                           (128, 128, 3, 2, 1, 13, 19, 0), (128, 128, 3, 2, 1, 12, 18, 0), (256, 256, 3, 2, 1, 100, 167, 0), (256, 512, 1, 2, 0, 13, 19, 0),
                                                            (256, 256, 3, 1, 1, 50, 84, 0), (64, 64, 3, 1, 1, 200, 334, 0)])
 def test_conv_tc_forward_and_dgrad(ops, cin, cout, k, stride, pad, H, W, bn):
     B = 2
@@ -146,8 +146,8 @@ def test_conv_tc_forward_and_dgrad(ops, cin, cout, k, stride, pad, H, W, bn):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias=shift, stride=stride, padding=pad)
     ref = F.relu(ref.permute(0, 2, 3, 1) + res.float())
     check("conv tc fwd", y_tc, ref, 1e-2, 2e-2)
-    if stride == 1:
-        # data gradient through the transposed gather (flipped taps), with the producer's ReLU mask
+    if stride == 1 or (stride == 2 and k == 3 and pad == 1):
+        # data gradient: stride 1 -> flipped-tap convolution; 3x3 stride 2 -> four parity-class sub-convolutions
         dy = rnd(B, oh, ow, cout, seed=5).to(BF)
         wd = w.reshape(cout, k * k, cin).permute(2, 1, 0).contiguous()
         mask = rnd(B, H, W, cin, seed=6).to(BF)
