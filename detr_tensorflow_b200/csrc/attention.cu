@@ -112,6 +112,7 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
     const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
     const float sl2 = p.scale * LOG2E;
     const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    const uint32_t rh[2] = {dropout_rowhash(seed, p.site, rowbase), dropout_rowhash(seed, p.site, rowbase + 8)};
 
     for (int kt = 0; kt < nkt; kt++) {
         if (kt + 1 < nkt) {
@@ -164,7 +165,7 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
                     bool k0, k1;
-                    dropout_keep2(dropout_bits(seed, p.site, rowbase + r * 8, pair), thresh, k0, k1);
+                    dropout_keep2(dropout_bits_rh(rh[r], pair), thresh, k0, k1);
                     s[j][r * 2 + 0] = k0 ? s[j][r * 2 + 0] * drop_scale : 0.f;
                     s[j][r * 2 + 1] = k1 ? s[j][r * 2 + 1] * drop_scale : 0.f;
                 }
@@ -233,6 +234,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
     __shared__ __align__(16) bf16 sQ[2][TKV * LDH];
     __shared__ __align__(16) bf16 sdO[2][TKV * LDH];
     __shared__ float sLse[2][TKV], sDelta[2][TKV];
+    __shared__ uint32_t sRh[2][TKV];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -244,6 +246,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
     const float *lse = p.lse + ((size_t)b * p.H + h) * p.Lq;
     const float *delta = p.delta + ((size_t)b * p.H + h) * p.Lq;
     const int nqt = (p.Lq + TKV - 1) / TKV;
+    const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
 
     auto load_q = [&](int st, int qt) {
         load_tile64(sQ[st], Q, p.ldq, qt * TKV, p.Lq, tid);
@@ -252,6 +255,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
             int q = qt * TKV + tid;
             sLse[st][tid] = q < p.Lq ? lse[q] * LOG2E : INFINITY;
             sDelta[st][tid] = q < p.Lq ? delta[q] : 0.f;
+            sRh[st][tid] = dropout_rowhash(seed, p.site, (uint32_t)((b * p.H + h) * p.Lq + q));
         }
     };
     load_tile64(sK, K, p.ldk, k0, p.Lk, tid);
@@ -269,7 +273,6 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int keyr[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
     const float sl2 = p.scale * LOG2E;
-    const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
 
     for (int qt = 0; qt < nqt; qt++) {
         if (qt + 1 < nqt) { load_q((qt + 1) & 1, qt + 1); cp_async_commit(); cp_async_wait<1>(); }
@@ -290,8 +293,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
                 float dpv = dpT[j][e];
                 float pd = pv;
                 if (p.drop_p > 0.f) {
-                    uint32_t row = (uint32_t)((b * p.H + h) * p.Lq + qt * TKV + ql);
-                    uint32_t bits = dropout_bits(seed, p.site, row, (uint32_t)(key >> 1));
+                    uint32_t bits = dropout_bits_rh(sRh[st][ql], (uint32_t)(key >> 1));
                     bool keep = ((key & 1) ? (bits >> 16) : (bits & 0xffffu)) >= thresh;
                     pd = keep ? pv * drop_scale : 0.f;
                     dpv = keep ? dpv * drop_scale : 0.f;
@@ -360,6 +362,7 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
     const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
     const float sl2 = p.scale * LOG2E;
     const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    const uint32_t rh[2] = {dropout_rowhash(seed, p.site, rowbase), dropout_rowhash(seed, p.site, rowbase + 8)};
 
     for (int kt = 0; kt < nkt; kt++) {
         if (kt + 1 < nkt) {
@@ -381,7 +384,7 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
                 uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
 #pragma unroll
                 for (int r = 0; r < 2; r++)
-                    dropout_keep2(dropout_bits(seed, p.site, rowbase + r * 8, pair), thresh, keep[r * 2], keep[r * 2 + 1]);
+                    dropout_keep2(dropout_bits_rh(rh[r], pair), thresh, keep[r * 2], keep[r * 2 + 1]);
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) {

@@ -98,18 +98,22 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- counter-based dropout RNG
-// 32 random bits for the counter (site, row, pair) under `seed`: two rounds of the "lowbias32"
-// integer finaliser.  One call serves two adjacent elements (16 bits each): element (row, col)
-// uses pair = col >> 1 and the low/high half for even/odd col.  keep <=> bits16 >= thresh16,
-// thresh16 = round(p * 65536).  Forward and backward regenerate identical masks from the counter.
+// 32 random bits for the counter (site, row, pair) under `seed`, from the "lowbias32" integer finaliser: one round for the
+// row (hoistable out of inner loops: dropout_rowhash) and one for the column pair.  One call serves two adjacent elements
+// (16 bits each): element (row, col) uses pair = col >> 1 and the low / high half for even / odd col.
+// keep <=> bits16 >= thresh16, thresh16 = round(p * 65536).  Forward and backward regenerate identical masks.
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
+__device__ __forceinline__ uint32_t dropout_rowhash(uint64_t seed, uint32_t site, uint32_t row) {
+    return lowbias32(row ^ (uint32_t)seed ^ (site * 0x9E3779B9U)) ^ (uint32_t)(seed >> 32);
+}
+__device__ __forceinline__ uint32_t dropout_bits_rh(uint32_t rowhash, uint32_t pair) {
+    return lowbias32(rowhash ^ (pair * 0x85EBCA77U));
+}
 __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint32_t site, uint32_t row, uint32_t pair) {
-    uint32_t h = lowbias32(row ^ (uint32_t)seed ^ (site * 0x9E3779B9U));
-    h = lowbias32(h ^ pair ^ (uint32_t)(seed >> 32));
-    return lowbias32(h + 0x6a09e667U + site);
+    return dropout_bits_rh(dropout_rowhash(seed, site, row), pair);
 }
 __host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
     return (uint32_t)(p * 65536.0f + 0.5f);

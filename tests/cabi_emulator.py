@@ -80,9 +80,8 @@ def keep_mask(rows, cols, drop_p, seed, site, seed_ptr=None):
         seed ^= int(T(seed_ptr, torch.int64, 1)[0]) & 0xffffffffffffffff
     r = np.asarray(rows, dtype=np.uint64)[:, None]
     c = np.asarray(cols, dtype=np.uint64)[None, :]
-    h = _lowbias32((r ^ (seed & 0xffffffff) ^ ((site * 0x9E3779B9) & 0xffffffff)) & 0xffffffff)
-    h = _lowbias32((h ^ (c >> 1) ^ (seed >> 32)) & 0xffffffff)
-    h = _lowbias32((h + 0x6a09e667 + site) & 0xffffffff)
+    rowhash = _lowbias32((r ^ (seed & 0xffffffff) ^ ((site * 0x9E3779B9) & 0xffffffff)) & 0xffffffff) ^ (seed >> 32)
+    h = _lowbias32((rowhash ^ (((c >> 1) * 0x85EBCA77) & 0xffffffff)) & 0xffffffff)
     bits = np.where((c & 1) == 1, h >> 16, h & 0xffff)
     thresh = int(drop_p * 65536.0 + 0.5)
     return torch.from_numpy(bits >= thresh)
