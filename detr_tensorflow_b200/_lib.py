@@ -18,7 +18,7 @@ _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", 
 _lib = None
 
 EXPORTS = [
-    "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
+    "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
     "detrb_attn_bwd", "detrb_layernorm_fwd", "detrb_layernorm_bwd", "detrb_add_rowbcast", "detrb_add",
     "detrb_image_to_nhwc4", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
     "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",

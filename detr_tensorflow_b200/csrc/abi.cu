@@ -26,3 +26,7 @@ extern "C" int detrb_check_device(void)
         DETRB_FAIL(DETRB_E_ARCH, "libdetrb is built for sm_100a only; device %d is sm_%d%d (no fallback path exists)", dev, prop.major, prop.minor);
     return DETRB_OK;
 }
+
+static int g_pdl = 1;
+bool detrb_pdl_enabled() { return g_pdl != 0; }
+extern "C" int detrb_set_pdl(int enable) { int old = g_pdl; g_pdl = enable; return old; }

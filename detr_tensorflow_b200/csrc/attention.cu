@@ -82,6 +82,8 @@ __device__ __forceinline__ void mma_p_tile(float (&o)[4][4], const float (&p)[8]
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const detrb_attn_fwd_t p)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     __shared__ __align__(16) bf16 sQ[TQ * LDH];
     __shared__ __align__(16) bf16 sK[2][TKV * LDH];
     __shared__ __align__(16) bf16 sV[2][TKV * LDH];
@@ -206,6 +208,8 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
 __global__ void attn_delta_kernel(const bf16 *O, const bf16 *dO, int ldo, int lddo, float *delta,
                                   int B, int H, int Lq)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * H * Lq) return;
     int q = idx % Lq, h = (idx / Lq) % H, b = idx / (Lq * H);
@@ -229,6 +233,8 @@ __global__ void attn_delta_kernel(const bf16 *O, const bf16 *dO, int ldo, int ld
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     __shared__ __align__(16) bf16 sK[TQ * LDH];
     __shared__ __align__(16) bf16 sV[TQ * LDH];
     __shared__ __align__(16) bf16 sQ[2][TKV * LDH];
@@ -323,6 +329,8 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     __shared__ __align__(16) bf16 sQ[TQ * LDH];
     __shared__ __align__(16) bf16 sdO[TQ * LDH];
     __shared__ __align__(16) bf16 sK[2][TKV * LDH];
@@ -419,7 +427,7 @@ extern "C" int detrb_attn_fwd(const detrb_attn_fwd_t *pp, detrb_stream_t stream_
     DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "detrb_attn_fwd: strides must be multiples of 8");
     DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_attn_fwd: drop_p");
     dim3 grid(ceil_div(p.Lq, TQ), p.H, p.B);
-    attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(p);
+    DETRB_LAUNCH(attn_fwd_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream_, p);
     DETRB_CHECK_LAUNCH("attn_fwd_kernel");
     return DETRB_OK;
 }
@@ -434,12 +442,12 @@ extern "C" int detrb_attn_bwd(const detrb_attn_bwd_t *pp, detrb_stream_t stream_
     DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 8 == 0 && p.lddo % 8 == 0,
                   "detrb_attn_bwd: strides must be multiples of 8");
     int n = p.B * p.H * p.Lq;
-    attn_delta_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
+    DETRB_LAUNCH(attn_delta_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
                                                             p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq);
     DETRB_CHECK_LAUNCH("attn_delta_kernel");
-    attn_bwd_dkv_kernel<<<dim3(ceil_div(p.Lk, TQ), p.H, p.B), 128, 0, stream>>>(p);
+    DETRB_LAUNCH(attn_bwd_dkv_kernel, dim3(dim3(ceil_div(p.Lk, TQ), p.H, p.B)), dim3(128), 0, stream, p);
     DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-    attn_bwd_dq_kernel<<<dim3(ceil_div(p.Lq, TQ), p.H, p.B), 128, 0, stream>>>(p);
+    DETRB_LAUNCH(attn_bwd_dq_kernel, dim3(dim3(ceil_div(p.Lq, TQ), p.H, p.B)), dim3(128), 0, stream, p);
     DETRB_CHECK_LAUNCH("attn_bwd_dq_kernel");
     return DETRB_OK;
 }

@@ -35,7 +35,31 @@ void *detrb_get_im2col_encode();
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
                           int upper_w, int upper_h, int stride, int pixels, int swizzle128);
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident and run its
+// prologue (barrier init, TMEM allocation, index setup) while the previous kernel of the stream drains, and only blocks in
+// pdl_wait() -- which returns once the predecessor has completed and its writes are visible -- before touching global memory.
+// ~660 dependent launches per train step: the launch gaps this removes are worth more than most kernel-level tuning.
+bool detrb_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = detrb_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define DETRB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    do { cudaError_t le_ = launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__); \
+         if (le_ != cudaSuccess) DETRB_FAIL(DETRB_E_CUDA, "launch %s: %s", #kernel, cudaGetErrorString(le_)); } while (0)
+
 // ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }

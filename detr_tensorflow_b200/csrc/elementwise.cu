@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf16 *y2, const bf16 *pos, int S,
               float *mean, float *rstd, int M)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -64,6 +66,8 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
               bf16 *dx, bf16 *dx_drop, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr,
               float *dgamma, float *dbeta, int M, int rows_per_block)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const uint64_t seed = seed_in ^ ((drop_p > 0.f && seed_ptr) ? *seed_ptr : 0ull);
     __shared__ float sg[8][D], sb[8][D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +136,8 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
 // ---------------------------------------------------------------- simple vector kernels
 __global__ void add_rowbcast_kernel(const uint4 *x, const uint4 *pos, uint4 *out, int64_t nvec, int64_t svec)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvec) return;
     float a[8], b[8];
@@ -142,6 +148,8 @@ __global__ void add_rowbcast_kernel(const uint4 *x, const uint4 *pos, uint4 *out
 }
 __global__ void add_kernel(const uint4 *x, const uint4 *y, uint4 *out, int64_t nvec)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvec) return;
     if (!y) { out[i] = x[i]; return; }
@@ -153,6 +161,8 @@ __global__ void add_kernel(const uint4 *x, const uint4 *y, uint4 *out, int64_t n
 }
 __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
     float r = img[i * 3], g = img[i * 3 + 1], b = img[i * 3 + 2];
@@ -160,6 +170,8 @@ __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix
 }
 __global__ void f32_to_bf16_kernel(const float *x, bf16 *y, int64_t n)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = __float2bfloat16(x[i]);
 }
@@ -168,6 +180,8 @@ __global__ void f32_to_bf16_kernel(const float *x, bf16 *y, int64_t n)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16 *x, int ldx, int M, int N, const float *scale, float *out, int rows_per_block)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     __shared__ float red[8][64];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int n = blockIdx.x * 64 + cx * 2;
@@ -195,6 +209,8 @@ colsum_kernel(const bf16 *x, int ldx, int M, int N, const float *scale, float *o
 // ---------------------------------------------------------------- max pool 3x3 s2 pad 1 (zero pad == -inf pad: x >= 0)
 __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int cv = C / 8;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)B * OH * OW * cv;
@@ -229,6 +245,8 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
 __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const bf16 *x, bf16 *dx,
                                    int B, int IH, int IW, int C, int OH, int OW)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int cv = C / 8;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)B * IH * IW * cv;
@@ -268,6 +286,8 @@ __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const 
 
 __global__ void dropout_mask_kernel(uint8_t *out, int M, int N, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const uint64_t seed = seed_in ^ (seed_ptr ? *seed_ptr : 0ull);
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * N) return;
@@ -284,7 +304,7 @@ extern "C" int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, cons
 {
     DETRB_REQUIRE(x && gamma && beta && y && M > 0, "detrb_layernorm_fwd: bad args");
     DETRB_REQUIRE(!y2 || (pos && S > 0), "detrb_layernorm_fwd: y2 needs pos and S");
-    ln_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, gamma, beta, (bf16 *)y, (bf16 *)y2,
+    DETRB_LAUNCH(ln_fwd_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, gamma, beta, (bf16 *)y, (bf16 *)y2,
                                                                    (const bf16 *)pos, S, mean, rstd, M);
     DETRB_CHECK_LAUNCH("ln_fwd_kernel");
     return DETRB_OK;
@@ -301,7 +321,7 @@ extern "C" int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, 
     if (blocks > 148 * 4) blocks = 148 * 4;
     int rpb = ceil_div(ceil_div(M, blocks), 8) * 8;
     blocks = ceil_div(M, rpb);
-    ln_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, (const bf16 *)dy2, (const bf16 *)x, gamma, mean, rstd,
+    DETRB_LAUNCH(ln_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, (const bf16 *)dy2, (const bf16 *)x, gamma, mean, rstd,
                                                             (bf16 *)dx, (bf16 *)dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M, rpb);
     DETRB_CHECK_LAUNCH("ln_bwd_kernel");
     return DETRB_OK;
@@ -311,7 +331,7 @@ extern "C" int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, de
 {
     DETRB_REQUIRE(x && pos && out && M > 0 && S > 0 && d % 8 == 0, "detrb_add_rowbcast: bad args");
     int64_t nvec = (int64_t)M * d / 8, svec = (int64_t)S * d / 8;
-    add_rowbcast_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x, (const uint4 *)pos, (uint4 *)out, nvec, svec);
+    DETRB_LAUNCH(add_rowbcast_kernel, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4 *)x, (const uint4 *)pos, (uint4 *)out, nvec, svec);
     DETRB_CHECK_LAUNCH("add_rowbcast_kernel");
     return DETRB_OK;
 }
@@ -320,7 +340,7 @@ extern "C" int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *o
 {
     DETRB_REQUIRE(a && out && n > 0 && n % 8 == 0, "detrb_add: bad args");
     int64_t nvec = n / 8;
-    add_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)a, (const uint4 *)b, (uint4 *)out, nvec);
+    DETRB_LAUNCH(add_kernel, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4 *)a, (const uint4 *)b, (uint4 *)out, nvec);
     DETRB_CHECK_LAUNCH("add_kernel");
     return DETRB_OK;
 }
@@ -328,7 +348,7 @@ extern "C" int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *o
 extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_stream_t stream)
 {
     DETRB_REQUIRE(img && out && npix > 0, "detrb_image_to_nhwc4: bad args");
-    image_to_nhwc4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (uint2 *)out, npix);
+    DETRB_LAUNCH(image_to_nhwc4_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint2 *)out, npix);
     DETRB_CHECK_LAUNCH("image_to_nhwc4_kernel");
     return DETRB_OK;
 }
@@ -336,7 +356,7 @@ extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t n
 extern "C" int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream)
 {
     DETRB_REQUIRE(x && y && n > 0, "detrb_f32_to_bf16: bad args");
-    f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16 *)y, n);
+    DETRB_LAUNCH(f32_to_bf16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16 *)y, n);
     DETRB_CHECK_LAUNCH("f32_to_bf16_kernel");
     return DETRB_OK;
 }
@@ -348,7 +368,7 @@ extern "C" int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const fl
     if (gy > 296) gy = 296;
     int rpb = ceil_div(M, gy);
     gy = ceil_div(M, rpb);
-    colsum_kernel<<<dim3(ceil_div(N, 64), gy), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, ldx, M, N, scale, out, rpb);
+    DETRB_LAUNCH(colsum_kernel, dim3(dim3(ceil_div(N, 64), gy)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, ldx, M, N, scale, out, rpb);
     DETRB_CHECK_LAUNCH("colsum_kernel");
     return DETRB_OK;
 }
@@ -359,7 +379,7 @@ extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *ar
     DETRB_REQUIRE(x && y && argmax && C % 8 == 0, "detrb_maxpool_fwd: bad args");
     DETRB_REQUIRE(OH == (IH + 2 - 3) / 2 + 1 && OW == (IW + 2 - 3) / 2 + 1, "detrb_maxpool_fwd: bad output size");
     int64_t total = (int64_t)B * OH * OW * (C / 8);
-    maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
+    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
     DETRB_CHECK_LAUNCH("maxpool_fwd_kernel");
     return DETRB_OK;
 }
@@ -369,7 +389,7 @@ extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, co
 {
     DETRB_REQUIRE(dy && argmax && x && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
     int64_t total = (int64_t)B * IH * IW * (C / 8);
-    maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
+    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
                                                                                           B, IH, IW, C, OH, OW);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
     return DETRB_OK;
@@ -380,7 +400,7 @@ extern "C" int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint
 {
     DETRB_REQUIRE(out && M > 0 && N > 0, "detrb_dropout_mask: bad args");
     int64_t total = (int64_t)M * N;
-    dropout_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, M, N, drop_p, seed, site, seed_ptr);
+    DETRB_LAUNCH(dropout_mask_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, out, M, N, drop_p, seed, site, seed_ptr);
     DETRB_CHECK_LAUNCH("dropout_mask_kernel");
     return DETRB_OK;
 }

@@ -82,10 +82,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -439,10 +441,12 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== A / W producer =====================
@@ -752,12 +756,12 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         }
         const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        gemm_tcp_kernel<BN, IM2COL><<<grid_p, NTHREADS_P, PL::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, aux, tma_epi, ntn, ntiles);
+        DETRB_LAUNCH((gemm_tcp_kernel<BN, IM2COL>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, tma_epi, ntn, ntiles);
         DETRB_CHECK_LAUNCH("gemm_tcp_kernel");
         return DETRB_OK;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
-    gemm_tc_kernel<BN, STAGES, IM2COL><<<grid, NTHREADS_TC, L::TOTAL, stream>>>(ma, mb, mc, mr, mm, p, aux, tma_epi);
+    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL>), dim3(grid), dim3(NTHREADS_TC), L::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, tma_epi);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
 }
@@ -814,8 +818,10 @@ template <bool IM2COL>
 static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
     if (bn == 0) {
+        // 64-wide tiles when there are too few 128-wide ones to fill the machine, and for very short k-loops (K <= 128):
+        // those tiles are pure latency chains (load -> 4-8 MMAs -> epilogue) and 4 small CTAs per SM overlap better than 3 large
         const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
-        bn = (p.N >= 128 && tiles128 >= 148) ? 128 : 64;
+        bn = (p.N >= 128 && tiles128 >= 148 && p.K > 128) ? 128 : 64;
     }
     // short k-loops (K <= 256) are latency bound: 2 stages -> 64 / 48 KB of smem -> 3-4 co-resident CTAs per SM hide each other
     const bool shallow = (p.K / TBK) <= 4 && !g_tc_persistent;

@@ -25,6 +25,8 @@ template <int BN, bool STEM>
 __global__ void __launch_bounds__(NTHREADS)
 igemm_kernel(const detrb_igemm_t p)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     constexpr int WN = (BN == 128) ? 4 : 2;      // warps along N
     constexpr int WM = 8 / WN;                   // warps along M
     constexpr int WTM = BM / WM;                 // warp tile M (64 or 32)
@@ -232,7 +234,7 @@ int launch(const detrb_igemm_t &p, cudaStream_t stream)
         configured = true;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-    igemm_kernel<BN, STEM><<<grid, NTHREADS, smem, stream>>>(p);
+    DETRB_LAUNCH((igemm_kernel<BN, STEM>), dim3(grid), dim3(NTHREADS), smem, stream, p);
     DETRB_CHECK_LAUNCH("igemm_kernel");
     return DETRB_OK;
 }

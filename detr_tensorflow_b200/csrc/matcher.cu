@@ -32,6 +32,8 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
                int64_t *p_indices, int64_t *t_indices, uint8_t *p_selector, int32_t *match, float *cost_out,
                int32_t *status)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: costT[n][Q] f32 | v[Q] f64 | spc[Q] f64 | u[MAXT] f64 | ints...
     double *v = reinterpret_cast<double *>(smem_raw);
@@ -196,6 +198,8 @@ set_loss_kernel(const float *logits, int ldl, const float *boxes, const float *t
                 const float *normalisers, float loss_scale, float *sums,
                 bf16 *d_logits, int ld_dl, bf16 *d_boxpre, int ld_db)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= L * B * Q) return;
@@ -286,6 +290,8 @@ __global__ void set_loss_finalize_kernel(const float *sums, const float *t_bbox,
                                          const float *normalisers, float loss_scale,
                                          float *losses, float *total)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float n_matched, sum_w;
     if (normalisers) { n_matched = normalisers[0]; sum_w = normalisers[1]; }
@@ -334,7 +340,7 @@ extern "C" int detrb_matcher(const float *logits, int ldl, const float *boxes, c
         DETRB_CUDA(cudaFuncSetAttribute(matcher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    matcher_kernel<<<P, 128, smem, (cudaStream_t)stream>>>(logits, ldl, boxes, t_bbox, t_class, B, Q, C,
+    DETRB_LAUNCH(matcher_kernel, dim3(P), dim3(128), smem, (cudaStream_t)stream, logits, ldl, boxes, t_bbox, t_class, B, Q, C,
                                                           fcost_class, fcost_bbox, fcost_giou,
                                                           p_indices, t_indices, p_selector, match, cost, status);
     DETRB_CHECK_LAUNCH("matcher_kernel");
@@ -353,10 +359,10 @@ extern "C" int detrb_set_loss(const float *logits, int ldl, const float *boxes, 
     DETRB_REQUIRE(!d_boxpre || (ld_db >= 4 && ld_db <= 64), "detrb_set_loss: ld_db=%d", ld_db);
     DETRB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 8 * L, stream));
     int rows = L * B * Q;
-    set_loss_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class,
+    DETRB_LAUNCH(set_loss_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class,
                                                            normalisers, loss_scale, sums, (bf16 *)d_logits, ld_dl, (bf16 *)d_boxpre, ld_db);
     DETRB_CHECK_LAUNCH("set_loss_kernel");
-    set_loss_finalize_kernel<<<1, 32, 0, stream>>>(sums, t_bbox, L, B, Q, normalisers, loss_scale, losses, total);
+    DETRB_LAUNCH(set_loss_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, t_bbox, L, B, Q, normalisers, loss_scale, losses, total);
     DETRB_CHECK_LAUNCH("set_loss_finalize_kernel");
     return DETRB_OK;
 }

@@ -9,6 +9,8 @@ constexpr int SLICES = 16;
 
 __global__ void adam_prologue_kernel(int32_t *steps, const uint8_t *enabled, int G, float *norms, int T)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < G && enabled[i]) steps[i] += 1;
     if (i < T) norms[i] = 0.f;
@@ -17,6 +19,8 @@ __global__ void adam_prologue_kernel(int32_t *steps, const uint8_t *enabled, int
 __global__ void __launch_bounds__(256)
 grad_sumsq_kernel(const float *grads, const int64_t *table, float *norms)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int t = blockIdx.x, s = blockIdx.y;
     const int64_t off = table[2 * t], n = table[2 * t + 1];
     const int64_t per = ((n + SLICES - 1) / SLICES + 3) & ~(int64_t)3;
@@ -40,6 +44,8 @@ adam_update_kernel(float *params, const float *grads, float *m, float *v, const 
                    const int32_t *lr_group, const float *lrs, const uint8_t *enabled, const int32_t *steps,
                    const float *norms, float clipnorm, float beta1, float beta2, float eps)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int t = blockIdx.x, s = blockIdx.y;
     const int g = lr_group[t];
     if (!enabled[g]) return;
@@ -62,6 +68,8 @@ adam_update_kernel(float *params, const float *grads, float *m, float *v, const 
 __global__ void prep_weight_kernel(const float *master, const float *fold, int N, int taps, int Cin,
                                    bf16 *Wf, int ldf, bf16 *Wd, int ldd)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)N * taps * Cin;
     if (idx >= total) return;
@@ -76,6 +84,8 @@ __global__ void prep_weight_kernel(const float *master, const float *fold, int N
 __global__ void __launch_bounds__(256)
 chunk_sumsq_kernel(const float *grads, const int32_t *chunks, float *norms)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int t = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
     const float4 *g4 = reinterpret_cast<const float4 *>(grads + start);
     float acc = 0.f;
@@ -99,6 +109,8 @@ chunk_adam_kernel(float *params, const float *grads, float *m, float *v, const i
                   const float *lrs, const uint8_t *enabled, const int32_t *steps, const float *norms,
                   float clipnorm, float beta1, float beta2, float eps)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     const int t = chunks[3 * blockIdx.x], start = chunks[3 * blockIdx.x + 1], len = chunks[3 * blockIdx.x + 2];
     const int g = lr_group[t];
     if (!enabled[g]) return;
@@ -133,6 +145,8 @@ chunk_adam_kernel(float *params, const float *grads, float *m, float *v, const i
 __global__ void __launch_bounds__(256)
 prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     __shared__ float tile[32][33];
     const int t = blockIdx.x;
     int lo = 0, hi = nslots - 1;                       // last slot whose tile_begin <= t
@@ -170,7 +184,7 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
 extern "C" int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream)
 {
     DETRB_REQUIRE(descs && nslots > 0 && total_tiles > 0, "detrb_prep_weights_multi: bad args");
-    prep_weights_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(descs, nslots);
+    DETRB_LAUNCH(prep_weights_multi_kernel, dim3(total_tiles), dim3(256), 0, (cudaStream_t)stream, descs, nslots);
     DETRB_CHECK_LAUNCH("prep_weights_multi_kernel");
     return DETRB_OK;
 }
@@ -184,11 +198,11 @@ extern "C" int detrb_adam_clipnorm(float *params, const float *grads, float *m, 
     DETRB_REQUIRE(params && grads && m && v && table && lr_group && lrs && group_enabled && steps && norms, "detrb_adam_clipnorm: null pointer");
     DETRB_REQUIRE(T > 0 && T <= 65535 && total > 0, "detrb_adam_clipnorm: bad sizes");
     // groups: at most 8 (the reference has 3: backbone, transformers, nlayers)
-    adam_prologue_kernel<<<ceil_div(T > 8 ? T : 8, 256), 256, 0, stream>>>(steps, group_enabled, 8, norms, T);
+    DETRB_LAUNCH(adam_prologue_kernel, dim3(ceil_div((T > 8 ? T : 8), 256)), dim3(256), 0, stream, steps, group_enabled, 8, norms, T);
     DETRB_CHECK_LAUNCH("adam_prologue_kernel");
-    grad_sumsq_kernel<<<dim3(T, SLICES), 256, 0, stream>>>(grads, table, norms);
+    DETRB_LAUNCH(grad_sumsq_kernel, dim3(dim3(T, SLICES)), dim3(256), 0, stream, grads, table, norms);
     DETRB_CHECK_LAUNCH("grad_sumsq_kernel");
-    adam_update_kernel<<<dim3(T, SLICES), 256, 0, stream>>>(params, grads, m, v, table, lr_group, lrs, group_enabled, steps, norms,
+    DETRB_LAUNCH(adam_update_kernel, dim3(dim3(T, SLICES)), dim3(256), 0, stream, params, grads, m, v, table, lr_group, lrs, group_enabled, steps, norms,
                                                            clipnorm, beta1, beta2, eps);
     DETRB_CHECK_LAUNCH("adam_update_kernel");
     return DETRB_OK;
@@ -202,11 +216,11 @@ extern "C" int detrb_adam_clipnorm_chunked(float *params, const float *grads, fl
     cudaStream_t stream = (cudaStream_t)stream_;
     DETRB_REQUIRE(params && grads && m && v && chunks && lr_group && lrs && group_enabled && steps && norms, "detrb_adam_clipnorm_chunked: null pointer");
     DETRB_REQUIRE(T > 0 && nchunks > 0, "detrb_adam_clipnorm_chunked: bad sizes");
-    adam_prologue_kernel<<<ceil_div(T > 8 ? T : 8, 256), 256, 0, stream>>>(steps, group_enabled, 8, norms, T);
+    DETRB_LAUNCH(adam_prologue_kernel, dim3(ceil_div((T > 8 ? T : 8), 256)), dim3(256), 0, stream, steps, group_enabled, 8, norms, T);
     DETRB_CHECK_LAUNCH("adam_prologue_kernel");
-    chunk_sumsq_kernel<<<nchunks, 256, 0, stream>>>(grads, chunks, norms);
+    DETRB_LAUNCH(chunk_sumsq_kernel, dim3(nchunks), dim3(256), 0, stream, grads, chunks, norms);
     DETRB_CHECK_LAUNCH("chunk_sumsq_kernel");
-    chunk_adam_kernel<<<nchunks, 256, 0, stream>>>(params, grads, m, v, chunks, lr_group, lrs, group_enabled, steps, norms,
+    DETRB_LAUNCH(chunk_adam_kernel, dim3(nchunks), dim3(256), 0, stream, params, grads, m, v, chunks, lr_group, lrs, group_enabled, steps, norms,
                                                    clipnorm, beta1, beta2, eps);
     DETRB_CHECK_LAUNCH("chunk_adam_kernel");
     return DETRB_OK;
@@ -219,7 +233,7 @@ extern "C" int detrb_prep_weight(const float *master, const float *fold, int N, 
     DETRB_REQUIRE(!Wf || ldf >= taps * Cin, "detrb_prep_weight: ldf");
     DETRB_REQUIRE(!Wd || ldd >= N, "detrb_prep_weight: ldd");
     int64_t total = (int64_t)N * taps * Cin;
-    prep_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(master, fold, N, taps, Cin, (bf16 *)Wf, ldf, (bf16 *)Wd, ldd);
+    DETRB_LAUNCH(prep_weight_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, master, fold, N, taps, Cin, (bf16 *)Wf, ldf, (bf16 *)Wd, ldd);
     DETRB_CHECK_LAUNCH("prep_weight_kernel");
     return DETRB_OK;
 }

@@ -18,6 +18,8 @@ template <bool STEM>
 __global__ void __launch_bounds__(NTHREADS)
 wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
 {
+    pdl_trigger();      // let the next kernel of the stream become resident
+    pdl_wait();         // predecessor complete, its writes visible
     extern __shared__ __align__(16) unsigned char smem_raw[];
     bf16 *sY = reinterpret_cast<bf16 *>(smem_raw);          // [STAGES][BP][LDT]  dY tile  (pixel, n)
     bf16 *sA = sY + STAGES * BP * LDT;                      // [STAGES][BP][LDT]  A tile   (pixel, k)
@@ -192,8 +194,8 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
         configured = true;
     }
     dim3 grid(ceil_div(p.K, TK), ceil_div(p.N, TN), splits);
-    if (stem) wgrad_kernel<true><<<grid, NTHREADS, smem, stream>>>(p, pix_per_split);
-    else      wgrad_kernel<false><<<grid, NTHREADS, smem, stream>>>(p, pix_per_split);
+    if (stem) DETRB_LAUNCH((wgrad_kernel<true>), dim3(grid), dim3(NTHREADS), smem, stream, p, pix_per_split);
+    else      DETRB_LAUNCH((wgrad_kernel<false>), dim3(grid), dim3(NTHREADS), smem, stream, p, pix_per_split);
     DETRB_CHECK_LAUNCH("wgrad_kernel");
     return DETRB_OK;                                       // bias gradient fused (column sums of the staged dY tiles)
 }

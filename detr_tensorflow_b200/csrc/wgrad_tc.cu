@@ -63,10 +63,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)WK) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -182,7 +184,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         if (rc) return rc;
     }
     const int tiles = ceil_div(p.K, WK) * ceil_div(p.N, WN);
-    int splits = ceil_div(148 * 4, tiles);
+    int splits = ceil_div(148 * 2, tiles);               // one wave of 2 CTAs per SM: fewer fp32 atomics per gradient element
     const int max_splits = ceil_div(p.M, WP * 4);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -195,8 +197,8 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         configured = true;
     }
     dim3 grid(ceil_div(p.K, WK), ceil_div(p.N, WN), splits);
-    if (plain) wgrad_tc_kernel<false><<<grid, WTHREADS, WSMEM, stream>>>(my, mx, p, pix_per_split);
-    else       wgrad_tc_kernel<true><<<grid, WTHREADS, WSMEM, stream>>>(my, mx, p, pix_per_split);
+    if (plain) DETRB_LAUNCH((wgrad_tc_kernel<false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split);
+    else       DETRB_LAUNCH((wgrad_tc_kernel<true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split);
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;
 }

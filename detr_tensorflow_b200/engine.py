@@ -878,3 +878,39 @@ class Engine:
         self.launches_per_step = self.launches - n0
         self._graph = graph
         return graph.replay
+
+    # ------------------------------------------------------------------------------------------ graph-replayed gradient step
+    def stage_inputs(self, images, t_bbox, t_class):
+        """host/device inputs -> the engine's resident buffers (async copies on the current stream)"""
+        B, H, W, _ = images.shape
+        self._plan(B, H, W)
+        a = self.a
+        a["images"].copy_(images, non_blocking=True)
+        self.set_targets(t_bbox, t_class)
+
+    def grads_step(self, background_class, loss_scale=1.0, use_graph=True):
+        """forward(training=True) + set loss + zero_grads + backward + gradient all-reduce on the staged batch
+        (training.py:9-25).  With use_graph the launch sequence is captured once per (shape, arguments) and replayed."""
+        def body():
+            self.training = True
+            self.seed_dev.add_(1)
+            self._forward_impl()
+            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
+            self.zero_grads()
+            self.backward(train_backbone=True)
+            self.allreduce_grads()
+        if not use_graph or self.device.type != "cuda":
+            return body()
+        key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None)
+        if getattr(self, "_gs_key", None) != key:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()                                     # warm-up (kernel attribute setup, NCCL channels)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._gs_graph, self._gs_key = g, key
+        self._gs_graph.replay()

@@ -55,6 +55,10 @@ def set_tc_wgrad(enable):
     return _lib.lib().detrb_set_tc_wgrad(c_int(int(enable)))
 
 
+def set_pdl(enable):
+    return _lib.lib().detrb_set_pdl(c_int(int(enable)))
+
+
 def set_tc_persistent(enable):
     return _lib.lib().detrb_set_tc_persistent(c_int(int(enable)))
 

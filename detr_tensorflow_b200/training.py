@@ -29,10 +29,15 @@ def run_train_step(model, images, t_bbox, t_class, optimizers, config):
     """training.py:9-25: forward(training=True) -> get_losses -> / gradient_aggregate -> gradients of every group."""
     eng = model.engine
     gradient_aggregate = int(config.target_batch // config.batch_size) if config.target_batch is not None else 1
-    m_outputs, total_loss, log = _forward_loss(model, images, t_bbox, t_class, config, True, 1.0 / gradient_aggregate, True)
-    eng.zero_grads()
-    eng.backward(train_backbone=True)
-    eng.allreduce_grads()
+    t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
+    eng.stage_inputs(_dev(images, torch.float32, eng.device), t_bbox_d, _dev(t_class, torch.int64, eng.device))
+    eng.set_global_normalisers(t_bbox_d)
+    # the reference traces this function once (@tf.function, training.py:9); here the launch sequence of
+    # forward + losses + backward + gradient all-reduce is captured once per input shape as a CUDA graph and replayed
+    eng.grads_step(int(config.background_class), 1.0 / gradient_aggregate, use_graph=getattr(config, "use_cuda_graph", True))
+    m_outputs = eng.outputs()
+    total_loss, log = eng.loss_dict()
+    log = dict(log)
     gradient_steps = gather_gradient(model, optimizers, total_loss, None, config, log)
     return m_outputs, total_loss, log, gradient_steps
 

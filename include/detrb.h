@@ -42,6 +42,8 @@ int detrb_version(void);
 const char *detrb_last_error(void);
 /* fails (DETRB_E_ARCH) unless the current device is compute capability 10.x */
 int detrb_check_device(void);
+/* programmatic dependent launch between consecutive kernels of the stream (default on); returns the previous setting */
+int detrb_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear layer:  C[M,N] = epilogue( gather(A)[M,K] * W[N,K]^T )
