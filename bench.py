@@ -136,6 +136,11 @@ def run_reference(args):
     }))
 
 
+def dbg(msg):
+    if os.environ.get("DETRB_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', 0)} t={time.time():.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +181,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dbg("model built")
     # ------------------------------------------------------------------ device-resident leg (`value`)
     eng.forward(images_h, training=True)                                # plans buffers, copies the batch into HBM
     eng.set_targets(tb_h, tc_h)
@@ -190,9 +196,11 @@ def main():
         step = lambda: eng.train_step(91, cfg.gradient_norm_clipping)
     else:
         step = eng.capture_train_step(91, cfg.gradient_norm_clipping)
+    dbg("captured")
     for _ in range(Wm):
         step()
     barrier()
+    dbg("warm")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -211,6 +219,7 @@ def main():
     loss_after = float(eng.a["total"][0])
     value = world * B * K / (ms / 1e3)
 
+    dbg(f"timed leg done {ms:.1f} ms")
     # ------------------------------------------------------------------ end-to-end leg through the public API
     Ke = min(K, 10)
 
@@ -231,18 +240,20 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(t_e2e)
     h2d = images_h.numel() * 4 + tb_h.numel() * 4 + tc_h.numel() * 8
+    dbg("e2e leg done")
 
     # ------------------------------------------------------------------ roofline of the dominant kernel, timed live
+    # (every rank runs the probe steps -- they contain the gradient all-reduce -- rank 0 reports)
     roof = None
+    peak_tf, peak_hbm, how = measured_peaks()
+    probe = "backbone/layer3/1/conv2"                                   # 3x3 256->256 @50x84: the heaviest repeated conv shape
+    eng.probe_name, eng.probe_events = probe, []
+    for _ in range(3):
+        eng.train_step(91, cfg.gradient_norm_clipping)
+    torch.cuda.synchronize()
+    times = [a.elapsed_time(b) for a, b in eng.probe_events]
+    eng.probe_name = None
     if rank == 0:
-        peak_tf, peak_hbm, how = measured_peaks()
-        probe = "backbone/layer3/1/conv2"                               # 3x3 256->256 @50x84: the heaviest repeated conv shape
-        eng.probe_name, eng.probe_events = probe, []
-        for _ in range(3):
-            eng.train_step(91, cfg.gradient_norm_clipping)
-        torch.cuda.synchronize()
-        times = [a.elapsed_time(b) for a, b in eng.probe_events]
-        eng.probe_name = None
         s = eng.slots[probe]
         blk = [b for b in eng.blocks if b["c2"] is s][0]
         M = B * blk["out_hw"][0] * blk["out_hw"][1]
@@ -252,7 +263,7 @@ def main():
                 "achieved": flops / t_k / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / t_k / 1e12 / peak_tf,
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
                 "flops_per_launch": flops, "us_per_launch": t_k * 1e6,
-                "whole_step": {"achieved": TRAIN_GFLOP_PER_IMAGE * 1e9 * B * K / (ms / 1e3) / 1e12 / 1.0, "unit": "TFLOP/s (per GPU x n_gpus)",
+                "whole_step": {"achieved": TRAIN_GFLOP_PER_IMAGE * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
                                "frac": TRAIN_GFLOP_PER_IMAGE * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf}}
         prof = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
         if os.path.exists(prof):

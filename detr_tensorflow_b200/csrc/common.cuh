@@ -33,7 +33,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream);
 // tma_probe.cu: im2col tensor maps
 void *detrb_get_im2col_encode();
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
-                          int upper_w, int upper_h, int stride, int pixels, int swizzle128);
+                          int upper_w, int upper_h, int stride, int pixels, int swizzle128, int channels = 64);
 
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident and run its

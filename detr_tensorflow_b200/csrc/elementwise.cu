@@ -168,6 +168,33 @@ __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix
     float r = img[i * 3], g = img[i * 3 + 1], b = img[i * 3 + 2];
     out[i] = make_uint2(pack_bf16x2(r, g), pack_bf16x2(b, 0.f));
 }
+// space-to-depth(2) of the fp32 NHWC3 image: out[b, y, x, (ry*2+rx)*3 + c] = img[b, 2y+ry, 2x+rx, c] (0 outside, 4 zero pad channels)
+// -> the 7x7 / stride-2 stem becomes a dense 4x4 / stride-1 convolution over 16-channel pixels (32 B: one TMA im2col row)
+__global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H, int W, int H2, int W2)
+{
+    pdl_trigger();
+    pdl_wait();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H2 * W2) return;
+    int x2 = i % W2; int y2 = (i / W2) % H2; int b = i / ((int64_t)W2 * H2);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.f;
+#pragma unroll
+    for (int ry = 0; ry < 2; ry++)
+#pragma unroll
+        for (int rx = 0; rx < 2; rx++) {
+            int y = 2 * y2 + ry, x = 2 * x2 + rx;
+            if (y < H && x < W) {
+                const float *px = img + (((size_t)b * H + y) * W + x) * 3;
+                v[(ry * 2 + rx) * 3 + 0] = px[0]; v[(ry * 2 + rx) * 3 + 1] = px[1]; v[(ry * 2 + rx) * 3 + 2] = px[2];
+            }
+        }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    out[i * 2] = o0; out[i * 2 + 1] = o1;
+}
 __global__ void f32_to_bf16_kernel(const float *x, bf16 *y, int64_t n)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
@@ -350,6 +377,16 @@ extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t n
     DETRB_REQUIRE(img && out && npix > 0, "detrb_image_to_nhwc4: bad args");
     DETRB_LAUNCH(image_to_nhwc4_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint2 *)out, npix);
     DETRB_CHECK_LAUNCH("image_to_nhwc4_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "detrb_image_to_s2d16: bad args");
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    int64_t n = (int64_t)B * H2 * W2;
+    DETRB_LAUNCH(image_to_s2d16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint4 *)out, B, H, W, H2, W2);
+    DETRB_CHECK_LAUNCH("image_to_s2d16_kernel");
     return DETRB_OK;
 }
 

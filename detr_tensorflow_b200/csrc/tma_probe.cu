@@ -61,9 +61,10 @@ void *detrb_get_im2col_encode()
     return fn;
 }
 
-// NHWC bf16 tensor [B,H,W,C] -> im2col tensor map (channelsPerPixel = 64, pixelsPerColumn = pixels)
+// NHWC bf16 tensor [B,H,W,C] -> im2col tensor map (channelsPerPixel = channels, pixelsPerColumn = pixels;
+// swizzle128: 0 none, 1 128-byte, 2 32-byte)
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
-                          int upper_w, int upper_h, int stride, int pixels, int swizzle128)
+                          int upper_w, int upper_h, int stride, int pixels, int swizzle128, int channels)
 {
     EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(detrb_get_im2col_encode());
     if (!fn) DETRB_FAIL(DETRB_E_CUDA, "cuTensorMapEncodeIm2col not available");
@@ -72,8 +73,8 @@ int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int
     int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(reinterpret_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides,
-                    lower, upper, 64, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) DETRB_FAIL(DETRB_E_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
     return DETRB_OK;
@@ -84,7 +85,7 @@ extern "C" int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, 
                                       int off_w, int off_h, uint8_t *out, detrb_stream_t stream)
 {
     CUtensorMap map;
-    int rc = detrb_make_im2col_map(&map, x, B, H, W, C, C, lower_w, lower_h, upper_w, upper_h, stride, pixels, swizzle128);
+    int rc = detrb_make_im2col_map(&map, x, B, H, W, C, C, lower_w, lower_h, upper_w, upper_h, stride, pixels, swizzle128, 64);
     if (rc) return rc;
     const int bytes = pixels * 64 * 2;
     static bool configured = false;

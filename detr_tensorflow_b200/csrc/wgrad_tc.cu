@@ -31,36 +31,53 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
     return d;
 }
+// MN-major operand made of [64 pixels x 32 B] boxes with 32-byte swizzle (16-channel pixels): 16-element MN blocks one box
+// (2048 B) apart (LBO), 8-pixel K atoms 256 B apart (SBO)
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(2048 >> 4) << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                                  // SWIZZLE_32B
+    return d;
+}
 // kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t WIDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
 constexpr uint32_t WIDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WK >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
 
-template <bool IM2COL>
+// C16: 16-channel pixels (space-to-depth stem, 4x4 taps): the whole K = 16 taps x 16 ch = 256 is one tile; every tap is a
+// [64 pixels x 32 B] box (32B swizzle), the UMMA N dimension is 256 and walks the 16 boxes through the leading byte offset.
+template <bool IM2COL, bool C16>
 __global__ void __launch_bounds__(WTHREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, const detrb_wgrad_t p,
-                const int pix_per_split)
+                const int pix_per_split, const int stem_mask)
 {
+    constexpr int KT = C16 ? 256 : WK;                                  // k columns of this CTA's dW tile (TMEM columns)
+    constexpr int STG = C16 ? 2 : WSTAGES;
+    constexpr int STG_BYTES = C16 ? (2 * BOX_BYTES + 16 * 2048) : WSTAGE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + WSTAGES * WSTAGE_BYTES;
+    const uint32_t bar_base = smem_base + STG * STG_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (WSTAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * WSTAGES);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * WSTAGES + 1);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STG + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STG);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STG + 1);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = blockIdx.x * WK, n0 = blockIdx.y * WN;
+    const int k0 = blockIdx.x * KT, n0 = blockIdx.y * WN;
     const int m_begin = blockIdx.z * pix_per_split;
     const int m_end = min(p.M, m_begin + pix_per_split);
     const int nsteps = (m_end - m_begin + WP - 1) / WP;     // >= 1 by construction of the grid
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < WSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STG; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)WK) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)KT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_trigger();
@@ -84,11 +101,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             for (int st = 0; st < nsteps; st++) {
                 const int m = m_begin + st * WP;
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                mbar_expect_tx(full_bar(stage), WSTAGE_BYTES);
-                const uint32_t dst = smem_base + stage * WSTAGE_BYTES;
+                mbar_expect_tx(full_bar(stage), STG_BYTES);
+                const uint32_t dst = smem_base + stage * STG_BYTES;
                 tma_load_2d(dst, &map_y, full_bar(stage), n0, m);                         // dY[m.., n0 .. n0+64)
                 tma_load_2d(dst + BOX_BYTES, &map_y, full_bar(stage), n0 + 64, m);
-                if (IM2COL) {
+                if (C16) {
+                    const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                    const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
+#pragma unroll 1
+                    for (int tp = 0; tp < 16; tp++) {
+                        const int kh = tp / p.KW, kw = tp - kh * p.KW;
+                        tma_load_im2col(dst + 2 * BOX_BYTES + tp * 2048, &map_x, full_bar(stage), 0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    }
+                } else if (IM2COL) {
                     const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                     const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
 #pragma unroll
@@ -100,7 +125,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                     tma_load_2d(dst + 2 * BOX_BYTES, &map_x, full_bar(stage), k0, m);
                     tma_load_2d(dst + 3 * BOX_BYTES, &map_x, full_bar(stage), k0 + 64, m);
                 }
-                if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == STG) { stage = 0; phase ^= 1; }
             }
         }
         __syncwarp();
@@ -110,13 +135,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             for (int st = 0; st < nsteps; st++) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t base = smem_base + stage * WSTAGE_BYTES;
-                const uint64_t da = make_desc_mn(base), db = make_desc_mn(base + 2 * BOX_BYTES);
+                const uint32_t base = smem_base + stage * STG_BYTES;
+                const uint64_t da = make_desc_mn(base);
+                if (C16) {
+                    // B: 16 taps x 16 ch, MN-major with 32B swizzle: 8-pixel atoms 256 B apart (SBO), next tap 2048 B further (LBO)
+                    const uint64_t db = make_desc_mn32(base + 2 * BOX_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < WP / 16; ks++)      // 16 pixels = 2 swizzle atoms = 2048 B further down the box
-                    tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
+                    for (int ks = 0; ks < WP / 16; ks++)  // 16 pixels: 2048 B down the dY box, 512 B down each tap box
+                        tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (512 >> 4)), WIDESC16, (st | ks) != 0);
+                } else {
+                    const uint64_t db = make_desc_mn(base + 2 * BOX_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < WP / 16; ks++)  // 16 pixels = 2 swizzle atoms = 2048 B further down the box
+                        tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
+                }
                 tc_commit(empty_bar(stage));
-                if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == STG) { stage = 0; phase ^= 1; }
             }
             tc_commit(tmem_full_bar);
         }
@@ -130,7 +164,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
         const float sc = (row_ok && p.rowscale) ? p.rowscale[n] : 1.f;
         float *drow = p.dW + (size_t)(row_ok ? n : 0) * p.ldw;
 #pragma unroll 1
-        for (int c0 = 0; c0 < WK; c0 += 16) {
+        for (int c0 = 0; c0 < KT; c0 += 16) {
             uint32_t r[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tc_wait_ld();
@@ -138,7 +172,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int k = k0 + c0 + i;
-                if (k < p.K) atomicAdd(drow + k, __uint_as_float(r[i]) * sc);
+                bool ok = k < p.K;
+                if (C16 && stem_mask) {
+                    // space-to-depth stem: column k = (ta, tb, (ry*2+rx)*3 + c) stands for the 7x7 tap (2ta+ry-1, 2tb+rx-1);
+                    // taps outside 0..6 and the 4 padding channels do not exist in the reference kernel: no gradient
+                    const int ch = k & 15, tb = (k >> 4) & 3, ta = k >> 6;
+                    const int ry = ch / 6, rx = (ch / 3) & 1, kh = 2 * ta + ry - 1, kw = 2 * tb + rx - 1;
+                    ok = ok && ch < 12 && kh >= 0 && kh <= 6 && kw >= 0 && kw <= 6;
+                }
+                if (ok) atomicAdd(drow + k, __uint_as_float(r[i]) * sc);
             }
         }
     }
@@ -146,7 +188,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)WK) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)KT) : "memory");
     }
 }
 
@@ -154,7 +196,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
 
 bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 {
-    if (p.Cin % 64 != 0 || p.K != p.KH * p.KW * p.Cin) return false;
+    const bool c16 = p.Cin == 16 && p.KH * p.KW == 16 && p.lda == 16;
+    if ((p.Cin % 64 != 0 && !c16) || p.K != p.KH * p.KW * p.Cin) return false;
     if (p.lda % 8 != 0 || p.ldy % 8 != 0 || ((uintptr_t)p.A & 15) || ((uintptr_t)p.dY & 15)) return false;
     if (p.KH > 16 || p.KW > 16 || p.stride > 8) return false;
     return detrb_get_im2col_encode() != nullptr;
@@ -169,7 +212,8 @@ bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {
-    const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
+    const bool c16 = p.Cin == 16;
+    const bool plain = !c16 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
     CUtensorMap my, mx;
     if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64))
         DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for dY failed (M=%d N=%d ldy=%d)", p.M, p.N, p.ldy);
@@ -177,28 +221,39 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         if (!detrb_make_tiled_map(&mx, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64))
             DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for A failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     } else {
-        const int lower = -p.pad, upper_w = p.pad - (p.KW - 1), upper_h = p.pad - (p.KH - 1);
-        if ((p.IW + upper_w - lower - 1) / p.stride + 1 != p.OW || (p.IH + upper_h - lower - 1) / p.stride + 1 != p.OH)
+        const int lower = -p.pad;
+        const int upper_w = (p.OW - 1) * p.stride + 1 + lower - p.IW, upper_h = (p.OH - 1) * p.stride + 1 + lower - p.IH;
+        if (upper_w > 0 || upper_h > 0 || upper_w < -16 || upper_h < -16)
             DETRB_FAIL(DETRB_E_SHAPE, "wgrad_tc: inconsistent conv geometry");
-        int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP, 1);
+        int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP,
+                                       c16 ? 2 : 1, c16 ? 16 : 64);
         if (rc) return rc;
     }
-    const int tiles = ceil_div(p.K, WK) * ceil_div(p.N, WN);
+    const int kt = c16 ? 256 : WK;
+    const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
     int splits = ceil_div(148 * 2, tiles);               // one wave of 2 CTAs per SM: fewer fp32 atomics per gradient element
     const int max_splits = ceil_div(p.M, WP * 4);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int pix_per_split = ceil_div(ceil_div(p.M, splits), WP) * WP;
     splits = ceil_div(p.M, pix_per_split);
+    constexpr int SMEM16 = 2 * (2 * BOX_BYTES + 16 * 2048) + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM16));
         configured = true;
     }
-    dim3 grid(ceil_div(p.K, WK), ceil_div(p.N, WN), splits);
-    if (plain) DETRB_LAUNCH((wgrad_tc_kernel<false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split);
-    else       DETRB_LAUNCH((wgrad_tc_kernel<true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split);
+    dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
+    const int stem_mask = (c16 && p.KH == 4 && p.KW == 4 && p.pad == 2) ? 1 : 0;
+    if (c16) {
+        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), SMEM16, stream, my, mx, p, pix_per_split, stem_mask);
+    } else if (plain) {
+        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
+    } else {
+        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
+    }
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;
 }

@@ -92,7 +92,7 @@ class Engine:
                 if p.kind == "conv":
                     kh, kw, ci, co = p.shape
                     if name == "backbone/conv1/kernel":
-                        n = co * kh * 8 * 4          # 7 x 8(padded) taps x 4(padded) channels
+                        n = co * 16 * 16             # space-to-depth form: 4 x 4 taps x 16 channels (see _stem_to_s2d)
                     else:
                         n = co * kh * kw * ci
                 else:
@@ -135,8 +135,8 @@ class Engine:
             s = Slot()
             s.name = prefix
             stem = (kname == "backbone/conv1/kernel")
-            kwp, cip = (8, 4) if stem else (kw, ci)
-            s.N, s.taps, s.Cin = co, kh * kwp, cip
+            kwp, cip = (4, 16) if stem else (kw, ci)
+            s.N, s.taps, s.Cin = co, (16 if stem else kh * kwp), cip
             s.K = s.taps * s.Cin
             s.master, s.grad = view(self.params, kname), view(self.grads, kname)
             if bias_name:
@@ -149,7 +149,7 @@ class Engine:
             if not stem:
                 s.ldd = _round_up(co, 32)
                 s.Wd = torch.zeros(ci, s.taps, s.ldd, dtype=BF16, device=dev)
-            s.geom = (kh, kw, kwp, stride, pad)
+            s.geom = (4, 4, 4, 1, 2) if stem else (kh, kw, kwp, stride, pad)
             self.slots[prefix] = s
             return s
 
@@ -226,9 +226,7 @@ class Engine:
                     kh, kw, ci, co = p.shape
                     t = t.permute(3, 0, 1, 2).contiguous()              # [co, kh, kw, ci]
                     if name == "backbone/conv1/kernel":
-                        tp = torch.zeros(co, kh, 8, 4)
-                        tp[:, :, :kw, :ci] = t
-                        t = tp
+                        t = self._stem_to_s2d(t)
                 o, n = self.layout[name]
                 self.params[o:o + n].copy_(t.reshape(-1))
         # FrozenBatchNorm2D (custom_layers.py:21-24): scale = w * rsqrt(var + eps); shift = b - mean * scale
@@ -259,11 +257,38 @@ class Engine:
         if p.kind == "conv":
             kh, kw, ci, co = p.shape
             if name == "backbone/conv1/kernel":
-                t = t.reshape(co, kh, 8, 4)[:, :, :kw, :ci]
+                t = self._stem_from_s2d(t.reshape(co, 4, 4, 16))
             else:
                 t = t.reshape(co, kh, kw, ci)
             return t.permute(1, 2, 3, 0).contiguous()
         return t.reshape(p.shape)
+
+    @staticmethod
+    def _stem_index():
+        """(ta, tb, ch) of the 4x4x16 space-to-depth kernel <-> (kh, kw, c) of the 7x7x3 kernel (resnet_backbone.py:11):
+        input row 2(oy + ta - 2) + ry = 2 oy - 3 + kh  =>  kh = 2 ta + ry - 1, likewise kw; ch = (ry*2+rx)*3 + c."""
+        idx = []
+        for ta in range(4):
+            for tb in range(4):
+                for ry in range(2):
+                    for rx in range(2):
+                        kh, kw = 2 * ta + ry - 1, 2 * tb + rx - 1
+                        if 0 <= kh <= 6 and 0 <= kw <= 6:
+                            for c in range(3):
+                                idx.append((ta, tb, (ry * 2 + rx) * 3 + c, kh, kw, c))
+        return idx
+
+    def _stem_to_s2d(self, t):                      # t [co, 7, 7, 3] -> [co, 4, 4, 16]
+        out = torch.zeros(t.shape[0], 4, 4, 16, dtype=t.dtype)
+        for ta, tb, ch, kh, kw, c in Engine._stem_index():
+            out[:, ta, tb, ch] = t[:, kh, kw, c]
+        return out
+
+    def _stem_from_s2d(self, t):                    # t [co, 4, 4, 16] -> [co, 7, 7, 3]
+        out = torch.zeros(t.shape[0], 7, 7, 3, dtype=t.dtype)
+        for ta, tb, ch, kh, kw, c in Engine._stem_index():
+            out[:, kh, kw, c] = t[:, ta, tb, ch]
+        return out
 
     def export_grads(self):
         return OrderedDict((name, self._to_ref_layout(name, self.grads)) for (name, _, _, _, _) in self.vars)
@@ -314,7 +339,8 @@ class Engine:
         h1, w1 = o(H, 7, 2, 3), o(W, 7, 2, 3)
         h2, w2 = o(h1, 3, 2, 1), o(w1, 3, 2, 1)
         self.hw_stem, self.hw_pool = (h1, w1), (h2, w2)
-        buf("img4", B, H, W, 4)
+        self.hw_s2d = ((H + 1) // 2, (W + 1) // 2)
+        buf("s2d", B, self.hw_s2d[0], self.hw_s2d[1], 16)
         buf("stem", B, h1, w1, 64)
         buf("pool", B, h2, w2, 64)
         buf("pool_arg", B, h2, w2, 64, dtype=torch.uint8)
@@ -525,10 +551,11 @@ class Engine:
         d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
         scale = float(d // Hh) ** -0.5
         # ---------------- backbone (resnet_backbone.py:20-32)
-        ops.image_to_nhwc4(a["images"], a["img4"], B * self.H0 * self.W0)
+        # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels (tcgen05 im2col kernel)
+        ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0)
         self.launches += 1
         stem = self.slots["backbone/conv1"]
-        self._conv_fwd(stem, a["img4"], (self.H0, self.W0), self.hw_stem, a["stem"], relu=True)
+        self._conv_fwd(stem, a["s2d"], self.hw_s2d, self.hw_stem, a["stem"], relu=True)
         ops.maxpool_fwd(a["stem"], a["pool"], a["pool_arg"], B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
         self.launches += 1
         x = a["pool"]
@@ -790,7 +817,7 @@ class Engine:
         self.launches += 1
         ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
         stem = self.slots["backbone/conv1"]
-        self._conv_wgrad(stem, a["img4"], g_in, (self.H0, self.W0), self.hw_stem)
+        self._conv_wgrad(stem, a["s2d"], g_in, self.hw_s2d, self.hw_stem)
         self._mark("bwd_backbone")
 
     # ------------------------------------------------------------------------------------------ optimizer
@@ -862,22 +889,56 @@ class Engine:
         self.optimizer_step(clipnorm)
         self._mark("adam_refresh")
 
+    def _distributed(self):
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
     def capture_train_step(self, background_class, clipnorm, loss_scale=1.0, train_backbone=True, warmup=2):
-        """Capture train_step into a CUDA graph (static shapes: fixed-size images).  Returns a callable replaying it."""
+        """Capture train_step into CUDA graphs (static shapes: fixed-size images).  Returns a callable replaying it.
+        Single rank: one graph for the whole step.  Data parallel: the gradient all-reduce stays an eager NCCL call between
+        two graphs (forward+loss+backward | optimizer) -- NCCL's watchdog threads and graph capture do not mix safely."""
+        def part1():
+            self.training = True
+            self.seed_dev.add_(1)
+            self._forward_impl()
+            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
+            self.zero_grads()
+            self.backward(train_backbone=train_backbone)
+
+        def part2():
+            self.optimizer_step(clipnorm)
+        dist_on = self._distributed()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self.train_step(background_class, clipnorm, loss_scale, train_backbone)
+                part1()
+                self.allreduce_grads()
+                part2()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
         n0 = self.launches
-        with torch.cuda.graph(graph):
-            self.train_step(background_class, clipnorm, loss_scale, train_backbone)
+        if not dist_on:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                part1()
+                part2()
+            self.launches_per_step = self.launches - n0
+            self._graph = graph
+            return graph.replay
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, capture_error_mode="thread_local"):
+            part1()
+        with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+            part2()
         self.launches_per_step = self.launches - n0
-        self._graph = graph
-        return graph.replay
+        self._graph = (g1, g2)
+
+        def replay():
+            g1.replay()
+            self.allreduce_grads()
+            g2.replay()
+        return replay
 
     # ------------------------------------------------------------------------------------------ graph-replayed gradient step
     def stage_inputs(self, images, t_bbox, t_class):
@@ -898,19 +959,20 @@ class Engine:
             self.loss(background_class, loss_scale=loss_scale, with_grad=True)
             self.zero_grads()
             self.backward(train_backbone=True)
-            self.allreduce_grads()
         if not use_graph or self.device.type != "cuda":
-            return body()
+            body()
+            return self.allreduce_grads()
         key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None)
         if getattr(self, "_gs_key", None) != key:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                body()                                     # warm-up (kernel attribute setup, NCCL channels)
+                body()                                     # warm-up (kernel attribute setup)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 body()
             self._gs_graph, self._gs_key = g, key
         self._gs_graph.replay()
+        self.allreduce_grads()                             # eager NCCL call (kept out of the graph)

@@ -122,6 +122,10 @@ def image_to_nhwc4(img, out, npix):
     check(_lib.lib().detrb_image_to_nhwc4(ptr(img), ptr(out), c_int64(npix), _stream()))
 
 
+def image_to_s2d16(img, out, B, H, W):
+    check(_lib.lib().detrb_image_to_s2d16(ptr(img), ptr(out), c_int(B), c_int(H), c_int(W), _stream()))
+
+
 def f32_to_bf16(x, y, n):
     check(_lib.lib().detrb_f32_to_bf16(ptr(x), ptr(y), c_int64(n), _stream()))
 

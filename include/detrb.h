@@ -170,6 +170,9 @@ int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *o
 int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *out, int64_t n, detrb_stream_t stream);
 /* fp32 NHWC3 image -> bf16 NHWC4 (4th channel 0): the layout the stem kernel gathers from */
 int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_stream_t stream);
+/* fp32 NHWC3 image -> bf16 space-to-depth(2) tensor [B, ceil(H/2), ceil(W/2), 16] (channel (ry*2+rx)*3+c, 4 zero channels):
+ * turns the 7x7/stride-2 stem (resnet_backbone.py:11-12) into a dense 4x4/stride-1 conv the tcgen05 im2col kernel can run */
+int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, detrb_stream_t stream);
 /* fp32 -> bf16 */
 int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream);
 /* column sums: out[n] += scale[n]* sum_m x[m,n]  (bias gradients) */

@@ -188,6 +188,13 @@ class FakeLib:
                      stem_real_kw=7 if stem else None)
         dY = M2(p.dY, _Act.dtype, p.M, p.N, p.ldy).to(F32)
         g = dY.t() @ Ag
+        if p.Cin == 16 and p.KH == 4 and p.KW == 4 and p.pad == 2:
+            # space-to-depth stem: columns of taps that do not exist in the 7x7x3 kernel get no gradient
+            k = torch.arange(p.K)
+            ch, tb, ta = k % 16, (k // 16) % 4, k // 64
+            ry, rx = ch // 6, (ch // 3) % 2
+            kh, kw = 2 * ta + ry - 1, 2 * tb + rx - 1
+            g = g * ((ch < 12) & (kh >= 0) & (kh <= 6) & (kw >= 0) & (kw <= 6)).to(F32)[None, :]
         sc = T(p.rowscale, F32, p.N) if _addr(p.rowscale) else None
         if sc is not None:
             g = g * sc[:, None]
@@ -303,6 +310,19 @@ class FakeLib:
         o = M2(out, _Act.dtype, npix, 4, 4)
         o[:, :3] = M2(img, F32, npix, 3, 3).to(_Act.dtype)
         o[:, 3] = 0
+        return 0
+
+    def detrb_image_to_s2d16(self, img, out, B, H, W, stream):
+        B, H, W = _v(B), _v(H), _v(W)
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        x = T(img, F32, B * H * W * 3).view(B, H, W, 3)
+        xp = torch.zeros(B, 2 * H2, 2 * W2, 3)
+        xp[:, :H, :W] = x
+        o = torch.zeros(B, H2, W2, 16)
+        for ry in range(2):
+            for rx in range(2):
+                o[..., (ry * 2 + rx) * 3:(ry * 2 + rx) * 3 + 3] = xp[:, ry::2, rx::2]
+        T(out, _Act.dtype, B * H2 * W2 * 16)[:] = o.reshape(-1).to(_Act.dtype)
         return 0
 
     def detrb_f32_to_bf16(self, x, y, n, stream):
