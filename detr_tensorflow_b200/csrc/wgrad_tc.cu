@@ -207,6 +207,7 @@ bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 {
     // large pixel counts (backbone) or large weight matrices (layer4 convs at M = 8400); small transformer linears stay on mma.sync
+    if (p.Cin == 16) return true;        // space-to-depth stem: only this kernel masks the taps that do not exist in the 7x7 kernel
     return p.M >= 16384 || (p.M >= 4096 && (long)p.N * p.K >= (1l << 20));
 }
 

@@ -223,7 +223,7 @@ def test_stem_space_to_depth_conv_and_wgrad(ops, H, W):
     dy = rnd(M, 64, seed=5).to(BF)
     scale = rnd(64, seed=6).abs() + 0.5
     dW = torch.zeros(64, 256, dtype=F32, device="cuda")
-    ops.wgrad(s2d, 16, dy, 64, M, 64, 256, g, dW, 256, rowscale=scale)
+    ops.wgrad(s2d, 16, dy, 64, M, 64, 256, g, dW, 256, rowscale=scale, force_tc=True)
     torch.cuda.synchronize()
     gw, = torch.autograd.grad(ref, [wt], dy.float().view(B, oh, ow, 64).permute(0, 3, 1, 2))
     ref16 = Engine._stem_to_s2d(None, (gw.permute(0, 2, 3, 1) * scale[:, None, None, None]).cpu()).reshape(64, 256).cuda()
