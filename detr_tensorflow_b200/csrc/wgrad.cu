@@ -142,6 +142,7 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
 
     if (do_bias && n0 + tid < p.N) atomicAdd(p.dbias + n0 + tid, bias_acc * (p.rowscale ? p.rowscale[n0 + tid] : 1.f));
     const int g = lane >> 2, t = lane & 3;
+    const bool vec_ok = (p.ldw % 2 == 0) && (((uintptr_t)p.dW & 7) == 0);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -152,8 +153,13 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 int k = k0 + wk * 32 + j * 8 + t * 2;
-                if (k < p.K)     atomicAdd(p.dW + (size_t)n * p.ldw + k,     acc[i][j][h * 2 + 0] * sc);
-                if (k + 1 < p.K) atomicAdd(p.dW + (size_t)n * p.ldw + k + 1, acc[i][j][h * 2 + 1] * sc);
+                float *dst = p.dW + (size_t)n * p.ldw + k;
+                if (k + 1 < p.K && vec_ok) {            // two adjacent columns: one vector reduction
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(dst), "f"(acc[i][j][h * 2 + 0] * sc), "f"(acc[i][j][h * 2 + 1] * sc) : "memory");
+                } else {
+                    if (k < p.K)     atomicAdd(dst,     acc[i][j][h * 2 + 0] * sc);
+                    if (k + 1 < p.K) atomicAdd(dst + 1, acc[i][j][h * 2 + 1] * sc);
+                }
             }
         }
 }

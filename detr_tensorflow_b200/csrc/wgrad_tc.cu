@@ -163,6 +163,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
         const bool row_ok = n < p.N;
         const float sc = (row_ok && p.rowscale) ? p.rowscale[n] : 1.f;
         float *drow = p.dW + (size_t)(row_ok ? n : 0) * p.ldw;
+        const bool vec_ok = (p.ldw % 4 == 0) && (((uintptr_t)p.dW & 15) == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < KT; c0 += 16) {
             uint32_t r[16];
@@ -170,17 +171,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             tc_wait_ld();
             if (!row_ok) continue;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int k = k0 + c0 + i;
-                bool ok = k < p.K;
-                if (C16 && stem_mask) {
-                    // space-to-depth stem: column k = (ta, tb, (ry*2+rx)*3 + c) stands for the 7x7 tap (2ta+ry-1, 2tb+rx-1);
-                    // taps outside 0..6 and the 4 padding channels do not exist in the reference kernel: no gradient
-                    const int ch = k & 15, tb = (k >> 4) & 3, ta = k >> 6;
-                    const int ry = ch / 6, rx = (ch / 3) & 1, kh = 2 * ta + ry - 1, kw = 2 * tb + rx - 1;
-                    ok = ok && ch < 12 && kh >= 0 && kh <= 6 && kw >= 0 && kw <= 6;
+            for (int i4 = 0; i4 < 16; i4 += 4) {
+                // 4 consecutive gradient elements of one row: one vector reduction (red.global.add.v4.f32) instead of 4 atomics --
+                // the L2 atomic units, not HBM, bound this kernel on the small layer1/2 weight matrices
+                float v[4]; bool ok[4]; bool all_ok = true;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = k0 + c0 + i4 + i;
+                    ok[i] = k < p.K;
+                    if (C16 && stem_mask) {
+                        // space-to-depth stem: column k = (ta, tb, (ry*2+rx)*3 + c) stands for the 7x7 tap (2ta+ry-1, 2tb+rx-1);
+                        // taps outside 0..6 and the 4 padding channels do not exist in the reference kernel: no gradient
+                        const int ch = k & 15, tb = (k >> 4) & 3, ta = k >> 6;
+                        const int ry = ch / 6, rx = (ch / 3) & 1, kh = 2 * ta + ry - 1, kw = 2 * tb + rx - 1;
+                        ok[i] = ok[i] && ch < 12 && kh >= 0 && kh <= 6 && kw >= 0 && kw <= 6;
+                    }
+                    v[i] = __uint_as_float(r[i4 + i]) * sc;
+                    all_ok = all_ok && ok[i];
                 }
-                if (ok) atomicAdd(drow + k, __uint_as_float(r[i]) * sc);
+                float *dst = drow + k0 + c0 + i4;
+                if (all_ok && vec_ok) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (ok[i]) atomicAdd(dst + i, v[i]);
+                }
             }
         }
     }

@@ -47,16 +47,76 @@ def run_val_step(model, images, t_bbox, t_class, config):
     return _forward_loss(model, images, t_bbox, t_class, config, False, 1.0, False)
 
 
-def fit(model, train_dt, optimizers, config, epoch_nb, class_names):
+class _Prefetcher:
+    """Overlaps the host->device copy of batch i+1 with the compute of batch i: batches are copied on a side stream into two
+    alternating device staging sets; run_train_step then stages them with a device-to-device copy (0.1 ms instead of ~2 ms of
+    PCIe time on the critical path for a 100 MB fp32 batch).  The reference feeds from tf.data, which prefetches the same way."""
+
+    def __init__(self, iterable, device):
+        self.it, self.device = iter(iterable), device
+        self.stream = torch.cuda.Stream() if device.type == "cuda" else None
+        self.slot = 0
+        self.bufs = [None, None]
+        self.next = self._load()
+
+    def _to(self, x, dtype, old):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        if x.device == self.device and x.dtype == dtype:
+            return x
+        if old is None or old.shape != x.shape:
+            old = torch.empty(x.shape, dtype=dtype, device=self.device)
+        old.copy_(x, non_blocking=True)
+        return old
+
+    def _load(self):
+        try:
+            images, t_bbox, t_class = next(self.it)
+        except StopIteration:
+            return None
+        if self.stream is None:
+            return (_dev(images, torch.float32, self.device), _dev(t_bbox, torch.float32, self.device),
+                    _dev(t_class, torch.int64, self.device), None)
+        old = self.bufs[self.slot] or (None, None, None)
+        with torch.cuda.stream(self.stream):
+            out = (self._to(images, torch.float32, old[0]), self._to(t_bbox, torch.float32, old[1]),
+                   self._to(t_class, torch.int64, old[2]))
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.bufs[self.slot] = out
+        self.slot ^= 1
+        return out + (ev,)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = self.next
+        if cur is None:
+            raise StopIteration
+        if cur[3] is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(cur[3])                              # batch i is on the device ...
+            done = torch.cuda.Event()
+            done.record(main)                                    # everything enqueued so far has consumed the staging set
+            self.stream.wait_event(done)                         # that batch i+1 is about to overwrite (two alternate)
+        self.next = self._load()                                 # ... and batch i+1 starts moving while batch i computes
+        return cur[:3]
+
+
+def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None):
     """training.py:35-65 -- one epoch.  `train_dt`: iterable of (images[B,H,W,3] f32, t_bbox[B,100,4] f32,
-    t_class[B,100,1] i64) (numpy arrays or torch tensors, host or device)."""
+    t_class[B,100,1] i64) (numpy arrays or torch tensors, host or device).  Extension: `on_step(step, total_loss, log)` is
+    called after every step (the reference only prints every 100 steps)."""
     t = None
-    for epoch_step, (images, t_bbox, t_class) in enumerate(train_dt):
+    for epoch_step, (images, t_bbox, t_class) in enumerate(_Prefetcher(train_dt, model.engine.device)):
         m_outputs, total_loss, log, gradient_steps = run_train_step(model, images, t_bbox, t_class, optimizers, config)
         if config.log:
             _train_log_hook(images, t_bbox, t_class, m_outputs, config, config.global_step, class_names, prefix="train/")
         for name in gradient_steps:
             aggregate_grad_and_apply(name, optimizers, gradient_steps[name]["gradients"], epoch_step, config)
+        if on_step is not None:
+            on_step(epoch_step, total_loss, log)
         if epoch_step % 100 == 0:
             t = t if t is not None else time.time()
             elapsed = time.time() - t
