@@ -66,10 +66,16 @@ class Engine:
         self.spec = model_params(num_classes, backbone, num_encoder_layers, num_decoder_layers, 256, 2048, num_queries)
         self._build_params()
         self.plan_key = None
+        self._in_backward = False
         self.sites = {}
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.launches = 0
         self.acc = None
+        # weight gradients run on a side stream, concurrently with the data-gradient chain (they only feed the optimizer)
+        self.overlap_wgrad = self.device.type == "cuda"
+        self._wstream = None
+        self._pending = {}
+        self._w_last = None
 
     # ------------------------------------------------------------------------------------------ parameters
     def _build_params(self):
@@ -470,9 +476,49 @@ class Engine:
             return dict(drop_p=self.dropout, seed=self.base_seed, site=self._site(name), seed_ptr=self.seed_dev)
         return {}
 
+    # ---- side-stream weight gradients with write-after-read tracking on the scratch buffers they read
+    @staticmethod
+    def _key(t):
+        return t.untyped_storage().data_ptr()
+
+    def _on_wstream(self, fn, reads):
+        if not (self.overlap_wgrad and self._in_backward):
+            return fn()
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._wstream.wait_event(ev)                 # operands produced by everything enqueued so far
+        with torch.cuda.stream(self._wstream):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self._wstream)
+        for t in reads:
+            self._pending[self._key(t)] = done
+        self._w_last = done
+
+    def _before_write(self, *tensors):
+        """a main-stream kernel is about to overwrite these buffers: wait for side-stream readers still pending on them"""
+        if not self._pending:
+            return
+        for t in tensors:
+            if t is None:
+                continue
+            ev = self._pending.pop(self._key(t), None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def _join_wgrad(self):
+        if self._w_last is not None:
+            torch.cuda.current_stream().wait_event(self._w_last)
+        self._w_last = None
+        self._pending.clear()
+
     def _lin(self, A, W, M, N, K, ldw, out=None, ldc=None, lda=None, **kw):
         """plain GEMM  out[M,N] = A[M,K] . W[N,K]^T (+epilogue)"""
         self.launches += 1
+        self._before_write(out, kw.get("Cf"))
         ops.igemm(A, W, M, N, K, lda or K, ldw, ops.plain_geom(M, K), C=out, ldc=(ldc if ldc is not None else N), **kw)
 
     def _conv_geom(self, s, B, ih, iw, oh, ow, mode=0):
@@ -500,6 +546,7 @@ class Engine:
         M = B * ihw[0] * ihw[1]
         g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=s.ldd, OH=ihw[0], OW=ihw[1], KH=kh, KW=kwp, stride=stride, pad=pad, mode=1)
         self.launches += 1
+        self._before_write(out)
         ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin, mask_scale=1.0,
                   residual=residual, ldr=s.Cin, C=out, ldc=s.Cin)
 
@@ -507,14 +554,15 @@ class Engine:
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
-        ops.wgrad(x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold, dbias=s.bias_grad)
+        self._on_wstream(lambda: ops.wgrad(x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold,
+                                           dbias=s.bias_grad), (x, dy))
 
     def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
         """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
         n_rows = n_rows or s.N
         self.launches += 1
-        ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
-                  s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:])
+        self._on_wstream(lambda: ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
+                                           s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:]), (x, dy))
 
     def _ln_fwd(self, x, n, y, mean, rstd, M, y2=None, pos=None, S=1):
         self.launches += 1
@@ -522,6 +570,7 @@ class Engine:
 
     def _ln_bwd(self, dy, dy2, x, n, mean, rstd, dx, dx_drop, M, drop_name=None):
         self.launches += 1
+        self._before_write(dx, dx_drop)
         d = self._drop(drop_name) if drop_name else {}
         ops.layernorm_bwd(dy, dy2, x, n["g"], mean, rstd, dx, dx_drop, d.get("drop_p", 0.0), d.get("seed", 0),
                           d.get("site", 0), d.get("seed_ptr"), n["dg"], n["db"], M)
@@ -691,6 +740,7 @@ class Engine:
         d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
         scale = float(d // Hh) ** -0.5
         LM = self.ndec * Mq
+        self._in_backward = True
         inv_keep = 1.0 / (1.0 - self.dropout) if (self.training and self.dropout > 0) else 1.0
         # ---------------- heads
         self._lin_wgrad(self.h_b2, a["hb2"], a["d_boxpre"], LM, ldy=32)
@@ -725,6 +775,7 @@ class Engine:
             self._lin_wgrad(Wo, t("o2"), a["gq_c"], Mq)
             self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o2
             self.launches += 3
+            self._before_write(a["gq_q2"], a["gm_k2"], a["gm_v2"], a["delta"])
             ops.attn_bwd(t("q2"), t("k2"), t("v2"), t("o2"), a["gq_d"], d, d, d, d, d, t("lse2"), a["delta"],
                          a["gq_q2"], a["gm_k2"], a["gm_v2"], d, d, d, B, Hh, Q, S, scale, **self._attn_drop(f"d{l}_attn2"))
             self._lin_wgrad(W, t("t1q"), a["gq_q2"], Mq, n_off=0, n_rows=d)
@@ -742,6 +793,7 @@ class Engine:
             self._lin_wgrad(Wo, t("o"), a["gq_c"], Mq)
             self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o
             self.launches += 3
+            self._before_write(a["gq_qk"], a["gq_v"], a["delta"])
             ops.attn_bwd(t("qk"), t("qk")[:, d:], t("v"), t("o"), a["gq_d"], 2 * d, 2 * d, d, d, d, t("lse1"), a["delta"],
                          a["gq_qk"], a["gq_qk"][:, d:], a["gq_v"], 2 * d, 2 * d, d, B, Hh, Q, Q, scale,
                          **self._attn_drop(f"d{l}_attn1"))
@@ -770,6 +822,7 @@ class Engine:
             self._lin_wgrad(Wo, e("o"), a["gm_b"], M)
             self._lin(a["gm_b"], Wo.Wd, M, d, d, d, out=a["gm_c"])                                             # d o
             self.launches += 3
+            self._before_write(a["gm_qk"], a["gm_v"], a["delta"])
             ops.attn_bwd(e("qk"), e("qk")[:, d:], e("v"), e("o"), a["gm_c"], 2 * d, 2 * d, d, d, d, e("lse"), a["delta"],
                          a["gm_qk"], a["gm_qk"][:, d:], a["gm_v"], 2 * d, 2 * d, d, B, Hh, S, S, scale,
                          **self._attn_drop(f"e{l}_attn"))
@@ -784,6 +837,8 @@ class Engine:
         ip = self.slots["input_proj"]
         self._lin_wgrad(ip, self.feat, g_y, M)
         if not train_backbone:
+            self._in_backward = False
+            self._join_wgrad()
             return
         nb = len(self.blocks)
         last = self.blocks[-1]
@@ -810,14 +865,18 @@ class Engine:
                 Mo = B * ohw[0] * ohw[1]
                 g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=cd.ldd, OH=ohw[0], OW=ohw[1], KH=1, KW=1, stride=1, pad=0, mode=0)
                 self.launches += 1
+                self._before_write(g_in)
                 ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask=xmask, ldm=cd.Cin, mask_scale=1.0,
                           C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True)
             g_out, g_in = g_in, g_out
         # g_out now holds d pool
         self.launches += 1
+        self._before_write(g_in)
         ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
         stem = self.slots["backbone/conv1"]
         self._conv_wgrad(stem, a["s2d"], g_in, self.hw_s2d, self.hw_stem)
+        self._in_backward = False
+        self._join_wgrad()
         self._mark("bwd_backbone")
 
     # ------------------------------------------------------------------------------------------ optimizer
