@@ -264,7 +264,7 @@ def main():
         M = B * blk["out_hw"][0] * blk["out_hw"][1]
         flops = 2.0 * M * s.N * s.K
         t_k = sorted(times)[len(times) // 2] * 1e-3
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<128,3,im2col> (tcgen05 implicit-GEMM conv 3x3 256->256, layer3, M=33600 N=256 K=2304)",
+        roof = {"bound": "tensor", "kernel": "gemm_tcp_kernel<256,4,im2col> (persistent tcgen05 implicit-GEMM conv 3x3 256->256, 128x256 tiles, layer3, M=33600 N=256 K=2304)",
                 "achieved": flops / t_k / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / t_k / 1e12 / peak_tf,
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
                 "flops_per_launch": flops, "us_per_launch": t_k * 1e6,

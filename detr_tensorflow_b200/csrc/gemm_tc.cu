@@ -46,6 +46,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// v[0..8) += 8 consecutive floats of the bias row staged in shared memory (all lanes read the same address: broadcast)
+__device__ __forceinline__ void add_bias8(float (&v)[8], uint32_t saddr) {
+    float4 b0, b1;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(saddr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(saddr + 16u));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
+
 // convolution side-band for the IM2COL kernels: effective padding and, per im2col tap, the weight tap to pair it with
 // (identity: forward; reversed: stride-1 data gradient; sparse: one parity class of a stride-2 data gradient)
 struct ConvAux { int pad; int c16; int wtap[16]; };   // c16: 16-channel pixels (space-to-depth stem): 4 taps per 64-wide k-block
@@ -56,7 +64,8 @@ struct SmemLayout {
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;      // barriers + slack for 1024-byte alignment
+    static constexpr int BIAS_OFF = BAR_OFF + 256;          // BN floats of bias (BN shift), staged once per CTA
+    static constexpr int TOTAL = BAR_OFF + 1024 + 1024;     // barriers + bias + slack for 1024-byte alignment
 };
 
 // IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
@@ -164,6 +173,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        const uint32_t sbias = smem_base + L::BIAS_OFF;
+        if (p.bias) {                                        // global-load latency hides behind the main loop
+            const int t = threadIdx.x - 64;
+            if (t < BN) {
+                const float b = (n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
+                asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
@@ -215,10 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hf * 8 + i]);
-                        if (p.bias && n < p.N) {
-                            float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
-                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                        }
+                        if (p.bias) add_bias8(v, sbias + 4u * (uint32_t)(n - n0));
                         float res[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) res[i] = 0.f;
@@ -292,10 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hf * 8 + i]);
-                if (p.bias) {
-                    float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
-                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
+                if (p.bias) add_bias8(v, sbias + 4u * (uint32_t)(n - n0));
                 float res[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) res[i] = 0.f;
@@ -364,28 +376,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ================================================================================================ persistent variant
-// One CTA per SM loops over output tiles; every latency is overlapped across tiles:
-//   warp 0   TMA producer for the A / W stages (4-deep ring that runs ahead across tile boundaries)
-//   warp 1   MMA issuer; accumulators ping-pong between two TMEM buffers (tmem_full / tmem_empty barriers)
-//   warp 2   TMEM allocator
-//   warp 3   TMA producer for the residual / mask tiles of the NEXT epilogue (resid_full / resid_empty barriers)
-//   warps 4-7  epilogue: tcgen05.ld -> fused math -> swizzled smem staging (double buffered) -> TMA store
-// The memory-bound layers of the backbone (K = 64..256: one to four k-blocks per tile) are limited by per-CTA latency chains
-// in the one-tile-per-CTA kernel above; here the TMA queue never drains between tiles.
-constexpr int PSTAGES = 4;
-constexpr int NTHREADS_P = 256;
+// One CTA per SM walks the output tiles (static round-robin); every latency chain of the one-tile kernel above is
+// overlapped across tiles:
+//   warp 0      TMA producer for the A / W stages (the ring runs ahead across tile boundaries)
+//   warp 1      MMA issuer; NACC accumulators rotate through TMEM (tmem_full / tmem_empty barriers)
+//   warp 2      TMEM allocator
+//   warp 3      TMA producer for the residual / mask chunks of upcoming epilogues (ring of `rs` [128 x 64] slots)
+//   warps 4-11  two epilogue warpgroups: the 64-column chunks alternate between them, each owns one swizzled staging tile
+//               and its TMA stores (tcgen05.ld -> fused math -> st.shared -> cp.async.bulk.tensor store)
+// BN = 256 halves the shared-memory operand traffic per flop (one 128x256x16 UMMA reads 96 B/clk instead of the 128 B/clk
+// of a 128x128 tile, which saturates the SM's shared-memory port) -- the compute-bound convolutions; BN = 64 / 128 with
+// 4 accumulators serve the HBM-bound 1x1 layers, whose tiles are one to four k-blocks long.
+constexpr int NTHREADS_P = 384;
+constexpr int MAXRS = 4;
 
-template <int BN>
+template <int BN, int PST>
 struct PLayout {
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NCH = BN / 64;                                   // 64-column chunks per tile
-    static constexpr int RBUF = PSTAGES * STAGE_BYTES;                    // residual tile  [NCH][128 x 64]
-    static constexpr int MBUF = RBUF + NCH * 16384;                       // mask tile
-    static constexpr int OBUF = MBUF + NCH * 16384;                       // output staging, 2 x [128 x 64]
-    static constexpr int BAR_OFF = OBUF + 2 * 16384;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int NACC = BN <= 128 ? 4 : 2;                        // accumulators in TMEM
+    static constexpr int TMEM_COLS = NACC * BN;                           // 256 or 512 columns (power of two)
+    static constexpr int OBUF = PST * STAGE_BYTES;                        // output staging, one [128 x 64] tile per warpgroup
+    static constexpr int RING = OBUF + 2 * 16384;                         // residual / mask ring
+    static constexpr int TOTAL = 227 * 1024;
+    static constexpr int BAR_OFF = TOTAL - 1024 - 1024;                   // 1 KB alignment slack, 512 B of barriers, 2 x 64 bias floats
+    static constexpr int BIAS_OFF = BAR_OFF + 512;
+    static constexpr int RING_BYTES = BAR_OFF - RING;
+    static_assert(RING_BYTES >= 0, "persistent GEMM: stages do not fit");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -398,12 +417,10 @@ __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
 }
 // fused epilogue arithmetic on 8 consecutive columns n..n+7 of row m (same order as igemm.cu)
 __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], const float (&mk)[8], bool has_mask,
-                                          const detrb_igemm_t &p, int m, int n, uint64_t seed, uint32_t thresh, float drop_scale)
+                                          const detrb_igemm_t &p, int m, int n, uint64_t seed, uint32_t thresh, float drop_scale,
+                                          uint32_t sbias8)
 {
-    if (p.bias) {
-        float4 b0 = *reinterpret_cast<const float4 *>(p.bias + n), b1 = *reinterpret_cast<const float4 *>(p.bias + n + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
+    if (p.bias) add_bias8(v, sbias8);
     if (!(p.drop_p > 0.f)) {
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] += res[i];
@@ -431,39 +448,40 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], 
     }
 }
 
-template <int BN, bool IM2COL>
+template <int BN, int PST, bool IM2COL>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                 const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux,
-                const int tma_epi, const int n_tiles_n, const int n_tiles)
+                const int n_tiles_n, const int n_tiles, const int rs)
 {
-    using L = PLayout<BN>;
+    using L = PLayout<BN, PST>;
+    constexpr int NACC = L::NACC;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + L::BAR_OFF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (PSTAGES + s); };
-    auto tmem_full = [&](int a) { return bar_base + 8u * (2 * PSTAGES + a); };
-    auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * PSTAGES + 2 + a); };
-    const uint32_t resid_full = bar_base + 8u * (2 * PSTAGES + 4);
-    const uint32_t resid_empty = bar_base + 8u * (2 * PSTAGES + 5);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * PSTAGES + 6);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (PST + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (2 * PST + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * PST + NACC + a); };
+    auto resid_full = [&](int i) { return bar_base + 8u * (2 * PST + 2 * NACC + i); };
+    auto resid_empty = [&](int i) { return bar_base + 8u * (2 * PST + 2 * NACC + MAXRS + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * PST + 2 * NACC + 2 * MAXRS);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = p.K / TBK;
-    const bool have_in = tma_epi && (p.residual != nullptr || p.mask != nullptr);
+    const bool has_r = p.residual != nullptr, has_m = p.mask != nullptr, have_in = has_r || has_m;
+    const uint32_t slot_bytes = 16384u * ((has_r ? 1u : 0u) + (has_m ? 1u : 0u));
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < PSTAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
-        mbar_init(resid_full, 1);
-        mbar_init(resid_empty, 4);
+        for (int s = 0; s < PST; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }
+        for (int i = 0; i < MAXRS; i++) { mbar_init(resid_full(i), 1); mbar_init(resid_empty(i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)L::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_trigger();
@@ -500,7 +518,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
                         tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
                     }
-                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == PST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -512,8 +530,8 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int stage = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-                const int acc = it & 1;
-                mbar_wait(tmem_empty(acc), ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                const int acc = it % NACC;
+                mbar_wait(tmem_empty(acc), ((it / NACC) & 1) ^ 1);        // both epilogue warpgroups have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < nk; kb++) {
@@ -525,151 +543,113 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int k = 0; k < TBK / 16; k++)
                         tc_mma_f16(d_addr, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     tc_commit(empty_bar(stage));
-                    if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == PST) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tmem_full(acc));
             }
         }
         __syncwarp();
     } else if (warp == 3) {
-        // ===================== residual / mask producer =====================
+        // ===================== residual / mask producer (one ring slot per 64-column chunk) =====================
         if (lane == 0 && have_in) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
-                mbar_wait(resid_empty, (it & 1) ^ 1);
-                int nch = 0;
-                for (int cb = 0; cb < L::NCH; cb++) if (n0 + cb * 64 < p.N) nch++;
-                mbar_expect_tx(resid_full, (uint32_t)nch * 16384u * ((p.residual ? 1u : 0u) + (p.mask ? 1u : 0u)));
-                for (int cb = 0; cb < nch; cb++) {
-                    if (p.residual) tma_load_2d(smem_base + L::RBUF + cb * 16384, &map_r, resid_full, n0 + cb * 64, m0);
-                    if (p.mask) tma_load_2d(smem_base + L::MBUF + cb * 16384, &map_m, resid_full, n0 + cb * 64, m0);
+                const int left = (p.N - n0 + 63) / 64, nch = left < L::NCH ? left : L::NCH;
+                for (int cb = 0; cb < nch; cb++, g++) {
+                    const int slot = g % rs;
+                    mbar_wait(resid_empty(slot), ((g / rs) & 1) ^ 1);
+                    mbar_expect_tx(resid_full(slot), slot_bytes);
+                    const uint32_t dst = smem_base + L::RING + (uint32_t)slot * slot_bytes;
+                    if (has_r) tma_load_2d(dst, &map_r, resid_full(slot), n0 + cb * 64, m0);
+                    if (has_m) tma_load_2d(dst + (has_r ? 16384u : 0u), &map_m, resid_full(slot), n0 + cb * 64, m0);
                 }
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
+        // ===================== epilogue: chunk g goes to warpgroup g % 2 =====================
+        const int wg = (warp - 4) >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
-        const bool leader = (warp == 4 && lane == 0);
+        const bool leader = (q == 0 && lane == 0);
+        const uint32_t obuf = smem_base + L::OBUF + (uint32_t)wg * 16384u;
+        const uint32_t sbias = smem_base + L::BIAS_OFF + (uint32_t)wg * 256u;
         const uint32_t thresh = dropout_thresh16(p.drop_p);
         const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
-        bf16 *C = reinterpret_cast<bf16 *>(p.C);
-        const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
-        const bf16 *Mk = reinterpret_cast<const bf16 *>(p.mask);
-        int it = 0, ob = 0;                                    // ob: output staging buffer toggle
+        int it = 0, g = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
-            const int acc = it & 1;
+            const int acc = it % NACC;
             const int m = m0 + row;
-            const bool row_ok = m < p.M;
-            mbar_wait(tmem_full(acc), (it >> 1) & 1);
-            tc_fence_after();
-            if (have_in) mbar_wait(resid_full, it & 1);
+            const int left = (p.N - n0 + 63) / 64, nch = left < L::NCH ? left : L::NCH;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            if (tma_epi) {
+            // every epilogue warp observes tmem_full before it arrives on tmem_empty below -- also a warpgroup without a chunk
+            // in this tile -- so no warp can run ahead and arrive twice in one phase of tmem_empty
+            mbar_wait(tmem_full(acc), (it / NACC) & 1);
+            tc_fence_after();
 #pragma unroll 1
-                for (int cb = 0; cb < L::NCH; cb++) {
-                    const int nb = n0 + cb * 64;
-                    if (nb >= p.N) break;
-                    const uint32_t obuf = smem_base + L::OBUF + ob * 16384;
-                    // the TMA store that last read this staging buffer (two chunks ago) must have finished reading it
-                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                    for (int c16 = 0; c16 < 4; c16++) {
-                        uint32_t r[16];
-                        tc_ld16(t_addr + (uint32_t)(cb * 64 + c16 * 16), r);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int hf = 0; hf < 2; hf++) {
-                            const int n = nb + c16 * 16 + hf * 8;
-                            const uint32_t soff = row_off + (((uint32_t)(c16 * 2 + hf) ^ sw) << 4);
-                            float v[8], res[8], mk[8];
-#pragma unroll
-                            for (int i = 0; i < 8; i++) { v[i] = __uint_as_float(r[hf * 8 + i]); res[i] = 0.f; mk[i] = 1.f; }
-                            if (p.residual) {
-                                uint4 u;
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                                             : "r"(smem_base + L::RBUF + cb * 16384 + soff));
-                                unpack8(u, res);
-                            }
-                            if (p.mask) {
-                                uint4 u;
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                                             : "r"(smem_base + L::MBUF + cb * 16384 + soff));
-                                unpack8(u, mk);
-                            }
-                            if (n < p.N) epi_math8(v, res, mk, p.mask != nullptr, p, m, n, seed, thresh, drop_scale);
-                            uint4 o;
-                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(obuf + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (leader) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     :: "l"(&map_c), "r"(obuf), "r"(nb), "r"(m0) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    ob ^= 1;
+            for (int cb = 0; cb < nch; cb++, g++) {
+                if ((g & 1) != wg) continue;
+                const int nb = n0 + cb * 64;
+                int slot = 0;
+                uint32_t rbuf = 0, mbuf = 0;
+                if (have_in) {
+                    slot = g % rs;
+                    mbar_wait(resid_full(slot), (g / rs) & 1);
+                    rbuf = smem_base + L::RING + (uint32_t)slot * slot_bytes;
+                    mbuf = rbuf + (has_r ? 16384u : 0u);
                 }
-            } else {
-                // direct stores (fp32 copy, strided scatter, read-modify-write): rare, small launches
-                size_t orow = m;
-                if (row_ok && p.out_stride > 1) {
-                    const int ohw = p.OH * p.OW;
-                    int b = m / ohw, rem = m - b * ohw;
-                    int oy = rem / p.OW, ox = rem - oy * p.OW;
-                    orow = ((size_t)b * p.SH + (size_t)oy * p.out_stride) * p.SW + (size_t)ox * p.out_stride;
+                if (p.bias && q < 2) {                          // this chunk's 64 bias values -> smem (visible after the barrier below)
+                    const int t = q * 32 + lane;
+                    const float b = (nb + t < p.N) ? p.bias[nb + t] : 0.f;
+                    asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
                 }
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                // the TMA store that last read this warpgroup's staging tile must have finished reading it
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+#pragma unroll
+                for (int c16 = 0; c16 < 4; c16++) {
                     uint32_t r[16];
-                    tc_ld16(t_addr + (uint32_t)c0, r);
+                    tc_ld16(t_addr + (uint32_t)(cb * 64 + c16 * 16), r);
                     tc_wait_ld();
-                    if (!row_ok || n0 + c0 >= p.N) continue;
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
-                        const int n = n0 + c0 + hf * 8;
-                        if (n >= p.N) continue;
+                        const int n = nb + c16 * 16 + hf * 8;
+                        const uint32_t soff = row_off + (((uint32_t)(c16 * 2 + hf) ^ sw) << 4);
                         float v[8], res[8], mk[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) { v[i] = __uint_as_float(r[hf * 8 + i]); res[i] = 0.f; mk[i] = 1.f; }
-                        if (R) unpack8(*reinterpret_cast<const uint4 *>(R + orow * p.ldr + n), res);
-                        if (Mk) unpack8(*reinterpret_cast<const uint4 *>(Mk + orow * p.ldm + n), mk);
-                        epi_math8(v, res, mk, Mk != nullptr, p, m, n, seed, thresh, drop_scale);
-                        if (C) {
-                            uint4 *dst = reinterpret_cast<uint4 *>(C + orow * p.ldc + n);
-                            if (p.accumulate) {
-                                float old[8];
-                                unpack8(*dst, old);
-#pragma unroll
-                                for (int i = 0; i < 8; i++) v[i] += old[i];
-                            }
-                            uint4 o;
-                            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                            *dst = o;
+                        if (has_r) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(rbuf + soff));
+                            unpack8(u, res);
                         }
-                        if (p.Cf) {
-                            float4 *dst = reinterpret_cast<float4 *>(p.Cf + orow * p.ldcf + n);
-                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        if (has_m) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(mbuf + soff));
+                            unpack8(u, mk);
                         }
+                        if (n < p.N) epi_math8(v, res, mk, has_m, p, m, n, seed, thresh, drop_scale, sbias + 4u * (uint32_t)(n - nb));
+                        uint4 o;
+                        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(obuf + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 :: "l"(&map_c), "r"(obuf), "r"(nb), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (have_in && lane == 0) mbar_arrive(resid_empty(slot));      // all four warps are past their smem reads
             }
-            // this warp is done with the accumulator and with the residual / mask tile of this output tile
+            // this warp is done with the accumulator of this tile (also when its warpgroup had no chunk in it)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(tmem_empty(acc));
-                if (have_in) mbar_arrive(resid_empty);
-            }
+            if (lane == 0) mbar_arrive(tmem_empty(acc));
         }
         if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -677,7 +657,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)L::TMEM_COLS) : "memory");
     }
 }
 
@@ -718,19 +698,14 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
 }
 
 static int g_tma_epilogue = 1;
-static int g_tc_persistent = 0;
+static int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
+static long g_tcp_min_tiles = 64, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
 
-template <int BN, int STAGES, bool IM2COL>
+template <int BN, int STAGES, bool IM2COL, bool PERSIST = false>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
-    using L = SmemLayout<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
     CUtensorMap ma, mb;
     ConvAux aux;
     aux.pad = 0; aux.c16 = 0;
@@ -775,27 +750,41 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         if (ok && p.mask) ok = make_map(&mm, p.mask, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldm, TBM);
         if (!ok) tma_epi = 0;
     }
-    if (g_tc_persistent && !aux.c16) {
-        using PL = PLayout<BN>;
+    if constexpr (PERSIST) {
+        using PL = PLayout<BN, STAGES>;
         static bool pconfigured = false;
         static int num_sms = 148;
         if (!pconfigured) {
-            DETRB_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
+            DETRB_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             pconfigured = true;
         }
+        if (!tma_epi || aux.c16) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc needs the TMA epilogue (plain bf16 output)");
+        const int slot = 16384 * ((p.residual ? 1 : 0) + (p.mask ? 1 : 0));
+        // even ring depth: chunk g lives in slot g % rs and is consumed by warpgroup g % 2, so each warpgroup owns its slots and
+        // never observes a slot barrier more than one phase behind (mbarrier parity waits cannot tell phases two apart)
+        int rs = slot ? (PL::RING_BYTES / slot) & ~1 : 0;
+        if (rs > MAXRS) rs = MAXRS;
+        if (slot && rs < 2) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc: no room for the residual / mask ring");
         const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        DETRB_LAUNCH((gemm_tcp_kernel<BN, IM2COL>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, tma_epi, ntn, ntiles);
+        DETRB_LAUNCH((gemm_tcp_kernel<BN, STAGES, IM2COL>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, ntn, ntiles, rs);
         DETRB_CHECK_LAUNCH("gemm_tcp_kernel");
         return DETRB_OK;
+    } else {
+    using L = SmemLayout<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
     DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL>), dim3(grid), dim3(NTHREADS_TC), L::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, tma_epi);
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
+    }
 }
 
 }  // namespace
@@ -841,15 +830,55 @@ static int g_tc_enabled = 1;      // validated on B200 (tests/test_gemm_tc_gpu.p
 extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
 bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
 
-extern "C" int detrb_set_tc_persistent(int enable) { int old = g_tc_persistent; g_tc_persistent = enable; return old; }
+extern "C" int detrb_set_tc_persistent(int enable)
+{
+    int old = g_tc_persistent;
+    g_tc_persistent = enable;
+    if (const char *e = getenv("DETRB_TCP_MIN_TILES")) g_tcp_min_tiles = atol(e);
+    if (const char *e = getenv("DETRB_TCP_MIN_NK256")) g_tcp_min_nk256 = atol(e);
+    return old;
+}
 extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
 static int g_tc_conv_enabled = 1;
 extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }
 bool detrb_gemm_tc_conv_enabled() { return g_tc_conv_enabled != 0; }
 
+// persistent-kernel policy.  g_tc_persistent: 0 off, 1 auto (where it measured faster), 2 wherever it is supported (tests)
+template <bool IM2COL>
+static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls, bool *taken)
+{
+    *taken = false;
+    const bool tma_epi = p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue;
+    if (!g_tc_persistent || !tma_epi || p.Cin == 16) return DETRB_OK;
+    const int nk = p.K / TBK;
+    const bool both = p.residual && p.mask;
+    const long mt = ceil_div(p.M, TBM);
+    int pick = 0;
+    if (g_tc_persistent >= 2) {
+        pick = bn ? bn : ((p.N % 256 == 0 && nk > 4) ? 256 : (p.N >= 128 && nk > 2) ? 128 : 64);
+        if (pick == 256 && both) pick = 128;        // 3 x 48 KB stages leave room for one residual+mask slot only
+    } else if (bn == 0) {
+        // measured on B200 (profiles/r01_tcp_sweep.log): long k-loops are compute bound and gain 1.2-2x from the persistent
+        // kernel (256-wide tiles once the k-loop amortises the wider epilogue); the HBM-bound 1x1 layers (K <= 256) are faster
+        // on the one-tile kernel, whose 4 co-resident CTAs give the epilogue 16 warps per SM
+        if (nk >= g_tcp_min_nk256 && p.N % 256 == 0 && !both && mt * (p.N / 256) >= g_tcp_min_tiles) pick = 256;
+        else if (nk > 4 && p.N >= 128 && mt * ceil_div(p.N, 128) >= g_tcp_min_tiles) pick = 128;
+        else if (nk == 4 && p.N == 64 && !p.residual && !p.mask && mt >= 4 * 148) pick = 64;
+    }
+    if (!pick) return DETRB_OK;
+    *taken = true;
+    if (pick == 256)
+        return (p.residual || p.mask) ? launch_tc<256, 3, IM2COL, true>(p, stream, cls) : launch_tc<256, 4, IM2COL, true>(p, stream, cls);
+    if (pick == 128) return launch_tc<128, 4, IM2COL, true>(p, stream, cls);
+    return launch_tc<64, 4, IM2COL, true>(p, stream, cls);
+}
+
 template <bool IM2COL>
 static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
+    bool taken = false;
+    int rc = dispatch_tcp<IM2COL>(p, bn, stream, cls, &taken);
+    if (taken || rc) return rc;
     if (bn == 0) {
         // 64-wide tiles when there are too few 128-wide ones to fill the machine, and for very short k-loops (K <= 128):
         // those tiles are pure latency chains (load -> 4-8 MMAs -> epilogue) and 4 small CTAs per SM overlap better than 3 large
@@ -857,7 +886,7 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
         bn = (p.N >= 128 && tiles128 >= 148 && p.K > 128) ? 128 : 64;
     }
     // short k-loops (K <= 256) are latency bound: 2 stages -> 64 / 48 KB of smem -> 3-4 co-resident CTAs per SM hide each other
-    const bool shallow = (p.K / TBK) <= 4 && !g_tc_persistent;
+    const bool shallow = (p.K / TBK) <= 4;
     if (bn == 128) return shallow ? launch_tc<128, 2, IM2COL>(p, stream, cls) : launch_tc<128, 3, IM2COL>(p, stream, cls);
     return shallow ? launch_tc<64, 2, IM2COL>(p, stream, cls) : launch_tc<64, 3, IM2COL>(p, stream, cls);
 }
@@ -912,7 +941,8 @@ extern "C" int detrb_gemm_tc_force(const detrb_igemm_t *pp, int bn, detrb_stream
     if (p.out_stride < 1) p.out_stride = 1;
     const int kind = detrb_gemm_tc_kind(p);
     if (kind == 0) DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc_force: problem not supported by the tcgen05 path");
-    if (bn != 0 && bn != 64 && bn != 128) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: bn must be 0, 64 or 128");
+    if (bn != 0 && bn != 64 && bn != 128 && bn != 256) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: bn must be 0, 64, 128 or 256");
+    if (bn == 256 && g_tc_persistent < 2) DETRB_FAIL(DETRB_E_BADARG, "detrb_gemm_tc_force: bn 256 exists only in the persistent kernel");
     if (kind == 3) return strided_dgrad_tc(p, (cudaStream_t)stream);
     return kind == 1 ? dispatch_tc<false>(p, bn, (cudaStream_t)stream) : dispatch_tc<true>(p, bn, (cudaStream_t)stream);
 }

@@ -13,7 +13,7 @@ def ops(request):
         pytest.skip("needs a GPU")
     from detr_tensorflow_b200 import _lib, ops as o
     _lib.check(_lib.lib().detrb_check_device())
-    old = o.set_tc_persistent(1 if request.param == "persistent" else 0)
+    old = o.set_tc_persistent(2 if request.param == "persistent" else 0)      # 2: persistent kernel wherever supported
     yield o
     o.set_tc_persistent(old)
 
@@ -66,6 +66,31 @@ def test_gemm_tc_tma_epilogue(ops, M, N, K, bn):
     ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), C=C, ldc=N, force_tc=bn)
     torch.cuda.synchronize()
     check("tma epi plain", C[:M], A.float() @ W.float().t(), 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(1050, 256, 512, 256), (8400, 512, 320, 256), (33600, 256, 2304, 256), (4175, 192, 64, 64), (20000, 320, 128, 128),
+                                      (20000, 320, 128, 256), (128 * 148 * 3 + 5, 64, 64, 64)])
+def test_gemm_tc_persistent_tiles(ops, M, N, K, bn):
+    """persistent kernel: 256-wide tiles, ragged N (partial last tile / chunk), residual+mask ring of depth 1..4, many tiles per CTA"""
+    if ops.set_tc_persistent(2) != 2:
+        ops.set_tc_persistent(0)
+        pytest.skip("persistent mode only")
+    A = rnd(M, K, seed=1).to(BF)
+    W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+    bias, res, mask = rnd(N, seed=3), rnd(M, N, seed=4).to(BF), rnd(M, N, seed=5).to(BF)
+    base = A.float() @ W.float().t() + bias
+    C = torch.full((M + 3, N), 7.0, dtype=BF, device="cuda")
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, force_tc=bn)
+    torch.cuda.synchronize()
+    check("plain", C[:M], F.relu(base), 1e-2, 1e-2)
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, residual=res, ldr=N, relu=True, C=C, ldc=N, force_tc=bn)
+    torch.cuda.synchronize()
+    check("res", C[:M], F.relu(base + res.float()), 1e-2, 1e-2)
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, residual=res, ldr=N, mask=mask, ldm=N, mask_scale=1.5, C=C, ldc=N,
+              force_tc=bn)
+    torch.cuda.synchronize()
+    check("res+mask", C[:M], torch.where(mask.float() > 0, (base + res.float()) * 1.5, torch.zeros_like(base)), 1e-2, 1e-2)
+    assert float((C[M:].float() - 7.0).abs().max()) == 0
 
 
 def test_gemm_tc_epilogues_match_mma_sync_kernel(ops):
