@@ -13,6 +13,13 @@ constexpr int TKV = 64;            // keys (or queries) per inner tile
 constexpr int LDH = DH + 8;        // smem row stride (bf16): 80 B
 constexpr float LOG2E = 1.4426950408889634f;
 
+// 2^x, one MUFU (exp2f() adds a denormal-range rescale: two FMULs and a compare per element); ex2(-inf) = 0
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // cooperative 64 x 32 bf16 tile load (rows beyond `nrows` zero-filled); 128 threads, 2 chunks each
 __device__ __forceinline__ void load_tile64(bf16 *dst, const bf16 *src, int ld, int row0, int nrows, int tid)
 {
@@ -130,46 +137,49 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
 
         float s[8][4];
         mma_a_tileT(s, aq, sK[kt & 1], lane);
-        // mask keys beyond Lk, convert to log2 domain
+        // row maxima on the raw scores (sl2 > 0: max commutes with the scaling); keys beyond Lk exist only in the last tile
         const int kbase = kt * TKV;
+        if (kbase + TKV > p.Lk) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (kbase + j * 8 + t * 2 + (e & 1) >= p.Lk) s[j][e] = -INFINITY;
+        }
         float tmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < 8; j++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int key = kbase + j * 8 + t * 2 + (e & 1);
-                float v = key < p.Lk ? s[j][e] * sl2 : -INFINITY;
-                s[j][e] = v;
-                tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
-            }
+            for (int e = 0; e < 4; e++) tmax[e >> 1] = fmaxf(tmax[e >> 1], s[j][e]);
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
             tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
         }
-        float alpha[2], mnew[2], rsum[2] = {0.f, 0.f};
+        float alpha[2], mneg[2], rsum[2] = {0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            mnew[r] = fmaxf(mrow[r], tmax[r]);
-            alpha[r] = exp2f(mrow[r] - mnew[r]);          // exp2(-inf) = 0 on the first tile
-            mrow[r] = mnew[r];
+            const float mnew = fmaxf(mrow[r], tmax[r] * sl2);  // log2 domain
+            alpha[r] = ex2(mrow[r] - mnew);                    // ex2(-inf) = 0 on the first tile
+            mrow[r] = mnew;
+            mneg[r] = -mnew;
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                float pv = exp2f(s[j][e] - mnew[e >> 1]);
+                float pv = ex2(fmaf(s[j][e], sl2, mneg[e >> 1]));
                 rsum[e >> 1] += pv;
                 s[j][e] = pv;
             }
-            if (p.drop_p > 0.f) {
+            if (p.drop_p > 0.f) {                              // the 1/(1-p) rescale is folded into the final normalisation
                 uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
                     bool k0, k1;
                     dropout_keep2(dropout_bits_rh(rh[r], pair), thresh, k0, k1);
-                    s[j][r * 2 + 0] = k0 ? s[j][r * 2 + 0] * drop_scale : 0.f;
-                    s[j][r * 2 + 1] = k1 ? s[j][r * 2 + 1] * drop_scale : 0.f;
+                    if (!k0) s[j][r * 2 + 0] = 0.f;
+                    if (!k1) s[j][r * 2 + 1] = 0.f;
                 }
             }
         }
@@ -193,7 +203,7 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
     for (int r = 0; r < 2; r++) {
         int q = q0 + warp * 16 + g + r * 8;
         if (q >= p.Lq) continue;
-        float inv = 1.f / lrow[r];
+        float inv = drop_scale / lrow[r];
 #pragma unroll
         for (int j = 0; j < 4; j++)
             *reinterpret_cast<uint32_t *>(O + (size_t)q * p.ldo + j * 8 + t * 2) =
@@ -259,8 +269,8 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
         load_tile64(sdO[st], dO, p.lddo, qt * TKV, p.Lq, tid);
         if (tid < TKV) {
             int q = qt * TKV + tid;
-            sLse[st][tid] = q < p.Lq ? lse[q] * LOG2E : INFINITY;
-            sDelta[st][tid] = q < p.Lq ? delta[q] : 0.f;
+            sLse[st][tid] = q < p.Lq ? -lse[q] * LOG2E : -INFINITY;      // negated, log2 domain
+            sDelta[st][tid] = q < p.Lq ? -delta[q] * p.scale : 0.f;       // -scale * delta
             sRh[st][tid] = dropout_rowhash(seed, p.site, (uint32_t)((b * p.H + h) * p.Lq + q));
         }
     };
@@ -278,7 +288,9 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
     const uint32_t thresh = dropout_thresh16(p.drop_p);
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int keyr[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
-    const float sl2 = p.scale * LOG2E;
+    const uint32_t kpair[2] = {(uint32_t)(keyr[0] >> 1), (uint32_t)(keyr[1] >> 1)};
+    const uint32_t kshift = (uint32_t)(keyr[0] & 1) * 16u;          // both rows of a thread have the same parity
+    const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
 
     for (int qt = 0; qt < nqt; qt++) {
         if (qt + 1 < nqt) { load_q((qt + 1) & 1, qt + 1); cp_async_commit(); cp_async_wait<1>(); }
@@ -289,23 +301,23 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
         float sT[8][4], dpT[8][4];
         mma_a_tileT(sT, ak, sQ[st], lane);        // S^T[key, q]
         mma_a_tileT(dpT, av, sdO[st], lane);      // dP^T[key, q]
+        // rows of S^T are keys: rows beyond Lk only feed their own (never stored) dK / dV rows, so no key mask is needed;
+        // queries beyond Lq carry lse = +inf -> p = 0.  The dropout rescale 1/(1-p) is folded into dss and the final dV.
 #pragma unroll
         for (int j = 0; j < 8; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                int ql = j * 8 + t * 2 + (e & 1);
-                int key = keyr[e >> 1];
-                float pv = key < p.Lk ? exp2f(sT[j][e] * sl2 - sLse[st][ql]) : 0.f;
+                const int ql = j * 8 + t * 2 + (e & 1);
+                const float pv = ex2(fmaf(sT[j][e], sl2, sLse[st][ql]));
                 float dpv = dpT[j][e];
                 float pd = pv;
                 if (p.drop_p > 0.f) {
-                    uint32_t bits = dropout_bits_rh(sRh[st][ql], (uint32_t)(key >> 1));
-                    bool keep = ((key & 1) ? (bits >> 16) : (bits & 0xffffu)) >= thresh;
-                    pd = keep ? pv * drop_scale : 0.f;
-                    dpv = keep ? dpv * drop_scale : 0.f;
+                    const uint32_t bits = dropout_bits_rh(sRh[st][ql], kpair[e >> 1]);
+                    const bool keep = ((bits >> kshift) & 0xffffu) >= thresh;
+                    if (!keep) { pd = 0.f; dpv = 0.f; }
                 }
-                sT[j][e] = pd;                                   // dropped probabilities (for dV)
-                dpT[j][e] = p.scale * pv * (dpv - sDelta[st][ql]); // scale * dS^T
+                sT[j][e] = pd;                                             // dropped probabilities (for dV), unscaled
+                dpT[j][e] = pv * fmaf(dpv, dss, sDelta[st][ql]);           // scale * dS^T
             }
         mma_p_tile(dv, sT, sdO[st], lane);        // dV += P_d^T dO
         mma_p_tile(dk, dpT, sQ[st], lane);        // dK += dS^T Q
@@ -320,7 +332,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             *reinterpret_cast<uint32_t *>(dK + (size_t)key * p.lddk + j * 8 + t * 2) = pack_bf16x2(dk[j][r * 2], dk[j][r * 2 + 1]);
-            *reinterpret_cast<uint32_t *>(dV + (size_t)key * p.lddv + j * 8 + t * 2) = pack_bf16x2(dv[j][r * 2], dv[j][r * 2 + 1]);
+            *reinterpret_cast<uint32_t *>(dV + (size_t)key * p.lddv + j * 8 + t * 2) = pack_bf16x2(dv[j][r * 2] * drop_scale, dv[j][r * 2 + 1] * drop_scale);
         }
     }
 }
@@ -362,13 +374,13 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
     for (int r = 0; r < 2; r++) {
         int q = q0 + warp * 16 + g + r * 8;
         size_t idx = ((size_t)b * p.H + h) * p.Lq + q;
-        lrow[r] = q < p.Lq ? p.lse[idx] * LOG2E : INFINITY;
-        drow[r] = q < p.Lq ? p.delta[idx] : 0.f;
+        lrow[r] = q < p.Lq ? -p.lse[idx] * LOG2E : -INFINITY;         // negated, log2 domain
+        drow[r] = q < p.Lq ? -p.delta[idx] * p.scale : 0.f;          // -scale * delta
     }
     const uint32_t thresh = dropout_thresh16(p.drop_p);
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
-    const float sl2 = p.scale * LOG2E;
+    const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
     const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
     const uint32_t rh[2] = {dropout_rowhash(seed, p.site, rowbase), dropout_rowhash(seed, p.site, rowbase + 8)};
 
@@ -396,11 +408,19 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
             }
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                int key = kbase + j * 8 + t * 2 + (e & 1);
-                float pv = key < p.Lk ? exp2f(s[j][e] * sl2 - lrow[e >> 1]) : 0.f;
-                float dpv = keep[e] ? dp[j][e] * drop_scale : 0.f;
-                s[j][e] = p.scale * pv * (dpv - drow[e >> 1]);  // scale * dS
+                const float pv = ex2(fmaf(s[j][e], sl2, lrow[e >> 1]));
+                const float dpv = keep[e] ? dp[j][e] : 0.f;
+                s[j][e] = pv * fmaf(dpv, dss, drow[e >> 1]);    // scale * dS
             }
+        }
+        // keys beyond Lk (last tile only): their zero-filled K rows give s = 0, p = exp(-lse), which overflows for rows whose
+        // scores are all very negative -- and inf * 0 would poison dQ
+        if (kbase + TKV > p.Lk) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (kbase + j * 8 + t * 2 + (e & 1) >= p.Lk) s[j][e] = 0.f;
         }
         mma_p_tile(dq, s, sK[kt & 1], lane);      // dQ += dS K
         __syncthreads();

@@ -122,7 +122,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- counter-based dropout RNG
-// 32 random bits for the counter (site, row, pair) under `seed`, from the "lowbias32" integer finaliser: one round for the
+// 32 random bits for the counter (site, row, pair) under `seed`, from the "lowbias32" integer finaliser: one full round for the
 // row (hoistable out of inner loops: dropout_rowhash) and one for the column pair.  One call serves two adjacent elements
 // (16 bits each): element (row, col) uses pair = col >> 1 and the low / high half for even / odd col.
 // keep <=> bits16 >= thresh16, thresh16 = round(p * 65536).  Forward and backward regenerate identical masks.
@@ -133,8 +133,12 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
 __device__ __forceinline__ uint32_t dropout_rowhash(uint64_t seed, uint32_t site, uint32_t row) {
     return lowbias32(row ^ (uint32_t)seed ^ (site * 0x9E3779B9U)) ^ (uint32_t)(seed >> 32);
 }
+// per-pair mixing: the row hash is already a full lowbias32 round, so the pair needs only the first half of one
+// (xorshift, multiply, xorshift: 7 integer ops per two elements -- this sits in the inner loop of the attention kernels)
 __device__ __forceinline__ uint32_t dropout_bits_rh(uint32_t rowhash, uint32_t pair) {
-    return lowbias32(rowhash ^ (pair * 0x85EBCA77U));
+    uint32_t x = rowhash ^ (pair * 0x85EBCA77U);
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15;
+    return x;
 }
 __device__ __forceinline__ uint32_t dropout_bits(uint64_t seed, uint32_t site, uint32_t row, uint32_t pair) {
     return dropout_bits_rh(dropout_rowhash(seed, site, row), pair);

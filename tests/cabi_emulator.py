@@ -81,7 +81,10 @@ def keep_mask(rows, cols, drop_p, seed, site, seed_ptr=None):
     r = np.asarray(rows, dtype=np.uint64)[:, None]
     c = np.asarray(cols, dtype=np.uint64)[None, :]
     rowhash = _lowbias32((r ^ (seed & 0xffffffff) ^ ((site * 0x9E3779B9) & 0xffffffff)) & 0xffffffff) ^ (seed >> 32)
-    h = _lowbias32((rowhash ^ (((c >> 1) * 0x85EBCA77) & 0xffffffff)) & 0xffffffff)
+    h = ((rowhash ^ (((c >> 1) * 0x85EBCA77) & 0xffffffff)) & 0xffffffff).astype(np.uint64)   # dropout_bits_rh (common.cuh)
+    h ^= h >> 16
+    h = (h * 0x7feb352d) & 0xffffffff
+    h ^= h >> 15
     bits = np.where((c & 1) == 1, h >> 16, h & 0xffff)
     thresh = int(drop_p * 65536.0 + 0.5)
     return torch.from_numpy(bits >= thresh)

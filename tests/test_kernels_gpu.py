@@ -261,6 +261,31 @@ def test_attention_fwd_bwd(ops, B, Lq, Lk, drop):
     assert float(dqk[:, d:].abs().max()) == 0
 
 
+def test_attention_bwd_very_negative_scores(ops):
+    """rows whose scores are all << 0 (lse < -88): exp(-lse) overflows on the zero-filled padding keys of the last tile;
+    the gradients must stay finite (regression: inf * 0 in dQ)"""
+    B, H, d, Lq, Lk, scale = 1, 8, 256, 70, 100, 32 ** -0.5
+    q = dev((rnd(B * Lq, d, seed=1) * 0.1 - 10.0).to(BF))
+    k = dev((rnd(B * Lk, d, seed=2) * 0.1 + 10.0).to(BF))
+    v = dev(rnd(B * Lk, d, seed=3).to(BF))
+    o = torch.zeros(B * Lq, d, dtype=BF, device="cuda")
+    lse = torch.zeros(B * H * Lq, dtype=F32, device="cuda")
+    ops.attn_fwd(q, k, v, d, d, d, o, d, lse, B, H, Lq, Lk, scale)
+    assert float(lse.max()) < -300
+    qf, kf, vf = (x.float().view(B, -1, d).clone().requires_grad_(True) for x in (q, k, v))
+    ref, ref_lse = attn_ref(qf, kf, vf, scale, None, 0.0)
+    close("attn out", o.view(B, Lq, d), ref, 2e-2, 2e-2)
+    do = dev(rnd(B * Lq, d, seed=5).to(BF))
+    gq, gk, gv = torch.autograd.grad(ref, [qf, kf, vf], do.float().view(B, Lq, d))
+    dq, dk, dv = (torch.zeros(B * n, d, dtype=BF, device="cuda") for n in (Lq, Lk, Lk))
+    delta = torch.zeros(B * H * max(Lq, Lk), dtype=F32, device="cuda")
+    ops.attn_bwd(q, k, v, o, do, d, d, d, d, d, lse, delta, dq, dk, dv, d, d, d, B, H, Lq, Lk, scale)
+    for name, got in (("dq", dq), ("dk", dk), ("dv", dv)):
+        assert bool(torch.isfinite(got.float()).all()), name
+    # (dQ / dK cancel catastrophically against the +-10 common mode of this contrived input; dV does not)
+    close("attn dv", dv.reshape(gv.shape), gv, 5e-2, 5e-2 * float(gv.abs().max()))
+
+
 # ------------------------------------------------------------------------------------------------ layer norm / elementwise
 def test_layernorm_fwd_bwd(ops):
     M, S, d = 1000, 250, 256
