@@ -141,6 +141,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
                     tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
                 }
+                if (kb == 0 && tma_epi && (p.residual || p.mask)) {
+                    // the epilogue's residual / mask tiles start their trip from DRAM now (into L2), not after the main loop
+                    for (int cb = 0; cb < BN / 64 && n0 + cb * 64 < p.N; cb++) {
+                        if (p.residual) tma_prefetch_2d(&map_r, n0 + cb * 64, m0);
+                        if (p.mask) tma_prefetch_2d(&map_m, n0 + cb * 64, m0);
+                    }
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -221,14 +228,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     parity ^= 1;
                 }
 #pragma unroll
-                for (int c16 = 0; c16 < 4; c16++) {
-                    uint32_t r[16];
-                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 64 + c16 * 16), r);
+                for (int c32 = 0; c32 < 2; c32++) {
+                    uint32_t r[32];                            // two TMEM loads in flight per wait
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 64 + c32 * 32), *reinterpret_cast<uint32_t (*)[16]>(&r[0]));
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 64 + c32 * 32 + 16), *reinterpret_cast<uint32_t (*)[16]>(&r[16]));
                     tc_wait_ld();
 #pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-                        const int n = nb + c16 * 16 + hf * 8;
-                        const uint32_t chunk = (uint32_t)(c16 * 2 + hf);
+                    for (int hf = 0; hf < 4; hf++) {
+                        const int n = nb + c32 * 32 + hf * 8;
+                        const uint32_t chunk = (uint32_t)(c32 * 4 + hf);
                         const uint32_t soff = row_off + ((chunk ^ sw) << 4);
                         float v[8];
 #pragma unroll
@@ -610,14 +618,15 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
 #pragma unroll
-                for (int c16 = 0; c16 < 4; c16++) {
-                    uint32_t r[16];
-                    tc_ld16(t_addr + (uint32_t)(cb * 64 + c16 * 16), r);
+                for (int c32 = 0; c32 < 2; c32++) {
+                    uint32_t r[32];                            // two TMEM loads in flight per wait
+                    tc_ld16(t_addr + (uint32_t)(cb * 64 + c32 * 32), *reinterpret_cast<uint32_t (*)[16]>(&r[0]));
+                    tc_ld16(t_addr + (uint32_t)(cb * 64 + c32 * 32 + 16), *reinterpret_cast<uint32_t (*)[16]>(&r[16]));
                     tc_wait_ld();
 #pragma unroll
-                    for (int hf = 0; hf < 2; hf++) {
-                        const int n = nb + c16 * 16 + hf * 8;
-                        const uint32_t soff = row_off + (((uint32_t)(c16 * 2 + hf) ^ sw) << 4);
+                    for (int hf = 0; hf < 4; hf++) {
+                        const int n = nb + c32 * 32 + hf * 8;
+                        const uint32_t soff = row_off + (((uint32_t)(c32 * 4 + hf) ^ sw) << 4);
                         float v[8], res[8], mk[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) { v[i] = __uint_as_float(r[hf * 8 + i]); res[i] = 0.f; mk[i] = 1.f; }
@@ -699,7 +708,7 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
 
 static int g_tma_epilogue = 1;
 static int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
-static long g_tcp_min_tiles = 64, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
+static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
 
@@ -834,8 +843,6 @@ extern "C" int detrb_set_tc_persistent(int enable)
 {
     int old = g_tc_persistent;
     g_tc_persistent = enable;
-    if (const char *e = getenv("DETRB_TCP_MIN_TILES")) g_tcp_min_tiles = atol(e);
-    if (const char *e = getenv("DETRB_TCP_MIN_NK256")) g_tcp_min_nk256 = atol(e);
     return old;
 }
 extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
@@ -848,6 +855,13 @@ template <bool IM2COL>
 static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls, bool *taken)
 {
     *taken = false;
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char *e = getenv("DETRB_TCP_MIN_TILES")) g_tcp_min_tiles = atol(e);
+        if (const char *e = getenv("DETRB_TCP_MIN_TILES256")) g_tcp_min_tiles256 = atol(e);
+        if (const char *e = getenv("DETRB_TCP_MIN_NK256")) g_tcp_min_nk256 = atol(e);
+    }
     const bool tma_epi = p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue;
     if (!g_tc_persistent || !tma_epi || p.Cin == 16) return DETRB_OK;
     const int nk = p.K / TBK;
@@ -861,7 +875,7 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
         // measured on B200 (profiles/r01_tcp_sweep.log): long k-loops are compute bound and gain 1.2-2x from the persistent
         // kernel (256-wide tiles once the k-loop amortises the wider epilogue); the HBM-bound 1x1 layers (K <= 256) are faster
         // on the one-tile kernel, whose 4 co-resident CTAs give the epilogue 16 warps per SM
-        if (nk >= g_tcp_min_nk256 && p.N % 256 == 0 && !both && mt * (p.N / 256) >= g_tcp_min_tiles) pick = 256;
+        if (nk >= g_tcp_min_nk256 && p.N % 256 == 0 && !both && mt * (p.N / 256) >= g_tcp_min_tiles256) pick = 256;
         else if (nk > 4 && p.N >= 128 && mt * ceil_div(p.N, 128) >= g_tcp_min_tiles) pick = 128;
         else if (nk == 4 && p.N == 64 && !p.residual && !p.mask && mt >= 4 * 148) pick = 64;
     }

@@ -25,6 +25,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// pull a 2-D tile into L2 only (no shared-memory destination, no barrier): hides DRAM latency of a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c, int w, int h, int n,
                                                 uint16_t off_w, uint16_t off_h) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"

@@ -221,9 +221,15 @@ bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 // small token counts (transformer: M = 800 / 8400) are latency bound and faster on the mma.sync split kernel
 bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 {
-    // large pixel counts (backbone) or large weight matrices (layer4 convs at M = 8400); small transformer linears stay on mma.sync
+    // large pixel counts (backbone) and the encoder-sized linears (M = 8400); the decoder's (M = 800) stay on the mma.sync split kernel
     if (p.Cin == 16) return true;        // space-to-depth stem: only this kernel masks the taps that do not exist in the 7x7 kernel
-    return p.M >= 16384 || (p.M >= 4096 && (long)p.N * p.K >= (1l << 20));
+    static long min_m = -1, min_nk = -1;                 // env overrides for tuning runs
+    if (min_m < 0) {
+        const char *e1 = getenv("DETRB_WGRAD_TC_MIN_M"), *e2 = getenv("DETRB_WGRAD_TC_MIN_NK");
+        min_m = e1 ? atol(e1) : 4096;
+        min_nk = e2 ? atol(e2) : (1l << 16);
+    }
+    return p.M >= 16384 || (p.M >= min_m && (long)p.N * p.K >= min_nk);
 }
 
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
