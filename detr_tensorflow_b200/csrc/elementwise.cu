@@ -238,12 +238,13 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
+    // grid = (row segments, OH, B): no 64-bit divisions in the index math
     const int cv = C / 8;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = (int64_t)B * OH * OW * cv;
-    if (idx >= total) return;
-    int c8 = idx % cv; int64_t pix = idx / cv;
-    int ox = pix % OW; int oy = (pix / OW) % OH; int b = pix / ((int64_t)OW * OH);
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ox = tx / cv, c8 = tx - ox * cv;
+    if (ox >= OW) return;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    const size_t pix = ((size_t)b * OH + oy) * OW + ox;
     float best[8]; int arg[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { best[i] = -INFINITY; arg[i] = 0; }
@@ -275,11 +276,11 @@ __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const 
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
     const int cv = C / 8;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = (int64_t)B * IH * IW * cv;
-    if (idx >= total) return;
-    int c8 = idx % cv; int64_t pix = idx / cv;
-    int ix = pix % IW; int iy = (pix / IW) % IH; int b = pix / ((int64_t)IW * IH);
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ix = tx / cv, c8 = tx - ix * cv;
+    if (ix >= IW) return;
+    const int iy = blockIdx.y, b = blockIdx.z;
+    const size_t pix = ((size_t)b * IH + iy) * IW + ix;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
@@ -296,11 +297,12 @@ __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const 
             float d[8];
             unpack8(*reinterpret_cast<const uint4 *>(dy + o), d);
             const int tap = kh * 3 + kw;
+            // byte-wise compare of the 8 argmax bytes with `tap`: (a ^ tap x 0x01010101) has a zero byte where they match
+            const uint32_t t4 = (uint32_t)tap * 0x01010101u;
+            const uint32_t m0 = a.x ^ t4, m1 = a.y ^ t4;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                int ai = ((i < 4 ? a.x : a.y) >> ((i & 3) * 8)) & 0xff;
-                if (ai == tap) acc[i] += d[i];
-            }
+            for (int i = 0; i < 8; i++)
+                if ((((i < 4 ? m0 : m1) >> ((i & 3) * 8)) & 0xffu) == 0u) acc[i] += d[i];
         }
     }
     float xv[8];
@@ -415,8 +417,8 @@ extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *ar
 {
     DETRB_REQUIRE(x && y && argmax && C % 8 == 0, "detrb_maxpool_fwd: bad args");
     DETRB_REQUIRE(OH == (IH + 2 - 3) / 2 + 1 && OW == (IW + 2 - 3) / 2 + 1, "detrb_maxpool_fwd: bad output size");
-    int64_t total = (int64_t)B * OH * OW * (C / 8);
-    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
+    DETRB_REQUIRE(OH <= 65535 && B <= 65535, "detrb_maxpool_fwd: grid too large");
+    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)ceil_div(OW * (C / 8), 256), (unsigned)OH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
     DETRB_CHECK_LAUNCH("maxpool_fwd_kernel");
     return DETRB_OK;
 }
@@ -425,8 +427,8 @@ extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, co
                                  int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream)
 {
     DETRB_REQUIRE(dy && argmax && x && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
-    int64_t total = (int64_t)B * IH * IW * (C / 8);
-    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
+    DETRB_REQUIRE(IH <= 65535 && B <= 65535, "detrb_maxpool_bwd: grid too large");
+    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(IW * (C / 8), 256), (unsigned)IH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
                                                                                           B, IH, IW, C, OH, OW);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
     return DETRB_OK;

@@ -25,6 +25,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// fetch a tensor map (kernel parameter) into the descriptor cache ahead of its first use
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
 // pull a 2-D tile into L2 only (no shared-memory destination, no barrier): hides DRAM latency of a later tma_load_2d
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");

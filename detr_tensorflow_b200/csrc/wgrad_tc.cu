@@ -72,6 +72,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     const int nsteps = (m_end - m_begin + WP - 1) / WP;     // >= 1 by construction of the grid
 
     if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_y);
+        tma_prefetch_desc(&map_x);
         for (int s = 0; s < STG; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,7 +228,7 @@ bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
     static long min_m = -1, min_nk = -1;                 // env overrides for tuning runs
     if (min_m < 0) {
         const char *e1 = getenv("DETRB_WGRAD_TC_MIN_M"), *e2 = getenv("DETRB_WGRAD_TC_MIN_NK");
-        min_m = e1 ? atol(e1) : 4096;
+        min_m = e1 ? atol(e1) : 512;
         min_nk = e2 ? atol(e2) : (1l << 16);
     }
     return p.M >= 16384 || (p.M >= min_m && (long)p.N * p.K >= min_nk);

@@ -57,7 +57,7 @@ def tcp_sweep():
     gemms = [(534400, 256, 64, "r"), (534400, 256, 64, "rm"), (534400, 64, 256, ""), (534400, 64, 64, ""), (133600, 512, 128, "r"),
              (133600, 512, 128, "rm"), (133600, 128, 512, ""), (33600, 1024, 256, "r"), (33600, 256, 1024, ""), (8400, 2048, 512, "r"),
              (8400, 512, 2048, ""), (8400, 2048, 256, ""), (8400, 256, 2048, "r"), (8400, 256, 256, "r")]
-    convs = [(8, 100, 167, 128), (8, 50, 84, 256), (8, 25, 42, 512)]
+    convs = [(8, 200, 334, 64), (8, 100, 167, 128), (8, 50, 84, 256), (8, 25, 42, 512)]
     def run(label, fn, flops, byts):
         row = {"shape": label}
         for name, mode, bn in (("1tile", 0, 0), ("p64", 2, 64), ("p128", 2, 128), ("p256", 2, 256), ("auto", 1, 0)):
