@@ -223,7 +223,7 @@ def main():
     # ------------------------------------------------------------------ end-to-end leg through the public API
     # the call a user makes: training.fit over an iterable of HOST batches (pinned fp32 images + padded targets); every step
     # copies its batch host->device inside the timed region and reads the step's loss back (on_step hook -> float())
-    Ke = min(K, 10)
+    Ke = K                                                              # same number of steps as the device-timed leg
     host_losses = []
 
     def on_step(step, total_loss, log):
@@ -235,7 +235,7 @@ def main():
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):                     # fit prints a progress line every 100 steps
-        D.training.fit(model, batches(2), opt, cfg, 0, None, on_step=on_step)          # warm-up (captures the step graph)
+        D.training.fit(model, batches(3), opt, cfg, 0, None, on_step=on_step)          # warm-up (captures the step graph)
         barrier()
         t0 = time.perf_counter()
         D.training.fit(model, batches(Ke), opt, cfg, 0, None, on_step=on_step)

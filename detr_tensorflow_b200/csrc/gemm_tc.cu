@@ -92,6 +92,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int nk = p.K / TBK;
 
     if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        if (tma_epi) {
+            tma_prefetch_desc(&map_c);
+            if (p.residual) tma_prefetch_desc(&map_r);
+            if (p.mask) tma_prefetch_desc(&map_m);
+        }
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
         mbar_init(epi_bar, 1);
@@ -483,6 +490,11 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t slot_bytes = 16384u * ((has_r ? 1u : 0u) + (has_m ? 1u : 0u));
 
     if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_c);
+        if (has_r) tma_prefetch_desc(&map_r);
+        if (has_m) tma_prefetch_desc(&map_m);
         for (int s = 0; s < PST; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < NACC; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }
         for (int i = 0; i < MAXRS; i++) { mbar_init(resid_full(i), 1); mbar_init(resid_empty(i), 4); }

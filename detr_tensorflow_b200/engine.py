@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from collections import OrderedDict
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -73,6 +75,8 @@ class Engine:
         self.acc = None
         # weight gradients run on a side stream, concurrently with the data-gradient chain (they only feed the optimizer)
         self.overlap_wgrad = self.device.type == "cuda"
+        self.overlap_fwd = os.environ.get("DETRB_NO_FWD_FORK") is None        # forward-pass branches on the side stream
+        self.overlap_dmem = os.environ.get("DETRB_NO_DMEM_FORK") is None      # d(memory) accumulation on the side stream
         self._wstream = None
         self._pending = {}
         self._w_last = None
@@ -498,6 +502,28 @@ class Engine:
             self._pending[self._key(t)] = done
         self._w_last = done
 
+    def _fork(self, fn):
+        """Run fn() on the side stream, ordered after everything enqueued on the main stream so far; returns the handle for
+        _join().  For branches of the forward pass whose inputs are ready and whose outputs are only needed later."""
+        if not (self.overlap_wgrad and self.overlap_fwd):
+            fn()
+            return None
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._wstream.wait_event(ev)
+        with torch.cuda.stream(self._wstream):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self._wstream)
+        return done
+
+    @staticmethod
+    def _join(done):
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+
     def _before_write(self, *tensors):
         """a main-stream kernel is about to overwrite these buffers: wait for side-stream readers still pending on them"""
         if not self._pending:
@@ -610,13 +636,15 @@ class Engine:
         x = a["pool"]
         for i, blk in enumerate(self.blocks):
             ihw, ohw = blk["in_hw"], blk["out_hw"]
-            self._conv_fwd(blk["c1"], x, ihw, ihw, a[f"b{i}_a1"])
-            self._conv_fwd(blk["c2"], a[f"b{i}_a1"], ihw, ohw, a[f"b{i}_a2"])
-            if blk["ds"]:
-                self._conv_fwd(blk["cd"], x, ihw, ohw, a[f"b{i}_idn"], relu=False)
+            ds = None
+            if blk["ds"]:                                     # the shortcut convolution runs beside conv1 -> conv2
+                ds = self._fork(lambda: self._conv_fwd(blk["cd"], x, ihw, ohw, a[f"b{i}_idn"], relu=False))
                 idn = a[f"b{i}_idn"]
             else:
                 idn = x
+            self._conv_fwd(blk["c1"], x, ihw, ihw, a[f"b{i}_a1"])
+            self._conv_fwd(blk["c2"], a[f"b{i}_a1"], ihw, ohw, a[f"b{i}_a2"])
+            self._join(ds)
             self._conv_fwd(blk["c3"], a[f"b{i}_a2"], ohw, ohw, a[f"b{i}_out"], relu=True, residual=idn)
             x = a[f"b{i}_out"]
         self.feat = x
@@ -631,8 +659,9 @@ class Engine:
         for l, E in enumerate(self.enc):
             e = lambda n: a[f"e{l}_{n}"]
             W = E["sa"]["inp"]
+            vj = self._fork(lambda: self._lin(xin, W.Wf[2 * d:], M, d, d, d, out=e("v"), bias=W.bias[2 * d:]))
             self._lin(xinp, W.Wf, M, 2 * d, d, d, out=e("qk"), bias=W.bias)
-            self._lin(xin, W.Wf[2 * d:], M, d, d, d, out=e("v"), bias=W.bias[2 * d:])
+            self._join(vj)
             self.launches += 1
             ops.attn_fwd(e("qk"), e("qk")[:, d:], e("v"), 2 * d, 2 * d, d, e("o"), d, e("lse"), B, Hh, S, S, scale,
                          **self._attn_drop(f"e{l}_attn"))
@@ -649,11 +678,21 @@ class Engine:
         self._mark("fwd_encoder")
         # ---------------- decoder (transformer.py:207-234, 104-133)
         tgt = a["tgt0"]
+        # the cross-attention key / value projections of the encoder memory do not depend on the decoder state: all layers'
+        # run on the side stream while the decoder's own chain proceeds
+        kv_ready = []
+        for l, D in enumerate(self.dec):
+            Wc = D["ca"]["inp"]
+
+            def kv(l=l, Wc=Wc):
+                self._lin(memp, Wc.Wf[d:], M, d, d, d, out=a[f"d{l}_k2"], bias=Wc.bias[d:])
+                self._lin(mem, Wc.Wf[2 * d:], M, d, d, d, out=a[f"d{l}_v2"], bias=Wc.bias[2 * d:])
+            kv_ready.append(self._fork(kv))
         for l, D in enumerate(self.dec):
             t = lambda n: a[f"d{l}_{n}"]
+            W = D["sa"]["inp"]
             ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d)
             self.launches += 1
-            W = D["sa"]["inp"]
             self._lin(t("tq"), W.Wf, Mq, 2 * d, d, d, out=t("qk"), bias=W.bias)
             self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:])
             self.launches += 1
@@ -664,8 +703,7 @@ class Engine:
             self._ln_fwd(t("pre1"), D["n1"], t("t1"), t("mean1"), t("rstd1"), Mq, y2=t("t1q"), pos=self.query_pos, S=Q)
             W = D["ca"]["inp"]
             self._lin(t("t1q"), W.Wf, Mq, d, d, d, out=t("q2"), bias=W.bias)
-            self._lin(memp, W.Wf[d:], M, d, d, d, out=t("k2"), bias=W.bias[d:])
-            self._lin(mem, W.Wf[2 * d:], M, d, d, d, out=t("v2"), bias=W.bias[2 * d:])
+            self._join(kv_ready[l])
             self.launches += 1
             ops.attn_fwd(t("q2"), t("k2"), t("v2"), d, d, d, t("o2"), d, t("lse2"), B, Hh, Q, S, scale,
                          **self._attn_drop(f"d{l}_attn2"))
@@ -782,8 +820,14 @@ class Engine:
             self._lin_wgrad(W, memp, a["gm_k2"], M, n_off=d, n_rows=d)
             self._lin_wgrad(W, mem, a["gm_v2"], M, n_off=2 * d, n_rows=d)
             # d memory accumulates over decoder layers (memory feeds every cross attention)
-            self._lin(a["gm_k2"], W.Wd[:, :, d:], M, d, d, W.ldd, out=a["g_mem"], residual=None if first_mem else a["g_mem"], ldr=d)
-            self._lin(a["gm_v2"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=a["g_mem"], residual=a["g_mem"], ldr=d)
+            # (side stream, in order with each other; only the encoder's backward needs g_mem -- joined there)
+            def dmem(W=W, first=first_mem):
+                self._lin(a["gm_k2"], W.Wd[:, :, d:], M, d, d, W.ldd, out=a["g_mem"], residual=None if first else a["g_mem"], ldr=d)
+                self._lin(a["gm_v2"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=a["g_mem"], residual=a["g_mem"], ldr=d)
+            if self.overlap_dmem:
+                self._on_wstream(dmem, (a["gm_k2"], a["gm_v2"]))
+            else:
+                dmem()
             first_mem = False
             self._lin(a["gq_q2"], W.Wd, Mq, d, d, W.ldd, out=a["gq_a"], residual=a["gq_b"], ldr=d)            # d t1
             # LN1
@@ -806,6 +850,7 @@ class Engine:
                 self._lin(a["gq_v"], W.Wd[:, :, 2 * d:], Mq, d, d, W.ldd, out=g_next, residual=a["gq_a"], ldr=d)
         self._mark("bwd_heads_decoder")
         # ---------------- encoder, last layer first.  g_mem = d y2 (last encoder layer output incl. its +pos use)
+        self._join_wgrad()                                     # g_mem (and the decoder's weight gradients) complete
         g_y = a["g_mem"]
         for l in reversed(range(self.nenc)):
             E = self.enc[l]
