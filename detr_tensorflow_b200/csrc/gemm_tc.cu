@@ -422,9 +422,6 @@ struct PLayout {
     static_assert(RING_BYTES >= 0, "persistent GEMM: stages do not fit");
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
 __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
     float2 t;
     t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y; t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;

@@ -176,10 +176,7 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(p.M == p.batch * p.OH * p.OW, "detrb_wgrad: M=%d != batch*OH*OW", p.M);
     DETRB_REQUIRE(p.ldy >= ((p.N + 7) & ~7) && p.ldy % 8 == 0, "detrb_wgrad: ldy=%d must cover N=%d rounded to 8", p.ldy, p.N);
     if (detrb_wgrad_tc_enabled() && detrb_wgrad_tc_supported(p) && detrb_wgrad_tc_profitable(p)) {           // tcgen05 / TMA im2col / TMEM
-        int rc = detrb_wgrad_tc(p, stream);
-        if (rc) return rc;
-        if (p.dbias) return detrb_colsum(p.dY, p.ldy, p.M, p.N, p.rowscale, p.dbias, stream_);
-        return DETRB_OK;
+        return detrb_wgrad_tc(p, stream);                      // bias gradient fused (k-tile 0 CTAs)
     }
     DETRB_REQUIRE(p.Cin != 16, "detrb_wgrad: 16-channel (space-to-depth stem) gradients need the tcgen05 kernel (detrb_set_tc_wgrad(1))");
     const bool stem = (p.Cin == 4);

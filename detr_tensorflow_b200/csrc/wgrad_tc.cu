@@ -71,10 +71,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     const int m_end = min(p.M, m_begin + pix_per_split);
     const int nsteps = (m_end - m_begin + WP - 1) / WP;     // >= 1 by construction of the grid
 
+    // bias gradient (column sums of dY) fused: the k-tile-0 CTAs' otherwise idle epilogue warps add up the dY boxes of every stage
+    const bool do_bias = p.dbias != nullptr && blockIdx.x == 0;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_y);
         tma_prefetch_desc(&map_x);
-        for (int s = 0; s < STG; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STG; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_bias ? 5 : 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -158,6 +160,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
         }
         __syncwarp();
     } else {
+        if (do_bias) {
+            // thread -> channel pair 2cp, 2cp+1 of the CTA's 128 and one half of the stage's 64 pixel rows.  dY box layout: pixel
+            // row r at r*128 B, its 16-byte chunk c (8 channels) at chunk c ^ (r % 8) (128-byte swizzle)
+            const int te = threadIdx.x - 64, cp = te & 63, half = te >> 6;
+            const uint32_t box_off = (uint32_t)(cp >> 5) * BOX_BYTES, chunk = (uint32_t)((cp & 31) >> 2), within = (uint32_t)(cp & 3) * 4u;
+            float s0 = 0.f, s1 = 0.f;
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t base = smem_base + stage * STG_BYTES + box_off + within;
+#pragma unroll 8
+                for (int r = half * 32; r < half * 32 + 32; r++) {
+                    uint32_t u;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(base + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+                    const float2 f = unpack_bf16x2(u);
+                    s0 += f.x; s1 += f.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(stage));            // this warp is done reading the stage
+                if (++stage == STG) { stage = 0; phase ^= 1; }
+            }
+            const int nb = n0 + 2 * cp;
+            if (nb < p.N) atomicAdd(p.dbias + nb, s0 * (p.rowscale ? p.rowscale[nb] : 1.f));
+            if (nb + 1 < p.N) atomicAdd(p.dbias + nb + 1, s1 * (p.rowscale ? p.rowscale[nb + 1] : 1.f));
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;
@@ -286,7 +313,7 @@ static int g_wgrad_tc_enabled = 1;     // validated on B200 (tests/test_gemm_tc_
 extern "C" int detrb_set_tc_wgrad(int enable) { int old = g_wgrad_tc_enabled; g_wgrad_tc_enabled = enable; return old; }
 bool detrb_wgrad_tc_enabled() { return g_wgrad_tc_enabled != 0; }
 
-// test entry: force the tcgen05 weight-gradient kernel (no bias gradient)
+// test entry: force the tcgen05 weight-gradient kernel
 extern "C" int detrb_wgrad_tc_force(const detrb_wgrad_t *pp, detrb_stream_t stream)
 {
     if (!pp) DETRB_FAIL(DETRB_E_BADARG, "detrb_wgrad_tc_force: null params");

@@ -207,8 +207,11 @@ def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
     dW_a = torch.zeros(cout, K, dtype=F32, device="cuda")
     dW_b = torch.zeros(cout, K, dtype=F32, device="cuda")
     ops.wgrad(x, cin, dy, ldy, M, cout, K, g, dW_a, K, rowscale=scale)
-    ops.wgrad(x, cin, dy, ldy, M, cout, K, g, dW_b, K, rowscale=scale, force_tc=True)
+    db = torch.zeros(cout, dtype=F32, device="cuda")
+    ops.wgrad(x, cin, dy, ldy, M, cout, K, g, dW_b, K, rowscale=scale, dbias=db, force_tc=True)
     torch.cuda.synchronize()
+    ref_b = dy[:, :cout].float().sum(0) * scale
+    check("fused bias gradient", db, ref_b, 2e-3, 2e-3 * float(ref_b.abs().max()) + 1e-3)
     xt = x.float().permute(0, 3, 1, 2)
     wt = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
     o = F.conv2d(xt, wt, stride=stride, padding=pad)
