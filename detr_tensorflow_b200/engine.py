@@ -21,7 +21,7 @@ import os
 import torch
 
 from . import _lib, ops
-from .networks.spec import RESNET_STAGES, model_params
+from .networks.spec import RESNET_STAGES, head_names, model_params
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -52,7 +52,7 @@ class Slot:
 
 class Engine:
     def __init__(self, device="cuda", backbone="resnet50", num_classes=92, num_encoder_layers=6,
-                 num_decoder_layers=6, num_queries=100, dropout=0.1, seed=0):
+                 num_decoder_layers=6, num_queries=100, dropout=0.1, seed=0, nb_class=None):
         self.device = torch.device(device)
         self.lib = _lib.lib()
         if self.device.type != "cuda" and not getattr(_lib, "_EMULATED", False):
@@ -60,12 +60,14 @@ class Engine:
         if self.device.type == "cuda":
             _lib.check(self.lib.detrb_check_device())
         self.backbone_name = backbone
-        self.C = num_classes
+        self.nb_class = nb_class                    # fine-tuning heads (detr.py:94-114): C = nb_class, 'nlayers' group
+        self.C = num_classes if nb_class is None else int(nb_class)
         self.nenc, self.ndec, self.Q = num_encoder_layers, num_decoder_layers, num_queries
         self.d, self.H, self.dff = 256, 8, 2048
         self.dropout = dropout
         self.base_seed = seed
-        self.spec = model_params(num_classes, backbone, num_encoder_layers, num_decoder_layers, 256, 2048, num_queries)
+        self.spec = model_params(num_classes, backbone, num_encoder_layers, num_decoder_layers, 256, 2048, num_queries,
+                                 nb_class=nb_class)
         self._build_params()
         self.plan_key = None
         self._in_backward = False
@@ -95,7 +97,7 @@ class Engine:
             off = _round_up(off + n, 64)
             return o
         layout = {}
-        for group in ("backbone", "transformers"):
+        for group in GROUPS:
             for name, p in spec.items():
                 if p.group != group:
                     continue
@@ -131,9 +133,10 @@ class Engine:
         self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
         self.nchunks = len(chunks)
         self.group_range = {}
-        for g in ("backbone", "transformers"):
+        for g in GROUPS:
             offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
-            self.group_range[g] = (offs[0][0], offs[-1][0] + offs[-1][1])
+            if offs:                                     # 'nlayers' is empty for the include_top=True model
+                self.group_range[g] = (offs[0][0], offs[-1][0] + offs[-1][1])
 
         def view(arena, name):
             o, n = layout[name]
@@ -167,6 +170,8 @@ class Engine:
             kname = kname or prefix + "/kernel"
             bname = bname or prefix + "/bias"
             o_, i_ = spec[kname].shape
+            if spec[kname].kind == "dense_w":            # Keras Dense kernel [in, out]; stored [out, in] in the arena
+                o_, i_ = i_, o_
             s = Slot()
             s.name = prefix
             s.N, s.taps, s.Cin, s.K = o_, 1, i_, i_
@@ -215,8 +220,7 @@ class Engine:
                                  l1=lin_slot(p + "/linear1"), l2=lin_slot(p + "/linear2"),
                                  n1=ln_views(p + "/norm1"), n2=ln_views(p + "/norm2"), n3=ln_views(p + "/norm3")))
         self.dec_norm = ln_views("transformer/decoder/norm")
-        self.h_cls = lin_slot("class_embed")
-        self.h_b0, self.h_b1, self.h_b2 = lin_slot("bbox_embed_0"), lin_slot("bbox_embed_1"), lin_slot("bbox_embed_2")
+        self.h_cls, self.h_b0, self.h_b1, self.h_b2 = (lin_slot(n) for n in head_names(self.nb_class))
         self.bn = {n: torch.zeros(p.shape, dtype=F32, device=dev) for n, p in spec.items() if p.kind.startswith("bn_")}
         self.query_embed = torch.zeros(self.Q, self.d, dtype=F32, device=dev)
         self.query_pos = torch.zeros(self.Q, self.d, dtype=BF16, device=dev)
@@ -237,6 +241,8 @@ class Engine:
                     t = t.permute(3, 0, 1, 2).contiguous()              # [co, kh, kw, ci]
                     if name == "backbone/conv1/kernel":
                         t = self._stem_to_s2d(t)
+                elif p.kind == "dense_w":
+                    t = t.t().contiguous()                               # [in, out] -> [out, in]
                 o, n = self.layout[name]
                 self.params[o:o + n].copy_(t.reshape(-1))
         # FrozenBatchNorm2D (custom_layers.py:21-24): scale = w * rsqrt(var + eps); shift = b - mean * scale
@@ -271,6 +277,8 @@ class Engine:
             else:
                 t = t.reshape(co, kh, kw, ci)
             return t.permute(1, 2, 3, 0).contiguous()
+        if p.kind == "dense_w":
+            return t.reshape(p.shape[1], p.shape[0]).t().contiguous()
         return t.reshape(p.shape)
 
     @staticmethod

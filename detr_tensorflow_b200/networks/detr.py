@@ -46,12 +46,16 @@ def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_ba
         raise NotImplementedError("tf_backbone=True (keras.applications ResNet50, detr.py:146-148) is out of scope")
     if weights is not None:
         raise NotImplementedError("pretrained checkpoint download (networks/weights.py) is out of scope: pass params=")
-    if nb_class is not None:
-        raise NotImplementedError("fine-tuning heads (add_heads_nlayers, detr.py:94-114) are a 'next' row (SURVEY 8f N4)")
+    # detr.py:178-181: nb_class only matters when include_top is False -> add_heads_nlayers (detr.py:94-114): new Keras
+    # Dense heads `cls_layer` (nb_class logits) and `pos_layer` (256-256-4 MLP), registered as config.nlayers (detr.py:103)
+    finetune = (include_top is False) and (nb_class is not None)
     eng = Engine(device=device, backbone=backbone, num_classes=92, num_encoder_layers=num_encoder_layers,
-                 num_decoder_layers=num_decoder_layers, seed=seed, dropout=dropout)
+                 num_decoder_layers=num_decoder_layers, seed=seed, dropout=dropout, nb_class=nb_class if finetune else None)
+    if finetune:
+        config.add_nlayers(["cls_layer", "pos_layer"])
     if params is None:
         params = init_params(seed, backbone=backbone, num_encoder_layers=num_encoder_layers,
-                             num_decoder_layers=num_decoder_layers)
+                             num_decoder_layers=num_decoder_layers, nb_class=nb_class if finetune else None)
     eng.load_params(params)
-    return DetrModel(eng, include_top, "detr_finetuning" if include_top else "detr")
+    has_heads = bool(include_top) or finetune
+    return DetrModel(eng, has_heads, "detr_finetuning" if has_heads else "detr")

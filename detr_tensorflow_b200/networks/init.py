@@ -31,7 +31,7 @@ def init_params(seed=0, **kw):
             t = 0.05 * torch.randn(shape, generator=g, dtype=torch.float64)
         elif kind == "bn_var":
             t = 1.0 + 0.1 * torch.rand(shape, generator=g, dtype=torch.float64)
-        elif kind in ("linear_w", "embed"):
+        elif kind in ("linear_w", "embed", "dense_w"):
             lim = math.sqrt(6.0 / (shape[0] + shape[1]))
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * lim
         elif kind == "linear_b":

@@ -20,9 +20,11 @@ class P:
 
 
 def model_params(num_classes=92, backbone="resnet50", num_encoder_layers=6, num_decoder_layers=6,
-                 model_dim=256, ffn_dim=2048, num_queries=100):
-    """OrderedDict name -> P.  kind: conv | bn_w | bn_b | bn_mean | bn_var | linear_w | linear_b | ln_g | ln_b | embed.
-    group: 'backbone' | 'transformers' | None (non-trainable / in no optimizer group)."""
+                 model_dim=256, ffn_dim=2048, num_queries=100, nb_class=None):
+    """OrderedDict name -> P.  kind: conv | bn_w | bn_b | bn_mean | bn_var | linear_w | dense_w | linear_b | ln_g | ln_b |
+    embed.  group: 'backbone' | 'transformers' | 'nlayers' | None (non-trainable / in no optimizer group).
+    nb_class: the fine-tuning model of add_heads_nlayers (detr.py:94-114) -- `cls_layer` / `pos_layer` Keras Dense heads
+    (kernel [in, out]) in the 'nlayers' group (optimizers.py:39-43) instead of class_embed / bbox_embed_*."""
     out = OrderedDict()
 
     def add(name, shape, kind, group):
@@ -87,8 +89,21 @@ def model_params(num_classes=92, backbone="resnet50", num_encoder_layers=6, num_
     ln("transformer/decoder/norm")
     # query_embed(None) is evaluated outside the Keras graph: in no optimizer group
     add("query_embed/kernel", (num_queries, d), "embed", None)
-    lin("class_embed", num_classes, d)
-    lin("bbox_embed_0", d, d)
-    lin("bbox_embed_1", d, d)
-    lin("bbox_embed_2", 4, d)
+    if nb_class is None:
+        lin("class_embed", num_classes, d)
+        lin("bbox_embed_0", d, d)
+        lin("bbox_embed_1", d, d)
+        lin("bbox_embed_2", 4, d)
+    else:
+        for p, i, o in (("cls_layer", d, nb_class), ("pos_layer/dense", d, d), ("pos_layer/dense_1", d, d),
+                        ("pos_layer/dense_2", d, 4)):
+            add(p + "/kernel", (i, o), "dense_w", "nlayers")
+            add(p + "/bias", (o,), "linear_b", "nlayers")
     return out
+
+
+def head_names(nb_class=None):
+    """(class head, box MLP layer 0, 1, 2) slot prefixes"""
+    if nb_class is None:
+        return "class_embed", "bbox_embed_0", "bbox_embed_1", "bbox_embed_2"
+    return "cls_layer", "pos_layer/dense", "pos_layer/dense_1", "pos_layer/dense_2"

@@ -39,7 +39,7 @@ RESNET_STAGES = {
 
 
 def param_shapes(num_classes=92, backbone="resnet50", num_encoder_layers=6,
-                 num_decoder_layers=6, model_dim=256, ffn_dim=2048, num_queries=100):
+                 num_decoder_layers=6, model_dim=256, ffn_dim=2048, num_queries=100, nb_class=None):
     """Ordered {name: (shape, kind)}; kind in {conv, bn_w, bn_b, bn_mean, bn_var, linear_w,
     linear_b, ln_g, ln_b, embed}.  Layouts are the reference's: Conv2D kernels HWIO
     (Keras), Linear kernels [out, in] (custom_layers.py:41-47), packed in_proj [3d, d]
@@ -105,10 +105,18 @@ def param_shapes(num_classes=92, backbone="resnet50", num_encoder_layers=6,
         ln(p + "/norm3")
     ln("transformer/decoder/norm")
     s["query_embed/kernel"] = ((num_queries, d), "embed")
-    lin("class_embed", num_classes, d)
-    lin("bbox_embed_0", d, d)
-    lin("bbox_embed_1", d, d)
-    lin("bbox_embed_2", 4, d)
+    if nb_class is None:
+        lin("class_embed", num_classes, d)
+        lin("bbox_embed_0", d, d)
+        lin("bbox_embed_1", d, d)
+        lin("bbox_embed_2", 4, d)
+    else:
+        # add_heads_nlayers (detr.py:94-114): Keras Dense layers, kernel [in, out] (x @ kernel + bias);
+        # pos_layer is a Sequential of three Dense layers (relu, relu, sigmoid)
+        for p, i, o in (("cls_layer", d, nb_class), ("pos_layer/dense", d, d), ("pos_layer/dense_1", d, d),
+                        ("pos_layer/dense_2", d, 4)):
+            s[p + "/kernel"] = ((i, o), "dense_w")
+            s[p + "/bias"] = ((o,), "linear_b")
     return s
 
 
@@ -146,9 +154,9 @@ def init_params(seed=0, dtype=torch.float32, stable=True, **kw):
             t = 0.05 * torch.randn(shape, generator=g, dtype=torch.float64)
         elif kind == "bn_var":
             t = 1.0 + 0.1 * torch.rand(shape, generator=g, dtype=torch.float64)
-        elif kind in ("linear_w", "embed"):
+        elif kind in ("linear_w", "embed", "dense_w"):
             o, i = shape
-            lim = math.sqrt(6.0 / (o + i))      # Glorot uniform, custom_layers.py:43-44
+            lim = math.sqrt(6.0 / (o + i))      # Glorot uniform, custom_layers.py:43-44 (Keras Dense default too)
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * lim
         elif kind == "linear_b":
             t = 0.02 * torch.randn(shape, generator=g, dtype=torch.float64)
@@ -316,10 +324,17 @@ def detr_forward(P, images_nhwc, backbone="resnet50", num_encoder_layers=6, num_
     pos = position_embedding_sine(h, w, dtype=feat.dtype).reshape(h * w, -1)
     hs = transformer_forward(P, proj, pos, num_encoder_layers, num_decoder_layers,
                              dropout_p if training else 0.0, gen)
-    logits = linear(hs, P, "class_embed")
-    t = F.relu(linear(hs, P, "bbox_embed_0"))
-    t = F.relu(linear(t, P, "bbox_embed_1"))
-    boxes = torch.sigmoid(linear(t, P, "bbox_embed_2"))
+    if "cls_layer/kernel" in P:                         # fine-tuning heads, detr.py:94-114 (Keras Dense: x @ kernel + bias)
+        dense = lambda x, p: x @ P[p + "/kernel"] + P[p + "/bias"]
+        logits = dense(hs, "cls_layer")
+        t = F.relu(dense(hs, "pos_layer/dense"))
+        t = F.relu(dense(t, "pos_layer/dense_1"))
+        boxes = torch.sigmoid(dense(t, "pos_layer/dense_2"))
+    else:
+        logits = linear(hs, P, "class_embed")
+        t = F.relu(linear(hs, P, "bbox_embed_0"))
+        t = F.relu(linear(t, P, "bbox_embed_1"))
+        boxes = torch.sigmoid(linear(t, P, "bbox_embed_2"))
     out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1],
            "aux": [{"pred_logits": logits[i], "pred_boxes": boxes[i]}
                    for i in range(num_decoder_layers - 1)]}
@@ -531,6 +546,8 @@ def param_group(name):
         return "backbone"
     if name.startswith("query_embed"):
         return None
+    if name.startswith("cls_layer/") or name.startswith("pos_layer/"):
+        return "nlayers"                # optimizers.py:39-43 (config.nlayers = ["cls_layer", "pos_layer"], detr.py:103)
     return "transformers"
 
 

@@ -197,3 +197,57 @@ def test_data_parallel_two_ranks_gloo(tmp_path):
         a, b = dp["grads"][k], single["grads"][k]
         if float(b.norm()) > 1e-6:
             assert rel(a, b) < 2e-3, (k, rel(a, b))
+
+
+def test_finetune_heads_nlayers_group(emu):
+    """get_detr_model(include_top=False, nb_class=N) (detr.py:94-114, the finetune_*.py scripts): Keras-Dense heads
+    `cls_layer` / `pos_layer` in the 'nlayers' optimizer group (optimizers.py:39-43); only that group is applied when
+    train_nlayers alone is set (finetune_voc.py:33-36 pattern), the other variables stay bit-identical."""
+    import detr_tensorflow_b200 as D
+    NB = 4                                                # 3 classes + background (class 0 in the VOC/CSV loaders)
+    P = O.init_params(seed=3, num_encoder_layers=NE, num_decoder_layers=ND, nb_class=NB)
+    assert P["cls_layer/kernel"].shape == (256, NB) and P["pos_layer/dense_2/kernel"].shape == (256, 4)
+    assert "class_embed/kernel" not in P
+    img = torch.randn(2, 64, 96, 3, generator=torch.Generator().manual_seed(3))
+    tb, tc = O.synthetic_targets(2, n=4, num_classes=NB - 1, seed=3)
+    tc = tc + (tb[:, :, 2:3] > 0).long()                  # class ids 1..NB-1, background = 0
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 0, 2, None
+    cfg.train_backbone, cfg.train_transformers, cfg.train_nlayers = False, False, True
+    cfg.nlayers_lr = 1e-2
+    model = D.get_detr_model(cfg, include_top=False, nb_class=NB, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu",
+                             params=P, dropout=0.0)
+    assert cfg.nlayers == ["cls_layer", "pos_layer"]      # detr.py:103
+    out = model(img, training=False)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img, num_encoder_layers=NE, num_decoder_layers=ND)
+    assert out["pred_logits"].shape == (2, 100, NB) and len(out["aux"]) == ND - 1
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 1e-4 and rel(out["pred_boxes"], ref["pred_boxes"]) < 1e-4
+    opt = D.setup_optimizers(model, cfg)
+    assert len(opt["nlayers_variables"]) == 8 and sum(v.numel() for v in opt["nlayers_variables"]) == 256 * NB + NB + 2 * (256 * 256 + 256) + 256 * 4 + 4
+    eng = model.engine
+    m_out, total_loss, log, gsteps = D.training.run_train_step(model, img, tb, tc, opt, cfg)
+    match = eng.a["match"].view(ND, 2, 100).clone()
+    _, ototal, olog, g = O.train_step(P, img, tb, tc, background_class=0, num_encoder_layers=NE, num_decoder_layers=ND,
+                                      match_override=match)
+    assert abs(float(total_loss) - float(ototal)) < 1e-4 * abs(float(ototal))
+    grads = eng.export_grads()
+    assert set(grads) == set(g)
+    for n_ in g:
+        if O.param_group(n_) == "nlayers":
+            assert grads[n_].shape == P[n_].shape and rel(grads[n_], g[n_]) < 2e-3, n_
+    for name in gsteps:
+        D.optimizers.aggregate_grad_and_apply(name, opt, gsteps[name]["gradients"], 0, cfg)
+    assert opt["nlayers_optimizer"].iterations == 1 and opt["backbone_optimizer"].iterations == 0
+    new = model.export_params()
+    for n_ in P:
+        if O.param_group(n_) == "nlayers":
+            p = P[n_].clone()
+            O.adam_clipnorm_step(p, g[n_], torch.zeros_like(p), torch.zeros_like(p), 1, cfg.nlayers_lr, 0.1)
+            assert rel(new[n_] - P[n_], p - P[n_]) < 5e-2, n_
+        else:
+            assert torch.equal(new[n_], P[n_]), n_         # frozen groups untouched
+    # include_top=False without nb_class: the bare transformer output hs [L, B, 100, 256] (detr.py:177-179)
+    bare = D.get_detr_model(D.TrainingConfig(), include_top=False, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu",
+                            params=O.init_params(seed=3, num_encoder_layers=NE, num_decoder_layers=ND))
+    assert tuple(bare(img, training=False).shape) == (ND, 2, 100, 256)

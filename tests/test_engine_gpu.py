@@ -148,3 +148,73 @@ def test_multi_tensor_weight_refresh(D, setup):
         if s.Wd is not None:
             assert torch.equal(s.Wd[:, :, :s.N], wb.permute(2, 1, 0)), name
             assert float(s.Wd[:, :, s.N:].float().abs().max()) == 0 if s.ldd > s.N else True
+
+
+def test_finetune_heads_nlayers_gpu(D):
+    """detr.py:94-114 fine-tuning model (nb_class heads, Keras Dense [in,out] kernels, 'nlayers' group) on the CUDA path:
+    forward parity, gradients of the new layers under the same assignment, and an nlayers-only Adam apply."""
+    from oracle import detr_oracle as O
+    NB = 4
+    P = O.init_params(seed=5, nb_class=NB)
+    img = torch.randn(2, 128, 160, 3, generator=torch.Generator().manual_seed(5))
+    tb, tc = O.synthetic_targets(2, n=4, num_classes=NB - 1, seed=5)
+    tc = tc + (tb[:, :, 2:3] > 0).long()
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 0, 2, None
+    cfg.train_backbone, cfg.train_transformers, cfg.train_nlayers = False, False, True
+    cfg.nlayers_lr = 1e-2
+    model = D.get_detr_model(cfg, include_top=False, nb_class=NB, params=P, dropout=0.0)
+    assert cfg.nlayers == ["cls_layer", "pos_layer"]
+    out = model(img, training=False)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img)
+    assert out["pred_logits"].shape == (2, 100, NB) and len(out["aux"]) == 5
+    # tolerance: bf16 storage through the whole network (same as test_forward_parity)
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    opt = D.setup_optimizers(model, cfg)
+    eng = model.engine
+    before = model.export_params()
+    m_out, total_loss, log, gsteps = D.training.run_train_step(model, img, tb, tc, opt, cfg)
+    match = eng.a["match"].view(6, 2, 100).clone().cpu()
+    _, ototal, olog, g = O.train_step(P, img, tb, tc, background_class=0, match_override=match)
+    assert abs(float(total_loss) - float(ototal)) < 3e-2 * abs(float(ototal))
+    grads = eng.export_grads()
+    for n_ in g:
+        if O.param_group(n_) == "nlayers":
+            assert rel(grads[n_], g[n_]) < 0.15, (n_, rel(grads[n_], g[n_]))      # head gradients: bf16 noise level
+    for name in gsteps:
+        D.optimizers.aggregate_grad_and_apply(name, opt, gsteps[name]["gradients"], 0, cfg)
+    torch.cuda.synchronize()
+    assert opt["nlayers_optimizer"].iterations == 1 and opt["backbone_optimizer"].iterations == 0
+    after = model.export_params()
+    for n_ in P:
+        if O.param_group(n_) == "nlayers":
+            assert float((after[n_] - before[n_]).abs().max()) > 0, n_
+        else:
+            assert torch.equal(after[n_], before[n_]), n_
+
+
+def test_resnet101_backbone_forward(D):
+    """BASELINE configs[3]: DETR-R101 (23 bottlenecks in layer3, resnet_backbone.py:52-66) through the same kernels."""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=2, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1)
+    img = torch.randn(1, 128, 160, 3, generator=torch.Generator().manual_seed(2))
+    model = D.get_detr_model(D.TrainingConfig(), include_top=True, params=P, dropout=0.0, backbone="resnet101",
+                             num_encoder_layers=1, num_decoder_layers=1)
+    out = model(img, training=False)
+    with torch.no_grad():
+        ref = O.detr_forward(P, img, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1)
+        feat = O.backbone_forward(P, img, "resnet101")
+    eng = model.engine
+    assert len(eng.blocks) == 33 and eng.total > 45_000_000          # 17 extra layer3 blocks (x 1 114 112 parameters)
+    assert rel(eng.feat.view(feat.shape), feat) < 4e-2
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    # one full train step runs (backward through 33 blocks, optimizer over the larger arena)
+    tb, tc = O.synthetic_targets(1, n=3, seed=2)
+    eng.set_targets(tb, tc)
+    eng.set_lrs(1e-5, 1e-4)
+    eng.set_enabled(True, True)
+    eng.train_step(91, 0.1)
+    torch.cuda.synchronize()
+    t = float(eng.a["total"][0])
+    assert t == t and 0 < t < 1e3
