@@ -115,6 +115,129 @@ def cpu_oracle_step_time(H, W, threads, steps=1, warmup=0):
     return (time.time() - t0) / steps
 
 
+def c5_inputs(B=256, Q=100, C=92, n=20, seed=1234, layers=1):
+    """SURVEY 8(d) C5 (BASELINE configs[4]): logits ~ N(0,1) [B,100,92]; pred boxes cx,cy~U(.05,.95), w,h~U(.02,.5);
+    n=20 targets per image; seed 1234.  `layers` stacks independent decoder-layer outputs ([L,B,Q,*])."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(layers, B, Q, C, generator=g)
+    boxes = torch.cat([torch.rand(layers, B, Q, 2, generator=g) * 0.9 + 0.05,
+                       torch.rand(layers, B, Q, 2, generator=g) * 0.48 + 0.02], -1)
+    tb, tc = synthetic_targets(B, seed, n)
+    return logits, boxes, tb, tc
+
+
+def synthetic_targets(B, seed, n=20):
+    """T0 wire format (data/processing.py:35-55): row 0 = [n,0,0,0], rows 1..n = (cx,cy,w,h); classes in t_class rows 1..n"""
+    import torch
+    g = torch.Generator().manual_seed(seed + 7)
+    tb = torch.zeros(B, 100, 4)
+    tc = torch.zeros(B, 100, 1, dtype=torch.int64)
+    for b in range(B):
+        tb[b, 0, 0] = n
+        tb[b, 1:1 + n, :2] = torch.rand(n, 2, generator=g) * 0.8 + 0.1
+        tb[b, 1:1 + n, 2:] = torch.rand(n, 2, generator=g) * 0.48 + 0.02
+        tc[b, 1:1 + n, 0] = torch.randint(0, 91, (n,), generator=g)
+    return tb, tc
+
+
+def matcher_cpu_us_per_image(logits, boxes, tb, tc, max_images=256):
+    """The reference's matcher arithmetic on ONE host core, the way the reference runs it (python loop over images under the
+    GIL, hungarian_matching.py:163-203): numpy cost build + the real scipy.optimize.linear_sum_assignment."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    lg, bx = logits[0].numpy(), boxes[0].numpy()
+    tbn, tcn = tb.numpy(), tc.numpy()
+    nimg = min(max_images, lg.shape[0])
+
+    def xyxy(b):
+        return np.clip(np.concatenate([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], -1), 0.0, 1.0)
+    t0 = time.perf_counter()
+    for i in range(nimg):
+        n = int(tbn[i, 0, 0])
+        t_b, t_c = tbn[i, 1:1 + n], tcn[i, 1:1 + n, 0]
+        e = np.exp(lg[i] - lg[i].max(-1, keepdims=True))
+        prob = e / e.sum(-1, keepdims=True)
+        cost_class = -prob[:, t_c]
+        cost_bbox = np.abs(bx[i][:, None, :] - t_b[None, :, :]).sum(-1)
+        p, t = xyxy(bx[i]), xyxy(t_b)
+        area_p, area_t = (p[:, 2] - p[:, 0]) * (p[:, 3] - p[:, 1]), (t[:, 2] - t[:, 0]) * (t[:, 3] - t[:, 1])
+        lt, rb = np.maximum(p[:, None, :2], t[None, :, :2]), np.minimum(p[:, None, 2:], t[None, :, 2:])
+        wh = np.clip(rb - lt, 0, None)
+        inter = wh[..., 0] * wh[..., 1]
+        union = area_p[:, None] + area_t[None, :] - inter
+        iou = inter / union
+        elt, erb = np.minimum(p[:, None, :2], t[None, :, :2]), np.maximum(p[:, None, 2:], t[None, :, 2:])
+        ewh = np.clip(erb - elt, 0, None)
+        earea = ewh[..., 0] * ewh[..., 1]
+        giou = iou - (earea - union) / earea
+        cost = 5.0 * cost_bbox + 1.0 * cost_class + 2.0 * (-giou)
+        linear_sum_assignment(cost.astype(np.float32))
+    return (time.perf_counter() - t0) / nimg * 1e6
+
+
+def matcher_microbench(D, iters=20):
+    """BASELINE metric part 2, 'matcher us/image' (configs[4]): 100 queries x 20 targets x batch 256.
+    (a) cost build + exact assignment of one decoder layer (256 problems, one launch of matcher_kernel);
+    (b) the whole set loss through the public API get_losses on 6 layers (1536 problems: matcher + loss kernels);
+    (c) the same with HOST inputs (h2d copies inside);  (d) the reference arithmetic on one host core."""
+    import torch
+    from detr_tensorflow_b200 import ops
+    B, Q, C = 256, 100, 92
+    logits, boxes, tb, tc = c5_inputs(B, Q, C, 20, 1234, layers=6)
+    dl, db, dtb, dtc = (x.cuda() for x in (logits, boxes, tb, tc))
+    out = dict(p=torch.empty(B, Q, dtype=torch.int64, device="cuda"), t=torch.empty(B, Q, dtype=torch.int64, device="cuda"),
+               s=torch.empty(B, Q, dtype=torch.uint8, device="cuda"), m=torch.empty(B, Q, dtype=torch.int32, device="cuda"),
+               st=torch.empty(B, dtype=torch.int32, device="cuda"))
+    flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+
+    def one_layer():
+        ops.matcher(dl[0], C, db[0], dtb, dtc, B, B, Q, C, out["p"], out["t"], out["s"], out["m"], None, out["st"])
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    m_dev = {"pred_logits": dl[5], "pred_boxes": db[5], "aux": [{"pred_logits": dl[i], "pred_boxes": db[i]} for i in range(5)]}
+    m_host = {"pred_logits": logits[5].pin_memory(), "pred_boxes": boxes[5].pin_memory(),
+              "aux": [{"pred_logits": logits[i].pin_memory(), "pred_boxes": boxes[i].pin_memory()} for i in range(5)]}
+    tbh, tch = tb.pin_memory(), tc.pin_memory()
+
+    def timed(fn, sync_result=False):
+        ts = []
+        for i in range(iters + 3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            r = fn()
+            e1.record()
+            if sync_result:
+                float(r[0])
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            if i >= 3:
+                ts.append((t1 - t0) * 1e3 if sync_result else e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+    ms_a = timed(one_layer)
+    assert int(out["st"].abs().sum()) == 0 and int((out["m"] >= 0).sum()) == B * 20
+    ms_b = timed(lambda: D.get_losses(m_dev, dtb, dtc, cfg))
+    ms_c = timed(lambda: D.get_losses({"pred_logits": m_host["pred_logits"].cuda(non_blocking=True),
+                                       "pred_boxes": m_host["pred_boxes"].cuda(non_blocking=True),
+                                       "aux": [{k: v.cuda(non_blocking=True) for k, v in a.items()} for a in m_host["aux"]]},
+                                      tbh, tch, cfg), sync_result=True)
+    cpu_us = matcher_cpu_us_per_image(logits, boxes, tb, tc)
+    alg_bytes = Q * C * 4 + Q * 4 * 4 + 20 * 24 + 420                              # SURVEY 8(d): ~39.3 KB / problem
+    _, peak_hbm, _ = measured_peaks()
+    return {"workload": "BASELINE configs[4]: 100 queries x 20 targets x batch 256, seed 1234; L2 flushed between iterations",
+            "us_per_image": ms_a * 1e3 / B, "problems": B, "kernel": "matcher_kernel (cost build + shortest-augmenting-path LSAP, 1 CTA/problem)",
+            "achieved_gbs": alg_bytes * B / (ms_a * 1e-3) / 1e9, "peak_gbs": peak_hbm, "bound": "latency (sequential augmentations)",
+            "set_loss_6layers_us_per_image": ms_b * 1e3 / B, "set_loss_6layers_problems": 6 * B,
+            "e2e_us_per_image": ms_c * 1e3 / B,
+            "e2e_path": "get_losses(m_outputs, t_bbox, t_class, config) with pinned HOST inputs (36.9 MB h2d) and the total loss read back",
+            "cpu_us_per_image": cpu_us, "cpu_cores": 1,
+            "cpu_kind": "reference arithmetic: numpy cost build + scipy.optimize.linear_sum_assignment, python loop over 256 images"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -152,6 +275,7 @@ def main():
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-matcher-bench", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,6 +407,11 @@ def main():
                "sample": "1 train step (fwd+matcher+set loss+bwd+Adam) on 1 synthetic 800x1333 image, PyTorch-CPU oracle "
                          "restatement of the reference (TensorFlow not installable offline)"}
 
+    # ------------------------------------------------------------------ BASELINE configs[4]: matcher us/image (rank 0, N=1)
+    matcher = None
+    if rank == 0 and world == 1 and not args.no_matcher_bench:
+        matcher = matcher_microbench(D)
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -295,7 +424,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(eng.launches_per_step * K),
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back"},
-            "roofline": roof, "cpu_baseline": cpu, "loss_after": loss_after,
+            "roofline": roof, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -9,3 +9,6 @@ from .loss.loss import get_losses  # noqa: F401
 from .loss.hungarian_matching import hungarian_matching  # noqa: F401
 from .optimizers import setup_optimizers  # noqa: F401
 from . import training  # noqa: F401
+from . import inference  # noqa: F401
+from .inference import get_model_inference  # noqa: F401
+from . import data  # noqa: F401

@@ -14,7 +14,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libdetrb.so")
-_SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu"]
+_SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu", "pipeline.cu"]
 _lib = None
 
 EXPORTS = [
@@ -23,6 +23,7 @@ EXPORTS = [
     "detrb_image_to_nhwc4", "detrb_image_to_s2d16", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
     "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",
     "detrb_set_tc", "detrb_set_tc_conv", "detrb_set_tc_tma_epilogue", "detrb_set_tc_persistent", "detrb_gemm_tc_force", "detrb_tma_im2col_probe", "detrb_prep_weights_multi", "detrb_adam_clipnorm_chunked", "detrb_set_tc_wgrad", "detrb_wgrad_tc_force",
+    "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess",
 ]
 
 

@@ -1,0 +1,210 @@
+// pipeline.cu -- the rows either side of the train step, on device:
+//   * input normalisation of uint8 frames (data/processing.py:6-23) as a 3x256-entry table lookup, either to the fp32 NHWC
+//     tensor the model call takes or fused straight into the bf16 space-to-depth tensor the stem convolution gathers from;
+//   * inference post-process (inference.py:68-95): softmax -> max score / argmax label -> background filter with an
+//     order-preserving compaction -> box format conversion, for a whole batch in one launch.
+// Both are HBM / latency bound byte work: coalesced vector accesses, no tensor cores.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ normalisation
+// lut[c*256 + v] = normalised value of byte v in OUTPUT channel c (built on the host with the reference's float64 arithmetic,
+// so the result is bit-identical to normalized_images()); swap != 0 reads input channel 2-c (tf_resnet: RGB -> BGR).
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t *__restrict__ img, const float *__restrict__ lut, int swap, float *__restrict__ out, int64_t npix4)
+{
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float s_lut[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 4 pixels = 12 bytes in, 48 bytes out
+    if (i >= npix4) return;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(img) + i * 3;
+    uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+    uint8_t b[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; }
+    float v[12];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[p * 3 + c] = s_lut[c * 256 + b[p * 3 + (swap ? 2 - c : c)]];
+    float4 *dst = reinterpret_cast<float4 *>(out) + i * 3;
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+}
+// tail pixels (npix % 4) and unaligned bases
+__global__ void normalize_u8_tail_kernel(const uint8_t *img, const float *lut, int swap, float *out, int64_t first, int64_t npix)
+{
+    pdl_trigger();
+    pdl_wait();
+    int64_t p = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    for (int c = 0; c < 3; c++) out[p * 3 + c] = lut[c * 256 + img[p * 3 + (swap ? 2 - c : c)]];
+}
+
+// uint8 NHWC3 frame -> normalised bf16 space-to-depth(2) tensor [B, ceil(H/2), ceil(W/2), 16]: the fp32 image never exists
+// (same channel order as image_to_s2d16_kernel: (ry*2+rx)*3 + c, 4 zero channels; pixels outside the frame are 0)
+__global__ void __launch_bounds__(256)
+image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restrict__ lut, int swap, uint4 *__restrict__ out,
+                         int B, int H, int W, int H2, int W2)
+{
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float s_lut[768];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y2 = blockIdx.y, b = blockIdx.z;
+    if (x2 >= W2) return;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = 0.f;
+#pragma unroll
+    for (int ry = 0; ry < 2; ry++) {
+        const int y = 2 * y2 + ry;
+        if (y >= H) continue;
+        const uint8_t *row = img + ((size_t)b * H + y) * (size_t)W * 3;
+#pragma unroll
+        for (int rx = 0; rx < 2; rx++) {
+            const int x = 2 * x2 + rx;
+            if (x >= W) continue;
+            const uint8_t *px = row + (size_t)x * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[(ry * 2 + rx) * 3 + c] = s_lut[c * 256 + px[swap ? 2 - c : c]];
+        }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    const size_t i = ((size_t)b * H2 + y2) * W2 + x2;
+    out[i * 2] = o0; out[i * 2 + 1] = o1;
+}
+
+// ------------------------------------------------------------------------------------------ inference post-process
+// One CTA per image, one warp per query row at a time.  The reference takes the argmax of the SOFTMAX output (inference.py:
+// 73-75), first index on ties: e_i = exp(x_i - max) is computed in fp32 and the (value desc, index asc) order is reduced over
+// the warp; score = e_max / sum = 1 / sum.  Kept queries are compacted in ascending query order (tf.where + tf.gather).
+constexpr int PP_MAXQ = 1024;
+
+__global__ void __launch_bounds__(128)
+postprocess_kernel(const float *__restrict__ logits, int ldl, const float *__restrict__ boxes, int Q, int C, int background_class,
+                   int bbox_format, float *__restrict__ out_boxes, int64_t *__restrict__ out_labels, float *__restrict__ out_scores,
+                   int32_t *__restrict__ out_query, int32_t *__restrict__ out_count)
+{
+    pdl_trigger();
+    pdl_wait();
+    __shared__ int s_label[PP_MAXQ];
+    __shared__ float s_score[PP_MAXQ];
+    __shared__ int s_warp_total[4];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *lg = logits + (size_t)b * Q * ldl;
+    for (int q = warp; q < Q; q += 4) {
+        const float *row = lg + (size_t)q * ldl;
+        float m = -INFINITY;
+        for (int c = lane; c < C; c += 32) m = fmaxf(m, row[c]);
+        m = warp_max(m);
+        float sum = 0.f, best = -1.f;
+        int besti = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            float e = expf(row[c] - m);
+            sum += e;
+            if (e > best) { best = e; besti = c; }                 // strict '>': keeps the lowest index within a lane
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) { s_label[q] = besti; s_score[q] = __fdiv_rn(best, sum); }
+    }
+    __syncthreads();
+    // order-preserving compaction: warp w owns queries [w*chunk, (w+1)*chunk), ballot scan in 32-query steps
+    const int chunk = ((Q + 3) / 4 + 31) / 32 * 32;
+    const int q0 = warp * chunk, q1 = min(Q, q0 + chunk);
+    int cnt = 0;
+    for (int q = q0 + lane; q < q0 + chunk; q += 32) {
+        bool keep = q < q1 && s_label[q] != background_class;
+        cnt += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == 0) s_warp_total[warp] = cnt;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += s_warp_total[w];
+    for (int q = q0 + lane; q < q0 + chunk; q += 32) {
+        bool keep = q < q1 && s_label[q] != background_class;
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int k = base + __popc(mask & ((1u << lane) - 1u));
+            const size_t o = (size_t)b * Q + k;
+            const float4 bx = reinterpret_cast<const float4 *>(boxes)[(size_t)b * Q + q];
+            float4 r = bx;                                             // xy_center: as predicted
+            if (bbox_format != 0) {                                    // bbox.py:171-183: corners, clipped to [0,1]
+                const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
+                const float x0 = fminf(fmaxf(__fsub_rn(bx.x, hw), 0.f), 1.f), y0 = fminf(fmaxf(__fsub_rn(bx.y, hh), 0.f), 1.f);
+                const float x1 = fminf(fmaxf(__fadd_rn(bx.x, hw), 0.f), 1.f), y1 = fminf(fmaxf(__fadd_rn(bx.y, hh), 0.f), 1.f);
+                r = (bbox_format == 1) ? make_float4(x0, y0, x1, y1) : make_float4(y0, x0, y1, x1);
+            }
+            reinterpret_cast<float4 *>(out_boxes)[o] = r;
+            out_labels[o] = s_label[q];
+            out_scores[o] = s_score[q];
+            if (out_query) out_query[o] = q;
+        }
+        base += __popc(mask);
+    }
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 4; w++) tot += s_warp_total[w];
+        out_count[b] = tot;
+    }
+}
+
+} // namespace
+
+extern "C" int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float *out, int64_t npix, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(img && lut && out && npix > 0, "detrb_normalize_u8: bad args");
+    int64_t n4 = 0;
+    if ((((uintptr_t)img) & 3) == 0 && (((uintptr_t)out) & 15) == 0) n4 = npix / 4;
+    if (n4 > 0) {
+        DETRB_LAUNCH(normalize_u8_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, lut, swap_rb, out, n4);
+        DETRB_CHECK_LAUNCH("normalize_u8_kernel");
+    }
+    if (n4 * 4 < npix) {
+        int64_t rest = npix - n4 * 4;
+        DETRB_LAUNCH(normalize_u8_tail_kernel, dim3((unsigned)((rest + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, lut, swap_rb, out, n4 * 4, npix);
+        DETRB_CHECK_LAUNCH("normalize_u8_tail_kernel");
+    }
+    return DETRB_OK;
+}
+
+extern "C" int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
+                                       detrb_stream_t stream)
+{
+    DETRB_REQUIRE(img && lut && out && B > 0 && H > 0 && W > 0, "detrb_image_u8_to_s2d16: bad args");
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    DETRB_REQUIRE(H2 <= 65535 && B <= 65535, "detrb_image_u8_to_s2d16: grid too large");
+    DETRB_LAUNCH(image_u8_to_s2d16_kernel, dim3((unsigned)ceil_div(W2, 256), (unsigned)H2, (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
+                 img, lut, swap_rb, (uint4 *)out, B, H, W, H2, W2);
+    DETRB_CHECK_LAUNCH("image_u8_to_s2d16_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_postprocess(const float *logits, int ldl, const float *boxes, int B, int Q, int C, int background_class,
+                                 int bbox_format, float *out_boxes, int64_t *out_labels, float *out_scores, int32_t *out_query,
+                                 int32_t *out_count, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(logits && boxes && out_boxes && out_labels && out_scores && out_count, "detrb_postprocess: null pointer");
+    DETRB_REQUIRE(B > 0 && Q > 0 && Q <= PP_MAXQ && C > 0 && ldl >= C, "detrb_postprocess: B=%d Q=%d C=%d ldl=%d", B, Q, C, ldl);
+    DETRB_REQUIRE(bbox_format >= 0 && bbox_format <= 2, "detrb_postprocess: bbox_format %d (0 xy_center, 1 xyxy, 2 yxyx)", bbox_format);
+    DETRB_REQUIRE((((uintptr_t)boxes) & 15) == 0 && (((uintptr_t)out_boxes) & 15) == 0, "detrb_postprocess: boxes must be 16-byte aligned");
+    DETRB_LAUNCH(postprocess_kernel, dim3((unsigned)B), dim3(128), 0, (cudaStream_t)stream, logits, ldl, boxes, Q, C, background_class,
+                 bbox_format, out_boxes, out_labels, out_scores, out_query, out_count);
+    DETRB_CHECK_LAUNCH("postprocess_kernel");
+    return DETRB_OK;
+}

@@ -421,6 +421,7 @@ class Engine:
         buf("t_bbox", B, 100, 4, dtype=F32)
         buf("t_class", B, 100, 1, dtype=torch.int64)
         buf("images", B, H, W, 3, dtype=F32)
+        self.u8_input = False                   # True: a["images_u8"] holds raw uint8 frames, normalised inside the stem's input stage
         self.ld_dl = _round_up(self.C, 32)
         buf("d_logits", L * Mq, self.ld_dl)
         buf("d_boxpre", L * Mq, 32)
@@ -616,11 +617,30 @@ class Engine:
         B, H, W, _ = images.shape
         self._plan(B, H, W)
         self.training = bool(training)
-        a = self.a
-        if images.device != self.device or images.data_ptr() != a["images"].data_ptr():
-            a["images"].copy_(images, non_blocking=True)
+        self._stage_images(images)
         self._forward_impl()
         return self.outputs()
+
+    def set_input_normalisation(self, normalized_method):
+        """uint8 input frames are normalised on device with the reference's normalized_images arithmetic (table lookup)"""
+        from .data.processing import device_lut
+        self.input_lut = device_lut(normalized_method, self.device)
+        self.input_method = normalized_method
+
+    def _stage_images(self, images):
+        a = self.a
+        if images.dtype == torch.uint8:
+            if getattr(self, "input_lut", None) is None:
+                self.set_input_normalisation("torch_resnet")
+            if "images_u8" not in a:
+                a["images_u8"] = torch.empty(a["images"].shape, dtype=torch.uint8, device=self.device)
+            if images.data_ptr() != a["images_u8"].data_ptr():
+                a["images_u8"].copy_(images, non_blocking=True)
+            self.u8_input = True
+        else:
+            if images.device != self.device or images.data_ptr() != a["images"].data_ptr():
+                a["images"].copy_(images, non_blocking=True)
+            self.u8_input = False
 
     def outputs(self):
         a, L, B, Q = self.a, self.ndec, self.B, self.Q
@@ -635,7 +655,10 @@ class Engine:
         scale = float(d // Hh) ** -0.5
         # ---------------- backbone (resnet_backbone.py:20-32)
         # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels (tcgen05 im2col kernel)
-        ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0)
+        if self.u8_input:                     # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
+            ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0)
+        else:
+            ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0)
         self.launches += 1
         stem = self.slots["backbone/conv1"]
         self._conv_fwd(stem, a["s2d"], self.hw_s2d, self.hw_stem, a["stem"], relu=True)
@@ -1057,8 +1080,7 @@ class Engine:
         """host/device inputs -> the engine's resident buffers (async copies on the current stream)"""
         B, H, W, _ = images.shape
         self._plan(B, H, W)
-        a = self.a
-        a["images"].copy_(images, non_blocking=True)
+        self._stage_images(images)
         self.set_targets(t_bbox, t_class)
 
     def grads_step(self, background_class, loss_scale=1.0, use_graph=True):
@@ -1074,7 +1096,8 @@ class Engine:
         if not use_graph or self.device.type != "cuda":
             body()
             return self.allreduce_grads()
-        key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None)
+        key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None, self.u8_input,
+               getattr(self, "input_method", None))
         if getattr(self, "_gs_key", None) != key:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

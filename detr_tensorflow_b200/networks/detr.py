@@ -7,8 +7,11 @@ from .init import init_params
 
 
 def _as_device_f32(x, device):
+    """float images go in as fp32 NHWC (the reference's input); uint8 frames stay uint8: the engine normalises them on device"""
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(x)
+    if x.dtype == torch.uint8:
+        return x.to(device=device, non_blocking=True)
     return x.to(device=device, dtype=torch.float32, non_blocking=True)
 
 
@@ -17,14 +20,22 @@ class DetrModel:
     {'pred_logits': [B,100,C], 'pred_boxes': [B,100,4], 'aux': [5 x same]} (detr.py:190-204).
     With include_top=False the call returns the stacked decoder states hs [L,B,100,256] (detr.py:177-179)."""
 
-    def __init__(self, engine, include_top, name):
+    def __init__(self, engine, include_top, name, config=None):
         self.engine = engine
         self.include_top = include_top
         self.name = name
+        self.config = config
 
     def __call__(self, images, training=False):
+        """images: [B,H,W,3] float32, already normalised (the reference's input) -- or, extension, raw uint8 frames, which are
+        normalised on device per config.normalized_method (data/processing.py:6-23) while being laid out for the stem."""
         eng = self.engine
-        out = eng.forward(_as_device_f32(images, eng.device), training=training)
+        images = _as_device_f32(images, eng.device)
+        if images.dtype == torch.uint8:
+            method = getattr(self.config, "normalized_method", "torch_resnet")
+            if getattr(eng, "input_method", None) != method:
+                eng.set_input_normalisation(method)
+        out = eng.forward(images, training=training)
         if self.include_top:
             return out
         return eng.a["hs"].view(eng.ndec, eng.B, eng.Q, eng.d)
@@ -58,4 +69,4 @@ def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_ba
                              num_decoder_layers=num_decoder_layers, nb_class=nb_class if finetune else None)
     eng.load_params(params)
     has_heads = bool(include_top) or finetune
-    return DetrModel(eng, has_heads, "detr_finetuning" if has_heads else "detr")
+    return DetrModel(eng, has_heads, "detr_finetuning" if has_heads else "detr", config)

@@ -186,3 +186,19 @@ def adam_clipnorm_chunked(params, grads, m, v, chunks, nchunks, lr_group, lrs, g
     check(_lib.lib().detrb_adam_clipnorm_chunked(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(chunks), c_int(nchunks), ptr(lr_group),
                                                  ptr(lrs), ptr(group_enabled), c_int(T), c_float(clipnorm), c_float(beta1), c_float(beta2),
                                                  c_float(eps), ptr(steps), ptr(norms), _stream()))
+
+
+def normalize_u8(img_u8, lut, swap_rb, out_f32, npix):
+    check(_lib.lib().detrb_normalize_u8(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out_f32), c_int64(npix), _stream()))
+
+
+def image_u8_to_s2d16(img_u8, lut, swap_rb, out, B, H, W):
+    check(_lib.lib().detrb_image_u8_to_s2d16(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out), c_int(B), c_int(H), c_int(W),
+                                             _stream()))
+
+
+def postprocess(logits, ldl, boxes, B, Q, C, background_class, bbox_format, out_boxes, out_labels, out_scores, out_query,
+                out_count):
+    check(_lib.lib().detrb_postprocess(ptr(logits), c_int(ldl), ptr(boxes), c_int(B), c_int(Q), c_int(C),
+                                       c_int(int(background_class)), c_int(int(bbox_format)), ptr(out_boxes), ptr(out_labels),
+                                       ptr(out_scores), ptr(out_query), ptr(out_count), _stream()))

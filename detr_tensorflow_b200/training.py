@@ -14,9 +14,21 @@ def _dev(x, dtype, device):
     return x.to(device=device, dtype=dtype, non_blocking=True)
 
 
+def _dev_img(x, config, eng):
+    """float images -> fp32 (the reference's input); uint8 frames stay uint8 and are normalised on device (extension)"""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    if x.dtype == torch.uint8:
+        method = getattr(config, "normalized_method", "torch_resnet")
+        if getattr(eng, "input_method", None) != method:
+            eng.set_input_normalisation(method)
+        return x.to(device=eng.device, non_blocking=True)
+    return x.to(device=eng.device, dtype=torch.float32, non_blocking=True)
+
+
 def _forward_loss(model, images, t_bbox, t_class, config, training, loss_scale, with_grad):
     eng = model.engine
-    m_outputs = eng.forward(_dev(images, torch.float32, eng.device), training=training)
+    m_outputs = eng.forward(_dev_img(images, config, eng), training=training)
     t_bbox = _dev(t_bbox, torch.float32, eng.device)
     eng.set_targets(t_bbox, _dev(t_class, torch.int64, eng.device))
     eng.set_global_normalisers(t_bbox)          # data parallel: batch-level normalisers of the GLOBAL batch
@@ -30,7 +42,7 @@ def run_train_step(model, images, t_bbox, t_class, optimizers, config):
     eng = model.engine
     gradient_aggregate = int(config.target_batch // config.batch_size) if config.target_batch is not None else 1
     t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
-    eng.stage_inputs(_dev(images, torch.float32, eng.device), t_bbox_d, _dev(t_class, torch.int64, eng.device))
+    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device))
     eng.set_global_normalisers(t_bbox_d)
     # the reference traces this function once (@tf.function, training.py:9); here the launch sequence of
     # forward + losses + backward + gradient all-reduce is captured once per input shape as a CUDA graph and replayed
@@ -59,12 +71,16 @@ class _Prefetcher:
         self.bufs = [None, None]
         self.next = self._load()
 
+    @staticmethod
+    def _img_dtype(images):
+        return torch.uint8 if str(images.dtype).endswith("uint8") else torch.float32
+
     def _to(self, x, dtype, old):
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(x)
         if x.device == self.device and x.dtype == dtype:
             return x
-        if old is None or old.shape != x.shape:
+        if old is None or old.shape != x.shape or old.dtype != dtype:
             old = torch.empty(x.shape, dtype=dtype, device=self.device)
         old.copy_(x, non_blocking=True)
         return old
@@ -75,11 +91,11 @@ class _Prefetcher:
         except StopIteration:
             return None
         if self.stream is None:
-            return (_dev(images, torch.float32, self.device), _dev(t_bbox, torch.float32, self.device),
+            return (_dev(images, self._img_dtype(images), self.device), _dev(t_bbox, torch.float32, self.device),
                     _dev(t_class, torch.int64, self.device), None)
         old = self.bufs[self.slot] or (None, None, None)
         with torch.cuda.stream(self.stream):
-            out = (self._to(images, torch.float32, old[0]), self._to(t_bbox, torch.float32, old[1]),
+            out = (self._to(images, self._img_dtype(images), old[0]), self._to(t_bbox, torch.float32, old[1]),
                    self._to(t_class, torch.int64, old[2]))
             ev = torch.cuda.Event()
             ev.record(self.stream)

@@ -266,6 +266,29 @@ int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int 
                            int upper_h, int stride, int pixels, int swizzle128, int c0, int w, int h, int n,
                            int off_w, int off_h, uint8_t *out, detrb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rows either side of the train step
+ * ------------------------------------------------------------------------------------------ */
+/* Input normalisation of uint8 frames (data/processing.py:6-23, normalized_images) as a table lookup:
+ *   img [npix, 3] u8 (NHWC, any batch), lut [3*256] f32 DEVICE: lut[c*256 + v] = value of byte v in OUTPUT channel c
+ *   (built by the host with the reference's float64 arithmetic -> results bit-identical to the reference);
+ *   swap_rb != 0 reads input channel 2-c (normalized_method "tf_resnet": RGB -> BGR).  out [npix, 3] f32. */
+int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float *out, int64_t npix, detrb_stream_t stream);
+/* The same normalisation fused into the stem's input layout: img [B,H,W,3] u8 -> bf16 space-to-depth(2) tensor
+ * [B, ceil(H/2), ceil(W/2), 16] (see detrb_image_to_s2d16); the fp32 image never exists in HBM. */
+int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
+                            detrb_stream_t stream);
+/* Inference post-process (inference.py:68-95, get_model_inference) for B images in one launch:
+ *   logits [B,Q,C] f32 (row stride ldl), boxes [B,Q,4] f32 cxcywh (16-byte aligned).
+ *   Per query: softmax, score = max probability, label = argmax of the softmax (first index on ties); queries whose label
+ *   == background_class are dropped; the rest are compacted in ascending query order.
+ *   bbox_format: 0 "xy_center" (as predicted), 1 "xyxy", 2 "yxyx" (corners clipped to [0,1], bbox.py:171-183).
+ * out: out_boxes [B,Q,4] f32, out_labels [B,Q] i64, out_scores [B,Q] f32, out_query [B,Q] i32 (source query; may be NULL):
+ *      first out_count[b] rows of image b valid.  Q <= 1024. */
+int detrb_postprocess(const float *logits, int ldl, const float *boxes, int B, int Q, int C, int background_class,
+                      int bbox_format, float *out_boxes, int64_t *out_labels, float *out_scores, int32_t *out_query,
+                      int32_t *out_count, detrb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

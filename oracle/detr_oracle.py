@@ -517,6 +517,38 @@ def pad_labels(boxes, classes):
     return tb, tc
 
 
+def normalized_images(image_u8, method="torch_resnet"):
+    """data/processing.py:6-23 (numpy float64 arithmetic, then float32): image [...,3] uint8 (or any numeric) pixels 0..255.
+    torch_resnet: (x/255 - mean)/std per RGB channel; tf_resnet: RGB -> BGR, minus the caffe means."""
+    image = np.asarray(image_u8)
+    if method == "torch_resnet":
+        channel_avg = np.array([0.485, 0.456, 0.406])
+        channel_std = np.array([0.229, 0.224, 0.225])
+        return ((image / 255.0 - channel_avg) / channel_std).astype(np.float32)
+    if method == "tf_resnet":
+        return (image[..., ::-1] - np.array([103.939, 116.779, 123.68])).astype(np.float32)
+    raise ValueError(method)
+
+
+def get_model_inference(m_outputs, background_class, bbox_format="xy_center"):
+    """inference.py:68-95 -- image 0 of the batch: softmax -> (max score, argmax label, first index on ties) -> drop the
+    queries whose label is the background class (ascending query order) -> boxes as cxcywh | clipped xyxy | clipped yxyx."""
+    boxes = torch.as_tensor(m_outputs["pred_boxes"])[0].float()
+    logits = torch.as_tensor(m_outputs["pred_logits"])[0].float()
+    sm = torch.softmax(logits, -1)
+    scores, labels = sm.max(-1)
+    labels = torch.from_numpy(np.argmax(sm.numpy(), -1))         # numpy argmax = first index, like tf.argmax
+    keep = torch.nonzero(labels != background_class).squeeze(-1)
+    scores, labels, boxes = scores[keep], labels[keep], boxes[keep]
+    if bbox_format == "xyxy":
+        boxes = xcycwh_to_xy_min_xy_max(boxes)
+    elif bbox_format == "yxyx":
+        boxes = xcycwh_to_xy_min_xy_max(boxes)[:, [1, 0, 3, 2]]
+    elif bbox_format != "xy_center":
+        raise NotImplementedError()
+    return boxes, labels, scores
+
+
 def synthetic_targets(B, n=20, num_classes=91, seed=0, n_range=None):
     """cx,cy~U(.1,.9), w,h~U(.02,.5), class~randint(0,91)."""
     g = torch.Generator().manual_seed(seed)

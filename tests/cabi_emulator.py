@@ -525,6 +525,48 @@ class FakeLib:
             t[:, :, :N] = wb.permute(2, 1, 0)
         return 0
 
+    # ---- rows either side of the train step (csrc/pipeline.cu)
+    @staticmethod
+    def _lut_apply(img, lut, swap, npix):
+        x = T(img, torch.uint8, npix * 3).view(npix, 3).long()
+        l = T(lut, F32, 768).view(3, 256)
+        if _v(swap):
+            x = x.flip(-1)
+        return torch.stack([l[c][x[:, c]] for c in range(3)], -1)
+
+    def detrb_normalize_u8(self, img, lut, swap, out, npix, stream):
+        npix = _v(npix)
+        T(out, F32, npix * 3)[:] = self._lut_apply(img, lut, swap, npix).reshape(-1)
+        return 0
+
+    def detrb_image_u8_to_s2d16(self, img, lut, swap, out, B, H, W, stream):
+        B, H, W = _v(B), _v(H), _v(W)
+        x = self._lut_apply(img, lut, swap, B * H * W).contiguous()
+        return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, stream)
+
+    def detrb_postprocess(self, logits, ldl, boxes, B, Q, C, bg, fmt, out_boxes, out_labels, out_scores, out_query, out_count,
+                          stream):
+        B, Q, C, ldl, bg, fmt = _v(B), _v(Q), _v(C), _v(ldl), _v(bg), _v(fmt)
+        lg = M2(logits, F32, B * Q, C, ldl).view(B, Q, C)
+        bx = T(boxes, F32, B * Q * 4).view(B, Q, 4)
+        ob, ol = T(out_boxes, F32, B * Q * 4).view(B, Q, 4), T(out_labels, torch.int64, B * Q).view(B, Q)
+        os_, oc = T(out_scores, F32, B * Q).view(B, Q), T(out_count, torch.int32, B)
+        oq = T(out_query, torch.int32, B * Q)
+        for b in range(B):
+            e = torch.exp(lg[b] - lg[b].max(-1, keepdim=True).values)
+            label = torch.from_numpy(np.argmax(e.numpy(), -1))
+            score = e.max(-1).values / e.sum(-1)
+            keep = torch.nonzero(label != bg).squeeze(-1)
+            k = keep.numel()
+            r = bx[b][keep]
+            if fmt != 0:
+                c = torch.cat([r[:, :2] - r[:, 2:] * 0.5, r[:, :2] + r[:, 2:] * 0.5], -1).clamp(0.0, 1.0)
+                r = c if fmt == 1 else c[:, [1, 0, 3, 2]]
+            ob[b, :k], ol[b, :k], os_[b, :k], oc[b] = r, label[keep], score[keep], k
+            if oq is not None:
+                oq.view(B, Q)[b, :k] = keep.int()
+        return 0
+
     def detrb_dropout_mask(self, out, M, N, drop_p, seed, site, seed_ptr, stream):
         M, N = _v(M), _v(N)
         T(out, torch.uint8, M * N)[:] = keep_mask(range(M), range(N), _v(drop_p), _v(seed), _v(site), seed_ptr).reshape(-1).to(torch.uint8)

@@ -40,6 +40,15 @@ def build():
     tf.reduce_mean = lambda x, axis=None: np.mean(_np(x), axis=axis, dtype=_np(x).dtype)
     tf.argmax = lambda x, axis=None: np.argmax(_np(x), axis=axis).astype(np.int64)
     tf.where = lambda c: np.argwhere(_np(c)).astype(np.int64)
+    tf.reduce_max = lambda x, axis=None: np.max(_np(x), axis=axis)
+    tf.constant = lambda v, dtype=None: np.array(v, dtype=dtype)
+
+    def pad(x, paddings, mode="CONSTANT", constant_values=0):
+        assert mode == "CONSTANT"
+        pw = [(int(a), int(b)) for a, b in paddings]
+        assert all(a >= 0 and b >= 0 for a, b in pw), "tf.pad rejects negative paddings"
+        return np.pad(_np(x), pw, mode="constant", constant_values=constant_values)
+    tf.pad = pad
 
     def slice_(x, begin, size):
         x = _np(x)

@@ -251,3 +251,41 @@ def test_finetune_heads_nlayers_group(emu):
     bare = D.get_detr_model(D.TrainingConfig(), include_top=False, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu",
                             params=O.init_params(seed=3, num_encoder_layers=NE, num_decoder_layers=ND))
     assert tuple(bare(img, training=False).shape) == (ND, 2, 100, 256)
+
+
+def test_inference_postprocess_and_uint8_input_host_logic(emu):
+    """Host side of the N1/N2 rows with the C ABI emulated: get_model_inference (inference.py:68-95) and normalized_images
+    (processing.py:6-23) against the vectors produced by the reference's own code; uint8 frames through the model equal the
+    normalised float frames through the model; pad_labels reproduces the wire format."""
+    import detr_tensorflow_b200 as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pipeline_golden.npz"))
+    logits, boxes = torch.from_numpy(g["i_logits"]), torch.from_numpy(g["i_boxes"])
+    for bg in (91, 0):
+        for fmt in ("xy_center", "xyxy", "yxyx"):
+            for b in range(3):
+                pb, pl, ps = D.inference.get_model_inference({"pred_logits": logits[b:b + 1], "pred_boxes": boxes[b:b + 1]}, bg, fmt,
+                                                              device="cpu")
+                k = f"i_{bg}_{fmt}_{b}"
+                assert np.array_equal(pl.numpy(), g[k + "_labels"])
+                np.testing.assert_allclose(ps.numpy(), g[k + "_scores"], rtol=1e-6)
+                np.testing.assert_allclose(pb.numpy(), g[k + "_bbox"], atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        D.inference.get_model_inference({"pred_logits": logits[:1], "pred_boxes": boxes[:1]}, 91, "cxcy", device="cpu")
+    cfg = D.TrainingConfig()
+    for method in ("torch_resnet", "tf_resnet"):
+        cfg.normalized_method = method
+        out = D.data.normalized_images(g["n_img"], cfg, device="cpu")
+        assert np.array_equal(out.numpy(), g[f"n_{method}"])                  # bit-exact (table built in float64 like the reference)
+    for k in range(4):
+        _, tb, tc = D.data.pad_labels(None, g[f"p_{k}_in_bbox"], g[f"p_{k}_in_class"])
+        assert np.array_equal(tb, g[f"p_{k}_bbox"]) and np.array_equal(tc, g[f"p_{k}_class"]) and tc.dtype == np.int64
+    with pytest.raises(ValueError):
+        D.data.pad_labels(None, np.zeros((100, 4), np.float32), np.zeros((100, 1), np.int64))
+    # uint8 frames straight into the model == normalised float frames into the model
+    P, _, tb, tc = _setup(B=2, H=33, W=47)
+    cfg.normalized_method = "torch_resnet"
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
+    u8 = torch.randint(0, 256, (2, 33, 47, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
+    a = model(u8, training=False)["pred_logits"].clone()
+    b = model(D.data.normalized_images(u8, cfg, device="cpu"), training=False)["pred_logits"].clone()
+    assert torch.equal(a, b)

@@ -160,3 +160,33 @@ def test_pos_embedding_layout():
     assert torch.allclose(pe[0, 0, :128], pe[0, 3, :128]) and torch.allclose(pe[0, 1, 128:], pe[2, 1, 128:])
     y = (1.0 / (3 + 1e-6)) * 2 * np.pi
     assert abs(float(pe[0, 0, 0]) - np.sin(y)) < 1e-6 and abs(float(pe[0, 0, 1]) - np.cos(y)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ N1 / N2 rows
+@pytest.fixture(scope="module")
+def pipeline_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_golden.npz"))
+
+
+def test_oracle_inference_postprocess_vs_reference_golden(pipeline_golden):
+    """oracle get_model_inference against the reference's own inference.py:68-95 outputs (make_golden_pipeline.py)"""
+    g = pipeline_golden
+    logits, boxes = torch.from_numpy(g["i_logits"]), torch.from_numpy(g["i_boxes"])
+    for bg in (91, 0):
+        for fmt in ("xy_center", "xyxy", "yxyx"):
+            for b in range(logits.shape[0]):
+                pb, pl, ps = O.get_model_inference({"pred_logits": logits[b:b + 1], "pred_boxes": boxes[b:b + 1]}, bg, fmt)
+                k = f"i_{bg}_{fmt}_{b}"
+                assert np.array_equal(pl.numpy(), g[k + "_labels"])                       # integer: exact
+                np.testing.assert_allclose(ps.numpy(), g[k + "_scores"], rtol=1e-6, atol=1e-7)
+                np.testing.assert_allclose(pb.numpy(), g[k + "_bbox"], rtol=0, atol=1e-7)
+
+
+def test_oracle_normalize_and_pad_labels_vs_reference_golden(pipeline_golden):
+    g = pipeline_golden
+    for method in ("torch_resnet", "tf_resnet"):
+        assert np.array_equal(O.normalized_images(g["n_img"], method), g[f"n_{method}"])   # same float64 arithmetic: bit-exact
+    for k in range(4):
+        tb, tc = O.pad_labels(torch.from_numpy(g[f"p_{k}_in_bbox"]), torch.from_numpy(g[f"p_{k}_in_class"])[:, 0])
+        assert np.array_equal(tb.numpy(), g[f"p_{k}_bbox"]) and np.array_equal(tc.numpy(), g[f"p_{k}_class"])

@@ -1,0 +1,115 @@
+"""GPU parity of the rows either side of the train step, through the C ABI (csrc/pipeline.cu):
+inference post-process and uint8 input normalisation, against vectors produced by the reference's own code
+(tests/golden/make_golden_pipeline.py) and against the oracle at full size.  Integer outputs (labels, kept query ids,
+counts) must be exact; normalised pixels are bit-exact by construction (table built with the reference's float64
+arithmetic); scores within 1e-6 relative (fp32 summation order of the softmax denominator)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import detr_tensorflow_b200 as D
+    return D
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(HERE, "golden", "pipeline_golden.npz"))
+
+
+def test_postprocess_vs_reference_golden(D, g):
+    logits, boxes = torch.from_numpy(g["i_logits"]).cuda(), torch.from_numpy(g["i_boxes"]).cuda()
+    for bg in (91, 0):
+        for fmt in ("xy_center", "xyxy", "yxyx"):
+            for b in range(3):
+                pb, pl, ps = D.get_model_inference({"pred_logits": logits[b:b + 1], "pred_boxes": boxes[b:b + 1]}, bg, fmt)
+                k = f"i_{bg}_{fmt}_{b}"
+                assert pl.dtype == torch.int64 and np.array_equal(pl.cpu().numpy(), g[k + "_labels"])      # exact
+                np.testing.assert_allclose(ps.cpu().numpy(), g[k + "_scores"], rtol=1e-6)
+                assert np.array_equal(pb.cpu().numpy(), g[k + "_bbox"])                                     # same fp32 ops: exact
+            # the batched launch returns the same rows for every image
+            ob, ol, os_, oq, cnt = D.inference.batched_model_inference({"pred_logits": logits, "pred_boxes": boxes}, bg, fmt)
+            for b in range(3):
+                k = f"i_{bg}_{fmt}_{b}"
+                n = int(cnt[b])
+                assert n == len(g[k + "_labels"]) and np.array_equal(ol[b, :n].cpu().numpy(), g[k + "_labels"])
+                assert np.array_equal(ob[b, :n].cpu().numpy(), g[k + "_bbox"])
+                q = oq[b, :n].cpu().numpy()
+                assert np.all(np.diff(q) > 0)                                                               # ascending query order
+
+
+def test_postprocess_full_size_vs_oracle_and_edges(D):
+    """B=256 x Q=100 x C=92 (config-5 sized) against the oracle; Q not a multiple of 32; all-background and none-background"""
+    from oracle import detr_oracle as O
+    gen = torch.Generator().manual_seed(11)
+    B, Q, C = 256, 100, 92
+    logits = torch.randn(B, Q, C, generator=gen) * 3
+    boxes = torch.cat([torch.rand(B, Q, 2, generator=gen), torch.rand(B, Q, 2, generator=gen) * 0.9 + 0.01], -1)
+    ob, ol, os_, oq, cnt = D.inference.batched_model_inference({"pred_logits": logits.cuda(), "pred_boxes": boxes.cuda()}, 91, "yxyx")
+    ob, ol, os_, cnt = ob.cpu(), ol.cpu(), os_.cpu(), cnt.cpu()
+    for b in range(0, B, 17):
+        rb, rl, rs = O.get_model_inference({"pred_logits": logits[b:b + 1], "pred_boxes": boxes[b:b + 1]}, 91, "yxyx")
+        n = int(cnt[b])
+        assert n == len(rl) and torch.equal(ol[b, :n], rl) and torch.equal(ob[b, :n], rb)
+        assert float((os_[b, :n] - rs).abs().max()) <= 1e-6 * float(rs.max())
+    for Q2, C2 in ((7, 4), (100, 4), (300, 1000)):
+        lg = torch.randn(2, Q2, C2, generator=gen)
+        bx = torch.rand(2, Q2, 4, generator=gen)
+        lg[0, :, 1] += 50.0                                  # image 0: every query predicts class 1
+        for bg, expect0 in ((1, 0), (0, Q2)):
+            _, ol2, _, oq2, c2 = D.inference.batched_model_inference({"pred_logits": lg.cuda(), "pred_boxes": bx.cuda()}, bg, "xyxy")
+            assert int(c2[0]) == expect0
+            rb, rl, rs = O.get_model_inference({"pred_logits": lg[1:2], "pred_boxes": bx[1:2]}, bg, "xyxy")
+            assert int(c2[1]) == len(rl) and torch.equal(ol2[1, :len(rl)].cpu(), rl)
+
+
+def test_normalize_u8_vs_reference_golden_and_s2d_fusion(D, g):
+    from detr_tensorflow_b200 import ops
+    cfg = D.TrainingConfig()
+    for method in ("torch_resnet", "tf_resnet"):
+        cfg.normalized_method = method
+        out = D.data.normalized_images(g["n_img"], cfg)
+        assert out.is_cuda and np.array_equal(out.cpu().numpy(), g[f"n_{method}"])                          # bit-exact
+        # odd pixel counts / unaligned views take the tail kernel
+        one = D.data.normalized_images(torch.from_numpy(g["n_img"][1, 3:4, 1:6]).contiguous(), cfg)
+        assert np.array_equal(one.cpu().numpy(), g[f"n_{method}"][1, 3:4, 1:6])
+        # fused uint8 -> normalised bf16 space-to-depth == (normalise to fp32, then the fp32 layout kernel)
+        u8 = torch.randint(0, 256, (2, 37, 53, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+        lut, swap = D.data.processing.device_lut(method, u8.device)
+        a = torch.zeros(2, 19, 27, 16, dtype=torch.bfloat16, device="cuda")
+        b = torch.ones_like(a)
+        ops.image_u8_to_s2d16(u8, lut, swap, a, 2, 37, 53)
+        ops.image_to_s2d16(D.data.normalized_images(u8, cfg), b, 2, 37, 53)
+        assert torch.equal(a, b)
+
+
+def test_uint8_frames_through_model_and_fit(D):
+    """uint8 batches through model() and training.fit (graph-replayed step) == the normalised float batches"""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=4, num_encoder_layers=1, num_decoder_layers=2)
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 2, None
+    cfg.train_backbone, cfg.train_transformers = True, True
+    u8 = torch.randint(0, 256, (2, 96, 128, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    f32 = torch.from_numpy(O.normalized_images(u8.numpy(), "torch_resnet"))
+    tb, tc = O.synthetic_targets(2, n=4, seed=4)
+    losses = {}
+    for name, imgs in (("u8", u8), ("f32", f32)):
+        model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=1, num_decoder_layers=2)
+        out = model(imgs, training=False)["pred_logits"].clone()
+        opt = D.setup_optimizers(model, cfg)
+        seen = []
+        D.training.fit(model, [(imgs, tb, tc)] * 3, opt, cfg, 0, None, on_step=lambda s, t, l: seen.append(float(t)))
+        losses[name] = (out, seen)
+    assert torch.equal(losses["u8"][0], losses["f32"][0])
+    assert losses["u8"][1] == losses["f32"][1] and len(losses["u8"][1]) == 3
+    assert losses["u8"][1][2] != losses["u8"][1][0]           # the optimizer moved
