@@ -236,15 +236,8 @@ class Engine:
             elif p.kind == "embed":
                 self.query_embed.copy_(t)
             else:
-                if p.kind == "conv":
-                    kh, kw, ci, co = p.shape
-                    t = t.permute(3, 0, 1, 2).contiguous()              # [co, kh, kw, ci]
-                    if name == "backbone/conv1/kernel":
-                        t = self._stem_to_s2d(t)
-                elif p.kind == "dense_w":
-                    t = t.t().contiguous()                               # [in, out] -> [out, in]
                 o, n = self.layout[name]
-                self.params[o:o + n].copy_(t.reshape(-1))
+                self.params[o:o + n].copy_(self._from_ref_layout(name, t))
         # FrozenBatchNorm2D (custom_layers.py:21-24): scale = w * rsqrt(var + eps); shift = b - mean * scale
         for s in self.slots.values():
             if s.fold is not None:
@@ -254,6 +247,38 @@ class Engine:
                 s.shift.copy_(self.bn[pre + "/bias"] - self.bn[pre + "/running_mean"] * scale)
         self.query_pos.copy_(self.query_embed.to(BF16))
         self.refresh_weights()
+
+    def _from_ref_layout(self, name, t):
+        """reference-layout tensor (HWIO conv / [out,in] Linear / [in,out] Dense) -> the flat arena layout of variable `name`"""
+        p = self.spec[name]
+        t = t.detach().to(torch.float32).cpu()
+        if p.kind == "conv":
+            t = t.permute(3, 0, 1, 2).contiguous()                      # [co, kh, kw, ci]
+            if name == "backbone/conv1/kernel":
+                t = self._stem_to_s2d(t)
+        elif p.kind == "dense_w":
+            t = t.t().contiguous()                                       # [in, out] -> [out, in]
+        return t.reshape(-1)
+
+    def export_state(self):
+        """everything a resume needs, in the reference's layouts: parameters, Adam moments, per-group iteration counts"""
+        out = OrderedDict()
+        for name, t in self.export_params().items():
+            out["param/" + name] = t
+        for (name, _, _, _, _) in self.vars:
+            out["adam_m/" + name] = self._to_ref_layout(name, self.adam_m)
+            out["adam_v/" + name] = self._to_ref_layout(name, self.adam_v)
+        out["adam_steps"] = self.steps[:3].detach().cpu().clone()
+        return out
+
+    def load_state(self, state):
+        self.load_params(OrderedDict((k[len("param/"):], torch.as_tensor(v)) for k, v in state.items() if k.startswith("param/")))
+        for (name, o, n, _, _) in self.vars:
+            for arena, pre in ((self.adam_m, "adam_m/"), (self.adam_v, "adam_v/")):
+                if pre + name in state:
+                    arena[o:o + n].copy_(self._from_ref_layout(name, torch.as_tensor(state[pre + name])))
+        if "adam_steps" in state:
+            self.steps[:3] = torch.as_tensor(state["adam_steps"]).to(self.steps.dtype)
 
     def export_params(self):
         out = OrderedDict()

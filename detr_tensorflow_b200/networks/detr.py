@@ -55,8 +55,6 @@ def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_ba
     `dropout` (transformer.py:9 default 0.1; 0 makes training-mode steps deterministic for tests)."""
     if tf_backbone:
         raise NotImplementedError("tf_backbone=True (keras.applications ResNet50, detr.py:146-148) is out of scope")
-    if weights is not None:
-        raise NotImplementedError("pretrained checkpoint download (networks/weights.py) is out of scope: pass params=")
     # detr.py:178-181: nb_class only matters when include_top is False -> add_heads_nlayers (detr.py:94-114): new Keras
     # Dense heads `cls_layer` (nb_class logits) and `pos_layer` (256-256-4 MLP), registered as config.nlayers (detr.py:103)
     finetune = (include_top is False) and (nb_class is not None)
@@ -69,4 +67,8 @@ def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_ba
                              num_decoder_layers=num_decoder_layers, nb_class=nb_class if finetune else None)
     eng.load_params(params)
     has_heads = bool(include_top) or finetune
-    return DetrModel(eng, has_heads, "detr_finetuning" if has_heads else "detr", config)
+    model = DetrModel(eng, has_heads, "detr_finetuning" if has_heads else "detr", config)
+    if weights is not None:                               # detr.py:143-144 -> networks/weights.py:14 (local files only)
+        from .weights import load_weights
+        load_weights(model, weights)
+    return model

@@ -289,3 +289,86 @@ def test_inference_postprocess_and_uint8_input_host_logic(emu):
     a = model(u8, training=False)["pred_logits"].clone()
     b = model(D.data.normalized_images(u8, cfg, device="cpu"), training=False)["pred_logits"].clone()
     assert torch.equal(a, b)
+
+
+def test_checkpoint_roundtrip_and_torch_detr_name_mapping(emu, tmp_path):
+    """save/load of parameters + Adam state (resume), and the original-DETR state_dict mapping: a torchvision
+    resnet50 (the module the original DETR wraps as backbone.0.body) and nn.MultiheadAttention / nn.Linear / nn.LayerNorm
+    modules with random weights, exported under the original key names, must drive the oracle to the torch modules' outputs."""
+    import detr_tensorflow_b200 as D
+    from detr_tensorflow_b200.networks import weights as Wt
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 1, None
+    cfg.train_backbone, cfg.train_transformers = True, True
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+    opt = D.setup_optimizers(model, cfg)
+    D.training.fit(model, [(img, tb, tc)] * 2, opt, cfg, 0, None)
+    path = str(tmp_path / "ck.npz")
+    Wt.save_checkpoint(model, path, cfg)
+    cfg2 = D.TrainingConfig()
+    cfg2.background_class, cfg2.batch_size, cfg2.target_batch = 91, 1, None
+    cfg2.train_backbone, cfg2.train_transformers = True, True
+    model2 = D.get_detr_model(cfg2, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", dropout=0.0,
+                              weights=path, seed=123)
+    Wt.load_checkpoint(model2, path, cfg2)
+    e1, e2 = model.engine, model2.engine
+    assert cfg2.global_step == 2 and torch.equal(e1.params, e2.params) and torch.equal(e1.adam_m, e2.adam_m)
+    assert torch.equal(e1.adam_v, e2.adam_v) and torch.equal(e1.steps, e2.steps)
+    # resumed training continues identically
+    opt2 = D.setup_optimizers(model2, cfg2)
+    D.training.fit(model, [(img, tb, tc)], opt, cfg, 0, None)
+    D.training.fit(model2, [(img, tb, tc)], opt2, cfg2, 0, None)
+    assert torch.equal(e1.params, e2.params)
+    with pytest.raises(Exception):
+        Wt.load_weights(model, "detr")                                   # the reference's bucket download: not offline
+
+    # ---- original-DETR key names -> reference layouts
+    import torchvision
+    torch.manual_seed(0)
+    r50 = torchvision.models.resnet50(weights=None).eval()
+    for mod in r50.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.05)
+            mod.running_var.uniform_(0.9, 1.1)
+            mod.weight.data.normal_(1, 0.1)
+            mod.bias.data.normal_(0, 0.05)
+    sd = {"backbone.0.body." + k: v for k, v in r50.state_dict().items() if not k.startswith("fc.")}
+    d = 256
+    tr = torch.nn.ModuleDict({
+        "input_proj": torch.nn.Conv2d(2048, d, 1), "query_embed": torch.nn.Embedding(100, d),
+        "class_embed": torch.nn.Linear(d, 92)})
+    for k, v in tr.state_dict().items():
+        sd[k] = v
+    for k in range(3):
+        lin = torch.nn.Linear(d, d if k < 2 else 4)
+        sd[f"bbox_embed.layers.{k}.weight"], sd[f"bbox_embed.layers.{k}.bias"] = lin.weight.data, lin.bias.data
+    enc = torch.nn.TransformerEncoderLayer(d, 8, 2048, 0.0)             # same submodule names as the original DETR layer
+    dec = torch.nn.TransformerDecoderLayer(d, 8, 2048, 0.0)
+    for k, v in enc.state_dict().items():
+        sd["transformer.encoder.layers.0." + k] = v
+    for k, v in dec.state_dict().items():
+        sd["transformer.decoder.layers.0." + k] = v
+    fn = torch.nn.LayerNorm(d)
+    fn.weight.data.normal_(1, 0.1)
+    sd["transformer.decoder.norm.weight"], sd["transformer.decoder.norm.bias"] = fn.weight.data, fn.bias.data
+    Pm = Wt.from_torch_detr_state_dict({"model": sd}, num_encoder_layers=1, num_decoder_layers=1)
+    assert list(Pm) == list(O.param_shapes(num_encoder_layers=1, num_decoder_layers=1))
+    x = torch.randn(1, 64, 96, 3)
+    with torch.no_grad():
+        feat = O.backbone_forward(Pm, x)
+        t = x.permute(0, 3, 1, 2)
+        t = r50.maxpool(r50.relu(r50.bn1(r50.conv1(t))))
+        t = r50.layer4(r50.layer3(r50.layer2(r50.layer1(t))))
+        assert rel(feat, t.permute(0, 2, 3, 1)) < 1e-5
+        # encoder layer with pos = 0 equals torch's post-norm TransformerEncoderLayer; MHA / FFN / LN names verified
+        src = torch.randn(2, 6, d)                                      # oracle layout [B, S, d]; torch layer is [S, B, d]
+        ours = O.encoder_layer(Pm, "transformer/encoder/layer_0", src, torch.zeros(6, d))
+        assert rel(ours, enc.eval()(src.transpose(0, 1)).transpose(0, 1)) < 1e-5
+        mem, tgt = torch.randn(2, 9, d), torch.randn(2, 5, d)
+        ours = O.decoder_layer(Pm, "transformer/decoder/layer_0", tgt, mem, torch.zeros(9, d), torch.zeros(5, d))
+        assert rel(ours, dec.eval()(tgt.transpose(0, 1), mem.transpose(0, 1)).transpose(0, 1)) < 1e-5
+        assert torch.equal(Pm["class_embed/kernel"], tr["class_embed"].weight) and Pm["input_proj/kernel"].shape == (1, 1, 2048, d)
+    with pytest.raises(KeyError):
+        Wt.from_torch_detr_state_dict({k: v for k, v in sd.items() if k != "query_embed.weight"}, num_encoder_layers=1,
+                                      num_decoder_layers=1)

@@ -111,5 +111,9 @@ def test_uint8_frames_through_model_and_fit(D):
         D.training.fit(model, [(imgs, tb, tc)] * 3, opt, cfg, 0, None, on_step=lambda s, t, l: seen.append(float(t)))
         losses[name] = (out, seen)
     assert torch.equal(losses["u8"][0], losses["f32"][0])
-    assert losses["u8"][1] == losses["f32"][1] and len(losses["u8"][1]) == 3
+    a, b = losses["u8"][1], losses["f32"][1]
+    # same bf16 stem input -> same forward, bit for bit (logits above); the loss sums and the weight gradients are reduced with
+    # fp32 atomics whose order varies run to run -> equal to rounding only
+    assert len(a) == 3 and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
+    assert all(abs(x - y) <= 1e-3 * abs(y) for x, y in zip(a, b)), (a, b)
     assert losses["u8"][1][2] != losses["u8"][1][0]           # the optimizer moved
