@@ -63,26 +63,51 @@ __device__ __forceinline__ void mma_a_tileT(float (&s)[8][4], const uint32_t (&a
         }
 }
 
-// O[16 x 32] += P(16 x 64, registers as S-layout) * T where T is a [64][LDH] tile (rows = k index, cols = dh)
-__device__ __forceinline__ void mma_p_tile(float (&o)[4][4], const float (&p)[8][4], const bf16 *tile, int lane)
+// P (16 x 64, fp32 registers in S-layout) -> bf16 A-operand fragments: pa[kk] = {(j=2kk, row g), (2kk, g+8), (2kk+1, g), (2kk+1, g+8)}
+__device__ __forceinline__ void pack_p(uint32_t (&pa)[4][4], const float (&p)[8][4])
 {
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
-        uint32_t a[4];
-        a[0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
-        a[1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
-        a[2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
-        a[3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+        pa[kk][0] = pack_bf16x2(p[2 * kk][0], p[2 * kk][1]);
+        pa[kk][1] = pack_bf16x2(p[2 * kk][2], p[2 * kk][3]);
+        pa[kk][2] = pack_bf16x2(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+        pa[kk][3] = pack_bf16x2(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+    }
+}
+// O[16 x 32] += P(16 x 64, packed fragments) * T where T is a [64][LDH] tile (rows = k index, cols = dh)
+__device__ __forceinline__ void mma_pa_tile(float (&o)[4][4], const uint32_t (&pa)[4][4], const bf16 *tile, int lane)
+{
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
             uint32_t b[2][2];
             int r = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
             int c = j * 8 + (lane >> 4) * 8;
             ldmatrix_x4_trans(b[0][0], b[0][1], b[1][0], b[1][1], smem_u32(tile + r * LDH + c));
-            mma_bf16_16816(o[j], a, b[0]);
-            mma_bf16_16816(o[j + 1], a, b[1]);
+            mma_bf16_16816(o[j], pa[kk], b[0]);
+            mma_bf16_16816(o[j + 1], pa[kk], b[1]);
         }
     }
+}
+__device__ __forceinline__ void mma_p_tile(float (&o)[4][4], const float (&p)[8][4], const bf16 *tile, int lane)
+{
+    uint32_t pa[4][4];
+    pack_p(pa, p);
+    mma_pa_tile(o, pa, tile, lane);
+}
+// Dropout keep bits of one thread's scores in the forward / dQ layout (rows g and g+8 of a warp's 16 query rows; columns
+// kbase + 8j + 2t + {0,1}, j = 0..7): kb[r][m][c] covers column 16m + 2t + c in its low field (j = 2m) and column
+// 16m + 8 + 2t + c in its high field (j = 2m + 1) -- see attn_drop_word (common.cuh).
+__device__ __forceinline__ void attn_keepbits_rowmajor(uint32_t (&kb)[2][4][2], const uint32_t (&rh)[2], int kbase, int t, uint32_t thresh2)
+{
+    const uint32_t p0 = (uint32_t)(kbase >> 4) * 8u + (uint32_t)t * 2u;
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) kb[r][m][c] = attn_drop_keepbits(attn_drop_word(rh[r], p0 + 8u * m + c), thresh2);
 }
 
 // --------------------------------------------------------------------------------------- forward
@@ -116,12 +141,12 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
     float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
     uint32_t aq[2][4];
 
-    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
     const float sl2 = p.scale * LOG2E;
     const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
-    const uint32_t rh[2] = {dropout_rowhash(seed, p.site, rowbase), dropout_rowhash(seed, p.site, rowbase + 8)};
+    const uint32_t rh[2] = {attn_drop_rowhash(seed, p.site, rowbase), attn_drop_rowhash(seed, p.site, rowbase + 8)};
 
     for (int kt = 0; kt < nkt; kt++) {
         if (kt + 1 < nkt) {
@@ -172,16 +197,6 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
                 rsum[e >> 1] += pv;
                 s[j][e] = pv;
             }
-            if (p.drop_p > 0.f) {                              // the 1/(1-p) rescale is folded into the final normalisation
-                uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    bool k0, k1;
-                    dropout_keep2(dropout_bits_rh(rh[r], pair), thresh, k0, k1);
-                    if (!k0) s[j][r * 2 + 0] = 0.f;
-                    if (!k1) s[j][r * 2 + 1] = 0.f;
-                }
-            }
         }
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -194,7 +209,20 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
             o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
             o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
         }
-        mma_p_tile(o, s, sV[kt & 1], lane);
+        uint32_t pa[4][4];
+        pack_p(pa, s);
+        if (p.drop_p > 0.f) {                                  // the 1/(1-p) rescale is folded into the final normalisation
+            uint32_t kb[2][4][2];
+            attn_keepbits_rowmajor(kb, rh, kbase, t, thresh2);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                for (int r = 0; r < 2; r++) {                  // packed pair = columns (2t, 2t+1): words c = 0 / 1
+                    pa[kk][r] &= attn_drop_mask2_lo(kb[r][kk][0], kb[r][kk][1]);          // j = 2kk
+                    pa[kk][2 + r] &= attn_drop_mask2_hi(kb[r][kk][0], kb[r][kk][1]);      // j = 2kk + 1
+                }
+        }
+        mma_pa_tile(o, pa, sV[kt & 1], lane);
         __syncthreads();
     }
 
@@ -271,7 +299,7 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
             int q = qt * TKV + tid;
             sLse[st][tid] = q < p.Lq ? -lse[q] * LOG2E : -INFINITY;      // negated, log2 domain
             sDelta[st][tid] = q < p.Lq ? -delta[q] * p.scale : 0.f;       // -scale * delta
-            sRh[st][tid] = dropout_rowhash(seed, p.site, (uint32_t)((b * p.H + h) * p.Lq + q));
+            sRh[st][tid] = attn_drop_rowhash(seed, p.site, (uint32_t)((b * p.H + h) * p.Lq + q));
         }
     };
     load_tile64(sK, K, p.ldk, k0, p.Lk, tid);
@@ -285,11 +313,11 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
 #pragma unroll
         for (int k = 0; k < 4; k++) { dk[j][k] = 0.f; dv[j][k] = 0.f; }
     uint32_t ak[2][4], av[2][4];
-    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int keyr[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
-    const uint32_t kpair[2] = {(uint32_t)(keyr[0] >> 1), (uint32_t)(keyr[1] >> 1)};
-    const uint32_t kshift = (uint32_t)(keyr[0] & 1) * 16u;          // both rows of a thread have the same parity
+    // this thread's two key rows (g, g + 8 of a 16-key group) are the low / high field of ONE dropout word per query
+    const uint32_t kpair = attn_drop_pair((uint32_t)keyr[0]);
     const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
 
     for (int qt = 0; qt < nqt; qt++) {
@@ -306,18 +334,22 @@ attn_bwd_dkv_kernel(const detrb_attn_bwd_t p)
 #pragma unroll
         for (int j = 0; j < 8; j++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int ql = j * 8 + t * 2 + (e & 1);
-                const float pv = ex2(fmaf(sT[j][e], sl2, sLse[st][ql]));
-                float dpv = dpT[j][e];
-                float pd = pv;
+            for (int c = 0; c < 2; c++) {
+                const int ql = j * 8 + t * 2 + c;
+                uint32_t mk[2] = {0xffffffffu, 0xffffffffu};
                 if (p.drop_p > 0.f) {
-                    const uint32_t bits = dropout_bits_rh(sRh[st][ql], kpair[e >> 1]);
-                    const bool keep = ((bits >> kshift) & 0xffffu) >= thresh;
-                    if (!keep) { pd = 0.f; dpv = 0.f; }
+                    const uint32_t kb = attn_drop_keepbits(attn_drop_word(sRh[st][ql], kpair), thresh2);
+                    mk[0] = attn_drop_mask_lo(kb);                         // key row g
+                    mk[1] = attn_drop_mask_hi(kb);                         // key row g + 8
                 }
-                sT[j][e] = pd;                                             // dropped probabilities (for dV), unscaled
-                dpT[j][e] = pv * fmaf(dpv, dss, sDelta[st][ql]);           // scale * dS^T
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int e = r * 2 + c;
+                    const float pv = ex2(fmaf(sT[j][e], sl2, sLse[st][ql]));
+                    const float dpv = __uint_as_float(__float_as_uint(dpT[j][e]) & mk[r]);
+                    sT[j][e] = __uint_as_float(__float_as_uint(pv) & mk[r]);   // dropped probabilities (for dV), unscaled
+                    dpT[j][e] = pv * fmaf(dpv, dss, sDelta[st][ql]);           // scale * dS^T
+                }
             }
         mma_p_tile(dv, sT, sdO[st], lane);        // dV += P_d^T dO
         mma_p_tile(dk, dpT, sQ[st], lane);        // dK += dS^T Q
@@ -377,12 +409,12 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
         lrow[r] = q < p.Lq ? -p.lse[idx] * LOG2E : -INFINITY;         // negated, log2 domain
         drow[r] = q < p.Lq ? -p.delta[idx] * p.scale : 0.f;          // -scale * delta
     }
-    const uint32_t thresh = dropout_thresh16(p.drop_p);
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const uint32_t rowbase = (uint32_t)((b * p.H + h) * p.Lq + q0 + warp * 16 + g);
     const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
     const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
-    const uint32_t rh[2] = {dropout_rowhash(seed, p.site, rowbase), dropout_rowhash(seed, p.site, rowbase + 8)};
+    const uint32_t rh[2] = {attn_drop_rowhash(seed, p.site, rowbase), attn_drop_rowhash(seed, p.site, rowbase + 8)};
 
     for (int kt = 0; kt < nkt; kt++) {
         if (kt + 1 < nkt) {
@@ -397,22 +429,25 @@ attn_bwd_dq_kernel(const detrb_attn_bwd_t p)
         mma_a_tileT(s, aq, sK[kt & 1], lane);
         mma_a_tileT(dp, ado, sV[kt & 1], lane);
         const int kbase = kt * TKV;
+        if (p.drop_p > 0.f) {                                   // dP of dropped probabilities is zero
+            uint32_t kb[2][4][2];
+            attn_keepbits_rowmajor(kb, rh, kbase, t, thresh2);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            bool keep[4] = {true, true, true, true};
-            if (p.drop_p > 0.f) {
-                uint32_t pair = (uint32_t)((kbase + j * 8 + t * 2) >> 1);
+            for (int j = 0; j < 8; j++)
 #pragma unroll
-                for (int r = 0; r < 2; r++)
-                    dropout_keep2(dropout_bits_rh(rh[r], pair), thresh, keep[r * 2], keep[r * 2 + 1]);
-            }
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t w = kb[e >> 1][j >> 1][e & 1];
+                    const uint32_t mk = (j & 1) ? attn_drop_mask_hi(w) : attn_drop_mask_lo(w);
+                    dp[j][e] = __uint_as_float(__float_as_uint(dp[j][e]) & mk);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const float pv = ex2(fmaf(s[j][e], sl2, lrow[e >> 1]));
-                const float dpv = keep[e] ? dp[j][e] : 0.f;
-                s[j][e] = pv * fmaf(dpv, dss, drow[e >> 1]);    // scale * dS
+                s[j][e] = pv * fmaf(dp[j][e], dss, drow[e >> 1]);    // scale * dS
             }
-        }
         // keys beyond Lk (last tile only): their zero-filled K rows give s = 0, p = exp(-lse), which overflows for rows whose
         // scores are all very negative -- and inf * 0 would poison dQ
         if (kbase + TKV > p.Lk) {

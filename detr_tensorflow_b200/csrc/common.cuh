@@ -151,3 +151,43 @@ __device__ __forceinline__ void dropout_keep2(uint32_t bits, uint32_t thresh, bo
     k0 = (bits & 0xffffu) >= thresh;
     k1 = (bits >> 16) >= thresh;
 }
+
+// ---------------------------------------------------------------- attention-probability dropout (attention.cu)
+// The attention kernels regenerate their masks three times per layer (forward, dK/dV, dQ) inside loops that are bound by
+// instruction issue, so this RNG is built for instruction count: one 32-bit word carries two 15-bit uniform fields (bits
+// [0,15) and [16,31)) for the KEY PAIR (k, k+8) of a 16-key group -- the two keys one thread owns in the transposed (dK/dV)
+// MMA layout, and the two column groups (j, j+1) it owns in the forward / dQ layout -- so every orientation needs half a word
+// per score.  word = ((rowhash' + pair * C') ^ (.. >> 15)) * M2: a Weyl step, one xorshift, one multiply (4 instructions;
+// serial / cross-row correlations and field uniformity checked in tests/test_box_math_cpu.py::test_attention_dropout_rng).
+// keep <=> field >= thresh15 = round(p * 32768).  Both compares are ONE subtraction on the guarded fields, and the keep bits
+// (15 and 31) become all-ones / all-zeros AND-masks with one PRMT (sign replication), applied to packed bf16x2 probabilities
+// or to fp32 values: no predicates, no selects.
+constexpr uint32_t ATTN_C1 = 0x9E3779B1u, ATTN_M1 = 0x21F0AAADu, ATTN_M2 = 0x735A2D97u;
+__device__ __forceinline__ uint32_t attn_drop_rowhash(uint64_t seed, uint32_t site, uint32_t row) {
+    return dropout_rowhash(seed, site, row) * ATTN_M1;
+}
+__host__ __device__ __forceinline__ uint32_t attn_drop_pair(uint32_t k) { return ((k >> 4) << 3) | (k & 7u); }   // half = (k >> 3) & 1
+__device__ __forceinline__ uint32_t attn_drop_word(uint32_t rowhash_m, uint32_t pair) {
+    uint32_t x = rowhash_m + pair * (ATTN_C1 * ATTN_M1);
+    x ^= x >> 15;
+    return x * ATTN_M2;
+}
+__host__ __device__ __forceinline__ uint32_t attn_drop_thresh2(float p) {       // threshold replicated into both fields
+    const uint32_t t = (uint32_t)(p * 32768.0f + 0.5f);
+    return t | (t << 16);
+}
+// bit 15 / bit 31 of the result: low / high field kept (0x8000 + field - t never borrows across the field boundary)
+__device__ __forceinline__ uint32_t attn_drop_keepbits(uint32_t word, uint32_t thresh2) {
+    return ((word & 0x7FFF7FFFu) | 0x80008000u) - thresh2;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// 32-bit all-ones / all-zeros mask from the low (bit 15) / high (bit 31) keep bit: selector nibble 8|n = sign of byte n
+__device__ __forceinline__ uint32_t attn_drop_mask_lo(uint32_t kb) { return prmt(kb, kb, 0x9999u); }
+__device__ __forceinline__ uint32_t attn_drop_mask_hi(uint32_t kb) { return prmt(kb, kb, 0xBBBBu); }
+// bf16x2 masks for the element pair (a, b) whose keep bits live in words ka (low half of the result) and kb (high half)
+__device__ __forceinline__ uint32_t attn_drop_mask2_lo(uint32_t ka, uint32_t kb) { return prmt(ka, kb, 0xDD99u); }
+__device__ __forceinline__ uint32_t attn_drop_mask2_hi(uint32_t ka, uint32_t kb) { return prmt(ka, kb, 0xFFBBu); }

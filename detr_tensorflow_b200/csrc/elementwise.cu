@@ -326,6 +326,19 @@ __global__ void dropout_mask_kernel(uint8_t *out, int M, int N, float drop_p, ui
     out[idx] = v >= dropout_thresh16(drop_p) ? 1 : 0;
 }
 
+// keep mask of an attention-probability dropout site: row = (b*H + h)*Lq + q, column = key (attn_drop_word, common.cuh)
+__global__ void attn_dropout_mask_kernel(uint8_t *out, int M, int N, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr)
+{
+    pdl_trigger();
+    pdl_wait();
+    const uint64_t seed = seed_in ^ (seed_ptr ? *seed_ptr : 0ull);
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    const uint32_t m = (uint32_t)(idx / N), k = (uint32_t)(idx % N);
+    const uint32_t kb = attn_drop_keepbits(attn_drop_word(attn_drop_rowhash(seed, site, m), attn_drop_pair(k)), attn_drop_thresh2(drop_p));
+    out[idx] = (((k >> 3) & 1u) ? attn_drop_mask_hi(kb) : attn_drop_mask_lo(kb)) & 1u;
+}
+
 }  // namespace
 
 extern "C" int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, const float *beta, detrb_bf16 *y, detrb_bf16 *y2,
@@ -431,6 +444,16 @@ extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, co
     DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(IW * (C / 8), 256), (unsigned)IH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
                                                                                           B, IH, IW, C, OH, OW);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_attn_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
+                                       const uint64_t *seed_ptr, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(out && M > 0 && N > 0, "detrb_attn_dropout_mask: bad args");
+    int64_t total = (int64_t)M * N;
+    DETRB_LAUNCH(attn_dropout_mask_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, out, M, N, drop_p, seed, site, seed_ptr);
+    DETRB_CHECK_LAUNCH("attn_dropout_mask_kernel");
     return DETRB_OK;
 }
 

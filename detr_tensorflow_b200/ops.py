@@ -177,6 +177,11 @@ def dropout_mask(out, M, N, drop_p, seed, site, seed_ptr=None):
                                         ptr(seed_ptr), _stream()))
 
 
+def attn_dropout_mask(out, M, N, drop_p, seed, site, seed_ptr=None):
+    check(_lib.lib().detrb_attn_dropout_mask(ptr(out), c_int(M), c_int(N), c_float(drop_p), c_uint64(seed), c_uint32(site),
+                                             ptr(seed_ptr), _stream()))
+
+
 def prep_weights_multi(descs_dev, nslots, total_tiles):
     check(_lib.lib().detrb_prep_weights_multi(ptr(descs_dev), c_int(nslots), c_int(total_tiles), _stream()))
 

@@ -260,6 +260,10 @@ int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int tot
 int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
                        const uint64_t *seed_ptr, detrb_stream_t stream);
 
+/* the same for an attention-probability dropout site (detrb_attn_fwd/bwd): M = B*H*Lq rows ((b*H + h)*Lq + q), N = Lk keys */
+int detrb_attn_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
+                            const uint64_t *seed_ptr, detrb_stream_t stream);
+
 /* test helper: one TMA im2col load (channelsPerPixel = 64, pixelsPerColumn = pixels) of NHWC bf16 x[B,H,W,C] dumped
  * raw into out[pixels*128 + 1] (last byte: 1 if the load completed).  Pins the cuTensorMapEncodeIm2col conventions. */
 int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int lower_w, int lower_h, int upper_w,

@@ -90,6 +90,23 @@ def keep_mask(rows, cols, drop_p, seed, site, seed_ptr=None):
     return torch.from_numpy(bits >= thresh)
 
 
+def attn_keep_mask(rows, keys, drop_p, seed, site, seed_ptr=None):
+    """bool [len(rows), len(keys)]: attention-probability dropout (attn_drop_word / attn_drop_keepbits, csrc/common.cuh)"""
+    seed = int(seed)
+    if _addr(seed_ptr):
+        seed ^= int(T(seed_ptr, torch.int64, 1)[0]) & 0xffffffffffffffff
+    r = np.asarray(rows, dtype=np.uint64)[:, None]
+    k = np.asarray(keys, dtype=np.uint64)[None, :]
+    rowhash = _lowbias32((r ^ (seed & 0xffffffff) ^ ((site * 0x9E3779B9) & 0xffffffff)) & 0xffffffff) ^ (seed >> 32)
+    rowhash = (rowhash * 0x21F0AAAD) & 0xffffffff
+    pair = ((k >> 4) << 3) | (k & 7)
+    x = (rowhash + pair * ((0x9E3779B1 * 0x21F0AAAD) & 0xffffffff)) & 0xffffffff
+    x ^= x >> 15
+    x = (x * 0x735A2D97) & 0xffffffff
+    field = np.where(((k >> 3) & 1) == 1, (x >> 16) & 0x7fff, x & 0x7fff)
+    return torch.from_numpy(field >= int(np.float32(drop_p) * np.float32(32768.0) + np.float32(0.5)))
+
+
 # ---------------------------------------------------------------- gather
 def _gather(p_A, lda, M, K, batch, IH, IW, Cin, OH, OW, KH, KW, stride, pad, mode, stem_real_kw=None):
     A = M2(p_A, _Act.dtype, batch * IH * IW, Cin, lda).to(F32)
@@ -218,7 +235,7 @@ class FakeLib:
         lse = torch.logsumexp(s, -1)
         w = torch.softmax(s, -1)
         if p.drop_p > 0:
-            keep = keep_mask(range(B * H * Lq), range(Lk), p.drop_p, p.seed, p.site, p.seed_ptr).view(B, H, Lq, Lk)
+            keep = attn_keep_mask(range(B * H * Lq), range(Lk), p.drop_p, p.seed, p.site, p.seed_ptr).view(B, H, Lq, Lk)
             w = torch.where(keep, w / (1 - p.drop_p), torch.zeros_like(w))
         o = (w.to(_Act.dtype).to(F32) @ v).transpose(1, 2).reshape(B, Lq, H * 32)
         return o, lse
@@ -565,6 +582,11 @@ class FakeLib:
             ob[b, :k], ol[b, :k], os_[b, :k], oc[b] = r, label[keep], score[keep], k
             if oq is not None:
                 oq.view(B, Q)[b, :k] = keep.int()
+        return 0
+
+    def detrb_attn_dropout_mask(self, out, M, N, drop_p, seed, site, seed_ptr, stream):
+        M, N = _v(M), _v(N)
+        T(out, torch.uint8, M * N)[:] = attn_keep_mask(range(M), range(N), _v(drop_p), _v(seed), _v(site), seed_ptr).reshape(-1).to(torch.uint8)
         return 0
 
     def detrb_dropout_mask(self, out, M, N, drop_p, seed, site, seed_ptr, stream):

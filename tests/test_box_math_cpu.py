@@ -82,3 +82,28 @@ def test_warp_parallel_lsap_rule_vs_scipy(harness):
         exp = -np.ones(Q, np.int32)
         exp[rows] = cols
         assert np.array_equal(r4c, exp), (Q, n, it)
+
+
+def test_attention_dropout_rng():
+    """Statistics of the attention-probability dropout RNG (csrc/common.cuh attn_drop_word, mirrored by
+    cabi_emulator.attn_keep_mask): drop rate = round(p * 2^15) / 2^15, row / column marginals binomial, no serial or
+    cross-row correlation beyond sampling noise, masks change with the seed."""
+    import numpy as np
+    import cabi_emulator as E
+    R, K, p = 2048, 1056, 0.1
+    keep = E.attn_keep_mask(range(1000, 1000 + R), range(K), p, 0x12345678_00000063, 11).numpy()
+    d = (~keep).astype(np.float64)
+    assert abs(d.mean() - 3277 / 32768) < 4 * np.sqrt(0.09 / (R * K))
+    assert abs(d.mean(1).std() / np.sqrt(0.09 / K) - 1) < 0.1 and abs(d.mean(0).std() / np.sqrt(0.09 / R) - 1) < 0.1
+
+    def corr(a, b):
+        a, b = a - a.mean(), b - b.mean()
+        return (a * b).mean() / np.sqrt((a * a).mean() * (b * b).mean())
+    tol = 5 / np.sqrt(R * K)
+    for lag in (1, 2, 7, 8, 9, 16, 64, 128):
+        assert abs(corr(d[:, :-lag], d[:, lag:])) < tol, ("key lag", lag)
+    for lag in (1, 2, 8, 64):
+        assert abs(corr(d[:-lag], d[lag:])) < tol, ("row lag", lag)
+    other = E.attn_keep_mask(range(1000, 1000 + R), range(K), p, 0x12345678_00000064, 11).numpy()
+    assert abs(corr(d, (~other).astype(np.float64))) < tol          # next step's seed: independent mask
+    assert E.attn_keep_mask(range(4), range(64), 0.0, 1, 1).all()

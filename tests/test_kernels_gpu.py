@@ -242,7 +242,7 @@ def test_attention_fwd_bwd(ops, B, Lq, Lk, drop):
     keep = None
     if drop > 0:
         keep = torch.zeros(B * H * Lq, Lk, dtype=torch.uint8, device="cuda")
-        ops.dropout_mask(keep, B * H * Lq, Lk, drop, 3, 11, seed_dev)
+        ops.attn_dropout_mask(keep, B * H * Lq, Lk, drop, 3, 11, seed_dev)
     qf = q.float().reshape(B, Lq, d).clone().requires_grad_(True)
     kf = k.float().view(B, Lk, d).clone().requires_grad_(True)
     vf = v.float().view(B, Lk, d).clone().requires_grad_(True)
