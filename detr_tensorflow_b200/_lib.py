@@ -13,7 +13,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_SO = os.path.join(_HERE, "libdetrb.so")
+# DETRB_SO: developer override (e.g. a -DDETRB_TRACE build next to the production library)
+_SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
 _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu", "pipeline.cu"]
 _lib = None
 
@@ -40,7 +41,7 @@ def build(force=False, verbose=False):
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + srcs
+           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + os.environ.get("DETRB_NVCC_FLAGS", "").split() + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

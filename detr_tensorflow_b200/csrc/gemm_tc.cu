@@ -13,6 +13,16 @@
 // columns each): one CTA's epilogue overlaps another's main loop -- the k-loops of this model are short (1..32 blocks).
 #include "tc_common.cuh"
 
+#ifdef DETRB_TRACE
+// developer build (-DDETRB_TRACE): per-phase cycle sums of the one-tile kernel's CTA life, read back by detrb_trace_read
+__device__ unsigned long long g_trace[16];
+#define TRACE_ADD(i, v) atomicAdd(&g_trace[i], (unsigned long long)(v))
+#define TRACE_NOW() clock64()
+#else
+#define TRACE_ADD(i, v) ((void)(v))
+#define TRACE_NOW() 0ll
+#endif
+
 namespace {
 
 constexpr int TBM = 128;
@@ -63,9 +73,15 @@ struct SmemLayout {
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = BAR_OFF + 256;          // BN floats of bias (BN shift), staged once per CTA
-    static constexpr int TOTAL = BAR_OFF + 1024 + 1024;     // barriers + bias + slack for 1024-byte alignment
+    static constexpr int NCH = BN / 64;                     // 64-column chunks of the output tile
+    static constexpr int BAR_OFF = 0;                       // barriers (256 B), then BN floats of bias (BN shift)
+    static constexpr int BIAS_OFF = 256;
+    static constexpr int STG_OFF = BN > 128 ? 2048 : 1024;  // pipeline stages (1024-byte aligned: SWIZZLE_128B)
+    static constexpr int EARLY_OFF = STG_OFF + STAGES * STAGE_BYTES;     // optional: residual chunks fetched at kernel start
+    static constexpr int BASE = EARLY_OFF + 1024;           // + slack for the 1024-byte alignment of the dynamic smem base
+    static constexpr int TOTAL = BASE + NCH * 16384;        // with the early-residual region
+    // the freed stages hold the late residual + mask tiles (one-stage kernels: one of them, the residual goes early)
+    static_assert(STAGES * STAGE_BYTES >= (STAGES == 1 ? 1 : 2) * NCH * 16384, "epilogue tiles do not fit in the pipeline stages");
 };
 
 // IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
@@ -78,18 +94,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B needs 1024-byte alignment
-    const uint32_t bar_base = smem_base + L::BAR_OFF;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B needs 1024-byte alignment
+    const uint32_t bar_base = smem0 + L::BAR_OFF;
+    const uint32_t smem_base = smem0 + L::STG_OFF;                           // pipeline stages
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-    const uint32_t epi_bar = bar_base + 8u * (2 * STAGES + 2);
+    const uint32_t epi_bar = bar_base + 8u * (2 * STAGES + 2);               // early residual chunks
+    const uint32_t late_bar = bar_base + 8u * (2 * STAGES + 3);              // mask (and late residual) chunks
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const bool r_early = (tma_epi & 2) != 0;                                 // residual tiles have their own smem: fetched at kernel start
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
     const int nk = p.K / TBK;
+    const long long t_entry = TRACE_NOW();
+    (void)t_entry;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -102,6 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(tmem_full_bar, 1);
         mbar_init(epi_bar, 1);
+        mbar_init(late_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -113,7 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const long long t_sync = TRACE_NOW();
     pdl_wait();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
+    const long long t_pdl = TRACE_NOW();
+    if (threadIdx.x == 0) { TRACE_ADD(0, 1); TRACE_ADD(1, t_sync - t_entry); TRACE_ADD(2, t_pdl - t_sync); }
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -148,10 +173,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
                     tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
                 }
-                if (kb == 0 && tma_epi && (p.residual || p.mask)) {
-                    // the epilogue's residual / mask tiles start their trip from DRAM now (into L2), not after the main loop
+                if (kb == 0 && tma_epi && ((p.residual && !r_early) || p.mask)) {
+                    // the epilogue's late residual / mask tiles start their trip from DRAM now (into L2), not after the main loop
                     for (int cb = 0; cb < BN / 64 && n0 + cb * 64 < p.N; cb++) {
-                        if (p.residual) tma_prefetch_2d(&map_r, n0 + cb * 64, m0);
+                        if (p.residual && !r_early) tma_prefetch_2d(&map_r, n0 + cb * 64, m0);
                         if (p.mask) tma_prefetch_2d(&map_m, n0 + cb * 64, m0);
                     }
                 }
@@ -183,14 +208,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             tc_commit(tmem_full_bar);                       // accumulator complete
+            TRACE_ADD(3, TRACE_NOW() - t_pdl);              // pdl -> all operand tiles landed, MMAs issued
         }
         __syncwarp();
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const uint32_t sbias = smem_base + L::BIAS_OFF;
+        const uint32_t sbias = smem0 + L::BIAS_OFF;
+        const bool leader = (warp == 2 && lane == 0);
+        int nch = (p.N - n0 + 63) / 64;                      // 64-column chunks of this tile that exist (uniform across the CTA)
+        if (nch > L::NCH) nch = L::NCH;
+        const uint32_t early = smem0 + L::EARLY_OFF;
+        if (tma_epi && r_early && p.residual && leader) {    // residual tiles: in flight together with the operand tiles
+            mbar_expect_tx(epi_bar, (uint32_t)nch * 16384u);
+            for (int cb = 0; cb < nch; cb++) tma_load_2d(early + (uint32_t)cb * 16384u, &map_r, epi_bar, n0 + cb * 64, m0);
+        }
         if (p.bias) {                                        // global-load latency hides behind the main loop
-            const int t = threadIdx.x - 64;
-            if (t < BN) {
+            for (int t = threadIdx.x - 64; t < BN; t += 128) {
                 const float b = (n0 + t < p.N) ? p.bias[n0 + t] : 0.f;
                 asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
             }
@@ -198,6 +231,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        const long long t_tf = TRACE_NOW();
+        if (leader) TRACE_ADD(4, t_tf - t_pdl);              // pdl -> accumulator complete
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < p.M;
@@ -213,27 +248,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
         if (tma_epi) {
             // ---------- coalesced epilogue: residual / mask tiles arrive by TMA, the bf16 result leaves by TMA store.
-            // The pipeline stages are free once tmem_full fired: reuse them as [128 x 64] staging tiles (128B swizzle).
-            const uint32_t bufR = smem_base, bufM = smem_base + 16384, bufO = smem_base + 32768;
-            const bool leader = (warp == 2 && lane == 0);
+            // The pipeline stages are free once tmem_full fired: they take the mask (and late residual) tiles, [128 x 64] each,
+            // 128B-swizzled.  Every chunk has its own tile and the result overwrites the residual (or mask) tile IN PLACE -- a
+            // thread reads and writes the same 16-byte slots -- so all chunks are computed back to back and stored together.
+            const bool r_late = p.residual && !r_early;
+            const uint32_t lateR = smem_base, lateM = smem_base + (r_late ? (uint32_t)L::NCH * 16384u : 0u);
+            if (leader && (r_late || p.mask)) {
+                mbar_expect_tx(late_bar, (uint32_t)nch * 16384u * ((r_late ? 1u : 0u) + (p.mask ? 1u : 0u)));
+                for (int cb = 0; cb < nch; cb++) {
+                    if (r_late) tma_load_2d(lateR + (uint32_t)cb * 16384u, &map_r, late_bar, n0 + cb * 64, m0);
+                    if (p.mask) tma_load_2d(lateM + (uint32_t)cb * 16384u, &map_m, late_bar, n0 + cb * 64, m0);
+                }
+            }
+            const uint32_t bufR = r_early ? early : lateR, bufM = lateM;
+            const uint32_t bufO = p.residual ? bufR : bufM;   // without residual and mask: lateM == smem_base, the free stages
             const int row = q * 32 + lane;                    // row inside the tile == TMEM lane
             const uint32_t row_off = (uint32_t)row * 128u;
             const uint32_t sw = (uint32_t)(row & 7);          // 16-byte chunk c of a row lives at chunk c ^ (row % 8)
-            uint32_t parity = 0;
+            if (r_early && p.residual) mbar_wait(epi_bar, 0);
+            if (r_late || p.mask) mbar_wait(late_bar, 0);
+            const long long t_in = TRACE_NOW();
+            if (leader) TRACE_ADD(5, t_in - t_tf);            // accumulator complete -> residual / mask tiles landed
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 64; cb++) {
+            for (int cb = 0; cb < nch; cb++) {
                 const int nb = n0 + cb * 64;
-                if (nb >= p.N) break;                         // uniform across the CTA
-                const bool have_in = (p.residual != nullptr) || (p.mask != nullptr);
-                if (have_in) {
-                    if (leader) {
-                        mbar_expect_tx(epi_bar, ((p.residual ? 1u : 0u) + (p.mask ? 1u : 0u)) * 16384u);
-                        if (p.residual) tma_load_2d(bufR, &map_r, epi_bar, nb, m0);
-                        if (p.mask) tma_load_2d(bufM, &map_m, epi_bar, nb, m0);
-                    }
-                    mbar_wait(epi_bar, parity);
-                    parity ^= 1;
-                }
+                const uint32_t cboff = (uint32_t)cb * 16384u;
 #pragma unroll
                 for (int c32 = 0; c32 < 2; c32++) {
                     uint32_t r[32];                            // two TMEM loads in flight per wait
@@ -244,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int hf = 0; hf < 4; hf++) {
                         const int n = nb + c32 * 32 + hf * 8;
                         const uint32_t chunk = (uint32_t)(c32 * 4 + hf);
-                        const uint32_t soff = row_off + ((chunk ^ sw) << 4);
+                        const uint32_t soff = cboff + row_off + ((chunk ^ sw) << 4);
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[hf * 8 + i]);
@@ -294,17 +333,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(bufO + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> visible to TMA
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (leader) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 :: "l"(&map_c), "r"(bufO), "r"(nb), "r"(m0) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // bufO may be overwritten afterwards
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the reads
+            const long long t_math = TRACE_NOW();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy writes -> visible to TMA
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (leader) {
+                const long long t_bar = TRACE_NOW();
+                for (int cb = 0; cb < nch; cb++)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 :: "l"(&map_c), "r"(bufO + (uint32_t)cb * 16384u), "r"(n0 + cb * 64), "r"(m0) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");         // smem may be released after the reads
+                TRACE_ADD(6, t_math - t_in);                  // tcgen05.ld + math + st.shared, all chunks
+                TRACE_ADD(7, t_bar - t_math);                 // fence + barrier
+                TRACE_ADD(8, TRACE_NOW() - t_bar);            // TMA store issue + smem read drained
+            }
         } else {
         bf16 *C = reinterpret_cast<bf16 *>(p.C);
         const bf16 *R = reinterpret_cast<const bf16 *>(p.residual);
@@ -387,6 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        if (lane == 0) TRACE_ADD(9, TRACE_NOW() - t_entry); // whole CTA life
     }
 }
 
@@ -405,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 constexpr int NTHREADS_P = 384;
 constexpr int MAXRS = 4;
 
-template <int BN, int PST>
+template <int BN, int PST, int OB = 1>
 struct PLayout {
     static constexpr int A_BYTES = TBM * TBK * 2;
     static constexpr int B_BYTES = BN * TBK * 2;
@@ -413,8 +457,8 @@ struct PLayout {
     static constexpr int NCH = BN / 64;                                   // 64-column chunks per tile
     static constexpr int NACC = BN <= 128 ? 4 : 2;                        // accumulators in TMEM
     static constexpr int TMEM_COLS = NACC * BN;                           // 256 or 512 columns (power of two)
-    static constexpr int OBUF = PST * STAGE_BYTES;                        // output staging, one [128 x 64] tile per warpgroup
-    static constexpr int RING = OBUF + 2 * 16384;                         // residual / mask ring
+    static constexpr int OBUF = PST * STAGE_BYTES;                        // output staging, OB [128 x 64] tiles per warpgroup
+    static constexpr int RING = OBUF + 2 * OB * 16384;                    // residual / mask ring
     static constexpr int TOTAL = 227 * 1024;
     static constexpr int BAR_OFF = TOTAL - 1024 - 1024;                   // 1 KB alignment slack, 512 B of barriers, 2 x 64 bias floats
     static constexpr int BIAS_OFF = BAR_OFF + 512;
@@ -460,14 +504,16 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], 
     }
 }
 
-template <int BN, int PST, bool IM2COL>
+// OB = 2: two output staging tiles per warpgroup -- the TMA store of chunk i drains while chunk i+1 is computed.  Measured on the
+// HBM-bound 1x1 layers (K <= 128): 15.37 vs 14.81 ms/step with the one-tile kernel, so only OB = 1 is instantiated.
+template <int BN, int PST, bool IM2COL, int OB = 1>
 __global__ void __launch_bounds__(NTHREADS_P, 1)
 gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                 const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux,
                 const int n_tiles_n, const int n_tiles, const int rs)
 {
-    using L = PLayout<BN, PST>;
+    using L = PLayout<BN, PST, OB>;
     constexpr int NACC = L::NACC;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -590,7 +636,8 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int row = q * 32 + lane;
         const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
         const bool leader = (q == 0 && lane == 0);
-        const uint32_t obuf = smem_base + L::OBUF + (uint32_t)wg * 16384u;
+        const uint32_t obuf0 = smem_base + L::OBUF + (uint32_t)wg * (uint32_t)(OB * 16384);
+        int oc = 0;                                             // chunks this warpgroup has produced (selects its staging tile)
         const uint32_t sbias = smem_base + L::BIAS_OFF + (uint32_t)wg * 256u;
         const uint32_t thresh = dropout_thresh16(p.drop_p);
         const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
@@ -623,8 +670,13 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const float b = (nb + t < p.N) ? p.bias[nb + t] : 0.f;
                     asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
                 }
-                // the TMA store that last read this warpgroup's staging tile must have finished reading it
-                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // the TMA store that last read this staging tile (OB chunks ago) must have finished reading it
+                const uint32_t obuf = obuf0 + (uint32_t)((oc % OB) * 16384);
+                oc++;
+                if (leader) {
+                    if (OB == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
 #pragma unroll
                 for (int c32 = 0; c32 < 2; c32++) {
@@ -716,12 +768,15 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
 }
 
 static int g_tma_epilogue = 1;
+static int g_r_early = 1;            // early residual fetch: 0 never, 1 policy (launch_tc), 2 always      (env DETRB_R_EARLY)
+static int g_deep_small = 1;         // one stage per k-block for K <= 256 on latency-bound grids           (env DETRB_DEEP_SMALL)
+static int g_one_stage = 1;          // one-stage kernel for K = 64                                          (env DETRB_ONE_STAGE)
 static int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
 static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
 
-template <int BN, int STAGES, bool IM2COL, bool PERSIST = false>
+template <int BN, int STAGES, bool IM2COL, bool PERSIST = false, int OB = 1>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
     CUtensorMap ma, mb;
@@ -769,11 +824,11 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         if (!ok) tma_epi = 0;
     }
     if constexpr (PERSIST) {
-        using PL = PLayout<BN, STAGES>;
+        using PL = PLayout<BN, STAGES, OB>;
         static bool pconfigured = false;
         static int num_sms = 148;
         if (!pconfigured) {
-            DETRB_CUDA(cudaFuncSetAttribute(gemm_tcp_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
+            DETRB_CUDA(cudaFuncSetAttribute((gemm_tcp_kernel<BN, STAGES, IM2COL, OB>), cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -788,7 +843,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         if (slot && rs < 2) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc: no room for the residual / mask ring");
         const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        DETRB_LAUNCH((gemm_tcp_kernel<BN, STAGES, IM2COL>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, ntn, ntiles, rs);
+        DETRB_LAUNCH((gemm_tcp_kernel<BN, STAGES, IM2COL, OB>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, ntn, ntiles, rs);
         DETRB_CHECK_LAUNCH("gemm_tcp_kernel");
         return DETRB_OK;
     } else {
@@ -799,7 +854,17 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         configured = true;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
-    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL>), dim3(grid), dim3(NTHREADS_TC), L::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, tma_epi);
+    // residual tiles in their own shared memory, fetched at kernel start together with the operands: always for one-stage
+    // kernels (the stage cannot hold residual + mask), for grids of at most two CTAs per SM (pure latency chains: occupancy is
+    // irrelevant, every microsecond of the chain counts) -- elsewhere the extra 16-32 KB would cost a co-resident CTA
+    int early = 0;
+    if (tma_epi && p.residual) {
+        const long ctas = (long)grid.x * grid.y;
+        early = (g_r_early == 2 || (g_r_early == 1 && (STAGES == 1 || ctas <= 2 * 148))) ? 1 : 0;
+        if (STAGES == 1 && p.mask) early = 1;
+    }
+    const size_t smem = early ? L::TOTAL : L::BASE;
+    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL>), dim3(grid), dim3(NTHREADS_TC), smem, stream, ma, mb, mc, mr, mm, p, aux, tma_epi | (early << 1));
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
     }
@@ -870,6 +935,9 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
         if (const char *e = getenv("DETRB_TCP_MIN_TILES")) g_tcp_min_tiles = atol(e);
         if (const char *e = getenv("DETRB_TCP_MIN_TILES256")) g_tcp_min_tiles256 = atol(e);
         if (const char *e = getenv("DETRB_TCP_MIN_NK256")) g_tcp_min_nk256 = atol(e);
+        if (const char *e = getenv("DETRB_R_EARLY")) g_r_early = atoi(e);
+        if (const char *e = getenv("DETRB_DEEP_SMALL")) g_deep_small = atoi(e);
+        if (const char *e = getenv("DETRB_ONE_STAGE")) g_one_stage = atoi(e);
     }
     const bool tma_epi = p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue;
     if (!g_tc_persistent || !tma_epi || p.Cin == 16) return DETRB_OK;
@@ -909,7 +977,19 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
         bn = (p.N >= 128 && tiles128 >= 148 && p.K > 128) ? 128 : 64;
     }
     // short k-loops (K <= 256) are latency bound: 2 stages -> 64 / 48 KB of smem -> 3-4 co-resident CTAs per SM hide each other
-    const bool shallow = (p.K / TBK) <= 4;
+    const int nk = p.K / TBK;
+    const bool shallow = nk <= 4;
+    if constexpr (!IM2COL) {
+        const long ctas = (long)ceil_div(p.N, bn) * ceil_div(p.M, TBM);
+        // K = 64: the whole k-loop is one stage -> 24 KB + the residual tile: five co-resident CTAs instead of four
+        if (nk == 1 && g_one_stage && (bn == 64 || bn == 0)) {
+            // (128- and 256-wide one-stage tiles measured no faster: 14.80 vs 14.81 ms/step)
+            return launch_tc<64, 1, false>(p, stream, cls);
+        }
+        // at most two CTAs per SM: nothing to overlap with -> fetch every k-block at once (one stage each)
+        if (g_deep_small && shallow && nk > 2 && ctas <= 2 * 148)
+            return bn == 128 ? launch_tc<128, 4, false>(p, stream, cls) : launch_tc<64, 4, false>(p, stream, cls);
+    }
     if (bn == 128) return shallow ? launch_tc<128, 2, IM2COL>(p, stream, cls) : launch_tc<128, 3, IM2COL>(p, stream, cls);
     return shallow ? launch_tc<64, 2, IM2COL>(p, stream, cls) : launch_tc<64, 3, IM2COL>(p, stream, cls);
 }
@@ -969,3 +1049,16 @@ extern "C" int detrb_gemm_tc_force(const detrb_igemm_t *pp, int bn, detrb_stream
     if (kind == 3) return strided_dgrad_tc(p, (cudaStream_t)stream);
     return kind == 1 ? dispatch_tc<false>(p, bn, (cudaStream_t)stream) : dispatch_tc<true>(p, bn, (cudaStream_t)stream);
 }
+
+#ifdef DETRB_TRACE
+extern "C" int detrb_trace_read(unsigned long long *out16, int reset)
+{
+    DETRB_CUDA(cudaDeviceSynchronize());
+    DETRB_CUDA(cudaMemcpyFromSymbol(out16, g_trace, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        DETRB_CUDA(cudaMemcpyToSymbol(g_trace, z, sizeof(z)));
+    }
+    return DETRB_OK;
+}
+#endif
