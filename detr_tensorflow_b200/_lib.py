@@ -56,7 +56,7 @@ class IgemmParams(Structure):
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int), ("mask", c_void_p), ("ldm", c_int),
         ("mask_scale", c_float), ("relu", c_int), ("sigmoid", c_int), ("drop_p", c_float), ("seed", c_uint64),
         ("site", c_uint32), ("seed_ptr", c_void_p), ("C", c_void_p), ("ldc", c_int), ("Cf", c_void_p), ("ldcf", c_int),
-        ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int),
+        ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int), ("a_kb_rows", c_int),
     ]
 
 
@@ -65,7 +65,7 @@ class WgradParams(Structure):
         ("A", c_void_p), ("lda", c_int), ("dY", c_void_p), ("ldy", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
         ("batch", c_int), ("IH", c_int), ("IW", c_int), ("Cin", c_int), ("OH", c_int), ("OW", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int),
-        ("rowscale", c_void_p), ("dW", c_void_p), ("ldw", c_int), ("dbias", c_void_p),
+        ("rowscale", c_void_p), ("dW", c_void_p), ("ldw", c_int), ("dbias", c_void_p), ("a_kb_rows", c_int), ("k_mask", c_int),
     ]
 
 

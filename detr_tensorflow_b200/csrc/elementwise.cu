@@ -170,26 +170,30 @@ __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix
 }
 // space-to-depth(2) of the fp32 NHWC3 image: out[b, y, x, (ry*2+rx)*3 + c] = img[b, 2y+ry, 2x+rx, c] (0 outside, 4 zero pad channels)
 // -> the 7x7 / stride-2 stem becomes a dense 4x4 / stride-1 convolution over 16-channel pixels (32 B: one TMA im2col row)
-__global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H, int W, int H2, int W2)
+__global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP)
 {
     pdl_trigger();
     pdl_wait();
+    // one thread per pixel of the (zero-padded) output [B, HP, WP, 16]; the frame's pixel (y2, x2) lands at (pt + y2, pl + x2)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * H2 * W2) return;
-    int x2 = i % W2; int y2 = (i / W2) % H2; int b = i / ((int64_t)W2 * H2);
+    if (i >= (int64_t)B * HP * WP) return;
+    int xp = i % WP; int yp = (i / WP) % HP; int b = i / ((int64_t)WP * HP);
+    const int x2 = xp - pl, y2 = yp - pt;
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.f;
+    if (x2 >= 0 && x2 < W2 && y2 >= 0 && y2 < H2) {
 #pragma unroll
-    for (int ry = 0; ry < 2; ry++)
+        for (int ry = 0; ry < 2; ry++)
 #pragma unroll
-        for (int rx = 0; rx < 2; rx++) {
-            int y = 2 * y2 + ry, x = 2 * x2 + rx;
-            if (y < H && x < W) {
-                const float *px = img + (((size_t)b * H + y) * W + x) * 3;
-                v[(ry * 2 + rx) * 3 + 0] = px[0]; v[(ry * 2 + rx) * 3 + 1] = px[1]; v[(ry * 2 + rx) * 3 + 2] = px[2];
+            for (int rx = 0; rx < 2; rx++) {
+                int y = 2 * y2 + ry, x = 2 * x2 + rx;
+                if (y < H && x < W) {
+                    const float *px = img + (((size_t)b * H + y) * W + x) * 3;
+                    v[(ry * 2 + rx) * 3 + 0] = px[0]; v[(ry * 2 + rx) * 3 + 1] = px[1]; v[(ry * 2 + rx) * 3 + 2] = px[2];
+                }
             }
-        }
+    }
     uint4 o0, o1;
     o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
     o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
@@ -234,7 +238,7 @@ colsum_kernel(const bf16 *x, int ldx, int M, int N, const float *scale, float *o
 }
 
 // ---------------------------------------------------------------- max pool 3x3 s2 pad 1 (zero pad == -inf pad: x >= 0)
-__global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW)
+__global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW, int XH, int XW)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -257,7 +261,7 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
             int iy = oy * 2 - 1 + kh, ix = ox * 2 - 1 + kw;
             if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;
             float v[8];
-            unpack8(*reinterpret_cast<const uint4 *>(x + (((size_t)b * IH + iy) * IW + ix) * C + c8 * 8), v);
+            unpack8(*reinterpret_cast<const uint4 *>(x + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8), v);   // x is [B, XH, XW, C]
 #pragma unroll
             for (int i = 0; i < 8; i++) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = kh * 3 + kw; }
         }
@@ -269,18 +273,23 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
     *reinterpret_cast<uint2 *>(argmax + o) = a;
 }
 
-// dx[b,iy,ix,c] = (x > 0) * sum over the <= 4 windows containing (iy,ix) whose argmax is this pixel
+// dx[b,iy,ix,c] = (x > 0) * sum over the <= 4 windows containing (iy,ix) whose argmax is this pixel.  x and dx are [B, XH, XW, C]
+// (XH >= IH, XW >= IW): the positions outside IH x IW are written as zeros
 __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const bf16 *x, bf16 *dx,
-                                   int B, int IH, int IW, int C, int OH, int OW)
+                                   int B, int IH, int IW, int C, int OH, int OW, int XH, int XW)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
     const int cv = C / 8;
     const int tx = blockIdx.x * blockDim.x + threadIdx.x;
     const int ix = tx / cv, c8 = tx - ix * cv;
-    if (ix >= IW) return;
+    if (ix >= XW) return;
     const int iy = blockIdx.y, b = blockIdx.z;
-    const size_t pix = ((size_t)b * IH + iy) * IW + ix;
+    const size_t pix = ((size_t)b * XH + iy) * XW + ix;
+    if (ix >= IW || iy >= IH) {
+        *reinterpret_cast<uint4 *>(dx + (size_t)pix * C + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
@@ -395,12 +404,15 @@ extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t n
     return DETRB_OK;
 }
 
-extern "C" int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, detrb_stream_t stream)
+extern "C" int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, int pad_top, int pad_left, int HP, int WP,
+                                    detrb_stream_t stream)
 {
     DETRB_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "detrb_image_to_s2d16: bad args");
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-    int64_t n = (int64_t)B * H2 * W2;
-    DETRB_LAUNCH(image_to_s2d16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint4 *)out, B, H, W, H2, W2);
+    DETRB_REQUIRE(pad_top >= 0 && pad_left >= 0 && HP >= H2 + pad_top && WP >= W2 + pad_left, "detrb_image_to_s2d16: padded size too small");
+    int64_t n = (int64_t)B * HP * WP;
+    DETRB_LAUNCH(image_to_s2d16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint4 *)out, B, H, W, H2, W2,
+                 pad_top, pad_left, HP, WP);
     DETRB_CHECK_LAUNCH("image_to_s2d16_kernel");
     return DETRB_OK;
 }
@@ -426,23 +438,25 @@ extern "C" int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const fl
 }
 
 extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW,
-                                 detrb_stream_t stream)
+                                 int XH, int XW, detrb_stream_t stream)
 {
     DETRB_REQUIRE(x && y && argmax && C % 8 == 0, "detrb_maxpool_fwd: bad args");
     DETRB_REQUIRE(OH == (IH + 2 - 3) / 2 + 1 && OW == (IW + 2 - 3) / 2 + 1, "detrb_maxpool_fwd: bad output size");
     DETRB_REQUIRE(OH <= 65535 && B <= 65535, "detrb_maxpool_fwd: grid too large");
-    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)ceil_div(OW * (C / 8), 256), (unsigned)OH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW);
+    DETRB_REQUIRE(XH >= IH && XW >= IW, "detrb_maxpool_fwd: allocated extent smaller than the image");
+    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)ceil_div(OW * (C / 8), 256), (unsigned)OH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW, XH, XW);
     DETRB_CHECK_LAUNCH("maxpool_fwd_kernel");
     return DETRB_OK;
 }
 
 extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
-                                 int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream)
+                                 int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream)
 {
     DETRB_REQUIRE(dy && argmax && x && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
-    DETRB_REQUIRE(IH <= 65535 && B <= 65535, "detrb_maxpool_bwd: grid too large");
-    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(IW * (C / 8), 256), (unsigned)IH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
-                                                                                          B, IH, IW, C, OH, OW);
+    DETRB_REQUIRE(XH <= 65535 && B <= 65535, "detrb_maxpool_bwd: grid too large");
+    DETRB_REQUIRE(XH >= IH && XW >= IW, "detrb_maxpool_bwd: allocated extent smaller than the image");
+    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(XW * (C / 8), 256), (unsigned)XH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
+                                                                                          B, IH, IW, C, OH, OW, XH, XW);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
     return DETRB_OK;
 }

@@ -87,7 +87,7 @@ struct SmemLayout {
 // IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
 // 3x3 / strided / transposed); `aux` carries the effective padding and the im2col-tap -> weight-tap map.
 template <int BN, int STAGES, bool IM2COL>
-__global__ void __launch_bounds__(NTHREADS_TC)
+__global__ void __launch_bounds__(NTHREADS_TC, BN == 64 ? 5 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux, const int tma_epi)
@@ -170,7 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
                     tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
                 } else {
-                    tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                    // sliding-window A (a_kb_rows > 0): k-block kb is the 64-element run that starts kb * a_kb_rows rows further down
+                    tma_load_2d(a_dst, &map_a, full_bar(stage), p.a_kb_rows ? 0 : kb * TBK, m0 + kb * p.a_kb_rows);
                     tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
                 }
                 if (kb == 0 && tma_epi && ((p.residual && !r_early) || p.mask)) {
@@ -578,7 +579,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
                         tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
                     } else {
-                        tma_load_2d(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                        tma_load_2d(a_dst, &map_a, full_bar(stage), p.a_kb_rows ? 0 : kb * TBK, m0 + kb * p.a_kb_rows);
                         tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
                     }
                     if (++stage == PST) { stage = 0; phase ^= 1; }
@@ -809,6 +810,12 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM,
                                        aux.c16 ? 2 : 1, aux.c16 ? 16 : 64);
         if (rc) return rc;
+    } else if (p.a_kb_rows > 0) {
+        // sliding-window operand: every row is one 64-element run, consecutive rows start lda elements apart (they overlap when
+        // lda < 64); the map spans the rows the last k-block of the last tile row can reach
+        const uint64_t rows = (uint64_t)p.M + (uint64_t)(p.K / TBK - 1) * (uint64_t)p.a_kb_rows;
+        if (!make_map(&ma, p.A, rows, TBK, (uint64_t)p.lda, TBM))
+            DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(sliding A) failed (rows=%llu lda=%d)", (unsigned long long)rows, p.lda);
     } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM)) {
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     }

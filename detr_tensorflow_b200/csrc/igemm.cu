@@ -259,6 +259,10 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(!p.mask || p.ldm % 2 == 0, "detrb_igemm: ldm must be even");
     DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_igemm: drop_p");
     if (p.out_stride < 1) p.out_stride = 1;
+    if (p.a_kb_rows) {                                                // sliding-window A: a plain GEMM as far as the tcgen05 kernel is concerned
+        DETRB_REQUIRE(p.a_kb_rows > 0 && detrb_gemm_tc_kind(p) == 1, "detrb_igemm: a_kb_rows needs plain geometry and the tcgen05 path");
+        return detrb_gemm_tc(p, stream);
+    }
     if (detrb_gemm_tc_enabled()) {                                    // tcgen05 / TMA / TMEM
         const int kind = detrb_gemm_tc_kind(p);
         if (kind == 1 || (kind >= 2 && detrb_gemm_tc_conv_enabled())) return detrb_gemm_tc(p, stream);

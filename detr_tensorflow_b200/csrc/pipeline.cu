@@ -50,23 +50,26 @@ __global__ void normalize_u8_tail_kernel(const uint8_t *img, const float *lut, i
 // (same channel order as image_to_s2d16_kernel: (ry*2+rx)*3 + c, 4 zero channels; pixels outside the frame are 0)
 __global__ void __launch_bounds__(256)
 image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restrict__ lut, int swap, uint4 *__restrict__ out,
-                         int B, int H, int W, int H2, int W2)
+                         int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP)
 {
     pdl_trigger();
     pdl_wait();
     __shared__ float s_lut[768];
     for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
-    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y2 = blockIdx.y, b = blockIdx.z;
-    if (x2 >= W2) return;
+    // one thread per pixel of the zero-padded output [B, HP, WP, 16]; frame pixel (y2, x2) lands at (pt + y2, pl + x2)
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yp = blockIdx.y, b = blockIdx.z;
+    if (xp >= WP) return;
+    const int x2 = xp - pl, y2 = yp - pt;
+    const bool inside = x2 >= 0 && x2 < W2 && y2 >= 0 && y2 < H2;
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) v[k] = 0.f;
 #pragma unroll
     for (int ry = 0; ry < 2; ry++) {
         const int y = 2 * y2 + ry;
-        if (y >= H) continue;
+        if (!inside || y >= H) continue;
         const uint8_t *row = img + ((size_t)b * H + y) * (size_t)W * 3;
 #pragma unroll
         for (int rx = 0; rx < 2; rx++) {
@@ -80,7 +83,7 @@ image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restric
     uint4 o0, o1;
     o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
     o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-    const size_t i = ((size_t)b * H2 + y2) * W2 + x2;
+    const size_t i = ((size_t)b * HP + yp) * WP + xp;
     out[i * 2] = o0; out[i * 2 + 1] = o1;
 }
 
@@ -184,13 +187,14 @@ extern "C" int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap
 }
 
 extern "C" int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
-                                       detrb_stream_t stream)
+                                       int pad_top, int pad_left, int HP, int WP, detrb_stream_t stream)
 {
     DETRB_REQUIRE(img && lut && out && B > 0 && H > 0 && W > 0, "detrb_image_u8_to_s2d16: bad args");
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-    DETRB_REQUIRE(H2 <= 65535 && B <= 65535, "detrb_image_u8_to_s2d16: grid too large");
-    DETRB_LAUNCH(image_u8_to_s2d16_kernel, dim3((unsigned)ceil_div(W2, 256), (unsigned)H2, (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
-                 img, lut, swap_rb, (uint4 *)out, B, H, W, H2, W2);
+    DETRB_REQUIRE(pad_top >= 0 && pad_left >= 0 && HP >= H2 + pad_top && WP >= W2 + pad_left, "detrb_image_u8_to_s2d16: padded size too small");
+    DETRB_REQUIRE(HP <= 65535 && B <= 65535, "detrb_image_u8_to_s2d16: grid too large");
+    DETRB_LAUNCH(image_u8_to_s2d16_kernel, dim3((unsigned)ceil_div(WP, 256), (unsigned)HP, (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
+                 img, lut, swap_rb, (uint4 *)out, B, H, W, H2, W2, pad_top, pad_left, HP, WP);
     DETRB_CHECK_LAUNCH("image_u8_to_s2d16_kernel");
     return DETRB_OK;
 }

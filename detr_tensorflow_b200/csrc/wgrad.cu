@@ -175,6 +175,11 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "detrb_wgrad: empty problem");
     DETRB_REQUIRE(p.M == p.batch * p.OH * p.OW, "detrb_wgrad: M=%d != batch*OH*OW", p.M);
     DETRB_REQUIRE(p.ldy >= ((p.N + 7) & ~7) && p.ldy % 8 == 0, "detrb_wgrad: ldy=%d must cover N=%d rounded to 8", p.ldy, p.N);
+    if (p.a_kb_rows || p.k_mask) {                             // sliding-window A / stem column mask: tcgen05 kernel only
+        DETRB_REQUIRE(p.a_kb_rows >= 0 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && detrb_wgrad_tc_supported(p),
+                      "detrb_wgrad: a_kb_rows / k_mask need plain geometry and the tcgen05 kernel");
+        return detrb_wgrad_tc(p, stream);
+    }
     if (detrb_wgrad_tc_enabled() && detrb_wgrad_tc_supported(p) && detrb_wgrad_tc_profitable(p)) {           // tcgen05 / TMA im2col / TMEM
         return detrb_wgrad_tc(p, stream);                      // bias gradient fused (k-tile 0 CTAs)
     }

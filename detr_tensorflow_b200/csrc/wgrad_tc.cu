@@ -126,8 +126,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                         tma_load_im2col(dst + (2 + j) * BOX_BYTES, &map_x, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
                     }
                 } else {
-                    tma_load_2d(dst + 2 * BOX_BYTES, &map_x, full_bar(stage), k0, m);
-                    tma_load_2d(dst + 3 * BOX_BYTES, &map_x, full_bar(stage), k0 + 64, m);
+                    // sliding-window A (a_kb_rows > 0): 64-column block j is the 64-element run j * a_kb_rows rows further down
+                    const int kb = k0 / 64, sl = p.a_kb_rows;
+                    tma_load_2d(dst + 2 * BOX_BYTES, &map_x, full_bar(stage), sl ? 0 : k0, m + kb * sl);
+                    tma_load_2d(dst + 3 * BOX_BYTES, &map_x, full_bar(stage), sl ? 0 : k0 + 64, m + (kb + 1) * sl);
                 }
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
@@ -208,7 +210,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 for (int i = 0; i < 4; i++) {
                     const int k = k0 + c0 + i4 + i;
                     ok[i] = k < p.K;
-                    if (C16 && stem_mask) {
+                    if (stem_mask) {
                         // space-to-depth stem: column k = (ta, tb, (ry*2+rx)*3 + c) stands for the 7x7 tap (2ta+ry-1, 2tb+rx-1);
                         // taps outside 0..6 and the 4 padding channels do not exist in the reference kernel: no gradient
                         const int ch = k & 15, tb = (k >> 4) & 3, ta = k >> 6;
@@ -268,7 +270,11 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     CUtensorMap my, mx;
     if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64))
         DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for dY failed (M=%d N=%d ldy=%d)", p.M, p.N, p.ldy);
-    if (plain) {
+    if (plain && p.a_kb_rows > 0) {
+        const uint64_t rows = (uint64_t)p.M + (uint64_t)(p.K / 64 - 1) * (uint64_t)p.a_kb_rows;
+        if (p.K % WK != 0 || !detrb_make_tiled_map(&mx, p.A, rows, 64, (uint64_t)p.lda, WP, 64))
+            DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for the sliding-window A failed (rows=%llu K=%d lda=%d)", (unsigned long long)rows, p.K, p.lda);
+    } else if (plain) {
         if (!detrb_make_tiled_map(&mx, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64))
             DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for A failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     } else {
@@ -297,11 +303,11 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         configured = true;
     }
     dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
-    const int stem_mask = (c16 && p.KH == 4 && p.KW == 4 && p.pad == 2) ? 1 : 0;
+    const int stem_mask = ((c16 && p.KH == 4 && p.KW == 4 && p.pad == 2) || p.k_mask) ? 1 : 0;
     if (c16) {
         DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), SMEM16, stream, my, mx, p, pix_per_split, stem_mask);
     } else if (plain) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
+        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, stem_mask);
     } else {
         DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
     }

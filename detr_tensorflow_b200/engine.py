@@ -383,12 +383,20 @@ class Engine:
         h2, w2 = o(h1, 3, 2, 1), o(w1, 3, 2, 1)
         self.hw_stem, self.hw_pool = (h1, w1), (h2, w2)
         self.hw_s2d = ((H + 1) // 2, (W + 1) // 2)
-        buf("s2d", B, self.hw_s2d[0], self.hw_s2d[1], 16)
-        buf("stem", B, h1, w1, 64)
+        # stem as a sliding-window GEMM: the space-to-depth image carries the stem's zero padding explicitly (2 pixels above / left,
+        # 1 below / right), so the 4 taps (tb) of window row ta at output pixel q are the 64 contiguous elements starting at flat
+        # pixel q + ta*WP -- the stem output (and its gradient) live at the same [HP, WP] pitch; the 3 extra rows / columns per
+        # image hold wrapped-window values that nothing reads (maxpool_fwd) and zeros in the gradient (maxpool_bwd)
+        self.hw_pad = (self.hw_s2d[0] + 3, self.hw_s2d[1] + 3)
+        HP, WP = self.hw_pad
+        self.M_stem = B * HP * WP
+        # + the reach of the last window (3 rows + 4 pixels): zero, never written
+        a["s2d"] = torch.zeros(self.M_stem + 3 * WP + 8, 16, dtype=BF16, device=dev)
+        buf("stem", B, HP, WP, 64)
         buf("pool", B, h2, w2, 64)
         buf("pool_arg", B, h2, w2, 64, dtype=torch.uint8)
         hh, ww = h2, w2
-        max_elems = B * h1 * w1 * 64
+        max_elems = self.M_stem * 64
         for i, blk in enumerate(self.blocks):
             st = blk["stride"]
             ho, wo = (o(hh, 3, st, 1), o(ww, 3, st, 1)) if st > 1 else (hh, ww)
@@ -680,14 +688,19 @@ class Engine:
         scale = float(d // Hh) ** -0.5
         # ---------------- backbone (resnet_backbone.py:20-32)
         # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels (tcgen05 im2col kernel)
+        HP, WP = self.hw_pad
         if self.u8_input:                     # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
-            ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0)
+            ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP)
         else:
-            ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0)
+            ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP)
         self.launches += 1
         stem = self.slots["backbone/conv1"]
-        self._conv_fwd(stem, a["s2d"], self.hw_s2d, self.hw_stem, a["stem"], relu=True)
-        ops.maxpool_fwd(a["stem"], a["pool"], a["pool_arg"], B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
+        # one plain GEMM [B*HP*WP, 256] x [64, 256]^T whose A rows are overlapping 128-byte windows of the padded image
+        self.launches += 1
+        ops.igemm(a["s2d"], stem.Wf, self.M_stem, stem.N, stem.K, 16, stem.K, ops.plain_geom(self.M_stem, stem.K),
+                  bias=stem.epi_bias, relu=True, C=a["stem"], ldc=stem.N, a_kb_rows=WP)
+        ops.maxpool_fwd(a["stem"], a["pool"], a["pool_arg"], B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
+                        XH=HP, XW=WP)
         self.launches += 1
         x = a["pool"]
         for i, blk in enumerate(self.blocks):
@@ -973,9 +986,14 @@ class Engine:
         # g_out now holds d pool
         self.launches += 1
         self._before_write(g_in)
-        ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1])
+        HP, WP = self.hw_pad
+        ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
+                        XH=HP, XW=WP)
         stem = self.slots["backbone/conv1"]
-        self._conv_wgrad(stem, a["s2d"], g_in, self.hw_s2d, self.hw_stem)
+        self.launches += 1
+        x, Ms = a["s2d"], self.M_stem
+        self._on_wstream(lambda: ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
+                                           rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True), (x, g_in))
         self._in_backward = False
         self._join_wgrad()
         self._mark("bwd_backbone")

@@ -30,7 +30,7 @@ def plain_geom(M, K):
 
 def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mask=None, ldm=0, mask_scale=1.0,
           relu=False, sigmoid=False, drop_p=0.0, seed=0, site=0, seed_ptr=None, C=None, ldc=0, Cf=None, ldcf=0,
-          out_stride=1, SH=0, SW=0, accumulate=False, force_tc=None):
+          out_stride=1, SH=0, SW=0, accumulate=False, a_kb_rows=0, force_tc=None):
     p = IgemmParams()
     p.A, p.W = ptr(A), ptr(W)
     p.M, p.N, p.K, p.lda, p.ldw = M, N, K, lda, ldw
@@ -39,7 +39,7 @@ def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mas
     p.bias, p.residual, p.ldr, p.mask, p.ldm, p.mask_scale = ptr(bias), ptr(residual), ldr, ptr(mask), ldm, mask_scale
     p.relu, p.sigmoid, p.drop_p, p.seed, p.site, p.seed_ptr = int(relu), int(sigmoid), drop_p, seed, site, ptr(seed_ptr)
     p.C, p.ldc, p.Cf, p.ldcf = ptr(C), ldc, ptr(Cf), ldcf
-    p.out_stride, p.SH, p.SW, p.accumulate = out_stride, SH, SW, int(accumulate)
+    p.out_stride, p.SH, p.SW, p.accumulate, p.a_kb_rows = out_stride, SH, SW, int(accumulate), a_kb_rows
     if force_tc is not None:
         check(_lib.lib().detrb_gemm_tc_force(byref(p), c_int(force_tc), _stream()))
     else:
@@ -67,13 +67,14 @@ def set_tc_conv(enable):
     return _lib.lib().detrb_set_tc_conv(c_int(int(enable)))
 
 
-def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None, force_tc=False):
+def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None, a_kb_rows=0, k_mask=False, force_tc=False):
     p = WgradParams()
     p.A, p.lda, p.dY, p.ldy, p.M, p.N, p.K = ptr(A), lda, ptr(dY), ldy, M, N, K
     for k, v in geom.items():
         if k != "mode":
             setattr(p, k, v)
     p.rowscale, p.dW, p.ldw, p.dbias = ptr(rowscale), ptr(dW), ldw, ptr(dbias)
+    p.a_kb_rows, p.k_mask = a_kb_rows, int(k_mask)
     if force_tc:
         check(_lib.lib().detrb_wgrad_tc_force(byref(p), _stream()))
     else:
@@ -122,8 +123,10 @@ def image_to_nhwc4(img, out, npix):
     check(_lib.lib().detrb_image_to_nhwc4(ptr(img), ptr(out), c_int64(npix), _stream()))
 
 
-def image_to_s2d16(img, out, B, H, W):
-    check(_lib.lib().detrb_image_to_s2d16(ptr(img), ptr(out), c_int(B), c_int(H), c_int(W), _stream()))
+def image_to_s2d16(img, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None):
+    HP, WP = HP or (H + 1) // 2, WP or (W + 1) // 2
+    check(_lib.lib().detrb_image_to_s2d16(ptr(img), ptr(out), c_int(B), c_int(H), c_int(W), c_int(pad_top), c_int(pad_left),
+                                          c_int(HP), c_int(WP), _stream()))
 
 
 def f32_to_bf16(x, y, n):
@@ -134,14 +137,14 @@ def colsum(x, ldx, M, N, scale, out):
     check(_lib.lib().detrb_colsum(ptr(x), c_int(ldx), c_int(M), c_int(N), ptr(scale), ptr(out), _stream()))
 
 
-def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW):
+def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW, XH=None, XW=None):
     check(_lib.lib().detrb_maxpool_fwd(ptr(x), ptr(y), ptr(argmax), c_int(B), c_int(IH), c_int(IW), c_int(C),
-                                       c_int(OH), c_int(OW), _stream()))
+                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
 
 
-def maxpool_bwd(dy, argmax, x, dx, B, IH, IW, C, OH, OW):
+def maxpool_bwd(dy, argmax, x, dx, B, IH, IW, C, OH, OW, XH=None, XW=None):
     check(_lib.lib().detrb_maxpool_bwd(ptr(dy), ptr(argmax), ptr(x), ptr(dx), c_int(B), c_int(IH), c_int(IW), c_int(C),
-                                       c_int(OH), c_int(OW), _stream()))
+                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
 
 
 def matcher(logits, ldl, boxes, t_bbox, t_class, P, B, Q, C, p_indices, t_indices, p_selector, match, cost, status,
@@ -197,9 +200,10 @@ def normalize_u8(img_u8, lut, swap_rb, out_f32, npix):
     check(_lib.lib().detrb_normalize_u8(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out_f32), c_int64(npix), _stream()))
 
 
-def image_u8_to_s2d16(img_u8, lut, swap_rb, out, B, H, W):
+def image_u8_to_s2d16(img_u8, lut, swap_rb, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None):
+    HP, WP = HP or (H + 1) // 2, WP or (W + 1) // 2
     check(_lib.lib().detrb_image_u8_to_s2d16(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out), c_int(B), c_int(H), c_int(W),
-                                             _stream()))
+                                             c_int(pad_top), c_int(pad_left), c_int(HP), c_int(WP), _stream()))
 
 
 def postprocess(logits, ldl, boxes, B, Q, C, background_class, bbox_format, out_boxes, out_labels, out_scores, out_query,

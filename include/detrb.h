@@ -86,6 +86,12 @@ typedef struct {
     float *Cf; int ldcf;
     int out_stride, SH, SW;
     int accumulate;
+    /* sliding-window A operand (0 = ordinary row-major A): k-block j (64 columns) of row m is the 64 contiguous elements at
+     * A + (m + j*a_kb_rows)*lda, and lda may be smaller than 64 (overlapping rows).  A zero-padded NHWC tensor with 16-channel
+     * pixels read this way IS the im2col matrix of a 4-tap-wide convolution at the pitch of the padded input (the
+     * space-to-depth stem: a_kb_rows = padded width).  The caller guarantees (M + (K/64-1)*a_kb_rows)*lda + 64 readable elements.
+     * Plain geometry only; tcgen05 path only (DETRB_E_SHAPE otherwise). */
+    int a_kb_rows;
 } detrb_igemm_t;
 
 int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
@@ -112,6 +118,9 @@ typedef struct {
     const float *rowscale;       /* [N] or NULL */
     float *dW; int ldw;          /* fp32 [N, K] */
     float *dbias;                /* fp32 [N] or NULL */
+    int a_kb_rows;               /* sliding-window A operand as in detrb_igemm_t: plain geometry, tcgen05 kernel only */
+    int k_mask;                  /* 1: A is the space-to-depth stem operand -- columns of dW that do not exist in the 7x7x3 kernel
+                                  * (resnet_backbone.py:11) receive no gradient */
 } detrb_wgrad_t;
 
 int detrb_wgrad(const detrb_wgrad_t *p, detrb_stream_t stream);
@@ -170,9 +179,13 @@ int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *o
 int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *out, int64_t n, detrb_stream_t stream);
 /* fp32 NHWC3 image -> bf16 NHWC4 (4th channel 0): the layout the stem kernel gathers from */
 int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_stream_t stream);
-/* fp32 NHWC3 image -> bf16 space-to-depth(2) tensor [B, ceil(H/2), ceil(W/2), 16] (channel (ry*2+rx)*3+c, 4 zero channels):
- * turns the 7x7/stride-2 stem (resnet_backbone.py:11-12) into a dense 4x4/stride-1 conv the tcgen05 im2col kernel can run */
-int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, detrb_stream_t stream);
+/* fp32 NHWC3 image -> bf16 space-to-depth(2) tensor (channel (ry*2+rx)*3+c, 4 zero channels): turns the 7x7/stride-2 stem
+ * (resnet_backbone.py:11-12) into a dense 4x4/stride-1 convolution over 16-channel (32-byte) pixels.  out is [B, HP, WP, 16]:
+ * the frame's ceil(H/2) x ceil(W/2) pixels start at (pad_top, pad_left), every other position is written as zero -- with
+ * pad 2/2 and HP = ceil(H/2)+3, WP = ceil(W/2)+3 the stem's zero padding is explicit and the convolution is a sliding-window
+ * GEMM over the flat tensor (detrb_igemm_t.a_kb_rows = WP).  pad 0/0, HP = ceil(H/2), WP = ceil(W/2): the dense tensor. */
+int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, int pad_top, int pad_left, int HP, int WP,
+                         detrb_stream_t stream);
 /* fp32 -> bf16 */
 int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream);
 /* column sums: out[n] += scale[n]* sum_m x[m,n]  (bias gradients) */
@@ -181,11 +194,14 @@ int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const float *scale,
 
 /* ZeroPadding2D(1)+MaxPool2D(3,2,'valid') (resnet_backbone.py:16-17,25-26), NHWC, C%8==0.
  * fwd stores the argmax tap (0..8) per output element; bwd routes dy to it and applies the
- * stem ReLU mask (x > 0). */
+ * stem ReLU mask (x > 0).
+ * x (and dx) are stored [B, XH, XW, C] with XH >= IH, XW >= IW (the image in the top-left corner; XH = IH, XW = IW: dense):
+ * fwd ignores the positions outside IH x IW, bwd writes them as zeros (they are the wrapped-window rows of the sliding-window
+ * stem GEMM, whose weight gradient must not see them). */
 int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax,
-                      int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream);
+                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
 int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
-                      int B, int IH, int IW, int C, int OH, int OW, detrb_stream_t stream);
+                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hungarian matcher (loss/hungarian_matching.py:163-203 + :27-46 -> scipy LSAP) for P = L*B
@@ -279,9 +295,9 @@ int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int 
  *   swap_rb != 0 reads input channel 2-c (normalized_method "tf_resnet": RGB -> BGR).  out [npix, 3] f32. */
 int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float *out, int64_t npix, detrb_stream_t stream);
 /* The same normalisation fused into the stem's input layout: img [B,H,W,3] u8 -> bf16 space-to-depth(2) tensor
- * [B, ceil(H/2), ceil(W/2), 16] (see detrb_image_to_s2d16); the fp32 image never exists in HBM. */
+ * [B, HP, WP, 16] (padding arguments as in detrb_image_to_s2d16); the fp32 image never exists in HBM. */
 int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
-                            detrb_stream_t stream);
+                            int pad_top, int pad_left, int HP, int WP, detrb_stream_t stream);
 /* Inference post-process (inference.py:68-95, get_model_inference) for B images in one launch:
  *   logits [B,Q,C] f32 (row stride ldl), boxes [B,Q,4] f32 cxcywh (16-byte aligned).
  *   Per query: softmax, score = max probability, label = argmax of the softmax (first index on ties); queries whose label

@@ -134,6 +134,18 @@ def _gather(p_A, lda, M, K, batch, IH, IW, Cin, OH, OW, KH, KW, stride, pad, mod
     return out
 
 
+def _sliding(p_A, lda, M, K, kb_rows):
+    """sliding-window A operand (detrb_igemm_t.a_kb_rows): k-block j of row m = 64 elements at A + (m + j*kb_rows)*lda"""
+    nk = K // 64
+    flat = T(p_A, _Act.dtype, (M + (nk - 1) * kb_rows) * lda + 64).to(F32)
+    m = torch.arange(M)
+    cols = []
+    for j in range(nk):
+        idx = ((m + j * kb_rows) * lda)[:, None] + torch.arange(64)[None, :]
+        cols.append(flat[idx])
+    return torch.cat(cols, dim=1)
+
+
 class FakeLib:
     def __init__(self):
         self.err = b""
@@ -163,7 +175,10 @@ class FakeLib:
     def detrb_igemm(self, pref, stream):
         p = pref._obj
         stem = p.Cin == 4
-        Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, p.mode)
+        if p.a_kb_rows:
+            Ag = _sliding(p.A, p.lda, p.M, p.K, p.a_kb_rows)
+        else:
+            Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, p.mode)
         W = M2(p.W, _Act.dtype, p.N, p.K, p.ldw).to(F32)
         v = Ag @ W.t()
         out_stride = max(p.out_stride, 1)
@@ -204,11 +219,14 @@ class FakeLib:
     def detrb_wgrad(self, pref, stream):
         p = pref._obj
         stem = p.Cin == 4
-        Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, 0,
-                     stem_real_kw=7 if stem else None)
+        if p.a_kb_rows:
+            Ag = _sliding(p.A, p.lda, p.M, p.K, p.a_kb_rows)
+        else:
+            Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, 0,
+                         stem_real_kw=7 if stem else None)
         dY = M2(p.dY, _Act.dtype, p.M, p.N, p.ldy).to(F32)
         g = dY.t() @ Ag
-        if p.Cin == 16 and p.KH == 4 and p.KW == 4 and p.pad == 2:
+        if p.k_mask or (p.Cin == 16 and p.KH == 4 and p.KW == 4 and p.pad == 2):
             # space-to-depth stem: columns of taps that do not exist in the 7x7x3 kernel get no gradient
             k = torch.arange(p.K)
             ch, tb, ta = k % 16, (k // 16) % 4, k // 64
@@ -332,17 +350,17 @@ class FakeLib:
         o[:, 3] = 0
         return 0
 
-    def detrb_image_to_s2d16(self, img, out, B, H, W, stream):
-        B, H, W = _v(B), _v(H), _v(W)
+    def detrb_image_to_s2d16(self, img, out, B, H, W, pad_top, pad_left, HP, WP, stream):
+        B, H, W, pt, pl, HP, WP = map(_v, (B, H, W, pad_top, pad_left, HP, WP))
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         x = T(img, F32, B * H * W * 3).view(B, H, W, 3)
         xp = torch.zeros(B, 2 * H2, 2 * W2, 3)
         xp[:, :H, :W] = x
-        o = torch.zeros(B, H2, W2, 16)
+        o = torch.zeros(B, HP, WP, 16)
         for ry in range(2):
             for rx in range(2):
-                o[..., (ry * 2 + rx) * 3:(ry * 2 + rx) * 3 + 3] = xp[:, ry::2, rx::2]
-        T(out, _Act.dtype, B * H2 * W2 * 16)[:] = o.reshape(-1).to(_Act.dtype)
+                o[:, pt:pt + H2, pl:pl + W2, (ry * 2 + rx) * 3:(ry * 2 + rx) * 3 + 3] = xp[:, ry::2, rx::2]
+        T(out, _Act.dtype, B * HP * WP * 16)[:] = o.reshape(-1).to(_Act.dtype)
         return 0
 
     def detrb_f32_to_bf16(self, x, y, n, stream):
@@ -358,9 +376,9 @@ class FakeLib:
         T(out, F32, N).add_(s)
         return 0
 
-    def detrb_maxpool_fwd(self, x, y, argmax, B, IH, IW, C, OH, OW, stream):
-        B, IH, IW, C, OH, OW = map(_v, (B, IH, IW, C, OH, OW))
-        xv = T(x, _Act.dtype, B * IH * IW * C).to(F32).view(B, IH, IW, C)
+    def detrb_maxpool_fwd(self, x, y, argmax, B, IH, IW, C, OH, OW, XH, XW, stream):
+        B, IH, IW, C, OH, OW, XH, XW = map(_v, (B, IH, IW, C, OH, OW, XH, XW))
+        xv = T(x, _Act.dtype, B * XH * XW * C).to(F32).view(B, XH, XW, C)[:, :IH, :IW]
         best = torch.full((B, OH, OW, C), -float("inf"))
         arg = torch.zeros((B, OH, OW, C), dtype=torch.uint8)
         oy, ox = torch.arange(OH), torch.arange(OW)
@@ -378,12 +396,12 @@ class FakeLib:
         T(argmax, torch.uint8, B * OH * OW * C)[:] = arg.reshape(-1)
         return 0
 
-    def detrb_maxpool_bwd(self, dy, argmax, x, dx, B, IH, IW, C, OH, OW, stream):
-        B, IH, IW, C, OH, OW = map(_v, (B, IH, IW, C, OH, OW))
+    def detrb_maxpool_bwd(self, dy, argmax, x, dx, B, IH, IW, C, OH, OW, XH, XW, stream):
+        B, IH, IW, C, OH, OW, XH, XW = map(_v, (B, IH, IW, C, OH, OW, XH, XW))
         d = T(dy, _Act.dtype, B * OH * OW * C).to(F32).view(B, OH, OW, C)
         arg = T(argmax, torch.uint8, B * OH * OW * C).view(B, OH, OW, C)
-        xv = T(x, _Act.dtype, B * IH * IW * C).to(F32).view(B, IH, IW, C)
-        out = torch.zeros(B, IH, IW, C)
+        xv = T(x, _Act.dtype, B * XH * XW * C).to(F32).view(B, XH, XW, C)
+        out = torch.zeros(B, XH, XW, C)
         for oy in range(OH):
             for ox in range(OW):
                 for kh in range(3):
@@ -392,7 +410,9 @@ class FakeLib:
                         if 0 <= iy < IH and 0 <= ix < IW:
                             out[:, iy, ix] += d[:, oy, ox] * (arg[:, oy, ox] == kh * 3 + kw).to(F32)
         out = out * (xv > 0).to(F32)
-        T(dx, _Act.dtype, B * IH * IW * C)[:] = out.reshape(-1).to(_Act.dtype)
+        out[:, IH:] = 0
+        out[:, :, IW:] = 0
+        T(dx, _Act.dtype, B * XH * XW * C)[:] = out.reshape(-1).to(_Act.dtype)
         return 0
 
     # -- matcher / loss
@@ -556,10 +576,10 @@ class FakeLib:
         T(out, F32, npix * 3)[:] = self._lut_apply(img, lut, swap, npix).reshape(-1)
         return 0
 
-    def detrb_image_u8_to_s2d16(self, img, lut, swap, out, B, H, W, stream):
+    def detrb_image_u8_to_s2d16(self, img, lut, swap, out, B, H, W, pad_top, pad_left, HP, WP, stream):
         B, H, W = _v(B), _v(H), _v(W)
         x = self._lut_apply(img, lut, swap, B * H * W).contiguous()
-        return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, stream)
+        return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, pad_top, pad_left, HP, WP, stream)
 
     def detrb_postprocess(self, logits, ldl, boxes, B, Q, C, bg, fmt, out_boxes, out_labels, out_scores, out_query, out_count,
                           stream):

@@ -256,3 +256,68 @@ def test_stem_space_to_depth_conv_and_wgrad(ops, H, W):
     gw, = torch.autograd.grad(ref, [wt], dy.float().view(B, oh, ow, 64).permute(0, 3, 1, 2))
     ref16 = Engine._stem_to_s2d(None, (gw.permute(0, 2, 3, 1) * scale[:, None, None, None]).cpu()).reshape(64, 256).cuda()
     check("s2d stem wgrad", dW, ref16, 1e-2, 1e-2 * float(ref16.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ stem as a sliding-window GEMM
+@pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224)])
+def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
+    """The production stem: zero-padded space-to-depth image [B, HP, WP, 16] read as a GEMM operand whose rows are overlapping
+    128-byte windows (detrb_igemm_t.a_kb_rows = WP, lda = 16) == 7x7 / stride 2 / pad 3 convolution (resnet_backbone.py:11-12,
+    20-24); max-pool forward / backward on the [HP, WP]-pitched output; weight gradient with the 7x7x3 column mask."""
+    from detr_tensorflow_b200.engine import Engine
+    B = 2
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    HP, WP = H2 + 3, W2 + 3
+    M = B * HP * WP
+    img = rnd(B, H, W, 3, seed=1)
+    s2d = torch.zeros(M + 3 * WP + 8, 16, dtype=BF, device="cuda")
+    s2d[:M].fill_(7.0)                                     # the kernel must overwrite the padding with zeros
+    ops.image_to_s2d16(img, s2d, B, H, W, 2, 2, HP, WP)
+    dense = torch.zeros(B, H2, W2, 16, dtype=BF, device="cuda")
+    ops.image_to_s2d16(img, dense, B, H, W)
+    ref_pad = torch.zeros(B, HP, WP, 16, dtype=BF, device="cuda")
+    ref_pad[:, 2:2 + H2, 2:2 + W2] = dense
+    assert torch.equal(s2d[:M].view(B, HP, WP, 16), ref_pad)
+    w7 = rnd(64, 7, 7, 3, scale=147 ** -0.5, seed=2).to(BF)
+    w16 = Engine._stem_to_s2d(None, w7.float().cpu()).to(BF).cuda().reshape(64, 256).contiguous()
+    shift = rnd(64, seed=3)
+    y = torch.zeros(B, HP, WP, 64, dtype=BF, device="cuda")
+    g = dict(batch=1, IH=1, IW=M, Cin=256, OH=1, OW=M, KH=1, KW=1, stride=1, pad=0, mode=0)
+    ops.igemm(s2d, w16, M, 64, 256, 16, 256, g, bias=shift, relu=True, C=y, ldc=64, a_kb_rows=WP)
+    torch.cuda.synchronize()
+    xt = img.to(BF).float().permute(0, 3, 1, 2)
+    wt = w7.float().permute(0, 3, 1, 2).requires_grad_(True)
+    conv = F.conv2d(xt, wt, bias=shift, stride=2, padding=3)
+    ref = F.relu(conv).permute(0, 2, 3, 1)
+    check("sliding stem fwd", y[:, :H2, :W2], ref, 1e-2, 2e-2)
+    # max-pool on the pitched tensor == max-pool on the dense copy, bit for bit
+    oh, ow = (H2 + 2 - 3) // 2 + 1, (W2 + 2 - 3) // 2 + 1
+    yd = y[:, :H2, :W2].contiguous()
+    p1, a1 = torch.zeros(B, oh, ow, 64, dtype=BF, device="cuda"), torch.zeros(B, oh, ow, 64, dtype=torch.uint8, device="cuda")
+    p2, a2 = torch.zeros_like(p1), torch.zeros_like(a1)
+    ops.maxpool_fwd(y, p1, a1, B, H2, W2, 64, oh, ow, XH=HP, XW=WP)
+    ops.maxpool_fwd(yd, p2, a2, B, H2, W2, 64, oh, ow)
+    assert torch.equal(p1, p2) and torch.equal(a1, a2)
+    dp = rnd(B, oh, ow, 64, seed=4).to(BF)
+    dx1 = torch.full((B, HP, WP, 64), 3.0, dtype=BF, device="cuda")
+    dx2 = torch.zeros(B, H2, W2, 64, dtype=BF, device="cuda")
+    ops.maxpool_bwd(dp, a1, y, dx1, B, H2, W2, 64, oh, ow, XH=HP, XW=WP)
+    ops.maxpool_bwd(dp, a2, yd, dx2, B, H2, W2, 64, oh, ow)
+    assert torch.equal(dx1[:, :H2, :W2], dx2)
+    assert float(dx1[:, H2:].abs().max()) == 0.0 and float(dx1[:, :, W2:].abs().max()) == 0.0
+    # weight gradient over the pitched gradient tensor (zeros in the wrapped rows / columns)
+    dy = torch.zeros(B, HP, WP, 64, dtype=BF, device="cuda")
+    dy[:, :H2, :W2] = rnd(B, H2, W2, 64, seed=5).to(BF)
+    scale = rnd(64, seed=6).abs() + 0.5
+    dW = torch.zeros(64, 256, dtype=F32, device="cuda")
+    db = torch.zeros(64, dtype=F32, device="cuda")
+    ops.wgrad(s2d, 16, dy, 64, M, 64, 256, g, dW, 256, rowscale=scale, dbias=db, a_kb_rows=WP, k_mask=True)
+    torch.cuda.synchronize()
+    gw, = torch.autograd.grad(conv, [wt], dy[:, :H2, :W2].float().permute(0, 3, 1, 2))
+    ref16 = Engine._stem_to_s2d(None, (gw.permute(0, 2, 3, 1) * scale[:, None, None, None]).cpu()).reshape(64, 256).cuda()
+    check("sliding stem wgrad", dW, ref16, 1e-2, 1e-2 * float(ref16.abs().max()))
+    refb = dy.float().sum((0, 1, 2)) * scale
+    check("sliding stem dbias", db, refb, 1e-2, 1e-2 * float(refb.abs().max()))
+    # the columns that do not exist in the 7x7x3 kernel receive exactly zero
+    exists = Engine._stem_to_s2d(None, torch.ones(1, 7, 7, 3)).reshape(256).bool().cuda()
+    assert float(dW[:, ~exists].abs().max()) == 0.0
