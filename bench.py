@@ -376,18 +376,20 @@ def main():
     roof = None
     peak_tf, peak_hbm, how = measured_peaks()
     probe = "backbone/layer3/1/conv2"                                   # 3x3 256->256 @50x84: the heaviest repeated conv shape
-    eng.probe_name, eng.probe_events = probe, []
+    probe_hbm = "backbone/layer1/1/conv3"                               # 1x1 64->256 + residual + ReLU @200x334: the largest HBM-bound launch
+    eng.probe_names, eng.probe_events = (probe, probe_hbm), {}
     for _ in range(3):
         eng.train_step(91, cfg.gradient_norm_clipping)
     torch.cuda.synchronize()
-    times = [a.elapsed_time(b) for a, b in eng.probe_events]
-    eng.probe_name = None
+    times = {k: sorted(a.elapsed_time(b) for a, b in v) for k, v in eng.probe_events.items()}
+    eng.probe_names = None
+    roof_hbm = None
     if rank == 0:
         s = eng.slots[probe]
         blk = [b for b in eng.blocks if b["c2"] is s][0]
         M = B * blk["out_hw"][0] * blk["out_hw"][1]
         flops = 2.0 * M * s.N * s.K
-        t_k = sorted(times)[len(times) // 2] * 1e-3
+        t_k = times[probe][len(times[probe]) // 2] * 1e-3
         roof = {"bound": "tensor", "kernel": "gemm_tcp_kernel<256,4,im2col> (persistent tcgen05 implicit-GEMM conv 3x3 256->256, 128x256 tiles, layer3, M=33600 N=256 K=2304)",
                 "achieved": flops / t_k / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / t_k / 1e12 / peak_tf,
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
@@ -397,6 +399,16 @@ def main():
         prof = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
         if os.path.exists(prof):
             roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        # the HBM-bound side of the step (layer1/2 1x1 convolutions = the largest share of the step by time): algorithmic bytes
+        # = input + weights + residual + output, bf16
+        s = eng.slots[probe_hbm]
+        blk = [b for b in eng.blocks if b["c3"] is s][0]
+        M = B * blk["out_hw"][0] * blk["out_hw"][1]
+        byts = 2.0 * (M * s.K + s.N * s.K + 2 * M * s.N)
+        t_h = times[probe_hbm][len(times[probe_hbm]) // 2] * 1e-3
+        roof_hbm = {"bound": "hbm", "kernel": "gemm_tc_kernel<64,1> (one-tile tcgen05 GEMM, 1x1 conv 64->256 + residual + ReLU, layer1, M=534400 N=256 K=64)",
+                    "achieved": byts / t_h / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": byts / t_h / 1e9 / peak_hbm, "traffic": None,
+                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})", "bytes_per_launch": byts, "us_per_launch": t_h * 1e6}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only, bounded sample)
     cpu = None
@@ -424,7 +436,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(eng.launches_per_step * K),
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back"},
-            "roofline": roof, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
+            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -267,59 +267,72 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
         }
     size_t o = (size_t)pix * C + c8 * 8;
     *reinterpret_cast<uint4 *>(y + o) = pack8(best);
+    // a window whose maximum is not positive passes no gradient through the stem's ReLU: tap 15 matches no input position,
+    // so the backward pass needs neither x nor y
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (!(best[i] > 0.f)) arg[i] = 15;
     uint2 a;
     a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
     a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
     *reinterpret_cast<uint2 *>(argmax + o) = a;
 }
 
-// dx[b,iy,ix,c] = (x > 0) * sum over the <= 4 windows containing (iy,ix) whose argmax is this pixel.  x and dx are [B, XH, XW, C]
-// (XH >= IH, XW >= IW): the positions outside IH x IW are written as zeros
-__global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, const bf16 *x, bf16 *dx,
+// dx[b,iy,ix,c] = sum over the <= 4 windows containing (iy,ix) whose argmax is this pixel (the stem's ReLU mask is already in the
+// argmax: non-positive maxima were stored as tap 15).  dx is [B, XH, XW, C] (XH >= IH, XW >= IW): the positions outside
+// IH x IW are written as zeros.
+// One thread owns the 2x2 input block (2a..2a+1, 2b..2b+1) x 8 channels: the only windows that reach it are (a,b), (a,b+1),
+// (a+1,b), (a+1,b+1) -- four (argmax, dy) loads for four stores (a thread per pixel loads 2.25 windows per store).
+__global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, bf16 *dx,
                                    int B, int IH, int IW, int C, int OH, int OW, int XH, int XW)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
     const int cv = C / 8;
     const int tx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ix = tx / cv, c8 = tx - ix * cv;
-    if (ix >= XW) return;
-    const int iy = blockIdx.y, b = blockIdx.z;
-    const size_t pix = ((size_t)b * XH + iy) * XW + ix;
-    if (ix >= IW || iy >= IH) {
-        *reinterpret_cast<uint4 *>(dx + (size_t)pix * C + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
-        return;
-    }
-    float acc[8];
+    const int bq = tx / cv, c8 = tx - bq * cv;
+    const int a = blockIdx.y, b = blockIdx.z;
+    if (2 * bq >= XW) return;
+    float acc[2][2][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    for (int kh = 0; kh < 3; kh++) {
-        int ty = iy + 1 - kh;
-        if (ty < 0 || (ty & 1)) continue;
-        int oy = ty >> 1; if (oy >= OH) continue;
-        for (int kw = 0; kw < 3; kw++) {
-            int tx = ix + 1 - kw;
-            if (tx < 0 || (tx & 1)) continue;
-            int ox = tx >> 1; if (ox >= OW) continue;
-            size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
-            uint2 a = *reinterpret_cast<const uint2 *>(argmax + o);
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[r][c][i] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 2; wy++)
+#pragma unroll
+        for (int wx = 0; wx < 2; wx++) {
+            const int oy = a + wy, ox = bq + wx;
+            if (oy >= OH || ox >= OW) continue;
+            const size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
+            const uint2 am = *reinterpret_cast<const uint2 *>(argmax + o);
             float d[8];
             unpack8(*reinterpret_cast<const uint4 *>(dy + o), d);
-            const int tap = kh * 3 + kw;
-            // byte-wise compare of the 8 argmax bytes with `tap`: (a ^ tap x 0x01010101) has a zero byte where they match
-            const uint32_t t4 = (uint32_t)tap * 0x01010101u;
-            const uint32_t m0 = a.x ^ t4, m1 = a.y ^ t4;
+            // window (oy, ox) covers input (2oy-1+kh, 2ox-1+kw): inside this block rows r >= wy, columns c >= wx, reached by
+            // kh = r + 1 - 2wy, kw = c + 1 - 2wx
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                if ((((i < 4 ? m0 : m1) >> ((i & 3) * 8)) & 0xffu) == 0u) acc[i] += d[i];
+            for (int r = wy; r < 2; r++)
+#pragma unroll
+                for (int c = wx; c < 2; c++) {
+                    const int tap = (r + 1 - 2 * wy) * 3 + (c + 1 - 2 * wx);
+                    // byte-wise compare of the 8 argmax bytes with `tap`: (a ^ tap x 0x01010101) has a zero byte where they match
+                    const uint32_t t4 = (uint32_t)tap * 0x01010101u;
+                    const uint32_t m0 = am.x ^ t4, m1 = am.y ^ t4;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        if ((((i < 4 ? m0 : m1) >> ((i & 3) * 8)) & 0xffu) == 0u) acc[r][c][i] += d[i];
+                }
         }
-    }
-    float xv[8];
-    size_t xo = (size_t)pix * C + c8 * 8;
-    unpack8(*reinterpret_cast<const uint4 *>(x + xo), xv);
 #pragma unroll
-    for (int i = 0; i < 8; i++) if (!(xv[i] > 0.f)) acc[i] = 0.f;
-    *reinterpret_cast<uint4 *>(dx + xo) = pack8(acc);
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int iy = 2 * a + r, ix = 2 * bq + c;
+            if (iy >= XH || ix >= XW) continue;
+            uint4 *dst = reinterpret_cast<uint4 *>(dx + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8);
+            *dst = (iy < IH && ix < IW) ? pack8(acc[r][c]) : make_uint4(0u, 0u, 0u, 0u);
+        }
 }
 
 __global__ void dropout_mask_kernel(uint8_t *out, int M, int N, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr)
@@ -449,13 +462,13 @@ extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *ar
     return DETRB_OK;
 }
 
-extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
+extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, detrb_bf16 *dx,
                                  int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream)
 {
-    DETRB_REQUIRE(dy && argmax && x && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
+    DETRB_REQUIRE(dy && argmax && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
     DETRB_REQUIRE(XH <= 65535 && B <= 65535, "detrb_maxpool_bwd: grid too large");
     DETRB_REQUIRE(XH >= IH && XW >= IW, "detrb_maxpool_bwd: allocated extent smaller than the image");
-    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(XW * (C / 8), 256), (unsigned)XH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (const bf16 *)x, (bf16 *)dx,
+    DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(((XW + 1) / 2) * (C / 8), 256), (unsigned)((XH + 1) / 2), (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (bf16 *)dx,
                                                                                           B, IH, IW, C, OH, OW, XH, XW);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
     return DETRB_OK;

@@ -996,6 +996,9 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
         // at most two CTAs per SM: nothing to overlap with -> fetch every k-block at once (one stage each)
         if (g_deep_small && shallow && nk > 2 && ctas <= 2 * 148)
             return bn == 128 ? launch_tc<128, 4, false>(p, stream, cls) : launch_tc<64, 4, false>(p, stream, cls);
+        // long k-loops on less than one CTA per SM (the decoder's K = 2048 linears, 28 CTAs): the loop runs at the speed of the
+        // bytes in flight per CTA -> eight stages (192 KB) instead of three
+        if (g_deep_small && nk >= 8 && ctas <= 148 && bn == 64) return launch_tc<64, 8, false>(p, stream, cls);
     }
     if (bn == 128) return shallow ? launch_tc<128, 2, IM2COL>(p, stream, cls) : launch_tc<128, 3, IM2COL>(p, stream, cls);
     return shallow ? launch_tc<64, 2, IM2COL>(p, stream, cls) : launch_tc<64, 3, IM2COL>(p, stream, cls);

@@ -597,7 +597,7 @@ class Engine:
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
-        probe = getattr(self, "probe_name", None) == s.name          # bench.py: CUDA-event timing of one launch
+        probe = s.name in (getattr(self, "probe_names", None) or ())  # bench.py: CUDA-event timing of single launches
         if probe:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -605,7 +605,7 @@ class Engine:
                   relu=relu, C=out, ldc=s.N)
         if probe:
             e1.record()
-            self.probe_events.append((e0, e1))
+            self.probe_events.setdefault(s.name, []).append((e0, e1))
 
     def _conv_dgrad(self, s, dy, ihw, ohw, out, mask=None, residual=None):
         """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]."""
@@ -987,7 +987,7 @@ class Engine:
         self.launches += 1
         self._before_write(g_in)
         HP, WP = self.hw_pad
-        ops.maxpool_bwd(g_out, a["pool_arg"], a["stem"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
+        ops.maxpool_bwd(g_out, a["pool_arg"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
                         XH=HP, XW=WP)
         stem = self.slots["backbone/conv1"]
         self.launches += 1

@@ -142,8 +142,8 @@ def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW, XH=None, XW=None):
                                        c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
 
 
-def maxpool_bwd(dy, argmax, x, dx, B, IH, IW, C, OH, OW, XH=None, XW=None):
-    check(_lib.lib().detrb_maxpool_bwd(ptr(dy), ptr(argmax), ptr(x), ptr(dx), c_int(B), c_int(IH), c_int(IW), c_int(C),
+def maxpool_bwd(dy, argmax, dx, B, IH, IW, C, OH, OW, XH=None, XW=None):
+    check(_lib.lib().detrb_maxpool_bwd(ptr(dy), ptr(argmax), ptr(dx), c_int(B), c_int(IH), c_int(IW), c_int(C),
                                        c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
 
 

@@ -192,15 +192,15 @@ int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t s
 int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const float *scale, float *out,
                  detrb_stream_t stream);
 
-/* ZeroPadding2D(1)+MaxPool2D(3,2,'valid') (resnet_backbone.py:16-17,25-26), NHWC, C%8==0.
- * fwd stores the argmax tap (0..8) per output element; bwd routes dy to it and applies the
- * stem ReLU mask (x > 0).
+/* ZeroPadding2D(1)+MaxPool2D(3,2,'valid') on the stem's ReLU output (resnet_backbone.py:16-17,25-26), NHWC, C%8==0, x >= 0.
+ * fwd stores the argmax tap (0..8) per output element, or 15 when the window maximum is not positive (no gradient passes the
+ * stem's ReLU there); bwd routes dy to the stored tap -- the ReLU mask of the stem is applied without re-reading x.
  * x (and dx) are stored [B, XH, XW, C] with XH >= IH, XW >= IW (the image in the top-left corner; XH = IH, XW = IW: dense):
  * fwd ignores the positions outside IH x IW, bwd writes them as zeros (they are the wrapped-window rows of the sliding-window
  * stem GEMM, whose weight gradient must not see them). */
 int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax,
                       int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
-int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, const detrb_bf16 *x, detrb_bf16 *dx,
+int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, detrb_bf16 *dx,
                       int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

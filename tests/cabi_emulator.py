@@ -392,15 +392,15 @@ class FakeLib:
                 upd = v > best
                 best = torch.where(upd, v, best)
                 arg = torch.where(upd, torch.full_like(arg, kh * 3 + kw), arg)
+        arg = torch.where(best > 0, arg, torch.full_like(arg, 15))      # no gradient through the stem's ReLU
         T(y, _Act.dtype, B * OH * OW * C)[:] = best.reshape(-1).to(_Act.dtype)
         T(argmax, torch.uint8, B * OH * OW * C)[:] = arg.reshape(-1)
         return 0
 
-    def detrb_maxpool_bwd(self, dy, argmax, x, dx, B, IH, IW, C, OH, OW, XH, XW, stream):
+    def detrb_maxpool_bwd(self, dy, argmax, dx, B, IH, IW, C, OH, OW, XH, XW, stream):
         B, IH, IW, C, OH, OW, XH, XW = map(_v, (B, IH, IW, C, OH, OW, XH, XW))
         d = T(dy, _Act.dtype, B * OH * OW * C).to(F32).view(B, OH, OW, C)
         arg = T(argmax, torch.uint8, B * OH * OW * C).view(B, OH, OW, C)
-        xv = T(x, _Act.dtype, B * XH * XW * C).to(F32).view(B, XH, XW, C)
         out = torch.zeros(B, XH, XW, C)
         for oy in range(OH):
             for ox in range(OW):
@@ -409,7 +409,6 @@ class FakeLib:
                         iy, ix = oy * 2 - 1 + kh, ox * 2 - 1 + kw
                         if 0 <= iy < IH and 0 <= ix < IW:
                             out[:, iy, ix] += d[:, oy, ox] * (arg[:, oy, ox] == kh * 3 + kw).to(F32)
-        out = out * (xv > 0).to(F32)
         out[:, IH:] = 0
         out[:, :, IW:] = 0
         T(dx, _Act.dtype, B * XH * XW * C)[:] = out.reshape(-1).to(_Act.dtype)

@@ -301,8 +301,8 @@ def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
     dp = rnd(B, oh, ow, 64, seed=4).to(BF)
     dx1 = torch.full((B, HP, WP, 64), 3.0, dtype=BF, device="cuda")
     dx2 = torch.zeros(B, H2, W2, 64, dtype=BF, device="cuda")
-    ops.maxpool_bwd(dp, a1, y, dx1, B, H2, W2, 64, oh, ow, XH=HP, XW=WP)
-    ops.maxpool_bwd(dp, a2, yd, dx2, B, H2, W2, 64, oh, ow)
+    ops.maxpool_bwd(dp, a1, dx1, B, H2, W2, 64, oh, ow, XH=HP, XW=WP)
+    ops.maxpool_bwd(dp, a2, dx2, B, H2, W2, 64, oh, ow)
     assert torch.equal(dx1[:, :H2, :W2], dx2)
     assert float(dx1[:, H2:].abs().max()) == 0.0 and float(dx1[:, :, W2:].abs().max()) == 0.0
     # weight gradient over the pitched gradient tensor (zeros in the wrapped rows / columns)

@@ -349,9 +349,22 @@ def test_maxpool_fwd_bwd(ops):
     ref = F.max_pool2d(F.pad(xt, (1, 1, 1, 1)), 3, 2)
     gx, = torch.autograd.grad(ref, [xt], dy.float().permute(0, 3, 1, 2))
     dx = torch.zeros(B, H, W, C, dtype=BF, device="cuda")
-    ops.maxpool_bwd(dy, arg, x2, dx, B, H, W, C, oh, ow)
+    ops.maxpool_bwd(dy, arg, dx, B, H, W, C, oh, ow)
     # bf16 ties inside a window can route the gradient to another equal element: compare sums per window-safe tolerance
     rel = float((dx.float() - gx.permute(0, 2, 3, 1)).norm() / gx.norm())
+    assert rel < 0.05, rel
+    # the stem's ReLU mask travels in the argmax (tap 15 = non-positive maximum): gradient w.r.t. the PRE-activation
+    x0 = rnd(B, H, W, C, seed=4) - 0.8                               # mostly negative: many all-zero windows after the ReLU
+    x3 = dev(F.relu(x0).to(BF))
+    ops.maxpool_fwd(x3, y, arg, B, H, W, C, oh, ow)
+    x0t = x0.to(BF).float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(F.pad(F.relu(x0t), (1, 1, 1, 1)), 3, 2)
+    assert torch.equal(y.float().cpu(), ref.permute(0, 2, 3, 1).detach().cpu())
+    gx, = torch.autograd.grad(ref, [x0t], dy.float().cpu().permute(0, 3, 1, 2))
+    ops.maxpool_bwd(dy, arg, dx, B, H, W, C, oh, ow)
+    got = dx.float().cpu()
+    assert float(got[(x3 <= 0).cpu()].abs().max()) == 0.0             # nothing flows where the stem output is zero
+    rel = float((got - gx.permute(0, 2, 3, 1)).norm() / gx.norm())
     assert rel < 0.05, rel
 
 

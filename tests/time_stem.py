@@ -46,5 +46,5 @@ for mode in (0, 2):
 ops.set_tc_persistent(1)
 t("stem sliding GEMM (auto)", lambda: ops.igemm(s2d, w16, M, 64, 256, 16, 256, g, bias=shift, relu=True, C=y, ldc=64, a_kb_rows=WP))
 t("maxpool fwd", lambda: ops.maxpool_fwd(y, p1, a1, B, H2, W2, 64, oh, ow, XH=HP, XW=WP))
-t("maxpool bwd", lambda: ops.maxpool_bwd(p1, a1, y, dy, B, H2, W2, 64, oh, ow, XH=HP, XW=WP))
+t("maxpool bwd", lambda: ops.maxpool_bwd(p1, a1, dy, B, H2, W2, 64, oh, ow, XH=HP, XW=WP))
 t("stem wgrad", lambda: ops.wgrad(s2d, 16, dy, 64, M, 64, 256, g, dW, 256, dbias=db, a_kb_rows=WP, k_mask=True))
