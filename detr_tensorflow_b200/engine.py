@@ -14,9 +14,8 @@ detr_tf/loss/{loss,hungarian_matching}.py, detr_tf/optimizers.py, detr_tf/traini
 from __future__ import annotations
 
 import math
-from collections import OrderedDict
-
 import os
+from collections import OrderedDict
 
 import torch
 
@@ -839,10 +838,23 @@ class Engine:
     def zero_grads(self):
         self.grads.zero_()
 
-    def backward(self, train_backbone=True):
+    def grad_buckets(self):
+        """[lo, hi) ranges of the flat gradient arena in the order the backward pass completes them: transformer + heads
+        (+ fine-tuning layers), then layer3-4 + input_proj, then stem + layer1-2.  Data parallel: bucket k's all-reduce runs
+        while the backward pass of bucket k+1 is still computing."""
+        t0 = self.group_range["transformers"][0]
+        l3 = min(o for (name, o, _, _, _) in self.vars if name.startswith("backbone/layer3/"))
+        return [(t0, self.total), (l3, t0), (0, l3)]
+
+    def backward(self, train_backbone=True, boundary=None):
         """Gradients of total_loss wrt every trainable variable, accumulated (+=) into self.grads.
         train_backbone=False stops after the transformer (results identical for the trained groups; the reference
-        computes the dead work anyway, optimizers.py:112-115 / SURVEY appendix A.7)."""
+        computes the dead work anyway, optimizers.py:112-115 / SURVEY appendix A.7).
+        boundary(k) is called when gradient bucket k (grad_buckets()) is complete, side-stream weight gradients included."""
+        def reached(k):
+            if boundary is not None:
+                self._join_wgrad()
+                boundary(k)
         a, B = self.a, self.B
         d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
         scale = float(d // Hh) ** -0.5
@@ -947,12 +959,15 @@ class Engine:
             g_y = a["gm_n0"] if (l & 1) else a["gm_n1"]
             self._lin(a["gm_v"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=g_y, residual=a["gm_c"], ldr=d)
         self._mark("bwd_encoder")
+        reached(0)
         # ---------------- input_proj
         ip = self.slots["input_proj"]
         self._lin_wgrad(ip, self.feat, g_y, M)
         if not train_backbone:
             self._in_backward = False
             self._join_wgrad()
+            reached(1)
+            reached(2)
             return
         nb = len(self.blocks)
         last = self.blocks[-1]
@@ -983,6 +998,8 @@ class Engine:
                 ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask=xmask, ldm=cd.Cin, mask_scale=1.0,
                           C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True)
             g_out, g_in = g_in, g_out
+            if blk["prefix"] == "backbone/layer3/0":
+                reached(1)
         # g_out now holds d pool
         self.launches += 1
         self._before_write(g_in)
@@ -996,6 +1013,7 @@ class Engine:
                                            rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True), (x, g_in))
         self._in_backward = False
         self._join_wgrad()
+        reached(2)
         self._mark("bwd_backbone")
 
     # ------------------------------------------------------------------------------------------ optimizer
@@ -1029,6 +1047,14 @@ class Engine:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
 
+    def allreduce_bucket(self, k):
+        """data parallel: asynchronous sum all-reduce of gradient bucket k (grad_buckets()); ordered after the work enqueued on
+        the current stream, runs on the process group's own stream beside the rest of the backward pass.  Returns the Work
+        handle -- wait() on it before the optimizer reads the gradients."""
+        import torch.distributed as dist
+        lo, hi = self.grad_buckets()[k]
+        return dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+
     def set_global_normalisers(self, t_bbox):
         """Under data parallelism the reference's batch-level normalisers (loss.py:66-67,82,94) must be those of the
         GLOBAL batch: N = sum n_i over all ranks, sum_w = 0.1*(B_glob*Q - N) + N.  They depend on the labels only, so
@@ -1061,8 +1087,13 @@ class Engine:
         self._forward_impl()
         self.loss(background_class, loss_scale=loss_scale, with_grad=True)
         self.zero_grads()
-        self.backward(train_backbone=train_backbone)
-        self.allreduce_grads()
+        if self._distributed():
+            works = []
+            self.backward(train_backbone=train_backbone, boundary=lambda k: works.append(self.allreduce_bucket(k)))
+            for w in works:
+                w.wait()
+        else:
+            self.backward(train_backbone=train_backbone)
         self._mark("allreduce")
         self.optimizer_step(clipnorm)
         self._mark("adam_refresh")
@@ -1073,8 +1104,9 @@ class Engine:
 
     def capture_train_step(self, background_class, clipnorm, loss_scale=1.0, train_backbone=True, warmup=2):
         """Capture train_step into CUDA graphs (static shapes: fixed-size images).  Returns a callable replaying it.
-        Single rank: one graph for the whole step.  Data parallel: the gradient all-reduce stays an eager NCCL call between
-        two graphs (forward+loss+backward | optimizer) -- NCCL's watchdog threads and graph capture do not mix safely."""
+        Single rank: one graph for the whole step.  Data parallel: the step is cut at the gradient-bucket boundaries
+        (grad_buckets()) into four graphs; the all-reduces stay eager NCCL calls between them (NCCL's watchdog threads and
+        graph capture do not mix safely), asynchronous, so bucket k is reduced over NVLink while graph k+1 computes."""
         def part1():
             self.training = True
             self.seed_dev.add_(1)
@@ -1104,18 +1136,53 @@ class Engine:
             self.launches_per_step = self.launches - n0
             self._graph = graph
             return graph.replay
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1, capture_error_mode="thread_local"):
-            part1()
-        with torch.cuda.graph(g2, capture_error_mode="thread_local"):
-            part2()
+        # data parallel: the backward pass is cut at the gradient-bucket boundaries into consecutive graphs; bucket k's eager
+        # all-reduce is enqueued between graph k and graph k+1 and runs (on NCCL's stream) while graph k+1 computes
+        import gc
+        graphs = []
+        pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream()
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool, capture_error_mode="thread_local")
+            graphs.append(g)
+
+        def cut(k):
+            graphs[-1].capture_end()
+            begin()
+        torch.cuda.synchronize()
+        gc.collect()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            begin()
+            self.training = True
+            self.seed_dev.add_(1)
+            self._forward_impl()
+            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
+            self.zero_grads()
+            self.backward(train_backbone=train_backbone, boundary=cut)      # graphs 0..2 end at the bucket boundaries
+            part2()                                                           # graph 3: optimizer
+            graphs[-1].capture_end()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
         self.launches_per_step = self.launches - n0
-        self._graph = (g1, g2)
+        self._graph = tuple(graphs)
+        assert len(graphs) == 4, len(graphs)
+
+        overlap = os.environ.get("DETRB_DP_OVERLAP", "1") != "0"      # 0: one flat all-reduce after the backward pass (A/B runs)
 
         def replay():
-            g1.replay()
-            self.allreduce_grads()
-            g2.replay()
+            works = []
+            for k in range(3):
+                graphs[k].replay()
+                if overlap:
+                    works.append(self.allreduce_bucket(k))
+            if not overlap:
+                self.allreduce_grads()
+            for w in works:
+                w.wait()
+            graphs[3].replay()
         return replay
 
     # ------------------------------------------------------------------------------------------ graph-replayed gradient step

@@ -20,7 +20,7 @@ cfg = D.TrainingConfig()
 cfg.background_class = 91
 
 
-def run(images, tbb, tcc, distributed):
+def run(images, tbb, tcc, distributed, bucketed=False):
     model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P)
     eng = model.engine
     eng.forward(images, training=False)
@@ -29,8 +29,17 @@ def run(images, tbb, tcc, distributed):
         eng.set_global_normalisers(tbb)
     eng.zero_grads()
     eng.loss(91)
-    eng.backward()
-    eng.allreduce_grads()
+    if bucketed:                                  # the product's N>1 train step: bucket k reduced while bucket k+1 is computed
+        works, order = [], []
+        eng.backward(boundary=lambda k: (order.append(k), works.append(eng.allreduce_bucket(k))))
+        for w in works:
+            w.wait()
+        assert order == [0, 1, 2], order
+        b = eng.grad_buckets()
+        assert sorted(b, key=lambda r: r[0])[0][0] == 0 and sum(hi - lo for lo, hi in b) == eng.total      # a partition of the arena
+    else:
+        eng.backward()
+        eng.allreduce_grads()
     total, _ = eng.loss_dict()
     return float(total), eng.export_grads()
 
@@ -42,6 +51,7 @@ dist.init_process_group("gloo", rank=rank, world_size=world)
 total, grads = run(img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], True)
 t = torch.tensor([total])
 dist.all_reduce(t)
+_, grads_b = run(img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], True, bucketed=True)
 if rank == 0:
-    torch.save({"total_global": float(t), "grads": grads}, f"{outdir}/dp_rank0.pt")
+    torch.save({"total_global": float(t), "grads": grads, "grads_bucketed": grads_b}, f"{outdir}/dp_rank0.pt")
 dist.destroy_process_group()

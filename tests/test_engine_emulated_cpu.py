@@ -197,6 +197,8 @@ def test_data_parallel_two_ranks_gloo(tmp_path):
         a, b = dp["grads"][k], single["grads"][k]
         if float(b.norm()) > 1e-6:
             assert rel(a, b) < 2e-3, (k, rel(a, b))
+        # three overlapped bucket all-reduces (Engine.grad_buckets) == the one flat all-reduce, bit for bit
+        assert torch.equal(dp["grads_bucketed"][k], a), k
 
 
 def test_finetune_heads_nlayers_group(emu):
