@@ -40,16 +40,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
     return d;
 }
-// 32-byte-swizzled K-major operand (rows of 16 bf16): 8-row atoms of 256 B; one UMMA (K = 16) consumes the whole row
-__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                                  // SWIZZLE_32B
-    return d;
-}
 // instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
 // N>>3 at bits [17,23), M>>4 at bits [24,29)   (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -66,7 +56,7 @@ __device__ __forceinline__ void add_bias8(float (&v)[8], uint32_t saddr) {
 
 // convolution side-band for the IM2COL kernels: effective padding and, per im2col tap, the weight tap to pair it with
 // (identity: forward; reversed: stride-1 data gradient; sparse: one parity class of a stride-2 data gradient)
-struct ConvAux { int pad; int c16; int wtap[16]; };   // c16: 16-channel pixels (space-to-depth stem): 4 taps per 64-wide k-block
+struct ConvAux { int pad; int wtap[16]; };
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -156,15 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
                 const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
-                if (IM2COL && aux.c16) {
-                    // 16-channel pixels: this 64-wide k-block is 4 filter taps, each a [128 x 32 B] box (32B swizzle)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int tap = kb * 4 + j, kh = tap / p.KW, kw = tap - kh * p.KW;
-                        tma_load_im2col(a_dst + j * (TBM * 32), &map_a, full_bar(stage), 0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
-                        tma_load_2d(a_dst + L::A_BYTES + j * (BN * 32), &map_b, full_bar(stage), aux.wtap[tap & 15] * 16, n0);
-                    }
-                } else if (IM2COL) {
+                if (IM2COL) {
                     const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
                     tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
@@ -194,17 +176,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
-                if (IM2COL && aux.c16) {
+                const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 4; j++)             // one UMMA per filter tap (16 channels = K 16)
-                        tc_mma_f16(tmem_base, make_smem_desc_sw32(a_addr + j * (TBM * 32)),
-                                   make_smem_desc_sw32(a_addr + L::A_BYTES + j * (BN * 32)), idesc, (kb | j) != 0);
-                } else {
-                    const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + L::A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TBK / 16; k++)      // advance 32 B (16 bf16) inside the 128 B swizzle row
-                        tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                }
+                for (int k = 0; k < TBK / 16; k++)          // advance 32 B (16 bf16) inside the 128 B swizzle row
+                    tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                 tc_commit(empty_bar(stage));                // frees this smem stage when the MMAs have read it
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -753,8 +728,7 @@ EncodeTiledFn get_encode_fn()
 }
 
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill
-bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = TBK,
-              bool sw32 = false)
+bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = TBK)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
@@ -763,7 +737,7 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -782,7 +756,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
 {
     CUtensorMap ma, mb;
     ConvAux aux;
-    aux.pad = 0; aux.c16 = 0;
+    aux.pad = 0;
     for (int i = 0; i < 16; i++) aux.wtap[i] = i;
     uint64_t w_cols = (uint64_t)p.K;                        // columns of the weight matrix the W tensor map spans
     if (IM2COL) {
@@ -803,12 +777,10 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
             upper_w = (p.OW - 1) * st + 1 + lower_w - p.IW;
             upper_h = (p.OH - 1) * st + 1 + lower_h - p.IH;
         }
-        aux.c16 = (p.Cin == 16);
         if (upper_w > 0 || upper_h > 0 || upper_w < -16 || upper_h < -16)
             DETRB_FAIL(DETRB_E_SHAPE, "gemm_tc im2col: inconsistent conv geometry IH=%d IW=%d OH=%d OW=%d k=%dx%d s=%d p=%d", p.IH, p.IW,
                        p.OH, p.OW, p.KH, p.KW, st, aux.pad);
-        int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM,
-                                       aux.c16 ? 2 : 1, aux.c16 ? 16 : 64);
+        int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM, 1, 64);
         if (rc) return rc;
     } else if (p.a_kb_rows > 0) {
         // sliding-window operand: every row is one 64-element run, consecutive rows start lda elements apart (they overlap when
@@ -819,7 +791,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
     } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM)) {
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     }
-    if (!make_map(&mb, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN, aux.c16 ? 16 : TBK, aux.c16 != 0))
+    if (!make_map(&mb, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN))
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(W) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
     // coalesced TMA epilogue whenever the output is a plain bf16 tile (no fp32 copy, scatter or read-modify-write)
     CUtensorMap mc = ma, mr = ma, mm = ma;
@@ -841,7 +813,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             pconfigured = true;
         }
-        if (!tma_epi || aux.c16) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc needs the TMA epilogue (plain bf16 output)");
+        if (!tma_epi) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc needs the TMA epilogue (plain bf16 output)");
         const int slot = 16384 * ((p.residual ? 1 : 0) + (p.mask ? 1 : 0));
         // even ring depth: chunk g lives in slot g % rs and is consumed by warpgroup g % 2, so each warpgroup owns its slots and
         // never observes a slot barrier more than one phase behind (mbarrier parity waits cannot tell phases two apart)
@@ -880,9 +852,9 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
 }  // namespace
 
 bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                          uint32_t box_cols, bool sw32)
+                          uint32_t box_cols)
 {
-    return make_map(map, base, rows, cols, ld, box_rows, box_cols, sw32);
+    return make_map(map, base, rows, cols, ld, box_rows, box_cols);
 }
 
 static bool aligned_epilogue(const detrb_igemm_t &p)
@@ -902,8 +874,7 @@ int detrb_gemm_tc_kind(const detrb_igemm_t &p)
     if (p.K % TBK != 0 || p.lda % 8 != 0 || ((uintptr_t)p.A & 15) || !aligned_epilogue(p)) return 0;
     const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && p.Cin == p.K;   // mode 0 and 1 coincide
     if (plain) return get_encode_fn() != nullptr ? 1 : 0;
-    const bool c16 = p.Cin == 16 && p.mode == 0 && (p.KH * p.KW) % 4 == 0 && p.KH * p.KW <= 16 && p.lda == 16;
-    if ((p.Cin % TBK != 0 && !c16) || p.K != p.KH * p.KW * p.Cin) return 0;
+    if (p.Cin % TBK != 0 || p.K != p.KH * p.KW * p.Cin) return 0;
     if (p.mode == 1 && p.stride != 1) {                     // 3x3 / stride 2 / pad 1: four parity-class sub-convolutions
         if (p.stride == 2 && p.KH == 3 && p.KW == 3 && p.pad == 1 && p.out_stride <= 1 && !p.accumulate && !p.Cf &&
             get_encode_fn() != nullptr && detrb_get_im2col_encode() != nullptr) return 3;
@@ -947,7 +918,7 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
         if (const char *e = getenv("DETRB_ONE_STAGE")) g_one_stage = atoi(e);
     }
     const bool tma_epi = p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue;
-    if (!g_tc_persistent || !tma_epi || p.Cin == 16) return DETRB_OK;
+    if (!g_tc_persistent || !tma_epi) return DETRB_OK;
     const int nk = p.K / TBK;
     const bool both = p.residual && p.mask;
     const long mt = ceil_div(p.M, TBM);
@@ -1025,7 +996,7 @@ static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
             if (q.mask) q.mask = q.mask + off * q.ldm;
             if (q.residual) q.residual = q.residual + off * q.ldr;
             ConvClass cls;
-            cls.aux.pad = 0; cls.aux.c16 = 0;
+            cls.aux.pad = 0;
             for (int i = 0; i < 16; i++) cls.aux.wtap[i] = 0;
             for (int ty = 0; ty < ny; ty++)
                 for (int tx = 0; tx < nx; tx++) cls.aux.wtap[ty * nx + tx] = kmap[py][ty] * 3 + kmap[px][tx];

@@ -140,14 +140,16 @@ chunk_adam_kernel(float *params, const float *grads, float *m, float *v, const i
     }
 }
 
-// multi-tensor weight refresh: one launch for all layers.  Work item = 32x32 (n, c) tile of one filter tap of one weight;
-// the tile is read coalesced along c, written coalesced to Wf (along c) and, through a shared-memory transpose, to Wd (along n).
+// multi-tensor weight refresh: one launch for all layers.  Work item = 64x64 (n, c) tile of one filter tap of one weight;
+// the tile is read coalesced along c (256-byte rows), written to Wf along c and, through a shared-memory transpose, to Wd
+// along n -- both as packed bf16 pairs in full 128-byte rows.  Cin and the row strides are even (checked on the host).
+constexpr int PT = 64;
 __global__ void __launch_bounds__(256)
 prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
-    __shared__ float tile[32][33];
+    __shared__ float tile[PT][PT + 1];
     const int t = blockIdx.x;
     int lo = 0, hi = nslots - 1;                       // last slot whose tile_begin <= t
     while (lo < hi) {
@@ -156,26 +158,30 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
     }
     const detrb_prep_desc_t d = descs[lo];
     const int local = t - d.tile_begin;
-    const int ct = (d.Cin + 31) / 32, nt = (d.N + 31) / 32;
+    const int ct = (d.Cin + PT - 1) / PT, nt = (d.N + PT - 1) / PT;
     const int ci = local % ct, ni = (local / ct) % nt, tap = local / (ct * nt);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = ci * 32 + tx;
-    for (int r = ty; r < 32; r += 8) {
-        const int n = ni * 32 + r;
-        float w = 0.f;
+    const int c = ci * PT + 2 * tx;                    // this thread's column pair
+    for (int r = ty; r < PT; r += 8) {
+        const int n = ni * PT + r;
+        float2 w = make_float2(0.f, 0.f);
         if (n < d.N && c < d.Cin) {
-            w = d.master[((size_t)n * d.taps + tap) * d.Cin + c] * (d.fold ? d.fold[n] : 1.f);
-            if (d.Wf) reinterpret_cast<bf16 *>(d.Wf)[(size_t)n * d.ldf + tap * d.Cin + c] = __float2bfloat16(w);
+            w = *reinterpret_cast<const float2 *>(d.master + ((size_t)n * d.taps + tap) * d.Cin + c);
+            const float f = d.fold ? d.fold[n] : 1.f;
+            w.x *= f; w.y *= f;
+            if (d.Wf) *reinterpret_cast<uint32_t *>(reinterpret_cast<bf16 *>(d.Wf) + (size_t)n * d.ldf + tap * d.Cin + c) = pack_bf16x2(w.x, w.y);
         }
-        tile[r][tx] = w;
+        tile[r][2 * tx] = w.x; tile[r][2 * tx + 1] = w.y;
     }
     if (!d.Wd) return;
     __syncthreads();
-    const int n = ni * 32 + tx;
-    for (int r = ty; r < 32; r += 8) {
-        const int cc = ci * 32 + r;
-        if (cc < d.Cin && n < d.N)
-            reinterpret_cast<bf16 *>(d.Wd)[((size_t)cc * d.taps + tap) * d.ldd + n] = __float2bfloat16(tile[tx][r]);
+    const int n = ni * PT + 2 * tx;                    // this thread's output-channel pair
+    for (int r = ty; r < PT; r += 8) {
+        const int cc = ci * PT + r;
+        if (cc >= d.Cin || n >= d.N) continue;
+        bf16 *dst = reinterpret_cast<bf16 *>(d.Wd) + ((size_t)cc * d.taps + tap) * d.ldd + n;
+        if (n + 1 < d.N) *reinterpret_cast<uint32_t *>(dst) = pack_bf16x2(tile[2 * tx][r], tile[2 * tx + 1][r]);
+        else *dst = __float2bfloat16(tile[2 * tx][r]);
     }
 }
 
@@ -184,6 +190,8 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
 extern "C" int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream)
 {
     DETRB_REQUIRE(descs && nslots > 0 && total_tiles > 0, "detrb_prep_weights_multi: bad args");
+    // descs live in device memory (the table is built once by the caller): tile_begin counts 64x64 tiles, taps * ceil(N/64) *
+    // ceil(Cin/64) per slot; Cin, ldf, ldd even and master / Wf / Wd 8 / 4 / 4-byte aligned
     DETRB_LAUNCH(prep_weights_multi_kernel, dim3(total_tiles), dim3(256), 0, (cudaStream_t)stream, descs, nslots);
     DETRB_CHECK_LAUNCH("prep_weights_multi_kernel");
     return DETRB_OK;

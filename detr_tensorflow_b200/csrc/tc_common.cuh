@@ -66,4 +66,4 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // 2-D bf16 tensor map helper (gemm_tc.cu): [rows, cols] row stride ld, box [box_rows, box_cols], 128-byte swizzle
 bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                          uint32_t box_cols, bool sw32 = false);
+                          uint32_t box_cols);

@@ -183,7 +183,6 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     if (detrb_wgrad_tc_enabled() && detrb_wgrad_tc_supported(p) && detrb_wgrad_tc_profitable(p)) {           // tcgen05 / TMA im2col / TMEM
         return detrb_wgrad_tc(p, stream);                      // bias gradient fused (k-tile 0 CTAs)
     }
-    DETRB_REQUIRE(p.Cin != 16, "detrb_wgrad: 16-channel (space-to-depth stem) gradients need the tcgen05 kernel (detrb_set_tc_wgrad(1))");
     const bool stem = (p.Cin == 4);
     if (stem) DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4, "detrb_wgrad: stem geometry");
     else DETRB_REQUIRE(p.Cin % 8 == 0 && p.K == p.KH * p.KW * p.Cin && p.lda % 8 == 0, "detrb_wgrad: Cin=%d K=%d lda=%d", p.Cin, p.K, p.lda);

@@ -6,7 +6,10 @@
 // convolution (one box per 64-channel slice of one filter tap), so 1x1, 3x3, strided convolutions and Linear layers share the
 // kernel.  D = 128 (out channels) x 128 (k = tap*Cin + c) fp32 in TMEM; CTAs split the pixel range and merge with fp32 atomics.
 //
-// Replaces wgrad.cu (mma.sync) for every layer whose Cin is a multiple of 64 (everything but the 7x7 stem).
+// Replaces wgrad.cu (mma.sync) for every layer whose Cin is a multiple of 64.  The 7x7 stem arrives as a plain problem too: its
+// space-to-depth image is a sliding-window operand (detrb_wgrad_t.a_kb_rows: 64-column block j of pixel m is the 64-element
+// run j * a_kb_rows pixels further down, rows overlap), K = 4 window rows x 4 taps x 16 channels = 256, and k_mask drops the
+// columns that do not exist in the 7x7x3 kernel.
 #include "tc_common.cuh"
 
 namespace {
@@ -31,31 +34,17 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
     return d;
 }
-// MN-major operand made of [64 pixels x 32 B] boxes with 32-byte swizzle (16-channel pixels): 16-element MN blocks one box
-// (2048 B) apart (LBO), 8-pixel K atoms 256 B apart (SBO)
-__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(2048 >> 4) << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                                  // SWIZZLE_32B
-    return d;
-}
 // kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t WIDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
 constexpr uint32_t WIDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WK >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
 
-// C16: 16-channel pixels (space-to-depth stem, 4x4 taps): the whole K = 16 taps x 16 ch = 256 is one tile; every tap is a
-// [64 pixels x 32 B] box (32B swizzle), the UMMA N dimension is 256 and walks the 16 boxes through the leading byte offset.
-template <bool IM2COL, bool C16>
+template <bool IM2COL>
 __global__ void __launch_bounds__(WTHREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, const detrb_wgrad_t p,
                 const int pix_per_split, const int stem_mask)
 {
-    constexpr int KT = C16 ? 256 : WK;                                  // k columns of this CTA's dW tile (TMEM columns)
-    constexpr int STG = C16 ? 2 : WSTAGES;
-    constexpr int STG_BYTES = C16 ? (2 * BOX_BYTES + 16 * 2048) : WSTAGE_BYTES;
+    constexpr int KT = WK;                                              // k columns of this CTA's dW tile (TMEM columns)
+    constexpr int STG = WSTAGES;
+    constexpr int STG_BYTES = WSTAGE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STG * STG_BYTES;
@@ -109,15 +98,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 const uint32_t dst = smem_base + stage * STG_BYTES;
                 tma_load_2d(dst, &map_y, full_bar(stage), n0, m);                         // dY[m.., n0 .. n0+64)
                 tma_load_2d(dst + BOX_BYTES, &map_y, full_bar(stage), n0 + 64, m);
-                if (C16) {
-                    const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
-                    const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
-#pragma unroll 1
-                    for (int tp = 0; tp < 16; tp++) {
-                        const int kh = tp / p.KW, kw = tp - kh * p.KW;
-                        tma_load_im2col(dst + 2 * BOX_BYTES + tp * 2048, &map_x, full_bar(stage), 0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
-                    }
-                } else if (IM2COL) {
+                if (IM2COL) {
                     const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                     const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
 #pragma unroll
@@ -143,18 +124,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 tc_fence_after();
                 const uint32_t base = smem_base + stage * STG_BYTES;
                 const uint64_t da = make_desc_mn(base);
-                if (C16) {
-                    // B: 16 taps x 16 ch, MN-major with 32B swizzle: 8-pixel atoms 256 B apart (SBO), next tap 2048 B further (LBO)
-                    const uint64_t db = make_desc_mn32(base + 2 * BOX_BYTES);
+                const uint64_t db = make_desc_mn(base + 2 * BOX_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < WP / 16; ks++)  // 16 pixels: 2048 B down the dY box, 512 B down each tap box
-                        tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (512 >> 4)), WIDESC16, (st | ks) != 0);
-                } else {
-                    const uint64_t db = make_desc_mn(base + 2 * BOX_BYTES);
-#pragma unroll
-                    for (int ks = 0; ks < WP / 16; ks++)  // 16 pixels = 2 swizzle atoms = 2048 B further down the box
-                        tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
-                }
+                for (int ks = 0; ks < WP / 16; ks++)      // 16 pixels = 2 swizzle atoms = 2048 B further down the box
+                    tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
                 tc_commit(empty_bar(stage));
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
@@ -242,8 +215,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
 
 bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 {
-    const bool c16 = p.Cin == 16 && p.KH * p.KW == 16 && p.lda == 16;
-    if ((p.Cin % 64 != 0 && !c16) || p.K != p.KH * p.KW * p.Cin) return false;
+    if (p.Cin % 64 != 0 || p.K != p.KH * p.KW * p.Cin) return false;
     if (p.lda % 8 != 0 || p.ldy % 8 != 0 || ((uintptr_t)p.A & 15) || ((uintptr_t)p.dY & 15)) return false;
     if (p.KH > 16 || p.KW > 16 || p.stride > 8) return false;
     return detrb_get_im2col_encode() != nullptr;
@@ -253,7 +225,6 @@ bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 {
     // large pixel counts (backbone) and the encoder-sized linears (M = 8400); the decoder's (M = 800) stay on the mma.sync split kernel
-    if (p.Cin == 16) return true;        // space-to-depth stem: only this kernel masks the taps that do not exist in the 7x7 kernel
     static long min_m = -1, min_nk = -1;                 // env overrides for tuning runs
     if (min_m < 0) {
         const char *e1 = getenv("DETRB_WGRAD_TC_MIN_M"), *e2 = getenv("DETRB_WGRAD_TC_MIN_NK");
@@ -265,8 +236,7 @@ bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {
-    const bool c16 = p.Cin == 16;
-    const bool plain = !c16 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
+    const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
     CUtensorMap my, mx;
     if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64))
         DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for dY failed (M=%d N=%d ldy=%d)", p.M, p.N, p.ldy);
@@ -282,11 +252,10 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         const int upper_w = (p.OW - 1) * p.stride + 1 + lower - p.IW, upper_h = (p.OH - 1) * p.stride + 1 + lower - p.IH;
         if (upper_w > 0 || upper_h > 0 || upper_w < -16 || upper_h < -16)
             DETRB_FAIL(DETRB_E_SHAPE, "wgrad_tc: inconsistent conv geometry");
-        int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP,
-                                       c16 ? 2 : 1, c16 ? 16 : 64);
+        int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP, 1, 64);
         if (rc) return rc;
     }
-    const int kt = c16 ? 256 : WK;
+    const int kt = WK;
     const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
     int splits = ceil_div(148 * 2, tiles);               // one wave of 2 CTAs per SM: fewer fp32 atomics per gradient element
     const int max_splits = ceil_div(p.M, WP * 4);
@@ -294,22 +263,18 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     if (splits < 1) splits = 1;
     int pix_per_split = ceil_div(ceil_div(p.M, splits), WP) * WP;
     splits = ceil_div(p.M, pix_per_split);
-    constexpr int SMEM16 = 2 * (2 * BOX_BYTES + 16 * 2048) + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM16));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
         configured = true;
     }
     dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
-    const int stem_mask = ((c16 && p.KH == 4 && p.KW == 4 && p.pad == 2) || p.k_mask) ? 1 : 0;
-    if (c16) {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), SMEM16, stream, my, mx, p, pix_per_split, stem_mask);
-    } else if (plain) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, stem_mask);
+    const int stem_mask = p.k_mask ? 1 : 0;
+    if (plain) {
+        DETRB_LAUNCH((wgrad_tc_kernel<false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, stem_mask);
     } else {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
+        DETRB_LAUNCH((wgrad_tc_kernel<true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
     }
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;

@@ -348,7 +348,8 @@ class Engine:
                 d.master, d.fold = s.master.data_ptr(), (s.fold.data_ptr() if s.fold is not None else None)
                 d.Wf, d.Wd = s.Wf.data_ptr(), (s.Wd.data_ptr() if s.Wd is not None else None)
                 d.N, d.taps, d.Cin, d.ldf, d.ldd, d.tile_begin = s.N, s.taps, s.Cin, s.K, s.ldd, begin
-                begin += s.taps * ((s.N + 31) // 32) * ((s.Cin + 31) // 32)
+                assert s.Cin % 2 == 0 and s.K % 2 == 0 and (s.Wd is None or s.ldd % 2 == 0)
+                begin += s.taps * ((s.N + 63) // 64) * ((s.Cin + 63) // 64)          # 64x64 tiles (optim.cu)
             raw = np.frombuffer(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr)), dtype=np.uint8).copy()
             self._prep_table = torch.from_numpy(raw).to(self.device)
             self._prep_n, self._prep_tiles = n, begin

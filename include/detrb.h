@@ -264,7 +264,8 @@ int detrb_prep_weight(const float *master, const float *fold, int N, int taps, i
                       detrb_bf16 *Wf, int ldf, detrb_bf16 *Wd, int ldd, detrb_stream_t stream);
 
 /* The same refresh for ALL weights in one launch.  descs: DEVICE array of nslots descriptors (device pointers inside);
- * tile_begin = exclusive prefix sum of taps * ceil(N/32) * ceil(Cin/32) over the slots; total_tiles = the full sum. */
+ * tile_begin = exclusive prefix sum of taps * ceil(N/64) * ceil(Cin/64) over the slots; total_tiles = the full sum.
+ * Cin, ldf, ldd even (packed bf16 pairs). */
 typedef struct {
     const float *master; const float *fold;
     detrb_bf16 *Wf; detrb_bf16 *Wd;

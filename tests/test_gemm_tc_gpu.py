@@ -222,42 +222,6 @@ def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
     check("wgrad tc vs mma.sync", dW_b, dW_a, 1e-2, tol)
 
 
-# ------------------------------------------------------------------------------------------------ space-to-depth stem (16-channel pixels)
-@pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224)])
-def test_stem_space_to_depth_conv_and_wgrad(ops, H, W):
-    """7x7 / stride 2 / pad 3 conv on 3 channels == 4x4 / stride 1 conv (2 rows above, 1 below) on the space-to-depth(2)
-    image with 16-channel pixels: tcgen05 kernel with 32-byte-swizzled [128 x 16ch] im2col boxes, one UMMA per tap."""
-    from detr_tensorflow_b200.engine import Engine
-    B = 2
-    H2, W2 = (H + 1) // 2, (W + 1) // 2
-    oh, ow = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-    assert (oh, ow) == (H2, W2)
-    img = rnd(B, H, W, 3, seed=1)
-    s2d = torch.zeros(B, H2, W2, 16, dtype=BF, device="cuda")
-    ops.image_to_s2d16(img, s2d, B, H, W)
-    w7 = rnd(64, 7, 7, 3, scale=147 ** -0.5, seed=2).to(BF)
-    w16 = Engine._stem_to_s2d(None, w7.float().cpu()).to(BF).cuda().reshape(64, 256).contiguous()
-    shift = rnd(64, seed=3)
-    M = B * oh * ow
-    g = conv_geom(B, H2, W2, 16, oh, ow, 4, 4, 1, 2)
-    y = torch.zeros(M, 64, dtype=BF, device="cuda")
-    ops.igemm(s2d, w16, M, 64, 256, 16, 256, g, bias=shift, relu=True, C=y, ldc=64, force_tc=0)
-    torch.cuda.synchronize()
-    xt = img.to(BF).float().permute(0, 3, 1, 2)
-    wt = w7.float().permute(0, 3, 1, 2).requires_grad_(True)
-    ref = F.conv2d(xt, wt, bias=shift, stride=2, padding=3)
-    check("s2d stem fwd", y.view(B, oh, ow, 64), F.relu(ref).permute(0, 2, 3, 1), 1e-2, 2e-2)
-    # weight gradient
-    dy = rnd(M, 64, seed=5).to(BF)
-    scale = rnd(64, seed=6).abs() + 0.5
-    dW = torch.zeros(64, 256, dtype=F32, device="cuda")
-    ops.wgrad(s2d, 16, dy, 64, M, 64, 256, g, dW, 256, rowscale=scale, force_tc=True)
-    torch.cuda.synchronize()
-    gw, = torch.autograd.grad(ref, [wt], dy.float().view(B, oh, ow, 64).permute(0, 3, 1, 2))
-    ref16 = Engine._stem_to_s2d(None, (gw.permute(0, 2, 3, 1) * scale[:, None, None, None]).cpu()).reshape(64, 256).cuda()
-    check("s2d stem wgrad", dW, ref16, 1e-2, 1e-2 * float(ref16.abs().max()))
-
-
 # ------------------------------------------------------------------------------------------------ stem as a sliding-window GEMM
 @pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224)])
 def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
