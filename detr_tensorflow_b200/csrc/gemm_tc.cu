@@ -918,7 +918,9 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
         if (const char *e = getenv("DETRB_ONE_STAGE")) g_one_stage = atoi(e);
     }
     const bool tma_epi = p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue;
-    if (!g_tc_persistent || !tma_epi) return DETRB_OK;
+    // (sliding-window stem: one-tile kernel measured faster, 198 vs 211 us.  Evict-first L2 hints on the read-once residual / mask /
+    //  A streams were measured too: no gain, 14.26 vs 14.25 ms/step -- not kept)
+    if (!g_tc_persistent || !tma_epi || p.a_kb_rows) return DETRB_OK;
     const int nk = p.K / TBK;
     const bool both = p.residual && p.mask;
     const long mt = ceil_div(p.M, TBM);
