@@ -409,6 +409,9 @@ def main():
         roof_hbm = {"bound": "hbm", "kernel": "gemm_tc_kernel<64,1> (one-tile tcgen05 GEMM, 1x1 conv 64->256 + residual + ReLU, layer1, M=534400 N=256 K=64)",
                     "achieved": byts / t_h / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": byts / t_h / 1e9 / peak_hbm, "traffic": None,
                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})", "bytes_per_launch": byts, "us_per_launch": t_h * 1e6}
+        prof = os.path.join(ROOT, "profiles", "hbm_kernel_traffic.json")
+        if os.path.exists(prof):
+            roof_hbm["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only, bounded sample)
     cpu = None

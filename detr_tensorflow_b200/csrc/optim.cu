@@ -219,13 +219,15 @@ extern "C" int detrb_adam_clipnorm(float *params, const float *grads, float *m, 
 extern "C" int detrb_adam_clipnorm_chunked(float *params, const float *grads, float *m, float *v, const int32_t *chunks, int nchunks,
                                            const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,
                                            float clipnorm, float beta1, float beta2, float eps, int32_t *steps, float *norms,
-                                           detrb_stream_t stream_)
+                                           int prologue, detrb_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     DETRB_REQUIRE(params && grads && m && v && chunks && lr_group && lrs && group_enabled && steps && norms, "detrb_adam_clipnorm_chunked: null pointer");
     DETRB_REQUIRE(T > 0 && nchunks > 0, "detrb_adam_clipnorm_chunked: bad sizes");
-    DETRB_LAUNCH(adam_prologue_kernel, dim3(ceil_div((T > 8 ? T : 8), 256)), dim3(256), 0, stream, steps, group_enabled, 8, norms, T);
-    DETRB_CHECK_LAUNCH("adam_prologue_kernel");
+    if (prologue) {                // first call of an optimizer step: bump the enabled groups' iteration counters, zero every norm
+        DETRB_LAUNCH(adam_prologue_kernel, dim3(ceil_div((T > 8 ? T : 8), 256)), dim3(256), 0, stream, steps, group_enabled, 8, norms, T);
+        DETRB_CHECK_LAUNCH("adam_prologue_kernel");
+    }
     DETRB_LAUNCH(chunk_sumsq_kernel, dim3(nchunks), dim3(256), 0, stream, grads, chunks, norms);
     DETRB_CHECK_LAUNCH("chunk_sumsq_kernel");
     DETRB_LAUNCH(chunk_adam_kernel, dim3(nchunks), dim3(256), 0, stream, params, grads, m, v, chunks, lr_group, lrs, group_enabled, steps, norms,

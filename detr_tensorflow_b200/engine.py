@@ -131,6 +131,8 @@ class Engine:
         chunks = [[t, o + c, min(CH, n - c)] for t, (_, o, n, _, _) in enumerate(self.vars) for c in range(0, n, CH)]
         self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
         self.nchunks = len(chunks)
+        assert self.vars[0][0] == "backbone/conv1/kernel"
+        self.stem_chunks = sum(1 for c in chunks if c[0] == 0)      # the stem kernel's chunks come first (optimizer_step)
         self.group_range = {}
         for g in GROUPS:
             offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
@@ -847,11 +849,14 @@ class Engine:
         l3 = min(o for (name, o, _, _, _) in self.vars if name.startswith("backbone/layer3/"))
         return [(t0, self.total), (l3, t0), (0, l3)]
 
-    def backward(self, train_backbone=True, boundary=None):
+    def backward(self, train_backbone=True, boundary=None, defer_tail=False):
         """Gradients of total_loss wrt every trainable variable, accumulated (+=) into self.grads.
         train_backbone=False stops after the transformer (results identical for the trained groups; the reference
         computes the dead work anyway, optimizers.py:112-115 / SURVEY appendix A.7).
-        boundary(k) is called when gradient bucket k (grad_buckets()) is complete, side-stream weight gradients included."""
+        boundary(k) is called when gradient bucket k (grad_buckets()) is complete, side-stream weight gradients included.
+        defer_tail: return without waiting for the stem's weight gradient (side stream); the optimizer_step() that follows
+        applies the other variables beside it and joins.  Single-rank train step only."""
+        self._tail = None
         def reached(k):
             if boundary is not None:
                 self._join_wgrad()
@@ -1010,9 +1015,14 @@ class Engine:
         stem = self.slots["backbone/conv1"]
         self.launches += 1
         x, Ms = a["s2d"], self.M_stem
+        before_stem = self._w_last if self._w_last is not None else True
         self._on_wstream(lambda: ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
                                            rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True), (x, g_in))
         self._in_backward = False
+        if defer_tail and boundary is None and self._w_last is not None and hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
+            self._tail = before_stem                               # joined by optimizer_step()
+            self._mark("bwd_backbone")
+            return
         self._join_wgrad()
         reached(2)
         self._mark("bwd_backbone")
@@ -1034,11 +1044,15 @@ class Engine:
         self._adam(grads_arena, clipnorm)
         self.refresh_weights()
 
-    def _adam(self, grads_arena, clipnorm):
+    def _adam(self, grads_arena, clipnorm, lo=0, hi=None, prologue=True):
+        """Adam + per-variable clipnorm over chunks [lo, hi) of the chunk table (whole variables); prologue: first call of the step"""
         if hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
-            ops.adam_clipnorm_chunked(self.params, grads_arena, self.adam_m, self.adam_v, self.chunks, self.nchunks, self.lr_group,
-                                      self.lrs, self.group_enabled, self.T, clipnorm, self.steps, self.norms)
+            hi = self.nchunks if hi is None else hi
+            ops.adam_clipnorm_chunked(self.params, grads_arena, self.adam_m, self.adam_v, self.chunks, hi - lo, self.lr_group,
+                                      self.lrs, self.group_enabled, self.T, clipnorm, self.steps, self.norms, first_chunk=lo,
+                                      prologue=prologue)
         else:
+            assert lo == 0 and hi is None
             ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
                               self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
 
@@ -1074,9 +1088,20 @@ class Engine:
         self.normalisers = self._norm_buf
 
     def optimizer_step(self, clipnorm):
-        """aggregate_grad_and_apply's apply branch (optimizers.py:160-163) for all enabled groups."""
-        self.launches += 3
-        self._adam(self.grads, clipnorm)
+        """aggregate_grad_and_apply's apply branch (optimizers.py:160-163) for all enabled groups.  After backward(defer_tail=True)
+        the stem's weight gradient -- the last kernel of the backward pass, 155 us alone on the GPU -- is still running on the side
+        stream: every other variable is applied beside it, the stem kernel (the first chunks of the table) afterwards."""
+        if getattr(self, "_tail", None) is not None:
+            before_stem, self._tail = self._tail, None
+            if before_stem is not True:
+                torch.cuda.current_stream().wait_event(before_stem)       # all weight gradients issued before the stem's
+            self.launches += 5
+            self._adam(self.grads, clipnorm, lo=self.stem_chunks, prologue=True)
+            self._join_wgrad()
+            self._adam(self.grads, clipnorm, lo=0, hi=self.stem_chunks, prologue=False)
+        else:
+            self.launches += 3
+            self._adam(self.grads, clipnorm)
         self.refresh_weights()
 
     # ------------------------------------------------------------------------------------------ fused fast path
@@ -1094,7 +1119,7 @@ class Engine:
             for w in works:
                 w.wait()
         else:
-            self.backward(train_backbone=train_backbone)
+            self.backward(train_backbone=train_backbone, defer_tail=True)
         self._mark("allreduce")
         self.optimizer_step(clipnorm)
         self._mark("adam_refresh")
@@ -1114,7 +1139,7 @@ class Engine:
             self._forward_impl()
             self.loss(background_class, loss_scale=loss_scale, with_grad=True)
             self.zero_grads()
-            self.backward(train_backbone=train_backbone)
+            self.backward(train_backbone=train_backbone, defer_tail=not self._distributed())
 
         def part2():
             self.optimizer_step(clipnorm)

@@ -190,10 +190,11 @@ def prep_weights_multi(descs_dev, nslots, total_tiles):
 
 
 def adam_clipnorm_chunked(params, grads, m, v, chunks, nchunks, lr_group, lrs, group_enabled, T, clipnorm, steps, norms,
-                          beta1=0.9, beta2=0.999, eps=1e-7):
-    check(_lib.lib().detrb_adam_clipnorm_chunked(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(chunks), c_int(nchunks), ptr(lr_group),
-                                                 ptr(lrs), ptr(group_enabled), c_int(T), c_float(clipnorm), c_float(beta1), c_float(beta2),
-                                                 c_float(eps), ptr(steps), ptr(norms), _stream()))
+                          beta1=0.9, beta2=0.999, eps=1e-7, first_chunk=0, prologue=True):
+    """chunks [first_chunk, first_chunk + nchunks) of the [*, 3] int32 chunk table"""
+    check(_lib.lib().detrb_adam_clipnorm_chunked(ptr(params), ptr(grads), ptr(m), ptr(v), ptr(chunks, 3 * first_chunk), c_int(nchunks),
+                                                 ptr(lr_group), ptr(lrs), ptr(group_enabled), c_int(T), c_float(clipnorm), c_float(beta1),
+                                                 c_float(beta2), c_float(eps), ptr(steps), ptr(norms), c_int(int(prologue)), _stream()))
 
 
 def normalize_u8(img_u8, lut, swap_rb, out_f32, npix):

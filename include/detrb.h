@@ -252,11 +252,14 @@ int detrb_adam_clipnorm(float *params, const float *grads, float *m, float *v,
                         int32_t *steps, float *norms, detrb_stream_t stream);
 
 /* Same step over uniform work items: chunks = DEVICE int32 [nchunks][3] = {table row, start offset in the arena (multiple of 4),
- * length <= 8192}; tensors are cut into chunks by the host once.  float4 accesses, balanced blocks. */
+ * length <= 8192}; tensors are cut into chunks by the host once.  float4 accesses, balanced blocks.
+ * One optimizer step may be issued as several calls over disjoint chunk ranges, each holding whole variables (the engine
+ * applies everything but the stem kernel while the stem's weight gradient is still being computed): prologue != 0 on the
+ * first call of the step (bumps the enabled groups' counters, zeroes all norms), 0 on the following ones. */
 int detrb_adam_clipnorm_chunked(float *params, const float *grads, float *m, float *v, const int32_t *chunks, int nchunks,
                                 const int32_t *lr_group, const float *lrs, const uint8_t *group_enabled, int T,
                                 float clipnorm, float beta1, float beta2, float eps, int32_t *steps, float *norms,
-                                detrb_stream_t stream);
+                                int prologue, detrb_stream_t stream);
 
 /* master fp32 weight [N, taps, Cin] (+ optional per-row fold[n]) -> bf16 forward copy Wf [N, ldf]
  * (K = taps*Cin, zero padded to ldf) and optional data-gradient copy Wd [Cin, taps, ldd] (cols>=N zero). */

@@ -548,6 +548,35 @@ class FakeLib:
             P_[o:o + n] -= lr_t * M_[o:o + n] / (V_[o:o + n].sqrt() + eps)
         return 0
 
+    def detrb_adam_clipnorm_chunked(self, params, grads, m, v, chunks, nchunks, lr_group, lrs, enabled, Tn, clipnorm, beta1, beta2, eps,
+                                    steps, norms, prologue, stream):
+        """one optimizer step issued over a chunk range holding whole variables (see include/detrb.h)"""
+        nchunks, Tn, clipnorm, beta1, beta2, eps, prologue = map(_v, (nchunks, Tn, clipnorm, beta1, beta2, eps, prologue))
+        ch = T(chunks, torch.int32, 3 * nchunks).view(nchunks, 3)
+        grp, lr, en = T(lr_group, torch.int32, Tn), T(lrs, F32, 8), T(enabled, torch.uint8, 8)
+        st, nr = T(steps, torch.int32, 8), T(norms, F32, Tn)
+        if prologue:
+            st += en.to(torch.int32)
+            nr.zero_()
+        end = int((ch[:, 1] + ch[:, 2]).max())
+        P_, G_, M_, V_ = (T(x, F32, end) for x in (params, grads, m, v))
+        for t, o, n in ch.tolist():
+            g = G_[o:o + n]
+            nr[t] += (g * g).sum()
+        for t, o, n in ch.tolist():
+            k = int(grp[t])
+            if not en[k]:
+                continue
+            norm = float(nr[t].sqrt())
+            g = G_[o:o + n]
+            g = g * (clipnorm / norm) if (clipnorm > 0 and norm > clipnorm) else g
+            step = float(st[k])
+            M_[o:o + n] = beta1 * M_[o:o + n] + (1 - beta1) * g
+            V_[o:o + n] = beta2 * V_[o:o + n] + (1 - beta2) * g * g
+            lr_t = float(lr[k]) * np.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
+            P_[o:o + n] -= lr_t * M_[o:o + n] / (V_[o:o + n].sqrt() + eps)
+        return 0
+
     def detrb_prep_weight(self, master, fold, N, taps, Cin, Wf, ldf, Wd, ldd, stream):
         N, taps, Cin, ldf, ldd = map(_v, (N, taps, Cin, ldf, ldd))
         w = T(master, F32, N * taps * Cin).view(N, taps, Cin)

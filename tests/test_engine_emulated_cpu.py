@@ -131,6 +131,35 @@ def test_training_fit_adam_and_accumulation(emu):
     assert torch.equal(new["backbone/bn1/weight"], P["backbone/bn1/weight"])
 
 
+def test_optimizer_step_split_around_the_stem_gradient(emu):
+    """optimizer_step after backward(defer_tail=True) applies every variable but the stem kernel first and the stem kernel
+    (the first chunks of the table) afterwards: identical to the one-call step"""
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    res = []
+    for split in (False, True):
+        model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+        eng = model.engine
+        eng.forward(img, training=False)
+        eng.set_targets(tb, tc)
+        eng.set_lrs(1e-3, 1e-2)
+        eng.set_enabled(True, True)
+        for _ in range(2):
+            eng.zero_grads()
+            eng.loss(91)
+            eng.backward()
+            assert eng.stem_chunks == 2 and eng._tail is None
+            if split:
+                eng._tail = True                           # what backward(defer_tail=True) leaves behind on a GPU
+            eng.optimizer_step(0.1)
+            assert eng._tail is None
+        res.append((eng.params.clone(), eng.adam_v.clone(), eng.steps.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert res[0][2][:2].tolist() == [2, 2]
+
+
 def test_fit_loop_runs(emu, capsys):
     import detr_tensorflow_b200 as D
     P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)

@@ -526,6 +526,21 @@ def test_adam_clipnorm_and_prep_weight(ops):
     close("chunked adam params", p2, p_d, 1e-6, 1e-7)
     close("chunked adam v", v2, v_d, 1e-5, 1e-12)
     assert steps2.cpu()[:3].tolist() == [3, 3, 0]
+    # one step issued as two calls over disjoint chunk ranges (whole variables each; the engine applies the stem kernel last)
+    p3, m3, v3 = dev(P.clone()), torch.zeros(total, device="cuda"), torch.zeros(total, device="cuda")
+    steps3, norms3 = torch.zeros(8, dtype=torch.int32, device="cuda"), torch.zeros(len(sizes), device="cuda")
+    n0 = int((chunks[:, 0] == 0).sum())
+    ch_d = dev(chunks)
+    for step in (1, 2, 3):
+        ops.adam_clipnorm_chunked(p3, g_d, m3, v3, ch_d, chunks.shape[0] - n0, dev(grp), dev(lrs), dev(en), len(sizes), 0.1, steps3, norms3,
+                                  first_chunk=n0, prologue=True)
+        ops.adam_clipnorm_chunked(p3, g_d, m3, v3, ch_d, n0, dev(grp), dev(lrs), dev(en), len(sizes), 0.1, steps3, norms3,
+                                  first_chunk=0, prologue=False)
+    torch.cuda.synchronize()
+    # (the per-variable norms are sums of fp32 atomics: equal up to the summation order)
+    close("split adam params", p3, p2, 1e-6, 1e-7)
+    close("split adam v", v3, v2, 1e-5, 1e-12)
+    assert steps3.cpu()[:3].tolist() == [3, 3, 0]
     # prep_weight
     N, taps, Cin = 96, 9, 64
     master = dev(rnd(N, taps, Cin, seed=4))
