@@ -133,6 +133,12 @@ class Engine:
         self.nchunks = len(chunks)
         assert self.vars[0][0] == "backbone/conv1/kernel"
         self.stem_chunks = sum(1 for c in chunks if c[0] == 0)      # the stem kernel's chunks come first (optimizer_step)
+        self.group_chunks = {}                                       # group -> [lo, hi) of the chunk table (groups are contiguous)
+        for gi, g in enumerate(GROUPS):
+            idx = [i for i, c in enumerate(chunks) if self.vars[c[0]][3] == g]
+            if idx:
+                assert idx == list(range(idx[0], idx[-1] + 1))
+                self.group_chunks[g] = (idx[0], idx[-1] + 1)
         self.group_range = {}
         for g in GROUPS:
             offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
@@ -653,6 +659,7 @@ class Engine:
         self._plan(B, H, W)
         self.training = bool(training)
         self._stage_images(images)
+        self._ensure_weights()
         self._forward_impl()
         return self.outputs()
 
@@ -1029,20 +1036,31 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ optimizer
     def set_lrs(self, backbone_lr, transformers_lr, nlayers_lr=0.0):
-        self.lrs[:3] = torch.tensor([backbone_lr, transformers_lr, nlayers_lr], dtype=F32)
+        key = (float(backbone_lr), float(transformers_lr), float(nlayers_lr))
+        if getattr(self, "_lrs_host", None) != key:             # (a host->device copy from pageable memory blocks the host)
+            self.lrs[:3] = torch.tensor(key, dtype=F32)
+            self._lrs_host = key
 
     def set_enabled(self, backbone, transformers, nlayers=False):
         self.group_enabled[:3] = torch.tensor([int(backbone), int(transformers), int(nlayers)], dtype=torch.uint8)
 
     def apply_group(self, name, grads_arena, clipnorm):
         """Adam apply for ONE group (the reference applies its three optimizers one after the other,
-        training.py:53-54 -> optimizers.py:160-163)."""
-        en = torch.zeros(8, dtype=torch.uint8)
-        en[GROUPS.index(name)] = 1
-        self.group_enabled.copy_(en)
+        training.py:53-54 -> optimizers.py:160-163): only the group's chunks of the table are visited; the bf16 kernel-layout
+        weight copies are refreshed once, before the next forward pass (_ensure_weights), not once per group."""
+        gi = GROUPS.index(name)
+        if getattr(self, "_en_one", None) is None:
+            self._en_one = [torch.zeros(8, dtype=torch.uint8).index_fill_(0, torch.tensor([i]), 1).to(self.device) for i in range(len(GROUPS))]
+        self.group_enabled.copy_(self._en_one[gi])              # device-to-device, asynchronous
+        lo, hi = self.group_chunks[name]
         self.launches += 3
-        self._adam(grads_arena, clipnorm)
-        self.refresh_weights()
+        self._adam(grads_arena, clipnorm, lo=lo, hi=hi)
+        self._weights_dirty = True
+
+    def _ensure_weights(self):
+        if getattr(self, "_weights_dirty", False):
+            self._weights_dirty = False
+            self.refresh_weights()
 
     def _adam(self, grads_arena, clipnorm, lo=0, hi=None, prologue=True):
         """Adam + per-variable clipnorm over chunks [lo, hi) of the chunk table (whole variables); prologue: first call of the step"""
@@ -1051,8 +1069,7 @@ class Engine:
             ops.adam_clipnorm_chunked(self.params, grads_arena, self.adam_m, self.adam_v, self.chunks, hi - lo, self.lr_group,
                                       self.lrs, self.group_enabled, self.T, clipnorm, self.steps, self.norms, first_chunk=lo,
                                       prologue=prologue)
-        else:
-            assert lo == 0 and hi is None
+        else:                                                    # table variant: every variable, the group flags select
             ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
                               self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
 
@@ -1109,6 +1126,7 @@ class Engine:
         """One optimizer step on the batch already resident in a['images'] / a['t_bbox'] / a['t_class']:
         training.py:9-25 + :53-54 with no accumulation.  Launch-only (no host sync): CUDA-graph capturable."""
         self.training = True
+        self._ensure_weights()
         self.seed_dev.add_(1)                   # fresh dropout masks every step, also under graph replay
         self._forward_impl()
         self.loss(background_class, loss_scale=loss_scale, with_grad=True)
@@ -1143,6 +1161,7 @@ class Engine:
 
         def part2():
             self.optimizer_step(clipnorm)
+        self._ensure_weights()
         dist_on = self._distributed()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -1229,6 +1248,7 @@ class Engine:
             self.loss(background_class, loss_scale=loss_scale, with_grad=True)
             self.zero_grads()
             self.backward(train_backbone=True)
+        self._ensure_weights()                             # a per-group apply (apply_group) since the last forward pass
         if not use_graph or self.device.type != "cuda":
             body()
             return self.allreduce_grads()

@@ -131,6 +131,7 @@ def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None
             _train_log_hook(images, t_bbox, t_class, m_outputs, config, config.global_step, class_names, prefix="train/")
         for name in gradient_steps:
             aggregate_grad_and_apply(name, optimizers, gradient_steps[name]["gradients"], epoch_step, config)
+        model.engine._ensure_weights()      # one refresh of the bf16 weight copies for all groups, enqueued before any host sync
         if on_step is not None:
             on_step(epoch_step, total_loss, log)
         if epoch_step % 100 == 0:
