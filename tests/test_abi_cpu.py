@@ -57,3 +57,45 @@ def test_no_product_import_of_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
                 assert "cabi_emulator" not in src
+
+
+def _prototypes():
+    """function name -> number of parameters, from include/detrb.h"""
+    h = re.sub(r"/\*.*?\*/", "", _header(), flags=re.S)
+    out = {}
+    for _, name, args in re.findall(r"\b(int|const char \*|void)\s*\*?\s*(detrb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", h):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_every_call_site_passes_the_declared_number_of_arguments():
+    """ctypes does not check arity: a call with a missing or extra argument would corrupt the callee's view of the stack.  Every
+    `<lib>.detrb_xxx(...)` call in the package must pass exactly the parameters include/detrb.h declares, and the CPU emulator
+    of the ABI (test infrastructure) must mirror the same signatures."""
+    import ast
+    import inspect
+    protos = _prototypes()
+    assert len(protos) >= 30
+    pkg = os.path.join(ROOT, "detr_tensorflow_b200")
+    seen = set()
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dp, f)).read())
+            for node in ast.walk(tree):
+                if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("detrb_"):
+                    name = node.func.attr
+                    assert name in protos, f"{f}: {name} is not declared in include/detrb.h"
+                    assert not node.keywords and not any(isinstance(a, ast.Starred) for a in node.args), (f, name)
+                    assert len(node.args) == protos[name], f"{f}:{node.lineno} {name}: {len(node.args)} arguments, header declares {protos[name]}"
+                    seen.add(name)
+    assert len(seen) >= 25, sorted(seen)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cabi_emulator
+    for name, fn in inspect.getmembers(cabi_emulator.FakeLib, inspect.isfunction):
+        if name.startswith("detrb_") and name in protos:
+            n = len(inspect.signature(fn).parameters) - 1          # minus self
+            assert n == protos[name], f"cabi_emulator.FakeLib.{name}: {n} parameters, header declares {protos[name]}"

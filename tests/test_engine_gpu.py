@@ -52,6 +52,24 @@ def test_forward_parity(D, setup):
     assert rel(eng.feat.view(feat.shape), feat) < 3e-2
 
 
+def test_baseline_config_c1_forward_480x640(D):
+    """BASELINE.json configs[0] (1 synthetic 480x640 image, forward only) through get_detr_model()/model(): same output dict as
+    the CPU oracle run of the same configuration, within the bf16-storage tolerance of test_forward_parity"""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=0)
+    img = torch.randn(1, 480, 640, 3, generator=torch.Generator().manual_seed(0))
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0)
+    out = model(img, training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.detr_forward(P, img)
+    assert out["pred_logits"].shape == (1, 100, 92) and out["pred_boxes"].shape == (1, 100, 4) and len(out["aux"]) == 5
+    assert (model.engine.fh, model.engine.fw) == (15, 20)
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+
+
 def test_matcher_exact_on_engine_outputs_and_loss_parity(D, setup):
     O, P, img, tb, tc, cfg, model = setup
     import numpy as np

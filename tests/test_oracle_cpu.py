@@ -153,6 +153,20 @@ def test_forward_shapes_and_param_count():
     assert len(out["aux"]) == 5
 
 
+def test_baseline_config_c1_forward_480x640_cpu():
+    """BASELINE.json configs[0]: DETR-R50 forward on 1 synthetic 480x640 image on the CPU (plumbing, no GPU): the reference-shaped
+    output dict with [1,100,92] logits, [1,100,4] boxes in [0,1] and 5 aux entries; feature map 15x20 (S = 300)."""
+    P = O.init_params(seed=0)
+    img = torch.randn(1, 480, 640, 3, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        feat = O.backbone_forward(P, img)
+        out = O.detr_forward(P, img)
+    assert tuple(feat.shape[1:3]) == (15, 20)
+    assert out["pred_logits"].shape == (1, 100, 92) and out["pred_boxes"].shape == (1, 100, 4) and len(out["aux"]) == 5
+    assert all(a["pred_logits"].shape == (1, 100, 92) and a["pred_boxes"].shape == (1, 100, 4) for a in out["aux"])
+    assert bool(torch.isfinite(out["pred_logits"]).all()) and float(out["pred_boxes"].min()) >= 0 and float(out["pred_boxes"].max()) <= 1
+
+
 def test_pos_embedding_layout():
     pe = O.position_embedding_sine(3, 4)
     assert pe.shape == (3, 4, 256)
