@@ -6,14 +6,22 @@ reference's hot path (Visual-Behavior/detr-tensorflow).  Only ``tests/``,
 product path (``detr_tensorflow_b200``) never does.
 
 PARITY STATUS: the reference ships no tests / golden vectors and TensorFlow is not
-installable here, so the *model* part (backbone, transformer, heads, optimizer) is
-"parity unpinned": a restatement by reading, cross-checked against independent
-implementations (torchvision resnet50, F.multi_head_attention_forward) in
-tests/test_oracle_cpu.py.  The *loss / matcher* part is pinned: the reference's own
-``detr_tf/loss/*.py`` + ``detr_tf/bbox.py`` were executed unmodified on a numpy-backed
-``tensorflow`` shim (tests/golden/make_golden.py) and this oracle is checked against
-those outputs, and the assignment step uses the real ``scipy.optimize.linear_sum_assignment``
-(the routine the reference calls, hungarian_matching.py:7,29).
+installable here.  What pins this oracle instead is the reference's OWN code, executed
+unmodified on stand-ins for the TensorFlow library:
+  * model forward (backbone, position embedding, transformer, heads): detr_tf/networks/
+    {detr,resnet_backbone,transformer,custom_layers,position_embeddings}.py run through
+    ``get_detr_model()`` on a torch-backed ``tensorflow`` shim with this oracle's seeded
+    weights injected by Keras variable name (tests/golden/make_golden_model.py ->
+    model_golden.npz); the oracle reproduces every captured activation to ~1e-5
+    (tests/test_oracle_cpu.py::test_model_forward_vs_reference_code_golden), and is also
+    cross-checked against torchvision resnet50 and F.multi_head_attention_forward;
+  * loss / matcher: detr_tf/loss/*.py + detr_tf/bbox.py on a numpy-backed shim
+    (tests/golden/make_golden.py), with the real ``scipy.optimize.linear_sum_assignment``
+    (the routine the reference calls, hungarian_matching.py:7,29);
+  * inference post-process / input normalisation / pad_labels: make_golden_pipeline.py.
+Still "parity unpinned" (TF library arithmetic, restated from its documentation): Keras
+Adam with per-variable clipnorm, and the dropout random stream (parity is defined in
+inference mode).  Gradients are torch autograd of the pinned forward + loss.
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/detr_tf).

@@ -1,0 +1,73 @@
+"""Generate golden vectors for the MODEL path (backbone -> input_proj -> position embedding -> transformer -> heads) by
+EXECUTING THE REFERENCE'S OWN CODE.
+
+    python tests/golden/make_golden_model.py            # needs /root/reference (build container only)
+
+detr_tf/networks/{detr,resnet_backbone,transformer,custom_layers,position_embeddings}.py are imported unmodified from
+/root/reference with `tensorflow` replaced by tests/golden/tf_torch_model_shim.py (TF itself is not installable here):
+`get_detr_model(config, include_top=True, ...)` (detr.py:116-204) builds the model and runs it on a seeded image with the
+oracle's seeded weights injected by variable name.  Outputs -> tests/golden/model_golden.npz (committed; /root/reference does
+not exist on the GPU box).  The weights are NOT stored: tests regenerate them from the same seed (oracle.init_params).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import tf_torch_model_shim as shim  # noqa: E402
+
+shim.install()
+sys.path.insert(0, "/root/reference")
+from detr_tf.networks import detr as ref_detr  # noqa: E402
+from oracle import detr_oracle as O  # noqa: E402
+
+CASES = {                # name: (seed, batch, H, W, encoder layers, decoder layers)
+    "a": (11, 2, 96, 128, 2, 3),
+    "b": (12, 1, 75, 110, 1, 2),           # odd sizes: every stride-2 stage rounds
+}
+
+
+class Cfg:
+    normalized_method = "torch_resnet"
+
+
+def main():
+    torch.manual_seed(0)
+    out = {}
+    for case, (seed, B, H, W, ne, nd) in CASES.items():
+        P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+        img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+        shim.set_weights({k: v.float() for k, v in P.items()})
+        shim.set_input(img)
+        with torch.no_grad():
+            model = ref_detr.get_detr_model(Cfg(), include_top=True, num_decoder_layers=nd, num_encoder_layers=ne)
+            res = model(img)
+        created = {n: s for n, s, _ in shim.STATE["created"]}
+        assert set(created) == set(P), (sorted(set(P) - set(created)), sorted(set(created) - set(P)))
+        assert all(tuple(P[n].shape) == created[n] for n in P)
+        trainable = sorted(n for n, _, t in shim.STATE["created"] if t)
+        acts = shim.STATE["outputs"]
+        out[f"{case}_meta"] = np.array([seed, B, H, W, ne, nd])
+        out[f"{case}_feat"] = acts["backbone"].numpy()                       # [B, h, w, 2048]
+        out[f"{case}_pos"] = acts["position_embedding_sine"].numpy()         # [B, h, w, 256]
+        out[f"{case}_hs"] = acts["transformer"][0].numpy()                   # [L, B, 100, 256]
+        out[f"{case}_memory"] = acts["transformer"][1].numpy()               # [B, h, w, 256]
+        out[f"{case}_pred_logits"] = res["pred_logits"].numpy()
+        out[f"{case}_pred_boxes"] = res["pred_boxes"].numpy()
+        for i, a in enumerate(res["aux"]):
+            out[f"{case}_aux{i}_logits"] = a["pred_logits"].numpy()
+            out[f"{case}_aux{i}_boxes"] = a["pred_boxes"].numpy()
+        out[f"{case}_trainable"] = np.array(trainable)
+        print(case, "feat", out[f"{case}_feat"].shape, "hs", out[f"{case}_hs"].shape, "aux", len(res["aux"]),
+              "variables", len(created), "trainable", len(trainable))
+    np.savez_compressed(os.path.join(HERE, "model_golden.npz"), **out)
+    print("wrote", os.path.join(HERE, "model_golden.npz"), os.path.getsize(os.path.join(HERE, "model_golden.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

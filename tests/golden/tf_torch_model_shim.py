@@ -1,0 +1,274 @@
+"""A torch-backed stand-in for the `tensorflow` / Keras symbols that the reference's MODEL code touches
+(detr_tf/networks/{detr,resnet_backbone,transformer,custom_layers,position_embeddings}.py).
+
+TensorFlow is not installable in the build container (no wheel, no network).  With this shim installed as
+``sys.modules['tensorflow']`` the reference's model files are imported from /root/reference and EXECUTED UNMODIFIED --
+`get_detr_model()` builds its layers, creates its variables and runs its `call()` methods line by line -- on float32 torch
+tensors, to produce the golden vectors of tests/golden/model_golden.npz (see make_golden_model.py).  What the shim supplies
+are Keras *library* semantics only (Conv2D / ZeroPadding2D / MaxPool2D / LayerNormalization / Dropout(training=False), the
+tf.* array functions, variable naming by layer-name path); every line of model wiring is the reference's own.
+
+The functional API (`tf.keras.Input`, `tf.keras.Model(inputs, outputs)`) is executed eagerly: `Input()` returns the concrete
+image tensor set with `set_input()`, so `get_detr_model` computes real activations while it "builds the graph".
+
+Test infrastructure only.
+"""
+import inspect
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+STATE = {"input": None, "weights": {}, "created": [], "outputs": {}, "layers": []}
+
+
+def set_input(x):
+    STATE["input"] = x
+
+
+def set_weights(named):
+    """name path (e.g. 'backbone/layer1/0/conv1/kernel') -> float32 torch tensor; every add_weight() must find its entry"""
+    STATE["weights"] = dict(named)
+    STATE["created"] = []
+    STATE["outputs"] = {}
+    STATE["layers"] = []
+
+
+def _relink():
+    """parents from attribute containment (lists included: the reference appends bottlenecks to a list after assigning it)"""
+    for L in STATE["layers"]:
+        for k, v in list(vars(L).items()):
+            if k == "_parent":
+                continue
+            for e in (v if isinstance(v, (list, tuple)) else (v,)):
+                if isinstance(e, Layer) and e is not L and e._parent is None:
+                    object.__setattr__(e, "_parent", L)
+
+
+class Layer:
+    _counters = {}
+
+    def __init__(self, name=None, **kwargs):
+        assert not kwargs or set(kwargs) <= {"dtype", "trainable"}, kwargs
+        if name is None:
+            base = type(self).__name__.lower()
+            n = Layer._counters.get(base, 0)
+            Layer._counters[base] = n + 1
+            name = base if n == 0 else f"{base}_{n}"
+        object.__setattr__(self, "_parent", None)
+        self.name = name
+        self._built = False
+        STATE["layers"].append(self)
+
+    # ---- variable naming: the path of layer names below the root model, as Keras scopes variable names
+    def _path(self):
+        names, node = [], self
+        while node is not None and node._parent is not None:
+            names.append(node.name)
+            node = node._parent
+        return "/".join(reversed(names))
+
+    def add_weight(self, name=None, shape=None, initializer=None, dtype=None, trainable=True):
+        full = (self._path() + "/" + name).lstrip("/")
+        assert full in STATE["weights"], f"no injected value for variable {full!r}"
+        w = STATE["weights"][full]
+        assert tuple(w.shape) == tuple(int(s) for s in shape), (full, tuple(w.shape), tuple(shape))
+        STATE["created"].append((full, tuple(w.shape), bool(trainable)))
+        return w.clone()
+
+    def build(self, input_shape):
+        pass
+
+    def __call__(self, *args, **kwargs):
+        if not self._built:
+            _relink()
+            x = args[0] if args else None
+            if isinstance(x, torch.Tensor):
+                shape = tuple(x.shape)
+            elif isinstance(x, (list, tuple)):
+                shape = [tuple(t.shape) for t in x]
+            else:
+                shape = None
+            self.build(shape)
+            self._built = True
+        params = inspect.signature(self.call).parameters
+        if "training" in kwargs and "training" not in params:        # Keras drops the argument for layers that do not take it
+            kwargs.pop("training")
+        out = self.call(*args, **kwargs)
+        STATE["outputs"].setdefault(self._path() or self.name, out)
+        return out
+
+
+class Model(Layer):
+    def __init__(self, *args, **kwargs):
+        if len(args) == 2:                                            # functional: Model(inputs, outputs, name=...)
+            super().__init__(name=kwargs.pop("name", None))
+            self._inputs, self._outputs = args
+            return
+        assert not args
+        super().__init__(**kwargs)
+
+    def call(self, x, **kwargs):                                      # functional models only: same concrete input -> stored output
+        assert x is self._inputs
+        return self._outputs
+
+    def get_layer(self, name):
+        for v in vars(self).values():
+            if isinstance(v, Layer) and v.name == name:
+                return v
+        raise ValueError(name)
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+class Conv2D(Layer):
+    def __init__(self, filters, kernel_size, strides=1, padding="valid", use_bias=True, dilation_rate=1, **kw):
+        super().__init__(**kw)
+        assert padding == "valid"
+        self.filters, self.k, self.s, self.use_bias, self.d = filters, kernel_size, strides, use_bias, dilation_rate
+
+    def build(self, input_shape):
+        self.kernel = self.add_weight(name="kernel", shape=(self.k, self.k, input_shape[-1], self.filters))
+        self.bias = self.add_weight(name="bias", shape=(self.filters,)) if self.use_bias else None
+
+    def call(self, x):
+        return _nhwc(F.conv2d(_nchw(x), self.kernel.permute(3, 2, 0, 1), self.bias, stride=self.s, padding=0, dilation=self.d))
+
+
+class ZeroPadding2D(Layer):
+    def __init__(self, padding=1, **kw):
+        super().__init__(**kw)
+        self.p = padding
+
+    def call(self, x):
+        return F.pad(x, (0, 0, self.p, self.p, self.p, self.p))
+
+
+class ReLU(Layer):
+    def call(self, x):
+        return torch.relu(x)
+
+
+class Activation(Layer):
+    def __init__(self, activation, **kw):
+        super().__init__(**kw)
+        assert activation == "relu"
+
+    def call(self, x):
+        return torch.relu(x)
+
+
+class MaxPool2D(Layer):
+    def __init__(self, pool_size=2, strides=None, padding="valid", **kw):
+        super().__init__(**kw)
+        assert padding == "valid"
+        self.k, self.s = pool_size, strides or pool_size
+
+    def call(self, x):
+        return _nhwc(F.max_pool2d(_nchw(x), self.k, self.s))
+
+
+class Dropout(Layer):
+    def __init__(self, rate=0.0, **kw):
+        super().__init__(**kw)
+
+    def call(self, x, training=False):
+        assert not training, "the golden vectors are taken in inference mode (TF's dropout RNG cannot be reproduced)"
+        return x
+
+
+class LayerNormalization(Layer):
+    def __init__(self, epsilon=1e-3, **kw):
+        super().__init__(**kw)
+        self.eps = epsilon
+
+    def build(self, input_shape):
+        self.gamma = self.add_weight(name="gamma", shape=(input_shape[-1],))
+        self.beta = self.add_weight(name="beta", shape=(input_shape[-1],))
+
+    def call(self, x):
+        mean = x.mean(-1, keepdim=True)
+        var = ((x - mean) ** 2).mean(-1, keepdim=True)
+        return (x - mean) * torch.rsqrt(var + self.eps) * self.gamma + self.beta
+
+
+class Dense(Layer):
+    def __init__(self, units, activation=None, **kw):
+        super().__init__(**kw)
+        self.units, self.act = units, activation
+
+    def build(self, input_shape):
+        self.kernel = self.add_weight(name="kernel", shape=(input_shape[-1], self.units))
+        self.bias = self.add_weight(name="bias", shape=(self.units,))
+
+    def call(self, x):
+        y = x @ self.kernel + self.bias
+        return torch.relu(y) if self.act == "relu" else torch.sigmoid(y) if self.act == "sigmoid" else y
+
+
+def _ints(shape):
+    return [int(s) for s in shape]
+
+
+def build():
+    tf = types.ModuleType("tensorflow")
+    tf.float32, tf.int32, tf.int64, tf.bool = torch.float32, torch.int32, torch.int64, torch.bool
+    tf.Tensor = torch.Tensor
+    tf.newaxis = None
+    tf.shape = lambda x: list(x.shape)
+    tf.reshape = lambda x, shape: x.reshape(_ints(shape)).clone()
+    tf.transpose = lambda x, perm: x.permute(*perm).contiguous()
+    tf.matmul = lambda a, b, transpose_b=False: a @ (b.transpose(-1, -2) if transpose_b else b)
+    tf.zeros = lambda shape, dtype=torch.float32: torch.zeros(_ints(shape), dtype=dtype)
+    tf.zeros_like = lambda x: torch.zeros_like(x)
+    tf.expand_dims = lambda x, axis: x.unsqueeze(axis)
+    tf.squeeze = lambda x, axis=None: x.squeeze() if axis is None else x.squeeze(axis)
+    tf.stack = lambda xs, axis=0: torch.stack(list(xs), dim=axis)
+    tf.concat = lambda xs, axis: torch.cat(list(xs), dim=axis)
+    tf.cast = lambda x, dt: x.to(dt)
+    tf.tile = lambda x, m: x.repeat(*_ints(m))
+    tf.sigmoid = torch.sigmoid
+    tf.range = lambda n, dtype=torch.int32: torch.arange(int(n), dtype=dtype)
+    tf.reduce_mean = lambda x, axis=None: x.mean() if axis is None else x.mean(axis)
+    tf.math = types.SimpleNamespace(sin=torch.sin, cos=torch.cos, rsqrt=torch.rsqrt, cumsum=lambda x, axis=0: torch.cumsum(x, dim=axis))
+    tf.nn = types.SimpleNamespace(softmax=lambda x, axis=-1: torch.softmax(x, dim=axis))
+
+    keras = types.ModuleType("tensorflow.keras")
+    layers = types.ModuleType("tensorflow.keras.layers")
+    for cls in (Layer, Conv2D, ZeroPadding2D, ReLU, Activation, MaxPool2D, Dropout, LayerNormalization, Dense):
+        setattr(layers, cls.__name__, cls)
+    keras.layers = layers
+    keras.Model = Model
+    keras.Input = lambda shape=None, **kw: STATE["input"]
+    keras.initializers = types.SimpleNamespace(GlorotUniform=lambda *a, **k: None)
+    keras.models = types.SimpleNamespace(Sequential=None)
+    keras.applications = types.SimpleNamespace(ResNet50=None)
+    tf.keras = keras
+    return tf, keras, layers
+
+
+def install():
+    tf, keras, layers = build()
+    sys.modules["tensorflow"] = tf
+    sys.modules["tensorflow.keras"] = keras
+    sys.modules["tensorflow.keras.layers"] = layers
+    for name in ("matplotlib", "matplotlib.pyplot"):                  # imported at module top by bbox.py / detr.py, unused on this path
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    if "matplotlib" in sys.modules and not hasattr(sys.modules["matplotlib"], "pyplot") and "matplotlib.pyplot" in sys.modules:
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    return tf
+
+
+__all__ = ["install", "set_input", "set_weights", "STATE", "np"]

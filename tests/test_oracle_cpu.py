@@ -2,6 +2,8 @@
 loss/matcher code (tests/golden/make_golden.py), (2) the C LSAP restatement against the installed scipy
 (the reference's real third-party arithmetic) incl. the tie known-answer table of SURVEY Appendix C,
 (3) model pieces against independent implementations (torchvision resnet50, F.multi_head_attention_forward)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -151,6 +153,42 @@ def test_forward_shapes_and_param_count():
         out = O.detr_forward(P, torch.randn(1, 64, 96, 3))
     assert out["pred_logits"].shape == (1, 100, 92) and out["pred_boxes"].shape == (1, 100, 4)
     assert len(out["aux"]) == 5
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_model_forward_vs_reference_code_golden(case):
+    """The MODEL part of the oracle against tests/golden/model_golden.npz: activations produced by the reference's own
+    detr.py / resnet_backbone.py / transformer.py / custom_layers.py / position_embeddings.py, executed unmodified on a
+    torch-backed TensorFlow shim (tests/golden/make_golden_model.py) with these same seeded weights injected by Keras
+    variable name.  Pins layer wiring, padding / stride placement, the packed in-projection split, the query scaling, the
+    [pos_y, pos_x] sin/cos interleave, the [S,B,256] <-> NHWC transposes and the head stack.  fp32 on both sides:
+    tolerance = accumulation-order noise."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz"))
+    seed, B, H, W, ne, nd = (int(v) for v in g[f"{case}_meta"])
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    # the reference created exactly these variables (names = Keras layer-name paths) and marks these trainable
+    assert sorted(n for n in P if not n.split("/")[-1] in ("weight", "bias", "running_mean", "running_var")
+                  or not ("bn" in n.split("/")[-2] or n.split("/")[-2] == "downsample_1")) == sorted(g[f"{case}_trainable"].tolist())
+    with torch.no_grad():
+        feat = O.backbone_forward(P, img)
+        out = O.detr_forward(P, img, num_encoder_layers=ne, num_decoder_layers=nd, return_hs=True)
+        pos = O.position_embedding_sine(feat.shape[1], feat.shape[2])
+
+    def close(name, got, ref, tol):
+        got, ref = torch.as_tensor(got).float(), torch.from_numpy(np.asarray(ref)).float()
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        err = float((got - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < tol, (name, err)
+    close("backbone", feat, g[f"{case}_feat"], 2e-5)
+    close("position embedding", pos.reshape(1, feat.shape[1], feat.shape[2], 256).expand(B, -1, -1, -1), g[f"{case}_pos"], 1e-5)
+    close("hs", out["hs"], g[f"{case}_hs"], 5e-5)
+    close("pred_logits", out["pred_logits"], g[f"{case}_pred_logits"], 5e-5)
+    close("pred_boxes", out["pred_boxes"], g[f"{case}_pred_boxes"], 5e-5)
+    assert len(out["aux"]) == nd - 1
+    for i, a in enumerate(out["aux"]):
+        close(f"aux{i} logits", a["pred_logits"], g[f"{case}_aux{i}_logits"], 5e-5)
+        close(f"aux{i} boxes", a["pred_boxes"], g[f"{case}_aux{i}_boxes"], 5e-5)
 
 
 def test_baseline_config_c1_forward_480x640_cpu():
