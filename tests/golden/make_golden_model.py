@@ -26,33 +26,42 @@ sys.path.insert(0, "/root/reference")
 from detr_tf.networks import detr as ref_detr  # noqa: E402
 from oracle import detr_oracle as O  # noqa: E402
 
-CASES = {                # name: (seed, batch, H, W, encoder layers, decoder layers)
-    "a": (11, 2, 96, 128, 2, 3),
-    "b": (12, 1, 75, 110, 1, 2),           # odd sizes: every stride-2 stage rounds
+CASES = {                # name: (seed, batch, H, W, encoder layers, decoder layers, nb_class)
+    "a": (11, 2, 96, 128, 2, 3, None),
+    "b": (12, 1, 75, 110, 1, 2, None),     # odd sizes: every stride-2 stage rounds
+    "ft": (13, 1, 64, 96, 1, 6, 3),        # include_top=False, nb_class=3: add_heads_nlayers (detr.py:94-114; 5 aux outputs hard-coded)
 }
 
 
 class Cfg:
     normalized_method = "torch_resnet"
+    nlayers = []
+
+    def add_nlayers(self, layers):           # training_config.py:79-82
+        self.nlayers = [l.name for l in layers]
 
 
 def main():
     torch.manual_seed(0)
     out = {}
-    for case, (seed, B, H, W, ne, nd) in CASES.items():
-        P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    for case, (seed, B, H, W, ne, nd, nb_class) in CASES.items():
+        P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd, nb_class=nb_class)
         img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
         shim.set_weights({k: v.float() for k, v in P.items()})
         shim.set_input(img)
         with torch.no_grad():
-            model = ref_detr.get_detr_model(Cfg(), include_top=True, num_decoder_layers=nd, num_encoder_layers=ne)
+            cfg = Cfg()
+            model = ref_detr.get_detr_model(cfg, include_top=nb_class is None, nb_class=nb_class, num_decoder_layers=nd,
+                                            num_encoder_layers=ne)
             res = model(img)
+        if nb_class is not None:
+            assert cfg.nlayers == ["cls_layer", "pos_layer"]
         created = {n: s for n, s, _ in shim.STATE["created"]}
         assert set(created) == set(P), (sorted(set(P) - set(created)), sorted(set(created) - set(P)))
         assert all(tuple(P[n].shape) == created[n] for n in P)
         trainable = sorted(n for n, _, t in shim.STATE["created"] if t)
         acts = shim.STATE["outputs"]
-        out[f"{case}_meta"] = np.array([seed, B, H, W, ne, nd])
+        out[f"{case}_meta"] = np.array([seed, B, H, W, ne, nd, nb_class or 0])
         out[f"{case}_feat"] = acts["backbone"].numpy()                       # [B, h, w, 2048]
         out[f"{case}_pos"] = acts["position_embedding_sine"].numpy()         # [B, h, w, 256]
         out[f"{case}_hs"] = acts["transformer"][0].numpy()                   # [L, B, 100, 256]

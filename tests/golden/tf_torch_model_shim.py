@@ -34,6 +34,7 @@ def set_weights(named):
     STATE["created"] = []
     STATE["outputs"] = {}
     STATE["layers"] = []
+    Layer._counters = {}                    # a fresh Keras session: auto-names restart at 'dense', 'dense_1', ...
 
 
 def _relink():
@@ -65,13 +66,15 @@ class Layer:
     # ---- variable naming: the path of layer names below the root model, as Keras scopes variable names
     def _path(self):
         names, node = [], self
-        while node is not None and node._parent is not None:
-            names.append(node.name)
+        while node is not None:
+            names.append((node.name, type(node).__name__))
             node = node._parent
-        return "/".join(reversed(names))
+        if names[-1][1] == "DETR":          # the layers of the DETR container are re-used at the top level of the functional
+            names.pop()                     # model (detr.py:149-177): their variables carry no 'detr/' prefix
+        return "/".join(n for n, _ in reversed(names))
 
     def add_weight(self, name=None, shape=None, initializer=None, dtype=None, trainable=True):
-        full = (self._path() + "/" + name).lstrip("/")
+        full = self._path() + "/" + name
         assert full in STATE["weights"], f"no injected value for variable {full!r}"
         w = STATE["weights"][full]
         assert tuple(w.shape) == tuple(int(s) for s in shape), (full, tuple(w.shape), tuple(shape))
@@ -119,6 +122,17 @@ class Model(Layer):
             if isinstance(v, Layer) and v.name == name:
                 return v
         raise ValueError(name)
+
+
+class Sequential(Model):
+    def __init__(self, layers=None, name=None):
+        Layer.__init__(self, name=name)
+        self.seq = list(layers or [])
+
+    def call(self, x):
+        for layer in self.seq:
+            x = layer(x)
+        return x
 
 
 def _nchw(x):
@@ -249,7 +263,7 @@ def build():
     keras.Model = Model
     keras.Input = lambda shape=None, **kw: STATE["input"]
     keras.initializers = types.SimpleNamespace(GlorotUniform=lambda *a, **k: None)
-    keras.models = types.SimpleNamespace(Sequential=None)
+    keras.models = types.SimpleNamespace(Sequential=Sequential)
     keras.applications = types.SimpleNamespace(ResNet50=None)
     tf.keras = keras
     return tf, keras, layers

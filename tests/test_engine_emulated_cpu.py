@@ -76,6 +76,33 @@ def test_forward_loss_backward_match_oracle_fp32(emu):
             assert torch.equal(exp, match[l, b])
 
 
+@pytest.mark.parametrize("case", ["a", "b", "ft"])
+def test_engine_forward_vs_reference_code_golden(emu, case):
+    """The product's host side (get_detr_model -> Engine orchestration: layouts, space-to-depth stem, sliding-window GEMM
+    geometry, head wiring, fine-tuning heads) with the C ABI emulated in fp32, against activations produced by the REFERENCE'S
+    OWN networks/*.py executed through get_detr_model() on the TensorFlow shim (tests/golden/make_golden_model.py) with the
+    same seeded weights: equal to fp32 rounding.  Cases: batch 2; odd image sizes; include_top=False + nb_class=3."""
+    import detr_tensorflow_b200 as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    seed, B, H, W, ne, nd, nbc = (int(v) for v in g[f"{case}_meta"])
+    nbc = nbc or None
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd, nb_class=nbc)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=nbc is None, nb_class=nbc, params=P, dropout=0.0, num_encoder_layers=ne,
+                             num_decoder_layers=nd, device="cpu")
+    out = model(img, training=False)
+    t = lambda k: torch.from_numpy(g[f"{case}_{k}"])
+    assert rel(model.engine.feat.view(t("feat").shape), t("feat")) < 1e-5
+    assert rel(out["pred_logits"], t("pred_logits")) < 1e-5 and rel(out["pred_boxes"], t("pred_boxes")) < 1e-5
+    assert len(out["aux"]) == nd - 1
+    for i, a in enumerate(out["aux"]):
+        assert rel(a["pred_logits"], t(f"aux{i}_logits")) < 1e-5 and rel(a["pred_boxes"], t(f"aux{i}_boxes")) < 1e-5
+    if nbc is not None:
+        assert cfg.nlayers == ["cls_layer", "pos_layer"]            # config.add_nlayers, detr.py:103
+
+
 def test_bf16_storage_forward_noise_level(emu):
     import detr_tensorflow_b200 as D
     emu.set_act_dtype(torch.bfloat16)

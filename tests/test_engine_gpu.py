@@ -52,6 +52,29 @@ def test_forward_parity(D, setup):
     assert rel(eng.feat.view(feat.shape), feat) < 3e-2
 
 
+def test_forward_vs_reference_code_golden(D):
+    """The product's forward pass against tests/golden/model_golden.npz case "a": activations produced by the reference's own
+    networks/*.py executed unmodified through get_detr_model() on the TensorFlow shim (tests/golden/make_golden_model.py), with
+    the same seeded weights.  Tolerance: bf16 activation storage (as test_forward_parity)."""
+    import os
+    import numpy as np
+    from oracle import detr_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz"))
+    seed, B, H, W, ne, nd, _ = (int(v) for v in g["a_meta"])
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=ne, num_decoder_layers=nd)
+    out = model(img, training=False)
+    torch.cuda.synchronize()
+    ref = {k: torch.from_numpy(g[f"a_{k}"]) for k in ("feat", "pred_logits", "pred_boxes", "aux0_logits", "aux1_boxes")}
+    assert len(out["aux"]) == nd - 1
+    assert rel(model.engine.feat.view(ref["feat"].shape), ref["feat"]) < 3e-2
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    assert rel(out["aux"][0]["pred_logits"], ref["aux0_logits"]) < 5e-2 and rel(out["aux"][1]["pred_boxes"], ref["aux1_boxes"]) < 3e-2
+
+
 def test_baseline_config_c1_forward_480x640(D):
     """BASELINE.json configs[0] (1 synthetic 480x640 image, forward only) through get_detr_model()/model(): same output dict as
     the CPU oracle run of the same configuration, within the bf16-storage tolerance of test_forward_parity"""

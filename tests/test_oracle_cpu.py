@@ -155,17 +155,19 @@ def test_forward_shapes_and_param_count():
     assert len(out["aux"]) == 5
 
 
-@pytest.mark.parametrize("case", ["a", "b"])
+@pytest.mark.parametrize("case", ["a", "b", "ft"])
 def test_model_forward_vs_reference_code_golden(case):
     """The MODEL part of the oracle against tests/golden/model_golden.npz: activations produced by the reference's own
     detr.py / resnet_backbone.py / transformer.py / custom_layers.py / position_embeddings.py, executed unmodified on a
     torch-backed TensorFlow shim (tests/golden/make_golden_model.py) with these same seeded weights injected by Keras
     variable name.  Pins layer wiring, padding / stride placement, the packed in-projection split, the query scaling, the
     [pos_y, pos_x] sin/cos interleave, the [S,B,256] <-> NHWC transposes and the head stack.  fp32 on both sides:
-    tolerance = accumulation-order noise."""
+    tolerance = accumulation-order noise.  Case "ft" goes through the fine-tuning heads (detr.py:94-114: Keras Dense
+    `cls_layer` + Sequential `pos_layer`, variables pos_layer/dense{,_1,_2}/...)."""
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz"))
-    seed, B, H, W, ne, nd = (int(v) for v in g[f"{case}_meta"])
-    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    seed, B, H, W, ne, nd, nb_class = (int(v) for v in g[f"{case}_meta"])
+    nb_class = nb_class or None                                        # "ft": include_top=False, nb_class=3 -> add_heads_nlayers
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd, nb_class=nb_class)
     img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
     # the reference created exactly these variables (names = Keras layer-name paths) and marks these trainable
     assert sorted(n for n in P if not n.split("/")[-1] in ("weight", "bias", "running_mean", "running_var")
