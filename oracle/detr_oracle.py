@@ -15,13 +15,17 @@ unmodified on stand-ins for the TensorFlow library:
     model_golden.npz); the oracle reproduces every captured activation to ~1e-5
     (tests/test_oracle_cpu.py::test_model_forward_vs_reference_code_golden), and is also
     cross-checked against torchvision resnet50 and F.multi_head_attention_forward;
+  * train-step gradients: the same shim with autograd on -- the gradient of the reference's
+    own get_losses through the reference's own model w.r.t. every trainable variable
+    (make_golden_model.py::train_case); train_step() below matches norm / projection / small
+    tensors of all of them (test_train_step_gradients_vs_reference_code_golden);
   * loss / matcher: detr_tf/loss/*.py + detr_tf/bbox.py on a numpy-backed shim
     (tests/golden/make_golden.py), with the real ``scipy.optimize.linear_sum_assignment``
     (the routine the reference calls, hungarian_matching.py:7,29);
   * inference post-process / input normalisation / pad_labels: make_golden_pipeline.py.
 Still "parity unpinned" (TF library arithmetic, restated from its documentation): Keras
-Adam with per-variable clipnorm, and the dropout random stream (parity is defined in
-inference mode).  Gradients are torch autograd of the pinned forward + loss.
+Adam with per-variable clipnorm, and the dropout random stream (parity is defined with
+dropout off).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/detr_tf).

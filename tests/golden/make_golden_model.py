@@ -41,6 +41,66 @@ class Cfg:
         self.nlayers = [l.name for l in layers]
 
 
+TRAIN = (21, 2, 96, 128, 1, 2, 4)          # seed, batch, H, W, encoder layers, decoder layers, targets per image
+
+
+def train_case():
+    """Gradient of the reference's own loss through the reference's own model: get_detr_model() output (autograd graph alive)
+    -> detr_tf/loss/loss.py get_losses (Hungarian matching through the real scipy) -> torch.autograd.grad w.r.t. every
+    variable the reference marks trainable (stand-in for tf.GradientTape, training.py:17-23; dropout is the identity: TF's
+    random stream cannot be reproduced, the gradient arithmetic is what is pinned)."""
+    from detr_tf.loss import hungarian_matching as ref_hm
+    from detr_tf.loss import loss as ref_loss
+    seed, B, H, W, ne, nd, n_t = TRAIN
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    t_bbox, t_class = O.synthetic_targets(B, n=n_t, seed=seed)
+    shim.set_weights({k: v.float() for k, v in P.items()}, autograd=True)
+    x = shim.set_input(img)
+    cfg = Cfg()
+    cfg.background_class = 91
+    model = ref_detr.get_detr_model(cfg, include_top=True, num_decoder_layers=nd, num_encoder_layers=ne)
+    res = model(x)
+    captured = []
+    orig = ref_hm.np_tf_linear_sum_assignment
+
+    def spy(matrix):
+        r = orig(matrix)
+        captured.append((np.array(matrix, copy=True), np.asarray(r[0]).copy(), np.asarray(r[1]).copy()))
+        return r
+    ref_hm.np_tf_linear_sum_assignment = spy
+    try:
+        total, losses = ref_loss.get_losses(res, shim.as_tf(t_bbox.float()), shim.as_tf(t_class), cfg)
+    finally:
+        ref_hm.np_tf_linear_sum_assignment = orig
+    names = sorted(n for n, _, t in shim.STATE["created"] if t)
+    grads = torch.autograd.grad(total, [shim.STATE["variables"][n] for n in names], allow_unused=True)
+    # assignments in call order: main output (all images), then aux 0, 1, ... -> [L, B, Q], layer order aux.., main last
+    Q = 100
+    match = -np.ones((nd, B, Q), np.int64)
+    assert len(captured) == nd * B
+    for i, (_, rows, cols) in enumerate(captured):
+        layer = (nd - 1) if i < B else (i // B - 1)
+        match[layer, i % B, rows] = cols
+    out = {"train_meta": np.array(TRAIN), "train_t_bbox": t_bbox.numpy(), "train_t_class": t_class.numpy(),
+           "train_total": np.float32(float(total)), "train_match": match,
+           "train_loss_keys": np.array(sorted(losses)), "train_loss_values": np.array([float(losses[k]) for k in sorted(losses)], np.float32),
+           "train_names": np.array(names)}
+    norms, projs = [], []
+    for i, (n, g) in enumerate(zip(names, grads)):
+        g = torch.zeros_like(P[n]).float() if g is None else g.detach().float()
+        r = torch.randn(g.shape, generator=torch.Generator().manual_seed(1000 + i))
+        norms.append(float(g.norm()))
+        projs.append(float((g * r).sum()))
+        if g.numel() <= 2048 or n in ("backbone/conv1/kernel", "class_embed/kernel"):
+            out["train_grad/" + n] = g.numpy()
+    out["train_grad_norms"] = np.array(norms, np.float64)
+    out["train_grad_projs"] = np.array(projs, np.float64)
+    print("train: total", float(total), "variables", len(names), "unused", sum(g is None for g in grads),
+          "full gradients stored", sum(k.startswith("train_grad/") for k in out))
+    return out
+
+
 def main():
     torch.manual_seed(0)
     out = {}
@@ -48,12 +108,12 @@ def main():
         P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd, nb_class=nb_class)
         img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
         shim.set_weights({k: v.float() for k, v in P.items()})
-        shim.set_input(img)
+        x = shim.set_input(img)
         with torch.no_grad():
             cfg = Cfg()
             model = ref_detr.get_detr_model(cfg, include_top=nb_class is None, nb_class=nb_class, num_decoder_layers=nd,
                                             num_encoder_layers=ne)
-            res = model(img)
+            res = model(x)
         if nb_class is not None:
             assert cfg.nlayers == ["cls_layer", "pos_layer"]
         created = {n: s for n, s, _ in shim.STATE["created"]}
@@ -74,6 +134,7 @@ def main():
         out[f"{case}_trainable"] = np.array(trainable)
         print(case, "feat", out[f"{case}_feat"].shape, "hs", out[f"{case}_hs"].shape, "aux", len(res["aux"]),
               "variables", len(created), "trainable", len(trainable))
+    out.update(train_case())
     np.savez_compressed(os.path.join(HERE, "model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "model_golden.npz"), os.path.getsize(os.path.join(HERE, "model_golden.npz")), "bytes")
 

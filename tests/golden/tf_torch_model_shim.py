@@ -21,16 +21,43 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-STATE = {"input": None, "weights": {}, "created": [], "outputs": {}, "layers": []}
+STATE = {"input": None, "weights": {}, "created": [], "outputs": {}, "layers": [], "autograd": False, "variables": {}}
+
+
+class T(torch.Tensor):
+    """TensorFlow tensors are immutable: `x += y` rebinds the name to a new tensor.  The reference relies on it (e.g.
+    transformer.py:169 `source += ...` after `source` was fed to the attention); torch's in-place `+=` would overwrite values
+    that autograd saved for the backward pass, so the in-place operators are made out-of-place."""
+
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __itruediv__(self, other):
+        return self / other
+
+
+def as_tf(x):
+    return x.as_subclass(T)
 
 
 def set_input(x):
-    STATE["input"] = x
+    STATE["input"] = as_tf(x)
+    return STATE["input"]
 
 
-def set_weights(named):
-    """name path (e.g. 'backbone/layer1/0/conv1/kernel') -> float32 torch tensor; every add_weight() must find its entry"""
+def set_weights(named, autograd=False):
+    """name path (e.g. 'backbone/layer1/0/conv1/kernel') -> float32 torch tensor; every add_weight() must find its entry.
+    autograd=True: trainable variables become leaves that require grad (STATE['variables'][name]) so that the gradient of a
+    loss computed by the reference's code can be taken with torch.autograd (stand-in for tf.GradientTape)."""
     STATE["weights"] = dict(named)
+    STATE["autograd"] = bool(autograd)
+    STATE["variables"] = {}
     STATE["created"] = []
     STATE["outputs"] = {}
     STATE["layers"] = []
@@ -79,7 +106,11 @@ class Layer:
         w = STATE["weights"][full]
         assert tuple(w.shape) == tuple(int(s) for s in shape), (full, tuple(w.shape), tuple(shape))
         STATE["created"].append((full, tuple(w.shape), bool(trainable)))
-        return w.clone()
+        v = as_tf(w.detach().clone())
+        if STATE["autograd"] and trainable:
+            v.requires_grad_(True)
+        STATE["variables"][full] = v
+        return v
 
     def build(self, input_shape):
         pass
@@ -254,6 +285,43 @@ def build():
     tf.reduce_mean = lambda x, axis=None: x.mean() if axis is None else x.mean(axis)
     tf.math = types.SimpleNamespace(sin=torch.sin, cos=torch.cos, rsqrt=torch.rsqrt, cumsum=lambda x, axis=0: torch.cumsum(x, dim=axis))
     tf.nn = types.SimpleNamespace(softmax=lambda x, axis=-1: torch.softmax(x, dim=axis))
+
+    # ---- the ops of the loss path (detr_tf/loss/*.py, detr_tf/bbox.py), differentiable where TF's are
+    _t = lambda x: x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+    tf.cast = lambda x, dt: _t(x).to(dt)
+    tf.abs = lambda x: _t(x).abs()
+    tf.clip_by_value = lambda x, lo, hi: _t(x).clamp(float(lo), float(hi))
+    tf.reduce_sum = lambda x, axis=None: _t(x).sum() if axis is None else _t(x).sum(axis)
+    tf.reduce_max = lambda x, axis=None: _t(x).max() if axis is None else _t(x).max(axis).values
+    tf.argmax = lambda x, axis=None: _t(x).argmax(axis)
+    tf.where = lambda c: torch.nonzero(_t(c))                         # single-argument form: coordinates of the true elements
+    tf.constant = lambda v, dtype=None: torch.as_tensor(v, dtype=dtype)
+    tf.gather = lambda params, indices, axis=0: torch.index_select(_t(params), axis, _t(indices).long().reshape(-1))
+
+    def slice_(x, begin, size):
+        idx = []
+        for b, n in zip(begin, size):
+            b, n = int(b), int(n)
+            idx.append(slice(b, None) if n == -1 else slice(b, b + n))
+        return x[tuple(idx)]
+    tf.slice = slice_
+
+    def norm(x, ord=2, axis=None):
+        assert ord == 1
+        return _t(x).abs().sum(axis)
+    tf.norm = norm
+
+    def numpy_function(fn, inp, Tout):
+        res = fn(*[_t(i).detach().cpu().numpy() for i in inp])
+        return [torch.as_tensor(np.asarray(r)).to(t) for r, t in zip(res, Tout)]
+    tf.numpy_function = numpy_function
+    tf.nn.relu = torch.relu
+    tf.nn.sparse_softmax_cross_entropy_with_logits = lambda labels, logits: F.cross_entropy(logits, _t(labels).long(), reduction="none")
+    tf.math.minimum, tf.math.maximum = torch.minimum, torch.maximum
+    tf.math.abs, tf.math.log = torch.abs, torch.log
+    tf.linalg = types.SimpleNamespace(diag_part=lambda x: torch.diagonal(x))
+    if not hasattr(np, "bool"):                                       # hungarian_matching.py:37,41 uses the removed alias
+        np.bool = bool
 
     keras = types.ModuleType("tensorflow.keras")
     layers = types.ModuleType("tensorflow.keras.layers")

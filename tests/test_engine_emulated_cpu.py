@@ -103,6 +103,47 @@ def test_engine_forward_vs_reference_code_golden(emu, case):
         assert cfg.nlayers == ["cls_layer", "pos_layer"]            # config.add_nlayers, detr.py:103
 
 
+def test_engine_train_step_gradients_vs_reference_code_golden(emu):
+    """The product's hand-written backward chain (Engine.loss + Engine.backward on the fp32-emulated C ABI) against the gradient
+    of the REFERENCE'S OWN loss code through the REFERENCE'S OWN model code (make_golden_model.py::train_case): same Hungarian
+    assignment, same total / per-term losses, and for every trainable variable the gradient norm, a seeded random projection
+    and the full tensor of the small ones."""
+    import detr_tensorflow_b200 as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    seed, B, H, W, ne, nd, n_t = (int(v) for v in g["train_meta"])
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    tb, tc = torch.from_numpy(g["train_t_bbox"]), torch.from_numpy(g["train_t_class"])
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=ne, num_decoder_layers=nd, device="cpu", params=P, dropout=0.0)
+    model(img, training=False)
+    eng = model.engine
+    eng.set_targets(tb, tc)
+    eng.zero_grads()
+    eng.loss(91)
+    total, log = eng.loss_dict()
+    eng.backward()
+    assert torch.equal(eng.a["match"].view(nd, B, 100).long(), torch.from_numpy(g["train_match"]))      # bit-exact assignment
+    assert abs(float(total) - float(g["train_total"])) < 1e-4 * abs(float(g["train_total"]))
+    for k, v in zip(g["train_loss_keys"].tolist(), g["train_loss_values"].tolist()):
+        assert abs(float(log[k]) - v) < 1e-4 + 1e-4 * abs(v), (k, float(log[k]), v)
+    grads = eng.export_grads()
+    names = g["train_names"].tolist()
+    assert set(names) - set(grads) == {"query_embed/kernel"} and set(grads) <= set(names)
+    for i, n in enumerate(names):
+        if n not in grads:
+            continue
+        gr = grads[n].float()
+        ref_norm, ref_proj = float(g["train_grad_norms"][i]), float(g["train_grad_projs"][i])
+        r = torch.randn(gr.shape, generator=torch.Generator().manual_seed(1000 + i))
+        assert abs(float(gr.norm()) - ref_norm) <= 2e-3 * ref_norm + 1e-8, (n, float(gr.norm()), ref_norm)
+        assert abs(float((gr * r).sum()) - ref_proj) <= 2e-3 * ref_norm * gr.numel() ** 0.5 + 1e-8, (n, float((gr * r).sum()), ref_proj)
+        if "train_grad/" + n in g:
+            full = torch.from_numpy(g["train_grad/" + n])
+            assert float((gr - full).abs().max()) <= 2e-3 * float(full.abs().max()) + 1e-8, n
+
+
 def test_bf16_storage_forward_noise_level(emu):
     import detr_tensorflow_b200 as D
     emu.set_act_dtype(torch.bfloat16)

@@ -193,6 +193,43 @@ def test_model_forward_vs_reference_code_golden(case):
         close(f"aux{i} boxes", a["pred_boxes"], g[f"{case}_aux{i}_boxes"], 5e-5)
 
 
+def test_train_step_gradients_vs_reference_code_golden():
+    """training.py:9-25 restated (forward -> get_losses -> gradients of every trainable variable) against the gradient of the
+    REFERENCE'S OWN loss code (loss.py / hungarian_matching.py / bbox.py, real scipy) through the REFERENCE'S OWN model code,
+    taken with torch.autograd on the TensorFlow shim (tests/golden/make_golden_model.py::train_case).  Every trainable
+    variable: gradient norm, a seeded random projection, and the full tensor for the 42 small ones."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz"))
+    seed, B, H, W, ne, nd, n_t = (int(v) for v in g["train_meta"])
+    P = O.init_params(seed=seed, num_encoder_layers=ne, num_decoder_layers=nd)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    tb, tc = torch.from_numpy(g["train_t_bbox"]), torch.from_numpy(g["train_t_class"])
+    match = torch.from_numpy(g["train_match"])
+    # the oracle's own Hungarian step finds the reference's assignment ...
+    out, total, log, grads = O.train_step(P, img, tb, tc, num_encoder_layers=ne, num_decoder_layers=nd)
+    _, idx = O.get_detr_losses(out["pred_logits"], out["pred_boxes"], tb, tc, 91, return_indices=True)
+    _, idx_ref = O.get_detr_losses(out["pred_logits"], out["pred_boxes"], tb, tc, 91, return_indices=True, match_override=match[nd - 1])
+    assert all(torch.equal(a, b) for a, b in zip(idx, idx_ref))
+    # ... and under it the same losses and gradients
+    assert abs(float(total) - float(g["train_total"])) < 2e-5 * abs(float(g["train_total"]))
+    for k, v in zip(g["train_loss_keys"].tolist(), g["train_loss_values"].tolist()):
+        assert abs(float(log[k]) - v) < 2e-5 * max(abs(v), 1e-3), (k, float(log[k]), v)
+    names = g["train_names"].tolist()
+    # variables the reference marks trainable == the oracle's three optimizer groups + query_embed (trainable, but called
+    # outside the functional graph, detr.py:175 -> reached by no optimizer: optimizers.py:10-43, SURVEY 3.1)
+    assert set(names) - set(grads) == {"query_embed/kernel"} and set(grads) <= set(names)
+    for i, n in enumerate(names):
+        if n not in grads:
+            continue
+        gr = grads[n].float()
+        ref_norm, ref_proj = float(g["train_grad_norms"][i]), float(g["train_grad_projs"][i])
+        r = torch.randn(gr.shape, generator=torch.Generator().manual_seed(1000 + i))
+        assert abs(float(gr.norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-9, (n, float(gr.norm()), ref_norm)
+        assert abs(float((gr * r).sum()) - ref_proj) <= 1e-3 * ref_norm * gr.numel() ** 0.5 + 1e-9, (n, float((gr * r).sum()), ref_proj)
+        if "train_grad/" + n in g:
+            full = torch.from_numpy(g["train_grad/" + n])
+            assert float((gr - full).abs().max()) <= 1e-3 * float(full.abs().max()) + 1e-9, n
+
+
 def test_baseline_config_c1_forward_480x640_cpu():
     """BASELINE.json configs[0]: DETR-R50 forward on 1 synthetic 480x640 image on the CPU (plumbing, no GPU): the reference-shaped
     output dict with [1,100,92] logits, [1,100,4] boxes in [0,1] and 5 aux entries; feature map 15x20 (S = 300)."""
