@@ -101,6 +101,47 @@ def train_case():
     return out
 
 
+def accumulate_case():
+    """optimizers.py:137-163 (aggregate_grad_and_apply) executed as is, with a recording stand-in for the Keras optimizer:
+    which steps zero the accumulator, which apply, and what is applied (the SUM of the micro-step gradients, not the mean),
+    for target_batch // batch_size = 3 over 7 steps, for no accumulation, and for a group whose train_<group> flag is off."""
+    from detr_tf import optimizers as ref_opt
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def apply_gradients(self, pairs):
+            self.calls.append([float(g.sum()) for g, _ in pairs])
+
+    class Cfg2:
+        batch_size = 2
+        train_backbone = True
+        train_transformers = False
+
+    out = {}
+    for label, target_batch in (("acc3", 6), ("none", None)):
+        cfg = Cfg2()
+        cfg.target_batch = target_batch
+        rec = {"backbone": Recorder(), "transformers": Recorder()}
+        variables = [torch.zeros(3), torch.zeros(2, 2)]
+        optimizers = {"backbone_optimizer": rec["backbone"], "backbone_variables": variables,
+                      "transformers_optimizer": rec["transformers"], "transformers_variables": variables}
+        applied_at = []
+        for step in range(7):
+            grads = [torch.full((3,), float(step + 1)), torch.full((2, 2), 10.0 * (step + 1))]
+            for name in ("backbone", "transformers"):
+                before = len(rec[name].calls)
+                ref_opt.aggregate_grad_and_apply(name, optimizers, grads, step, cfg)
+                if len(rec[name].calls) > before:
+                    applied_at.append((step, name))
+        assert not rec["transformers"].calls                                  # train_transformers = False: never applied
+        out[f"accum_{label}_steps"] = np.array([s for s, _ in applied_at])
+        out[f"accum_{label}_sums"] = np.array(rec["backbone"].calls, np.float64)     # [n_applies, 2]: sum over each gradient tensor
+        print("accumulate", label, "applied at", out[f"accum_{label}_steps"].tolist(), out[f"accum_{label}_sums"].tolist())
+    return out
+
+
 def main():
     torch.manual_seed(0)
     out = {}
@@ -135,6 +176,7 @@ def main():
         print(case, "feat", out[f"{case}_feat"].shape, "hs", out[f"{case}_hs"].shape, "aux", len(res["aux"]),
               "variables", len(created), "trainable", len(trainable))
     out.update(train_case())
+    out.update(accumulate_case())
     np.savez_compressed(os.path.join(HERE, "model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "model_golden.npz"), os.path.getsize(os.path.join(HERE, "model_golden.npz")), "bytes")
 

@@ -144,6 +144,38 @@ def test_engine_train_step_gradients_vs_reference_code_golden(emu):
             assert float((gr - full).abs().max()) <= 2e-3 * float(full.abs().max()) + 1e-8, n
 
 
+def test_gradient_accumulation_cadence_vs_reference_code_golden(emu):
+    """aggregate_grad_and_apply against the reference's own optimizers.py:137-163 executed with a recording optimizer
+    (make_golden_model.py::accumulate_case): zero at step % k == 0, SUM of the micro-step gradients, apply at (step+1) % k == 0,
+    nothing for a group whose train_<group> flag is off; k = 3 over 7 steps, and no accumulation."""
+    import detr_tensorflow_b200 as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    for label, target_batch in (("acc3", 6), ("none", None)):
+        cfg = D.TrainingConfig()
+        cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 2, target_batch
+        cfg.train_backbone, cfg.train_transformers = True, False
+        model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+        opt = D.setup_optimizers(model, cfg)
+        eng = model.engine
+        lo, hi = eng.group_range["backbone"]
+        calls = []
+        eng.apply_group = lambda name, src, clip: calls.append((name, float(src[lo:lo + 3].sum()), float(src[lo + 3:lo + 7].sum())))
+        steps = []
+        for step in range(7):
+            eng.grads.zero_()
+            eng.grads[lo:lo + 3] = float(step + 1)
+            eng.grads[lo + 3:lo + 7] = 10.0 * (step + 1)
+            for name in ("backbone", "transformers"):
+                n0 = len(calls)
+                D.optimizers.aggregate_grad_and_apply(name, opt, None, step, cfg)
+                if len(calls) > n0:
+                    steps.append(step)
+        assert all(c[0] == "backbone" for c in calls)
+        assert steps == g[f"accum_{label}_steps"].tolist()
+        np.testing.assert_allclose(np.array([c[1:] for c in calls]), g[f"accum_{label}_sums"], rtol=1e-6)
+
+
 def test_bf16_storage_forward_noise_level(emu):
     import detr_tensorflow_b200 as D
     emu.set_act_dtype(torch.bfloat16)
