@@ -169,7 +169,8 @@ __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix
     out[i] = make_uint2(pack_bf16x2(r, g), pack_bf16x2(b, 0.f));
 }
 // space-to-depth(2) of the fp32 NHWC3 image: out[b, y, x, (ry*2+rx)*3 + c] = img[b, 2y+ry, 2x+rx, c] (0 outside, 4 zero pad channels)
-// -> the 7x7 / stride-2 stem becomes a dense 4x4 / stride-1 convolution over 16-channel pixels (32 B: one TMA im2col row)
+// -> the 7x7 / stride-2 stem becomes a dense 4x4 / stride-1 convolution over 16-channel pixels (32 B: four consecutive pixels are
+//    one 128-byte row of the sliding-window GEMM operand, see detrb_igemm_t.a_kb_rows)
 __global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP)
 {
     pdl_trigger();

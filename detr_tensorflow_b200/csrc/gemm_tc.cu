@@ -4,13 +4,17 @@
 // mbarriers (tcgen05.commit), the epilogue warps read the accumulator with tcgen05.ld and apply the same fused epilogue as
 // igemm.cu (bias / residual / ReLU / ReLU-mask / sigmoid / dropout / bf16+fp32 stores / strided scatter-accumulate).
 //
-// Used by detrb_igemm for every *plain* GEMM of the train step (1x1 stride-1 convolutions and their data gradients,
-// input_proj, all Linear layers of the transformer and the heads) -- ~57 % of the model's FLOPs.  Gathered convolutions
-// (3x3, 7x7, strided) stay on igemm.cu until their TMA-im2col variant lands.
+// Used by detrb_igemm for every GEMM-shaped launch of the train step: plain GEMMs (1x1 stride-1 convolutions and their data
+// gradients, input_proj, all Linear layers of the transformer and the heads), implicit-GEMM convolutions through TMA im2col
+// tensor maps (3x3, strided, transposed / data-gradient; stride-2 data gradients as four parity-class sub-convolutions), and
+// the 7x7 stem as a sliding-window GEMM over the zero-padded space-to-depth image (detrb_igemm_t.a_kb_rows: the A tensor map
+// has overlapping 128-byte rows).  Only unaligned shapes (the N = 92 / 4 heads) fall through to igemm.cu (mma.sync).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane
-// quarter = warp_id % 4).  BN x STAGES are sized so that 2-3 CTAs are co-resident per SM (<= 96 KB smem, <= 128 TMEM
-// columns each): one CTA's epilogue overlaps another's main loop -- the k-loops of this model are short (1..32 blocks).
+// Two kernels.  gemm_tc_kernel: one output tile per CTA; warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  BN x STAGES are sized so that 3-5 CTAs are
+// co-resident per SM (the BN = 64 variants are capped at 64 registers): one CTA's epilogue overlaps another's loads -- the
+// k-loops of the HBM-bound layers are 1..4 blocks long.  gemm_tcp_kernel (further down): persistent, one CTA per SM, 128x256
+// tiles, for the tensor-bound shapes.  dispatch_tc / dispatch_tcp hold the measured policy.
 #include "tc_common.cuh"
 
 #ifdef DETRB_TRACE

@@ -696,7 +696,7 @@ class Engine:
         d, dff, S, Q, M, Mq, Hh = self.d, self.dff, self.S, self.Q, self.M, self.Mq, self.H
         scale = float(d // Hh) ** -0.5
         # ---------------- backbone (resnet_backbone.py:20-32)
-        # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels (tcgen05 im2col kernel)
+        # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels = a sliding-window GEMM
         HP, WP = self.hw_pad
         if self.u8_input:                     # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
             ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP)
