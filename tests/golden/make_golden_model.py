@@ -142,6 +142,24 @@ def accumulate_case():
     return out
 
 
+def resnet101_case():
+    """BASELINE configs[3] uses a ResNet-101 backbone: networks/resnet_backbone.py:52-66 (ResNet101Backbone, 23 bottlenecks in
+    layer3) executed on the shim.  (The reference's DETR class always instantiates ResNet50Backbone, detr.py:31; the deeper
+    backbone is selected in the product by get_detr_model(..., backbone='resnet101').)"""
+    from detr_tf.networks import resnet_backbone as ref_rb
+    seed = 31
+    P = O.init_params(seed=seed, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1)
+    img = torch.randn(1, 64, 96, 3, generator=torch.Generator().manual_seed(seed))
+    shim.set_weights({k: v.float() for k, v in P.items() if k.startswith("backbone/")})
+    with torch.no_grad():
+        net = ref_rb.ResNet101Backbone(name="backbone")
+        feat = net(shim.as_tf(img))
+    created = {n for n, _, _ in shim.STATE["created"]}
+    assert created == {k for k in P if k.startswith("backbone/")}, len(created)
+    print("resnet101: feat", tuple(feat.shape), "variables", len(created))
+    return {"r101_meta": np.array([seed, 1, 64, 96]), "r101_feat": feat.numpy()}
+
+
 def main():
     torch.manual_seed(0)
     out = {}
@@ -177,6 +195,7 @@ def main():
               "variables", len(created), "trainable", len(trainable))
     out.update(train_case())
     out.update(accumulate_case())
+    out.update(resnet101_case())
     np.savez_compressed(os.path.join(HERE, "model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "model_golden.npz"), os.path.getsize(os.path.join(HERE, "model_golden.npz")), "bytes")
 

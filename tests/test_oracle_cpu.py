@@ -193,6 +193,18 @@ def test_model_forward_vs_reference_code_golden(case):
         close(f"aux{i} boxes", a["pred_boxes"], g[f"{case}_aux{i}_boxes"], 5e-5)
 
 
+def test_resnet101_backbone_vs_reference_code_golden():
+    """resnet_backbone.py:52-66 (ResNet101Backbone, the C4 configuration's backbone) executed on the shim vs the oracle"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz"))
+    seed, B, H, W = (int(v) for v in g["r101_meta"])
+    P = O.init_params(seed=seed, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    with torch.no_grad():
+        feat = O.backbone_forward(P, img, backbone="resnet101")
+    ref = torch.from_numpy(g["r101_feat"])
+    assert feat.shape == ref.shape and float((feat - ref).abs().max()) < 5e-5 * float(ref.abs().max())
+
+
 def test_train_step_gradients_vs_reference_code_golden():
     """training.py:9-25 restated (forward -> get_losses -> gradients of every trainable variable) against the gradient of the
     REFERENCE'S OWN loss code (loss.py / hungarian_matching.py / bbox.py, real scipy) through the REFERENCE'S OWN model code,
