@@ -103,6 +103,23 @@ def test_engine_forward_vs_reference_code_golden(emu, case):
         assert cfg.nlayers == ["cls_layer", "pos_layer"]            # config.add_nlayers, detr.py:103
 
 
+def test_engine_resnet101_backbone_vs_reference_code_golden(emu):
+    """get_detr_model(..., backbone='resnet101') (the BASELINE configs[3] backbone) on the fp32-emulated ABI against the
+    reference's ResNet101Backbone (resnet_backbone.py:52-66) executed on the shim"""
+    import detr_tensorflow_b200 as D
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    seed, B, H, W = (int(v) for v in g["r101_meta"])
+    P = O.init_params(seed=seed, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1)
+    img = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed))
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, backbone="resnet101", num_encoder_layers=1, num_decoder_layers=1, device="cpu",
+                             params=P, dropout=0.0)
+    model(img, training=False)
+    ref = torch.from_numpy(g["r101_feat"])
+    assert rel(model.engine.feat.view(ref.shape), ref) < 1e-5
+
+
 def test_engine_train_step_gradients_vs_reference_code_golden(emu):
     """The product's hand-written backward chain (Engine.loss + Engine.backward on the fp32-emulated C ABI) against the gradient
     of the REFERENCE'S OWN loss code through the REFERENCE'S OWN model code (make_golden_model.py::train_case): same Hungarian
