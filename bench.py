@@ -466,7 +466,7 @@ def main():
                        "cuda_graph": not args.no_graph, "targets_per_image": 20},
             "clocks": clocks, "gpu_launches": int(eng.launches_per_step * K),
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back",
+                    "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back (on_step hook -> float(); fit calls the hook of step i after step i+1 is enqueued)",
                     "passes_img_per_s": [world * B * Ke / t for t in passes], "reported": "best of the two passes",
                     "cpu_affinity": ("bound to the GPU-local CPUs (NVML affinity): " + str(len(bound)) + " cpus") if bound else "unchanged"},
             "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,

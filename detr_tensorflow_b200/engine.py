@@ -833,16 +833,19 @@ class Engine:
                      a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32)
         self._mark("matcher_loss")
 
-    def loss_dict(self):
-        """36 scalars with the reference's keys (loss.py:172-179; aux layer i -> suffix _i, main = last layer)."""
+    def loss_dict(self, snapshot=False):
+        """36 scalars with the reference's keys (loss.py:172-179; aux layer i -> suffix _i, main = last layer).
+        The scalars are views of the engine's resident loss buffers, overwritten by the next step; snapshot=True returns views of
+        a device copy instead (two small device-to-device copies), safe to read after later steps were enqueued."""
         a, L = self.a, self.ndec
+        losses, total = (a["losses"].clone(), a["total"].clone()) if snapshot else (a["losses"], a["total"])
         names = ("label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss")
         out = OrderedDict()
         for l in [L - 1] + list(range(L - 1)):
             suf = "" if l == L - 1 else f"_{l}"
             for k, n in enumerate(names):
-                out[n + suf] = a["losses"][l, k]
-        return a["total"][0], out
+                out[n + suf] = losses[l, k]
+        return total[0], out
 
     # ------------------------------------------------------------------------------------------ backward
     def zero_grads(self):

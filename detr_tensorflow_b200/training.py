@@ -48,7 +48,7 @@ def run_train_step(model, images, t_bbox, t_class, optimizers, config):
     # forward + losses + backward + gradient all-reduce is captured once per input shape as a CUDA graph and replayed
     eng.grads_step(int(config.background_class), 1.0 / gradient_aggregate, use_graph=getattr(config, "use_cuda_graph", True))
     m_outputs = eng.outputs()
-    total_loss, log = eng.loss_dict()
+    total_loss, log = eng.loss_dict(snapshot=True)     # like the reference's fresh tensors: still this step's after the next one ran
     log = dict(log)
     gradient_steps = gather_gradient(model, optimizers, total_loss, None, config, log)
     return m_outputs, total_loss, log, gradient_steps
@@ -123,8 +123,11 @@ class _Prefetcher:
 def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None):
     """training.py:35-65 -- one epoch.  `train_dt`: iterable of (images[B,H,W,3] f32, t_bbox[B,100,4] f32,
     t_class[B,100,1] i64) (numpy arrays or torch tensors, host or device).  Extension: `on_step(step, total_loss, log)` is
-    called after every step (the reference only prints every 100 steps)."""
+    called once per step, in order (the reference only prints every 100 steps).  The call for step i is made after step i+1 has
+    been enqueued (and after the loop for the last step): a hook that reads the loss back -- a host sync -- then waits for a step
+    that is already finishing while the GPU works on the next one, instead of leaving the GPU idle until the host comes back."""
     t = None
+    pending = None
     for epoch_step, (images, t_bbox, t_class) in enumerate(_Prefetcher(train_dt, model.engine.device)):
         m_outputs, total_loss, log, gradient_steps = run_train_step(model, images, t_bbox, t_class, optimizers, config)
         if config.log:
@@ -133,7 +136,9 @@ def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None
             aggregate_grad_and_apply(name, optimizers, gradient_steps[name]["gradients"], epoch_step, config)
         model.engine._ensure_weights()      # one refresh of the bf16 weight copies for all groups, enqueued before any host sync
         if on_step is not None:
-            on_step(epoch_step, total_loss, log)
+            if pending is not None:
+                on_step(*pending)
+            pending = (epoch_step, total_loss, log)
         if epoch_step % 100 == 0:
             t = t if t is not None else time.time()
             elapsed = time.time() - t
@@ -141,6 +146,8 @@ def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None
                   f"giou : [{float(log['giou_loss']):.2f}] \t l1 : [{float(log['l1_loss']):.2f}] \t time : [{elapsed:.2f}]")
             t = time.time()
         config.global_step += 1
+    if pending is not None:
+        on_step(*pending)
 
 
 def eval(model, valid_dt, config, class_name, evaluation_step=200):

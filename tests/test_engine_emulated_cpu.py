@@ -277,6 +277,55 @@ def test_optimizer_step_split_around_the_stem_gradient(emu):
     assert res[0][2][:2].tolist() == [2, 2]
 
 
+def test_fit_on_step_hook_is_deferred_by_one_step_with_snapshot_values(emu, capsys):
+    """fit() calls on_step(i) after step i+1 has been enqueued (a loss read-back then does not idle the GPU): every step is still
+    reported exactly once, in order, with ITS OWN loss -- run_train_step returns snapshots, not views of the live loss buffers."""
+    import detr_tensorflow_b200 as D
+    P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
+    _, img2, tb2, tc2 = _setup(B=1, H=32, W=48, n=4, seed=2)
+    batches = [(img, tb, tc), (img2, tb2, tc2), (img, tb, tc)]
+
+    def make():
+        cfg = D.TrainingConfig()
+        cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 1, None
+        cfg.train_backbone, cfg.train_transformers = True, True
+        cfg.backbone_lr, cfg.transformers_lr = 1e-3, 1e-2
+        model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+        return cfg, model, D.setup_optimizers(model, cfg)
+    # reference sequence: one step at a time, values read immediately
+    cfg, model, opt = make()
+    expect = []
+    for step, (im, b_, c_) in enumerate(batches):
+        _, total, log, gsteps = D.training.run_train_step(model, im, b_, c_, opt, cfg)
+        expect.append((step, float(total), float(log["label_cost"]), float(log["l1_loss_0"])))
+        held = (total, log["giou_loss"])
+        for name in gsteps:
+            D.optimizers.aggregate_grad_and_apply(name, opt, gsteps[name]["gradients"], step, cfg)
+    # the values returned for the last step are snapshots: another step does not change them
+    before = (float(held[0]), float(held[1]))
+    D.training.run_train_step(model, img2, tb2, tc2, opt, cfg)
+    assert (float(held[0]), float(held[1])) == before
+    # fit: hook order, count and values
+    cfg, model, opt = make()
+    seen, enq = [], []
+    orig = D.training.run_train_step
+
+    def spy(*a, **k):
+        enq.append(len(seen))                              # how many hooks had run when this step was enqueued
+        return orig(*a, **k)
+    D.training.run_train_step = spy
+    try:
+        D.training.fit(model, batches, opt, cfg, 0, None,
+                       on_step=lambda s, t, l: seen.append((s, float(t), float(l["label_cost"]), float(l["l1_loss_0"]))))
+    finally:
+        D.training.run_train_step = orig
+    assert enq == [0, 0, 1]                                # hook i runs after step i+1 was enqueued
+    assert [x[0] for x in seen] == [0, 1, 2]
+    for a, b in zip(seen, expect):
+        assert a[0] == b[0] and all(abs(x - y) <= 1e-6 * abs(y) for x, y in zip(a[1:], b[1:])), (a, b)
+    assert len({x[1] for x in seen}) == 3                  # three different losses (the optimizer moved, the batches differ)
+
+
 def test_fit_loop_runs(emu, capsys):
     import detr_tensorflow_b200 as D
     P, img, tb, tc = _setup(B=1, H=32, W=48, n=3)
