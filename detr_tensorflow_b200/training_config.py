@@ -5,26 +5,36 @@ import argparse
 import os
 
 
+# flag -> (kind, default, help); kinds: "path" (optional str), "int", "float", "switch" (store_true)
+_FLAGS = (
+    ("data_dir", "path", None, "dataset directory"),
+    ("img_dir", "path", None, "image directory, relative to data_dir"),
+    ("ann_file", "path", None, "annotation file, relative to data_dir"),
+    ("ann_dir", "path", None, "annotation directory, relative to data_dir"),
+    ("background_class", "int", 0, "index of the background class"),
+    ("train_backbone", "switch", False, "update the backbone group"),
+    ("train_transformers", "switch", False, "update the transformers group"),
+    ("train_nlayers", "switch", False, "update the fine-tuning layers"),
+    ("finetuning", "switch", False, "load model weights before training"),
+    ("batch_size", "int", 1, "images per step"),
+    ("gradient_norm_clipping", "float", 0.1, "per-variable clipnorm"),
+    ("target_batch", "int", None, "accumulate gradients until target_batch images were seen"),
+    ("backbone_lr", "float", 1e-5, "learning rate of the backbone group"),
+    ("transformers_lr", "float", 1e-4, "learning rate of the transformers group"),
+    ("nlayers_lr", "float", 1e-4, "learning rate of the fine-tuning layers"),
+    ("log", "switch", False, "log to wandb (hook only)"),
+)
+
+
 def training_config_parser():
-    """training_config.py:6-38 (the reference declares the lr flags as type=bool, :31-33 -- a bug; floats here)."""
+    """The command-line flags of training_config.py:6-38, same names and defaults (the reference declares the three lr flags
+    as type=bool, :31-33 -- a bug; floats here)."""
     parser = argparse.ArgumentParser()
-    parser.add_argument("--data_dir", type=str, required=False, help="Path to the dataset directory")
-    parser.add_argument("--img_dir", type=str, required=False, help="Image directory relative to data_dir")
-    parser.add_argument("--ann_file", type=str, required=False, help="Annotation file relative to data_dir")
-    parser.add_argument("--ann_dir", type=str, required=False, help="Annotation directory relative to data_dir")
-    parser.add_argument("--background_class", type=int, required=False, default=0, help="Default background class")
-    parser.add_argument("--train_backbone", action="store_true", required=False, default=False, help="Train backbone")
-    parser.add_argument("--train_transformers", action="store_true", required=False, default=False, help="Train transformers")
-    parser.add_argument("--train_nlayers", action="store_true", required=False, default=False, help="Train new layers")
-    parser.add_argument("--finetuning", default=False, required=False, action="store_true", help="Load the model weight before to train")
-    parser.add_argument("--batch_size", type=int, required=False, default=1, help="Batch size to use to train the model")
-    parser.add_argument("--gradient_norm_clipping", type=float, required=False, default=0.1, help="Gradient norm clipping")
-    parser.add_argument("--target_batch", type=int, required=False, default=None,
-                        help="When running on a single GPU, aggretate the gradient before to apply.")
-    parser.add_argument("--backbone_lr", type=float, required=False, default=1e-5, help="Backbone learning rate")
-    parser.add_argument("--transformers_lr", type=float, required=False, default=1e-4, help="Transformers learning rate")
-    parser.add_argument("--nlayers_lr", type=float, required=False, default=1e-4, help="New layers learning rate")
-    parser.add_argument("--log", required=False, action="store_true", default=False, help="Log into wandb")
+    for flag, kind, default, text in _FLAGS:
+        if kind == "switch":
+            parser.add_argument("--" + flag, action="store_true", default=default, help=text)
+        else:
+            parser.add_argument("--" + flag, type={"path": str, "int": int, "float": float}[kind], default=default, help=text)
     return parser
 
 

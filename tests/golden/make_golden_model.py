@@ -160,6 +160,20 @@ def resnet101_case():
     return {"r101_meta": np.array([seed, 1, 64, 96]), "r101_feat": feat.numpy()}
 
 
+def config_case():
+    """training_config.py executed as is: the attribute defaults of TrainingConfig() and the defaults of its argument parser"""
+    import json
+    from detr_tf import training_config as ref_tc
+    c = ref_tc.TrainingConfig()
+    attrs = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(c).items() if k != "data"}
+    attrs = {k: (float(v) if k.endswith("_lr") else v) for k, v in attrs.items()}
+    parser = {a.dest: a.default for a in ref_tc.training_config_parser()._actions if a.dest != "help"}
+    c.add_nlayers([type("L", (), {"name": "cls_layer"})(), type("L", (), {"name": "pos_layer"})()])
+    print("config:", len(attrs), "attributes,", len(parser), "flags")
+    return {"config_attrs_json": np.array(json.dumps(attrs, sort_keys=True)), "config_parser_json": np.array(json.dumps(parser, sort_keys=True)),
+            "config_nlayers_json": np.array(json.dumps(c.nlayers))}
+
+
 def main():
     torch.manual_seed(0)
     out = {}
@@ -196,6 +210,7 @@ def main():
     out.update(train_case())
     out.update(accumulate_case())
     out.update(resnet101_case())
+    out.update(config_case())
     np.savez_compressed(os.path.join(HERE, "model_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "model_golden.npz"), os.path.getsize(os.path.join(HERE, "model_golden.npz")), "bytes")
 

@@ -269,6 +269,7 @@ def build():
     tf.Tensor = torch.Tensor
     tf.newaxis = None
     tf.shape = lambda x: list(x.shape)
+    tf.Variable = lambda v, **kw: v                                   # training_config.py:66-68 wraps the learning rates
     tf.reshape = lambda x, shape: x.reshape(_ints(shape)).clone()
     tf.transpose = lambda x, perm: x.permute(*perm).contiguous()
     tf.matmul = lambda a, b, transpose_b=False: a @ (b.transpose(-1, -2) if transpose_b else b)

@@ -161,6 +161,25 @@ def test_engine_train_step_gradients_vs_reference_code_golden(emu):
             assert float((gr - full).abs().max()) <= 2e-3 * float(full.abs().max()) + 1e-8, n
 
 
+def test_training_config_defaults_vs_reference_code_golden():
+    """TrainingConfig() attribute defaults, parser flags / defaults and add_nlayers against training_config.py executed as is
+    (the learning rates are plain floats here, tf.Variable there; the lr flags are floats, type=bool in the reference)"""
+    import json
+    from detr_tensorflow_b200.training_config import TrainingConfig, training_config_parser
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+    ref_attrs = json.loads(str(g["config_attrs_json"]))
+    c = TrainingConfig()
+    mine = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(c).items() if k != "data"}
+    assert set(mine) == set(ref_attrs)
+    for k, v in ref_attrs.items():
+        assert mine[k] == pytest.approx(v) if isinstance(v, float) else mine[k] == v, (k, mine[k], v)
+    ref_flags = json.loads(str(g["config_parser_json"]))
+    flags = {a.dest: a.default for a in training_config_parser()._actions if a.dest != "help"}
+    assert flags == ref_flags
+    c.add_nlayers([type("L", (), {"name": "cls_layer"})(), type("L", (), {"name": "pos_layer"})()])
+    assert c.nlayers == json.loads(str(g["config_nlayers_json"]))
+
+
 def test_gradient_accumulation_cadence_vs_reference_code_golden(emu):
     """aggregate_grad_and_apply against the reference's own optimizers.py:137-163 executed with a recording optimizer
     (make_golden_model.py::accumulate_case): zero at step % k == 0, SUM of the micro-step gradients, apply at (step+1) % k == 0,
