@@ -17,6 +17,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
 _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu", "pipeline.cu"]
 _lib = None
+ABI_VERSION = 200          # detrb_version() of the library these ctypes structures / call sites were written for
 
 EXPORTS = [
     "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
@@ -24,7 +25,7 @@ EXPORTS = [
     "detrb_image_to_nhwc4", "detrb_image_to_s2d16", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
     "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",
     "detrb_set_tc", "detrb_set_tc_conv", "detrb_set_tc_tma_epilogue", "detrb_set_tc_persistent", "detrb_gemm_tc_force", "detrb_tma_im2col_probe", "detrb_prep_weights_multi", "detrb_adam_clipnorm_chunked", "detrb_set_tc_wgrad", "detrb_wgrad_tc_force",
-    "detrb_attn_dropout_mask", "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess",
+    "detrb_attn_dropout_mask", "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess", "detrb_accumulate",
 ]
 
 
@@ -57,6 +58,7 @@ class IgemmParams(Structure):
         ("mask_scale", c_float), ("relu", c_int), ("sigmoid", c_int), ("drop_p", c_float), ("seed", c_uint64),
         ("site", c_uint32), ("seed_ptr", c_void_p), ("C", c_void_p), ("ldc", c_int), ("Cf", c_void_p), ("ldcf", c_int),
         ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int), ("a_kb_rows", c_int),
+        ("split", c_int64), ("wsplit", c_int64),
     ]
 
 
@@ -66,6 +68,7 @@ class WgradParams(Structure):
         ("batch", c_int), ("IH", c_int), ("IW", c_int), ("Cin", c_int), ("OH", c_int), ("OW", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int),
         ("rowscale", c_void_p), ("dW", c_void_p), ("ldw", c_int), ("dbias", c_void_p), ("a_kb_rows", c_int), ("k_mask", c_int),
+        ("split", c_int64),
     ]
 
 
@@ -81,6 +84,7 @@ class AttnFwdParams(Structure):
         ("Q", c_void_p), ("K", c_void_p), ("V", c_void_p), ("ldq", c_int), ("ldk", c_int), ("ldv", c_int),
         ("O", c_void_p), ("ldo", c_int), ("lse", c_void_p), ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int),
         ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64), ("site", c_uint32), ("seed_ptr", c_void_p),
+        ("split", c_int64),
     ]
 
 
@@ -91,20 +95,28 @@ class AttnBwdParams(Structure):
         ("lse", c_void_p), ("delta", c_void_p), ("dQ", c_void_p), ("dK", c_void_p), ("dV", c_void_p),
         ("lddq", c_int), ("lddk", c_int), ("lddv", c_int), ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int),
         ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64), ("site", c_uint32), ("seed_ptr", c_void_p),
+        ("split", c_int64),
     ]
 
 
 def lib():
-    """Load libdetrb.so (building it first if the sources are newer and nvcc is present)."""
+    """Load libdetrb.so, (re)building it first when it is missing or older than its sources and nvcc is present (build() is a
+    no-op for an up-to-date binary).  A library whose detrb_version() differs from ABI_VERSION is refused: the ctypes structures
+    above are passed by reference, so a stale binary would misread their fields silently."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.environ.get("DETRB_SO") and (not os.path.exists(_SO) or (os.path.exists(nvcc) and os.path.isdir(_CSRC))):
         build()
     L = ctypes.CDLL(_SO)
     L.detrb_last_error.restype = c_char_p
+    L.detrb_version.restype = c_int
     for name in EXPORTS:
         getattr(L, name)         # raises AttributeError if a declared symbol is missing
+    if L.detrb_version() != ABI_VERSION:
+        raise RuntimeError("%s reports ABI version %d, this package needs %d: rebuild it (detr_tensorflow_b200._lib.build(force=True))"
+                           % (_SO, L.detrb_version(), ABI_VERSION))
     _lib = L
     return L
 

@@ -12,7 +12,8 @@ void detrb_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-extern "C" int detrb_version(void) { return 100; }   // 0.1.0
+extern "C" int detrb_version(void) { return 200; }   // 0.2.0: parity-precision planes (split / wsplit), detrb_accumulate, set_loss status
+// (bump on EVERY change of a struct or prototype in include/detrb.h: _lib.py refuses to load a library of another version)
 
 extern "C" const char *detrb_last_error(void) { return g_err; }
 

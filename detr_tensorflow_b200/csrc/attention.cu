@@ -244,26 +244,134 @@ attn_fwd_kernel(const detrb_attn_fwd_t p)
 // --------------------------------------------------------------------------------------- backward
 // delta[b,h,q] = sum_d dO[b,q,h*32+d] * O[b,q,h*32+d]
 __global__ void attn_delta_kernel(const bf16 *O, const bf16 *dO, int ldo, int lddo, float *delta,
-                                  int B, int H, int Lq)
+                                  int B, int H, int Lq, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * H * Lq) return;
     int q = idx % Lq, h = (idx / Lq) % H, b = idx / (Lq * H);
-    const uint4 *o = reinterpret_cast<const uint4 *>(O + ((size_t)b * Lq + q) * ldo + h * DH);
-    const uint4 *d = reinterpret_cast<const uint4 *>(dO + ((size_t)b * Lq + q) * lddo + h * DH);
+    const bf16 *o = O + ((size_t)b * Lq + q) * ldo + h * DH;
+    const bf16 *d = dO + ((size_t)b * Lq + q) * lddo + h * DH;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        uint4 ov = o[i], dv = d[i];
-        float2 a, c;
-        a = unpack_bf16x2(ov.x); c = unpack_bf16x2(dv.x); acc += a.x * c.x + a.y * c.y;
-        a = unpack_bf16x2(ov.y); c = unpack_bf16x2(dv.y); acc += a.x * c.x + a.y * c.y;
-        a = unpack_bf16x2(ov.z); c = unpack_bf16x2(dv.z); acc += a.x * c.x + a.y * c.y;
-        a = unpack_bf16x2(ov.w); c = unpack_bf16x2(dv.w); acc += a.x * c.x + a.y * c.y;
+        float ov[8], dv[8];
+        sp_ld8(o + i * 8, split, ov);
+        sp_ld8(d + i * 8, split, dv);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) acc += ov[j] * dv[j] + ov[j + 1] * dv[j + 1];
     }
     delta[idx] = acc;
+}
+
+// --------------------------------------------------------------------------------------- parity precision (p.split != 0)
+// The reference computes attention in fp32 (transformer.py:308-345).  These kernels do the same arithmetic in fp32 on the bf16
+// pairs: one warp per (batch, head, row), lane = head channel (head_dim == 32 == warp size), a warp reduction per score.  They
+// exist for the fp32-tolerance parity tests (small batches); the throughput path is the tensor-core kernels above.  Dropout
+// uses the same counter-based masks as the tensor-core kernels.
+__device__ __forceinline__ bool attn_keep(uint32_t rowhash_m, uint32_t k, uint32_t thresh2) {
+    const uint32_t kb = attn_drop_keepbits(attn_drop_word(rowhash_m, attn_drop_pair(k)), thresh2);
+    return ((((k >> 3) & 1u) ? attn_drop_mask_hi(kb) : attn_drop_mask_lo(kb)) & 1u) != 0u;
+}
+
+__global__ void __launch_bounds__(256)
+attn_fwd_sp_kernel(const detrb_attn_fwd_t p)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (b*H + h)*Lq + q
+    if (row >= (long long)p.B * p.H * p.Lq) return;
+    const int q = (int)(row % p.Lq), h = (int)((row / p.Lq) % p.H), b = (int)(row / ((long long)p.Lq * p.H));
+    const long long sp = p.split;
+    const bf16 *K = reinterpret_cast<const bf16 *>(p.K) + (size_t)b * p.Lk * p.ldk + h * DH + lane;
+    const bf16 *V = reinterpret_cast<const bf16 *>(p.V) + (size_t)b * p.Lk * p.ldv + h * DH + lane;
+    const float qv = sp_ld1(reinterpret_cast<const bf16 *>(p.Q) + ((size_t)b * p.Lq + q) * p.ldq + h * DH + lane, sp) * p.scale;
+    const bool drop = p.drop_p > 0.f;
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
+    const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    const uint32_t rh = attn_drop_rowhash(seed, p.site, (uint32_t)row);
+    float m = -INFINITY, l = 0.f, acc = 0.f;
+    for (int k = 0; k < p.Lk; k++) {
+        const float s = warp_sum(qv * sp_ld1(K + (size_t)k * p.ldk, sp));
+        const float mn = fmaxf(m, s);
+        const float alpha = expf(m - mn), pr = expf(s - mn);
+        l = l * alpha + pr;
+        const float pd = (!drop || attn_keep(rh, (uint32_t)k, thresh2)) ? pr : 0.f;
+        acc = acc * alpha + pd * sp_ld1(V + (size_t)k * p.ldv, sp);
+        m = mn;
+    }
+    const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    sp_st1(reinterpret_cast<bf16 *>(p.O) + ((size_t)b * p.Lq + q) * p.ldo + h * DH + lane, sp, acc * drop_scale / l);
+    if (lane == 0 && p.lse) p.lse[row] = m + logf(l);
+}
+
+// dQ[q] = scale * sum_k dS[q,k] K[k],  dS = P * (dP - delta),  dP = keep/(1-p) * (dO . V[k])
+__global__ void __launch_bounds__(256)
+attn_bwd_dq_sp_kernel(const detrb_attn_bwd_t p)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)p.B * p.H * p.Lq) return;
+    const int q = (int)(row % p.Lq), h = (int)((row / p.Lq) % p.H), b = (int)(row / ((long long)p.Lq * p.H));
+    const long long sp = p.split;
+    const bf16 *K = reinterpret_cast<const bf16 *>(p.K) + (size_t)b * p.Lk * p.ldk + h * DH + lane;
+    const bf16 *V = reinterpret_cast<const bf16 *>(p.V) + (size_t)b * p.Lk * p.ldv + h * DH + lane;
+    const float qv = sp_ld1(reinterpret_cast<const bf16 *>(p.Q) + ((size_t)b * p.Lq + q) * p.ldq + h * DH + lane, sp) * p.scale;
+    const float dov = sp_ld1(reinterpret_cast<const bf16 *>(p.dO) + ((size_t)b * p.Lq + q) * p.lddo + h * DH + lane, sp);
+    const float lse = p.lse[row], delta = p.delta[row];
+    const bool drop = p.drop_p > 0.f;
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
+    const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    const uint32_t rh = attn_drop_rowhash(seed, p.site, (uint32_t)row);
+    float acc = 0.f;
+    for (int k = 0; k < p.Lk; k++) {
+        const float kv = sp_ld1(K + (size_t)k * p.ldk, sp);
+        const float s = warp_sum(qv * kv);
+        float dp = warp_sum(dov * sp_ld1(V + (size_t)k * p.ldv, sp));
+        dp = (!drop || attn_keep(rh, (uint32_t)k, thresh2)) ? dp * drop_scale : 0.f;
+        acc += expf(s - lse) * (dp - delta) * kv;
+    }
+    sp_st1(reinterpret_cast<bf16 *>(p.dQ) + ((size_t)b * p.Lq + q) * p.lddq + h * DH + lane, sp, acc * p.scale);
+}
+
+// dK[k] = scale * sum_q dS[q,k] Q[q],  dV[k] = sum_q keep/(1-p) P[q,k] dO[q]
+__global__ void __launch_bounds__(256)
+attn_bwd_dkv_sp_kernel(const detrb_attn_bwd_t p)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (b*H + h)*Lk + key
+    if (row >= (long long)p.B * p.H * p.Lk) return;
+    const int key = (int)(row % p.Lk), h = (int)((row / p.Lk) % p.H), b = (int)(row / ((long long)p.Lk * p.H));
+    const long long sp = p.split;
+    const bf16 *Q = reinterpret_cast<const bf16 *>(p.Q) + (size_t)b * p.Lq * p.ldq + h * DH + lane;
+    const bf16 *dO = reinterpret_cast<const bf16 *>(p.dO) + (size_t)b * p.Lq * p.lddo + h * DH + lane;
+    const float kv = sp_ld1(reinterpret_cast<const bf16 *>(p.K) + ((size_t)b * p.Lk + key) * p.ldk + h * DH + lane, sp) * p.scale;
+    const float vv = sp_ld1(reinterpret_cast<const bf16 *>(p.V) + ((size_t)b * p.Lk + key) * p.ldv + h * DH + lane, sp);
+    const float *lse = p.lse + ((size_t)b * p.H + h) * p.Lq, *delta = p.delta + ((size_t)b * p.H + h) * p.Lq;
+    const bool drop = p.drop_p > 0.f;
+    const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
+    const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+    float dk = 0.f, dv = 0.f;
+    for (int q = 0; q < p.Lq; q++) {
+        const float qv = sp_ld1(Q + (size_t)q * p.ldq, sp), dov = sp_ld1(dO + (size_t)q * p.lddo, sp);
+        const float s = warp_sum(qv * kv);
+        const float pr = expf(s - lse[q]);
+        float dp = warp_sum(dov * vv);
+        const bool keep = !drop || attn_keep(attn_drop_rowhash(seed, p.site, (uint32_t)(((size_t)b * p.H + h) * p.Lq + q)), (uint32_t)key, thresh2);
+        dp = keep ? dp * drop_scale : 0.f;
+        dv += (keep ? pr * drop_scale : 0.f) * dov;
+        dk += pr * (dp - delta[q]) * qv;
+    }
+    sp_st1(reinterpret_cast<bf16 *>(p.dK) + ((size_t)b * p.Lk + key) * p.lddk + h * DH + lane, sp, dk * p.scale);
+    sp_st1(reinterpret_cast<bf16 *>(p.dV) + ((size_t)b * p.Lk + key) * p.lddv + h * DH + lane, sp, dv);
 }
 
 // dK, dV: CTA owns 64 keys (warp: 16), loops over query tiles; works on S^T so that P^T / dS^T come out
@@ -481,6 +589,12 @@ extern "C" int detrb_attn_fwd(const detrb_attn_fwd_t *pp, detrb_stream_t stream_
     DETRB_REQUIRE(p.B > 0 && p.H > 0 && p.Lq > 0 && p.Lk > 0, "detrb_attn_fwd: empty problem");
     DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 2 == 0, "detrb_attn_fwd: strides must be multiples of 8");
     DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_attn_fwd: drop_p");
+    if (p.split) {
+        const long long rows = (long long)p.B * p.H * p.Lq;
+        DETRB_LAUNCH(attn_fwd_sp_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream_, p);
+        DETRB_CHECK_LAUNCH("attn_fwd_sp_kernel");
+        return DETRB_OK;
+    }
     dim3 grid(ceil_div(p.Lq, TQ), p.H, p.B);
     DETRB_LAUNCH(attn_fwd_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream_, p);
     DETRB_CHECK_LAUNCH("attn_fwd_kernel");
@@ -498,8 +612,16 @@ extern "C" int detrb_attn_bwd(const detrb_attn_bwd_t *pp, detrb_stream_t stream_
                   "detrb_attn_bwd: strides must be multiples of 8");
     int n = p.B * p.H * p.Lq;
     DETRB_LAUNCH(attn_delta_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
-                                                            p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq);
+                                                            p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq, (long long)p.split);
     DETRB_CHECK_LAUNCH("attn_delta_kernel");
+    if (p.split) {
+        const long long rq = (long long)p.B * p.H * p.Lq, rk = (long long)p.B * p.H * p.Lk;
+        DETRB_LAUNCH(attn_bwd_dkv_sp_kernel, dim3((unsigned)((rk + 7) / 8)), dim3(256), 0, stream, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dkv_sp_kernel");
+        DETRB_LAUNCH(attn_bwd_dq_sp_kernel, dim3((unsigned)((rq + 7) / 8)), dim3(256), 0, stream, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dq_sp_kernel");
+        return DETRB_OK;
+    }
     DETRB_LAUNCH(attn_bwd_dkv_kernel, dim3(dim3(ceil_div(p.Lk, TQ), p.H, p.B)), dim3(128), 0, stream, p);
     DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
     DETRB_LAUNCH(attn_bwd_dq_kernel, dim3(dim3(ceil_div(p.Lq, TQ), p.H, p.B)), dim3(128), 0, stream, p);

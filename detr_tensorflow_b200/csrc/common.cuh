@@ -121,6 +121,76 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------- parity precision: bf16 pairs (include/detrb.h header comment)
+// element x = hi + lo, hi = bf16(x) at p, lo = bf16(x - hi) at p + split; split == 0: plain bf16 (lo does not exist)
+__device__ __forceinline__ void sp_unpack8(const uint4 &u, float (&f)[8]) {
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 sp_pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    return u;
+}
+// 8 consecutive elements (16-byte aligned)
+__device__ __forceinline__ void sp_ld8(const bf16 *p, long long split, float (&f)[8]) {
+    sp_unpack8(*reinterpret_cast<const uint4 *>(p), f);
+    if (split) {
+        float l[8];
+        sp_unpack8(*reinterpret_cast<const uint4 *>(p + split), l);
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] += l[i];
+    }
+}
+__device__ __forceinline__ void sp_st8(bf16 *p, long long split, const float (&f)[8]) {
+    const uint4 hi = sp_pack8(f);
+    *reinterpret_cast<uint4 *>(p) = hi;
+    if (split) {
+        float h[8], l[8];
+        sp_unpack8(hi, h);
+#pragma unroll
+        for (int i = 0; i < 8; i++) l[i] = f[i] - h[i];
+        *reinterpret_cast<uint4 *>(p + split) = sp_pack8(l);
+    }
+}
+// the value a later sp_ld8 of the same location returns (the pair's rounding applied to f)
+__device__ __forceinline__ void sp_round8(long long split, float (&f)[8]) {
+    float h[8];
+    sp_unpack8(sp_pack8(f), h);
+    if (split) {
+        float l[8], lr[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) l[i] = f[i] - h[i];
+        sp_unpack8(sp_pack8(l), lr);
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = h[i] + lr[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) f[i] = h[i];
+    }
+}
+// 2 consecutive elements (4-byte aligned)
+__device__ __forceinline__ float2 sp_ld2(const bf16 *p, long long split) {
+    float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(p));
+    if (split) { const float2 l = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(p + split)); v.x += l.x; v.y += l.y; }
+    return v;
+}
+__device__ __forceinline__ void sp_st2(bf16 *p, long long split, float a, float b) {
+    const uint32_t hi = pack_bf16x2(a, b);
+    *reinterpret_cast<uint32_t *>(p) = hi;
+    if (split) { const float2 h = unpack_bf16x2(hi); *reinterpret_cast<uint32_t *>(p + split) = pack_bf16x2(a - h.x, b - h.y); }
+}
+__device__ __forceinline__ float sp_ld1(const bf16 *p, long long split) {
+    float v = __bfloat162float(*p);
+    if (split) v += __bfloat162float(p[split]);
+    return v;
+}
+__device__ __forceinline__ void sp_st1(bf16 *p, long long split, float a) {
+    const bf16 h = __float2bfloat16(a);
+    *p = h;
+    if (split) p[split] = __float2bfloat16(a - __bfloat162float(h));
+}
+
 // ---------------------------------------------------------------- counter-based dropout RNG
 // 32 random bits for the counter (site, row, pair) under `seed`, from the "lowbias32" integer finaliser: one full round for the
 // row (hoistable out of inner loops: dropout_rowhash) and one for the column pair.  One call serves two adjacent elements

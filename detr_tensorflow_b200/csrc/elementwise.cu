@@ -21,7 +21,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ---------------------------------------------------------------- LayerNorm forward: warp per row
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf16 *y2, const bf16 *pos, int S,
-              float *mean, float *rstd, int M)
+              float *mean, float *rstd, int M, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -29,7 +29,7 @@ ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf1
     int lane = threadIdx.x & 31;
     if (row >= M) return;
     float v[8];
-    unpack8(*reinterpret_cast<const uint4 *>(x + (size_t)row * D + lane * 8), v);
+    sp_ld8(x + (size_t)row * D + lane * 8, split, v);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) s += v[i];
@@ -45,16 +45,15 @@ ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf1
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) o[i] = (v[i] - mu) * rs * gg[i] + bb[i];
-    uint4 packed = pack8(o);
-    *reinterpret_cast<uint4 *>(y + (size_t)row * D + lane * 8) = packed;
+    sp_st8(y + (size_t)row * D + lane * 8, split, o);
     if (y2) {
-        // y2 = bf16(y) + pos : add to the ROUNDED y so that y2 == (stored y) + pos exactly like a separate add
-        float yr[8], pp[8];
-        unpack8(packed, yr);
-        unpack8(*reinterpret_cast<const uint4 *>(pos + (size_t)(row % S) * D + lane * 8), pp);
+        // y2 = stored(y) + pos : add to the ROUNDED y so that y2 == (stored y) + pos exactly like a separate add
+        float pp[8];
+        sp_round8(split, o);
+        sp_ld8(pos + (size_t)(row % S) * D + lane * 8, split, pp);
 #pragma unroll
-        for (int i = 0; i < 8; i++) yr[i] += pp[i];
-        *reinterpret_cast<uint4 *>(y2 + (size_t)row * D + lane * 8) = pack8(yr);
+        for (int i = 0; i < 8; i++) o[i] += pp[i];
+        sp_st8(y2 + (size_t)row * D + lane * 8, split, o);
     }
     if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
 }
@@ -64,7 +63,7 @@ ln_fwd_kernel(const bf16 *x, const float *gamma, const float *beta, bf16 *y, bf1
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma, const float *mean, const float *rstd,
               bf16 *dx, bf16 *dx_drop, float drop_p, uint64_t seed_in, uint32_t site, const uint64_t *seed_ptr,
-              float *dgamma, float *dbeta, int M, int rows_per_block)
+              float *dgamma, float *dbeta, int M, int rows_per_block, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -82,14 +81,14 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
     const int r_end = min(M, r_begin + rows_per_block);
     for (int row = r_begin + warp; row < r_end; row += 8) {
         float d[8], xv[8];
-        unpack8(*reinterpret_cast<const uint4 *>(dy + (size_t)row * D + lane * 8), d);
+        sp_ld8(dy + (size_t)row * D + lane * 8, split, d);
         if (dy2) {
             float d2[8];
-            unpack8(*reinterpret_cast<const uint4 *>(dy2 + (size_t)row * D + lane * 8), d2);
+            sp_ld8(dy2 + (size_t)row * D + lane * 8, split, d2);
 #pragma unroll
             for (int i = 0; i < 8; i++) d[i] += d2[i];
         }
-        unpack8(*reinterpret_cast<const uint4 *>(x + (size_t)row * D + lane * 8), xv);
+        sp_ld8(x + (size_t)row * D + lane * 8, split, xv);
         const float mu = mean[row], rs = rstd[row];
         float s1 = 0.f, s2 = 0.f, xh[8], gv[8];
 #pragma unroll
@@ -103,11 +102,12 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) o[i] = rs * (gv[i] - s1 - xh[i] * s2);
-        uint4 packed = pack8(o);
-        *reinterpret_cast<uint4 *>(dx + (size_t)row * D + lane * 8) = packed;
+        sp_st8(dx + (size_t)row * D + lane * 8, split, o);
         if (dx_drop) {
             float od[8];
-            unpack8(packed, od);
+#pragma unroll
+            for (int i = 0; i < 8; i++) od[i] = o[i];
+            sp_round8(split, od);
             if (drop_p > 0.f) {
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
@@ -117,7 +117,7 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
                     od[i + 1] = k1 ? od[i + 1] * drop_scale : 0.f;
                 }
             }
-            *reinterpret_cast<uint4 *>(dx_drop + (size_t)row * D + lane * 8) = pack8(od);
+            sp_st8(dx_drop + (size_t)row * D + lane * 8, split, od);
         }
     }
     if (dgamma) {
@@ -134,17 +134,17 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
 }
 
 // ---------------------------------------------------------------- simple vector kernels
-__global__ void add_rowbcast_kernel(const uint4 *x, const uint4 *pos, uint4 *out, int64_t nvec, int64_t svec)
+__global__ void add_rowbcast_kernel(const bf16 *x, const bf16 *pos, bf16 *out, int64_t nvec, int64_t svec, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nvec) return;
     float a[8], b[8];
-    unpack8(x[i], a); unpack8(pos[i % svec], b);
+    sp_ld8(x + i * 8, split, a); sp_ld8(pos + (i % svec) * 8, split, b);
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] += b[k];
-    out[i] = pack8(a);
+    sp_st8(out + i * 8, split, a);
 }
 __global__ void add_kernel(const uint4 *x, const uint4 *y, uint4 *out, int64_t nvec)
 {
@@ -171,7 +171,8 @@ __global__ void image_to_nhwc4_kernel(const float *img, uint2 *out, int64_t npix
 // space-to-depth(2) of the fp32 NHWC3 image: out[b, y, x, (ry*2+rx)*3 + c] = img[b, 2y+ry, 2x+rx, c] (0 outside, 4 zero pad channels)
 // -> the 7x7 / stride-2 stem becomes a dense 4x4 / stride-1 convolution over 16-channel pixels (32 B: four consecutive pixels are
 //    one 128-byte row of the sliding-window GEMM operand, see detrb_igemm_t.a_kb_rows)
-__global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP)
+__global__ void image_to_s2d16_kernel(const float *img, bf16 *out, int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP,
+                                      long long split)
 {
     pdl_trigger();
     pdl_wait();
@@ -195,10 +196,11 @@ __global__ void image_to_s2d16_kernel(const float *img, uint4 *out, int B, int H
                 }
             }
     }
-    uint4 o0, o1;
-    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-    out[i * 2] = o0; out[i * 2 + 1] = o1;
+    float lo8[8], hi8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo8[k] = v[k]; hi8[k] = v[8 + k]; }
+    sp_st8(out + i * 16, split, lo8);
+    sp_st8(out + i * 16 + 8, split, hi8);
 }
 __global__ void f32_to_bf16_kernel(const float *x, bf16 *y, int64_t n)
 {
@@ -239,7 +241,8 @@ colsum_kernel(const bf16 *x, int ldx, int M, int N, const float *scale, float *o
 }
 
 // ---------------------------------------------------------------- max pool 3x3 s2 pad 1 (zero pad == -inf pad: x >= 0)
-__global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW, int XH, int XW)
+__global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW, int XH, int XW,
+                                   long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -262,12 +265,12 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
             int iy = oy * 2 - 1 + kh, ix = ox * 2 - 1 + kw;
             if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;
             float v[8];
-            unpack8(*reinterpret_cast<const uint4 *>(x + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8), v);   // x is [B, XH, XW, C]
+            sp_ld8(x + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8, split, v);   // x is [B, XH, XW, C]
 #pragma unroll
             for (int i = 0; i < 8; i++) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = kh * 3 + kw; }
         }
     size_t o = (size_t)pix * C + c8 * 8;
-    *reinterpret_cast<uint4 *>(y + o) = pack8(best);
+    sp_st8(y + o, split, best);
     // a window whose maximum is not positive passes no gradient through the stem's ReLU: tap 15 matches no input position,
     // so the backward pass needs neither x nor y
 #pragma unroll
@@ -284,7 +287,7 @@ __global__ void maxpool_fwd_kernel(const bf16 *x, bf16 *y, uint8_t *argmax, int 
 // One thread owns the 2x2 input block (2a..2a+1, 2b..2b+1) x 8 channels: the only windows that reach it are (a,b), (a,b+1),
 // (a+1,b), (a+1,b+1) -- four (argmax, dy) loads for four stores (a thread per pixel loads 2.25 windows per store).
 __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, bf16 *dx,
-                                   int B, int IH, int IW, int C, int OH, int OW, int XH, int XW)
+                                   int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -309,7 +312,7 @@ __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, bf16 *
             const size_t o = (((size_t)b * OH + oy) * OW + ox) * C + c8 * 8;
             const uint2 am = *reinterpret_cast<const uint2 *>(argmax + o);
             float d[8];
-            unpack8(*reinterpret_cast<const uint4 *>(dy + o), d);
+            sp_ld8(dy + o, split, d);
             // window (oy, ox) covers input (2oy-1+kh, 2ox-1+kw): inside this block rows r >= wy, columns c >= wx, reached by
             // kh = r + 1 - 2wy, kw = c + 1 - 2wx
 #pragma unroll
@@ -331,8 +334,9 @@ __global__ void maxpool_bwd_kernel(const bf16 *dy, const uint8_t *argmax, bf16 *
         for (int c = 0; c < 2; c++) {
             const int iy = 2 * a + r, ix = 2 * bq + c;
             if (iy >= XH || ix >= XW) continue;
-            uint4 *dst = reinterpret_cast<uint4 *>(dx + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8);
-            *dst = (iy < IH && ix < IW) ? pack8(acc[r][c]) : make_uint4(0u, 0u, 0u, 0u);
+            bf16 *dst = dx + (((size_t)b * XH + iy) * XW + ix) * C + c8 * 8;
+            const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (iy < IH && ix < IW) sp_st8(dst, split, acc[r][c]); else sp_st8(dst, split, zero8);
         }
 }
 
@@ -365,12 +369,12 @@ __global__ void attn_dropout_mask_kernel(uint8_t *out, int M, int N, float drop_
 }  // namespace
 
 extern "C" int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, const float *beta, detrb_bf16 *y, detrb_bf16 *y2,
-                                   const detrb_bf16 *pos, int S, float *mean, float *rstd, int M, detrb_stream_t stream)
+                                   const detrb_bf16 *pos, int S, float *mean, float *rstd, int M, int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(x && gamma && beta && y && M > 0, "detrb_layernorm_fwd: bad args");
     DETRB_REQUIRE(!y2 || (pos && S > 0), "detrb_layernorm_fwd: y2 needs pos and S");
     DETRB_LAUNCH(ln_fwd_kernel, dim3(ceil_div(M, 8)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, gamma, beta, (bf16 *)y, (bf16 *)y2,
-                                                                   (const bf16 *)pos, S, mean, rstd, M);
+                                                                   (const bf16 *)pos, S, mean, rstd, M, (long long)split);
     DETRB_CHECK_LAUNCH("ln_fwd_kernel");
     return DETRB_OK;
 }
@@ -378,7 +382,7 @@ extern "C" int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, cons
 extern "C" int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, const detrb_bf16 *x, const float *gamma,
                                    const float *mean, const float *rstd, detrb_bf16 *dx, detrb_bf16 *dx_drop,
                                    float drop_p, uint64_t seed, uint32_t site, const uint64_t *seed_ptr,
-                                   float *dgamma, float *dbeta, int M, detrb_stream_t stream)
+                                   float *dgamma, float *dbeta, int M, int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(dy && x && gamma && mean && rstd && dx && M > 0, "detrb_layernorm_bwd: bad args");
     DETRB_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "detrb_layernorm_bwd: dgamma/dbeta must both be set or both NULL");
@@ -387,16 +391,17 @@ extern "C" int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, 
     int rpb = ceil_div(ceil_div(M, blocks), 8) * 8;
     blocks = ceil_div(M, rpb);
     DETRB_LAUNCH(ln_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, (const bf16 *)dy2, (const bf16 *)x, gamma, mean, rstd,
-                                                            (bf16 *)dx, (bf16 *)dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M, rpb);
+                                                            (bf16 *)dx, (bf16 *)dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M, rpb, (long long)split);
     DETRB_CHECK_LAUNCH("ln_bwd_kernel");
     return DETRB_OK;
 }
 
-extern "C" int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *out, int M, int S, int d, detrb_stream_t stream)
+extern "C" int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *out, int M, int S, int d, int64_t split,
+                                  detrb_stream_t stream)
 {
     DETRB_REQUIRE(x && pos && out && M > 0 && S > 0 && d % 8 == 0, "detrb_add_rowbcast: bad args");
     int64_t nvec = (int64_t)M * d / 8, svec = (int64_t)S * d / 8;
-    DETRB_LAUNCH(add_rowbcast_kernel, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4 *)x, (const uint4 *)pos, (uint4 *)out, nvec, svec);
+    DETRB_LAUNCH(add_rowbcast_kernel, dim3((unsigned)((nvec + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (const bf16 *)pos, (bf16 *)out, nvec, svec, (long long)split);
     DETRB_CHECK_LAUNCH("add_rowbcast_kernel");
     return DETRB_OK;
 }
@@ -419,14 +424,14 @@ extern "C" int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t n
 }
 
 extern "C" int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, int pad_top, int pad_left, int HP, int WP,
-                                    detrb_stream_t stream)
+                                    int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(img && out && B > 0 && H > 0 && W > 0, "detrb_image_to_s2d16: bad args");
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
     DETRB_REQUIRE(pad_top >= 0 && pad_left >= 0 && HP >= H2 + pad_top && WP >= W2 + pad_left, "detrb_image_to_s2d16: padded size too small");
     int64_t n = (int64_t)B * HP * WP;
-    DETRB_LAUNCH(image_to_s2d16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (uint4 *)out, B, H, W, H2, W2,
-                 pad_top, pad_left, HP, WP);
+    DETRB_LAUNCH(image_to_s2d16_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, img, (bf16 *)out, B, H, W, H2, W2,
+                 pad_top, pad_left, HP, WP, (long long)split);
     DETRB_CHECK_LAUNCH("image_to_s2d16_kernel");
     return DETRB_OK;
 }
@@ -452,25 +457,25 @@ extern "C" int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const fl
 }
 
 extern "C" int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax, int B, int IH, int IW, int C, int OH, int OW,
-                                 int XH, int XW, detrb_stream_t stream)
+                                 int XH, int XW, int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(x && y && argmax && C % 8 == 0, "detrb_maxpool_fwd: bad args");
     DETRB_REQUIRE(OH == (IH + 2 - 3) / 2 + 1 && OW == (IW + 2 - 3) / 2 + 1, "detrb_maxpool_fwd: bad output size");
     DETRB_REQUIRE(OH <= 65535 && B <= 65535, "detrb_maxpool_fwd: grid too large");
     DETRB_REQUIRE(XH >= IH && XW >= IW, "detrb_maxpool_fwd: allocated extent smaller than the image");
-    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)ceil_div(OW * (C / 8), 256), (unsigned)OH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW, XH, XW);
+    DETRB_LAUNCH(maxpool_fwd_kernel, dim3((unsigned)ceil_div(OW * (C / 8), 256), (unsigned)OH, (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)x, (bf16 *)y, argmax, B, IH, IW, C, OH, OW, XH, XW, (long long)split);
     DETRB_CHECK_LAUNCH("maxpool_fwd_kernel");
     return DETRB_OK;
 }
 
 extern "C" int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, detrb_bf16 *dx,
-                                 int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream)
+                                 int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(dy && argmax && dx && C % 8 == 0, "detrb_maxpool_bwd: bad args");
     DETRB_REQUIRE(XH <= 65535 && B <= 65535, "detrb_maxpool_bwd: grid too large");
     DETRB_REQUIRE(XH >= IH && XW >= IW, "detrb_maxpool_bwd: allocated extent smaller than the image");
     DETRB_LAUNCH(maxpool_bwd_kernel, dim3((unsigned)ceil_div(((XW + 1) / 2) * (C / 8), 256), (unsigned)((XH + 1) / 2), (unsigned)B), dim3(256), 0, (cudaStream_t)stream, (const bf16 *)dy, argmax, (bf16 *)dx,
-                                                                                          B, IH, IW, C, OH, OW, XH, XW);
+                                                                                          B, IH, IW, C, OH, OW, XH, XW, (long long)split);
     DETRB_CHECK_LAUNCH("maxpool_bwd_kernel");
     return DETRB_OK;
 }

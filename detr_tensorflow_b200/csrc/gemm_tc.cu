@@ -80,11 +80,15 @@ struct SmemLayout {
 
 // IM2COL: the A operand is gathered by a TMA im2col tensor map over the NHWC activation (implicit-GEMM convolution:
 // 3x3 / strided / transposed); `aux` carries the effective padding and the im2col-tap -> weight-tap map.
-template <int BN, int STAGES, bool IM2COL>
-__global__ void __launch_bounds__(NTHREADS_TC, BN == 64 ? 5 : 1)
+// SPLIT (parity precision, include/detrb.h): A and W are bf16 pairs (hi plane / lo plane, tensor maps map_a2 / map_b2 for the lo
+// planes); the k-loop runs three passes -- A_hi*W_hi, A_lo*W_hi, A_hi*W_lo -- through the same stages into the same TMEM
+// accumulator; the epilogue (direct stores) reads residuals as hi + lo and writes the result as a pair.
+template <int BN, int STAGES, bool IM2COL, bool SPLIT = false>
+__global__ void __launch_bounds__(NTHREADS_TC, (BN == 64 && !SPLIT) ? 5 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const __grid_constant__ CUtensorMap map_m, const detrb_igemm_t p, const ConvAux aux, const int tma_epi)
+               const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_b2, const detrb_igemm_t p, const ConvAux aux, const int tma_epi)
 {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -102,13 +106,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
-    const int nk = p.K / TBK;
+    const int nk1 = p.K / TBK;
+    const int nk = SPLIT ? 3 * nk1 : nk1;
+    const long long split = SPLIT ? (long long)p.split : 0ll;
     const long long t_entry = TRACE_NOW();
     (void)t_entry;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (SPLIT) { tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b2); }
         if (tma_epi) {
             tma_prefetch_desc(&map_c);
             if (p.residual) tma_prefetch_desc(&map_r);
@@ -146,21 +153,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int st = p.mode == 0 ? p.stride : 1;
                 w0 = ox * st - aux.pad; h0 = oy * st - aux.pad;
             }
-            for (int kb = 0; kb < nk; kb++) {
+            for (int kbt = 0; kbt < nk; kbt++) {
+                const int part = SPLIT ? kbt / nk1 : 0, kb = kbt - part * nk1;
+                const CUtensorMap *pa = (SPLIT && part == 1) ? &map_a2 : &map_a;
+                const CUtensorMap *pb = (SPLIT && part == 2) ? &map_b2 : &map_b;
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
                 const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
                 if (IM2COL) {
                     const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                    tma_load_im2col(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
-                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
+                    tma_load_im2col(a_dst, pa, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    tma_load_2d(a_dst + L::A_BYTES, pb, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
                 } else {
                     // sliding-window A (a_kb_rows > 0): k-block kb is the 64-element run that starts kb * a_kb_rows rows further down
-                    tma_load_2d(a_dst, &map_a, full_bar(stage), p.a_kb_rows ? 0 : kb * TBK, m0 + kb * p.a_kb_rows);
-                    tma_load_2d(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                    tma_load_2d(a_dst, pa, full_bar(stage), p.a_kb_rows ? 0 : kb * TBK, m0 + kb * p.a_kb_rows);
+                    tma_load_2d(a_dst + L::A_BYTES, pb, full_bar(stage), kb * TBK, n0);
                 }
-                if (kb == 0 && tma_epi && ((p.residual && !r_early) || p.mask)) {
+                if (kbt == 0 && tma_epi && ((p.residual && !r_early) || p.mask)) {
                     // the epilogue's late residual / mask tiles start their trip from DRAM now (into L2), not after the main loop
                     for (int cb = 0; cb < BN / 64 && n0 + cb * 64 < p.N; cb++) {
                         if (p.residual && !r_early) tma_prefetch_2d(&map_r, n0 + cb * 64, m0);
@@ -349,12 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float res[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) res[i] = 0.f;
-                if (R) {
-                    uint4 u = *reinterpret_cast<const uint4 *>(R + orow * p.ldr + n);
-                    float2 t;
-                    t = unpack_bf16x2(u.x); res[0] = t.x; res[1] = t.y; t = unpack_bf16x2(u.y); res[2] = t.x; res[3] = t.y;
-                    t = unpack_bf16x2(u.z); res[4] = t.x; res[5] = t.y; t = unpack_bf16x2(u.w); res[6] = t.x; res[7] = t.y;
-                }
+                if (R) sp_ld8(R + orow * p.ldr + n, split, res);
                 if (!(p.drop_p > 0.f)) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] += res[i];
@@ -385,15 +390,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
                 if (C) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(C + orow * p.ldc + n);
+                    bf16 *dst = C + orow * p.ldc + n;
                     if (p.accumulate) {
-                        uint4 u = *dst; float2 t;
-                        t = unpack_bf16x2(u.x); v[0] += t.x; v[1] += t.y; t = unpack_bf16x2(u.y); v[2] += t.x; v[3] += t.y;
-                        t = unpack_bf16x2(u.z); v[4] += t.x; v[5] += t.y; t = unpack_bf16x2(u.w); v[6] += t.x; v[7] += t.y;
+                        float old[8];
+                        sp_ld8(dst, split, old);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] += old[i];
                     }
-                    uint4 o;
-                    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                    *dst = o;
+                    sp_st8(dst, split, v);
                 }
                 if (p.Cf) {
                     float4 *dst = reinterpret_cast<float4 *>(p.Cf + orow * p.ldcf + n);
@@ -755,10 +759,11 @@ static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
 
-template <int BN, int STAGES, bool IM2COL, bool PERSIST = false, int OB = 1>
+template <int BN, int STAGES, bool IM2COL, bool PERSIST = false, int OB = 1, bool SPLIT = false>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
-    CUtensorMap ma, mb;
+    static_assert(!(PERSIST && SPLIT), "parity precision runs on the one-tile kernel");
+    CUtensorMap ma, mb, ma2, mb2;
     ConvAux aux;
     aux.pad = 0;
     for (int i = 0; i < 16; i++) aux.wtap[i] = i;
@@ -786,20 +791,27 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
                        p.OH, p.OW, p.KH, p.KW, st, aux.pad);
         int rc = detrb_make_im2col_map(&ma, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM, 1, 64);
         if (rc) return rc;
+        if (SPLIT) {
+            rc = detrb_make_im2col_map(&ma2, p.A + p.split, p.batch, p.IH, p.IW, p.Cin, p.lda, lower_w, lower_h, upper_w, upper_h, st, TBM, 1, 64);
+            if (rc) return rc;
+        }
     } else if (p.a_kb_rows > 0) {
         // sliding-window operand: every row is one 64-element run, consecutive rows start lda elements apart (they overlap when
         // lda < 64); the map spans the rows the last k-block of the last tile row can reach
         const uint64_t rows = (uint64_t)p.M + (uint64_t)(p.K / TBK - 1) * (uint64_t)p.a_kb_rows;
-        if (!make_map(&ma, p.A, rows, TBK, (uint64_t)p.lda, TBM))
+        if (!make_map(&ma, p.A, rows, TBK, (uint64_t)p.lda, TBM) || (SPLIT && !make_map(&ma2, p.A + p.split, rows, TBK, (uint64_t)p.lda, TBM)))
             DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(sliding A) failed (rows=%llu lda=%d)", (unsigned long long)rows, p.lda);
-    } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM)) {
+    } else if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM) ||
+               (SPLIT && !make_map(&ma2, p.A + p.split, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, TBM))) {
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(A) failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     }
-    if (!make_map(&mb, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN))
+    if (!make_map(&mb, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN) ||
+        (SPLIT && !make_map(&mb2, p.W + p.wsplit, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN)))
         DETRB_FAIL(DETRB_E_CUDA, "gemm_tc: cuTensorMapEncodeTiled(W) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
+    if (!SPLIT) { ma2 = ma; mb2 = mb; }
     // coalesced TMA epilogue whenever the output is a plain bf16 tile (no fp32 copy, scatter or read-modify-write)
     CUtensorMap mc = ma, mr = ma, mm = ma;
-    int tma_epi = (p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue) ? 1 : 0;
+    int tma_epi = (!SPLIT && p.C && !p.Cf && p.out_stride <= 1 && !p.accumulate && g_tma_epilogue) ? 1 : 0;
     if (tma_epi) {
         bool ok = make_map(&mc, p.C, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc, TBM);
         if (ok && p.residual) ok = make_map(&mr, p.residual, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldr, TBM);
@@ -833,7 +845,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
     using L = SmemLayout<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        DETRB_CUDA(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT>), cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
@@ -847,7 +859,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         if (STAGES == 1 && p.mask) early = 1;
     }
     const size_t smem = early ? L::TOTAL : L::BASE;
-    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL>), dim3(grid), dim3(NTHREADS_TC), smem, stream, ma, mb, mc, mr, mm, p, aux, tma_epi | (early << 1));
+    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT>), dim3(grid), dim3(NTHREADS_TC), smem, stream, ma, mb, mc, mr, mm, ma2, mb2, p, aux, tma_epi | (early << 1));
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
     }
@@ -951,6 +963,10 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
 template <bool IM2COL>
 static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
+    if (p.split) {            // parity precision: one-tile kernel, three k passes, direct-store epilogue
+        const bool wide = bn == 128 || (bn == 0 && p.N >= 128);
+        return wide ? launch_tc<128, 3, IM2COL, false, 1, true>(p, stream, cls) : launch_tc<64, 3, IM2COL, false, 1, true>(p, stream, cls);
+    }
     bool taken = false;
     int rc = dispatch_tcp<IM2COL>(p, bn, stream, cls, &taken);
     if (taken || rc) return rc;

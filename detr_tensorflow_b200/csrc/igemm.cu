@@ -67,12 +67,16 @@ igemm_kernel(const detrb_igemm_t p)
             rows[i].base = nullptr; rows[i].y0 = 0; rows[i].x0 = 0;
         }
     }
-    const int nk = p.K / BK;
+    // parity precision (p.split): three passes over the k-loop -- A_hi*W_hi, A_lo*W_hi, A_hi*W_lo -- into the same accumulators
+    const int nk1 = p.K / BK;
+    const int nk = p.split ? 3 * nk1 : nk1;
 
     auto load_stage = [&](int stage, int kb) {
         bf16 *a_dst = sA + stage * BM * LDS;
         bf16 *b_dst = sB + stage * BN * LDS;
-        const int k0 = kb * BK;
+        const int part = kb / nk1;
+        const int k0 = (kb - part * nk1) * BK;
+        const long long a_off = part == 1 ? p.split : 0, w_off = part == 2 ? p.wsplit : 0;
         if (STEM) {
             // k-block == one kernel row kh; 8 taps kw (8th has zero weights) x 4 channels
             const int kh = kb, kw = a_chunk;
@@ -102,7 +106,7 @@ igemm_kernel(const detrb_igemm_t p)
                     } else { iy = ty; ix = tx; }
                 }
                 ok = ok && iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW;
-                const bf16 *src = ok ? rows[i].base + ((size_t)iy * p.IW + ix) * p.lda + c0 + a_chunk * 8 : A;
+                const bf16 *src = ok ? rows[i].base + a_off + ((size_t)iy * p.IW + ix) * p.lda + c0 + a_chunk * 8 : A;
                 cp_async16(smem_u32(a_dst + r * LDS + a_chunk * 8), src, ok ? 16 : 0);
             }
         }
@@ -113,7 +117,7 @@ igemm_kernel(const detrb_igemm_t p)
                 int r = (tid >> 2) + i * 64;
                 int n = n0 + r;
                 bool ok = n < p.N;
-                const bf16 *src = ok ? W + (size_t)n * p.ldw + k0 + chunk * 8 : W;
+                const bf16 *src = ok ? W + w_off + (size_t)n * p.ldw + k0 + chunk * 8 : W;
                 cp_async16(smem_u32(b_dst + r * LDS + chunk * 8), src, ok ? 16 : 0);
             }
         }
@@ -193,7 +197,7 @@ igemm_kernel(const detrb_igemm_t p)
                 float v0 = acc[i][j][h * 2 + 0], v1 = acc[i][j][h * 2 + 1];
                 if (p.bias) { v0 += p.bias[n]; v1 += p.bias[n + 1]; }
                 float2 res = make_float2(0.f, 0.f);
-                if (R) res = unpack_bf16x2(*reinterpret_cast<const uint32_t *>(R + orow * p.ldr + n));
+                if (R) res = sp_ld2(R + orow * p.ldr + n, p.split);
                 // residual joins before the activation (conv blocks) unless dropout is active, in which case it
                 // is the un-dropped skip path and joins last (x + dropout(sublayer(x)), transformer.py:169,176)
                 if (!(p.drop_p > 0.f)) { v0 += res.x; v1 += res.y; }
@@ -211,9 +215,9 @@ igemm_kernel(const detrb_igemm_t p)
                     v1 = (k1 ? v1 * drop_scale : 0.f) + res.y;
                 }
                 if (C) {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(C + orow * p.ldc + n);
-                    if (p.accumulate) { float2 o = unpack_bf16x2(*dst); v0 += o.x; v1 += o.y; }
-                    *dst = pack_bf16x2(v0, v1);
+                    bf16 *dst = C + orow * p.ldc + n;
+                    if (p.accumulate) { float2 o = sp_ld2(dst, p.split); v0 += o.x; v1 += o.y; }
+                    sp_st2(dst, p.split, v0, v1);
                 }
                 if (p.Cf) {
                     float2 *dst = reinterpret_cast<float2 *>(p.Cf + orow * p.ldcf + n);
@@ -258,6 +262,8 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(!p.residual || p.ldr % 2 == 0, "detrb_igemm: ldr must be even");
     DETRB_REQUIRE(!p.mask || p.ldm % 2 == 0, "detrb_igemm: ldm must be even");
     DETRB_REQUIRE(p.drop_p >= 0.f && p.drop_p < 1.f, "detrb_igemm: drop_p");
+    DETRB_REQUIRE((p.split != 0) == (p.wsplit != 0) && p.split >= 0 && p.wsplit >= 0 && p.split % 8 == 0 && p.wsplit % 8 == 0,
+                  "detrb_igemm: split=%lld wsplit=%lld (both zero, or both positive multiples of 8)", (long long)p.split, (long long)p.wsplit);
     if (p.out_stride < 1) p.out_stride = 1;
     if (p.a_kb_rows) {                                                // sliding-window A: a plain GEMM as far as the tcgen05 kernel is concerned
         DETRB_REQUIRE(p.a_kb_rows > 0 && detrb_gemm_tc_kind(p) == 1, "detrb_igemm: a_kb_rows needs plain geometry and the tcgen05 path");
@@ -269,6 +275,7 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
     }
     const bool stem = (p.Cin == 4);
     if (stem) {
+        DETRB_REQUIRE(!p.split, "detrb_igemm: the Cin=4 stem path has no parity-precision variant");
         DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4 && p.mode == 0,
                       "detrb_igemm: stem path needs Cin=4, KW=8, K=KH*32, lda=4, mode=0");
         return p.N >= 128 ? launch<128, true>(p, stream) : launch<64, true>(p, stream);

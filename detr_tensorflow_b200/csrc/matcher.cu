@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256)
 set_loss_kernel(const float *logits, int ldl, const float *boxes, const float *t_bbox, const int64_t *t_class,
                 const int32_t *match, int L, int B, int Q, int C, int bg,
                 const float *normalisers, float loss_scale, float *sums,
-                bf16 *d_logits, int ld_dl, bf16 *d_boxpre, int ld_db)
+                bf16 *d_logits, int ld_dl, bf16 *d_boxpre, int ld_db, long long split)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -253,7 +253,7 @@ set_loss_kernel(const float *logits, int ldl, const float *boxes, const float *t
             int c = lane + 32 * k;
             if (c < ld_dl) {
                 float gval = c < C ? gs * (e[k] / se - (c == cls ? 1.f : 0.f)) : 0.f;
-                dl[c] = __float2bfloat16(gval);
+                sp_st1(dl + c, split, gval);
             }
         }
     }
@@ -281,17 +281,21 @@ set_loss_kernel(const float *logits, int ldl, const float *boxes, const float *t
         }
         if (d_boxpre) {
             bf16 *db = d_boxpre + (size_t)row * ld_db;
-            for (int k = 0; k < ld_db; k++) db[k] = __float2bfloat16(k < 4 ? g4[k] : 0.f);
+            for (int k = 0; k < ld_db; k++) sp_st1(db + k, split, k < 4 ? g4[k] : 0.f);
         }
     }
 }
 
 __global__ void set_loss_finalize_kernel(const float *sums, const float *t_bbox, int L, int B, int Q,
                                          const float *normalisers, float loss_scale,
-                                         float *losses, float *total)
+                                         float *losses, float *total, const int32_t *status, int nstatus)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
+    // a matcher problem with NaN / -inf costs (status != 0): the reference raises through scipy; here the result is poisoned
+    int bad = 0;
+    if (status) for (int i = threadIdx.x; i < nstatus; i += 32) bad |= status[i];
+    bad = __any_sync(0xffffffffu, bad != 0);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float n_matched, sum_w;
     if (normalisers) { n_matched = normalisers[0]; sum_w = normalisers[1]; }
@@ -312,8 +316,9 @@ __global__ void set_loss_finalize_kernel(const float *sums, const float *t_bbox,
         o[4] = s[6] / n_matched;         // giou_loss
         o[5] = s[7] / n_matched;         // l1_loss
         tot += 1.f * o[0] + 2.f * o[4] + 5.f * o[5];
+        if (bad) for (int k = 0; k < 6; k++) o[k] = __int_as_float(0x7fc00000);
     }
-    *total = tot * loss_scale;
+    *total = bad ? __int_as_float(0x7fc00000) : tot * loss_scale;
 }
 
 constexpr size_t matcher_smem_bytes()
@@ -335,10 +340,12 @@ extern "C" int detrb_matcher(const float *logits, int ldl, const float *boxes, c
     DETRB_REQUIRE(Q > 0 && Q <= MAXQ, "detrb_matcher: Q=%d out of range (1..%d)", Q, MAXQ);
     DETRB_REQUIRE(C > 0 && ldl >= C, "detrb_matcher: C=%d ldl=%d", C, ldl);
     constexpr size_t smem = matcher_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};          // the opt-in is per device
+    int dev = 0;
+    DETRB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         DETRB_CUDA(cudaFuncSetAttribute(matcher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     DETRB_LAUNCH(matcher_kernel, dim3(P), dim3(128), smem, (cudaStream_t)stream, logits, ldl, boxes, t_bbox, t_class, B, Q, C,
                                                           fcost_class, fcost_bbox, fcost_giou,
@@ -350,7 +357,8 @@ extern "C" int detrb_matcher(const float *logits, int ldl, const float *boxes, c
 extern "C" int detrb_set_loss(const float *logits, int ldl, const float *boxes, const float *t_bbox, const int64_t *t_class,
                               const int32_t *match, int L, int B, int Q, int C, int background_class,
                               const float *normalisers, float loss_scale, float *sums, float *losses, float *total,
-                              detrb_bf16 *d_logits, int ld_dl, detrb_bf16 *d_boxpre, int ld_db, detrb_stream_t stream_)
+                              detrb_bf16 *d_logits, int ld_dl, detrb_bf16 *d_boxpre, int ld_db, const int32_t *status, int64_t split,
+                              detrb_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     DETRB_REQUIRE(logits && boxes && t_bbox && t_class && match && sums && losses && total, "detrb_set_loss: null pointer");
@@ -360,9 +368,9 @@ extern "C" int detrb_set_loss(const float *logits, int ldl, const float *boxes, 
     DETRB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 8 * L, stream));
     int rows = L * B * Q;
     DETRB_LAUNCH(set_loss_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class,
-                                                           normalisers, loss_scale, sums, (bf16 *)d_logits, ld_dl, (bf16 *)d_boxpre, ld_db);
+                                                           normalisers, loss_scale, sums, (bf16 *)d_logits, ld_dl, (bf16 *)d_boxpre, ld_db, (long long)split);
     DETRB_CHECK_LAUNCH("set_loss_kernel");
-    DETRB_LAUNCH(set_loss_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, t_bbox, L, B, Q, normalisers, loss_scale, losses, total);
+    DETRB_LAUNCH(set_loss_finalize_kernel, dim3(1), dim3(32), 0, stream, sums, t_bbox, L, B, Q, normalisers, loss_scale, losses, total, status, L * B);
     DETRB_CHECK_LAUNCH("set_loss_finalize_kernel");
     return DETRB_OK;
 }

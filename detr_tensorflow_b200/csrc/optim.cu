@@ -145,7 +145,7 @@ chunk_adam_kernel(float *params, const float *grads, float *m, float *v, const i
 // along n -- both as packed bf16 pairs in full 128-byte rows.  Cin and the row strides are even (checked on the host).
 constexpr int PT = 64;
 __global__ void __launch_bounds__(256)
-prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
+prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots, long long wsplit)
 {
     pdl_trigger();      // let the next kernel of the stream become resident
     pdl_wait();         // predecessor complete, its writes visible
@@ -169,7 +169,7 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
             w = *reinterpret_cast<const float2 *>(d.master + ((size_t)n * d.taps + tap) * d.Cin + c);
             const float f = d.fold ? d.fold[n] : 1.f;
             w.x *= f; w.y *= f;
-            if (d.Wf) *reinterpret_cast<uint32_t *>(reinterpret_cast<bf16 *>(d.Wf) + (size_t)n * d.ldf + tap * d.Cin + c) = pack_bf16x2(w.x, w.y);
+            if (d.Wf) sp_st2(reinterpret_cast<bf16 *>(d.Wf) + (size_t)n * d.ldf + tap * d.Cin + c, wsplit, w.x, w.y);
         }
         tile[r][2 * tx] = w.x; tile[r][2 * tx + 1] = w.y;
     }
@@ -180,19 +180,46 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots)
         const int cc = ci * PT + r;
         if (cc >= d.Cin || n >= d.N) continue;
         bf16 *dst = reinterpret_cast<bf16 *>(d.Wd) + ((size_t)cc * d.taps + tap) * d.ldd + n;
-        if (n + 1 < d.N) *reinterpret_cast<uint32_t *>(dst) = pack_bf16x2(tile[2 * tx][r], tile[2 * tx + 1][r]);
-        else *dst = __float2bfloat16(tile[2 * tx][r]);
+        if (n + 1 < d.N) sp_st2(dst, wsplit, tile[2 * tx][r], tile[2 * tx + 1][r]);
+        else sp_st1(dst, wsplit, tile[2 * tx][r]);
+    }
+}
+
+// gradient accumulation over micro-batches (optimizers.py:150-157): acc = (zero_first ? 0 : acc) + g, float4 grid-stride
+__global__ void __launch_bounds__(256)
+accumulate_kernel(float4 *acc, const float4 *g, long long n4, int zero_first)
+{
+    pdl_trigger();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 b = g[i];
+        float4 a = zero_first ? make_float4(0.f, 0.f, 0.f, 0.f) : acc[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        acc[i] = a;
     }
 }
 
 }  // namespace
 
-extern "C" int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream)
+extern "C" int detrb_accumulate(float *acc, const float *g, int64_t n, int zero_first, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(acc && g && n > 0 && n % 4 == 0 && (((uintptr_t)acc | (uintptr_t)g) & 15) == 0, "detrb_accumulate: bad args");
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    DETRB_LAUNCH(accumulate_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<float4 *>(acc),
+                 reinterpret_cast<const float4 *>(g), n4, zero_first);
+    DETRB_CHECK_LAUNCH("accumulate_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, int64_t wsplit, detrb_stream_t stream)
 {
     DETRB_REQUIRE(descs && nslots > 0 && total_tiles > 0, "detrb_prep_weights_multi: bad args");
     // descs live in device memory (the table is built once by the caller): tile_begin counts 64x64 tiles, taps * ceil(N/64) *
     // ceil(Cin/64) per slot; Cin, ldf, ldd even and master / Wf / Wd 8 / 4 / 4-byte aligned
-    DETRB_LAUNCH(prep_weights_multi_kernel, dim3(total_tiles), dim3(256), 0, (cudaStream_t)stream, descs, nslots);
+    DETRB_LAUNCH(prep_weights_multi_kernel, dim3(total_tiles), dim3(256), 0, (cudaStream_t)stream, descs, nslots, (long long)wsplit);
     DETRB_CHECK_LAUNCH("prep_weights_multi_kernel");
     return DETRB_OK;
 }

@@ -49,8 +49,8 @@ __global__ void normalize_u8_tail_kernel(const uint8_t *img, const float *lut, i
 // uint8 NHWC3 frame -> normalised bf16 space-to-depth(2) tensor [B, ceil(H/2), ceil(W/2), 16]: the fp32 image never exists
 // (same channel order as image_to_s2d16_kernel: (ry*2+rx)*3 + c, 4 zero channels; pixels outside the frame are 0)
 __global__ void __launch_bounds__(256)
-image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restrict__ lut, int swap, uint4 *__restrict__ out,
-                         int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP)
+image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restrict__ lut, int swap, bf16 *__restrict__ out,
+                         int B, int H, int W, int H2, int W2, int pt, int pl, int HP, int WP, long long split)
 {
     pdl_trigger();
     pdl_wait();
@@ -80,11 +80,12 @@ image_u8_to_s2d16_kernel(const uint8_t *__restrict__ img, const float *__restric
             for (int c = 0; c < 3; c++) v[(ry * 2 + rx) * 3 + c] = s_lut[c * 256 + px[swap ? 2 - c : c]];
         }
     }
-    uint4 o0, o1;
-    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    float lo8[8], hi8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo8[k] = v[k]; hi8[k] = v[8 + k]; }
     const size_t i = ((size_t)b * HP + yp) * WP + xp;
-    out[i * 2] = o0; out[i * 2 + 1] = o1;
+    sp_st8(out + i * 16, split, lo8);
+    sp_st8(out + i * 16 + 8, split, hi8);
 }
 
 // ------------------------------------------------------------------------------------------ inference post-process
@@ -187,14 +188,14 @@ extern "C" int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap
 }
 
 extern "C" int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
-                                       int pad_top, int pad_left, int HP, int WP, detrb_stream_t stream)
+                                       int pad_top, int pad_left, int HP, int WP, int64_t split, detrb_stream_t stream)
 {
     DETRB_REQUIRE(img && lut && out && B > 0 && H > 0 && W > 0, "detrb_image_u8_to_s2d16: bad args");
     const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
     DETRB_REQUIRE(pad_top >= 0 && pad_left >= 0 && HP >= H2 + pad_top && WP >= W2 + pad_left, "detrb_image_u8_to_s2d16: padded size too small");
     DETRB_REQUIRE(HP <= 65535 && B <= 65535, "detrb_image_u8_to_s2d16: grid too large");
     DETRB_LAUNCH(image_u8_to_s2d16_kernel, dim3((unsigned)ceil_div(WP, 256), (unsigned)HP, (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
-                 img, lut, swap_rb, (uint4 *)out, B, H, W, H2, W2, pad_top, pad_left, HP, WP);
+                 img, lut, swap_rb, (bf16 *)out, B, H, W, H2, W2, pad_top, pad_left, HP, WP, (long long)split);
     DETRB_CHECK_LAUNCH("image_u8_to_s2d16_kernel");
     return DETRB_OK;
 }

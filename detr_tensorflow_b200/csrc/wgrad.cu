@@ -30,7 +30,9 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
     const int m_begin = blockIdx.z * pix_per_split;
     const int m_end = min(p.M, m_begin + pix_per_split);
     if (m_begin >= m_end) return;
-    const int nsteps = (m_end - m_begin + BP - 1) / BP;
+    // parity precision (p.split): three passes over the pixel range -- dY_hi^T A_hi, dY_lo^T A_hi, dY_hi^T A_lo
+    const int nsteps1 = (m_end - m_begin + BP - 1) / BP;
+    const int nsteps = p.split ? 3 * nsteps1 : nsteps1;
 
     const bf16 *A = reinterpret_cast<const bf16 *>(p.A);
     const bf16 *dY = reinterpret_cast<const bf16 *>(p.dY);
@@ -60,13 +62,15 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
     auto load_stage = [&](int stage, int step) {
         bf16 *y_dst = sY + stage * BP * LDT;
         bf16 *a_dst = sA + stage * BP * LDT;
-        const int mb = m_begin + step * BP;
+        const int part = step / nsteps1;
+        const long long y_off = part == 1 ? p.split : 0, a_off = part == 2 ? p.split : 0;
+        const int mb = m_begin + (step - part * nsteps1) * BP;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             int r = y_row0 + i * 16;
             int m = mb + r;
             bool ok = ny_ok && m < m_end;
-            const bf16 *src = ok ? dY + (size_t)m * p.ldy + ny : dY;
+            const bf16 *src = ok ? dY + y_off + (size_t)m * p.ldy + ny : dY;
             cp_async16(smem_u32(y_dst + r * LDT + y_chunk * 8), src, ok ? 16 : 0);
         }
 #pragma unroll
@@ -80,7 +84,7 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
                 int oy = rem / p.OW, ox = rem - oy * p.OW;
                 int iy = oy * p.stride - p.pad + a_kh, ix = ox * p.stride - p.pad + a_kw;
                 ok = iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW;
-                if (ok) src = A + (((size_t)b * p.IH + iy) * p.IW + ix) * p.lda + a_c;
+                if (ok) src = A + a_off + (((size_t)b * p.IH + iy) * p.IW + ix) * p.lda + a_c;
             }
             if (STEM) cp_async8(smem_u32(a_dst + r * LDT + a_chunk * 4), src, ok ? 8 : 0);
             else      cp_async16(smem_u32(a_dst + r * LDT + a_chunk * 8), src, ok ? 16 : 0);
@@ -112,7 +116,7 @@ wgrad_kernel(const detrb_wgrad_t p, int pix_per_split)
         }
         const bf16 *y_s = sY + (step % STAGES) * BP * LDT;
         const bf16 *a_s = sA + (step % STAGES) * BP * LDT;
-        if (do_bias) {                                    // bias gradient = column sums of dY: free ride on the staged tile
+        if (do_bias && step < 2 * nsteps1) {              // bias gradient = column sums of dY (hi and lo passes): free ride on the staged tile
 #pragma unroll 8
             for (int pix = 0; pix < BP; pix++) bias_acc += __bfloat162float(y_s[pix * LDT + tid]);
         }
@@ -175,6 +179,7 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     DETRB_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "detrb_wgrad: empty problem");
     DETRB_REQUIRE(p.M == p.batch * p.OH * p.OW, "detrb_wgrad: M=%d != batch*OH*OW", p.M);
     DETRB_REQUIRE(p.ldy >= ((p.N + 7) & ~7) && p.ldy % 8 == 0, "detrb_wgrad: ldy=%d must cover N=%d rounded to 8", p.ldy, p.N);
+    DETRB_REQUIRE(p.split >= 0 && p.split % 8 == 0, "detrb_wgrad: split=%lld", (long long)p.split);
     if (p.a_kb_rows || p.k_mask) {                             // sliding-window A / stem column mask: tcgen05 kernel only
         DETRB_REQUIRE(p.a_kb_rows >= 0 && p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0 && detrb_wgrad_tc_supported(p),
                       "detrb_wgrad: a_kb_rows / k_mask need plain geometry and the tcgen05 kernel");
@@ -184,7 +189,7 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
         return detrb_wgrad_tc(p, stream);                      // bias gradient fused (k-tile 0 CTAs)
     }
     const bool stem = (p.Cin == 4);
-    if (stem) DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4, "detrb_wgrad: stem geometry");
+    if (stem) DETRB_REQUIRE(p.KW == 8 && p.K == p.KH * 32 && p.lda == 4 && !p.split, "detrb_wgrad: stem geometry");
     else DETRB_REQUIRE(p.Cin % 8 == 0 && p.K == p.KH * p.KW * p.Cin && p.lda % 8 == 0, "detrb_wgrad: Cin=%d K=%d lda=%d", p.Cin, p.K, p.lda);
 
     const int tiles = ceil_div(p.K, TK) * ceil_div(p.N, TN);

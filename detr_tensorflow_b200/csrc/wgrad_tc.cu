@@ -37,9 +37,12 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 // kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t WIDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WK >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
 
-template <bool IM2COL>
+// SPLIT (parity precision, include/detrb.h): dY and A are bf16 pairs (lo planes through map_y2 / map_x2); the pixel range is
+// walked three times -- dY_hi^T A_hi, dY_lo^T A_hi, dY_hi^T A_lo -- into the same TMEM accumulator.
+template <bool IM2COL, bool SPLIT>
 __global__ void __launch_bounds__(WTHREADS)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, const detrb_wgrad_t p,
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ CUtensorMap map_y2, const __grid_constant__ CUtensorMap map_x2, const detrb_wgrad_t p,
                 const int pix_per_split, const int stem_mask)
 {
     constexpr int KT = WK;                                              // k columns of this CTA's dW tile (TMEM columns)
@@ -58,13 +61,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     const int k0 = blockIdx.x * KT, n0 = blockIdx.y * WN;
     const int m_begin = blockIdx.z * pix_per_split;
     const int m_end = min(p.M, m_begin + pix_per_split);
-    const int nsteps = (m_end - m_begin + WP - 1) / WP;     // >= 1 by construction of the grid
+    const int nsteps1 = (m_end - m_begin + WP - 1) / WP;    // >= 1 by construction of the grid
+    const int nsteps = SPLIT ? 3 * nsteps1 : nsteps1;
 
     // bias gradient (column sums of dY) fused: the k-tile-0 CTAs' otherwise idle epilogue warps add up the dY boxes of every stage
     const bool do_bias = p.dbias != nullptr && blockIdx.x == 0;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_y);
         tma_prefetch_desc(&map_x);
+        if (SPLIT) { tma_prefetch_desc(&map_y2); tma_prefetch_desc(&map_x2); }
         for (int s = 0; s < STG; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_bias ? 5 : 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -92,25 +97,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             const int ohw = p.OH * p.OW;
             int stage = 0; uint32_t phase = 0;
             for (int st = 0; st < nsteps; st++) {
-                const int m = m_begin + st * WP;
+                const int part = SPLIT ? st / nsteps1 : 0;
+                const CUtensorMap *py = (SPLIT && part == 1) ? &map_y2 : &map_y;
+                const CUtensorMap *px = (SPLIT && part == 2) ? &map_x2 : &map_x;
+                const int m = m_begin + (st - part * nsteps1) * WP;
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), STG_BYTES);
                 const uint32_t dst = smem_base + stage * STG_BYTES;
-                tma_load_2d(dst, &map_y, full_bar(stage), n0, m);                         // dY[m.., n0 .. n0+64)
-                tma_load_2d(dst + BOX_BYTES, &map_y, full_bar(stage), n0 + 64, m);
+                tma_load_2d(dst, py, full_bar(stage), n0, m);                             // dY[m.., n0 .. n0+64)
+                tma_load_2d(dst + BOX_BYTES, py, full_bar(stage), n0 + 64, m);
                 if (IM2COL) {
                     const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                     const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int kh = tap[j] / p.KW, kw = tap[j] - kh * p.KW;
-                        tma_load_im2col(dst + (2 + j) * BOX_BYTES, &map_x, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                        tma_load_im2col(dst + (2 + j) * BOX_BYTES, px, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
                     }
                 } else {
                     // sliding-window A (a_kb_rows > 0): 64-column block j is the 64-element run j * a_kb_rows rows further down
                     const int kb = k0 / 64, sl = p.a_kb_rows;
-                    tma_load_2d(dst + 2 * BOX_BYTES, &map_x, full_bar(stage), sl ? 0 : k0, m + kb * sl);
-                    tma_load_2d(dst + 3 * BOX_BYTES, &map_x, full_bar(stage), sl ? 0 : k0 + 64, m + (kb + 1) * sl);
+                    tma_load_2d(dst + 2 * BOX_BYTES, px, full_bar(stage), sl ? 0 : k0, m + kb * sl);
+                    tma_load_2d(dst + 3 * BOX_BYTES, px, full_bar(stage), sl ? 0 : k0 + 64, m + (kb + 1) * sl);
                 }
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
@@ -145,8 +153,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             for (int st = 0; st < nsteps; st++) {
                 mbar_wait(full_bar(stage), phase);
                 const uint32_t base = smem_base + stage * STG_BYTES + box_off + within;
+                const bool count = !SPLIT || st < 2 * nsteps1;            // the third pass stages dY_hi again
 #pragma unroll 8
-                for (int r = half * 32; r < half * 32 + 32; r++) {
+                for (int r = half * 32; count && r < half * 32 + 32; r++) {
                     uint32_t u;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(base + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
                     const float2 f = unpack_bf16x2(u);
@@ -237,15 +246,19 @@ bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {
     const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
-    CUtensorMap my, mx;
-    if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64))
+    CUtensorMap my, mx, my2, mx2;
+    const bool sp = p.split != 0;
+    if (!detrb_make_tiled_map(&my, p.dY, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64) ||
+        (sp && !detrb_make_tiled_map(&my2, p.dY + p.split, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldy, WP, 64)))
         DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for dY failed (M=%d N=%d ldy=%d)", p.M, p.N, p.ldy);
     if (plain && p.a_kb_rows > 0) {
         const uint64_t rows = (uint64_t)p.M + (uint64_t)(p.K / 64 - 1) * (uint64_t)p.a_kb_rows;
-        if (p.K % WK != 0 || !detrb_make_tiled_map(&mx, p.A, rows, 64, (uint64_t)p.lda, WP, 64))
+        if (p.K % WK != 0 || !detrb_make_tiled_map(&mx, p.A, rows, 64, (uint64_t)p.lda, WP, 64) ||
+            (sp && !detrb_make_tiled_map(&mx2, p.A + p.split, rows, 64, (uint64_t)p.lda, WP, 64)))
             DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for the sliding-window A failed (rows=%llu K=%d lda=%d)", (unsigned long long)rows, p.K, p.lda);
     } else if (plain) {
-        if (!detrb_make_tiled_map(&mx, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64))
+        if (!detrb_make_tiled_map(&mx, p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64) ||
+            (sp && !detrb_make_tiled_map(&mx2, p.A + p.split, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, WP, 64)))
             DETRB_FAIL(DETRB_E_CUDA, "wgrad_tc: tensor map for A failed (M=%d K=%d lda=%d)", p.M, p.K, p.lda);
     } else {
         const int lower = -p.pad;
@@ -254,7 +267,12 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
             DETRB_FAIL(DETRB_E_SHAPE, "wgrad_tc: inconsistent conv geometry");
         int rc = detrb_make_im2col_map(&mx, p.A, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP, 1, 64);
         if (rc) return rc;
+        if (sp) {
+            rc = detrb_make_im2col_map(&mx2, p.A + p.split, p.batch, p.IH, p.IW, p.Cin, p.lda, lower, lower, upper_w, upper_h, p.stride, WP, 1, 64);
+            if (rc) return rc;
+        }
     }
+    if (!sp) { my2 = my; mx2 = mx; }
     const int kt = WK;
     const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
     int splits = ceil_div(148 * 2, tiles);               // one wave of 2 CTAs per SM: fewer fp32 atomics per gradient element
@@ -265,16 +283,22 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     splits = ceil_div(p.M, pix_per_split);
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
+        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
         configured = true;
     }
     dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
     const int stem_mask = p.k_mask ? 1 : 0;
-    if (plain) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, stem_mask);
+    if (plain && !sp) {
+        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask);
+    } else if (!sp) {
+        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0);
+    } else if (plain) {
+        DETRB_LAUNCH((wgrad_tc_kernel<false, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask);
     } else {
-        DETRB_LAUNCH((wgrad_tc_kernel<true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, p, pix_per_split, 0);
+        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0);
     }
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;

@@ -7,6 +7,10 @@ Data layout in HBM
                  kernels are stored [Cout][tap][Cin] (GEMM K-major), Linear kernels [out][in] as in the reference
   * bf16 weight copies in kernel layouts (forward [N][K], data-gradient [Cin][tap][N]) refreshed after each
                  optimizer step; FrozenBatchNorm2D is folded into them (scale) and into the epilogue bias (shift)
+  * precision="parity": every bf16 activation / weight copy is a PAIR of bf16 planes (hi, lo = x - hi; include/detrb.h):
+                 all activation buffers are carved from one [2, P] arena so that the lo twin of any view sits exactly P
+                 elements after it (one plane stride for every kernel call); the GEMM kernels run three tensor-core passes
+                 per product, attention runs in fp32 -- the mode the fp32-tolerance parity tests use
 
 Reference being replaced: detr_tf/networks/{detr,resnet_backbone,transformer,position_embeddings,custom_layers}.py,
 detr_tf/loss/{loss,hungarian_matching}.py, detr_tf/optimizers.py, detr_tf/training.py:9-25.
@@ -51,7 +55,13 @@ class Slot:
 
 class Engine:
     def __init__(self, device="cuda", backbone="resnet50", num_classes=92, num_encoder_layers=6,
-                 num_decoder_layers=6, num_queries=100, dropout=0.1, seed=0, nb_class=None):
+                 num_decoder_layers=6, num_queries=100, dropout=0.1, seed=0, nb_class=None, precision="bf16"):
+        if precision not in ("bf16", "parity"):
+            raise ValueError("precision must be 'bf16' (throughput) or 'parity' (bf16 pairs, fp32-class arithmetic)")
+        self.precision = precision
+        self.paired = precision == "parity"
+        self.plane = 0                              # activation plane stride (elements), set by _plan in parity precision
+        self.wplane = 0                             # weight-copy plane stride
         self.device = torch.device(device)
         self.lib = _lib.lib()
         if self.device.type != "cuda" and not getattr(_lib, "_EMULATED", False):
@@ -75,7 +85,7 @@ class Engine:
         self.launches = 0
         self.acc = None
         # weight gradients run on a side stream, concurrently with the data-gradient chain (they only feed the optimizer)
-        self.overlap_wgrad = self.device.type == "cuda"
+        self.overlap_wgrad = self.device.type == "cuda" and not self.paired     # (parity precision: one stream, one arena)
         self.overlap_fwd = os.environ.get("DETRB_NO_FWD_FORK") is None        # forward-pass branches on the side stream
         self.overlap_dmem = os.environ.get("DETRB_NO_DMEM_FORK") is None      # d(memory) accumulation on the side stream
         self._wstream = None
@@ -165,10 +175,10 @@ class Engine:
                 s.fold = torch.ones(co, dtype=F32, device=dev)
                 s.shift = torch.zeros(co, dtype=F32, device=dev)
                 s.bn_prefix = bn_prefix
-            s.Wf = torch.zeros(co, s.K, dtype=BF16, device=dev)
+            s.wf_shape = (co, s.K)
             if not stem:
                 s.ldd = _round_up(co, 32)
-                s.Wd = torch.zeros(ci, s.taps, s.ldd, dtype=BF16, device=dev)
+                s.wd_shape = (ci, s.taps, s.ldd)
             s.geom = (4, 4, 4, 1, 2) if stem else (kh, kw, kwp, stride, pad)
             self.slots[prefix] = s
             return s
@@ -184,9 +194,9 @@ class Engine:
             s.N, s.taps, s.Cin, s.K = o_, 1, i_, i_
             s.master, s.grad = view(self.params, kname), view(self.grads, kname)
             s.bias, s.bias_grad = view(self.params, bname), view(self.grads, bname)
-            s.Wf = torch.zeros(o_, i_, dtype=BF16, device=dev)
+            s.wf_shape = (o_, i_)
             s.ldd = _round_up(o_, 32)
-            s.Wd = torch.zeros(i_, 1, s.ldd, dtype=BF16, device=dev)
+            s.wd_shape = (i_, 1, s.ldd)
             self.slots[prefix] = s
             return s
 
@@ -228,9 +238,29 @@ class Engine:
                                  n1=ln_views(p + "/norm1"), n2=ln_views(p + "/norm2"), n3=ln_views(p + "/norm3")))
         self.dec_norm = ln_views("transformer/decoder/norm")
         self.h_cls, self.h_b0, self.h_b1, self.h_b2 = (lin_slot(n) for n in head_names(self.nb_class))
+        # bf16 kernel-layout weight copies: one tensor per layout, or (parity precision) slices of one [2, PW] arena of pairs
+        def numel(shape):
+            n = 1
+            for v in shape:
+                n *= v
+            return n
+        if self.paired:
+            total = sum(_round_up(numel(sh), 64) for s in self.slots.values() for sh in (s.wf_shape, getattr(s, "wd_shape", None)) if sh)
+            self.wplane = _round_up(total, 64)
+            self._warena = torch.zeros(2 * self.wplane, dtype=BF16, device=dev)
+        woff = 0
+        for s in self.slots.values():
+            for attr, sh in (("Wf", s.wf_shape), ("Wd", getattr(s, "wd_shape", None))):
+                if sh is None:
+                    continue
+                if self.paired:
+                    setattr(s, attr, self._warena[woff:woff + numel(sh)].view(*sh))
+                    woff += _round_up(numel(sh), 64)
+                else:
+                    setattr(s, attr, torch.zeros(*sh, dtype=BF16, device=dev))
         self.bn = {n: torch.zeros(p.shape, dtype=F32, device=dev) for n, p in spec.items() if p.kind.startswith("bn_")}
         self.query_embed = torch.zeros(self.Q, self.d, dtype=F32, device=dev)
-        self.query_pos = torch.zeros(self.Q, self.d, dtype=BF16, device=dev)
+        self.query_pos = None if self.paired else torch.zeros(self.Q, self.d, dtype=BF16, device=dev)   # parity: lives in the arena (_plan)
 
     def load_params(self, ref_params):
         """ref_params: {reference name: tensor in the reference layout} (HWIO convs, [out,in] linears)."""
@@ -252,8 +282,26 @@ class Engine:
                 scale = self.bn[pre + "/weight"] * torch.rsqrt(self.bn[pre + "/running_var"] + 1e-5)
                 s.fold.copy_(scale)
                 s.shift.copy_(self.bn[pre + "/bias"] - self.bn[pre + "/running_mean"] * scale)
-        self.query_pos.copy_(self.query_embed.to(BF16))
+        if self.query_pos is not None:
+            self._store(self.query_pos, self.query_embed)
         self.refresh_weights()
+
+    # ---- parity precision: bf16 pairs
+    def _lo(self, t):
+        """the lo-plane twin of an activation view (parity precision only)"""
+        return self._arena.as_strided(t.size(), t.stride(), t.storage_offset() + self.plane)
+
+    def _store(self, dst, x):
+        """fp32 tensor -> activation storage (a bf16 tensor, or the pair of planes)"""
+        x = x.to(self.device, F32)
+        hi = x.to(BF16)
+        dst.copy_(hi)
+        if self.paired:
+            self._lo(dst).copy_((x - hi.to(F32)).to(BF16))
+
+    def value(self, t):
+        """fp32 value of an activation view (hi + lo in parity precision)"""
+        return t.to(F32) + self._lo(t).to(F32) if self.paired else t.to(F32)
 
     def _from_ref_layout(self, name, t):
         """reference-layout tensor (HWIO conv / [out,in] Linear / [in,out] Dense) -> the flat arena layout of variable `name`"""
@@ -362,9 +410,10 @@ class Engine:
             self._prep_table = torch.from_numpy(raw).to(self.device)
             self._prep_n, self._prep_tiles = n, begin
         if hasattr(self.lib, "detrb_prep_weights_multi"):
-            ops.prep_weights_multi(self._prep_table, self._prep_n, self._prep_tiles)
+            ops.prep_weights_multi(self._prep_table, self._prep_n, self._prep_tiles, wsplit=self.wplane)
             self.launches += 1
         else:
+            assert not self.paired
             for s in self.slots.values():
                 ops.prep_weight(s.master, s.fold, s.N, s.taps, s.Cin, s.Wf, s.K, s.Wd, s.ldd)
                 self.launches += 1
@@ -381,9 +430,13 @@ class Engine:
         def o(n, k, s, p):
             return (n + 2 * p - k) // s + 1
         a = {}
+        pending = []                                # parity precision: bf16 buffers are carved from one arena of pairs afterwards
 
-        def buf(name, *shape, dtype=BF16):
-            a[name] = torch.empty(*shape, dtype=dtype, device=dev)
+        def buf(name, *shape, dtype=BF16, zero=False):
+            if self.paired and dtype == BF16:
+                pending.append((name, shape))
+                return None
+            a[name] = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=dev)
             return a[name]
         self.a = a
         self.H0, self.W0 = H, W
@@ -399,7 +452,7 @@ class Engine:
         HP, WP = self.hw_pad
         self.M_stem = B * HP * WP
         # + the reach of the last window (3 rows + 4 pixels): zero, never written
-        a["s2d"] = torch.zeros(self.M_stem + 3 * WP + 8, 16, dtype=BF16, device=dev)
+        buf("s2d", self.M_stem + 3 * WP + 8, 16, zero=True)
         buf("stem", B, HP, WP, 64)
         buf("pool", B, h2, w2, 64)
         buf("pool_arg", B, h2, w2, 64, dtype=torch.uint8)
@@ -422,7 +475,9 @@ class Engine:
         M, Mq, d, dff, Q = B * S, B * self.Q, self.d, self.dff, self.Q
         self.M, self.Mq = M, Mq
         # position embedding: input independent (all-False mask, detr.py:172) -> computed once, fp32 then bf16
-        self.pos = self._pos_embedding(hh, ww).to(dev).to(BF16).contiguous()
+        buf("pos", S, d)
+        if self.paired:
+            buf("query_pos", self.Q, d)
         buf("src", M, d)
         buf("srcp", M, d)
         for l in range(self.nenc):
@@ -432,7 +487,7 @@ class Engine:
             buf(f"e{l}_lse", B * self.H * S, dtype=F32)
             for nm in ("mean1", "rstd1", "mean2", "rstd2"):
                 buf(f"e{l}_{nm}", M, dtype=F32)
-        buf("tgt0", Mq, d).zero_()
+        buf("tgt0", Mq, d, zero=True)
         for l in range(self.ndec):
             for nm, shp in (("tq", (Mq, d)), ("qk", (Mq, 2 * d)), ("v", (Mq, d)), ("o", (Mq, d)), ("pre1", (Mq, d)),
                             ("t1", (Mq, d)), ("t1q", (Mq, d)), ("q2", (Mq, d)), ("k2", (M, d)), ("v2", (M, d)),
@@ -481,6 +536,22 @@ class Engine:
         buf("g_y", max_elems)
         buf("g_1", max_elems)
         buf("g_2", max_elems)
+        if self.paired:
+            def numel(shape):
+                n = 1
+                for v in shape:
+                    n *= int(v)
+                return n
+            self.plane = _round_up(sum(_round_up(numel(sh), 128) for _, sh in pending), 128)
+            self._arena = torch.zeros(2 * self.plane, dtype=BF16, device=dev)         # zero: s2d padding, tgt0, both planes
+            off = 0
+            for name, sh in pending:
+                a[name] = self._arena[off:off + numel(sh)].view(*[int(v) for v in sh])
+                off += _round_up(numel(sh), 128)
+            self.query_pos = a["query_pos"]
+            self._store(self.query_pos, self.query_embed)
+        self.pos = a["pos"]
+        self._store(self.pos, self._pos_embedding(hh, ww))
         self.normalisers = None
 
     def _pos_embedding(self, h, w):
@@ -595,7 +666,8 @@ class Engine:
         """plain GEMM  out[M,N] = A[M,K] . W[N,K]^T (+epilogue)"""
         self.launches += 1
         self._before_write(out, kw.get("Cf"))
-        ops.igemm(A, W, M, N, K, lda or K, ldw, ops.plain_geom(M, K), C=out, ldc=(ldc if ldc is not None else N), **kw)
+        ops.igemm(A, W, M, N, K, lda or K, ldw, ops.plain_geom(M, K), C=out, ldc=(ldc if ldc is not None else N),
+                  split=self.plane, wsplit=self.wplane, **kw)
 
     def _conv_geom(self, s, B, ih, iw, oh, ow, mode=0):
         kh, kw, kwp, stride, pad = s.geom
@@ -610,7 +682,7 @@ class Engine:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual, ldr=s.N,
-                  relu=relu, C=out, ldc=s.N)
+                  relu=relu, C=out, ldc=s.N, split=self.plane, wsplit=self.wplane)
         if probe:
             e1.record()
             self.probe_events.setdefault(s.name, []).append((e0, e1))
@@ -624,32 +696,32 @@ class Engine:
         self.launches += 1
         self._before_write(out)
         ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin, mask_scale=1.0,
-                  residual=residual, ldr=s.Cin, C=out, ldc=s.Cin)
+                  residual=residual, ldr=s.Cin, C=out, ldc=s.Cin, split=self.plane, wsplit=self.wplane)
 
     def _conv_wgrad(self, s, x, dy, ihw, ohw):
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
         self._on_wstream(lambda: ops.wgrad(x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold,
-                                           dbias=s.bias_grad), (x, dy))
+                                           dbias=s.bias_grad, split=self.plane), (x, dy))
 
     def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
         """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
         n_rows = n_rows or s.N
         self.launches += 1
         self._on_wstream(lambda: ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
-                                           s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:]), (x, dy))
+                                           s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:], split=self.plane), (x, dy))
 
     def _ln_fwd(self, x, n, y, mean, rstd, M, y2=None, pos=None, S=1):
         self.launches += 1
-        ops.layernorm_fwd(x, n["g"], n["b"], y, y2, pos, S, mean, rstd, M)
+        ops.layernorm_fwd(x, n["g"], n["b"], y, y2, pos, S, mean, rstd, M, split=self.plane)
 
     def _ln_bwd(self, dy, dy2, x, n, mean, rstd, dx, dx_drop, M, drop_name=None):
         self.launches += 1
         self._before_write(dx, dx_drop)
         d = self._drop(drop_name) if drop_name else {}
         ops.layernorm_bwd(dy, dy2, x, n["g"], mean, rstd, dx, dx_drop, d.get("drop_p", 0.0), d.get("seed", 0),
-                          d.get("site", 0), d.get("seed_ptr"), n["dg"], n["db"], M)
+                          d.get("site", 0), d.get("seed_ptr"), n["dg"], n["db"], M, split=self.plane)
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, images, training=False):
@@ -699,17 +771,18 @@ class Engine:
         # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels = a sliding-window GEMM
         HP, WP = self.hw_pad
         if self.u8_input:                     # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
-            ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP)
+            ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP,
+                                  split=self.plane)
         else:
-            ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP)
+            ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP, split=self.plane)
         self.launches += 1
         stem = self.slots["backbone/conv1"]
         # one plain GEMM [B*HP*WP, 256] x [64, 256]^T whose A rows are overlapping 128-byte windows of the padded image
         self.launches += 1
         ops.igemm(a["s2d"], stem.Wf, self.M_stem, stem.N, stem.K, 16, stem.K, ops.plain_geom(self.M_stem, stem.K),
-                  bias=stem.epi_bias, relu=True, C=a["stem"], ldc=stem.N, a_kb_rows=WP)
+                  bias=stem.epi_bias, relu=True, C=a["stem"], ldc=stem.N, a_kb_rows=WP, split=self.plane, wsplit=self.wplane)
         ops.maxpool_fwd(a["stem"], a["pool"], a["pool_arg"], B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
-                        XH=HP, XW=WP)
+                        XH=HP, XW=WP, split=self.plane)
         self.launches += 1
         x = a["pool"]
         for i, blk in enumerate(self.blocks):
@@ -730,7 +803,7 @@ class Engine:
         # ---------------- input_proj (detr.py:44,175) + pos add
         ip = self.slots["input_proj"]
         self._lin(x, ip.Wf, M, d, ip.K, ip.K, out=a["src"], bias=ip.bias)
-        ops.add_rowbcast(a["src"], self.pos, a["srcp"], M, S, d)
+        ops.add_rowbcast(a["src"], self.pos, a["srcp"], M, S, d, split=self.plane)
         self.launches += 1
         # ---------------- encoder (transformer.py:157-179)
         xin, xinp = a["src"], a["srcp"]
@@ -769,7 +842,7 @@ class Engine:
         for l, D in enumerate(self.dec):
             t = lambda n: a[f"d{l}_{n}"]
             W = D["sa"]["inp"]
-            ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d)
+            ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d, split=self.plane)
             self.launches += 1
             self._lin(t("tq"), W.Wf, Mq, 2 * d, d, d, out=t("qk"), bias=W.bias)
             self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:])
@@ -804,7 +877,7 @@ class Engine:
         self._mark("fwd_decoder_heads")
 
     def _attn_drop(self, name):
-        return self._drop(name)
+        return dict(self._drop(name), split=self.plane)
 
     # ------------------------------------------------------------------------------------------ loss
     def match(self, want_cost=False):
@@ -830,7 +903,8 @@ class Engine:
         self.launches += 2
         ops.set_loss(a["logits"], self.C, a["boxes"], a["t_bbox"], a["t_class"], a["match"], L, B, Q, self.C,
                      background_class, self.normalisers, loss_scale, a["loss_sums"], a["losses"], a["total"],
-                     a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32)
+                     a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32,
+                     status=a["status"], split=self.plane)
         self._mark("matcher_loss")
 
     def loss_dict(self, snapshot=False):
@@ -1012,7 +1086,7 @@ class Engine:
                 self.launches += 1
                 self._before_write(g_in)
                 ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask=xmask, ldm=cd.Cin, mask_scale=1.0,
-                          C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True)
+                          C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True, split=self.plane, wsplit=self.wplane)
             g_out, g_in = g_in, g_out
             if blk["prefix"] == "backbone/layer3/0":
                 reached(1)
@@ -1021,13 +1095,13 @@ class Engine:
         self._before_write(g_in)
         HP, WP = self.hw_pad
         ops.maxpool_bwd(g_out, a["pool_arg"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
-                        XH=HP, XW=WP)
+                        XH=HP, XW=WP, split=self.plane)
         stem = self.slots["backbone/conv1"]
         self.launches += 1
         x, Ms = a["s2d"], self.M_stem
         before_stem = self._w_last if self._w_last is not None else True
         self._on_wstream(lambda: ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
-                                           rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True), (x, g_in))
+                                           rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True, split=self.plane), (x, g_in))
         self._in_backward = False
         if defer_tail and boundary is None and self._w_last is not None and hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
             self._tail = before_stem                               # joined by optimizer_step()
@@ -1054,10 +1128,10 @@ class Engine:
         gi = GROUPS.index(name)
         if getattr(self, "_en_one", None) is None:
             self._en_one = [torch.zeros(8, dtype=torch.uint8).index_fill_(0, torch.tensor([i]), 1).to(self.device) for i in range(len(GROUPS))]
-        self.group_enabled.copy_(self._en_one[gi])              # device-to-device, asynchronous
         lo, hi = self.group_chunks[name]
         self.launches += 3
-        self._adam(grads_arena, clipnorm, lo=lo, hi=hi)
+        # its own one-hot flag vector: self.group_enabled (read at replay time by the captured whole-step graph) stays untouched
+        self._adam(grads_arena, clipnorm, lo=lo, hi=hi, enabled=self._en_one[gi])
         self._weights_dirty = True
 
     def _ensure_weights(self):
@@ -1065,16 +1139,17 @@ class Engine:
             self._weights_dirty = False
             self.refresh_weights()
 
-    def _adam(self, grads_arena, clipnorm, lo=0, hi=None, prologue=True):
+    def _adam(self, grads_arena, clipnorm, lo=0, hi=None, prologue=True, enabled=None):
         """Adam + per-variable clipnorm over chunks [lo, hi) of the chunk table (whole variables); prologue: first call of the step"""
+        enabled = self.group_enabled if enabled is None else enabled
         if hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
             hi = self.nchunks if hi is None else hi
             ops.adam_clipnorm_chunked(self.params, grads_arena, self.adam_m, self.adam_v, self.chunks, hi - lo, self.lr_group,
-                                      self.lrs, self.group_enabled, self.T, clipnorm, self.steps, self.norms, first_chunk=lo,
+                                      self.lrs, enabled, self.T, clipnorm, self.steps, self.norms, first_chunk=lo,
                                       prologue=prologue)
         else:                                                    # table variant: every variable, the group flags select
             ops.adam_clipnorm(self.params, grads_arena, self.adam_m, self.adam_v, self.table, self.lr_group, self.lrs,
-                              self.group_enabled, self.T, self.total, clipnorm, self.steps, self.norms)
+                              enabled, self.T, self.total, clipnorm, self.steps, self.norms)
 
     def allreduce_grads(self):
         """data parallel: ONE sum all-reduce over the flat gradient arena (NCCL over NVLink); no-op on one rank."""

@@ -18,7 +18,8 @@ def _dev(x, dtype, device):
 def get_losses(m_outputs, t_bbox, t_class, config):
     """m_outputs: {'pred_logits': [B,Q,C], 'pred_boxes': [B,Q,4], 'aux': [...]}; t_bbox [B,100,4], t_class [B,100,1]
     (wire format data/processing.py:35-55).  Returns (total_loss, losses) with the reference's 36 keys; every value is a
-    0-dim device tensor (no host sync)."""
+    0-dim device tensor (no host sync).  A cost matrix with NaN / -inf entries -- the reference raises through scipy,
+    hungarian_matching.py:29 -- makes every returned value NaN (checked on device, visible at the caller's read-back)."""
     layers = list(m_outputs.get("aux", [])) + [m_outputs]
     device = layers[0]["pred_logits"].device if isinstance(layers[0]["pred_logits"], torch.Tensor) else torch.device("cuda")
     logits = torch.stack([_dev(l["pred_logits"], torch.float32, device) for l in layers])      # [L,B,Q,C]
@@ -37,7 +38,7 @@ def get_losses(m_outputs, t_bbox, t_class, config):
     losses = torch.empty(L, 6, dtype=torch.float32, device=device)
     total = torch.empty(1, dtype=torch.float32, device=device)
     ops.set_loss(logits, C, boxes, tb, tc, match, L, B, Q, C, int(config.background_class), None, 1.0, sums, losses,
-                 total, None, 0, None, 0)
+                 total, None, 0, None, 0, status=status)
     out = OrderedDict()
     for l in [L - 1] + list(range(L - 1)):
         suf = "" if l == L - 1 else f"_{l}"

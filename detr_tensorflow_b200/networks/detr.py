@@ -49,17 +49,20 @@ class DetrModel:
 
 
 def get_detr_model(config, include_top=False, nb_class=None, weights=None, tf_backbone=False, num_decoder_layers=6,
-                   num_encoder_layers=6, backbone="resnet50", device="cuda", seed=0, params=None, dropout=0.1):
+                   num_encoder_layers=6, backbone="resnet50", device="cuda", seed=0, params=None, dropout=0.1, precision="bf16"):
     """detr.py:116-204.  Extensions: `backbone` ("resnet50" | "resnet101": the reference ignores its own backbone
     argument, detr.py:21,31), `device`, `seed`/`params` (synthetic or caller-provided weights in reference layouts),
-    `dropout` (transformer.py:9 default 0.1; 0 makes training-mode steps deterministic for tests)."""
+    `dropout` (transformer.py:9 default 0.1; 0 makes training-mode steps deterministic for tests), `precision`: "bf16"
+    (throughput: bf16 activations, one tensor-core pass) or "parity" (activations and weight copies as bf16 PAIRS = 16
+    significant bits, three tensor-core passes per product, fp32 attention: the reference's fp32 arithmetic to ~1e-4)."""
     if tf_backbone:
         raise NotImplementedError("tf_backbone=True (keras.applications ResNet50, detr.py:146-148) is out of scope")
     # detr.py:178-181: nb_class only matters when include_top is False -> add_heads_nlayers (detr.py:94-114): new Keras
     # Dense heads `cls_layer` (nb_class logits) and `pos_layer` (256-256-4 MLP), registered as config.nlayers (detr.py:103)
     finetune = (include_top is False) and (nb_class is not None)
     eng = Engine(device=device, backbone=backbone, num_classes=92, num_encoder_layers=num_encoder_layers,
-                 num_decoder_layers=num_decoder_layers, seed=seed, dropout=dropout, nb_class=nb_class if finetune else None)
+                 num_decoder_layers=num_decoder_layers, seed=seed, dropout=dropout, nb_class=nb_class if finetune else None,
+                 precision=precision)
     if finetune:
         config.add_nlayers(["cls_layer", "pos_layer"])
     if params is None:

@@ -30,7 +30,7 @@ def plain_geom(M, K):
 
 def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mask=None, ldm=0, mask_scale=1.0,
           relu=False, sigmoid=False, drop_p=0.0, seed=0, site=0, seed_ptr=None, C=None, ldc=0, Cf=None, ldcf=0,
-          out_stride=1, SH=0, SW=0, accumulate=False, a_kb_rows=0, force_tc=None):
+          out_stride=1, SH=0, SW=0, accumulate=False, a_kb_rows=0, force_tc=None, split=0, wsplit=0):
     p = IgemmParams()
     p.A, p.W = ptr(A), ptr(W)
     p.M, p.N, p.K, p.lda, p.ldw = M, N, K, lda, ldw
@@ -40,6 +40,7 @@ def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mas
     p.relu, p.sigmoid, p.drop_p, p.seed, p.site, p.seed_ptr = int(relu), int(sigmoid), drop_p, seed, site, ptr(seed_ptr)
     p.C, p.ldc, p.Cf, p.ldcf = ptr(C), ldc, ptr(Cf), ldcf
     p.out_stride, p.SH, p.SW, p.accumulate, p.a_kb_rows = out_stride, SH, SW, int(accumulate), a_kb_rows
+    p.split, p.wsplit = split, wsplit
     if force_tc is not None:
         check(_lib.lib().detrb_gemm_tc_force(byref(p), c_int(force_tc), _stream()))
     else:
@@ -67,52 +68,52 @@ def set_tc_conv(enable):
     return _lib.lib().detrb_set_tc_conv(c_int(int(enable)))
 
 
-def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None, a_kb_rows=0, k_mask=False, force_tc=False):
+def wgrad(A, lda, dY, ldy, M, N, K, geom, dW, ldw, *, rowscale=None, dbias=None, a_kb_rows=0, k_mask=False, force_tc=False, split=0):
     p = WgradParams()
     p.A, p.lda, p.dY, p.ldy, p.M, p.N, p.K = ptr(A), lda, ptr(dY), ldy, M, N, K
     for k, v in geom.items():
         if k != "mode":
             setattr(p, k, v)
     p.rowscale, p.dW, p.ldw, p.dbias = ptr(rowscale), ptr(dW), ldw, ptr(dbias)
-    p.a_kb_rows, p.k_mask = a_kb_rows, int(k_mask)
+    p.a_kb_rows, p.k_mask, p.split = a_kb_rows, int(k_mask), split
     if force_tc:
         check(_lib.lib().detrb_wgrad_tc_force(byref(p), _stream()))
     else:
         check(_lib.lib().detrb_wgrad(byref(p), _stream()))
 
 
-def attn_fwd(Q, K, V, ldq, ldk, ldv, O, ldo, lse, B, H, Lq, Lk, scale, drop_p=0.0, seed=0, site=0, seed_ptr=None):
+def attn_fwd(Q, K, V, ldq, ldk, ldv, O, ldo, lse, B, H, Lq, Lk, scale, drop_p=0.0, seed=0, site=0, seed_ptr=None, split=0):
     p = AttnFwdParams()
     p.Q, p.K, p.V, p.ldq, p.ldk, p.ldv = ptr(Q), ptr(K), ptr(V), ldq, ldk, ldv
     p.O, p.ldo, p.lse, p.B, p.H, p.Lq, p.Lk = ptr(O), ldo, ptr(lse), B, H, Lq, Lk
-    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr = scale, drop_p, seed, site, ptr(seed_ptr)
+    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr, p.split = scale, drop_p, seed, site, ptr(seed_ptr), split
     check(_lib.lib().detrb_attn_fwd(byref(p), _stream()))
 
 
 def attn_bwd(Q, K, V, O, dO, ldq, ldk, ldv, ldo, lddo, lse, delta, dQ, dK, dV, lddq, lddk, lddv, B, H, Lq, Lk,
-             scale, drop_p=0.0, seed=0, site=0, seed_ptr=None):
+             scale, drop_p=0.0, seed=0, site=0, seed_ptr=None, split=0):
     p = AttnBwdParams()
     p.Q, p.K, p.V, p.O, p.dO = ptr(Q), ptr(K), ptr(V), ptr(O), ptr(dO)
     p.ldq, p.ldk, p.ldv, p.ldo, p.lddo = ldq, ldk, ldv, ldo, lddo
     p.lse, p.delta, p.dQ, p.dK, p.dV = ptr(lse), ptr(delta), ptr(dQ), ptr(dK), ptr(dV)
     p.lddq, p.lddk, p.lddv, p.B, p.H, p.Lq, p.Lk = lddq, lddk, lddv, B, H, Lq, Lk
-    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr = scale, drop_p, seed, site, ptr(seed_ptr)
+    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr, p.split = scale, drop_p, seed, site, ptr(seed_ptr), split
     check(_lib.lib().detrb_attn_bwd(byref(p), _stream()))
 
 
-def layernorm_fwd(x, gamma, beta, y, y2, pos, S, mean, rstd, M):
+def layernorm_fwd(x, gamma, beta, y, y2, pos, S, mean, rstd, M, split=0):
     check(_lib.lib().detrb_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(y2), ptr(pos), c_int(S),
-                                         ptr(mean), ptr(rstd), c_int(M), _stream()))
+                                         ptr(mean), ptr(rstd), c_int(M), c_int64(split), _stream()))
 
 
-def layernorm_bwd(dy, dy2, x, gamma, mean, rstd, dx, dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M):
+def layernorm_bwd(dy, dy2, x, gamma, mean, rstd, dx, dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta, M, split=0):
     check(_lib.lib().detrb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx),
                                          ptr(dx_drop), c_float(drop_p), c_uint64(seed), c_uint32(site), ptr(seed_ptr),
-                                         ptr(dgamma), ptr(dbeta), c_int(M), _stream()))
+                                         ptr(dgamma), ptr(dbeta), c_int(M), c_int64(split), _stream()))
 
 
-def add_rowbcast(x, pos, out, M, S, d):
-    check(_lib.lib().detrb_add_rowbcast(ptr(x), ptr(pos), ptr(out), c_int(M), c_int(S), c_int(d), _stream()))
+def add_rowbcast(x, pos, out, M, S, d, split=0):
+    check(_lib.lib().detrb_add_rowbcast(ptr(x), ptr(pos), ptr(out), c_int(M), c_int(S), c_int(d), c_int64(split), _stream()))
 
 
 def add(a, b, out, n):
@@ -123,10 +124,10 @@ def image_to_nhwc4(img, out, npix):
     check(_lib.lib().detrb_image_to_nhwc4(ptr(img), ptr(out), c_int64(npix), _stream()))
 
 
-def image_to_s2d16(img, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None):
+def image_to_s2d16(img, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None, split=0):
     HP, WP = HP or (H + 1) // 2, WP or (W + 1) // 2
     check(_lib.lib().detrb_image_to_s2d16(ptr(img), ptr(out), c_int(B), c_int(H), c_int(W), c_int(pad_top), c_int(pad_left),
-                                          c_int(HP), c_int(WP), _stream()))
+                                          c_int(HP), c_int(WP), c_int64(split), _stream()))
 
 
 def f32_to_bf16(x, y, n):
@@ -137,14 +138,14 @@ def colsum(x, ldx, M, N, scale, out):
     check(_lib.lib().detrb_colsum(ptr(x), c_int(ldx), c_int(M), c_int(N), ptr(scale), ptr(out), _stream()))
 
 
-def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW, XH=None, XW=None):
+def maxpool_fwd(x, y, argmax, B, IH, IW, C, OH, OW, XH=None, XW=None, split=0):
     check(_lib.lib().detrb_maxpool_fwd(ptr(x), ptr(y), ptr(argmax), c_int(B), c_int(IH), c_int(IW), c_int(C),
-                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
+                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), c_int64(split), _stream()))
 
 
-def maxpool_bwd(dy, argmax, dx, B, IH, IW, C, OH, OW, XH=None, XW=None):
+def maxpool_bwd(dy, argmax, dx, B, IH, IW, C, OH, OW, XH=None, XW=None, split=0):
     check(_lib.lib().detrb_maxpool_bwd(ptr(dy), ptr(argmax), ptr(dx), c_int(B), c_int(IH), c_int(IW), c_int(C),
-                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), _stream()))
+                                       c_int(OH), c_int(OW), c_int(XH or IH), c_int(XW or IW), c_int64(split), _stream()))
 
 
 def matcher(logits, ldl, boxes, t_bbox, t_class, P, B, Q, C, p_indices, t_indices, p_selector, match, cost, status,
@@ -156,11 +157,11 @@ def matcher(logits, ldl, boxes, t_bbox, t_class, P, B, Q, C, p_indices, t_indice
 
 
 def set_loss(logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class, normalisers, loss_scale,
-             sums, losses, total, d_logits, ld_dl, d_boxpre, ld_db):
+             sums, losses, total, d_logits, ld_dl, d_boxpre, ld_db, status=None, split=0):
     check(_lib.lib().detrb_set_loss(ptr(logits), c_int(ldl), ptr(boxes), ptr(t_bbox), ptr(t_class), ptr(match),
                                     c_int(L), c_int(B), c_int(Q), c_int(C), c_int(background_class), ptr(normalisers),
                                     c_float(loss_scale), ptr(sums), ptr(losses), ptr(total), ptr(d_logits), c_int(ld_dl),
-                                    ptr(d_boxpre), c_int(ld_db), _stream()))
+                                    ptr(d_boxpre), c_int(ld_db), ptr(status), c_int64(split), _stream()))
 
 
 def adam_clipnorm(params, grads, m, v, table, lr_group, lrs, group_enabled, T, total, clipnorm, steps, norms,
@@ -185,8 +186,13 @@ def attn_dropout_mask(out, M, N, drop_p, seed, site, seed_ptr=None):
                                              ptr(seed_ptr), _stream()))
 
 
-def prep_weights_multi(descs_dev, nslots, total_tiles):
-    check(_lib.lib().detrb_prep_weights_multi(ptr(descs_dev), c_int(nslots), c_int(total_tiles), _stream()))
+def prep_weights_multi(descs_dev, nslots, total_tiles, wsplit=0):
+    check(_lib.lib().detrb_prep_weights_multi(ptr(descs_dev), c_int(nslots), c_int(total_tiles), c_int64(wsplit), _stream()))
+
+
+def accumulate(acc, g, n, zero_first):
+    """acc[:n] = (0 if zero_first else acc[:n]) + g[:n]  (fp32; optimizers.py:150-157)"""
+    check(_lib.lib().detrb_accumulate(ptr(acc), ptr(g), c_int64(n), c_int(int(zero_first)), _stream()))
 
 
 def adam_clipnorm_chunked(params, grads, m, v, chunks, nchunks, lr_group, lrs, group_enabled, T, clipnorm, steps, norms,
@@ -201,10 +207,10 @@ def normalize_u8(img_u8, lut, swap_rb, out_f32, npix):
     check(_lib.lib().detrb_normalize_u8(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out_f32), c_int64(npix), _stream()))
 
 
-def image_u8_to_s2d16(img_u8, lut, swap_rb, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None):
+def image_u8_to_s2d16(img_u8, lut, swap_rb, out, B, H, W, pad_top=0, pad_left=0, HP=None, WP=None, split=0):
     HP, WP = HP or (H + 1) // 2, WP or (W + 1) // 2
     check(_lib.lib().detrb_image_u8_to_s2d16(ptr(img_u8), ptr(lut), c_int(int(swap_rb)), ptr(out), c_int(B), c_int(H), c_int(W),
-                                             c_int(pad_top), c_int(pad_left), c_int(HP), c_int(WP), _stream()))
+                                             c_int(pad_top), c_int(pad_left), c_int(HP), c_int(WP), c_int64(split), _stream()))
 
 
 def postprocess(logits, ldl, boxes, B, Q, C, background_class, bbox_format, out_boxes, out_labels, out_scores, out_query,

@@ -17,6 +17,15 @@
  *   - activations are NHWC / row-major bf16; accumulators, losses, gradients of parameters
  *     and optimizer state are fp32; matcher indices are int64 like the reference's.
  *   - there is no CPU fallback: detrb_check_device() fails unless the device is CC 10.x.
+ *
+ * Parity precision ("split" storage).  The reference computes in fp32 (custom_layers.py:49-50, transformer.py:317,340).
+ * Every entry point that reads or writes bf16 ACTIVATIONS takes a plane stride `split` (in elements; 0 = plain bf16, the
+ * throughput mode).  With split != 0 a tensor element x lives as a PAIR of bf16 values, hi = bf16(x) at the given pointer and
+ * lo = bf16(x - hi) `split` elements further (same shape and strides): 16 significant bits, the same bytes per element as fp32.
+ * The GEMM / convolution / weight-gradient kernels then issue three tensor-core passes per product (hi*hi + lo*hi + hi*lo,
+ * fp32 accumulation in tensor memory) over the same TMA / tcgen05 pipeline; weights are paired the same way (`wsplit`), the
+ * attention core runs in fp32 arithmetic, all other kernels read hi + lo and write the rounded pair.  This is what the
+ * fp32-tolerance parity tests run; it is selected per call, not per process.
  */
 #ifndef DETRB_H
 #define DETRB_H
@@ -92,6 +101,9 @@ typedef struct {
      * space-to-depth stem: a_kb_rows = padded width).  The caller guarantees (M + (K/64-1)*a_kb_rows)*lda + 64 readable elements.
      * Plain geometry only; tcgen05 path only (DETRB_E_SHAPE otherwise). */
     int a_kb_rows;
+    /* parity precision (see the header comment): plane stride of the bf16 pairs of A / residual / mask / C (0 = plain bf16) and
+     * of W.  Both zero or both non-zero. */
+    int64_t split, wsplit;
 } detrb_igemm_t;
 
 int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
@@ -121,6 +133,7 @@ typedef struct {
     int a_kb_rows;               /* sliding-window A operand as in detrb_igemm_t: plain geometry, tcgen05 kernel only */
     int k_mask;                  /* 1: A is the space-to-depth stem operand -- columns of dW that do not exist in the 7x7x3 kernel
                                   * (resnet_backbone.py:11) receive no gradient */
+    int64_t split;               /* parity precision: plane stride of the bf16 pairs of A and dY (0 = plain bf16) */
 } detrb_wgrad_t;
 
 int detrb_wgrad(const detrb_wgrad_t *p, detrb_stream_t stream);
@@ -142,6 +155,7 @@ typedef struct {
     int B, H, Lq, Lk;
     float scale;                 /* scores = scale * Q K^T  (head_dim^-0.5, transformer.py:307) */
     float drop_p; uint64_t seed; uint32_t site; const uint64_t *seed_ptr;
+    int64_t split;               /* parity precision: plane stride of the bf16 pairs of Q / K / V / O; fp32 arithmetic (0 = plain bf16) */
 } detrb_attn_fwd_t;
 int detrb_attn_fwd(const detrb_attn_fwd_t *p, detrb_stream_t stream);
 
@@ -153,6 +167,7 @@ typedef struct {
     int B, H, Lq, Lk;
     float scale;
     float drop_p; uint64_t seed; uint32_t site; const uint64_t *seed_ptr;
+    int64_t split;               /* parity precision: plane stride of the bf16 pairs of every bf16 operand (0 = plain bf16) */
 } detrb_attn_bwd_t;
 int detrb_attn_bwd(const detrb_attn_bwd_t *p, detrb_stream_t stream);
 
@@ -165,16 +180,16 @@ int detrb_attn_bwd(const detrb_attn_bwd_t *p, detrb_stream_t stream);
  * ------------------------------------------------------------------------------------------ */
 int detrb_layernorm_fwd(const detrb_bf16 *x, const float *gamma, const float *beta,
                         detrb_bf16 *y, detrb_bf16 *y2, const detrb_bf16 *pos, int S,
-                        float *mean, float *rstd, int M, detrb_stream_t stream);
+                        float *mean, float *rstd, int M, int64_t split, detrb_stream_t stream);
 int detrb_layernorm_bwd(const detrb_bf16 *dy, const detrb_bf16 *dy2, const detrb_bf16 *x,
                         const float *gamma, const float *mean, const float *rstd,
                         detrb_bf16 *dx, detrb_bf16 *dx_drop, float drop_p, uint64_t seed, uint32_t site,
-                        const uint64_t *seed_ptr, float *dgamma, float *dbeta, int M, detrb_stream_t stream);
+                        const uint64_t *seed_ptr, float *dgamma, float *dbeta, int M, int64_t split, detrb_stream_t stream);
 
 /* elementwise helpers (bf16, n multiple of 8) */
 /* out[r, :] = x[r, :] + pos[r % S, :]          (transformer.py:161: source + pos_encoding) */
 int detrb_add_rowbcast(const detrb_bf16 *x, const detrb_bf16 *pos, detrb_bf16 *out,
-                       int M, int S, int d, detrb_stream_t stream);
+                       int M, int S, int d, int64_t split, detrb_stream_t stream);
 /* out = a + b (b may be NULL -> copy) */
 int detrb_add(const detrb_bf16 *a, const detrb_bf16 *b, detrb_bf16 *out, int64_t n, detrb_stream_t stream);
 /* fp32 NHWC3 image -> bf16 NHWC4 (4th channel 0): the layout the stem kernel gathers from */
@@ -185,7 +200,7 @@ int detrb_image_to_nhwc4(const float *img, detrb_bf16 *out, int64_t npix, detrb_
  * pad 2/2 and HP = ceil(H/2)+3, WP = ceil(W/2)+3 the stem's zero padding is explicit and the convolution is a sliding-window
  * GEMM over the flat tensor (detrb_igemm_t.a_kb_rows = WP).  pad 0/0, HP = ceil(H/2), WP = ceil(W/2): the dense tensor. */
 int detrb_image_to_s2d16(const float *img, detrb_bf16 *out, int B, int H, int W, int pad_top, int pad_left, int HP, int WP,
-                         detrb_stream_t stream);
+                         int64_t split, detrb_stream_t stream);
 /* fp32 -> bf16 */
 int detrb_f32_to_bf16(const float *x, detrb_bf16 *y, int64_t n, detrb_stream_t stream);
 /* column sums: out[n] += scale[n]* sum_m x[m,n]  (bias gradients) */
@@ -199,9 +214,9 @@ int detrb_colsum(const detrb_bf16 *x, int ldx, int M, int N, const float *scale,
  * fwd ignores the positions outside IH x IW, bwd writes them as zeros (they are the wrapped-window rows of the sliding-window
  * stem GEMM, whose weight gradient must not see them). */
 int detrb_maxpool_fwd(const detrb_bf16 *x, detrb_bf16 *y, uint8_t *argmax,
-                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
+                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, int64_t split, detrb_stream_t stream);
 int detrb_maxpool_bwd(const detrb_bf16 *dy, const uint8_t *argmax, detrb_bf16 *dx,
-                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, detrb_stream_t stream);
+                      int B, int IH, int IW, int C, int OH, int OW, int XH, int XW, int64_t split, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hungarian matcher (loss/hungarian_matching.py:163-203 + :27-46 -> scipy LSAP) for P = L*B
@@ -228,14 +243,18 @@ int detrb_matcher(const float *logits, int ldl, const float *boxes,
  *   normalisers: device float[2] = {n_matched, sum_w}, the batch-level normalisers (loss.py:66-67, 82, 94);
  *   pass the GLOBAL values under data parallelism; NULL: computed from this batch's targets.
  *   d_logits bf16 [P*Q, ld_dl] (cols >= C zeroed), d_boxpre bf16 [P*Q, ld_db]: gradient wrt the
- *   pre-sigmoid box head output (boxes = sigmoid(pre), detr.py:188), cols >= 4 zeroed.  NULL -> fwd only. */
+ *   pre-sigmoid box head output (boxes = sigmoid(pre), detr.py:188), cols >= 4 zeroed.  NULL -> fwd only.
+ *   status: the matcher's per-problem status [L*B] i32 or NULL.  The reference raises through scipy ("matrix contains invalid
+ *   numeric entries") when a cost matrix holds NaN / -inf; a stream-ordered library cannot raise, so a non-zero status
+ *   poisons the result instead: total and all 6*L loss scalars become NaN (visible at the caller's next read-back).
+ *   split: plane stride of the bf16 pairs of d_logits / d_boxpre (parity precision; 0 = plain bf16). */
 int detrb_set_loss(const float *logits, int ldl, const float *boxes,
                    const float *t_bbox, const int64_t *t_class, const int32_t *match,
                    int L, int B, int Q, int C, int background_class,
                    const float *normalisers, float loss_scale,
                    float *sums, float *losses, float *total,
                    detrb_bf16 *d_logits, int ld_dl, detrb_bf16 *d_boxpre, int ld_db,
-                   detrb_stream_t stream);
+                   const int32_t *status, int64_t split, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer (optimizers.py:86-88,137-163): Keras Adam(beta1=.9, beta2=.999, eps=1e-7) with
@@ -274,7 +293,13 @@ typedef struct {
     detrb_bf16 *Wf; detrb_bf16 *Wd;
     int N, taps, Cin, ldf, ldd, tile_begin;
 } detrb_prep_desc_t;
-int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, detrb_stream_t stream);
+/* wsplit != 0 (parity precision): Wf / Wd are written as bf16 pairs, the lo plane wsplit elements after the hi plane. */
+int detrb_prep_weights_multi(const detrb_prep_desc_t *descs, int nslots, int total_tiles, int64_t wsplit, detrb_stream_t stream);
+
+/* Gradient accumulation over micro-batches (optimizers.py:137-163, aggregate_grad_and_apply): acc[i] = (zero_first ? 0 :
+ * acc[i]) + g[i] over n fp32 elements (n % 4 == 0, 16-byte aligned): the reference zeroes its accumulators at
+ * step % k == 0 (:150-153) and adds every micro-step's gradient (:155-157). */
+int detrb_accumulate(float *acc, const float *g, int64_t n, int zero_first, detrb_stream_t stream);
 
 /* debug/test helper: writes the dropout keep-mask (0/1 bytes) the kernels use for an [M,N] site */
 int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
@@ -301,7 +326,7 @@ int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float 
 /* The same normalisation fused into the stem's input layout: img [B,H,W,3] u8 -> bf16 space-to-depth(2) tensor
  * [B, HP, WP, 16] (padding arguments as in detrb_image_to_s2d16); the fp32 image never exists in HBM. */
 int detrb_image_u8_to_s2d16(const uint8_t *img, const float *lut, int swap_rb, detrb_bf16 *out, int B, int H, int W,
-                            int pad_top, int pad_left, int HP, int WP, detrb_stream_t stream);
+                            int pad_top, int pad_left, int HP, int WP, int64_t split, detrb_stream_t stream);
 /* Inference post-process (inference.py:68-95, get_model_inference) for B images in one launch:
  *   logits [B,Q,C] f32 (row stride ldl), boxes [B,Q,4] f32 cxcywh (16-byte aligned).
  *   Per query: softmax, score = max probability, label = argmax of the softmax (first index on ties); queries whose label

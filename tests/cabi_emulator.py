@@ -62,6 +62,45 @@ def _v(x):
     return x.value if hasattr(x, "value") else x
 
 
+# ---- parity precision (include/detrb.h): an activation element is a PAIR of storage values, hi at p and lo = x - hi at
+#      p + split elements; split == 0: plain storage
+def _lo(p, split):
+    return _addr(p) + int(_v(split)) * _ITEM[_Act.dtype]
+
+
+def RD(p, rows, cols, ld, split=0):
+    """fp32 [rows, cols] value of a (possibly paired) activation matrix"""
+    v = M2(p, _Act.dtype, rows, cols, ld).to(F32)
+    if _v(split):
+        v = v + M2(_lo(p, split), _Act.dtype, rows, cols, ld).to(F32)
+    return v
+
+
+def WR(p, rows, cols, ld, val, split=0, index=None):
+    """store fp32 val as the (pair of) storage values; index: row subset"""
+    hi = val.to(_Act.dtype)
+    dst = M2(p, _Act.dtype, rows, cols, ld)
+    if index is None:
+        dst[:] = hi
+    else:
+        dst[index] = hi
+    if _v(split):
+        lo = (val - hi.to(F32)).to(_Act.dtype)
+        dst = M2(_lo(p, split), _Act.dtype, rows, cols, ld)
+        if index is None:
+            dst[:] = lo
+        else:
+            dst[index] = lo
+
+
+def RND(val, split=0):
+    """the value a later RD of a WR(val) returns"""
+    hi = val.to(_Act.dtype).to(F32)
+    if _v(split):
+        return hi + (val - hi).to(_Act.dtype).to(F32)
+    return hi
+
+
 # ---------------------------------------------------------------- dropout hash (mirrors csrc/common.cuh)
 def _lowbias32(x):
     x = x.astype(np.uint64)
@@ -153,7 +192,7 @@ class FakeLib:
 
     # -- plumbing
     def detrb_version(self):
-        return 100
+        return _lib.ABI_VERSION
 
     def detrb_last_error(self):
         return self.err
@@ -175,12 +214,19 @@ class FakeLib:
     def detrb_igemm(self, pref, stream):
         p = pref._obj
         stem = p.Cin == 4
-        if p.a_kb_rows:
-            Ag = _sliding(p.A, p.lda, p.M, p.K, p.a_kb_rows)
-        else:
-            Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, p.mode)
+        def gathered(addr):
+            if p.a_kb_rows:
+                return _sliding(addr, p.lda, p.M, p.K, p.a_kb_rows)
+            return _gather(addr, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, p.mode)
+        Ag = gathered(p.A)
         W = M2(p.W, _Act.dtype, p.N, p.K, p.ldw).to(F32)
         v = Ag @ W.t()
+        sp = int(p.split)
+        if sp:                           # three products: hi*hi + lo*hi + hi*lo
+            assert p.wsplit
+            Al = gathered(_lo(p.A, sp))
+            Wl = M2(_lo(p.W, p.wsplit), _Act.dtype, p.N, p.K, p.ldw).to(F32)
+            v = v + Al @ W.t() + Ag @ Wl.t()
         out_stride = max(p.out_stride, 1)
         m = torch.arange(p.M)
         if out_stride > 1:
@@ -192,7 +238,7 @@ class FakeLib:
             orow, nrows = m, p.M
         if _addr(p.bias):
             v = v + T(p.bias, F32, p.N)
-        res = M2(p.residual, _Act.dtype, nrows, p.N, p.ldr)[orow].to(F32) if _addr(p.residual) else None
+        res = RD(p.residual, nrows, p.N, p.ldr, sp)[orow] if _addr(p.residual) else None
         if res is not None and not p.drop_p > 0:
             v = v + res
         if p.relu:
@@ -208,10 +254,9 @@ class FakeLib:
             if res is not None:
                 v = v + res
         if _addr(p.C):
-            C = M2(p.C, _Act.dtype, nrows, p.N, p.ldc)
             if p.accumulate:
-                v = v + C[orow].to(F32)
-            C[orow] = v.to(_Act.dtype)
+                v = v + RD(p.C, nrows, p.N, p.ldc, sp)[orow]
+            WR(p.C, nrows, p.N, p.ldc, v, sp, index=orow)
         if _addr(p.Cf):
             M2(p.Cf, F32, nrows, p.N, p.ldcf)[orow] = v
         return 0
@@ -219,13 +264,19 @@ class FakeLib:
     def detrb_wgrad(self, pref, stream):
         p = pref._obj
         stem = p.Cin == 4
-        if p.a_kb_rows:
-            Ag = _sliding(p.A, p.lda, p.M, p.K, p.a_kb_rows)
-        else:
-            Ag = _gather(p.A, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, 0,
-                         stem_real_kw=7 if stem else None)
+        def gathered(addr):
+            if p.a_kb_rows:
+                return _sliding(addr, p.lda, p.M, p.K, p.a_kb_rows)
+            return _gather(addr, p.lda, p.M, p.K, p.batch, p.IH, p.IW, p.Cin, p.OH, p.OW, p.KH, p.KW, p.stride, p.pad, 0,
+                           stem_real_kw=7 if stem else None)
+        Ag = gathered(p.A)
         dY = M2(p.dY, _Act.dtype, p.M, p.N, p.ldy).to(F32)
         g = dY.t() @ Ag
+        sp = int(p.split)
+        if sp:
+            dYl = M2(_lo(p.dY, sp), _Act.dtype, p.M, p.N, p.ldy).to(F32)
+            g = g + dYl.t() @ Ag + dY.t() @ gathered(_lo(p.A, sp))
+            dY = dY + dYl
         if p.k_mask or (p.Cin == 16 and p.KH == 4 and p.KW == 4 and p.pad == 2):
             # space-to-depth stem: columns of taps that do not exist in the 7x7x3 kernel get no gradient
             k = torch.arange(p.K)
@@ -255,17 +306,20 @@ class FakeLib:
         if p.drop_p > 0:
             keep = attn_keep_mask(range(B * H * Lq), range(Lk), p.drop_p, p.seed, p.site, p.seed_ptr).view(B, H, Lq, Lk)
             w = torch.where(keep, w / (1 - p.drop_p), torch.zeros_like(w))
-        o = (w.to(_Act.dtype).to(F32) @ v).transpose(1, 2).reshape(B, Lq, H * 32)
+        if not p.split:
+            w = w.to(_Act.dtype).to(F32)           # the tensor-core kernels feed bf16 probabilities to the P.V product
+        o = (w @ v).transpose(1, 2).reshape(B, Lq, H * 32)
         return o, lse
 
     def detrb_attn_fwd(self, pref, stream):
         p = pref._obj
         B, H, Lq, Lk = p.B, p.H, p.Lq, p.Lk
-        Q = M2(p.Q, _Act.dtype, B * Lq, H * 32, p.ldq).to(F32).view(B, Lq, -1)
-        K = M2(p.K, _Act.dtype, B * Lk, H * 32, p.ldk).to(F32).view(B, Lk, -1)
-        V = M2(p.V, _Act.dtype, B * Lk, H * 32, p.ldv).to(F32).view(B, Lk, -1)
+        sp = int(p.split)
+        Q = RD(p.Q, B * Lq, H * 32, p.ldq, sp).view(B, Lq, -1)
+        K = RD(p.K, B * Lk, H * 32, p.ldk, sp).view(B, Lk, -1)
+        V = RD(p.V, B * Lk, H * 32, p.ldv, sp).view(B, Lk, -1)
         o, lse = self._attn_core(Q, K, V, p, B, H, Lq, Lk)
-        M2(p.O, _Act.dtype, B * Lq, H * 32, p.ldo)[:] = o.reshape(B * Lq, -1).to(_Act.dtype)
+        WR(p.O, B * Lq, H * 32, p.ldo, o.reshape(B * Lq, -1), sp)
         if _addr(p.lse):
             T(p.lse, F32, B * H * Lq)[:] = lse.reshape(-1)
         return 0
@@ -273,29 +327,30 @@ class FakeLib:
     def detrb_attn_bwd(self, pref, stream):
         p = pref._obj
         B, H, Lq, Lk = p.B, p.H, p.Lq, p.Lk
-        Q = M2(p.Q, _Act.dtype, B * Lq, H * 32, p.ldq).to(F32).view(B, Lq, -1).clone().requires_grad_(True)
-        K = M2(p.K, _Act.dtype, B * Lk, H * 32, p.ldk).to(F32).view(B, Lk, -1).clone().requires_grad_(True)
-        V = M2(p.V, _Act.dtype, B * Lk, H * 32, p.ldv).to(F32).view(B, Lk, -1).clone().requires_grad_(True)
-        dO = M2(p.dO, _Act.dtype, B * Lq, H * 32, p.lddo).to(F32).view(B, Lq, -1)
+        sp = int(p.split)
+        Q = RD(p.Q, B * Lq, H * 32, p.ldq, sp).view(B, Lq, -1).clone().requires_grad_(True)
+        K = RD(p.K, B * Lk, H * 32, p.ldk, sp).view(B, Lk, -1).clone().requires_grad_(True)
+        V = RD(p.V, B * Lk, H * 32, p.ldv, sp).view(B, Lk, -1).clone().requires_grad_(True)
+        dO = RD(p.dO, B * Lq, H * 32, p.lddo, sp).view(B, Lq, -1)
         o, _ = self._attn_core(Q, K, V, p, B, H, Lq, Lk)
         gq, gk, gv = torch.autograd.grad(o, [Q, K, V], dO)
-        M2(p.dQ, _Act.dtype, B * Lq, H * 32, p.lddq)[:] = gq.reshape(B * Lq, -1).to(_Act.dtype)
-        M2(p.dK, _Act.dtype, B * Lk, H * 32, p.lddk)[:] = gk.reshape(B * Lk, -1).to(_Act.dtype)
-        M2(p.dV, _Act.dtype, B * Lk, H * 32, p.lddv)[:] = gv.reshape(B * Lk, -1).to(_Act.dtype)
+        WR(p.dQ, B * Lq, H * 32, p.lddq, gq.reshape(B * Lq, -1), sp)
+        WR(p.dK, B * Lk, H * 32, p.lddk, gk.reshape(B * Lk, -1), sp)
+        WR(p.dV, B * Lk, H * 32, p.lddv, gv.reshape(B * Lk, -1), sp)
         return 0
 
     # -- layer norm
-    def detrb_layernorm_fwd(self, x, gamma, beta, y, y2, pos, S, mean, rstd, M, stream):
-        S, M = _v(S), _v(M)
-        xv = M2(x, _Act.dtype, M, 256, 256).to(F32)
+    def detrb_layernorm_fwd(self, x, gamma, beta, y, y2, pos, S, mean, rstd, M, split, stream):
+        S, M, sp = _v(S), _v(M), _v(split)
+        xv = RD(x, M, 256, 256, sp)
         mu = xv.mean(-1, keepdim=True)
         var = ((xv - mu) ** 2).mean(-1, keepdim=True)
         rs = torch.rsqrt(var + 1e-5)
-        o = ((xv - mu) * rs * T(gamma, F32, 256) + T(beta, F32, 256)).to(_Act.dtype)
-        M2(y, _Act.dtype, M, 256, 256)[:] = o
+        o = (xv - mu) * rs * T(gamma, F32, 256) + T(beta, F32, 256)
+        WR(y, M, 256, 256, o, sp)
         if _addr(y2):
-            pv = M2(pos, _Act.dtype, S, 256, 256).to(F32)
-            M2(y2, _Act.dtype, M, 256, 256)[:] = (o.to(F32) + pv[torch.arange(M) % S]).to(_Act.dtype)
+            pv = RD(pos, S, 256, 256, sp)
+            WR(y2, M, 256, 256, RND(o, sp) + pv[torch.arange(M) % S], sp)
         if _addr(mean):
             T(mean, F32, M)[:] = mu[:, 0]
         if _addr(rstd):
@@ -303,36 +358,35 @@ class FakeLib:
         return 0
 
     def detrb_layernorm_bwd(self, dy, dy2, x, gamma, mean, rstd, dx, dx_drop, drop_p, seed, site, seed_ptr, dgamma, dbeta,
-                            M, stream):
-        M, drop_p, seed, site = _v(M), _v(drop_p), _v(seed), _v(site)
-        d = M2(dy, _Act.dtype, M, 256, 256).to(F32)
+                            M, split, stream):
+        M, drop_p, seed, site, sp = _v(M), _v(drop_p), _v(seed), _v(site), _v(split)
+        d = RD(dy, M, 256, 256, sp)
         if _addr(dy2):
-            d = d + M2(dy2, _Act.dtype, M, 256, 256).to(F32)
-        xv = M2(x, _Act.dtype, M, 256, 256).to(F32)
+            d = d + RD(dy2, M, 256, 256, sp)
+        xv = RD(x, M, 256, 256, sp)
         mu, rs = T(mean, F32, M)[:, None], T(rstd, F32, M)[:, None]
         g = T(gamma, F32, 256)
         xh = (xv - mu) * rs
         gv = d * g
         o = rs * (gv - gv.mean(-1, keepdim=True) - xh * (gv * xh).mean(-1, keepdim=True))
-        ob = o.to(_Act.dtype)
-        M2(dx, _Act.dtype, M, 256, 256)[:] = ob
+        WR(dx, M, 256, 256, o, sp)
         if _addr(dx_drop):
-            od = ob.to(F32)
+            od = RND(o, sp)
             if drop_p > 0:
                 keep = keep_mask(range(M), range(256), drop_p, seed, site, seed_ptr)
                 od = torch.where(keep, od / (1 - drop_p), torch.zeros_like(od))
-            M2(dx_drop, _Act.dtype, M, 256, 256)[:] = od.to(_Act.dtype)
+            WR(dx_drop, M, 256, 256, od, sp)
         if _addr(dgamma):
             T(dgamma, F32, 256).add_((d * xh).sum(0))
             T(dbeta, F32, 256).add_(d.sum(0))
         return 0
 
     # -- elementwise
-    def detrb_add_rowbcast(self, x, pos, out, M, S, d, stream):
-        M, S, d = _v(M), _v(S), _v(d)
-        xv = M2(x, _Act.dtype, M, d, d).to(F32)
-        pv = M2(pos, _Act.dtype, S, d, d).to(F32)
-        M2(out, _Act.dtype, M, d, d)[:] = (xv + pv[torch.arange(M) % S]).to(_Act.dtype)
+    def detrb_add_rowbcast(self, x, pos, out, M, S, d, split, stream):
+        M, S, d, sp = _v(M), _v(S), _v(d), _v(split)
+        xv = RD(x, M, d, d, sp)
+        pv = RD(pos, S, d, d, sp)
+        WR(out, M, d, d, xv + pv[torch.arange(M) % S], sp)
         return 0
 
     def detrb_add(self, a, b, out, n, stream):
@@ -350,7 +404,7 @@ class FakeLib:
         o[:, 3] = 0
         return 0
 
-    def detrb_image_to_s2d16(self, img, out, B, H, W, pad_top, pad_left, HP, WP, stream):
+    def detrb_image_to_s2d16(self, img, out, B, H, W, pad_top, pad_left, HP, WP, split, stream):
         B, H, W, pt, pl, HP, WP = map(_v, (B, H, W, pad_top, pad_left, HP, WP))
         H2, W2 = (H + 1) // 2, (W + 1) // 2
         x = T(img, F32, B * H * W * 3).view(B, H, W, 3)
@@ -360,7 +414,7 @@ class FakeLib:
         for ry in range(2):
             for rx in range(2):
                 o[:, pt:pt + H2, pl:pl + W2, (ry * 2 + rx) * 3:(ry * 2 + rx) * 3 + 3] = xp[:, ry::2, rx::2]
-        T(out, _Act.dtype, B * HP * WP * 16)[:] = o.reshape(-1).to(_Act.dtype)
+        WR(out, B * HP * WP, 16, 16, o.reshape(-1, 16), _v(split))
         return 0
 
     def detrb_f32_to_bf16(self, x, y, n, stream):
@@ -376,9 +430,9 @@ class FakeLib:
         T(out, F32, N).add_(s)
         return 0
 
-    def detrb_maxpool_fwd(self, x, y, argmax, B, IH, IW, C, OH, OW, XH, XW, stream):
-        B, IH, IW, C, OH, OW, XH, XW = map(_v, (B, IH, IW, C, OH, OW, XH, XW))
-        xv = T(x, _Act.dtype, B * XH * XW * C).to(F32).view(B, XH, XW, C)[:, :IH, :IW]
+    def detrb_maxpool_fwd(self, x, y, argmax, B, IH, IW, C, OH, OW, XH, XW, split, stream):
+        B, IH, IW, C, OH, OW, XH, XW, sp = map(_v, (B, IH, IW, C, OH, OW, XH, XW, split))
+        xv = RD(x, B * XH * XW, C, C, sp).view(B, XH, XW, C)[:, :IH, :IW]
         best = torch.full((B, OH, OW, C), -float("inf"))
         arg = torch.zeros((B, OH, OW, C), dtype=torch.uint8)
         oy, ox = torch.arange(OH), torch.arange(OW)
@@ -393,13 +447,13 @@ class FakeLib:
                 best = torch.where(upd, v, best)
                 arg = torch.where(upd, torch.full_like(arg, kh * 3 + kw), arg)
         arg = torch.where(best > 0, arg, torch.full_like(arg, 15))      # no gradient through the stem's ReLU
-        T(y, _Act.dtype, B * OH * OW * C)[:] = best.reshape(-1).to(_Act.dtype)
+        WR(y, B * OH * OW, C, C, best.reshape(-1, C), sp)
         T(argmax, torch.uint8, B * OH * OW * C)[:] = arg.reshape(-1)
         return 0
 
-    def detrb_maxpool_bwd(self, dy, argmax, dx, B, IH, IW, C, OH, OW, XH, XW, stream):
-        B, IH, IW, C, OH, OW, XH, XW = map(_v, (B, IH, IW, C, OH, OW, XH, XW))
-        d = T(dy, _Act.dtype, B * OH * OW * C).to(F32).view(B, OH, OW, C)
+    def detrb_maxpool_bwd(self, dy, argmax, dx, B, IH, IW, C, OH, OW, XH, XW, split, stream):
+        B, IH, IW, C, OH, OW, XH, XW, sp = map(_v, (B, IH, IW, C, OH, OW, XH, XW, split))
+        d = RD(dy, B * OH * OW, C, C, sp).view(B, OH, OW, C)
         arg = T(argmax, torch.uint8, B * OH * OW * C).view(B, OH, OW, C)
         out = torch.zeros(B, XH, XW, C)
         for oy in range(OH):
@@ -411,7 +465,7 @@ class FakeLib:
                             out[:, iy, ix] += d[:, oy, ox] * (arg[:, oy, ox] == kh * 3 + kw).to(F32)
         out[:, IH:] = 0
         out[:, :, IW:] = 0
-        T(dx, _Act.dtype, B * XH * XW * C)[:] = out.reshape(-1).to(_Act.dtype)
+        WR(dx, B * XH * XW, C, C, out.reshape(-1, C), sp)
         return 0
 
     # -- matcher / loss
@@ -460,8 +514,8 @@ class FakeLib:
         return 0
 
     def detrb_set_loss(self, logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, bg, normalisers, loss_scale, sums, losses,
-                       total, d_logits, ld_dl, d_boxpre, ld_db, stream):
-        ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db = map(_v, (ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db))
+                       total, d_logits, ld_dl, d_boxpre, ld_db, status, split, stream):
+        ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db, sp = map(_v, (ldl, L, B, Q, C, bg, loss_scale, ld_dl, ld_db, split))
         lg = M2(logits, F32, L * B * Q, C, ldl).clone().view(L, B, Q, C).requires_grad_(True)
         bx = T(boxes, F32, L * B * Q * 4).clone().view(L, B, Q, 4).requires_grad_(True)
         tb = T(t_bbox, F32, B * 400).view(B, 100, 4)
@@ -509,15 +563,18 @@ class FakeLib:
             tot = tot + label + 2 * gl + 5 * l1
         tot = tot * loss_scale
         T(total, F32, 1)[0] = tot.detach()
+        if _addr(status) and int(T(status, torch.int32, L * B).abs().sum()) != 0:      # NaN / -inf cost matrix: poisoned result
+            T(total, F32, 1)[0] = float("nan")
+            out[:] = float("nan")
         if _addr(d_logits):
             gl_, gb_ = torch.autograd.grad(tot, [lg, bx])
-            dl = M2(d_logits, _Act.dtype, L * B * Q, ld_dl, ld_dl)
-            dl.zero_()
-            dl[:, :C] = gl_.reshape(-1, C).to(_Act.dtype)
-            db = M2(d_boxpre, _Act.dtype, L * B * Q, ld_db, ld_db)
-            db.zero_()
+            dl = torch.zeros(L * B * Q, ld_dl)
+            dl[:, :C] = gl_.reshape(-1, C)
+            WR(d_logits, L * B * Q, ld_dl, ld_dl, dl, sp)
+            db = torch.zeros(L * B * Q, ld_db)
             bxd = bx.detach()
-            db[:, :4] = (gb_ * bxd * (1 - bxd)).reshape(-1, 4).to(_Act.dtype)
+            db[:, :4] = (gb_ * bxd * (1 - bxd)).reshape(-1, 4)
+            WR(d_boxpre, L * B * Q, ld_db, ld_db, db, sp)
         return 0
 
     # -- optimizer
@@ -590,6 +647,27 @@ class FakeLib:
             t[:, :, :N] = wb.permute(2, 1, 0)
         return 0
 
+    def detrb_prep_weights_multi(self, descs, nslots, total_tiles, wsplit, stream):
+        n, ws = _v(nslots), _v(wsplit)
+        arr = (_lib.PrepDesc * n).from_address(_addr(descs))
+        for d in arr:
+            w = T(d.master, F32, d.N * d.taps * d.Cin).view(d.N, d.taps, d.Cin)
+            if d.fold:
+                w = w * T(d.fold, F32, d.N)[:, None, None]
+            if d.Wf:
+                WR(d.Wf, d.N, d.taps * d.Cin, d.ldf, w.reshape(d.N, d.taps * d.Cin), ws)
+            if d.Wd:
+                WR(d.Wd, d.Cin * d.taps, d.N, d.ldd, w.permute(2, 1, 0).reshape(d.Cin * d.taps, d.N), ws)
+        return 0
+
+    def detrb_accumulate(self, acc, g, n, zero_first, stream):
+        n = _v(n)
+        a, b = T(acc, F32, n), T(g, F32, n)
+        if _v(zero_first):
+            a.zero_()
+        a.add_(b)
+        return 0
+
     # ---- rows either side of the train step (csrc/pipeline.cu)
     @staticmethod
     def _lut_apply(img, lut, swap, npix):
@@ -604,10 +682,10 @@ class FakeLib:
         T(out, F32, npix * 3)[:] = self._lut_apply(img, lut, swap, npix).reshape(-1)
         return 0
 
-    def detrb_image_u8_to_s2d16(self, img, lut, swap, out, B, H, W, pad_top, pad_left, HP, WP, stream):
+    def detrb_image_u8_to_s2d16(self, img, lut, swap, out, B, H, W, pad_top, pad_left, HP, WP, split, stream):
         B, H, W = _v(B), _v(H), _v(W)
         x = self._lut_apply(img, lut, swap, B * H * W).contiguous()
-        return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, pad_top, pad_left, HP, WP, stream)
+        return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, pad_top, pad_left, HP, WP, split, stream)
 
     def detrb_postprocess(self, logits, ldl, boxes, B, Q, C, bg, fmt, out_boxes, out_labels, out_scores, out_query, out_count,
                           stream):
