@@ -23,16 +23,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TRAIN_GFLOP_PER_IMAGE = 604.9          # R50 800x1333, fwd 203.3 + bwd 2*203.3 - 5.0
+# train-step GFLOP per 800x1333 image = 3 x forward - 5.0 (no data gradient into the image)
+TRAIN_GFLOP_PER_IMAGE = {"resnet50": 604.9, "resnet101": 1082.2}
 METRIC = "images/sec DETR-R50 800x1333 train step"
 
 
 def measured_peaks():
+    """(sustained bf16 TF/s, burst bf16 TF/s, HBM GB/s, source).  MEASURED_PEAKS.json is driver-written; B200_PROFILING.md's
+    fallback figures otherwise."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+def tensor_peak(clocks):
+    """Which measured tensor peak applies: a kernel timed while the SM clock sits at its maximum with no power cap active runs
+    in the burst regime (MEASURED_PEAKS bf16_tflops); under the power cap / at reduced clocks the sustained figure applies."""
+    sus, burst, _, how = measured_peaks()
+    if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] \
+            and "sw_power_cap" not in (clocks.get("reasons") or []):
+        return burst, f"MEASURED_PEAKS.json bf16_tflops (burst: SM clock {clocks['sm_mhz']:.0f} of {clocks['sm_max_mhz']:.0f} MHz, no power cap; {how})"
+    return sus, f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})"
 
 
 class ClockSampler:
@@ -227,7 +240,7 @@ def matcher_microbench(D, iters=20):
                                       tbh, tch, cfg), sync_result=True)
     cpu_us = matcher_cpu_us_per_image(logits, boxes, tb, tc)
     alg_bytes = Q * C * 4 + Q * 4 * 4 + 20 * 24 + 420                              # ~39.3 KB / problem
-    _, peak_hbm, _ = measured_peaks()
+    _, _, peak_hbm, _ = measured_peaks()
     return {"workload": "BASELINE configs[4]: 100 queries x 20 targets x batch 256, seed 1234; L2 flushed between iterations",
             "us_per_image": ms_a * 1e3 / B, "problems": B, "kernel": "matcher_kernel (cost build + shortest-augmenting-path LSAP, 1 CTA/problem)",
             "achieved_gbs": alg_bytes * B / (ms_a * 1e-3) / 1e9, "peak_gbs": peak_hbm, "bound": "latency (sequential augmentations)",
@@ -298,6 +311,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-matcher-bench", action="store_true")
+    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "resnet101"],
+                    help="resnet101 + --batch 4 = BASELINE configs[3] per GPU (DETR-R101, 32 images on 8 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -317,7 +332,7 @@ def main():
     cfg = D.TrainingConfig()
     cfg.background_class, cfg.batch_size, cfg.target_batch = 91, B, None
     cfg.train_backbone, cfg.train_transformers = True, True
-    model = D.get_detr_model(cfg, include_top=True, seed=0)            # identical replicas on every rank
+    model = D.get_detr_model(cfg, include_top=True, seed=0, backbone=args.backbone)    # identical replicas on every rank
     opt = D.setup_optimizers(model, cfg)
     eng = model.engine
     images, tb, tc = synthetic_batch(B, H, W, seed=rank)
@@ -384,7 +399,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):                     # fit prints a progress line every 100 steps
         D.training.fit(model, batches(3), opt, cfg, 0, None, on_step=on_step)          # warm-up (captures the step graph)
         passes = []
-        for _ in range(2):                                              # two passes of Ke steps each: host-side hiccups (this leg
+        for _ in range(3):                                              # three passes of Ke steps each: host-side hiccups (this leg
             barrier()                                                   # syncs with the host every step) show up as a slow pass
             t0 = time.perf_counter()
             D.training.fit(model, batches(Ke), opt, cfg, 0, None, on_step=on_step)
@@ -393,51 +408,73 @@ def main():
             if world > 1:
                 dist.all_reduce(t_pass, op=dist.ReduceOp.MAX)
             passes.append(float(t_pass))
-    e2e_value = world * B * Ke / min(passes)
+    e2e_value = world * B * Ke / sorted(passes)[1]                      # the median pass
     h2d = images_h.numel() * 4 + tb_h.numel() * 4 + tc_h.numel() * 8
     dbg("e2e leg done")
 
-    # ------------------------------------------------------------------ roofline of the dominant kernel, timed live
-    # (every rank runs the probe steps -- they contain the gradient all-reduce -- rank 0 reports)
-    roof = None
-    peak_tf, peak_hbm, how = measured_peaks()
-    probe = "backbone/layer3/1/conv2"                                   # 3x3 256->256 @50x84: the heaviest repeated conv shape
-    probe_hbm = "backbone/layer1/1/conv3"                               # 1x1 64->256 + residual + ReLU @200x334: the largest HBM-bound launch
-    eng.probe_names, eng.probe_events = (probe, probe_hbm), {}
+    # ------------------------------------------------------------------ rooflines, timed live (CUDA events on the launching stream)
+    # One object per kernel family of the step; `roofline` is the family with the largest share of the step BY TIME (the one-tile
+    # tcgen05 GEMM kernel on the HBM-bound 1x1 layers, 42 % -- shares from the committed ncu launch list, profiles/), the others
+    # follow in `rooflines`.  Every rank runs the probe steps (they contain the gradient all-reduce), rank 0 reports.
+    peak_sus, peak_burst, peak_hbm, how = measured_peaks()
+    peak_tf, peak_tf_src = tensor_peak(clocks)
+    if world > 1:                                                       # every rank needs the same probe set; clocks only exist on rank 0
+        peak_tf, peak_tf_src = peak_sus, f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})"
+    p_t, p_h = "backbone/layer3/1/conv2", "backbone/layer1/1/conv3"     # 3x3 256->256 @50x84 | 1x1 64->256 + residual + ReLU @200x334
+    eng.probe_names = (p_t, p_h, p_t + "#wgrad", p_h + "#wgrad", p_h + "#dgrad", "e2_attn#fwd", "e2_attn#bwd")
+    eng.probe_events = {}
     for _ in range(3):
         eng.train_step(91, cfg.gradient_norm_clipping)
     torch.cuda.synchronize()
     times = {k: sorted(a.elapsed_time(b) for a, b in v) for k, v in eng.probe_events.items()}
     eng.probe_names = None
-    roof_hbm = None
+    roof, roofs = None, None
     if rank == 0:
-        s = eng.slots[probe]
-        blk = [b for b in eng.blocks if b["c2"] is s][0]
-        M = B * blk["out_hw"][0] * blk["out_hw"][1]
-        flops = 2.0 * M * s.N * s.K
-        t_k = times[probe][len(times[probe]) // 2] * 1e-3
-        roof = {"bound": "tensor", "kernel": "gemm_tcp_kernel<256,4,im2col> (persistent tcgen05 implicit-GEMM conv 3x3 256->256, 128x256 tiles, layer3, M=33600 N=256 K=2304)",
-                "achieved": flops / t_k / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / t_k / 1e12 / peak_tf,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
-                "flops_per_launch": flops, "us_per_launch": t_k * 1e6,
-                "whole_step": {"achieved": TRAIN_GFLOP_PER_IMAGE * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
-                               "frac": TRAIN_GFLOP_PER_IMAGE * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf}}
-        prof = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-        if os.path.exists(prof):
-            roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        # the HBM-bound side of the step (layer1/2 1x1 convolutions = the largest share of the step by time): algorithmic bytes
-        # = input + weights + residual + output, bf16
-        s = eng.slots[probe_hbm]
-        blk = [b for b in eng.blocks if b["c3"] is s][0]
-        M = B * blk["out_hw"][0] * blk["out_hw"][1]
-        byts = 2.0 * (M * s.K + s.N * s.K + 2 * M * s.N)
-        t_h = times[probe_hbm][len(times[probe_hbm]) // 2] * 1e-3
-        roof_hbm = {"bound": "hbm", "kernel": "gemm_tc_kernel<64,1> (one-tile tcgen05 GEMM, 1x1 conv 64->256 + residual + ReLU, layer1, M=534400 N=256 K=64)",
-                    "achieved": byts / t_h / 1e9, "peak": peak_hbm, "unit": "GB/s", "frac": byts / t_h / 1e9 / peak_hbm, "traffic": None,
-                    "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})", "bytes_per_launch": byts, "us_per_launch": t_h * 1e6}
-        prof = os.path.join(ROOT, "profiles", "hbm_kernel_traffic.json")
-        if os.path.exists(prof):
-            roof_hbm["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        med = lambda k: times[k][len(times[k]) // 2] * 1e-3             # seconds
+        gf = TRAIN_GFLOP_PER_IMAGE[args.backbone]
+
+        def traffic(fname):
+            prof = os.path.join(ROOT, "profiles", fname)
+            return json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
+
+        def tensor_obj(kernel, flops, t, tr=None):
+            return {"bound": "tensor", "kernel": kernel, "achieved": flops / t / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": flops / t / 1e12 / peak_tf, "traffic": tr, "peak_source": peak_tf_src, "flops_per_launch": flops,
+                    "us_per_launch": t * 1e6}
+
+        def hbm_obj(kernel, byts, t, tr=None):
+            return {"bound": "hbm", "kernel": kernel, "achieved": byts / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": byts / t / 1e9 / peak_hbm, "traffic": tr, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({how})",
+                    "bytes_per_launch": byts, "us_per_launch": t * 1e6}
+        st, sh = eng.slots[p_t], eng.slots[p_h]
+        bt = [b for b in eng.blocks if b["c2"] is st][0]
+        bh = [b for b in eng.blocks if b["c3"] is sh][0]
+        Mt, Mh = B * bt["out_hw"][0] * bt["out_hw"][1], B * bh["out_hw"][0] * bh["out_hw"][1]
+        S = eng.S
+        # algorithmic bytes (bf16): forward = input + weights + residual + output; data gradient = dY + weights
+        # + ReLU mask + output; weight gradient = input + dY (+ the fp32 gradient tile, negligible)
+        roof = hbm_obj(f"gemm_tc_kernel<64,1> one-tile tcgen05 GEMM: 1x1 conv 64->256 + residual + ReLU, layer1, M={Mh} N=256 K=64",
+                       2.0 * (Mh * sh.K + sh.N * sh.K + 2 * Mh * sh.N), med(p_h), traffic("hbm_kernel_traffic.json"))
+        roof["family"] = "one-tile tcgen05 GEMM / conv (gemm_tc_kernel): the largest share of the step by time (see profiles/: ncu launch list of this round)"
+        roof["whole_step"] = {"achieved": gf * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
+                              "frac_of_tensor_peak": gf * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf, "peak": peak_tf, "peak_source": peak_tf_src}
+        roofs = {
+            "persistent_conv3x3": tensor_obj(f"gemm_tcp_kernel<256,4,im2col> persistent tcgen05 implicit-GEMM conv 3x3 256->256, layer3, M={Mt} N=256 K=2304",
+                                             2.0 * Mt * st.N * st.K, med(p_t), traffic("top_kernel_traffic.json")),
+            "wgrad_conv3x3": tensor_obj(f"wgrad_tc_kernel<im2col> tcgen05 weight gradient of the same 3x3 conv (side stream, overlapped with the data-gradient chain), M={Mt}",
+                                        2.0 * Mt * st.N * st.K, med(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
+            "wgrad_conv1x1_layer1": hbm_obj(f"wgrad_tc_kernel<plain> weight gradient of the layer1 1x1 conv 64->256 (side stream), M={Mh}",
+                                            2.0 * (Mh * sh.K + Mh * sh.N), med(p_h + "#wgrad")),
+            "dgrad_conv1x1_layer1": hbm_obj(f"gemm_tc_kernel one-tile: data gradient of the layer1 1x1 conv 256->64 + ReLU mask, M={Mh}",
+                                            2.0 * (Mh * sh.N + sh.N * sh.K + 2 * Mh * sh.K), med(p_h + "#dgrad")),
+            "attention_fwd": tensor_obj(f"encoder self-attention forward, B={B} H=8 S={S} dh=32 (QK^T + PV flops; {B * 8 * S * S / 1e6:.1f} M exponentials)",
+                                        4.0 * B * 8 * S * S * 32, med("e2_attn#fwd")),
+            "attention_bwd": tensor_obj(f"encoder self-attention backward (delta + dK/dV + dQ kernels), B={B} H=8 S={S} dh=32",
+                                        14.0 * B * 8 * S * S * 32, med("e2_attn#bwd")),
+        }
+        shares = os.path.join(ROOT, "profiles", "family_shares.json")
+        if os.path.exists(shares):
+            roof["family_shares_of_step"] = json.load(open(shares))
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only, bounded sample)
     cpu = None
@@ -445,10 +482,10 @@ def main():
         if bound and orig_affinity:
             os.sched_setaffinity(0, orig_affinity)                      # the CPU baseline may use every host core
         cores = os.cpu_count() or 1
-        t_cpu = cpu_oracle_step_time(H, W, cores, steps=1, warmup=0)
+        t_cpu = cpu_oracle_step_time(H, W, cores, steps=3, warmup=1)    # warm, like the reference arm (--impl reference)
         cpu = {"value": 1.0 / t_cpu, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": "1 train step (fwd+matcher+set loss+bwd+Adam) on 1 synthetic 800x1333 image, PyTorch-CPU oracle "
-                         "restatement of the reference (TensorFlow not installable offline)"}
+               "sample": "3 train steps after 1 warm-up step (fwd+matcher+set loss+bwd+Adam) on 1 synthetic 800x1333 image, R50, "
+                         "PyTorch-CPU oracle restatement of the reference (TensorFlow not installable offline)"}
 
     # ------------------------------------------------------------------ BASELINE configs[4]: matcher us/image (rank 0, N=1)
     matcher = None
@@ -457,19 +494,23 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": METRIC if args.backbone == "resnet50" else METRIC.replace("R50", "R101"),
+            "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "DETR-R50 6enc/6dec, 100 queries, batch 8 per GPU, fixed 800x1333 synthetic, full train step "
-                                   "(fwd w/ dropout, on-device Hungarian + set loss, bwd, grad all-reduce, Adam+clipnorm)",
+            "config": {"workload": f"DETR-{'R50' if args.backbone == 'resnet50' else 'R101'} 6enc/6dec, 100 queries, batch {B} per GPU, fixed {H}x{W} synthetic, full train step "
+                                   "(fwd w/ dropout, on-device Hungarian + set loss, bwd, grad all-reduce, Adam+clipnorm)"
+                                   + ("" if args.backbone == "resnet50" and B == 8 else " [BASELINE configs[3] per GPU]" if args.backbone == "resnet101" and B == 4 else ""),
+                       "precision": "bf16 operands and activations, fp32 accumulation / master weights / optimizer / loss (the fp32-tolerance "
+                                    "parity tests run the same kernels in precision='parity': bf16 pairs, three passes)",
                        "global_batch": world * B, "parallelism": f"dp{world}", "l2": "working set (>3 GB activations/step) exceeds the 126 MB L2",
                        "cuda_graph": not args.no_graph, "targets_per_image": 20},
             "clocks": clocks, "gpu_launches": int(eng.launches_per_step * K),
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back (on_step hook -> float(); fit calls the hook of step i after step i+1 is enqueued)",
-                    "passes_img_per_s": [world * B * Ke / t for t in passes], "reported": "best of the two passes",
+                    "passes_img_per_s": [world * B * Ke / t for t in passes], "reported": "median of the three passes",
                     "cpu_affinity": ("bound to the GPU-local CPUs (NVML affinity): " + str(len(bound)) + " cpus") if bound else "unchanged"},
-            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
+            "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
         }))
     if world > 1:
         dist.destroy_process_group()

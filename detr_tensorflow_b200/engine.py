@@ -153,7 +153,7 @@ class Engine:
         for g in GROUPS:
             offs = [(o, n) for (_, o, n, gg, _) in self.vars if gg == g]
             if offs:                                     # 'nlayers' is empty for the include_top=True model
-                self.group_range[g] = (offs[0][0], offs[-1][0] + offs[-1][1])
+                self.group_range[g] = (offs[0][0], _round_up(offs[-1][0] + offs[-1][1], 64))     # (allocations are 64-aligned)
 
         def view(arena, name):
             o, n = layout[name]
@@ -677,15 +677,18 @@ class Engine:
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
-        probe = s.name in (getattr(self, "probe_names", None) or ())  # bench.py: CUDA-event timing of single launches
-        if probe:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual, ldr=s.N,
-                  relu=relu, C=out, ldc=s.N, split=self.plane, wsplit=self.wplane)
-        if probe:
-            e1.record()
-            self.probe_events.setdefault(s.name, []).append((e0, e1))
+        self._probed(s.name, lambda: ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual,
+                                               ldr=s.N, relu=relu, C=out, ldc=s.N, split=self.plane, wsplit=self.wplane))
+
+    def _probed(self, name, fn):
+        """bench.py: CUDA-event timing of single launches (events on the stream the launch goes to); plain call otherwise"""
+        if name not in (getattr(self, "probe_names", None) or ()):
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.probe_events.setdefault(name, []).append((e0, e1))
 
     def _conv_dgrad(self, s, dy, ihw, ohw, out, mask=None, residual=None):
         """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]."""
@@ -695,15 +698,16 @@ class Engine:
         g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=s.ldd, OH=ihw[0], OW=ihw[1], KH=kh, KW=kwp, stride=stride, pad=pad, mode=1)
         self.launches += 1
         self._before_write(out)
-        ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin, mask_scale=1.0,
-                  residual=residual, ldr=s.Cin, C=out, ldc=s.Cin, split=self.plane, wsplit=self.wplane)
+        self._probed(s.name + "#dgrad", lambda: ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin,
+                                                          mask_scale=1.0, residual=residual, ldr=s.Cin, C=out, ldc=s.Cin,
+                                                          split=self.plane, wsplit=self.wplane))
 
     def _conv_wgrad(self, s, x, dy, ihw, ohw):
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
-        self._on_wstream(lambda: ops.wgrad(x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold,
-                                           dbias=s.bias_grad, split=self.plane), (x, dy))
+        self._on_wstream(lambda: self._probed(s.name + "#wgrad", lambda: ops.wgrad(
+            x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold, dbias=s.bias_grad, split=self.plane)), (x, dy))
 
     def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
         """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
@@ -814,8 +818,8 @@ class Engine:
             self._lin(xinp, W.Wf, M, 2 * d, d, d, out=e("qk"), bias=W.bias)
             self._join(vj)
             self.launches += 1
-            ops.attn_fwd(e("qk"), e("qk")[:, d:], e("v"), 2 * d, 2 * d, d, e("o"), d, e("lse"), B, Hh, S, S, scale,
-                         **self._attn_drop(f"e{l}_attn"))
+            self._probed(f"e{l}_attn#fwd", lambda: ops.attn_fwd(e("qk"), e("qk")[:, d:], e("v"), 2 * d, 2 * d, d, e("o"), d, e("lse"),
+                                                                 B, Hh, S, S, scale, **self._attn_drop(f"e{l}_attn")))
             Wo = E["sa"]["out"]
             self._lin(e("o"), Wo.Wf, M, d, d, d, out=e("pre1"), bias=Wo.bias, residual=xin, ldr=d, **self._drop(f"e{l}_do1"))
             self._ln_fwd(e("pre1"), E["n1"], e("y1"), e("mean1"), e("rstd1"), M)
@@ -907,12 +911,29 @@ class Engine:
                      status=a["status"], split=self.plane)
         self._mark("matcher_loss")
 
+    def check_matcher_status(self):
+        """HOST SYNC.  The reference raises through scipy ("matrix contains invalid numeric entries", hungarian_matching.py:29) when
+        a cost matrix holds NaN / -inf; on device that condition sets status != 0 and turns the loss scalars into NaN
+        (detrb_set_loss).  Callers that already sync with the host (fit / eval progress prints) turn it back into the exception."""
+        if int(self.a["status"].abs().sum()) != 0:
+            raise ValueError("matrix contains invalid numeric entries")
+
     def loss_dict(self, snapshot=False):
         """36 scalars with the reference's keys (loss.py:172-179; aux layer i -> suffix _i, main = last layer).
         The scalars are views of the engine's resident loss buffers, overwritten by the next step; snapshot=True returns views of
         a device copy instead (two small device-to-device copies), safe to read after later steps were enqueued."""
         a, L = self.a, self.ndec
-        losses, total = (a["losses"].clone(), a["total"].clone()) if snapshot else (a["losses"], a["total"])
+        losses, total = a["losses"], a["total"]
+        if snapshot:
+            snap = torch.cat((losses.reshape(-1), total))                    # one small device-to-device copy
+            if self._distributed() and self.normalisers is not None:
+                # data parallel: every rank holds its share of the global-batch loss (local sums / GLOBAL normalisers) -> the
+                # logged loss terms are the SUM over ranks; the three accuracy ratios (columns 1-3) are averaged.  One tiny
+                # all-reduce on the snapshot; the gradients never depended on it.
+                import torch.distributed as dist
+                dist.all_reduce(snap, op=dist.ReduceOp.SUM)
+                snap[:-1].view(L, 6)[:, 1:4] /= dist.get_world_size()
+            losses, total = snap[:-1].view(L, 6), snap[-1:]
         names = ("label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss")
         out = OrderedDict()
         for l in [L - 1] + list(range(L - 1)):
@@ -1039,9 +1060,9 @@ class Engine:
             self._lin(a["gm_b"], Wo.Wd, M, d, d, d, out=a["gm_c"])                                             # d o
             self.launches += 3
             self._before_write(a["gm_qk"], a["gm_v"], a["delta"])
-            ops.attn_bwd(e("qk"), e("qk")[:, d:], e("v"), e("o"), a["gm_c"], 2 * d, 2 * d, d, d, d, e("lse"), a["delta"],
-                         a["gm_qk"], a["gm_qk"][:, d:], a["gm_v"], 2 * d, 2 * d, d, B, Hh, S, S, scale,
-                         **self._attn_drop(f"e{l}_attn"))
+            self._probed(f"e{l}_attn#bwd", lambda: ops.attn_bwd(
+                e("qk"), e("qk")[:, d:], e("v"), e("o"), a["gm_c"], 2 * d, 2 * d, d, d, d, e("lse"), a["delta"],
+                a["gm_qk"], a["gm_qk"][:, d:], a["gm_v"], 2 * d, 2 * d, d, B, Hh, S, S, scale, **self._attn_drop(f"e{l}_attn")))
             self._lin_wgrad(W, xinp, a["gm_qk"], M, n_off=0, n_rows=2 * d)
             self._lin_wgrad(W, xin, a["gm_v"], M, n_off=2 * d, n_rows=d)
             # d x = d_pre1 + dqk.Wqk + dv.Wv   (xp = x + pos shares x's gradient)

@@ -3,6 +3,8 @@ clipnorm, gradient split, accumulation and apply -- backed by one multi-tensor k
 """
 import torch
 
+from . import ops
+
 GROUPS = ("backbone", "transformers", "nlayers")
 
 
@@ -71,9 +73,9 @@ def aggregate_grad_and_apply(name, optimizers, gradients, step, config):
     if k is not None:
         if eng.acc is None:
             eng.acc = torch.zeros_like(eng.grads)
-        if step % k == 0:
-            eng.acc[lo:hi].zero_()
-        eng.acc[lo:hi].add_(eng.grads[lo:hi])
+        # optimizers.py:150-157 on device: one kernel zeroes (at step % k == 0) and adds this micro-step's gradient
+        eng.launches += 1
+        ops.accumulate(eng.acc[lo:hi], eng.grads[lo:hi], hi - lo, step % k == 0)
         src = eng.acc
         optimizers[f"{name}_gradients"] = _group_views(eng, name, eng.acc)
     else:

@@ -38,7 +38,10 @@ def _forward_loss(model, images, t_bbox, t_class, config, training, loss_scale, 
 
 
 def run_train_step(model, images, t_bbox, t_class, optimizers, config):
-    """training.py:9-25: forward(training=True) -> get_losses -> / gradient_aggregate -> gradients of every group."""
+    """training.py:9-25: forward(training=True) -> get_losses -> / gradient_aggregate -> gradients of every group.
+    total_loss and the log scalars are snapshots (safe to read after later steps were enqueued).  m_outputs are VIEWS of the
+    engine's resident logits / boxes buffers, overwritten by the next step (the reference returns fresh tensors): clone what you
+    keep -- in particular inside fit's on_step hook, which runs after the NEXT step has been enqueued."""
     eng = model.engine
     gradient_aggregate = int(config.target_batch // config.batch_size) if config.target_batch is not None else 1
     t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
@@ -142,6 +145,7 @@ def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None
         if epoch_step % 100 == 0:
             t = t if t is not None else time.time()
             elapsed = time.time() - t
+            model.engine.check_matcher_status()            # (this block syncs with the host anyway)
             print(f"Epoch: [{epoch_nb}], \t Step: [{epoch_step}], \t ce: [{float(log['label_cost']):.2f}] \t "
                   f"giou : [{float(log['giou_loss']):.2f}] \t l1 : [{float(log['l1_loss']):.2f}] \t time : [{elapsed:.2f}]")
             t = time.time()
@@ -161,6 +165,7 @@ def eval(model, valid_dt, config, class_name, evaluation_step=200):
         if val_step % 10 == 0:
             t = t if t is not None else time.time()
             elapsed = time.time() - t
+            model.engine.check_matcher_status()
             print(f"Validation step: [{val_step}], \t ce: [{float(log['label_cost']):.2f}] \t "
                   f"giou : [{float(log['giou_loss']):.2f}] \t l1 : [{float(log['l1_loss']):.2f}] \t time : [{elapsed:.2f}]")
         if val_step + 1 >= evaluation_step:

@@ -1,0 +1,188 @@
+"""The public API rows that round 1 only exercised on the CPU emulator, now through the CUDA path: gradient accumulation
+(optimizers.py:137-163, `target_batch`), eval / run_val_step (training.py:28-32, 68-87), the standalone get_losses /
+hungarian_matching wrappers (loss.py:22, hungarian_matching.py:163), checkpoint save / resume, the matcher-status poison."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NE, ND = 1, 2
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import detr_tensorflow_b200 as D
+    return D
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _cfg(D, batch, target_batch):
+    cfg = D.TrainingConfig()
+    cfg.background_class, cfg.batch_size, cfg.target_batch = 91, batch, target_batch
+    cfg.train_backbone, cfg.train_transformers = True, True
+    return cfg
+
+
+def test_accumulate_kernel(D):
+    from detr_tensorflow_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 4 * 100003
+    acc, a, b = torch.full((n,), 7.0, device="cuda"), torch.randn(n, device="cuda", generator=g), torch.randn(n, device="cuda", generator=g)
+    ops.accumulate(acc, a, n, True)
+    ops.accumulate(acc, b, n, False)
+    torch.cuda.synchronize()
+    assert torch.equal(acc, a + b)
+
+
+def test_gradient_accumulation_target_batch_on_device(D):
+    """target_batch = 2 * batch_size (optimizers.py:137-163): two micro-steps accumulate on device (detrb_accumulate), the
+    optimizer applies once, on the SUM of the two micro-step gradients each computed from total_loss / 2 (training.py:20);
+    parity precision + dropout 0 so that the applied update can be checked against the oracle's Adam on the summed gradients."""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=3, num_encoder_layers=NE, num_decoder_layers=ND)
+    imgs = [torch.randn(1, 96, 128, 3, generator=torch.Generator().manual_seed(30 + i)) for i in range(2)]
+    tgts = [O.synthetic_targets(1, n=4, seed=30 + i) for i in range(2)]
+    cfg = _cfg(D, 1, 2)
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=NE, num_decoder_layers=ND, precision="parity")
+    opt = D.setup_optimizers(model, cfg)
+    eng = model.engine
+    p0 = eng.params.clone()
+    sums = None
+    for step in range(2):
+        m_out, total, log, gsteps = D.training.run_train_step(model, imgs[step], tgts[step][0], tgts[step][1], opt, cfg)
+        gnow = eng.grads.clone()
+        sums = gnow if sums is None else sums + gnow
+        for name in gsteps:
+            D.optimizers.aggregate_grad_and_apply(name, opt, gsteps[name]["gradients"], step, cfg)
+        torch.cuda.synchronize()
+        if step == 0:
+            assert torch.equal(eng.params, p0), "no apply before the accumulation window is full"
+            assert torch.equal(eng.acc, gnow)
+    assert torch.equal(eng.acc, sums)                                     # SUM of the micro-step gradients, on device
+    assert opt["backbone_optimizer"].iterations == 1 and opt["transformers_optimizer"].iterations == 1
+    assert float((eng.params - p0).abs().max()) > 0
+    # the oracle: gradients of total / 2 per micro-batch (same assignment), summed, clipped per variable, one Keras-Adam step
+    og = None
+    for step in range(2):
+        _, _, _, g_ = O.train_step(P, imgs[step], tgts[step][0], tgts[step][1], num_encoder_layers=NE, num_decoder_layers=ND,
+                                   gradient_aggregate=2)
+        og = g_ if og is None else {k: (og[k] + g_[k] if g_[k] is not None else og[k]) for k in og}
+    after = model.export_params()
+    worst = 0.0
+    for n_, gsum in og.items():
+        grp = O.param_group(n_)
+        if gsum is None or grp is None:
+            continue
+        p_ref = P[n_].clone()
+        O.adam_clipnorm_step(p_ref, gsum, torch.zeros_like(p_ref), torch.zeros_like(p_ref), 1,
+                             cfg.backbone_lr if grp == "backbone" else cfg.transformers_lr, cfg.gradient_norm_clipping)
+        upd_ref, upd = p_ref - P[n_], after[n_] - P[n_]
+        if float(upd_ref.norm()) > 0:
+            worst = max(worst, rel(upd, upd_ref))
+    print("accumulated Adam update vs oracle: worst relative error of the parameter update", worst)
+    assert worst < 5e-2          # first Adam step: update = lr * g / (|g| + eps) -- a sign-like quantity, sensitive only where g ~ eps
+
+
+def test_eval_and_run_val_step_on_device(D, capsys):
+    """training.eval / run_val_step (training.py:28-32, 68-87): forward(training=False) + losses, no gradients, no update"""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=2, num_encoder_layers=NE, num_decoder_layers=ND)
+    img = torch.randn(2, 96, 128, 3, generator=torch.Generator().manual_seed(2))
+    tb, tc = O.synthetic_targets(2, n=5, seed=2)
+    cfg = _cfg(D, 2, None)
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.1, num_encoder_layers=NE, num_decoder_layers=ND, precision="parity")
+    eng = model.engine
+    p0 = eng.params.clone()
+    m_out, total, log = D.training.run_val_step(model, img, tb, tc, cfg)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.detr_forward(P, img, num_encoder_layers=NE, num_decoder_layers=ND)     # eval mode: dropout off
+    ototal, olog = O.get_losses(ref, tb, tc, 91)
+    assert rel(m_out["pred_logits"], ref["pred_logits"]) < 5e-4
+    assert abs(float(total) - float(ototal)) < 1e-3 * abs(float(ototal))
+    for k in olog:
+        assert abs(float(log[k]) - float(olog[k])) < 1e-3 + 1e-3 * abs(float(olog[k])), k
+    D.training.eval(model, [(img, tb, tc)] * 3, cfg, None, evaluation_step=2)
+    text = capsys.readouterr().out
+    assert "Validation step: [0]" in text and torch.equal(eng.params, p0)
+
+
+def test_standalone_loss_and_matching_wrappers_on_device(D):
+    """D.get_losses / D.hungarian_matching (the functions a user of the reference calls directly) against the reference-code
+    golden vectors (tests/golden/loss_golden.npz: loss.py / hungarian_matching.py / bbox.py executed with the real scipy)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "loss_golden.npz"))
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    logits, boxes = torch.from_numpy(g["l_logits"]), torch.from_numpy(g["l_boxes"])          # [6,B,Q,C], [6,B,Q,4]
+    out = {"pred_logits": logits[5], "pred_boxes": boxes[5], "aux": [{"pred_logits": logits[i], "pred_boxes": boxes[i]} for i in range(5)]}
+    total, losses = D.get_losses(out, g["l_t_bbox"], g["l_t_class"], cfg)
+    assert abs(float(total) - float(g["l_total"])) < 2e-4 * float(g["l_total"])
+    assert list(losses)[:6] == ["label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss"] and len(losses) == 36
+    for k, v in zip(g["l_keys"], g["l_values"]):
+        assert abs(float(losses[str(k)]) - float(v)) < 1e-4 + 1e-4 * abs(float(v)), k
+    for b in range(6):                       # hungarian_matching on one image at a time, the reference's 6-tuple
+        r = D.hungarian_matching(g["m_t_bbox"][b], g["m_t_class"][b], g["m_boxes"][b], g["m_logits"][b])
+        assert np.array_equal(r[0].cpu().numpy(), g[f"m_t_indices_{b}"]) and np.array_equal(r[1].cpu().numpy(), g[f"m_p_indices_{b}"])
+        assert np.array_equal(r[3].cpu().numpy(), g[f"m_p_selector_{b}"]) and bool(r[2].all())
+        np.testing.assert_array_equal(r[4].cpu().numpy(), g[f"m_tb_{b}"])
+
+
+def test_hungarian_matching_wrapper_and_nan_status(D):
+    from oracle import detr_oracle as O
+    gen = torch.Generator().manual_seed(9)
+    logits = torch.randn(100, 92, generator=gen)
+    boxes = torch.cat([torch.rand(100, 2, generator=gen) * 0.9 + 0.05, torch.rand(100, 2, generator=gen) * 0.4 + 0.05], -1)
+    tb, tc = O.synthetic_targets(1, n=7, seed=9)
+    ti, pi, tsel, psel, tbox, tcls = D.hungarian_matching(tb[0], tc[0], boxes, logits)
+    oti, opi, _, _, _, _ = O.hungarian_matching(tb[0], tc[0], boxes, logits)
+    assert torch.equal(ti.cpu(), oti) and torch.equal(pi.cpu(), opi) and int(psel.sum()) == 7 and tbox.shape == (7, 4)
+    bad = logits.clone()
+    bad[3, 5] = float("nan")
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        D.hungarian_matching(tb[0], tc[0], boxes, bad)
+    # get_losses: the same condition poisons every returned scalar (stream-ordered, no exception possible)
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    total, losses = D.get_losses({"pred_logits": bad[None], "pred_boxes": boxes[None], "aux": []}, tb, tc, cfg)
+    assert float(total) != float(total) and all(float(v) != float(v) for v in losses.values())
+    total, losses = D.get_losses({"pred_logits": logits[None], "pred_boxes": boxes[None], "aux": []}, tb, tc, cfg)
+    assert float(total) == float(total)
+
+
+def test_checkpoint_roundtrip_and_resume_on_device(D, tmp_path):
+    """SURVEY 8f N3 on the CUDA path: parameters + Adam moments + step counters survive save / load bit for bit and a resumed
+    run continues identically (dropout 0: the step is deterministic up to the fp32 atomics of the weight gradients)"""
+    from oracle import detr_oracle as O
+    from detr_tensorflow_b200.networks import weights as Wt
+    P = O.init_params(seed=4, num_encoder_layers=NE, num_decoder_layers=ND)
+    img = torch.randn(1, 96, 128, 3, generator=torch.Generator().manual_seed(4))
+    tb, tc = O.synthetic_targets(1, n=3, seed=4)
+    cfg = _cfg(D, 1, None)
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=NE, num_decoder_layers=ND)
+    opt = D.setup_optimizers(model, cfg)
+    D.training.fit(model, [(img, tb, tc)] * 2, opt, cfg, 0, None)
+    path = str(tmp_path / "ck.npz")
+    Wt.save_checkpoint(model, path, cfg)
+    cfg2 = _cfg(D, 1, None)
+    model2 = D.get_detr_model(cfg2, include_top=True, dropout=0.0, num_encoder_layers=NE, num_decoder_layers=ND, weights=path, seed=123)
+    Wt.load_checkpoint(model2, path, cfg2)
+    e1, e2 = model.engine, model2.engine
+    torch.cuda.synchronize()
+    assert cfg2.global_step == 2 and torch.equal(e1.params, e2.params) and torch.equal(e1.adam_m, e2.adam_m)
+    assert torch.equal(e1.adam_v, e2.adam_v) and torch.equal(e1.steps, e2.steps)
+    out1, out2 = model(img, training=False), model2(img, training=False)
+    assert torch.equal(out1["pred_logits"], out2["pred_logits"])
+    opt2 = D.setup_optimizers(model2, cfg2)
+    D.training.fit(model, [(img, tb, tc)], opt, cfg, 0, None)
+    D.training.fit(model2, [(img, tb, tc)], opt2, cfg2, 0, None)
+    torch.cuda.synchronize()
+    assert rel(e2.params - e1.params, e1.params) < 1e-6          # identical up to the summation order of the gradient atomics
