@@ -4,7 +4,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 
 NAMES = ("label_cost", "true_neg", "true_pos", "pos_accuracy", "giou_loss", "l1_loss")
 
@@ -22,6 +22,8 @@ def get_losses(m_outputs, t_bbox, t_class, config):
     hungarian_matching.py:29 -- makes every returned value NaN (checked on device, visible at the caller's read-back)."""
     layers = list(m_outputs.get("aux", [])) + [m_outputs]
     device = layers[0]["pred_logits"].device if isinstance(layers[0]["pred_logits"], torch.Tensor) else torch.device("cuda")
+    if device.type != "cuda" and not getattr(_lib, "_EMULATED", False):
+        device = torch.device("cuda")            # host tensors (numpy / CPU torch) are copied in: the kernels take device pointers only
     logits = torch.stack([_dev(l["pred_logits"], torch.float32, device) for l in layers])      # [L,B,Q,C]
     boxes = torch.stack([_dev(l["pred_boxes"], torch.float32, device) for l in layers])
     L, B, Q, C = logits.shape
