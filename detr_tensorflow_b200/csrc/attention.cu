@@ -595,6 +595,7 @@ extern "C" int detrb_attn_fwd(const detrb_attn_fwd_t *pp, detrb_stream_t stream_
         DETRB_CHECK_LAUNCH("attn_fwd_sp_kernel");
         return DETRB_OK;
     }
+    if (detrb_attn_tc_enabled() && detrb_attn_fwd_tc_supported(p)) return detrb_attn_fwd_tc(p, (cudaStream_t)stream_);   // tcgen05 / TMA / TMEM
     dim3 grid(ceil_div(p.Lq, TQ), p.H, p.B);
     DETRB_LAUNCH(attn_fwd_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream_, p);
     DETRB_CHECK_LAUNCH("attn_fwd_kernel");

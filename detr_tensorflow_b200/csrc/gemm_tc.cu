@@ -736,7 +736,8 @@ EncodeTiledFn get_encode_fn()
 }
 
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128-byte swizzle, zero OOB fill
-bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = TBK)
+bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = TBK,
+              int swizzle_bytes = 128)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
@@ -744,9 +745,10 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                                                  : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -868,9 +870,9 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
 }  // namespace
 
 bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                          uint32_t box_cols)
+                          uint32_t box_cols, int swizzle_bytes)
 {
-    return make_map(map, base, rows, cols, ld, box_rows, box_cols);
+    return make_map(map, base, rows, cols, ld, box_rows, box_cols, swizzle_bytes);
 }
 
 static bool aligned_epilogue(const detrb_igemm_t &p)

@@ -275,7 +275,9 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     if (!sp) { my2 = my; mx2 = mx; }
     const int kt = WK;
     const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
-    int splits = ceil_div(148 * 2, tiles);               // one wave of 2 CTAs per SM: fewer fp32 atomics per gradient element
+    // one wave of 2 CTAs per SM (fewer fp32 atomics per gradient element) -- rounded DOWN: 36 tiles x 9 splits = 324 CTAs on 296
+    // slots ran a second, nearly empty wave (ncu, round 2: SMs active 56 % of the 3x3 256->256 kernel's duration)
+    int splits = (148 * 2) / tiles;
     const int max_splits = ceil_div(p.M, WP * 4);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -56,6 +56,11 @@ def set_tc_wgrad(enable):
     return _lib.lib().detrb_set_tc_wgrad(c_int(int(enable)))
 
 
+def set_tc_attn(enable):
+    """attention forward on the tcgen05 kernel (attention_tc.cu); returns the previous setting"""
+    return _lib.lib().detrb_set_tc_attn(c_int(int(enable)))
+
+
 def set_pdl(enable):
     return _lib.lib().detrb_set_pdl(c_int(int(enable)))
 

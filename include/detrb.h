@@ -158,6 +158,10 @@ typedef struct {
     int64_t split;               /* parity precision: plane stride of the bf16 pairs of Q / K / V / O; fp32 arithmetic (0 = plain bf16) */
 } detrb_attn_fwd_t;
 int detrb_attn_fwd(const detrb_attn_fwd_t *p, detrb_stream_t stream);
+/* The forward runs on the tcgen05 / TMA / TMEM kernel (attention_tc.cu: S and P.V in tensor memory, thread-per-row softmax) when the
+ * strides are multiples of 8 and the operands 16-byte aligned; detrb_set_tc_attn(0) routes it back to the mma.sync kernel
+ * (A/B measurements, tests).  Returns the previous setting.  Both kernels draw identical dropout masks. */
+int detrb_set_tc_attn(int enable);
 
 typedef struct {
     const detrb_bf16 *Q, *K, *V, *O, *dO; int ldq, ldk, ldv, ldo, lddo;

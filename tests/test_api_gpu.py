@@ -77,19 +77,22 @@ def test_gradient_accumulation_target_batch_on_device(D):
                                    gradient_aggregate=2)
         og = g_ if og is None else {k: (og[k] + g_[k] if g_[k] is not None else og[k]) for k in og}
     after = model.export_params()
-    worst = 0.0
+    worst_g, worst_u = 0.0, 0.0
     for n_, gsum in og.items():
         grp = O.param_group(n_)
-        if gsum is None or grp is None:
+        if gsum is None or grp is None or float(gsum.norm()) < 1e-6:
             continue
+        acc = eng._to_ref_layout(n_, eng.acc)                             # the accumulated gradient the optimizer was given
+        worst_g = max(worst_g, rel(acc, gsum))
+        lr = cfg.backbone_lr if grp == "backbone" else cfg.transformers_lr
         p_ref = P[n_].clone()
-        O.adam_clipnorm_step(p_ref, gsum, torch.zeros_like(p_ref), torch.zeros_like(p_ref), 1,
-                             cfg.backbone_lr if grp == "backbone" else cfg.transformers_lr, cfg.gradient_norm_clipping)
-        upd_ref, upd = p_ref - P[n_], after[n_] - P[n_]
-        if float(upd_ref.norm()) > 0:
-            worst = max(worst, rel(upd, upd_ref))
-    print("accumulated Adam update vs oracle: worst relative error of the parameter update", worst)
-    assert worst < 5e-2          # first Adam step: update = lr * g / (|g| + eps) -- a sign-like quantity, sensitive only where g ~ eps
+        O.adam_clipnorm_step(p_ref, gsum, torch.zeros_like(p_ref), torch.zeros_like(p_ref), 1, lr, cfg.gradient_norm_clipping)
+        # first Adam step: update = -lr * g / (|g| + eps'), a sign-like quantity: compare where the gradient is significant
+        sig = gsum.abs() > 1e-3 * gsum.abs().max()
+        upd_ref, upd = (p_ref - P[n_])[sig], (after[n_] - P[n_])[sig]
+        worst_u = max(worst_u, float((upd - upd_ref).abs().max()) / lr)
+    print("accumulated gradient vs oracle: worst rel", worst_g, "; Adam update vs oracle: worst |diff| / lr", worst_u)
+    assert worst_g < 2e-2 and worst_u < 5e-2
 
 
 def test_eval_and_run_val_step_on_device(D, capsys):
@@ -185,4 +188,4 @@ def test_checkpoint_roundtrip_and_resume_on_device(D, tmp_path):
     D.training.fit(model, [(img, tb, tc)], opt, cfg, 0, None)
     D.training.fit(model2, [(img, tb, tc)], opt2, cfg2, 0, None)
     torch.cuda.synchronize()
-    assert rel(e2.params - e1.params, e1.params) < 1e-6          # identical up to the summation order of the gradient atomics
+    assert rel(e2.params, e1.params) < 1e-6                       # identical up to the summation order of the gradient atomics

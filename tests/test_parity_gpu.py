@@ -254,12 +254,24 @@ def test_parity_forward_and_assignment_c2_800x1333(D):
     _close(out, ref, "C2 800x1333")
     match = eng.a["match"].cpu().view(eng.ndec, 1, 100)
     assert int(eng.a["status"].abs().sum()) == 0
+    # Random-init queries give near-identical decoder outputs, so several assignments tie to ~1e-6 of the total cost: the
+    # assignment found on the engine's outputs must be OPTIMAL for the oracle's own cost matrix to fp32 noise (and is usually
+    # identical; the reference-code golden test below pins a bit-exact case)
+    same = 0
     for l in range(eng.ndec):
         o_ = ref if l == eng.ndec - 1 else ref["aux"][l]
         ti, pi, _, _, _, _ = O.hungarian_matching(tb[0], tc[0], o_["pred_boxes"][0], o_["pred_logits"][0])
+        n = int(tb[0, 0, 0])
+        C = O.cost_matrix(tb[0], tc[0], o_["pred_boxes"][0], o_["pred_logits"][0])[0].double()                      # [100, n]
         exp = -torch.ones(100, dtype=torch.int32)
         exp[pi] = ti.int()
-        assert torch.equal(exp, match[l, 0]), f"layer {l}: assignment differs from the oracle's"
+        ours = match[l, 0]
+        assert int((ours >= 0).sum()) == n and len(set(ours[ours >= 0].tolist())) == n           # a complete assignment
+        q = torch.nonzero(ours >= 0).squeeze(-1)
+        cost_ours, cost_opt = float(C[q, ours[q].long()].sum()), float(C[pi, ti].sum())
+        assert cost_ours <= cost_opt + 2e-5 * abs(cost_opt), (l, cost_ours, cost_opt)
+        same += int(torch.equal(exp, ours))
+    print(f"assignment identical to the oracle's in {same} of {eng.ndec} decoder layers; optimal for the oracle's cost in all")
 
 
 def test_parity_forward_vs_reference_code_golden(D):
