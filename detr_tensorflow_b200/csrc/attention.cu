@@ -623,6 +623,7 @@ extern "C" int detrb_attn_bwd(const detrb_attn_bwd_t *pp, detrb_stream_t stream_
         DETRB_CHECK_LAUNCH("attn_bwd_dq_sp_kernel");
         return DETRB_OK;
     }
+    if (detrb_attn_tc_enabled() && detrb_attn_bwd_tc_supported(p)) return detrb_attn_bwd_tc(p, stream);            // tcgen05 / TMA / TMEM
     DETRB_LAUNCH(attn_bwd_dkv_kernel, dim3(dim3(ceil_div(p.Lk, TQ), p.H, p.B)), dim3(128), 0, stream, p);
     DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
     DETRB_LAUNCH(attn_bwd_dq_kernel, dim3(dim3(ceil_div(p.Lq, TQ), p.H, p.B)), dim3(128), 0, stream, p);

@@ -190,22 +190,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (int c = 0; c < BKV; c++)
                     if (kbase + c >= p.Lk) s[c] = 0xff800000u;           // -inf
             }
-            float tmax = -INFINITY;
+            float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains (the softmax warps are latency bound)
 #pragma unroll
-            for (int c = 0; c < BKV; c++) tmax = fmaxf(tmax, __uint_as_float(s[c]));
+            for (int c = 0; c < BKV; c += 4) {
+                tm[0] = fmaxf(tm[0], __uint_as_float(s[c])); tm[1] = fmaxf(tm[1], __uint_as_float(s[c + 1]));
+                tm[2] = fmaxf(tm[2], __uint_as_float(s[c + 2])); tm[3] = fmaxf(tm[3], __uint_as_float(s[c + 3]));
+            }
+            const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
             const float mnew = fmaxf(m, tmax * sl2);                     // log2 domain (sl2 > 0: max commutes with the scaling)
             const float alpha = ex2(m - mnew);                           // ex2(-inf) = 0 on the first tile
             const float mneg = -mnew;
-            float rsum = 0.f;
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t pk[BKV / 2];                                        // packed bf16 pairs (keys 2i, 2i+1)
 #pragma unroll
-            for (int c = 0; c < BKV; c += 2) {
+            for (int c = 0; c < BKV; c += 4) {
                 const float p0 = ex2(fmaf(__uint_as_float(s[c]), sl2, mneg));
                 const float p1 = ex2(fmaf(__uint_as_float(s[c + 1]), sl2, mneg));
-                rsum += p0 + p1;
+                const float p2 = ex2(fmaf(__uint_as_float(s[c + 2]), sl2, mneg));
+                const float p3 = ex2(fmaf(__uint_as_float(s[c + 3]), sl2, mneg));
+                rs[0] += p0; rs[1] += p1; rs[2] += p2; rs[3] += p3;
                 pk[c >> 1] = pack_bf16x2(p0, p1);
+                pk[(c >> 1) + 1] = pack_bf16x2(p2, p3);
             }
-            l = l * alpha + rsum;
+            l = l * alpha + ((rs[0] + rs[1]) + (rs[2] + rs[3]));
             if (drop) {                                                  // the 1/(1-p) rescale is folded into the final normalisation
 #pragma unroll
                 for (int g16 = 0; g16 < BKV / 16; g16++) {
@@ -279,6 +286,415 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
 }
 
+
+// ================================================================================================ backward
+// Two kernels with the forward kernel's anatomy (TMA producer warp, MMA issuer warp, four thread-per-row warps) and only the
+// operand layouts the forward kernel uses: K-major 64-byte-swizzled [rows x 32] tiles from TMA, K-major 128-byte-swizzled
+// [128 x 64] tiles written by the row threads, MN-major reads of the [row][channel] tiles.  delta = rowsum(dO * O) comes from
+// attn_delta_kernel (attention.cu); the 1/(1-p) dropout rescale and the score scale are folded into dss / the final dV.
+//
+//   attn_bwd_dq_tc_kernel   CTA = 128 queries (thread = query row: lse, delta, the dropout row hash are per-thread scalars), loop
+//                           over 64-key tiles:  S = Q K_j^T, dP = dO V_j^T (TMEM), dS = P * (dP - delta) -> shared memory,
+//                           dQ += dS K_j accumulated in TMEM over all key tiles
+//   attn_bwd_dkv_tc_kernel  CTA = 128 keys (thread = key row), loop over 64-query tiles:  S^T = K Q_j^T, dP^T = V dO_j^T (TMEM),
+//                           P^T and dS^T -> shared memory, dV += P^T dO_j and dK += dS^T Q_j accumulated in TMEM; the per-query
+//                           values (lse, delta, row hash) of a tile are staged in shared memory and read as broadcasts
+constexpr int BSTG = 4;                                   // pipeline stages of the streamed operand pair
+constexpr int TILE128 = BQ * DH * 2;                      // [128 x 32] bf16 tile: 8 KB
+constexpr int TILE64 = BKV * DH * 2;                      // [64 x 32] bf16 tile: 4 KB
+constexpr int DS_BYTES = BQ * BKV * 2;                    // [128 x 64] bf16 tile: 16 KB
+// dQ kernel: Q, dO (resident) | BSTG x (K_j, V_j) | 2 x dS | barriers
+constexpr int DQ_OFF_Q = 0, DQ_OFF_DO = TILE128, DQ_OFF_KV = 2 * TILE128, DQ_OFF_DS = DQ_OFF_KV + BSTG * 2 * TILE64;
+constexpr int DQ_OFF_BAR = DQ_OFF_DS + 2 * DS_BYTES;
+constexpr int SMEM_DQ = DQ_OFF_BAR + 256 + 1024;
+// dK/dV kernel: K, V (resident) | BSTG x (Q_j, dO_j) | P^T, dS^T | 2 x per-query arrays (lse, delta, row hash) | barriers
+constexpr int DKV_OFF_K = 0, DKV_OFF_V = TILE128, DKV_OFF_QDO = 2 * TILE128, DKV_OFF_P = DKV_OFF_QDO + BSTG * 2 * TILE64;
+constexpr int DKV_OFF_DS = DKV_OFF_P + DS_BYTES, DKV_OFF_ARR = DKV_OFF_DS + DS_BYTES, DKV_OFF_BAR = DKV_OFF_ARR + 2 * 3 * BKV * 4;
+constexpr int SMEM_DKV = DKV_OFF_BAR + 256 + 1024;
+
+// one swizzled 128-byte row (64 bf16 as 32 packed words) of a K-major [128 x 64] tile: chunk c of row r lives at chunk c ^ (r % 8)
+__device__ __forceinline__ void st_row_half(uint32_t row_addr, uint32_t sw, int half, const uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(row_addr + ((((uint32_t)(half * 4 + c4)) ^ sw) << 4)),
+                     "r"(pk[4 * c4]), "r"(pk[4 * c4 + 1]), "r"(pk[4 * c4 + 2]), "r"(pk[4 * c4 + 3]) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                      const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const detrb_attn_bwd_t p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem0 + DQ_OFF_BAR;
+    const uint32_t q_full = bar0;
+    auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar0 + 8u * (1 + BSTG + s); };
+    const uint32_t sdp_full = bar0 + 8u * (1 + 2 * BSTG), sdp_empty = bar0 + 8u * (2 + 2 * BSTG), dq_full = bar0 + 8u * (3 + 2 * BSTG);
+    auto ds_full = [&](int b) { return bar0 + 8u * (4 + 2 * BSTG + b); };
+    auto ds_empty = [&](int b) { return bar0 + 8u * (6 + 2 * BSTG + b); };
+    const uint32_t tmem_slot = bar0 + 8u * (8 + 2 * BSTG);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DQ = 128;             // TMEM columns
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int nkt = (p.Lk + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < BSTG; s++) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4); mbar_init(dq_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(ds_full(i), 4); mbar_init(ds_empty(i), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * TILE128);
+            tma_load_2d(smem0 + DQ_OFF_Q, &map_q, q_full, h * DH, b * p.Lq + q0);
+            tma_load_2d(smem0 + DQ_OFF_DO, &map_do, q_full, h * DH, b * p.Lq + q0);
+            for (int j = 0; j < nkt; j++) {
+                const int st = j % BSTG;
+                mbar_wait(kv_empty(st), ((j / BSTG) & 1) ^ 1);
+                mbar_expect_tx(kv_full(st), 2 * TILE64);
+                const uint32_t dst = smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64);
+                tma_load_2d(dst, &map_k, kv_full(st), h * DH, b * p.Lk + j * BKV);
+                tma_load_2d(dst + TILE64, &map_v, kv_full(st), h * DH, b * p.Lk + j * BKV);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV, 0), IDESC_DQ = idesc_f16(BQ, DH, 1);
+            mbar_wait(q_full, 0);
+            const uint64_t dq_ = desc_k_sw64(smem0 + DQ_OFF_Q), ddo = desc_k_sw64(smem0 + DQ_OFF_DO);
+            auto issue_sdp = [&](int j) {                                // S = Q K_j^T and dP = dO V_j^T (single-buffered in TMEM)
+                const int st = j % BSTG;
+                mbar_wait(kv_full(st), (j / BSTG) & 1);
+                mbar_wait(sdp_empty, (j & 1) ^ 1);                       // the row threads hold tile j-1 in registers
+                tc_fence_after();
+                const uint32_t kv = smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64);
+                const uint64_t dk = desc_k_sw64(kv), dv = desc_k_sw64(kv + TILE64);
+#pragma unroll
+                for (int k = 0; k < DH / 16; k++) tc_mma_f16(tmem_base + COL_S, dq_ + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_S, k != 0);
+#pragma unroll
+                for (int k = 0; k < DH / 16; k++) tc_mma_f16(tmem_base + COL_DP, ddo + (uint64_t)(k * 2), dv + (uint64_t)(k * 2), IDESC_S, k != 0);
+                tc_commit(sdp_full);
+            };
+            issue_sdp(0);
+            for (int j = 0; j < nkt; j++) {
+                if (j + 1 < nkt) issue_sdp(j + 1);
+                const int st = j % BSTG, db = j & 1;
+                mbar_wait(ds_full(db), (j >> 1) & 1);
+                tc_fence_after();
+                const uint64_t dds = desc_k_sw128(smem0 + DQ_OFF_DS + (uint32_t)db * DS_BYTES);
+                const uint64_t dkm = desc_mn_sw64(smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64));
+#pragma unroll
+                for (int k = 0; k < BKV / 16; k++)                       // dQ += dS_j K_j (K_j read MN-major: [key][channel])
+                    tc_mma_f16(tmem_base + COL_DQ, dds + (uint64_t)(k * 2), dkm + (uint64_t)(k * (1024 >> 4)), IDESC_DQ, (j | k) != 0);
+                tc_commit(kv_empty(st));
+                tc_commit(ds_empty(db));
+            }
+            tc_commit(dq_full);
+        }
+        __syncwarp();
+    } else {
+        const int qr = warp & 3, row = qr * 32 + lane, q = q0 + row;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
+        const bool drop = p.drop_p > 0.f, qok = q < p.Lq;
+        const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
+        const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+        const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
+        const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        const size_t rowg = ((size_t)b * p.H + h) * p.Lq + q;
+        const uint32_t rh = attn_drop_rowhash(seed, p.site, (uint32_t)rowg);
+        const float lse2 = qok ? -p.lse[rowg] * LOG2E : -INFINITY;       // negated, log2 domain (rows beyond Lq: p = 0)
+        const float dlt = qok ? p.delta[rowg] * p.scale : 0.f;           // scale * delta
+        const uint32_t prow = (uint32_t)row * 128u, psw = (uint32_t)(row & 7);
+        for (int j = 0; j < nkt; j++) {
+            const int db = j & 1, kbase = j * BKV;
+            mbar_wait(sdp_full, j & 1);
+            tc_fence_after();
+            uint32_t pk[2][16];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t s[32], dp[32];
+                tc_ld32(lane_addr + COL_S + (uint32_t)(half * 32), s);
+                tc_ld32(lane_addr + COL_DP + (uint32_t)(half * 32), dp);
+                tc_wait_ld();
+                if (half == 1) {                                         // both halves are in registers: the next tile may be computed
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sdp_empty);
+                }
+#pragma unroll
+                for (int g16 = 0; g16 < 2; g16++) {
+                    uint32_t kw[8];
+                    if (drop) {
+                        const uint32_t pair0 = (uint32_t)((kbase >> 4) + half * 2 + g16) * 8u;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) kw[i] = attn_drop_keepbits(attn_drop_word(rh, pair0 + i), thresh2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float ds2[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int c = g16 * 16 + i + e;              // column within this half; key = kbase + half*32 + c
+                            const float pv = ex2(fmaf(__uint_as_float(s[c]), sl2, lse2));
+                            uint32_t dpu = dp[c];
+                            if (drop) dpu &= ((i + e) & 8) ? attn_drop_mask_hi(kw[(i + e) & 7]) : attn_drop_mask_lo(kw[(i + e) & 7]);
+                            float dsv = pv * fmaf(__uint_as_float(dpu), dss, -dlt);      // scale * dS
+                            // keys beyond Lk (last tile): their K rows are not this problem's; exp(0 - lse) may even overflow
+                            if (kbase + half * 32 + c >= p.Lk) dsv = 0.f;
+                            ds2[e] = dsv;
+                        }
+                        pk[half][(g16 * 16 + i) >> 1] = pack_bf16x2(ds2[0], ds2[1]);
+                    }
+                }
+            }
+            mbar_wait(ds_empty(db), ((j >> 1) & 1) ^ 1);
+            const uint32_t dst = smem0 + DQ_OFF_DS + (uint32_t)db * DS_BYTES + prow;
+            st_row_half(dst, psw, 0, pk[0]);
+            st_row_half(dst, psw, 1, pk[1]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_full(db));
+        }
+        mbar_wait(dq_full, 0);
+        tc_fence_after();
+        uint32_t r[DH];
+        tc_ld32(lane_addr + COL_DQ, r);
+        tc_wait_ld();
+        if (qok) {
+            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(p.dQ) + ((size_t)b * p.Lq + q) * p.lddq + h * DH);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]));
+                v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+                v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+                v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+                dst[i] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                       const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, const detrb_attn_bwd_t p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem0 + DKV_OFF_BAR;
+    const uint32_t kv_full = bar0;
+    auto q_full = [&](int s) { return bar0 + 8u * (1 + s); };
+    auto q_empty = [&](int s) { return bar0 + 8u * (1 + BSTG + s); };
+    const uint32_t sdp_full = bar0 + 8u * (1 + 2 * BSTG), sdp_empty = bar0 + 8u * (2 + 2 * BSTG), dkv_full = bar0 + 8u * (3 + 2 * BSTG);
+    const uint32_t pds_full = bar0 + 8u * (4 + 2 * BSTG), pds_empty = bar0 + 8u * (5 + 2 * BSTG);
+    const uint32_t tmem_slot = bar0 + 8u * (6 + 2 * BSTG);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DV = 128, COL_DK = 160;
+    float *arr = reinterpret_cast<float *>(smem_raw + (smem0 + DKV_OFF_ARR - smem_u32(smem_raw)));   // [2][3][64]: lse2 | dlt | row hash
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+    const int nqt = (p.Lq + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        mbar_init(kv_full, 1);
+        for (int s = 0; s < BSTG; s++) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4); mbar_init(dkv_full, 1);
+        mbar_init(pds_full, 4); mbar_init(pds_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * TILE128);
+            tma_load_2d(smem0 + DKV_OFF_K, &map_k, kv_full, h * DH, b * p.Lk + k0);
+            tma_load_2d(smem0 + DKV_OFF_V, &map_v, kv_full, h * DH, b * p.Lk + k0);
+            for (int j = 0; j < nqt; j++) {
+                const int st = j % BSTG;
+                mbar_wait(q_empty(st), ((j / BSTG) & 1) ^ 1);
+                mbar_expect_tx(q_full(st), 2 * TILE64);
+                const uint32_t dst = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
+                tma_load_2d(dst, &map_q, q_full(st), h * DH, b * p.Lq + j * BKV);
+                tma_load_2d(dst + TILE64, &map_do, q_full(st), h * DH, b * p.Lq + j * BKV);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV, 0), IDESC_D = idesc_f16(BQ, DH, 1);
+            mbar_wait(kv_full, 0);
+            const uint64_t dk = desc_k_sw64(smem0 + DKV_OFF_K), dv = desc_k_sw64(smem0 + DKV_OFF_V);
+            auto issue_sdp = [&](int j) {                                // S^T = K Q_j^T and dP^T = V dO_j^T
+                const int st = j % BSTG;
+                mbar_wait(q_full(st), (j / BSTG) & 1);
+                mbar_wait(sdp_empty, (j & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t qd = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
+                const uint64_t dq_ = desc_k_sw64(qd), ddo = desc_k_sw64(qd + TILE64);
+#pragma unroll
+                for (int k = 0; k < DH / 16; k++) tc_mma_f16(tmem_base + COL_S, dk + (uint64_t)(k * 2), dq_ + (uint64_t)(k * 2), IDESC_S, k != 0);
+#pragma unroll
+                for (int k = 0; k < DH / 16; k++) tc_mma_f16(tmem_base + COL_DP, dv + (uint64_t)(k * 2), ddo + (uint64_t)(k * 2), IDESC_S, k != 0);
+                tc_commit(sdp_full);
+            };
+            issue_sdp(0);
+            for (int j = 0; j < nqt; j++) {
+                if (j + 1 < nqt) issue_sdp(j + 1);
+                const int st = j % BSTG;
+                mbar_wait(pds_full, j & 1);
+                tc_fence_after();
+                const uint32_t qd = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
+                const uint64_t dp_ = desc_k_sw128(smem0 + DKV_OFF_P), dds = desc_k_sw128(smem0 + DKV_OFF_DS);
+                const uint64_t dqm = desc_mn_sw64(qd), ddom = desc_mn_sw64(qd + TILE64);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; k++)                       // dV += P^T dO_j
+                    tc_mma_f16(tmem_base + COL_DV, dp_ + (uint64_t)(k * 2), ddom + (uint64_t)(k * (1024 >> 4)), IDESC_D, (j | k) != 0);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; k++)                       // dK += dS^T Q_j
+                    tc_mma_f16(tmem_base + COL_DK, dds + (uint64_t)(k * 2), dqm + (uint64_t)(k * (1024 >> 4)), IDESC_D, (j | k) != 0);
+                tc_commit(q_empty(st));
+                tc_commit(pds_empty);
+            }
+            tc_commit(dkv_full);
+        }
+        __syncwarp();
+    } else {
+        const int qr = warp & 3, row = qr * 32 + lane, key = k0 + row;
+        const int te = threadIdx.x - 64;                                 // 0..127 among the row threads
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qr * 32) << 16);
+        const bool drop = p.drop_p > 0.f;
+        const uint32_t thresh2 = attn_drop_thresh2(p.drop_p);
+        const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+        const float sl2 = p.scale * LOG2E, dss = p.scale * drop_scale;
+        const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        // this thread's key is one field of the dropout word (key pair (k, k+8) of a 16-key group): fixed pair index, fixed field
+        const uint32_t kpair = attn_drop_pair((uint32_t)key);
+        const uint32_t fsel = ((key >> 3) & 1) ? 0xBBBBu : 0x9999u;      // PRMT selector: sign of byte 3 (high field) / byte 1 (low field)
+        const uint32_t prow = (uint32_t)row * 128u, psw = (uint32_t)(row & 7);
+        const size_t rowbase = ((size_t)b * p.H + h) * p.Lq;
+        for (int j = 0; j < nqt; j++) {
+            // per-query values of this tile -> shared memory (double-buffered; one named barrier per tile among the 128 row threads)
+            float *a_lse = arr + (j & 1) * 3 * BKV, *a_dlt = a_lse + BKV;
+            uint32_t *a_rh = reinterpret_cast<uint32_t *>(a_dlt + BKV);
+            if (te < BKV) {
+                const int q = j * BKV + te;
+                const bool ok = q < p.Lq;
+                a_lse[te] = ok ? -p.lse[rowbase + q] * LOG2E : -INFINITY;   // queries beyond Lq: p = 0
+                a_dlt[te] = ok ? p.delta[rowbase + q] * p.scale : 0.f;
+                a_rh[te] = attn_drop_rowhash(seed, p.site, (uint32_t)(rowbase + q));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(sdp_full, j & 1);
+            tc_fence_after();
+            uint32_t ppk[2][16], dpk[2][16];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t s[32], dp[32];
+                tc_ld32(lane_addr + COL_S + (uint32_t)(half * 32), s);
+                tc_ld32(lane_addr + COL_DP + (uint32_t)(half * 32), dp);
+                tc_wait_ld();
+                if (half == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sdp_empty);
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 32; c4 += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4 *>(a_lse + half * 32 + c4);
+                    const float4 d4 = *reinterpret_cast<const float4 *>(a_dlt + half * 32 + c4);
+                    const uint4 h4 = *reinterpret_cast<const uint4 *>(a_rh + half * 32 + c4);
+                    const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
+                    const uint32_t hq[4] = {h4.x, h4.y, h4.z, h4.w};
+                    float pd[4], ds[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float pv = ex2(fmaf(__uint_as_float(s[c4 + e]), sl2, lq[e]));
+                        uint32_t mk = 0xffffffffu;
+                        if (drop) { const uint32_t kb = attn_drop_keepbits(attn_drop_word(hq[e], kpair), thresh2); mk = prmt(kb, kb, fsel); }
+                        pd[e] = __uint_as_float(__float_as_uint(pv) & mk);                       // dropped probability (for dV), unscaled
+                        ds[e] = pv * fmaf(__uint_as_float(dp[c4 + e] & mk), dss, -dq4[e]);     // scale * dS^T
+                    }
+                    ppk[half][c4 >> 1] = pack_bf16x2(pd[0], pd[1]); ppk[half][(c4 >> 1) + 1] = pack_bf16x2(pd[2], pd[3]);
+                    dpk[half][c4 >> 1] = pack_bf16x2(ds[0], ds[1]); dpk[half][(c4 >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+                }
+            }
+            mbar_wait(pds_empty, (j & 1) ^ 1);                           // the dV / dK products of tile j-1 have read the tiles
+            st_row_half(smem0 + DKV_OFF_P + prow, psw, 0, ppk[0]);
+            st_row_half(smem0 + DKV_OFF_P + prow, psw, 1, ppk[1]);
+            st_row_half(smem0 + DKV_OFF_DS + prow, psw, 0, dpk[0]);
+            st_row_half(smem0 + DKV_OFF_DS + prow, psw, 1, dpk[1]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+        }
+        mbar_wait(dkv_full, 0);
+        tc_fence_after();
+        uint32_t rv[DH], rk[DH];
+        tc_ld32(lane_addr + COL_DV, rv);
+        tc_ld32(lane_addr + COL_DK, rk);
+        tc_wait_ld();
+        if (key < p.Lk) {
+            uint4 *dstv = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(p.dV) + ((size_t)b * p.Lk + key) * p.lddv + h * DH);
+            uint4 *dstk = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(p.dK) + ((size_t)b * p.Lk + key) * p.lddk + h * DH);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4 v, k;
+                v.x = pack_bf16x2(__uint_as_float(rv[8 * i]) * drop_scale, __uint_as_float(rv[8 * i + 1]) * drop_scale);
+                v.y = pack_bf16x2(__uint_as_float(rv[8 * i + 2]) * drop_scale, __uint_as_float(rv[8 * i + 3]) * drop_scale);
+                v.z = pack_bf16x2(__uint_as_float(rv[8 * i + 4]) * drop_scale, __uint_as_float(rv[8 * i + 5]) * drop_scale);
+                v.w = pack_bf16x2(__uint_as_float(rv[8 * i + 6]) * drop_scale, __uint_as_float(rv[8 * i + 7]) * drop_scale);
+                k.x = pack_bf16x2(__uint_as_float(rk[8 * i]), __uint_as_float(rk[8 * i + 1]));
+                k.y = pack_bf16x2(__uint_as_float(rk[8 * i + 2]), __uint_as_float(rk[8 * i + 3]));
+                k.z = pack_bf16x2(__uint_as_float(rk[8 * i + 4]), __uint_as_float(rk[8 * i + 5]));
+                k.w = pack_bf16x2(__uint_as_float(rk[8 * i + 6]), __uint_as_float(rk[8 * i + 7]));
+                dstv[i] = v;
+                dstk[i] = k;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace
 
 static int g_attn_tc = 1;
@@ -310,5 +726,38 @@ int detrb_attn_fwd_tc(const detrb_attn_fwd_t &p, cudaStream_t stream)
     dim3 grid(ceil_div(p.Lq, BQ), p.H, p.B);
     DETRB_LAUNCH(attn_fwd_tc_kernel, dim3(grid), dim3(NTHREADS), SMEM_FWD, stream, mq, mk, mv, p);
     DETRB_CHECK_LAUNCH("attn_fwd_tc_kernel");
+    return DETRB_OK;
+}
+
+bool detrb_attn_bwd_tc_supported(const detrb_attn_bwd_t &p)
+{
+    if (p.split) return false;
+    if (p.ldq % 8 || p.ldk % 8 || p.ldv % 8 || p.lddo % 8 || p.lddq % 8 || p.lddk % 8 || p.lddv % 8) return false;
+    if (((uintptr_t)p.Q | (uintptr_t)p.K | (uintptr_t)p.V | (uintptr_t)p.dO | (uintptr_t)p.dQ | (uintptr_t)p.dK | (uintptr_t)p.dV) & 15) return false;
+    if ((long long)p.B * p.Lq >= (1ll << 31) || (long long)p.B * p.Lk >= (1ll << 31)) return false;
+    return true;
+}
+
+// dK/dV then dQ (delta is computed by the caller: attn_delta_kernel)
+int detrb_attn_bwd_tc(const detrb_attn_bwd_t &p, cudaStream_t stream)
+{
+    const uint64_t cols = (uint64_t)p.H * DH;
+    const uint64_t rq = (uint64_t)p.B * p.Lq, rk = (uint64_t)p.B * p.Lk;
+    CUtensorMap q128, do128, k64, v64, q64, do64, k128, v128;
+    if (!detrb_make_tiled_map(&q128, p.Q, rq, cols, (uint64_t)p.ldq, BQ, DH, 64) || !detrb_make_tiled_map(&do128, p.dO, rq, cols, (uint64_t)p.lddo, BQ, DH, 64) ||
+        !detrb_make_tiled_map(&k64, p.K, rk, cols, (uint64_t)p.ldk, BKV, DH, 64) || !detrb_make_tiled_map(&v64, p.V, rk, cols, (uint64_t)p.ldv, BKV, DH, 64) ||
+        !detrb_make_tiled_map(&q64, p.Q, rq, cols, (uint64_t)p.ldq, BKV, DH, 64) || !detrb_make_tiled_map(&do64, p.dO, rq, cols, (uint64_t)p.lddo, BKV, DH, 64) ||
+        !detrb_make_tiled_map(&k128, p.K, rk, cols, (uint64_t)p.ldk, BQ, DH, 64) || !detrb_make_tiled_map(&v128, p.V, rk, cols, (uint64_t)p.ldv, BQ, DH, 64))
+        DETRB_FAIL(DETRB_E_CUDA, "attn_bwd_tc: cuTensorMapEncodeTiled failed (B=%d H=%d Lq=%d Lk=%d)", p.B, p.H, p.Lq, p.Lk);
+    static bool configured = false;
+    if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
+        DETRB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
+        configured = true;
+    }
+    DETRB_LAUNCH(attn_bwd_dkv_tc_kernel, dim3(ceil_div(p.Lk, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DKV, stream, q64, do64, k128, v128, p);
+    DETRB_CHECK_LAUNCH("attn_bwd_dkv_tc_kernel");
+    DETRB_LAUNCH(attn_bwd_dq_tc_kernel, dim3(ceil_div(p.Lq, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DQ, stream, q128, do128, k64, v64, p);
+    DETRB_CHECK_LAUNCH("attn_bwd_dq_tc_kernel");
     return DETRB_OK;
 }

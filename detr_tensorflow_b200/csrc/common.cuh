@@ -34,6 +34,8 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream);
 bool detrb_attn_tc_enabled();
 bool detrb_attn_fwd_tc_supported(const detrb_attn_fwd_t &p);
 int detrb_attn_fwd_tc(const detrb_attn_fwd_t &p, cudaStream_t stream);
+bool detrb_attn_bwd_tc_supported(const detrb_attn_bwd_t &p);
+int detrb_attn_bwd_tc(const detrb_attn_bwd_t &p, cudaStream_t stream);
 // tma_probe.cu: im2col tensor maps
 void *detrb_get_im2col_encode();
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,

@@ -1,7 +1,9 @@
-"""End-to-end GPU parity of the engine (all kernels chained) against the CPU oracle, through the public API.
-Tolerances reflect bf16 activation storage (8-bit mantissa) against the oracle's fp32: forward outputs within a few
-1e-2 relative; gradients are compared under the SAME assignment (match_override) because the Hungarian assignment of
-near-identical random-init queries flips under 1e-3 perturbations."""
+"""End-to-end GPU parity of the engine in the THROUGHPUT precision (plain bf16 activation storage, 8-bit mantissa) against the CPU
+oracle, through the public API.  The fp32-tolerance parity tests are in test_parity_gpu.py (precision="parity").  Bounds here are
+within 2x of the error levels measured on B200 (profiles/r02_parity_errors.txt): forward logits 1.1e-2 / boxes 4.4e-3 relative;
+gradients are compared under the SAME assignment (match_override) because the Hungarian assignment of near-identical random-init
+queries flips under bf16 perturbations; their error (median 6.7e-2, worst 0.38 on the early backbone) is ReLU-mask flips:
+sqrt(forward error), see that file."""
 import pytest
 import torch
 
@@ -44,12 +46,12 @@ def test_forward_parity(D, setup):
             "aux0": rel(out["aux"][0]["pred_logits"], ref["aux"][0]["pred_logits"])}
     print("forward rel errors", errs)
     # tolerance: bf16 storage through 50 conv layers + 12 transformer layers
-    assert errs["logits"] < 5e-2 and errs["boxes"] < 3e-2 and errs["aux0"] < 5e-2, errs
+    assert errs["logits"] < 2.5e-2 and errs["boxes"] < 1e-2 and errs["aux0"] < 2e-2, errs      # measured 1.1e-2 / 4.4e-3 / 8.5e-3
     # backbone feature map itself
     eng = model.engine
     with torch.no_grad():
         feat = O.backbone_forward(P, img)
-    assert rel(eng.feat.view(feat.shape), feat) < 3e-2
+    assert rel(eng.feat.view(feat.shape), feat) < 2e-2
 
 
 def test_forward_vs_reference_code_golden(D):
@@ -75,7 +77,8 @@ def test_forward_vs_reference_code_golden(D):
             "boxes": rel(out["pred_boxes"], ref["pred_boxes"]), "aux0_logits": rel(out["aux"][0]["pred_logits"], ref["aux0_logits"]),
             "aux1_boxes": rel(out["aux"][1]["pred_boxes"], ref["aux1_boxes"])}
     print("rel errors vs reference-code golden", errs)
-    assert errs["feat"] < 4e-2 and errs["logits"] < 6e-2 and errs["boxes"] < 4e-2 and errs["aux0_logits"] < 6e-2 and errs["aux1_boxes"] < 4e-2, errs
+    # measured: feat 7.7e-3, logits 1.4e-2, boxes 4.1e-3, aux0 logits 1.2e-2, aux1 boxes 3.9e-3
+    assert errs["feat"] < 1.6e-2 and errs["logits"] < 3e-2 and errs["boxes"] < 1e-2 and errs["aux0_logits"] < 2.5e-2 and errs["aux1_boxes"] < 1e-2, errs
 
 
 def test_baseline_config_c1_forward_480x640(D):
@@ -93,7 +96,7 @@ def test_baseline_config_c1_forward_480x640(D):
         ref = O.detr_forward(P, img)
     assert out["pred_logits"].shape == (1, 100, 92) and out["pred_boxes"].shape == (1, 100, 4) and len(out["aux"]) == 5
     assert (model.engine.fh, model.engine.fw) == (15, 20)
-    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 3e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 1.2e-2
 
 
 def test_matcher_exact_on_engine_outputs_and_loss_parity(D, setup):
@@ -143,9 +146,11 @@ def test_gradient_parity_under_same_assignment(D, setup):
     print("worst gradient rel errors", worst)
     heads = [n for n in rels if n.startswith(("class_embed", "bbox_embed"))]
     assert max(rels[n] for n in heads) < 0.15, [(n, rels[n]) for n in heads]
-    # bf16 noise amplifies going down the network (relu-mask flips, 60+ chained bf16 tensors): direction must hold
+    # ReLU-mask flips: relative L2 error = sqrt(fraction of flipped elements) ~ sqrt(forward error 1e-2); measured median 6.7e-2,
+    # worst 0.38 (early backbone).  The fp32-class check of the same chain is test_parity_gpu.py::test_parity_gradients_vs_oracle_full_model
     import numpy as np
-    assert float(np.median(list(rels.values()))) < 0.35 and max(rels.values()) < 0.8, worst
+    print("gradient rel errors: median", float(np.median(list(rels.values()))), "max", max(rels.values()))
+    assert float(np.median(list(rels.values()))) < 0.14 and max(rels.values()) < 0.75, worst
 
 
 def test_training_mode_steps_graph_and_dropout(D, setup):
@@ -214,7 +219,8 @@ def test_finetune_heads_nlayers_gpu(D):
         ref = O.detr_forward(P, img)
     assert out["pred_logits"].shape == (2, 100, NB) and len(out["aux"]) == 5
     # tolerance: bf16 storage through the whole network (same as test_forward_parity)
-    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    print("bf16 forward rel errors (logits, boxes)", rel(out["pred_logits"], ref["pred_logits"]), rel(out["pred_boxes"], ref["pred_boxes"]))
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 4e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 2e-2
     opt = D.setup_optimizers(model, cfg)
     eng = model.engine
     before = model.export_params()
@@ -252,7 +258,8 @@ def test_resnet101_backbone_forward(D):
     eng = model.engine
     assert len(eng.blocks) == 33 and eng.total > 45_000_000          # 17 extra layer3 blocks (x 1 114 112 parameters)
     assert rel(eng.feat.view(feat.shape), feat) < 4e-2
-    assert rel(out["pred_logits"], ref["pred_logits"]) < 5e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 3e-2
+    print("bf16 forward rel errors (logits, boxes)", rel(out["pred_logits"], ref["pred_logits"]), rel(out["pred_boxes"], ref["pred_boxes"]))
+    assert rel(out["pred_logits"], ref["pred_logits"]) < 4e-2 and rel(out["pred_boxes"], ref["pred_boxes"]) < 2e-2
     # one full train step runs (backward through 33 blocks, optimizer over the larger arena)
     tb, tc = O.synthetic_targets(1, n=3, seed=2)
     eng.set_targets(tb, tc)
