@@ -1337,32 +1337,83 @@ class Engine:
         self._stage_images(images)
         self.set_targets(t_bbox, t_class)
 
+    def _capture_bucketed(self, body):
+        """Capture body(boundary) -- a backward pass that calls boundary(k) when gradient bucket k is complete -- as consecutive
+        CUDA graphs cut at the bucket boundaries (three graphs for grad_buckets()).  NCCL calls stay out of the graphs (NCCL's
+        watchdog threads and graph capture do not mix safely): the caller replays graph k, enqueues bucket k's asynchronous
+        all-reduce, replays graph k+1, ... so that bucket k crosses NVLink while graph k+1 computes."""
+        import gc
+        graphs = []
+        pool = torch.cuda.graph_pool_handle()
+        cap = torch.cuda.Stream()
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool, capture_error_mode="thread_local")
+            graphs.append(g)
+        nb = len(self.grad_buckets())
+
+        def cut(k):
+            graphs[-1].capture_end()
+            if k + 1 < nb:
+                begin()
+        torch.cuda.synchronize()
+        gc.collect()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            begin()
+            body(cut)
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        assert len(graphs) == nb, len(graphs)
+        return graphs
+
     def grads_step(self, background_class, loss_scale=1.0, use_graph=True):
         """forward(training=True) + set loss + zero_grads + backward + gradient all-reduce on the staged batch
-        (training.py:9-25).  With use_graph the launch sequence is captured once per (shape, arguments) and replayed."""
-        def body():
+        (training.py:9-25).  With use_graph the launch sequence is captured once per (shape, arguments) and replayed.
+        Data parallel: the step is cut at the gradient-bucket boundaries (grad_buckets()); bucket k's sum all-reduce is enqueued
+        asynchronously as soon as its part of the backward pass has been replayed and runs over NVLink while the next part
+        computes; the current stream waits for all of them before returning (stream-level wait, no host sync)."""
+        def body(boundary=None):
             self.training = True
             self.seed_dev.add_(1)
             self._forward_impl()
             self.loss(background_class, loss_scale=loss_scale, with_grad=True)
             self.zero_grads()
-            self.backward(train_backbone=True)
+            self.backward(train_backbone=True, boundary=boundary)
         self._ensure_weights()                             # a per-group apply (apply_group) since the last forward pass
+        dist_on = self._distributed()
         if not use_graph or self.device.type != "cuda":
-            body()
-            return self.allreduce_grads()
+            if not dist_on:
+                return body()
+            works = []
+            body(lambda k: works.append(self.allreduce_bucket(k)))
+            for w in works:
+                w.wait()
+            return
         key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None, self.u8_input,
-               getattr(self, "input_method", None))
+               getattr(self, "input_method", None), dist_on)
         if getattr(self, "_gs_key", None) != key:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 body()                                     # warm-up (kernel attribute setup)
+                self.allreduce_grads()                     # (and NCCL's communicator, outside any capture)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                body()
-            self._gs_graph, self._gs_key = g, key
-        self._gs_graph.replay()
-        self.allreduce_grads()                             # eager NCCL call (kept out of the graph)
+            if dist_on:
+                self._gs_graph = self._capture_bucketed(body)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    body()
+                self._gs_graph = g
+            self._gs_key = key
+        if not dist_on:
+            return self._gs_graph.replay()
+        works = []
+        for k, g in enumerate(self._gs_graph):
+            g.replay()
+            works.append(self.allreduce_bucket(k))         # eager, asynchronous NCCL call between two graphs
+        for w in works:
+            w.wait()
