@@ -168,7 +168,101 @@ postprocess_kernel(const float *__restrict__ logits, int ldl, const float *__res
     }
 }
 
-} // namespace
+
+// ------------------------------------------------------------------------------------------ mAP matching
+// loss/compute_map.py:183-272 (cal_map, 'box' entries) for one image per warp.  Detections are visited in descending score order
+// (stable); each takes the unused ground-truth box of its class with the highest IoU above the threshold (strictly greater, first
+// maximum wins: :231-241); lane t runs the greedy pass of IoU threshold t.  IoU in the reference's fp32 operation order
+// (compute_iou :104-122: inter / ((area_gt + area_pred) - inter), no FMA contraction), compared as doubles like the reference's
+// python floats.
+__device__ __forceinline__ float map_iou(const float4 g, float ga, const float4 q, float qa)
+{
+    const float y1 = fmaxf(g.x, q.x), y2 = fminf(g.z, q.z), x1 = fmaxf(g.y, q.y), x2 = fminf(g.w, q.w);
+    const float inter = __fmul_rn(fmaxf(__fsub_rn(x2, x1), 0.f), fmaxf(__fsub_rn(y2, y1), 0.f));
+    const float uni = __fsub_rn(__fadd_rn(ga, qa), inter);
+    return __fdiv_rn(inter, uni);
+}
+
+constexpr int MAPQ = 256, MAPT = 100;
+__global__ void __launch_bounds__(32)
+map_match_kernel(const float *__restrict__ pred_boxes, const int64_t *__restrict__ pred_labels, const float *__restrict__ pred_scores,
+                 const int32_t *__restrict__ pred_count, int Q, const float *__restrict__ t_boxes, const int64_t *__restrict__ t_labels,
+                 const int32_t *__restrict__ t_count, int NT, int t_wire, const double *__restrict__ thresholds, int T, int num_classes,
+                 int32_t *__restrict__ rank, uint8_t *__restrict__ tp, int32_t *__restrict__ gt_count)
+{
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float4 s_pb[MAPQ], s_tb[MAPT];
+    __shared__ float s_pa[MAPQ], s_ps[MAPQ], s_ta[MAPT];
+    __shared__ int s_pc[MAPQ], s_tc[MAPT], s_order[MAPQ];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    int cnt = pred_count[b];
+    cnt = cnt < 0 ? 0 : (cnt > Q ? Q : cnt);
+    int n;
+    if (t_wire) {                                   // data/processing.py:35-55: row 0 = [n, 0, 0, 0], rows 1..n = (cx, cy, w, h)
+        const float hdr = t_boxes[(size_t)b * NT * 4];
+        n = (int)fminf(fmaxf(hdr, 0.f), (float)(NT - 1));
+    } else {
+        n = t_count[b];
+        n = n < 0 ? 0 : (n > NT ? NT : n);
+    }
+    if (n > MAPT) n = MAPT;
+    for (int i = lane; i < cnt; i += 32) {
+        const float4 q = *reinterpret_cast<const float4 *>(pred_boxes + ((size_t)b * Q + i) * 4);
+        s_pb[i] = q;
+        s_pa[i] = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+        s_ps[i] = pred_scores[(size_t)b * Q + i];
+        s_pc[i] = (int)pred_labels[(size_t)b * Q + i];
+    }
+    for (int j = lane; j < n; j += 32) {
+        float4 g;
+        if (t_wire) {                               // bbox.py:171-183 + :125-138: clipped corners, yx order
+            const float4 c = *reinterpret_cast<const float4 *>(t_boxes + ((size_t)b * NT + 1 + j) * 4);
+            const float hw = __fmul_rn(c.z, 0.5f), hh = __fmul_rn(c.w, 0.5f);
+            const float xmin = fminf(fmaxf(__fsub_rn(c.x, hw), 0.f), 1.f), ymin = fminf(fmaxf(__fsub_rn(c.y, hh), 0.f), 1.f);
+            const float xmax = fminf(fmaxf(__fadd_rn(c.x, hw), 0.f), 1.f), ymax = fminf(fmaxf(__fadd_rn(c.y, hh), 0.f), 1.f);
+            g = make_float4(ymin, xmin, ymax, xmax);
+            s_tc[j] = (int)t_labels[(size_t)b * NT + 1 + j];
+        } else {
+            g = *reinterpret_cast<const float4 *>(t_boxes + ((size_t)b * NT + j) * 4);
+            s_tc[j] = (int)t_labels[(size_t)b * NT + j];
+        }
+        s_tb[j] = g;
+        s_ta[j] = __fmul_rn(__fsub_rn(g.z, g.x), __fsub_rn(g.w, g.y));
+        if (gt_count && s_tc[j] >= 0 && s_tc[j] < num_classes) atomicAdd(gt_count + s_tc[j], 1);
+    }
+    __syncwarp();
+    // descending-score order, stable (sorted(range(num_pred), key=lambda i: -score[i]), :211)
+    for (int i = lane; i < cnt; i += 32) {
+        const float si = s_ps[i];
+        int r = 0;
+        for (int k = 0; k < cnt; k++) r += (s_ps[k] > si) || (s_ps[k] == si && k < i);
+        s_order[r] = i;
+        rank[(size_t)b * Q + i] = r;
+    }
+    for (int i = cnt + lane; i < Q; i += 32) rank[(size_t)b * Q + i] = -1;
+    __syncwarp();
+    if (lane < T) {
+        const double thr = thresholds[lane];
+        uint32_t used[4] = {0u, 0u, 0u, 0u};
+        uint8_t *out = tp + ((size_t)b * T + lane) * Q;
+        for (int pos = 0; pos < cnt; pos++) {
+            const int i = s_order[pos], cls = s_pc[i];
+            double best = thr;
+            int bj = -1;
+            for (int j = 0; j < n; j++) {
+                if (s_tc[j] != cls || ((used[j >> 5] >> (j & 31)) & 1u)) continue;
+                const double v = (double)map_iou(s_tb[j], s_ta[j], s_pb[i], s_pa[i]);
+                if (v > best) { best = v; bj = j; }
+            }
+            if (bj >= 0) used[bj >> 5] |= 1u << (bj & 31);
+            out[i] = bj >= 0 ? 1 : 0;
+        }
+        for (int i = cnt; i < Q; i++) out[i] = 0;
+    }
+}
+
+}  // namespace
 
 extern "C" int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float *out, int64_t npix, detrb_stream_t stream)
 {
@@ -211,5 +305,22 @@ extern "C" int detrb_postprocess(const float *logits, int ldl, const float *boxe
     DETRB_LAUNCH(postprocess_kernel, dim3((unsigned)B), dim3(128), 0, (cudaStream_t)stream, logits, ldl, boxes, Q, C, background_class,
                  bbox_format, out_boxes, out_labels, out_scores, out_query, out_count);
     DETRB_CHECK_LAUNCH("postprocess_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_map_match(const float *pred_boxes, const int64_t *pred_labels, const float *pred_scores, const int32_t *pred_count,
+                               int B, int Q, const float *t_boxes, const int64_t *t_labels, const int32_t *t_count, int NT, int t_wire,
+                               const double *thresholds, int T, int num_classes, int32_t *rank, uint8_t *tp, int32_t *gt_count,
+                               detrb_stream_t stream)
+{
+    DETRB_REQUIRE(pred_boxes && pred_labels && pred_scores && pred_count && t_boxes && t_labels && thresholds && rank && tp,
+                  "detrb_map_match: null pointer");
+    DETRB_REQUIRE(t_wire || t_count, "detrb_map_match: t_count is required unless the targets are in the padded wire format");
+    DETRB_REQUIRE(B > 0 && Q > 0 && Q <= MAPQ && NT > 0 && NT <= MAPT + 1 && T > 0 && T <= 32, "detrb_map_match: B=%d Q=%d (<= %d) NT=%d T=%d (<= 32)",
+                  B, Q, MAPQ, NT, T);
+    DETRB_REQUIRE((((uintptr_t)pred_boxes | (uintptr_t)t_boxes) & 15) == 0, "detrb_map_match: boxes must be 16-byte aligned");
+    DETRB_LAUNCH(map_match_kernel, dim3(B), dim3(32), 0, (cudaStream_t)stream, pred_boxes, pred_labels, pred_scores, pred_count, Q, t_boxes,
+                 t_labels, t_count, NT, t_wire, thresholds, T, num_classes, rank, tp, gt_count);
+    DETRB_CHECK_LAUNCH("map_match_kernel");
     return DETRB_OK;
 }

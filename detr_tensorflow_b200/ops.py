@@ -223,3 +223,10 @@ def postprocess(logits, ldl, boxes, B, Q, C, background_class, bbox_format, out_
     check(_lib.lib().detrb_postprocess(ptr(logits), c_int(ldl), ptr(boxes), c_int(B), c_int(Q), c_int(C),
                                        c_int(int(background_class)), c_int(int(bbox_format)), ptr(out_boxes), ptr(out_labels),
                                        ptr(out_scores), ptr(out_query), ptr(out_count), _stream()))
+
+
+def map_match(pred_boxes, pred_labels, pred_scores, pred_count, B, Q, t_boxes, t_labels, t_count, NT, t_wire, thresholds, T, num_classes,
+              rank, tp, gt_count):
+    check(_lib.lib().detrb_map_match(ptr(pred_boxes), ptr(pred_labels), ptr(pred_scores), ptr(pred_count), c_int(B), c_int(Q), ptr(t_boxes),
+                                     ptr(t_labels), ptr(t_count), c_int(NT), c_int(int(t_wire)), ptr(thresholds), c_int(T), c_int(num_classes),
+                                     ptr(rank), ptr(tp), ptr(gt_count), _stream()))

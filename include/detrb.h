@@ -342,6 +342,22 @@ int detrb_postprocess(const float *logits, int ldl, const float *boxes, int B, i
                       int bbox_format, float *out_boxes, int64_t *out_labels, float *out_scores, int32_t *out_query,
                       int32_t *out_count, detrb_stream_t stream);
 
+/* mAP matching (loss/compute_map.py:183-272, cal_map 'box' entries; driven per image by eval.py:38-52) for B images in one launch.
+ *   detections: pred_boxes [B,Q,4] f32 in yxyx corners, pred_labels [B,Q] i64, pred_scores [B,Q] f32, the first pred_count[b] rows of
+ *   image b valid (= the outputs of detrb_postprocess with bbox_format 2).  Q <= 256.
+ *   ground truth: t_wire != 0: the padded wire format of data/processing.py:35-55 (t_boxes [B,NT,4] cxcywh with header row, t_labels
+ *   [B,NT,1], NT = 100; converted to clipped yxyx corners like bbox.py:171-183 / :125-138); t_wire == 0: t_boxes [B,NT,4] yxyx rows,
+ *   t_labels [B,NT], t_count [B].  At most 100 boxes per image.
+ *   thresholds [T] f64 (DEVICE; the reference's python floats), T <= 32.
+ * out: rank [B,Q] i32 = position of detection i in the stable descending-score order (-1 beyond pred_count); tp [B,T,Q] u8 = 1 when
+ *      detection i is a true positive at threshold t: visited in that order it takes the unused ground-truth box of its class with the
+ *      highest IoU strictly above the threshold (first maximum wins); IoU in the reference's fp32 operation order, compared in fp64.
+ *      gt_count [num_classes] i32 (optional) += ground-truth boxes per class (add_gt_positives, :225). */
+int detrb_map_match(const float *pred_boxes, const int64_t *pred_labels, const float *pred_scores, const int32_t *pred_count,
+                    int B, int Q, const float *t_boxes, const int64_t *t_labels, const int32_t *t_count, int NT, int t_wire,
+                    const double *thresholds, int T, int num_classes, int32_t *rank, uint8_t *tp, int32_t *gt_count,
+                    detrb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

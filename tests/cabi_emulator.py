@@ -52,6 +52,9 @@ def T(p, dtype, count):
     return torch.frombuffer(buf, dtype=dtype, count=count)
 
 
+T_ = T        # (alias: some emulator methods have a parameter called T)
+
+
 def M2(p, dtype, rows, cols, ld):
     """[rows, cols] strided view with row stride ld"""
     t = T(p, dtype, (rows - 1) * ld + cols)
@@ -708,6 +711,61 @@ class FakeLib:
             ob[b, :k], ol[b, :k], os_[b, :k], oc[b] = r, label[keep], score[keep], k
             if oq is not None:
                 oq.view(B, Q)[b, :k] = keep.int()
+        return 0
+
+    def detrb_map_match(self, pred_boxes, pred_labels, pred_scores, pred_count, B, Q, t_boxes, t_labels, t_count, NT, t_wire, thresholds, T,
+                        num_classes, rank, tp, gt_count, stream):
+        B, Q, NT, t_wire, Tn, ncls = map(_v, (B, Q, NT, t_wire, T, num_classes))
+        pb = T_(pred_boxes, F32, B * Q * 4).view(B, Q, 4).numpy()
+        pl = T_(pred_labels, torch.int64, B * Q).view(B, Q).numpy()
+        ps = T_(pred_scores, F32, B * Q).view(B, Q).numpy()
+        pc = T_(pred_count, torch.int32, B).numpy()
+        thr = T_(thresholds, torch.float64, Tn).numpy()
+        rk = T_(rank, torch.int32, B * Q).view(B, Q)
+        out = T_(tp, torch.uint8, B * Tn * Q).view(B, Tn, Q)
+        gc = T_(gt_count, torch.int32, ncls) if _addr(gt_count) else None
+        f = np.float32
+        for b in range(B):
+            k = int(min(max(pc[b], 0), Q))
+            if t_wire:
+                tb_ = T_(t_boxes, F32, B * NT * 4).view(B, NT, 4).numpy()[b]
+                n = int(min(max(tb_[0, 0], 0), NT - 1))
+                c = tb_[1:1 + n]
+                xy = np.clip(np.concatenate([c[:, :2] - c[:, 2:] * f(0.5), c[:, :2] + c[:, 2:] * f(0.5)], -1), f(0), f(1)).astype(f)
+                gtb = xy[:, [1, 0, 3, 2]]
+                gtc = T_(t_labels, torch.int64, B * NT).view(B, NT).numpy()[b, 1:1 + n]
+            else:
+                n = int(min(max(T_(t_count, torch.int32, B).numpy()[b], 0), NT))
+                gtb = T_(t_boxes, F32, B * NT * 4).view(B, NT, 4).numpy()[b, :n]
+                gtc = T_(t_labels, torch.int64, B * NT).view(B, NT).numpy()[b, :n]
+            if gc is not None:
+                for cc in gtc:
+                    if 0 <= cc < ncls:
+                        gc[int(cc)] += 1
+            order = sorted(range(k), key=lambda i: -float(ps[b, i]))
+            rk[b] = -1
+            for r, i in enumerate(order):
+                rk[b, i] = r
+            ga = (gtb[:, 2] - gtb[:, 0]) * (gtb[:, 3] - gtb[:, 1])
+            out[b] = 0
+            with np.errstate(invalid="ignore", divide="ignore"):
+                for t in range(Tn):
+                    used = [False] * n
+                    for i in order:
+                        q = pb[b, i]
+                        qa = (q[2] - q[0]) * (q[3] - q[1])
+                        best, bj = float(thr[t]), -1
+                        for j in range(n):
+                            if used[j] or gtc[j] != pl[b, i]:
+                                continue
+                            g = gtb[j]
+                            inter = max(min(g[3], q[3]) - max(g[1], q[1]), f(0)) * max(min(g[2], q[2]) - max(g[0], q[0]), f(0))
+                            v = float(f(inter) / f(f(ga[j] + qa) - f(inter)))
+                            if v > best:
+                                best, bj = v, j
+                        if bj >= 0:
+                            used[bj] = True
+                            out[b, t, i] = 1
         return 0
 
     def detrb_attn_dropout_mask(self, out, M, N, drop_p, seed, site, seed_ptr, stream):

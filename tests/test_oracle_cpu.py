@@ -293,3 +293,28 @@ def test_oracle_normalize_and_pad_labels_vs_reference_golden(pipeline_golden):
     for k in range(4):
         tb, tc = O.pad_labels(torch.from_numpy(g[f"p_{k}_in_bbox"]), torch.from_numpy(g[f"p_{k}_in_class"])[:, 0])
         assert np.array_equal(tb.numpy(), g[f"p_{k}_bbox"]) and np.array_equal(tc.numpy(), g[f"p_{k}_class"])
+
+
+def test_map_oracle_vs_reference_code_golden():
+    """oracle/map_oracle.py against the reference's own compute_map.py (tests/golden/make_golden_map.py -> map_golden.npz):
+    per (IoU threshold, class) AP, ground-truth counts, number of detections, and the rounded summary dict"""
+    import os
+    import numpy as np
+    from oracle import map_oracle as M
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "map_golden.npz"))
+    ncls, nimg = int(g["ncls"]), int(g["nimg"])
+    thr = [x / 100. for x in range(50, 100, 5)]
+    ap = [[M.APData() for _ in range(ncls)] for _ in thr]
+    for i in range(nimg):
+        M.cal_map_image(M.yxyx_from_xcycwh(g[f"p_bbox_{i}"]), g[f"p_cls_{i}"], g[f"p_score_{i}"], M.yxyx_from_xcycwh(g[f"t_bbox_{i}"]),
+                        g[f"t_cls_{i}"], ap, thr)
+    for a in range(len(thr)):
+        for c in range(ncls):
+            assert ap[a][c].num_gt_positives == g["box_ngt"][a, c] and len(ap[a][c].data_points) == g["box_npts"][a, c]
+            if g["box_ap"][a, c] >= 0:
+                assert abs(ap[a][c].get_ap() - g["box_ap"][a, c]) < 1e-12, (a, c)
+            else:
+                assert ap[a][c].is_empty()
+    maps = M.calc_map(ap, thr, ncls)
+    assert [str(k) for k in maps.keys()] == g["box_map_keys"].tolist()
+    np.testing.assert_allclose(list(maps.values()), g["box_map_values"], atol=1e-9)

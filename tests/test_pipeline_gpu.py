@@ -117,3 +117,94 @@ def test_uint8_frames_through_model_and_fit(D):
     assert len(a) == 3 and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
     assert all(abs(x - y) <= 1e-3 * abs(y) for x, y in zip(a, b)), (a, b)
     assert losses["u8"][1][2] != losses["u8"][1][0]           # the optimizer moved
+
+
+def test_map_matching_and_evaluation_vs_reference_golden(D):
+    """the mAP path on device (map_match_kernel behind loss/compute_map.py) against the reference's own
+    compute_map.py (tests/golden/map_golden.npz): per-image reference-style cal_map calls, and the batched wire-format matcher"""
+    import os
+    from detr_tensorflow_b200.loss import compute_map as CM
+    from oracle import map_oracle as MO
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "map_golden.npz"))
+    ncls, nimg = int(g["ncls"]), int(g["nimg"])
+    names = [f"c{i}" for i in range(ncls)]
+    thr = CM.IOU_THRESHOLDS
+    ap = {"box": [[CM.APDataObject() for _ in names] for _ in thr], "mask": [[CM.APDataObject() for _ in names] for _ in thr]}
+    for i in range(nimg):
+        CM.cal_map(MO.yxyx_from_xcycwh(g[f"p_bbox_{i}"]), g[f"p_cls_{i}"], g[f"p_score_{i}"], None, MO.yxyx_from_xcycwh(g[f"t_bbox_{i}"]),
+                   g[f"t_cls_{i}"], None, ap, thr)
+    for a in range(len(thr)):
+        for c in range(ncls):
+            obj = ap["box"][a][c]
+            assert obj.num_gt_positives == g["box_ngt"][a, c] and len(obj.data_points) == g["box_npts"][a, c]
+            if g["box_ap"][a, c] >= 0:
+                assert abs(obj.get_ap() - g["box_ap"][a, c]) < 1e-12, (a, c)
+    maps = CM.calc_map(ap, thr, names)
+    np.testing.assert_allclose(list(maps["box"].values()), g["box_map_values"], atol=1e-9)
+    np.testing.assert_allclose(list(maps["mask"].values()), g["mask_map_values"], atol=1e-9)
+
+
+def test_map_matching_batched_vs_oracle(D):
+    """64 random images (up to 100 detections, up to 30 targets, 20 classes, score ties and duplicate boxes) through ONE matching
+    launch in the padded wire format: true-positive flags, ranks and the summary must equal the oracle's (bit-exact integers)"""
+    from detr_tensorflow_b200.loss import compute_map as CM
+    from oracle import map_oracle as MO
+    rs = np.random.RandomState(5)
+    B, Q, ncls = 64, 100, 20
+    thr = CM.IOU_THRESHOLDS
+    boxes, labels, scores = np.zeros((B, Q, 4), np.float32), np.zeros((B, Q), np.int64), np.zeros((B, Q), np.float32)
+    count = np.zeros(B, np.int32)
+    tb, tc = np.zeros((B, 100, 4), np.float32), np.zeros((B, 100, 1), np.int64)
+    oap = [[MO.APData() for _ in range(ncls)] for _ in thr]
+    for b in range(B):
+        n, k = int(rs.randint(0, 31)), int(rs.randint(0, Q + 1))
+        t = np.concatenate([rs.uniform(0.1, 0.9, (n, 2)), rs.uniform(0.05, 0.6, (n, 2))], -1).astype(np.float32)
+        tcls = rs.randint(0, ncls, n)
+        if n:
+            src = rs.randint(0, n, k)
+            p = (t[src] + rs.normal(0, 0.02, (k, 4)) * (rs.rand(k, 1) < 0.7)).astype(np.float32)
+            pcls = np.where(rs.rand(k) < 0.8, tcls[src], rs.randint(0, ncls, k))
+        else:
+            p = np.concatenate([rs.uniform(0.1, 0.9, (k, 2)), rs.uniform(0.05, 0.6, (k, 2))], -1).astype(np.float32)
+            pcls = rs.randint(0, ncls, k)
+        sc = np.round(rs.uniform(0.05, 1.0, k), 2).astype(np.float32)              # two decimals: many exact score ties
+        pyx = MO.yxyx_from_xcycwh(p)
+        boxes[b, :k], labels[b, :k], scores[b, :k], count[b] = pyx, pcls, sc, k
+        tb[b, 0, 0] = n
+        tb[b, 1:1 + n], tc[b, 1:1 + n, 0] = t, tcls
+        MO.cal_map_image(pyx, pcls, sc, MO.yxyx_from_xcycwh(t), tcls, oap, thr)
+    dev = "cuda"
+    rank, tp, gtc = CM._match(torch.from_numpy(boxes).to(dev), torch.from_numpy(labels).to(dev), torch.from_numpy(scores).to(dev),
+                              torch.from_numpy(count).to(dev), torch.from_numpy(tb).to(dev), torch.from_numpy(tc).to(dev), None, True, thr, ncls)
+    ev = CM.MapEvaluator([f"c{i}" for i in range(ncls)], with_mask_rows=False)
+    ev.batches.append((torch.from_numpy(labels), torch.from_numpy(scores), rank, tp, torch.from_numpy(count), torch.from_numpy(tb[:, 0, 0]),
+                       torch.from_numpy(tc[:, :, 0])))
+    ap = ev.ap_data()
+    for a in range(len(thr)):
+        for c in range(ncls):
+            o, m = oap[a][c], ap["box"][a][c]
+            assert o.num_gt_positives == m.num_gt_positives and len(o.data_points) == len(m.data_points)
+            assert sorted(o.data_points, key=lambda x: -x[0]) == sorted(((float(s), bool(f)) for s, f in m.data_points), key=lambda x: -x[0]), (a, c)
+            assert abs(o.get_ap() - m.get_ap()) < 1e-12
+    expect = MO.calc_map(oap, thr, ncls)
+    got = ev.summary()["box"]
+    assert list(got.values()) == list(expect.values())
+    expect_gt = np.zeros(ncls, np.int64)
+    for b in range(B):
+        expect_gt += np.bincount(tc[b, 1:1 + int(tb[b, 0, 0]), 0], minlength=ncls)
+    assert gtc.cpu().tolist() == expect_gt.tolist()
+
+
+def test_eval_model_runs_end_to_end(D, capsys):
+    """eval.py:30-61 through the engine: forward -> device post-process -> device matching -> summary dict with the reference's keys"""
+    from oracle import detr_oracle as O
+    from detr_tensorflow_b200.loss import compute_map as CM
+    P = O.init_params(seed=6, num_encoder_layers=1, num_decoder_layers=1)
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=1, num_decoder_layers=1)
+    img = torch.randn(2, 96, 128, 3, generator=torch.Generator().manual_seed(6))
+    tb, tc = O.synthetic_targets(2, n=4, seed=6)
+    maps = CM.eval_model(model, cfg, [f"c{i}" for i in range(92)], [(img, tb, tc)] * 2, print_result=True)
+    assert list(maps["box"].keys()) == ["all", 50, 55, 60, 65, 70, 75, 80, 85, 90, 95] and "mask" in maps
+    assert "box" in capsys.readouterr().out
