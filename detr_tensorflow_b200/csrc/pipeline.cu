@@ -262,6 +262,51 @@ map_match_kernel(const float *__restrict__ pred_boxes, const int64_t *__restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ resize / augmentation geometry
+// data/transformation.py:54-114 (detr_aug_seq: Fliplr, Resize / CropToFixedSize / Affine scale, final Resize to
+// config.image_size) collapses into ONE axis-aligned affine map per image; the host samples it and transforms the boxes, this
+// kernel resamples the pixels: B ragged uint8 source frames -> one [B, H, W, 3] uint8 batch, bilinear, one thread per output
+// pixel.  inv[b] = {ax, bx, ay, by}: source coordinates of the output pixel centre (x + .5, y + .5) are
+// xs = ax * (x + .5) + bx - .5, ys = ay * (y + .5) + by - .5 (pixel-centre convention of cv2.resize / imgaug).  Samples outside
+// the source frame read 0 (imgaug's constant fill) when zero_border, the nearest edge pixel otherwise (plain resize).
+// Explicit round-to-nearest arithmetic (no FMA contraction): the numpy restatement in oracle/ reproduces it bit for bit.
+__global__ void __launch_bounds__(256)
+resize_affine_u8_kernel(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_off, const int32_t *__restrict__ src_hw,
+                        const float *__restrict__ inv, const uint8_t *__restrict__ zero_border, uint8_t *__restrict__ out, int H, int W)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const int sh = src_hw[2 * b], sw = src_hw[2 * b + 1];
+    const uint8_t *img = src + src_off[b];
+    const float ax = inv[4 * b], bx = inv[4 * b + 1], ay = inv[4 * b + 2], by = inv[4 * b + 3];
+    const float xs = __fsub_rn(__fadd_rn(__fmul_rn(ax, (float)x + 0.5f), bx), 0.5f);
+    const float ys = __fsub_rn(__fadd_rn(__fmul_rn(ay, (float)y + 0.5f), by), 0.5f);
+    const float x0f = floorf(xs), y0f = floorf(ys);
+    const float fx = __fsub_rn(xs, x0f), fy = __fsub_rn(ys, y0f);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const bool zb = zero_border[b] != 0;
+    float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+            int xx = x0 + dx, yy = y0 + dy;
+            const float w = __fmul_rn(dx ? fx : __fsub_rn(1.f, fx), dy ? fy : __fsub_rn(1.f, fy));
+            bool inside = xx >= 0 && xx < sw && yy >= 0 && yy < sh;
+            if (!inside && zb) continue;
+            xx = min(max(xx, 0), sw - 1); yy = min(max(yy, 0), sh - 1);
+            const uint8_t *px = img + ((size_t)yy * sw + xx) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] = __fadd_rn(v[c], __fmul_rn(w, (float)px[c]));
+        }
+    uint8_t *o = out + (((size_t)b * H + y) * W + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) o[c] = (uint8_t)fminf(fmaxf(rintf(v[c]), 0.f), 255.f);
+}
+
 }  // namespace
 
 extern "C" int detrb_normalize_u8(const uint8_t *img, const float *lut, int swap_rb, float *out, int64_t npix, detrb_stream_t stream)
@@ -322,5 +367,16 @@ extern "C" int detrb_map_match(const float *pred_boxes, const int64_t *pred_labe
     DETRB_LAUNCH(map_match_kernel, dim3(B), dim3(32), 0, (cudaStream_t)stream, pred_boxes, pred_labels, pred_scores, pred_count, Q, t_boxes,
                  t_labels, t_count, NT, t_wire, thresholds, T, num_classes, rank, tp, gt_count);
     DETRB_CHECK_LAUNCH("map_match_kernel");
+    return DETRB_OK;
+}
+
+extern "C" int detrb_resize_affine_u8(const uint8_t *src, const int64_t *src_off, const int32_t *src_hw, const float *inv,
+                                      const uint8_t *zero_border, uint8_t *out, int B, int H, int W, detrb_stream_t stream)
+{
+    DETRB_REQUIRE(src && src_off && src_hw && inv && zero_border && out && B > 0 && H > 0 && W > 0, "detrb_resize_affine_u8: bad args");
+    DETRB_REQUIRE(H <= 65535 && B <= 65535, "detrb_resize_affine_u8: grid too large");
+    DETRB_LAUNCH(resize_affine_u8_kernel, dim3((unsigned)ceil_div(W, 256), (unsigned)H, (unsigned)B), dim3(256), 0, (cudaStream_t)stream,
+                 src, src_off, src_hw, inv, zero_border, out, H, W);
+    DETRB_CHECK_LAUNCH("resize_affine_u8_kernel");
     return DETRB_OK;
 }

@@ -230,3 +230,8 @@ def map_match(pred_boxes, pred_labels, pred_scores, pred_count, B, Q, t_boxes, t
     check(_lib.lib().detrb_map_match(ptr(pred_boxes), ptr(pred_labels), ptr(pred_scores), ptr(pred_count), c_int(B), c_int(Q), ptr(t_boxes),
                                      ptr(t_labels), ptr(t_count), c_int(NT), c_int(int(t_wire)), ptr(thresholds), c_int(T), c_int(num_classes),
                                      ptr(rank), ptr(tp), ptr(gt_count), _stream()))
+
+
+def resize_affine_u8(src, src_off, src_hw, inv, zero_border, out, B, H, W):
+    check(_lib.lib().detrb_resize_affine_u8(ptr(src), ptr(src_off), ptr(src_hw), ptr(inv), ptr(zero_border), ptr(out), c_int(B), c_int(H),
+                                            c_int(W), _stream()))

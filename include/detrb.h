@@ -342,6 +342,16 @@ int detrb_postprocess(const float *logits, int ldl, const float *boxes, int B, i
                       int bbox_format, float *out_boxes, int64_t *out_labels, float *out_scores, int32_t *out_query,
                       int32_t *out_count, detrb_stream_t stream);
 
+/* Input geometry on device (data/transformation.py:54-114, detr_aug_seq: Fliplr, Resize / CropToFixedSize / Affine scale and the
+ * final Resize to config.image_size collapse into one axis-aligned affine map per image, sampled on the host together with the box
+ * transform): B ragged uint8 RGB source frames -> one [B,H,W,3] uint8 batch, bilinear.
+ *   src: all frames in one DEVICE buffer, frame b = [src_hw[2b], src_hw[2b+1], 3] bytes at src + src_off[b]
+ *   inv [B,4] f32 = {ax, bx, ay, by}: source coordinates of output pixel centre (x+.5, y+.5): xs = ax*(x+.5) + bx - .5, ys likewise
+ *   zero_border [B] u8: samples outside the source read 0 (imgaug's constant fill) / the nearest edge pixel (plain resize)
+ * The result feeds the model as uint8 frames (normalisation fused into the stem's input layout: detrb_image_u8_to_s2d16). */
+int detrb_resize_affine_u8(const uint8_t *src, const int64_t *src_off, const int32_t *src_hw, const float *inv,
+                           const uint8_t *zero_border, uint8_t *out, int B, int H, int W, detrb_stream_t stream);
+
 /* mAP matching (loss/compute_map.py:183-272, cal_map 'box' entries; driven per image by eval.py:38-52) for B images in one launch.
  *   detections: pred_boxes [B,Q,4] f32 in yxyx corners, pred_labels [B,Q] i64, pred_scores [B,Q] f32, the first pred_count[b] rows of
  *   image b valid (= the outputs of detrb_postprocess with bbox_format 2).  Q <= 256.

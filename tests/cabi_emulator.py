@@ -690,6 +690,16 @@ class FakeLib:
         x = self._lut_apply(img, lut, swap, B * H * W).contiguous()
         return self.detrb_image_to_s2d16(ctypes.c_void_p(x.data_ptr()), out, B, H, W, pad_top, pad_left, HP, WP, split, stream)
 
+    def detrb_resize_affine_u8(self, src, src_off, src_hw, inv, zero_border, out, B, H, W, stream):
+        from oracle.resize_oracle import resize_affine_u8
+        B, H, W = _v(B), _v(H), _v(W)
+        off, hw = T(src_off, torch.int64, B).numpy(), T(src_hw, torch.int32, 2 * B).numpy()
+        frames = [T(ctypes.c_void_p(_addr(src) + int(off[b])), torch.uint8, int(hw[2 * b]) * int(hw[2 * b + 1]) * 3).view(int(hw[2 * b]), int(hw[2 * b + 1]), 3).numpy()
+                  for b in range(B)]
+        res = resize_affine_u8(frames, T(inv, F32, 4 * B).view(B, 4).numpy(), T(zero_border, torch.uint8, B).numpy(), H, W)
+        T(out, torch.uint8, B * H * W * 3)[:] = torch.from_numpy(res).reshape(-1)
+        return 0
+
     def detrb_postprocess(self, logits, ldl, boxes, B, Q, C, bg, fmt, out_boxes, out_labels, out_scores, out_query, out_count,
                           stream):
         B, Q, C, ldl, bg, fmt = _v(B), _v(Q), _v(C), _v(ldl), _v(bg), _v(fmt)

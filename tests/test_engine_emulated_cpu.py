@@ -507,6 +507,43 @@ def test_inference_postprocess_and_uint8_input_host_logic(emu):
     assert torch.equal(a, b)
 
 
+def test_detr_transform_host_logic(emu):
+    """data/transformation.py on the emulated ABI.  The product's vectorised box transform equals the oracle's
+    per-box restatement of transformation.py:11-34/117-142/178-186 for every geometry the sampler draws; the sampled maps keep
+    the output inside the source unless zero_border is set; detr_transform keeps the reference's return order and dtypes."""
+    import detr_tensorflow_b200 as D
+    from oracle.resize_oracle import resize_affine_u8, transform_boxes as o_boxes
+    cfg = D.TrainingConfig()
+    cfg.image_size = (40, 56)
+    rng = np.random.default_rng(3)
+    g = np.random.default_rng(5)
+    seen = set()
+    for it in range(200):
+        h, w = int(g.integers(20, 90)), int(g.integers(20, 90))
+        fwd, zb = D.data.sample_geometry((h, w), cfg, True, rng)
+        seen.add((fwd[0] < 0, zb))
+        n = int(g.integers(0, 6))
+        bb = np.concatenate([g.uniform(0.1, 0.9, (n, 2)), g.uniform(0.05, 0.6, (n, 2))], -1)
+        cc = g.integers(1, 91, n)
+        a, ac = D.data.transform_boxes(bb, cc, fwd, cfg.image_size, (h, w))
+        b, bc = o_boxes(bb, cc, fwd, cfg.image_size, (h, w))
+        assert np.array_equal(ac, bc) and a.shape == b.shape
+        np.testing.assert_allclose(a, b, atol=1e-12)
+        assert (a >= 0).all() and (a <= 1).all()
+        if not zb:                              # the output frame maps into the source frame
+            ax, bx, ay, by = D.data.transformation.inverse_map(fwd)
+            xs = sorted([bx, ax * cfg.image_size[1] + bx])
+            ys = sorted([by, ay * cfg.image_size[0] + by])
+            assert xs[0] > -1e-6 and xs[1] < w + 1e-6 and ys[0] > -1e-6 and ys[1] < h + 1e-6
+    assert len(seen) == 4                       # flips and zero-fill scalings both occur
+    img = g.integers(0, 256, (30, 44, 3), dtype=np.uint8)
+    out, nb, nc = D.data.detr_transform(img, np.array([[0.5, 0.5, 0.2, 0.2]]), np.array([7]), cfg, False, device="cpu")
+    assert out.dtype == torch.float32 and tuple(out.shape) == (40, 56, 3) and nc.tolist() == [7]
+    np.testing.assert_allclose(nb, [[0.5, 0.5, 0.2, 0.2]], atol=1e-12)          # plain resize keeps normalised boxes
+    ref = resize_affine_u8([img], np.array([[44 / 56, 0, 30 / 40, 0]], np.float32), [0], 40, 56)[0]
+    assert np.array_equal(out.numpy().astype(np.uint8), ref)
+
+
 def test_checkpoint_roundtrip_and_torch_detr_name_mapping(emu, tmp_path):
     """save/load of parameters + Adam state (resume), and the original-DETR state_dict mapping: a torchvision
     resnet50 (the module the original DETR wraps as backbone.0.body) and nn.MultiheadAttention / nn.Linear / nn.LayerNorm

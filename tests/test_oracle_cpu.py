@@ -318,3 +318,37 @@ def test_map_oracle_vs_reference_code_golden():
     maps = M.calc_map(ap, thr, ncls)
     assert [str(k) for k in maps.keys()] == g["box_map_keys"].tolist()
     np.testing.assert_allclose(list(maps.values()), g["box_map_values"], atol=1e-9)
+
+
+def test_oracle_resize_vs_torch_interpolate_and_box_geometry():
+    """SURVEY 8f N1 (transformation.py:54-114, 163-195).  imgaug is not installed: the bilinear pixel-centre convention of the
+    oracle's resampler is pinned against torch.nn.functional.interpolate(align_corners=False) (same convention as
+    cv2.INTER_LINEAR, float arithmetic) to +-1 grey level, up- and down-scaling; flips, crops and zero fill by construction."""
+    import torch
+    import torch.nn.functional as F
+    from oracle.resize_oracle import resize_affine_u8, transform_boxes
+    rng = np.random.default_rng(0)
+    for (h, w, H, W) in ((37, 53, 64, 80), (120, 90, 48, 64), (33, 47, 33, 47)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        out = resize_affine_u8([img], np.array([[w / W, 0.0, h / H, 0.0]], np.float32), [0], H, W)[0]
+        ref = F.interpolate(torch.from_numpy(img).permute(2, 0, 1)[None].float(), size=(H, W), mode="bilinear", align_corners=False)
+        ref = ref[0].permute(1, 2, 0).round().clamp(0, 255).numpy()
+        assert np.abs(out.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+        if (h, w) == (H, W):
+            assert np.array_equal(out, img)                                                 # identity map: exact
+    img = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    flip = resize_affine_u8([img], np.array([[-1.0, 30.0, 1.0, 0.0]], np.float32), [0], 20, 30)[0]
+    assert np.array_equal(flip, img[:, ::-1])                                               # Fliplr
+    crop = resize_affine_u8([img], np.array([[1.0, 5.0, 1.0, 3.0]], np.float32), [0], 10, 12)[0]
+    assert np.array_equal(crop, img[3:13, 5:17])                                            # CropToFixedSize at offset (5, 3)
+    small = resize_affine_u8([img], np.array([[2.0, -15.0, 2.0, -10.0]], np.float32), [1], 20, 30)[0]
+    assert small[0, 0].sum() == 0 and small[19, 29].sum() == 0 and small[10, 15].sum() > 0   # Affine scale 0.5: zero fill around
+    # boxes: flip + scale, the 0.7 out-of-image rule, clipping
+    bb = np.array([[0.25, 0.5, 0.2, 0.4], [0.95, 0.5, 0.4, 0.2], [0.995, 0.5, 0.2, 0.2]])
+    nb, nc = transform_boxes(bb, np.array([3, 4, 5]), (-2.0, 200.0, 2.0, 0.0), (100, 200), (50, 100))
+    np.testing.assert_allclose(nb[0], [0.75, 0.5, 0.2, 0.4], atol=1e-12)
+    assert list(nc) == [3, 4, 5]
+    nb, nc = transform_boxes(bb, np.array([3, 4, 5]), (2.0, 0.0, 2.0, 0.0), (100, 150), (50, 100))     # right part cut off
+    assert list(nc) == [3] and nb.shape == (1, 4)                                                      # both others >= 70 % outside
+    nb, nc = transform_boxes(bb[1:2], np.array([4]), (1.0, 0.0, 1.0, 0.0), (50, 100), (50, 100))       # 37.5 % outside: kept, clipped
+    np.testing.assert_allclose(nb[0], [0.875, 0.5, 0.25, 0.2], atol=1e-12)

@@ -208,3 +208,45 @@ def test_eval_model_runs_end_to_end(D, capsys):
     maps = CM.eval_model(model, cfg, [f"c{i}" for i in range(92)], [(img, tb, tc)] * 2, print_result=True)
     assert list(maps["box"].keys()) == ["all", 50, 55, 60, 65, 70, 75, 80, 85, 90, 95] and "mask" in maps
     assert "box" in capsys.readouterr().out
+
+
+def test_resize_affine_kernel_bit_exact_vs_oracle(D):
+    """resize_affine_u8_kernel (transformation.py:54-114 as one affine map per image) against the numpy oracle,
+    bit for bit: ragged batch, flips, crops, zero-filled down-scaling, up- and down-sampling; then the benchmark geometry
+    (8 frames of ~480x640 -> 800x1333) and detr_transform_batch end to end into the model's uint8 input."""
+    from oracle.resize_oracle import resize_affine_u8
+    g = np.random.default_rng(11)
+    frames = [g.integers(0, 256, (int(g.integers(17, 120)), int(g.integers(17, 120)), 3), dtype=np.uint8) for _ in range(7)]
+    H, W = 61, 83
+    fwds, zbs = [], []
+    for i, f in enumerate(frames):
+        h, w = f.shape[:2]
+        fx, fy = W / w * g.uniform(0.5, 1.5), H / h * g.uniform(0.5, 1.5)
+        if i % 2:
+            fwds.append((-fx, W - g.uniform(-5, 5), fy, g.uniform(-5, 5)))
+        else:
+            fwds.append((fx, g.uniform(-5, 5), fy, g.uniform(-5, 5)))
+        zbs.append(i % 3 == 0)
+    out = D.data.resample_batch(frames, fwds, zbs, (H, W)).cpu().numpy()
+    inv = np.array([D.data.transformation.inverse_map(f) for f in fwds], np.float32)
+    ref = resize_affine_u8(frames, inv, zbs, H, W)
+    assert np.array_equal(out, ref)
+    # identity and flip are exact copies
+    same = D.data.resample_batch(frames[:1], [(1.0, 0.0, 1.0, 0.0)], [False], frames[0].shape[:2]).cpu().numpy()[0]
+    assert np.array_equal(same, frames[0])
+    w0 = frames[0].shape[1]
+    flip = D.data.resample_batch(frames[:1], [(-1.0, float(w0), 1.0, 0.0)], [False], frames[0].shape[:2]).cpu().numpy()[0]
+    assert np.array_equal(flip, frames[0][:, ::-1])
+    # benchmark geometry, through the public function; one image checked against the oracle
+    cfg = D.TrainingConfig()
+    cfg.image_size = (800, 1333)
+    big = [g.integers(0, 256, (480 + 8 * i, 640 - 8 * i, 3), dtype=np.uint8) for i in range(8)]
+    boxes = [np.array([[0.5, 0.5, 0.3, 0.3], [0.2, 0.7, 0.1, 0.2]]) for _ in big]
+    cls = [np.array([1, 2]) for _ in big]
+    batch, nb, nc = D.data.detr_transform_batch(big, boxes, cls, cfg, False)
+    assert batch.dtype == torch.uint8 and tuple(batch.shape) == (8, 800, 1333, 3) and batch.is_cuda
+    ref3 = resize_affine_u8([big[3]], np.array([[big[3].shape[1] / 1333, 0, big[3].shape[0] / 800, 0]], np.float32), [0], 800, 1333)[0]
+    assert np.array_equal(batch[3].cpu().numpy(), ref3)
+    np.testing.assert_allclose(nb[3], boxes[3], atol=1e-12)
+    aug, _, _ = D.data.detr_transform_batch(big, boxes, cls, cfg, True, rng=np.random.default_rng(1))
+    assert tuple(aug.shape) == (8, 800, 1333, 3)
