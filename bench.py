@@ -421,7 +421,8 @@ def main():
     if world > 1:                                                       # every rank needs the same probe set; clocks only exist on rank 0
         peak_tf, peak_tf_src = peak_sus, f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})"
     p_t, p_h = "backbone/layer3/1/conv2", "backbone/layer1/1/conv3"     # 3x3 256->256 @50x84 | 1x1 64->256 + residual + ReLU @200x334
-    eng.probe_names = (p_t, p_h, p_t + "#wgrad", p_h + "#wgrad", p_h + "#dgrad", "e2_attn#fwd", "e2_attn#bwd")
+    p_c = "backbone/layer1/1/conv2"                                     # 3x3 64->64 @200x334 (halo-reusing row kernel)
+    eng.probe_names = (p_t, p_h, p_c, p_c + "#dgrad", p_t + "#wgrad", p_h + "#wgrad", p_h + "#dgrad", "e2_attn#fwd", "e2_attn#bwd")
     eng.probe_events = {}
     for _ in range(3):
         eng.train_step(91, cfg.gradient_norm_clipping)
@@ -453,9 +454,11 @@ def main():
         S = eng.S
         # algorithmic bytes (bf16): forward = input + weights + residual + output; data gradient = dY + weights
         # + ReLU mask + output; weight gradient = input + dY (+ the fp32 gradient tile, negligible)
-        roof = hbm_obj(f"gemm_tc_kernel<64,1> one-tile tcgen05 GEMM: 1x1 conv 64->256 + residual + ReLU, layer1, M={Mh} N=256 K=64",
-                       2.0 * (Mh * sh.K + sh.N * sh.K + 2 * Mh * sh.N), med(p_h), traffic("hbm_kernel_traffic.json"))
-        roof["family"] = "one-tile tcgen05 GEMM / conv (gemm_tc_kernel): the largest share of the step by time (see profiles/: ncu launch list of this round)"
+        # (+ M*N/8 bytes of 1-bit ReLU mask written by the forward, read by the data gradient instead of the bf16 activation)
+        roof = hbm_obj(f"gemm_stream_kernel<256,residual,bits-out> streaming tcgen05 GEMM (weights resident in smem, in-place chunk slots): "
+                       f"1x1 conv 64->256 + residual + ReLU, layer1, M={Mh} N=256 K=64",
+                       2.0 * (Mh * sh.K + sh.N * sh.K + 2 * Mh * sh.N) + Mh * sh.N / 8, med(p_h), traffic("hbm_kernel_traffic.json"))
+        roof["family"] = "HBM-bound 1x1 convolutions of layer1-3 (gemm_stream_kernel): the largest share of the step by time (see profiles/: ncu launch list of this round)"
         roof["whole_step"] = {"achieved": gf * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
                               "frac_of_tensor_peak": gf * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf, "peak": peak_tf, "peak_source": peak_tf_src}
         roofs = {
@@ -465,8 +468,13 @@ def main():
                                         2.0 * Mt * st.N * st.K, med(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
             "wgrad_conv1x1_layer1": hbm_obj(f"wgrad_tc_kernel<plain> weight gradient of the layer1 1x1 conv 64->256 (side stream), M={Mh}",
                                             2.0 * (Mh * sh.K + Mh * sh.N), med(p_h + "#wgrad")),
-            "dgrad_conv1x1_layer1": hbm_obj(f"gemm_tc_kernel one-tile: data gradient of the layer1 1x1 conv 256->64 + ReLU mask, M={Mh}",
-                                            2.0 * (Mh * sh.N + sh.N * sh.K + 2 * Mh * sh.K), med(p_h + "#dgrad")),
+            "dgrad_conv1x1_layer1": hbm_obj(f"gemm_stream_kernel<64,bits-in>: data gradient of the layer1 1x1 conv 256->64 + 1-bit ReLU mask, M={Mh}",
+                                            2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8, med(p_h + "#dgrad")),
+            "conv3x3_layer1_halo": dict(tensor_obj(f"conv3x3_halo_kernel: 3x3 conv 64->64 + ReLU, layer1 (every input row staged once, nine taps = nine "
+                                                   f"descriptor views), M={Mh} N=64 K=576", 2.0 * Mh * 64 * 576, med(p_c)),
+                                        hbm_gbs=(2.0 * 2 * Mh * 64 + Mh * 8) / med(p_c) / 1e9),
+            "dgrad_conv3x3_layer1_halo": tensor_obj(f"conv3x3_halo_kernel: data gradient of the same conv (+ 1-bit ReLU mask), M={Mh}",
+                                                    2.0 * Mh * 64 * 576, med(p_c + "#dgrad")),
             "attention_fwd": tensor_obj(f"encoder self-attention forward, B={B} H=8 S={S} dh=32 (QK^T + PV flops; {B * 8 * S * S / 1e6:.1f} M exponentials)",
                                         4.0 * B * 8 * S * S * 32, med("e2_attn#fwd")),
             "attention_bwd": tensor_obj(f"encoder self-attention backward (delta + dK/dV + dQ kernels), B={B} H=8 S={S} dh=32",

@@ -15,9 +15,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 # DETRB_SO: developer override (e.g. a -DDETRB_TRACE build next to the production library)
 _SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
-_SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu", "pipeline.cu", "attention_tc.cu"]
+_SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_probe.cu", "wgrad_tc.cu", "pipeline.cu", "attention_tc.cu", "conv_halo.cu"]
 _lib = None
-ABI_VERSION = 200          # detrb_version() of the library these ctypes structures / call sites were written for
+ABI_VERSION = 210          # detrb_version() of the library these ctypes structures / call sites were written for
 
 EXPORTS = [
     "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
@@ -25,7 +25,7 @@ EXPORTS = [
     "detrb_image_to_nhwc4", "detrb_image_to_s2d16", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
     "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",
     "detrb_set_tc", "detrb_set_tc_conv", "detrb_set_tc_tma_epilogue", "detrb_set_tc_persistent", "detrb_gemm_tc_force", "detrb_tma_im2col_probe", "detrb_prep_weights_multi", "detrb_adam_clipnorm_chunked", "detrb_set_tc_wgrad", "detrb_wgrad_tc_force",
-    "detrb_attn_dropout_mask", "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess", "detrb_accumulate", "detrb_set_tc_attn", "detrb_map_match", "detrb_resize_affine_u8",
+    "detrb_attn_dropout_mask", "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess", "detrb_accumulate", "detrb_set_tc_attn", "detrb_map_match", "detrb_resize_affine_u8", "detrb_set_tc_stream", "detrb_set_tc_halo",
 ]
 
 
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + os.environ.get("DETRB_NVCC_FLAGS", "").split() + srcs
+           "-t", str(min(8, os.cpu_count() or 1)), "-Xcompiler", "-fPIC", "-shared", "-o", _SO] + os.environ.get("DETRB_NVCC_FLAGS", "").split() + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
@@ -58,7 +58,7 @@ class IgemmParams(Structure):
         ("mask_scale", c_float), ("relu", c_int), ("sigmoid", c_int), ("drop_p", c_float), ("seed", c_uint64),
         ("site", c_uint32), ("seed_ptr", c_void_p), ("C", c_void_p), ("ldc", c_int), ("Cf", c_void_p), ("ldcf", c_int),
         ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int), ("a_kb_rows", c_int),
-        ("split", c_int64), ("wsplit", c_int64),
+        ("split", c_int64), ("wsplit", c_int64), ("mask_bits", c_void_p), ("ldmb", c_int), ("out_bits", c_void_p), ("ldob", c_int),
     ]
 
 

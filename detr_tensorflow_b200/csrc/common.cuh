@@ -25,6 +25,9 @@ bool detrb_gemm_tc_enabled();
 bool detrb_gemm_tc_conv_enabled();
 int detrb_gemm_tc_kind(const detrb_igemm_t &p);
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
+// conv_halo.cu (3x3 / 64-channel convolution, every input pixel staged once)
+bool detrb_conv_halo_supported(const detrb_igemm_t &p);
+int detrb_conv_halo(const detrb_igemm_t &p, cudaStream_t stream);
 // wgrad_tc.cu
 bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p);
 bool detrb_wgrad_tc_enabled();

@@ -16,6 +16,7 @@
 // k-loops of the HBM-bound layers are 1..4 blocks long.  gemm_tcp_kernel (further down): persistent, one CTA per SM, 128x256
 // tiles, for the tensor-bound shapes.  dispatch_tc / dispatch_tcp hold the measured policy.
 #include "tc_common.cuh"
+#include <type_traits>
 
 #ifdef DETRB_TRACE
 // developer build (-DDETRB_TRACE): per-phase cycle sums of the one-tile kernel's CTA life, read back by detrb_trace_read
@@ -29,34 +30,7 @@ __device__ unsigned long long g_trace[16];
 
 namespace {
 
-constexpr int TBM = 128;
-constexpr int TBK = 64;                 // 64 bf16 = 128 B = one swizzle row
 constexpr int NTHREADS_TC = 192;
-
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row core groups 1024 B apart (SBO), LBO unused (=1),
-// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                                  // version
-    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
-    return d;
-}
-// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
-// N>>3 at bits [17,23), M>>4 at bits [24,29)   (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// v[0..8) += 8 consecutive floats of the bias row staged in shared memory (all lanes read the same address: broadcast)
-__device__ __forceinline__ void add_bias8(float (&v)[8], uint32_t saddr) {
-    float4 b0, b1;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(saddr));
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(saddr + 16u));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-}
 
 // convolution side-band for the IM2COL kernels: effective padding and, per im2col tap, the weight tap to pair it with
 // (identity: forward; reversed: stride-1 data gradient; sparse: one parity class of a stride-2 data gradient)
@@ -219,13 +193,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+        uint2 mb0 = make_uint2(0u, 0u), mb1 = make_uint2(0u, 0u);   // this row's mask bits of the tile's (at most two) 64-column chunks
+        if (tma_epi && p.mask_bits && row_ok) {              // in flight during the main loop
+            const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
+            mb0 = ld_bits8(mp);
+            if (L::NCH > 1 && nch > 1) mb1 = ld_bits8(mp + 8);
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const long long t_tf = TRACE_NOW();
         if (leader) TRACE_ADD(4, t_tf - t_pdl);              // pdl -> accumulator complete
-        const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < p.M;
         size_t orow = m;
         if (row_ok && p.out_stride > 1) {
             const int ohw = p.OH * p.OW;
@@ -259,10 +239,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (r_late || p.mask) mbar_wait(late_bar, 0);
             const long long t_in = TRACE_NOW();
             if (leader) TRACE_ADD(5, t_in - t_tf);            // accumulator complete -> residual / mask tiles landed
+            // the bit-mask code is compiled into its own copy of the chunk loop: the common (bit-free) path keeps its instruction
+            // count and registers (the extra flag tests inside the 8-column groups cost the BN = 128 kernel 40 % on layer3)
+            auto chunks = [&](auto bits_tag) {
+            constexpr bool BITS = decltype(bits_tag)::value;
 #pragma unroll 1
             for (int cb = 0; cb < nch; cb++) {
                 const int nb = n0 + cb * 64;
                 const uint32_t cboff = (uint32_t)cb * 16384u;
+                const uint2 mbc = cb == 0 ? mb0 : mb1;
+                uint2 ob = make_uint2(0u, 0u);
 #pragma unroll
                 for (int c32 = 0; c32 < 2; c32++) {
                     uint32_t r[32];                            // two TMEM loads in flight per wait
@@ -305,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
                         }
+                        if (BITS && p.mask_bits) apply_bits8(v, mbc, (int)chunk, p.mask_scale);
                         if (p.sigmoid) {
 #pragma unroll
                             for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
@@ -318,12 +305,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 v[i + 1] = (k1 ? v[i + 1] * drop_scale : 0.f) + res[i + 1];
                             }
                         }
+                        if (BITS && p.out_bits) collect_bits8(v, ob, (int)chunk);
                         uint4 o;
                         o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(bufO + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                 }
+                if (BITS && p.out_bits && row_ok) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
             }
+            };
+            if (p.mask_bits || p.out_bits) chunks(std::true_type{}); else chunks(std::false_type{});
             const long long t_math = TRACE_NOW();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy writes -> visible to TMA
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -376,6 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
                 }
+                if (p.mask_bits) apply_bits8(v, make_uint2((uint32_t)p.mask_bits[orow * p.ldmb + (n >> 3)], 0u), 0, p.mask_scale);
                 if (p.sigmoid) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
@@ -398,6 +390,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int i = 0; i < 8; i++) v[i] += old[i];
                     }
                     sp_st8(dst, split, v);
+                }
+                if (p.out_bits) {
+                    uint2 ob = make_uint2(0u, 0u);
+                    collect_bits8(v, ob, 0);
+                    p.out_bits[orow * p.ldob + (n >> 3)] = (uint8_t)ob.x;
                 }
                 if (p.Cf) {
                     float4 *dst = reinterpret_cast<float4 *>(p.Cf + orow * p.ldcf + n);
@@ -450,15 +447,10 @@ struct PLayout {
     static_assert(RING_BYTES >= 0, "persistent GEMM: stages do not fit");
 };
 
-__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
-    float2 t;
-    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y; t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y; t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
-}
 // fused epilogue arithmetic on 8 consecutive columns n..n+7 of row m (same order as igemm.cu)
 __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], const float (&mk)[8], bool has_mask,
                                           const detrb_igemm_t &p, int m, int n, uint64_t seed, uint32_t thresh, float drop_scale,
-                                          uint32_t sbias8)
+                                          uint32_t sbias8, const uint2 &mbits, int c)
 {
     if (p.bias) add_bias8(v, sbias8);
     if (!(p.drop_p > 0.f)) {
@@ -473,6 +465,7 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], 
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
     }
+    if (p.mask_bits) apply_bits8(v, mbits, c, p.mask_scale);
     if (p.sigmoid) {
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
@@ -486,6 +479,20 @@ __device__ __forceinline__ void epi_math8(float (&v)[8], const float (&res)[8], 
             v[i + 1] = (k1 ? v[i + 1] * drop_scale : 0.f) + res[i + 1];
         }
     }
+}
+// this row's mask bits of tile `tile` (NCH chunks of 8 bytes), zero past the edges
+template <int NCH>
+__device__ __forceinline__ void load_tile_bits(uint2 (&b)[NCH], const detrb_igemm_t &p, int tile, int n_tiles, int n_tiles_n, int row)
+{
+#pragma unroll
+    for (int i = 0; i < NCH; i++) b[i] = make_uint2(0u, 0u);
+    if (tile >= n_tiles) return;
+    const int m = (tile / n_tiles_n) * TBM + row, n0 = (tile % n_tiles_n) * (NCH * 64);
+    if (m >= p.M) return;
+    const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
+#pragma unroll
+    for (int i = 0; i < NCH; i++)
+        if (n0 + i * 64 < p.N) b[i] = ld_bits8(mp + 8 * i);
 }
 
 // OB = 2: two output staging tiles per warpgroup -- the TMA store of chunk i drains while chunk i+1 is computed.  Measured on the
@@ -627,10 +634,18 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
         int it = 0, g = 0;
+        const bool fast = !has_m && !p.sigmoid && !(p.drop_p > 0.f) && p.N % 64 == 0;
+        uint2 mb_cur[L::NCH], mb_nxt[L::NCH];                   // 1-bit mask of this row: current tile, next tile (prefetched)
+        if (p.mask_bits) load_tile_bits<L::NCH>(mb_nxt, p, blockIdx.x, n_tiles, n_tiles_n, row);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int m0 = (tile / n_tiles_n) * TBM, n0 = (tile % n_tiles_n) * BN;
             const int acc = it % NACC;
             const int m = m0 + row;
+            if (p.mask_bits) {
+#pragma unroll
+                for (int i = 0; i < L::NCH; i++) mb_cur[i] = mb_nxt[i];
+                load_tile_bits<L::NCH>(mb_nxt, p, tile + (int)gridDim.x, n_tiles, n_tiles_n, row);
+            }
             const int left = (p.N - n0 + 63) / 64, nch = left < L::NCH ? left : L::NCH;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             // every epilogue warp observes tmem_full before it arrives on tmem_empty below -- also a warpgroup without a chunk
@@ -649,9 +664,9 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     rbuf = smem_base + L::RING + (uint32_t)slot * slot_bytes;
                     mbuf = rbuf + (has_r ? 16384u : 0u);
                 }
-                if (p.bias && q < 2) {                          // this chunk's 64 bias values -> smem (visible after the barrier below)
+                if ((p.bias || fast) && q < 2) {                // this chunk's 64 bias values -> smem (visible after the barrier below)
                     const int t = q * 32 + lane;
-                    const float b = (nb + t < p.N) ? p.bias[nb + t] : 0.f;
+                    const float b = (p.bias && nb + t < p.N) ? p.bias[nb + t] : 0.f;
                     asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
                 }
                 // the TMA store that last read this staging tile (OB chunks ago) must have finished reading it
@@ -662,6 +677,29 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+                uint2 mbc = make_uint2(0u, 0u), ob = make_uint2(0u, 0u);
+                if (p.mask_bits) {
+                    mbc = mb_cur[0];
+#pragma unroll
+                    for (int i = 1; i < L::NCH; i++) if (cb == i) mbc = mb_cur[i];
+                }
+                if (fast) {                                     // bias / residual / ReLU / bit masks only: the straight-line chunk
+                    uint32_t acc_r[64];
+                    tc_ld64(t_addr + (uint32_t)(cb * 64), acc_r);
+                    uint4 rr[8];
+                    if (has_r) lds_row8(rr, rbuf + row_off, sw);
+                    tc_wait_ld();
+                    const bool relu = p.relu != 0;
+                    if (has_r) {
+                        if (p.mask_bits) epi_chunk_math<true, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, obuf + row_off, sw);
+                        else if (p.out_bits) epi_chunk_math<true, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                        else epi_chunk_math<true, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                    } else {
+                        if (p.mask_bits) epi_chunk_math<false, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, obuf + row_off, sw);
+                        else if (p.out_bits) epi_chunk_math<false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                        else epi_chunk_math<false, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                    }
+                } else
 #pragma unroll
                 for (int c32 = 0; c32 < 2; c32++) {
                     uint32_t r[32];                            // two TMEM loads in flight per wait
@@ -685,12 +723,14 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(mbuf + soff));
                             unpack8(u, mk);
                         }
-                        if (n < p.N) epi_math8(v, res, mk, has_m, p, m, n, seed, thresh, drop_scale, sbias + 4u * (uint32_t)(n - nb));
+                        if (n < p.N) epi_math8(v, res, mk, has_m, p, m, n, seed, thresh, drop_scale, sbias + 4u * (uint32_t)(n - nb), mbc, c32 * 4 + hf);
+                        if (p.out_bits) collect_bits8(v, ob, c32 * 4 + hf);
                         uint4 o;
                         o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(obuf + soff), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
                 }
+                if (p.out_bits && m < p.M) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
                 if (leader) {
@@ -712,6 +752,221 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)L::TMEM_COLS) : "memory");
+    }
+}
+
+// ================================================================================================ streaming variant
+// The HBM-bound 1x1 layers of layer1 / layer2 (M = 133600 .. 534400 rows, K and N in 64 .. 512): 2-8 flops per byte, the job is
+// to keep the memory system full.  One persistent CTA per SM owns a fixed column range of BN <= 256 columns and streams 128-row
+// tiles of A through it:
+//   * the WEIGHTS of the column range are loaded once and stay in shared memory (<= 64 KB) -- the other kernels re-fetch them per tile;
+//   * a ring of `nst` 16 KB A stages runs ahead across tile boundaries (two or more tiles in flight);
+//   * a ring of `rs` [128 x 64] slots carries each output chunk through its whole life IN PLACE: residual tile in by TMA (warp 3) ->
+//     fused epilogue overwrites it -> TMA store from the same slot -> released when the store has read it (one chunk later, so the
+//     epilogue warps never wait for a store); without a residual the slots are plain output staging;
+//   * ReLU masks arrive as bits in registers, prefetched one tile ahead (no mask tiles in shared memory at all).
+// warp 0: A (+W) producer, warp 1: MMA issuer (NACC accumulators rotate through TMEM), warp 2: TMEM allocator, warp 3: residual
+// producer, warps 4-11: two epilogue warpgroups alternating over the 64-column chunks.
+constexpr int ST_BAR_BYTES = 2048;                       // 512 B of barriers, up to 256 bias floats
+constexpr int ST_MAX_NST = 12, ST_MAX_RS = 10;
+
+template <int BN, bool HAS_R, bool MBITS, bool OBITS>
+__global__ void __launch_bounds__(NTHREADS_P, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r, const detrb_igemm_t p,
+                   const int n_parts, const int m_tiles, const int nst, const int rs, const int diag)
+{
+    // diag (developer switch DETRB_STREAM_DIAG, wrong results, timing only): 1 no TMA stores, 2 no epilogue arithmetic, 4 no tcgen05.ld
+    constexpr int NCH = BN / 64;
+    constexpr int NACC = BN == 256 ? 2 : 4;
+    constexpr int TMEM_COLS = NACC * BN;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int nk = p.K / TBK;
+    const uint32_t w_bytes = (uint32_t)(BN * TBK * 2) * (uint32_t)nk;
+    const uint32_t a_base = smem_base + w_bytes, r_base = a_base + (uint32_t)nst * 16384u;
+    const uint32_t bar_base = smem_base + (uint32_t)(227 * 1024 - 1024 - ST_BAR_BYTES);
+    auto a_full = [&](int s) { return bar_base + 8u * s; };
+    auto a_empty = [&](int s) { return bar_base + 8u * (ST_MAX_NST + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (2 * ST_MAX_NST + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * ST_MAX_NST + 4 + a); };
+    auto slot_full = [&](int i) { return bar_base + 8u * (2 * ST_MAX_NST + 8 + i); };
+    auto slot_free = [&](int i) { return bar_base + 8u * (2 * ST_MAX_NST + 8 + ST_MAX_RS + i); };
+    const uint32_t w_full = bar_base + 8u * (2 * ST_MAX_NST + 8 + 2 * ST_MAX_RS);
+    const uint32_t tmem_slot = w_full + 8u;
+    const uint32_t sbias = bar_base + 512u;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool has_r = HAS_R;
+    const int part = blockIdx.x % n_parts, first_tile = blockIdx.x / n_parts, tile_step = gridDim.x / n_parts;
+    const int n0 = part * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_c);
+        if (has_r) tma_prefetch_desc(&map_r);
+        for (int s = 0; s < nst; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int a = 0; a < NACC; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 8); }
+        for (int i = 0; i < rs; i++) { mbar_init(slot_full(i), 1); mbar_init(slot_free(i), 1); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== weights once, then the A stream =====================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, w_bytes);
+            for (int kb = 0; kb < nk; kb++) tma_load_2d(smem_base + (uint32_t)kb * (uint32_t)(BN * 128), &map_b, w_full, kb * TBK, n0);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = first_tile; t < m_tiles; t += tile_step) {
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(a_empty(stage), phase ^ 1);
+                    mbar_expect_tx(a_full(stage), 16384u);
+                    // sliding-window A (the space-to-depth stem): k-block kb is the 64-element run a_kb_rows rows further down
+                    tma_load_2d(a_base + (uint32_t)stage * 16384u, &map_a, a_full(stage), p.a_kb_rows ? 0 : kb * TBK,
+                                t * TBM + kb * p.a_kb_rows);
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TBM, BN);
+            mbar_wait(w_full, 0);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int t = first_tile; t < m_tiles; t += tile_step, it++) {
+                const int acc = it % NACC;
+                mbar_wait(tmem_empty(acc), ((it / NACC) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(a_full(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc(a_base + (uint32_t)stage * 16384u);
+                    const uint64_t db = make_smem_desc(smem_base + (uint32_t)kb * (uint32_t)(BN * 128));
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; k++)
+                        tc_mma_f16(d_addr, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    tc_commit(a_empty(stage));
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full(acc));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== residual producer: chunk g -> slot g % rs =====================
+        if (lane == 0 && has_r) {
+            int g = 0;
+            for (int t = first_tile; t < m_tiles; t += tile_step) {
+                for (int cb = 0; cb < NCH; cb++, g++) {
+                    const int slot = g % rs;
+                    mbar_wait(slot_free(slot), ((g / rs) & 1) ^ 1);
+                    mbar_expect_tx(slot_full(slot), 16384u);
+                    tma_load_2d(r_base + (uint32_t)slot * 16384u, &map_r, slot_full(slot), n0 + cb * 64, t * TBM);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue: chunk g goes to warpgroup g % 2 =====================
+        const int wg = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const bool leader = (q == 0 && lane == 0);
+        // the CTA's column range is fixed: its bias values (zeros without a bias) go to shared memory once
+        for (int t = threadIdx.x - 128; t < BN; t += 256)
+            asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * (uint32_t)t), "f"(p.bias ? p.bias[n0 + t] : 0.f) : "memory");
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        const bool relu = p.relu != 0;
+        const float mscale = p.mask_scale;
+        uint2 mb_cur[NCH], mb_nxt[NCH];
+        auto load_bits = [&](uint2 (&b)[NCH], int t) {
+#pragma unroll
+            for (int i = 0; i < NCH; i++) b[i] = make_uint2(0u, 0u);
+            const int m = t * TBM + row;
+            if (t >= m_tiles || m >= p.M) return;
+            const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
+#pragma unroll
+            for (int i = 0; i < NCH; i++) b[i] = ld_bits8(mp + 8 * i);
+        };
+        if (MBITS) load_bits(mb_nxt, first_tile);
+        int it = 0, g = 0, prev_slot = -1;
+        for (int t = first_tile; t < m_tiles; t += tile_step, it++) {
+            const int m0 = t * TBM, m = m0 + row;
+            const int acc = it % NACC;
+            if (MBITS) {
+#pragma unroll
+                for (int i = 0; i < NCH; i++) mb_cur[i] = mb_nxt[i];
+                load_bits(mb_nxt, t + tile_step);
+            }
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            mbar_wait(tmem_full(acc), (it / NACC) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < NCH; cb++, g++) {
+                if ((g & 1) != wg) continue;
+                const int nb = n0 + cb * 64;
+                const int slot = g % rs;
+                const uint32_t sbuf = r_base + (uint32_t)slot * 16384u;
+                // the whole chunk is straight-line code (no data-dependent or flag branches): every shared-memory and tensor-memory
+                // load of the chunk is in flight before the first use -- with branches between the 8-column groups each group was a
+                // serial load -> use chain at loaded shared-memory latency, and the epilogue, not HBM, set the pace (170 vs 102 us)
+                uint32_t acc_r[64];
+                tc_ld64(t_addr + (uint32_t)(cb * 64), acc_r);
+                if (has_r) mbar_wait(slot_full(slot), (g / rs) & 1);           // residual tile landed
+                else mbar_wait(slot_free(slot), ((g / rs) & 1) ^ 1);           // the store that last used this slot has read it
+                uint4 rr[8];
+                if (HAS_R) lds_row8(rr, sbuf + row_off, sw);
+                uint2 mbc = make_uint2(0u, 0u), ob = make_uint2(0u, 0u);
+                if (MBITS) {
+                    mbc = mb_cur[0];
+#pragma unroll
+                    for (int i = 1; i < NCH; i++) if (cb == i) mbc = mb_cur[i];
+                }
+                tc_wait_ld();
+                if (!(diag & 2)) epi_chunk_math<HAS_R, MBITS, OBITS>(acc_r, rr, sbias + 4u * (uint32_t)(cb * 64), relu, mbc, mscale, ob, sbuf + row_off, sw);
+                if (OBITS && m < p.M) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+                if (leader) {
+                    if (!(diag & 1))
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     :: "l"(&map_c), "r"(sbuf), "r"(nb), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (prev_slot >= 0) {                     // the previous chunk's store has read its slot by now (or we wait for it)
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        mbar_arrive(slot_free(prev_slot));
+                    }
+                    prev_slot = slot;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(acc));
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -867,7 +1122,92 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
     }
 }
 
+// streaming kernel: plain GEMM, bf16 TMA output, weights of one column range resident in shared memory
+static int g_tc_stream = 1;          // 0 off, 1 auto (stream_pick), 2 wherever supported (tests)      (env DETRB_STREAM)
+static int g_stream_nst = 0, g_stream_rs = 0;      // overrides (env DETRB_STREAM_NST / DETRB_STREAM_RS), 0 = policy
+static int g_stream_diag = 0, g_stream_bn = 0;     // developer switches (env DETRB_STREAM_DIAG / DETRB_STREAM_BN)
+
+// column width per CTA (0: not a streaming shape)
+int stream_pick(const detrb_igemm_t &p)
+{
+    static bool env_read = false;
+    if (!env_read) {
+        env_read = true;
+        if (const char *e = getenv("DETRB_STREAM")) g_tc_stream = atoi(e);
+        if (const char *e = getenv("DETRB_STREAM_NST")) g_stream_nst = atoi(e);
+        if (const char *e = getenv("DETRB_STREAM_RS")) g_stream_rs = atoi(e);
+        if (const char *e = getenv("DETRB_STREAM_DIAG")) g_stream_diag = atoi(e);
+        if (const char *e = getenv("DETRB_STREAM_BN")) g_stream_bn = atoi(e);
+    }
+    if (!g_tc_stream || p.split || p.mask || !p.C || p.Cf || p.out_stride > 1 || p.accumulate || !g_tma_epilogue) return 0;
+    if (p.sigmoid || p.drop_p > 0.f || (p.mask_bits && p.out_bits)) return 0;           // backbone epilogues only: bias, residual, ReLU, bit masks
+    if (p.N % 64 != 0 || p.K % TBK != 0 || p.K > 512) return 0;
+    int bn = 0;
+    if (p.N == 64 || p.N == 128 || p.N == 256) bn = p.N;
+    else if (p.N % 256 == 0 && p.N <= 1024) bn = 256;
+    if (g_stream_bn && p.N % g_stream_bn == 0 && g_stream_bn < bn) bn = g_stream_bn;        // narrower column ranges (more parts)
+    // the weights of one column range must fit 64 KB: K = 256 layers (layer3, N = 1024) take 128-column ranges, eight parts
+    if (bn == 256 && (long)bn * p.K * 2 > 64 * 1024 && p.N % 128 == 0 && p.N / 128 <= 8) bn = 128;
+    if (!bn || (long)bn * p.K * 2 > 64 * 1024) return 0;
+    if (g_tc_stream >= 2) return bn;
+    // auto: the long HBM-bound streams (at least four tiles per CTA); shorter problems stay on the latency-oriented kernels
+    const long tiles = (long)ceil_div(p.M, TBM) * (p.N / bn);
+    return tiles >= 4 * 148 ? bn : 0;
+}
+
+template <int BN, bool HAS_R, bool MBITS, bool OBITS>
+int launch_stream(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    CUtensorMap ma, mb, mc, mr;
+    // sliding-window A: rows are overlapping 64-element runs lda elements apart (see launch_tc)
+    const uint64_t a_rows = p.a_kb_rows ? (uint64_t)p.M + (uint64_t)(p.K / TBK - 1) * (uint64_t)p.a_kb_rows : (uint64_t)p.M;
+    if (!make_map(&ma, p.A, a_rows, p.a_kb_rows ? (uint64_t)TBK : (uint64_t)p.K, (uint64_t)p.lda, TBM) ||
+        !make_map(&mb, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN) ||
+        !make_map(&mc, p.C, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldc, TBM))
+        DETRB_FAIL(DETRB_E_CUDA, "gemm_stream: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)", p.M, p.N, p.K);
+    mr = mc;
+    if (p.residual && !make_map(&mr, p.residual, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldr, TBM))
+        DETRB_FAIL(DETRB_E_CUDA, "gemm_stream: cuTensorMapEncodeTiled(residual) failed");
+    static bool configured = false;
+    static int num_sms = 148;
+    if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute((gemm_stream_kernel<BN, HAS_R, MBITS, OBITS>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    const int nk = p.K / TBK, n_parts = p.N / BN, m_tiles = ceil_div(p.M, TBM);
+    // 16 KB units: 224 KB of data = weights + A stages + chunk slots.  A: two tiles in flight (at least 4 stages); the rest are slots
+    const int units = (227 * 1024 - 1024 - ST_BAR_BYTES) / 16384 - ceil_div(BN * p.K * 2, 16384);
+    int nst = g_stream_nst ? g_stream_nst : (2 * nk > 4 ? 2 * nk : 4);
+    if (nst > ST_MAX_NST) nst = ST_MAX_NST;
+    if (nst > units - 4) nst = units - 4;
+    int rs = g_stream_rs ? g_stream_rs : units - nst;
+    if (rs > units - nst) rs = units - nst;
+    rs &= ~1;
+    if (rs > ST_MAX_RS) rs = ST_MAX_RS;
+    if (nst < nk || nst < 1 || rs < 4) DETRB_FAIL(DETRB_E_SHAPE, "gemm_stream: no room for the rings (K=%d N=%d: %d stages, %d slots)", p.K, p.N, nst, rs);
+    int ctas_per_part = num_sms / n_parts;
+    if (ctas_per_part > m_tiles) ctas_per_part = m_tiles;
+    DETRB_LAUNCH((gemm_stream_kernel<BN, HAS_R, MBITS, OBITS>), dim3(ctas_per_part * n_parts), dim3(NTHREADS_P), 227 * 1024, stream, ma, mb, mc, mr, p, n_parts, m_tiles,
+                 nst, rs, g_stream_diag);
+    DETRB_CHECK_LAUNCH("gemm_stream_kernel");
+    return DETRB_OK;
+}
+
+template <int BN>
+int dispatch_stream(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    const bool r = p.residual != nullptr;
+    if (p.mask_bits) return r ? launch_stream<BN, true, true, false>(p, stream) : launch_stream<BN, false, true, false>(p, stream);
+    if (p.out_bits) return r ? launch_stream<BN, true, false, true>(p, stream) : launch_stream<BN, false, false, true>(p, stream);
+    return r ? launch_stream<BN, true, false, false>(p, stream) : launch_stream<BN, false, false, false>(p, stream);
+}
+
 }  // namespace
+
+extern "C" int detrb_set_tc_stream(int enable) { stream_pick(detrb_igemm_t{}); int old = g_tc_stream; g_tc_stream = enable; return old; }
 
 bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols, int swizzle_bytes)
@@ -878,6 +1218,8 @@ bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uin
 static bool aligned_epilogue(const detrb_igemm_t &p)
 {
     if (p.N % 8 != 0 || p.ldw % 8 != 0 || ((uintptr_t)p.W & 15)) return false;
+    if (p.mask_bits && (p.mask || p.N % 64 != 0 || p.ldmb % 8 != 0 || p.ldmb * 8 < p.N || ((uintptr_t)p.mask_bits & 7))) return false;
+    if (p.out_bits && (p.N % 64 != 0 || p.ldob % 8 != 0 || p.ldob * 8 < p.N || ((uintptr_t)p.out_bits & 7))) return false;
     if (p.C && (p.ldc % 8 != 0 || ((uintptr_t)p.C & 15))) return false;
     if (p.Cf && (p.ldcf % 4 != 0 || ((uintptr_t)p.Cf & 15))) return false;
     if (p.residual && (p.ldr % 8 != 0 || ((uintptr_t)p.residual & 15))) return false;
@@ -969,6 +1311,12 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
         const bool wide = bn == 128 || (bn == 0 && p.N >= 128);
         return wide ? launch_tc<128, 3, IM2COL, false, 1, true>(p, stream, cls) : launch_tc<64, 3, IM2COL, false, 1, true>(p, stream, cls);
     }
+    if constexpr (!IM2COL) {
+        if (bn == 0) {
+            const int sbn = stream_pick(p);
+            if (sbn) return sbn == 256 ? dispatch_stream<256>(p, stream) : sbn == 128 ? dispatch_stream<128>(p, stream) : dispatch_stream<64>(p, stream);
+        }
+    }
     bool taken = false;
     int rc = dispatch_tcp<IM2COL>(p, bn, stream, cls, &taken);
     if (taken || rc) return rc;
@@ -1018,6 +1366,8 @@ static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
             if (q.C) q.C = q.C + off * q.ldc;
             if (q.Cf) q.Cf = q.Cf + off * q.ldcf;
             if (q.mask) q.mask = q.mask + off * q.ldm;
+            if (q.mask_bits) q.mask_bits = q.mask_bits + off * q.ldmb;
+            if (q.out_bits) q.out_bits = q.out_bits + off * q.ldob;
             if (q.residual) q.residual = q.residual + off * q.ldr;
             ConvClass cls;
             cls.aux.pad = 0;
@@ -1036,7 +1386,10 @@ int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
 {
     const int kind = detrb_gemm_tc_kind(p);
     if (kind == 1) return dispatch_tc<false>(p, 0, stream);
-    if (kind == 2) return dispatch_tc<true>(p, 0, stream);
+    if (kind == 2) {
+        if (detrb_conv_halo_supported(p)) return detrb_conv_halo(p, stream);      // 3x3, 64 -> 64 channels: halo-reusing row kernel (conv_halo.cu)
+        return dispatch_tc<true>(p, 0, stream);
+    }
     if (kind == 3) return strided_dgrad_tc(p, stream);
     DETRB_FAIL(DETRB_E_SHAPE, "detrb_gemm_tc: unsupported problem");
 }

@@ -273,6 +273,8 @@ extern "C" int detrb_igemm(const detrb_igemm_t *pp, detrb_stream_t stream_)
         const int kind = detrb_gemm_tc_kind(p);
         if (kind == 1 || (kind >= 2 && detrb_gemm_tc_conv_enabled())) return detrb_gemm_tc(p, stream);
     }
+    if (p.mask_bits || p.out_bits)
+        DETRB_FAIL(DETRB_E_SHAPE, "detrb_igemm: 1-bit masks need the tcgen05 path (N %% 64 == 0, 8-byte aligned rows, not together with `mask`)");
     const bool stem = (p.Cin == 4);
     if (stem) {
         DETRB_REQUIRE(!p.split, "detrb_igemm: the Cin=4 stem path has no parity-precision variant");

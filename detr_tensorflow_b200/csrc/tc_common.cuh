@@ -77,3 +77,102 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // 2-D bf16 tensor map helper (gemm_tc.cu): [rows, cols] row stride ld, box [box_rows, box_cols], 128- / 64- / 32-byte swizzle
 bool detrb_make_tiled_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols, int swizzle_bytes = 128);
+
+// ------------------------------------------------------------------------------------------------ shared by the tcgen05 GEMM / convolution kernels
+constexpr int TBM = 128;
+constexpr int TBK = 64;                 // 64 bf16 = 128 B = one swizzle row
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row core groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                  // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                                  // version
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A and B,
+// N>>3 at bits [17,23), M>>4 at bits [24,29)   (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// v[0..8) += 8 consecutive floats of the bias row staged in shared memory (all lanes read the same address: broadcast)
+__device__ __forceinline__ void add_bias8(float (&v)[8], uint32_t saddr) {
+    float4 b0, b1;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(saddr));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(saddr + 16u));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
+
+// 1-bit ReLU masks (detrb_igemm_t.mask_bits / out_bits): the 8 bytes of one row x 64-column chunk travel as a uint2; byte c (0..7)
+// holds columns 8c .. 8c+7
+__device__ __forceinline__ uint2 ld_bits8(const uint8_t *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void apply_bits8(float (&v)[8], const uint2 &bits, int c, float scale) {
+    const uint32_t b = ((c < 4 ? bits.x : bits.y) >> (8 * (c & 3))) & 0xffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = ((b >> i) & 1u) ? v[i] * scale : 0.f;
+}
+__device__ __forceinline__ void collect_bits8(const float (&v)[8], uint2 &bits, int c) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) b |= (v[i] > 0.f ? 1u : 0u) << i;
+    if (c < 4) bits.x |= b << (8 * (c & 3)); else bits.y |= b << (8 * (c & 3));
+}
+
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y; t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y; t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// Straight-line epilogue of one 64-column chunk of one accumulator row (thread = row): acc_r = the row's 64 fp32 accumulators, rr =
+// its 64 residual values (8 x 16 B as they lie in the swizzled tile), bias from shared memory (zeros when there is none).  No flag or
+// data-dependent branches inside: every load of the chunk is in flight before the first use.  With branches between the 8-column
+// groups each group is a serial load -> use chain at LOADED shared-memory latency, and the epilogue, not HBM, sets the pace of the
+// memory-bound layers (measured on the layer1 1x1 conv + residual: 170 us branchy, 102 us straight-line, same memory pipeline).
+template <bool HAS_R, bool MBITS, bool OBITS>
+__device__ __forceinline__ void epi_chunk_math(const uint32_t (&acc_r)[64], const uint4 (&rr)[8], uint32_t sbias64, bool relu, const uint2 &mbc,
+                                               float mscale, uint2 &ob, uint32_t obuf_row, uint32_t sw)
+{
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __uint_as_float(acc_r[c * 8 + i]);
+        add_bias8(v, sbias64 + 32u * (uint32_t)c);
+        if (HAS_R) {
+            float res[8];
+            unpack8(rr[c], res);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] += res[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = relu ? fmaxf(v[i], 0.f) : v[i];
+        if (MBITS) apply_bits8(v, mbc, c, mscale);
+        if (OBITS) collect_bits8(v, ob, c);
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(obuf_row + (((uint32_t)c ^ sw) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    }
+}
+__device__ __forceinline__ void lds_row8(uint4 (&rr)[8], uint32_t row_addr, uint32_t sw) {
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[c].x), "=r"(rr[c].y), "=r"(rr[c].z), "=r"(rr[c].w)
+                     : "r"(row_addr + (((uint32_t)c ^ sw) << 4)));
+}
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+    tc_ld16(taddr, *reinterpret_cast<uint32_t (*)[16]>(&r[0]));
+    tc_ld16(taddr + 16u, *reinterpret_cast<uint32_t (*)[16]>(&r[16]));
+    tc_ld16(taddr + 32u, *reinterpret_cast<uint32_t (*)[16]>(&r[32]));
+    tc_ld16(taddr + 48u, *reinterpret_cast<uint32_t (*)[16]>(&r[48]));
+}
+

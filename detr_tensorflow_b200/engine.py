@@ -467,6 +467,11 @@ class Engine:
             if blk["ds"]:
                 buf(f"b{i}_idn", B, ho, wo, blk["d2"])
             buf(f"b{i}_out", B, ho, wo, blk["d2"])
+            # 1-bit ReLU masks of the three activations (written by the forward epilogues, read by the data gradients instead of
+            # the bf16 activations: 1/16 of the bytes)
+            buf(f"b{i}_a1_bits", B * hh * ww, blk["d1"] // 8, dtype=torch.uint8)
+            buf(f"b{i}_a2_bits", B * ho * wo, blk["d1"] // 8, dtype=torch.uint8)
+            buf(f"b{i}_out_bits", B * ho * wo, blk["d2"] // 8, dtype=torch.uint8)
             max_elems = max(max_elems, B * hh * ww * max(blk["cin"], blk["d1"]), B * ho * wo * blk["d2"])
             hh, ww = ho, wo
         self.fh, self.fw = hh, ww
@@ -673,12 +678,13 @@ class Engine:
         kh, kw, kwp, stride, pad = s.geom
         return dict(batch=B, IH=ih, IW=iw, Cin=s.Cin, OH=oh, OW=ow, KH=kh, KW=kwp, stride=stride, pad=pad, mode=mode)
 
-    def _conv_fwd(self, s, x, ihw, ohw, out, relu=True, residual=None):
+    def _conv_fwd(self, s, x, ihw, ohw, out, relu=True, residual=None, out_bits=None):
         B = self.B
         g = self._conv_geom(s, B, ihw[0], ihw[1], ohw[0], ohw[1])
         self.launches += 1
         self._probed(s.name, lambda: ops.igemm(x, s.Wf, B * ohw[0] * ohw[1], s.N, s.K, s.Cin, s.K, g, bias=s.epi_bias, residual=residual,
-                                               ldr=s.N, relu=relu, C=out, ldc=s.N, split=self.plane, wsplit=self.wplane))
+                                               ldr=s.N, relu=relu, C=out, ldc=s.N, split=self.plane, wsplit=self.wplane,
+                                               out_bits=out_bits, ldob=s.N // 8))
 
     def _probed(self, name, fn):
         """bench.py: CUDA-event timing of single launches (events on the stream the launch goes to); plain call otherwise"""
@@ -690,16 +696,17 @@ class Engine:
         e1.record()
         self.probe_events.setdefault(name, []).append((e0, e1))
 
-    def _conv_dgrad(self, s, dy, ihw, ohw, out, mask=None, residual=None):
-        """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]."""
+    def _conv_dgrad(self, s, dy, ihw, ohw, out, mask_bits=None, residual=None):
+        """data gradient of conv `s` (input ihw -> output ohw): out[B,ih,iw,Cin] from dy[B,oh,ow,N]; mask_bits: the 1-bit ReLU mask
+        of the conv's input activation."""
         B = self.B
         kh, kw, kwp, stride, pad = s.geom
         M = B * ihw[0] * ihw[1]
         g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=s.ldd, OH=ihw[0], OW=ihw[1], KH=kh, KW=kwp, stride=stride, pad=pad, mode=1)
         self.launches += 1
         self._before_write(out)
-        self._probed(s.name + "#dgrad", lambda: ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask=mask, ldm=s.Cin,
-                                                          mask_scale=1.0, residual=residual, ldr=s.Cin, C=out, ldc=s.Cin,
+        self._probed(s.name + "#dgrad", lambda: ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask_bits=mask_bits,
+                                                          ldmb=s.Cin // 8, mask_scale=1.0, residual=residual, ldr=s.Cin, C=out, ldc=s.Cin,
                                                           split=self.plane, wsplit=self.wplane))
 
     def _conv_wgrad(self, s, x, dy, ihw, ohw):
@@ -797,10 +804,10 @@ class Engine:
                 idn = a[f"b{i}_idn"]
             else:
                 idn = x
-            self._conv_fwd(blk["c1"], x, ihw, ihw, a[f"b{i}_a1"])
-            self._conv_fwd(blk["c2"], a[f"b{i}_a1"], ihw, ohw, a[f"b{i}_a2"])
+            self._conv_fwd(blk["c1"], x, ihw, ihw, a[f"b{i}_a1"], out_bits=a[f"b{i}_a1_bits"])
+            self._conv_fwd(blk["c2"], a[f"b{i}_a1"], ihw, ohw, a[f"b{i}_a2"], out_bits=a[f"b{i}_a2_bits"])
             self._join(ds)
-            self._conv_fwd(blk["c3"], a[f"b{i}_a2"], ohw, ohw, a[f"b{i}_out"], relu=True, residual=idn)
+            self._conv_fwd(blk["c3"], a[f"b{i}_a2"], ohw, ohw, a[f"b{i}_out"], relu=True, residual=idn, out_bits=a[f"b{i}_out_bits"])
             x = a[f"b{i}_out"]
         self.feat = x
         self._mark("fwd_backbone")
@@ -1083,7 +1090,7 @@ class Engine:
         nb = len(self.blocks)
         last = self.blocks[-1]
         g_out = a["g_x"]
-        self._lin(g_y, ip.Wd, M, self.c_feat, d, ip.ldd, out=g_out, mask=self.feat, ldm=self.c_feat)
+        self._lin(g_y, ip.Wd, M, self.c_feat, d, ip.ldd, out=g_out, mask_bits=a[f"b{nb - 1}_out_bits"], ldmb=self.c_feat // 8)
         # ---------------- backbone, last block first
         g_in = a["g_y"]
         for i in reversed(range(nb)):
@@ -1091,13 +1098,13 @@ class Engine:
             ihw, ohw = blk["in_hw"], blk["out_hw"]
             x = a["pool"] if i == 0 else a[f"b{i - 1}_out"]
             a1, a2 = a[f"b{i}_a1"], a[f"b{i}_a2"]
-            xmask = None if blk["first"] else x
+            xbits = None if blk["first"] else a[f"b{i - 1}_out_bits"]
             self._conv_wgrad(blk["c3"], a2, g_out, ohw, ohw)
-            self._conv_dgrad(blk["c3"], g_out, ohw, ohw, a["g_2"], mask=a2)
+            self._conv_dgrad(blk["c3"], g_out, ohw, ohw, a["g_2"], mask_bits=a[f"b{i}_a2_bits"])
             self._conv_wgrad(blk["c2"], a1, a["g_2"], ihw, ohw)
-            self._conv_dgrad(blk["c2"], a["g_2"], ihw, ohw, a["g_1"], mask=a1)
+            self._conv_dgrad(blk["c2"], a["g_2"], ihw, ohw, a["g_1"], mask_bits=a[f"b{i}_a1_bits"])
             self._conv_wgrad(blk["c1"], x, a["g_1"], ihw, ihw)
-            self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask=xmask, residual=None if blk["ds"] else g_out)
+            self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask_bits=xbits, residual=None if blk["ds"] else g_out)
             if blk["ds"]:
                 cd = blk["cd"]
                 self._conv_wgrad(cd, x, g_out, ihw, ohw)
@@ -1106,7 +1113,7 @@ class Engine:
                 g = dict(batch=B, IH=ohw[0], IW=ohw[1], Cin=cd.ldd, OH=ohw[0], OW=ohw[1], KH=1, KW=1, stride=1, pad=0, mode=0)
                 self.launches += 1
                 self._before_write(g_in)
-                ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask=xmask, ldm=cd.Cin, mask_scale=1.0,
+                ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask_bits=xbits, ldmb=cd.Cin // 8, mask_scale=1.0,
                           C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True, split=self.plane, wsplit=self.wplane)
             g_out, g_in = g_in, g_out
             if blk["prefix"] == "backbone/layer3/0":

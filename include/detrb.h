@@ -69,7 +69,7 @@ int detrb_set_pdl(int enable);
  *           t = oy + pad - kh ; valid iff t % stride == 0 ; iy = t / stride
  *   W     : [N, K] bf16, K = KH*KW*Cin ordered (kh, kw, c); ldw = row stride.
  *   stem  : Cin == 4 (RGB padded to 4 channels) with KW padded to 8 (7x8 taps, K = 224).
- *   epilogue, in this order:  acc (+bias[n]) (+residual[m,n]) (relu) (*mask: (mask[m,n]>0)*mask_scale)
+ *   epilogue, in this order:  acc (+bias[n]) (+residual[m,n]) (relu) (*mask: (mask[m,n]>0)*mask_scale, or its 1-bit form mask_bits)
  *           (sigmoid) (dropout keep/(1-p), counter-based on (m,n))  -> C bf16 and/or Cf fp32.
  *           With drop_p > 0 the residual is the un-dropped skip path and is added AFTER the dropout.
  *   scatter: if out_stride > 1 the GEMM row (b,oy,ox) is written to pixel (b, oy*out_stride,
@@ -104,6 +104,14 @@ typedef struct {
     /* parity precision (see the header comment): plane stride of the bf16 pairs of A / residual / mask / C (0 = plain bf16) and
      * of W.  Both zero or both non-zero. */
     int64_t split, wsplit;
+    /* 1-bit ReLU masks (the backbone's backward pass; custom_layers / resnet_backbone.py:116-136 under tape.gradient): a [rows, N/8]
+     * byte matrix, bit (n % 8) of byte n / 8 of row m belongs to element (m, n); row stride ldmb / ldob bytes.
+     *   mask_bits: consumed like `mask` (element kept and scaled by mask_scale iff its bit is set), instead of re-reading the
+     *              bf16 activation: 1/16 of the bytes.  Not together with `mask`.
+     *   out_bits : produced: bit = (stored result > 0), next to C.  Rows are indexed like C (scatter rows when out_stride > 1).
+     * N % 64 == 0, strides multiples of 8 bytes, 8-byte aligned bases; tcgen05 path only (DETRB_E_SHAPE otherwise). */
+    const uint8_t *mask_bits; int ldmb;
+    uint8_t *out_bits; int ldob;
 } detrb_igemm_t;
 
 int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);
@@ -114,6 +122,8 @@ int detrb_set_tc(int enable);
 int detrb_set_tc_conv(int enable);
 int detrb_set_tc_tma_epilogue(int enable);
 int detrb_set_tc_persistent(int enable);     /* persistent tile loop (one CTA per SM, epilogue overlapped with the next main loop) */   /* coalesced TMA-load/TMA-store epilogue of the tcgen05 kernel (default on) */   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
+int detrb_set_tc_stream(int enable);         /* streaming kernel for the HBM-bound 1x1 layers (weights resident in shared memory): 0 off, 1 auto, 2 wherever supported */
+int detrb_set_tc_halo(int enable);           /* halo-reusing row kernel for 3x3 / stride 1 / 64 -> 64 channel convolutions (conv_halo.cu): 0 off, 1 on */
 int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)

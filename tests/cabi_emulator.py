@@ -249,6 +249,11 @@ class FakeLib:
         if _addr(p.mask):
             mk = M2(p.mask, _Act.dtype, nrows, p.N, p.ldm)[orow].to(F32)
             v = torch.where(mk > 0, v * p.mask_scale, torch.zeros_like(v))
+        if _addr(p.mask_bits):
+            assert not _addr(p.mask) and p.N % 64 == 0
+            by = M2(p.mask_bits, torch.uint8, nrows, p.N // 8, p.ldmb)[orow]
+            bit = (by[:, :, None] >> torch.arange(8, dtype=torch.uint8)[None, None, :]) & 1
+            v = torch.where(bit.reshape(p.M, p.N) > 0, v * p.mask_scale, torch.zeros_like(v))
         if p.sigmoid:
             v = torch.sigmoid(v)
         if p.drop_p > 0:
@@ -262,6 +267,11 @@ class FakeLib:
             WR(p.C, nrows, p.N, p.ldc, v, sp, index=orow)
         if _addr(p.Cf):
             M2(p.Cf, F32, nrows, p.N, p.ldcf)[orow] = v
+        if _addr(p.out_bits):
+            assert p.N % 64 == 0
+            w = (1 << torch.arange(8, dtype=torch.int32))[None, None, :]
+            by = ((v > 0).reshape(p.M, p.N // 8, 8).to(torch.int32) * w).sum(-1).to(torch.uint8)
+            M2(p.out_bits, torch.uint8, nrows, p.N // 8, p.ldob)[orow] = by
         return 0
 
     def detrb_wgrad(self, pref, stream):

@@ -7,15 +7,17 @@ pytestmark = pytest.mark.gpu
 BF, F32 = torch.bfloat16, torch.float32
 
 
-@pytest.fixture(scope="module", params=["one-tile-per-CTA", "persistent"])
+@pytest.fixture(scope="module", params=["one-tile-per-CTA", "persistent", "streaming"])
 def ops(request):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     from detr_tensorflow_b200 import _lib, ops as o
     _lib.check(_lib.lib().detrb_check_device())
     old = o.set_tc_persistent(2 if request.param == "persistent" else 0)      # 2: persistent kernel wherever supported
+    olds = o.set_tc_stream(2 if request.param == "streaming" else 0)          # 2: streaming kernel wherever supported (bn = 0 launches)
     yield o
     o.set_tc_persistent(old)
+    o.set_tc_stream(olds)
 
 
 def rnd(*shape, scale=1.0, seed=0):
@@ -285,3 +287,176 @@ def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
     # the columns that do not exist in the 7x7x3 kernel receive exactly zero
     exists = Engine._stem_to_s2d(None, torch.ones(1, 7, 7, 3)).reshape(256).bool().cuda()
     assert float(dW[:, ~exists].abs().max()) == 0.0
+
+
+def _bits_to_bool(bits, N):
+    """[M, N/8] uint8 -> [M, N] bool (bit n % 8 of byte n / 8)"""
+    sh = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    return (((bits[:, :, None] >> sh[None, None, :]) & 1) > 0).reshape(bits.shape[0], N)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(1000, 256, 64, 0), (4175, 64, 256, 0), (1300, 512, 128, 0), (777, 128, 512, 128), (20000, 256, 64, 256),
+                                      (5000, 1024, 256, 0), (128 * 148 * 2 + 77, 64, 64, 64)])
+def test_gemm_tc_one_bit_relu_masks(ops, M, N, K, bn):
+    """detrb_igemm_t.out_bits / mask_bits (the backbone's ReLU masks at 1 bit per element): the forward epilogue writes
+    bit = (result > 0) next to C; a data gradient that consumes the bits gives the bytes of the same launch with the bf16 mask."""
+    if bn == 256 and ops.set_tc_persistent(2) != 2:
+        ops.set_tc_persistent(0)
+        pytest.skip("256-wide tiles exist only in the persistent kernel")
+    A = rnd(M, K, seed=1).to(BF)
+    W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4).to(BF)
+    C = torch.full((M + 2, N), 7.0, dtype=BF, device="cuda")
+    bits = torch.full((M + 2, N // 8), 0xA5, dtype=torch.uint8, device="cuda")
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, residual=res, ldr=N, relu=True, C=C, ldc=N, out_bits=bits, ldob=N // 8,
+              force_tc=bn)
+    torch.cuda.synchronize()
+    check("fwd", C[:M], F.relu(A.float() @ W.float().t() + bias + res.float()), 1e-2, 1e-2)
+    assert torch.equal(_bits_to_bool(bits[:M], N), C[:M].float() > 0)
+    assert int((bits[M:] != 0xA5).sum()) == 0 and float((C[M:].float() - 7.0).abs().max()) == 0       # guard rows untouched
+    # consumer: same launch with the bf16 activation as mask and with its bits
+    G = rnd(M, K, seed=6).to(BF)
+    D1 = torch.empty(M, N, dtype=BF, device="cuda")
+    D2 = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.igemm(G, W, M, N, K, K, K, ops.plain_geom(M, K), residual=res, ldr=N, mask=C, ldm=N, mask_scale=1.0, C=D1, ldc=N, force_tc=bn)
+    ops.igemm(G, W, M, N, K, K, K, ops.plain_geom(M, K), residual=res, ldr=N, mask_bits=bits, ldmb=N // 8, mask_scale=1.0, C=D2, ldc=N,
+              force_tc=bn)
+    torch.cuda.synchronize()
+    assert torch.equal(D1, D2)
+    assert float(D1.float().abs().max()) > 0
+
+
+def test_one_bit_masks_conv_and_direct_store_paths(ops):
+    """out_bits from an im2col (3x3) forward, mask_bits in the strided scatter-accumulate data gradient of a 1x1/stride-2 shortcut
+    (direct-store epilogue) and in a 3x3/stride-2 data gradient (parity-class sub-convolutions)"""
+    B, H, Wd, Ci, Co = 2, 30, 44, 64, 128
+    x = F.relu(rnd(B, H, Wd, Ci, seed=1)).to(BF)
+    w = rnd(Co, 9 * Ci, scale=(9 * Ci) ** -0.5, seed=2).to(BF)
+    M = B * H * Wd
+    y = torch.empty(M, Co, dtype=BF, device="cuda")
+    bits = torch.zeros(M, Co // 8, dtype=torch.uint8, device="cuda")
+    g = dict(batch=B, IH=H, IW=Wd, Cin=Ci, OH=H, OW=Wd, KH=3, KW=3, stride=1, pad=1, mode=0)
+    ops.igemm(x, w, M, Co, 9 * Ci, Ci, 9 * Ci, g, relu=True, C=y, ldc=Co, out_bits=bits, ldob=Co // 8)
+    torch.cuda.synchronize()
+    assert torch.equal(_bits_to_bool(bits, Co), y.float() > 0)
+    # 1x1 / stride-2 shortcut data gradient: scatter to the even pixels of the input grid, accumulate, mask of the input activation
+    xb = torch.zeros(M, Ci // 8, dtype=torch.uint8, device="cuda")
+    xin = rnd(B, H, Wd, Ci, seed=3).to(BF)
+    ops.igemm(xin, torch.eye(Ci, device="cuda").to(BF).contiguous(), M, Ci, Ci, Ci, Ci, ops.plain_geom(M, Ci), relu=True,
+              C=torch.empty(M, Ci, dtype=BF, device="cuda"), ldc=Ci, out_bits=xb, ldob=Ci // 8)
+    oh, ow = H // 2, Wd // 2
+    Mo = B * oh * ow
+    dy = rnd(Mo, Co, seed=4).to(BF)
+    wd = rnd(Ci, Co, scale=Co ** -0.5, seed=5).to(BF)
+    base = rnd(M, Ci, seed=6).to(BF)
+    g1 = dict(batch=B, IH=oh, IW=ow, Cin=Co, OH=oh, OW=ow, KH=1, KW=1, stride=1, pad=0, mode=0)
+    outs = []
+    for kw in (dict(mask=F.relu(xin.float()).to(BF).view(M, Ci), ldm=Ci), dict(mask_bits=xb, ldmb=Ci // 8)):
+        o = base.clone()
+        ops.igemm(dy, wd, Mo, Ci, Co, Co, Co, g1, mask_scale=1.0, C=o, ldc=Ci, out_stride=2, SH=H, SW=Wd, accumulate=True, **kw)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], base)
+    # 3x3 / stride-2 / pad-1 data gradient (four parity classes) with the bits of its input activation
+    w3 = rnd(Ci, 9 * Co, scale=(9 * Co) ** -0.5, seed=7).to(BF)
+    g3 = dict(batch=B, IH=oh, IW=ow, Cin=Co, OH=H, OW=Wd, KH=3, KW=3, stride=2, pad=1, mode=1)
+    outs = []
+    for kw in (dict(mask=F.relu(xin.float()).to(BF).view(M, Ci), ldm=Ci), dict(mask_bits=xb, ldmb=Ci // 8)):
+        o = torch.zeros(M, Ci, dtype=BF, device="cuda")
+        ops.igemm(dy, w3, M, Ci, 9 * Co, Co, 9 * Co, g3, mask_scale=1.0, C=o, ldc=Ci, **kw)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and float(outs[0].float().abs().max()) > 0
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(534400, 256, 64, "r"), (534400, 256, 64, "rb"), (534400, 64, 256, "b"), (534400, 64, 64, ""), (133600, 512, 128, "r"),
+                                       (133600, 512, 128, "rb"), (534400, 128, 256, ""), (128 * 148 * 4 + 13, 256, 128, "rb"), (300, 128, 64, "r"),
+                                       (128 * 5, 1024, 64, "rb")])
+def test_gemm_stream_kernel(M, N, K, epi):
+    """gemm_stream_kernel (weights resident in shared memory, in-place chunk slots) on the layer1 / layer2 1x1 shapes at full size,
+    a ragged last tile, fewer tiles than CTAs, four column parts: against fp32 PyTorch on sampled rows, and bit for bit against the
+    one-tile kernel on the whole output (same bf16 products, same fp32 accumulation order inside a k-block chain)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from detr_tensorflow_b200 import ops
+    A = rnd(M, K, seed=1).to(BF)
+    W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+    bias = rnd(N, seed=3)
+    kw = {}
+    if "r" in epi:
+        kw.update(residual=rnd(M, N, seed=4).to(BF), ldr=N)
+    if "b" in epi:
+        kw.update(mask_bits=torch.randint(0, 256, (M, N // 8), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda(), ldmb=N // 8,
+                  mask_scale=1.0)
+    outs, bits = [], []
+    for mode in (2, 0):
+        olds, oldp = ops.set_tc_stream(mode), ops.set_tc_persistent(0)
+        try:
+            C = torch.full((M + 2, N), 7.0, dtype=BF, device="cuda")
+            ob = torch.full((M + 2, N // 8), 0x5A, dtype=torch.uint8, device="cuda")
+            ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, out_bits=ob, ldob=N // 8, **kw)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_tc_stream(olds)
+            ops.set_tc_persistent(oldp)
+        outs.append(C)
+        bits.append(ob)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(bits[0], bits[1])
+    C = outs[0]
+    assert float((C[M:].float() - 7.0).abs().max()) == 0 and int((bits[0][M:] != 0x5A).sum()) == 0
+    rows = torch.cat([torch.arange(0, min(M, 300)), torch.randint(0, M, (2000,), generator=torch.Generator().manual_seed(6)),
+                      torch.arange(max(0, M - 300), M)]).cuda()
+    ref = A[rows].float() @ W.float().t() + bias
+    if "r" in epi:
+        ref = ref + kw["residual"][rows].float()
+    ref = F.relu(ref)
+    if "b" in epi:
+        ref = torch.where(_bits_to_bool(kw["mask_bits"][rows], N), ref, torch.zeros_like(ref))
+    check("stream", C[rows], ref, 1e-2, 1e-2)
+    assert torch.equal(_bits_to_bool(bits[0][:M], N), C[:M].float() > 0)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 20, 334), (1, 7, 100), (3, 33, 300), (1, 1, 5), (8, 200, 334), (2, 150, 129)])
+def test_conv3x3_halo_kernel(B, H, W):
+    """conv_halo.cu (3x3 / stride 1 / 64 -> 64 channels, every input row staged once, the nine taps as shifted descriptor views):
+    forward (+ folded-BN shift, ReLU, 1-bit mask out) and data gradient (+ 1-bit mask in) against fp32 PyTorch, and bit for bit
+    against the TMA-im2col kernel (same products, same accumulation order); 1..3 column strips, partial last strip, runs that start
+    and end inside an image, fewer units than CTAs."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from detr_tensorflow_b200 import ops
+    C = 64
+    x = rnd(B, H, W, C, seed=1).to(BF)
+    w = rnd(C, 3, 3, C, scale=(9 * C) ** -0.5, seed=2).to(BF)
+    shift = rnd(C, seed=3)
+    M, K = B * H * W, 9 * C
+    g = conv_geom(B, H, W, C, H, W, 3, 3, 1, 1)
+    dy = rnd(B, H, W, C, seed=5).to(BF)
+    wd = w.reshape(C, 9, C).permute(2, 1, 0).contiguous()
+    mbits = torch.randint(0, 256, (M, C // 8), dtype=torch.uint8, generator=torch.Generator().manual_seed(7)).cuda()
+    gd = conv_geom(B, H, W, C, H, W, 3, 3, 1, 1, mode=1)
+    res = {}
+    for halo in (1, 0):
+        old = ops.set_tc_halo(halo)
+        try:
+            y = torch.full((M + 1, C), 7.0, dtype=BF, device="cuda")
+            ob = torch.full((M + 1, C // 8), 0x5A, dtype=torch.uint8, device="cuda")
+            ops.igemm(x, w, M, C, K, C, K, g, bias=shift, relu=True, C=y, ldc=C, out_bits=ob, ldob=C // 8)
+            dx = torch.full((M + 1, C), 7.0, dtype=BF, device="cuda")
+            ops.igemm(dy, wd, M, C, K, C, K, gd, mask_bits=mbits, ldmb=C // 8, mask_scale=1.0, C=dx, ldc=C)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_tc_halo(old)
+        res[halo] = (y, ob, dx)
+    y, ob, dx = res[1]
+    assert float((y[M:].float() - 7.0).abs().max()) == 0 and int((ob[M:] != 0x5A).sum()) == 0 and float((dx[M:].float() - 7.0).abs().max()) == 0
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias=shift, padding=1).permute(0, 2, 3, 1)).reshape(M, C)
+    check("halo fwd", y[:M], ref, 1e-2, 2e-2)
+    assert torch.equal(_bits_to_bool(ob[:M], C), y[:M].float() > 0)
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    o = F.conv2d(xt, w.float().permute(0, 3, 1, 2), padding=1)
+    gx, = torch.autograd.grad(o, [xt], dy.float().permute(0, 3, 1, 2))
+    refd = gx.permute(0, 2, 3, 1).reshape(M, C) * _bits_to_bool(mbits, C)
+    check("halo dgrad", dx[:M], refd, 1e-2, 2e-2)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)

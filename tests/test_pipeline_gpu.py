@@ -113,9 +113,14 @@ def test_uint8_frames_through_model_and_fit(D):
     assert torch.equal(losses["u8"][0], losses["f32"][0])
     a, b = losses["u8"][1], losses["f32"][1]
     # same bf16 stem input -> same forward, bit for bit (logits above); the loss sums and the weight gradients are reduced with
-    # fp32 atomics whose order varies run to run -> equal to rounding only
-    assert len(a) == 3 and abs(a[0] - b[0]) <= 1e-6 * abs(b[0])
-    assert all(abs(x - y) <= 1e-3 * abs(y) for x, y in zip(a, b)), (a, b)
+    # fp32 atomics whose order varies run to run -> the first loss is equal to rounding.  After an optimizer step the trajectories
+    # may separate DISCRETELY: the first Adam step is sign-like (lr * g / (|g| + eps)), so gradients that differ in their last bits
+    # move near-zero weights in opposite directions, and with random-init weights the 100 queries are near-ties for the matcher
+    # (costs within 1e-6): one flipped assignment changes the later losses by ~1e-3.  Measured over 24 runs of the SAME input
+    # (tests/repro_fit_race.py, also on the build before this test existed): two outcomes, 16.7182 / 14.7337 and 16.7216 / 14.7544.
+    print("losses u8", a, "f32", b)
+    assert len(a) == 3 and abs(a[0] - b[0]) <= 5e-6 * abs(b[0]), (a, b)      # ~400 fp32 terms summed in varying order: a few 1e-7 .. 1e-6
+    assert all(abs(x - y) <= 5e-3 * abs(y) for x, y in zip(a, b)), (a, b)
     assert losses["u8"][1][2] != losses["u8"][1][0]           # the optimizer moved
 
 

@@ -1,5 +1,6 @@
 """Developer tool: time one GEMM shape through detrb_igemm (auto policy; env switches select kernel variants).
 python tests/time_gemm.py M N K epi [mode bn nobias]  (epi: -, r, m, rm; mode 0 one-tile / 2 persistent; bn 0|64|128|256)"""
+import os
 import sys
 
 import torch
@@ -31,6 +32,14 @@ if "r" in epi:
     kw.update(residual=R, ldr=N)
 if "m" in epi:
     kw.update(mask=Mk, ldm=N, mask_scale=1.0)
+if "b" in epi:                      # 1-bit mask instead of the bf16 one
+    Mb = torch.randint(0, 256, (M, N // 8), dtype=torch.uint8, device="cuda")
+    kw.update(mask_bits=Mb, ldmb=N // 8, mask_scale=1.0)
+if "o" in epi:                      # also write the 1-bit ReLU mask of the result
+    Ob = torch.empty(M, N // 8, dtype=torch.uint8, device="cuda")
+    kw.update(out_bits=Ob, ldob=N // 8)
+if os.environ.get("STREAM") is not None:
+    ops.set_tc_stream(int(os.environ["STREAM"]))
 fn = lambda: ops.igemm(A, Wt, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, **kw)
 for _ in range(3):
     fn()
@@ -42,10 +51,13 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / 20 * 1e3
-byts = (M * K + N * K + (1 + len(epi)) * M * N) * 2
+byts = (M * K + N * K + (1 + len(epi.replace("b", "").replace("o", ""))) * M * N) * 2 + (("b" in epi) + ("o" in epi)) * M * N // 8
 ref = torch.relu(A[:256].float() @ Wt.float().t() + (R[:256].float() if "r" in epi else 0))
 if "m" in epi:
     ref = torch.where(Mk[:256].float() > 0, ref, torch.zeros_like(ref))
+if "b" in epi:
+    bit = ((Mb[:256, :, None] >> torch.arange(8, device="cuda", dtype=torch.uint8)[None, None, :]) & 1).reshape(256, N) > 0
+    ref = torch.where(bit, ref, torch.zeros_like(ref))
 err = float((C[:256].float() - ref).abs().max() / (ref.abs().max() + 1e-9))
 print(f"{M}x{N}x{K} {epi or '-'}: {us:.1f} us  {byts / us / 1e3:.0f} GB/s  {2.0 * M * N * K / us / 1e6:.0f} TF/s  relerr {err:.4f}")
 if os.environ.get("DETRB_SO"):
