@@ -82,7 +82,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     if (warp == 0) {
         // ===================== weights once, then one new input row per unit (three at the start of a run) =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(w_full, W_BYTES);
             for (int t = 0; t < 9; t++) tma_load_2d(smem0 + (uint32_t)(t * W_TAP_BYTES), &map_w, w_full, t * HC, 0);
             int seq = 0;
@@ -103,7 +103,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer: nine taps = nine views of the three resident rows =====================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(TBM, HC);
             mbar_wait(w_full, 0);
             int top = 0, next_seq = 0, it = 0;

@@ -42,6 +42,15 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap 
                  " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
+// One thread of the (converged) warp: elect.sync.  Branching on THIS predicate tells ptxas that exactly one thread runs the block,
+// so single-thread instructions that take uniform-register operands (tcgen05.mma, tcgen05.commit, TMA) are emitted once; under
+// `if (lane == 0)` it wraps every one of them in an ELECT / BRA.U.ANY loop over the active mask (~50 cycles per tcgen05.mma:
+// more than the 32 cycles a 128x64x16 MMA occupies the tensor pipe).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
