@@ -189,6 +189,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 uint4 rr[8];
                 uint2 ob = make_uint2(0u, 0u);
                 tc_wait_ld();
+                // the accumulator is in registers: hand it back to the MMA warp now, not after the store (the leader waits for the
+                // TMA store to read the slot, which would hold the accumulator for another microsecond)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
                 if (diag & 4) {}                                                                  // developer switch: no epilogue arithmetic
                 else if (mbits) epi_chunk_math<false, true, false>(acc_r, rr, sbias, relu, mb_cur, p.mask_scale, ob, sbuf + row_off, sw);
                 else if (obits) epi_chunk_math<false, false, true>(acc_r, rr, sbias, relu, mb_cur, 1.f, ob, sbuf + row_off, sw);
@@ -203,10 +208,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the warpgroup's only slot: free as soon as the store has read it
                     mbar_arrive(slot_free(slot));
                 }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(acc));
         }
         if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }

@@ -57,8 +57,10 @@ struct SmemLayout {
 // SPLIT (parity precision, include/detrb.h): A and W are bf16 pairs (hi plane / lo plane, tensor maps map_a2 / map_b2 for the lo
 // planes); the k-loop runs three passes -- A_hi*W_hi, A_lo*W_hi, A_hi*W_lo -- through the same stages into the same TMEM
 // accumulator; the epilogue (direct stores) reads residuals as hi + lo and writes the result as a pair.
-template <int BN, int STAGES, bool IM2COL, bool SPLIT = false>
-__global__ void __launch_bounds__(NTHREADS_TC, (BN == 64 && !SPLIT) ? 5 : 1)
+// BITS: the 1-bit ReLU-mask code (mask_bits / out_bits) is compiled only into its own instantiations (and the SPLIT ones): inside the
+// common kernels its flag tests cost the 64-register variants spills and every small GEMM of the transformer ~8 us.
+template <int BN, int STAGES, bool IM2COL, bool SPLIT = false, bool BITS_T = false>
+__global__ void __launch_bounds__(NTHREADS_TC, (BN == 64 && !SPLIT && !BITS_T) ? 5 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_a2,
@@ -196,12 +198,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < p.M;
-        uint2 mb0 = make_uint2(0u, 0u), mb1 = make_uint2(0u, 0u);   // this row's mask bits of the tile's (at most two) 64-column chunks
-        if (tma_epi && p.mask_bits && row_ok) {              // in flight during the main loop
-            const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
-            mb0 = ld_bits8(mp);
-            if (L::NCH > 1 && nch > 1) mb1 = ld_bits8(mp + 8);
-        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const long long t_tf = TRACE_NOW();
@@ -241,8 +237,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (leader) TRACE_ADD(5, t_in - t_tf);            // accumulator complete -> residual / mask tiles landed
             // the bit-mask code is compiled into its own copy of the chunk loop: the common (bit-free) path keeps its instruction
             // count and registers (the extra flag tests inside the 8-column groups cost the BN = 128 kernel 40 % on layer3)
-            auto chunks = [&](auto bits_tag) {
-            constexpr bool BITS = decltype(bits_tag)::value;
+            constexpr bool BITS = BITS_T || SPLIT;
+            {
+            // this row's mask bits of the tile's (at most two) 64-column chunks (loaded here, not before the main loop: two more live
+            // registers across the accumulator wait spill in the 64-register kernels, and the co-resident CTAs hide the latency)
+            uint2 mb0 = make_uint2(0u, 0u), mb1 = make_uint2(0u, 0u);
+            if (BITS && p.mask_bits && row_ok) {
+                const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
+                mb0 = ld_bits8(mp);
+                if (L::NCH > 1 && nch > 1) mb1 = ld_bits8(mp + 8);
+            }
 #pragma unroll 1
             for (int cb = 0; cb < nch; cb++) {
                 const int nb = n0 + cb * 64;
@@ -313,8 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (BITS && p.out_bits && row_ok) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
             }
-            };
-            if (p.mask_bits || p.out_bits) chunks(std::true_type{}); else chunks(std::false_type{});
+            }
             const long long t_math = TRACE_NOW();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy writes -> visible to TMA
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -367,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.f ? v[i] * p.mask_scale : 0.f;
                 }
-                if (p.mask_bits) apply_bits8(v, make_uint2((uint32_t)p.mask_bits[orow * p.ldmb + (n >> 3)], 0u), 0, p.mask_scale);
+                if ((BITS_T || SPLIT) && p.mask_bits) apply_bits8(v, make_uint2((uint32_t)p.mask_bits[orow * p.ldmb + (n >> 3)], 0u), 0, p.mask_scale);
                 if (p.sigmoid) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[i] = 1.f / (1.f + __expf(-v[i]));
@@ -391,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     sp_st8(dst, split, v);
                 }
-                if (p.out_bits) {
+                if ((BITS_T || SPLIT) && p.out_bits) {
                     uint2 ob = make_uint2(0u, 0u);
                     collect_bits8(v, ob, 0);
                     p.out_bits[orow * p.ldob + (n >> 3)] = (uint8_t)ob.x;
@@ -918,6 +921,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             mbar_wait(tmem_full(acc), (it / NACC) & 1);
             tc_fence_after();
+            bool released = false;
 #pragma unroll 1
             for (int cb = 0; cb < NCH; cb++, g++) {
                 if ((g & 1) != wg) continue;
@@ -940,6 +944,14 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     for (int i = 1; i < NCH; i++) if (cb == i) mbc = mb_cur[i];
                 }
                 tc_wait_ld();
+                // this warpgroup's last chunk of the tile (chunks alternate between the two warpgroups): the accumulator goes back to
+                // the MMA warp as soon as it is in registers, not after the stores
+                if (cb + 2 >= NCH) {
+                    released = true;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty(acc));
+                }
                 if (!(diag & 2)) epi_chunk_math<HAS_R, MBITS, OBITS>(acc_r, rr, sbias + 4u * (uint32_t)(cb * 64), relu, mbc, mscale, ob, sbuf + row_off, sw);
                 if (OBITS && m < p.M) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -956,9 +968,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     prev_slot = slot;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(acc));
+            if (!released) {                                  // a warpgroup without a chunk in this tile (BN = 64: every other tile)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(acc));
+            }
         }
         if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -1016,7 +1030,7 @@ static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
 
-template <int BN, int STAGES, bool IM2COL, bool PERSIST = false, int OB = 1, bool SPLIT = false>
+template <int BN, int STAGES, bool IM2COL, bool PERSIST = false, int OB = 1, bool SPLIT = false, bool BITS_T = false>
 int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls = nullptr)
 {
     static_assert(!(PERSIST && SPLIT), "parity precision runs on the one-tile kernel");
@@ -1102,7 +1116,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
     using L = SmemLayout<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT>), cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        DETRB_CUDA(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT, BITS_T>), cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
     dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TBM));
@@ -1116,7 +1130,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         if (STAGES == 1 && p.mask) early = 1;
     }
     const size_t smem = early ? L::TOTAL : L::BASE;
-    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT>), dim3(grid), dim3(NTHREADS_TC), smem, stream, ma, mb, mc, mr, mm, ma2, mb2, p, aux, tma_epi | (early << 1));
+    DETRB_LAUNCH((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT, BITS_T>), dim3(grid), dim3(NTHREADS_TC), smem, stream, ma, mb, mc, mr, mm, ma2, mb2, p, aux, tma_epi | (early << 1));
     DETRB_CHECK_LAUNCH("gemm_tc_kernel");
     return DETRB_OK;
     }
@@ -1326,6 +1340,10 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
         const long tiles128 = (long)ceil_div(p.N, 128) * ceil_div(p.M, TBM);
         bn = (p.N >= 128 && tiles128 >= 148 && p.K > 128) ? 128 : 64;
     }
+    // 1-bit ReLU masks: the kernels that carry the bit code (the full-size backbone layers run on the streaming / halo / persistent
+    // kernels; this is the path of small images, strided data gradients and scatter-accumulate shortcuts)
+    if (p.mask_bits || p.out_bits)
+        return bn == 128 ? launch_tc<128, 3, IM2COL, false, 1, false, true>(p, stream, cls) : launch_tc<64, 3, IM2COL, false, 1, false, true>(p, stream, cls);
     // short k-loops (K <= 256) are latency bound: 2 stages -> 64 / 48 KB of smem -> 3-4 co-resident CTAs per SM hide each other
     const int nk = p.K / TBK;
     const bool shallow = nk <= 4;
