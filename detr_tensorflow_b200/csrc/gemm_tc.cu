@@ -637,7 +637,7 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
         int it = 0, g = 0;
-        const bool fast = !has_m && !p.sigmoid && !(p.drop_p > 0.f) && p.N % 64 == 0;
+        const bool fast = !has_m && !p.sigmoid && p.N % 64 == 0;               // bias / residual / ReLU / bit masks / dropout: the straight-line chunk
         uint2 mb_cur[L::NCH], mb_nxt[L::NCH];                   // 1-bit mask of this row: current tile, next tile (prefetched)
         if (p.mask_bits) load_tile_bits<L::NCH>(mb_nxt, p, blockIdx.x, n_tiles, n_tiles_n, row);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
@@ -693,7 +693,12 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (has_r) lds_row8(rr, rbuf + row_off, sw);
                     tc_wait_ld();
                     const bool relu = p.relu != 0;
-                    if (has_r) {
+                    if (p.drop_p > 0.f) {
+                        EpiDrop dr;
+                        dr.rowhash = dropout_rowhash(seed, p.site, (uint32_t)m); dr.thresh = thresh; dr.col0 = (uint32_t)nb; dr.scale = drop_scale;
+                        if (has_r) epi_chunk_math<true, false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw, dr);
+                        else epi_chunk_math<false, false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw, dr);
+                    } else if (has_r) {
                         if (p.mask_bits) epi_chunk_math<true, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, obuf + row_off, sw);
                         else if (p.out_bits) epi_chunk_math<true, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
                         else epi_chunk_math<true, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
@@ -898,6 +903,10 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("bar.sync 3, 256;" ::: "memory");
         const bool relu = p.relu != 0;
         const float mscale = p.mask_scale;
+        const bool drop = p.drop_p > 0.f;
+        const uint32_t thresh = dropout_thresh16(p.drop_p);
+        const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+        const uint64_t seed = p.seed ^ ((drop && p.seed_ptr) ? *p.seed_ptr : 0ull);
         uint2 mb_cur[NCH], mb_nxt[NCH];
         auto load_bits = [&](uint2 (&b)[NCH], int t) {
 #pragma unroll
@@ -952,7 +961,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty(acc));
                 }
-                if (!(diag & 2)) epi_chunk_math<HAS_R, MBITS, OBITS>(acc_r, rr, sbias + 4u * (uint32_t)(cb * 64), relu, mbc, mscale, ob, sbuf + row_off, sw);
+                if (!MBITS && !OBITS && drop) {
+                    EpiDrop dr;
+                    dr.rowhash = dropout_rowhash(seed, p.site, (uint32_t)m); dr.thresh = thresh; dr.col0 = (uint32_t)nb; dr.scale = drop_scale;
+                    epi_chunk_math<HAS_R, false, false, true>(acc_r, rr, sbias + 4u * (uint32_t)(cb * 64), relu, mbc, mscale, ob, sbuf + row_off, sw, dr);
+                } else if (!(diag & 2)) epi_chunk_math<HAS_R, MBITS, OBITS>(acc_r, rr, sbias + 4u * (uint32_t)(cb * 64), relu, mbc, mscale, ob, sbuf + row_off, sw);
                 if (OBITS && m < p.M) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
@@ -1154,14 +1167,15 @@ int stream_pick(const detrb_igemm_t &p)
         if (const char *e = getenv("DETRB_STREAM_BN")) g_stream_bn = atoi(e);
     }
     if (!g_tc_stream || p.split || p.mask || !p.C || p.Cf || p.out_stride > 1 || p.accumulate || !g_tma_epilogue) return 0;
-    if (p.sigmoid || p.drop_p > 0.f || (p.mask_bits && p.out_bits)) return 0;           // backbone epilogues only: bias, residual, ReLU, bit masks
+    if (p.sigmoid || (p.mask_bits && p.out_bits) || (p.drop_p > 0.f && (p.mask_bits || p.out_bits))) return 0;   // bias, residual, ReLU, bit masks or dropout
     if (p.N % 64 != 0 || p.K % TBK != 0 || p.K > 512) return 0;
     int bn = 0;
     if (p.N == 64 || p.N == 128 || p.N == 256) bn = p.N;
-    else if (p.N % 256 == 0 && p.N <= 1024) bn = 256;
+    else if (p.N % 256 == 0 && p.N <= 2048) bn = 256;
     if (g_stream_bn && p.N % g_stream_bn == 0 && g_stream_bn < bn) bn = g_stream_bn;        // narrower column ranges (more parts)
     // the weights of one column range must fit 64 KB: K = 256 layers (layer3, N = 1024) take 128-column ranges, eight parts
-    if (bn == 256 && (long)bn * p.K * 2 > 64 * 1024 && p.N % 128 == 0 && p.N / 128 <= 8) bn = 128;
+    // (the encoder's FFN1, N = 2048: sixteen parts)
+    if (bn == 256 && ((long)bn * p.K * 2 > 64 * 1024 || p.N > 1024) && p.N % 128 == 0 && p.N / 128 <= 16) bn = 128;
     if (!bn || (long)bn * p.K * 2 > 64 * 1024) return 0;
     if (g_tc_stream >= 2) return bn;
     // auto: the long HBM-bound streams (at least four tiles per CTA); shorter problems stay on the latency-oriented kernels

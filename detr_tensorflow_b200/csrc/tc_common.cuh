@@ -147,25 +147,38 @@ __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
 // data-dependent branches inside: every load of the chunk is in flight before the first use.  With branches between the 8-column
 // groups each group is a serial load -> use chain at LOADED shared-memory latency, and the epilogue, not HBM, sets the pace of the
 // memory-bound layers (measured on the layer1 1x1 conv + residual: 170 us branchy, 102 us straight-line, same memory pipeline).
-template <bool HAS_R, bool MBITS, bool OBITS>
+// the dropout of a chunk: rowhash = dropout_rowhash(seed, site, row) (once per row), col0 = global column of the chunk
+struct EpiDrop { uint32_t rowhash, thresh, col0; float scale; };
+template <bool HAS_R, bool MBITS, bool OBITS, bool DROP = false>
 __device__ __forceinline__ void epi_chunk_math(const uint32_t (&acc_r)[64], const uint4 (&rr)[8], uint32_t sbias64, bool relu, const uint2 &mbc,
-                                               float mscale, uint2 &ob, uint32_t obuf_row, uint32_t sw)
+                                               float mscale, uint2 &ob, uint32_t obuf_row, uint32_t sw, const EpiDrop &dr = EpiDrop())
 {
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-        float v[8];
+        float v[8], res[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = __uint_as_float(acc_r[c * 8 + i]);
         add_bias8(v, sbias64 + 32u * (uint32_t)c);
         if (HAS_R) {
-            float res[8];
             unpack8(rr[c], res);
+            if (!DROP) {                                    // with dropout the residual is the un-dropped skip path: it joins last
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] += res[i];
+                for (int i = 0; i < 8; i++) v[i] += res[i];
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = relu ? fmaxf(v[i], 0.f) : v[i];
         if (MBITS) apply_bits8(v, mbc, c, mscale);
+        if (DROP) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                bool k0, k1;
+                dropout_keep2(dropout_bits_rh(dr.rowhash, (dr.col0 + (uint32_t)(c * 8 + i)) >> 1), dr.thresh, k0, k1);
+                v[i] = k0 ? v[i] * dr.scale : 0.f;
+                v[i + 1] = k1 ? v[i + 1] * dr.scale : 0.f;
+                if (HAS_R) { v[i] += res[i]; v[i + 1] += res[i + 1]; }
+            }
+        }
         if (OBITS) collect_bits8(v, ob, c);
         uint4 o;
         o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);

@@ -1104,8 +1104,21 @@ class Engine:
             self._conv_wgrad(blk["c2"], a1, a["g_2"], ihw, ohw)
             self._conv_dgrad(blk["c2"], a["g_2"], ihw, ohw, a["g_1"], mask_bits=a[f"b{i}_a1_bits"])
             self._conv_wgrad(blk["c1"], x, a["g_1"], ihw, ihw)
-            self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask_bits=xbits, residual=None if blk["ds"] else g_out)
-            if blk["ds"]:
+            if blk["ds"] and blk["stride"] == 1:
+                # stride-1 shortcut (layer1 block 0): its data gradient goes first, as a plain GEMM into g_in; conv1's data gradient
+                # then adds it IN PLACE as its residual (read tile -> add -> mask -> write the same tile) -- two launches of the fast
+                # streaming kernel instead of a read-modify-write scatter epilogue (120 -> ~75 us at batch 8)
+                cd = blk["cd"]
+                self._conv_wgrad(cd, x, g_out, ihw, ohw)
+                Mo = B * ohw[0] * ohw[1]
+                self.launches += 1
+                self._before_write(g_in)
+                ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, ops.plain_geom(Mo, cd.ldd), C=g_in, ldc=cd.Cin,
+                          split=self.plane, wsplit=self.wplane)
+                self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask_bits=xbits, residual=g_in)
+            else:
+                self._conv_dgrad(blk["c1"], a["g_1"], ihw, ihw, g_in, mask_bits=xbits, residual=None if blk["ds"] else g_out)
+            if blk["ds"] and blk["stride"] != 1:
                 cd = blk["cd"]
                 self._conv_wgrad(cd, x, g_out, ihw, ohw)
                 st = blk["stride"]

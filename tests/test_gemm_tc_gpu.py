@@ -371,7 +371,7 @@ def test_one_bit_masks_conv_and_direct_store_paths(ops):
 
 @pytest.mark.parametrize("M,N,K,epi", [(534400, 256, 64, "r"), (534400, 256, 64, "rb"), (534400, 64, 256, "b"), (534400, 64, 64, ""), (133600, 512, 128, "r"),
                                        (133600, 512, 128, "rb"), (534400, 128, 256, ""), (128 * 148 * 4 + 13, 256, 128, "rb"), (300, 128, 64, "r"),
-                                       (128 * 5, 1024, 64, "rb")])
+                                       (128 * 5, 1024, 64, "rb"), (8400, 2048, 256, "d"), (8400, 1024, 128, "rd"), (33600, 1024, 256, "r")])
 def test_gemm_stream_kernel(M, N, K, epi):
     """gemm_stream_kernel (weights resident in shared memory, in-place chunk slots) on the layer1 / layer2 1x1 shapes at full size,
     a ragged last tile, fewer tiles than CTAs, four column parts: against fp32 PyTorch on sampled rows, and bit for bit against the
@@ -388,13 +388,16 @@ def test_gemm_stream_kernel(M, N, K, epi):
     if "b" in epi:
         kw.update(mask_bits=torch.randint(0, 256, (M, N // 8), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda(), ldmb=N // 8,
                   mask_scale=1.0)
+    if "d" in epi:                  # the transformer's epilogue: ReLU -> dropout (counter-based) -> + residual; no bit masks
+        kw.update(drop_p=0.1, seed=11, site=3, seed_ptr=torch.tensor([77], dtype=torch.int64, device="cuda"))
     outs, bits = [], []
     for mode in (2, 0):
         olds, oldp = ops.set_tc_stream(mode), ops.set_tc_persistent(0)
         try:
             C = torch.full((M + 2, N), 7.0, dtype=BF, device="cuda")
             ob = torch.full((M + 2, N // 8), 0x5A, dtype=torch.uint8, device="cuda")
-            ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, out_bits=ob, ldob=N // 8, **kw)
+            okw = {} if "d" in epi else dict(out_bits=ob, ldob=N // 8)
+            ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), bias=bias, relu=True, C=C, ldc=N, **okw, **kw)
             torch.cuda.synchronize()
         finally:
             ops.set_tc_stream(olds)
@@ -406,6 +409,13 @@ def test_gemm_stream_kernel(M, N, K, epi):
     assert float((C[M:].float() - 7.0).abs().max()) == 0 and int((bits[0][M:] != 0x5A).sum()) == 0
     rows = torch.cat([torch.arange(0, min(M, 300)), torch.randint(0, M, (2000,), generator=torch.Generator().manual_seed(6)),
                       torch.arange(max(0, M - 300), M)]).cuda()
+    if "d" in epi:                  # dropout: exact agreement with the one-tile kernel above; statistics of the kept fraction here
+        base = F.relu(A[rows].float() @ W.float().t() + bias)
+        got = C[rows].float() - (kw["residual"][rows].float() if "r" in epi else 0)
+        kept = (got.abs() > 1e-3) & (base > 0.05)
+        frac = float(kept.sum()) / float((base > 0.05).sum())
+        assert abs(frac - 0.9) < 0.01, frac
+        return
     ref = A[rows].float() @ W.float().t() + bias
     if "r" in epi:
         ref = ref + kw["residual"][rows].float()
