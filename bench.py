@@ -386,10 +386,12 @@ def main():
     # the call a user makes: training.fit over an iterable of HOST batches (pinned fp32 images + padded targets); every step
     # copies its batch host->device inside the timed region and reads the step's loss back (on_step hook -> float())
     Ke = K                                                              # same number of steps as the device-timed leg
-    host_losses = []
+    We = max(Wm, 3)                                                     # steps at the head of every fit() call that are not timed
+    host_losses, stamps = [], []
 
     def on_step(step, total_loss, log):
         host_losses.append(float(total_loss))                           # device -> host read of the step's loss
+        stamps.append(time.perf_counter())                              # = "step `step` is finished" (the read-back waited for it)
 
     def batches(n):
         for _ in range(n):
@@ -398,13 +400,21 @@ def main():
     import io
     with contextlib.redirect_stdout(io.StringIO()):                     # fit prints a progress line every 100 steps
         D.training.fit(model, batches(3), opt, cfg, 0, None, on_step=on_step)          # warm-up (captures the step graph)
-        passes = []
-        for _ in range(3):                                              # three passes of Ke steps each: host-side hiccups (this leg
-            barrier()                                                   # syncs with the host every step) show up as a slow pass
-            t0 = time.perf_counter()
-            D.training.fit(model, batches(Ke), opt, cfg, 0, None, on_step=on_step)
+        passes, calls = [], []
+        # Three fit() calls of We + Ke + 1 steps.  fit calls the hook of step i after step i+1 has been enqueued, and the hook's
+        # read-back (a synchronous copy on the compute stream) returns when everything enqueued so far has finished: hook We-1 returns
+        # at the end of step We, the last hook (called after the loop) at the end of step We+Ke -> the region between them holds exactly
+        # Ke full steps (copy in, compute, optimizer, loss out).  (Were the read-back to wait for its own step only, the same region
+        # would hold Ke + 1 steps: the figure can only err on the low side.)  The first batch's un-overlapped copy and the step-0
+        # progress print are warm-up; `whole_call_img_per_s` is the cross-check with everything included.
+        for _ in range(3):
             barrier()
-            t_pass = torch.tensor([time.perf_counter() - t0], device="cuda")
+            del stamps[:]
+            t_call = time.perf_counter()
+            D.training.fit(model, batches(We + Ke + 1), opt, cfg, 0, None, on_step=on_step)
+            t_pass = torch.tensor([stamps[We + Ke] - stamps[We - 1]], device="cuda")
+            barrier()
+            calls.append(world * B * (We + Ke + 1) / (time.perf_counter() - t_call))
             if world > 1:
                 dist.all_reduce(t_pass, op=dist.ReduceOp.MAX)
             passes.append(float(t_pass))
@@ -515,8 +525,8 @@ def main():
                        "cuda_graph": not args.no_graph, "targets_per_image": 20},
             "clocks": clocks, "gpu_launches": int(eng.launches_per_step * K),
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back (on_step hook -> float(); fit calls the hook of step i after step i+1 is enqueued)",
-                    "passes_img_per_s": [world * B * Ke / t for t in passes], "reported": "median of the three passes",
+                    "steps": Ke, "path": "training.fit(model, host_batches, optimizers, config, ...) with a per-step loss read-back (on_step hook -> float(); fit calls the hook of step i after step i+1 is enqueued); timed: `steps` full steps inside one fit() call of warm + steps + 1 steps (between two loss read-backs), median of three calls",
+                    "passes_img_per_s": [world * B * Ke / t for t in passes], "whole_call_img_per_s": calls, "reported": "median of the three passes",
                     "cpu_affinity": ("bound to the GPU-local CPUs (NVML affinity): " + str(len(bound)) + " cpus") if bound else "unchanged"},
             "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "matcher": matcher, "loss_after": loss_after,
         }))

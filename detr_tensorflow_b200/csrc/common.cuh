@@ -39,7 +39,7 @@ bool detrb_attn_fwd_tc_supported(const detrb_attn_fwd_t &p);
 int detrb_attn_fwd_tc(const detrb_attn_fwd_t &p, cudaStream_t stream);
 bool detrb_attn_bwd_tc_supported(const detrb_attn_bwd_t &p);
 int detrb_attn_bwd_tc(const detrb_attn_bwd_t &p, cudaStream_t stream);
-// tma_probe.cu: im2col tensor maps
+// tma_maps.cu: im2col tensor maps
 void *detrb_get_im2col_encode();
 int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
                           int upper_w, int upper_h, int stride, int pixels, int swizzle128, int channels = 64);

@@ -323,12 +323,6 @@ int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, 
 int detrb_attn_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint64_t seed, uint32_t site,
                             const uint64_t *seed_ptr, detrb_stream_t stream);
 
-/* test helper: one TMA im2col load (channelsPerPixel = 64, pixelsPerColumn = pixels) of NHWC bf16 x[B,H,W,C] dumped
- * raw into out[pixels*128 + 1] (last byte: 1 if the load completed).  Pins the cuTensorMapEncodeIm2col conventions. */
-int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int lower_w, int lower_h, int upper_w,
-                           int upper_h, int stride, int pixels, int swizzle128, int c0, int w, int h, int n,
-                           int off_w, int off_h, uint8_t *out, detrb_stream_t stream);
-
 /* ------------------------------------------------------------------------------------------
  * Rows either side of the train step
  * ------------------------------------------------------------------------------------------ */

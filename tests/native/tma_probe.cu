@@ -1,7 +1,8 @@
-// tma_probe.cu -- test helper: one TMA im2col load (cp.async.bulk.tensor.4d ... .im2col) of an NHWC bf16 tensor
-// into shared memory, dumped raw to global memory.  Used by tests/test_tma_im2col_gpu.py to pin down the coordinate /
-// bounding-box conventions of cuTensorMapEncodeIm2col that conv_tc.cu relies on.  Not on the product path.
-#include "common.cuh"
+// tma_probe.cu -- TEST INFRASTRUCTURE (built into tests/_harness_build/libdetrb_probe.so by __graft_entry__.build(), linked against
+// libdetrb.so; not part of the product library): one TMA im2col load (cp.async.bulk.tensor.4d ... .im2col) of an NHWC bf16 tensor
+// into shared memory, dumped raw to global memory.  tests/test_tma_im2col_gpu.py uses it to pin down the coordinate / bounding-box
+// conventions of cuTensorMapEncodeIm2col that the convolution kernels rely on.
+#include "../../detr_tensorflow_b200/csrc/common.cuh"
 #include <cuda.h>
 
 namespace {
@@ -41,45 +42,10 @@ __global__ void tma_im2col_probe_kernel(const __grid_constant__ CUtensorMap map,
     if (threadIdx.x == 0) out[bytes] = done ? 1 : 0;
 }
 
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                   const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 }  // namespace
 
-void *detrb_get_im2col_encode()
-{
-    static void *fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        cudaDriverEntryPointQueryResult q;
-        void *ptr = nullptr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = ptr;
-    }
-    return fn;
-}
-
-// NHWC bf16 tensor [B,H,W,C] -> im2col tensor map (channelsPerPixel = channels, pixelsPerColumn = pixels;
-// swizzle128: 0 none, 1 128-byte, 2 32-byte)
-int detrb_make_im2col_map(void *map_out, const void *x, int B, int H, int W, int C, int ldc, int lower_w, int lower_h,
-                          int upper_w, int upper_h, int stride, int pixels, int swizzle128, int channels)
-{
-    EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(detrb_get_im2col_encode());
-    if (!fn) DETRB_FAIL(DETRB_E_CUDA, "cuTensorMapEncodeIm2col not available");
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)ldc * 2, (cuuint64_t)W * ldc * 2, (cuuint64_t)H * W * ldc * 2};
-    int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = fn(reinterpret_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides,
-                    lower, upper, (cuuint32_t)channels, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) DETRB_FAIL(DETRB_E_CUDA, "cuTensorMapEncodeIm2col failed: %d", (int)r);
-    return DETRB_OK;
-}
-
+/* one TMA im2col load (channelsPerPixel = 64, pixelsPerColumn = pixels) of NHWC bf16 x[B,H,W,C] dumped raw into
+ * out[pixels*128 + 1] (last byte: 1 if the load completed) */
 extern "C" int detrb_tma_im2col_probe(const detrb_bf16 *x, int B, int H, int W, int C, int lower_w, int lower_h, int upper_w,
                                       int upper_h, int stride, int pixels, int swizzle128, int c0, int w, int h, int n,
                                       int off_w, int off_h, uint8_t *out, detrb_stream_t stream)

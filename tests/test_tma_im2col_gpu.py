@@ -10,11 +10,33 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+_PROBE = None
+
+
+def _probe_lib():
+    """tests/_harness_build/libdetrb_probe.so (tests/native/tma_probe.cu, built by __graft_entry__.build()): test infrastructure,
+    linked against the product library"""
+    global _PROBE
+    if _PROBE is None:
+        import os
+        from detr_tensorflow_b200 import _lib
+        _lib.lib()                                                   # libdetrb.so first (the probe library resolves its symbols from it)
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "_harness_build", "libdetrb_probe.so")
+        if not os.path.exists(so):
+            import sys
+            sys.path.insert(0, os.path.dirname(here))
+            import __graft_entry__ as g
+            g.build_test_probe(_lib._SO)
+        _PROBE = ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL)
+    return _PROBE
+
+
 def probe(x, lower, upper, stride, pixels, swz, c0, w, h, n, off_w, off_h):
     from detr_tensorflow_b200 import _lib
     B, H, W, C = x.shape
     out = torch.zeros(pixels * 128 + 1, dtype=torch.uint8, device="cuda")
-    _lib.check(_lib.lib().detrb_tma_im2col_probe(ctypes.c_void_p(x.data_ptr()), B, H, W, C, lower[0], lower[1], upper[0], upper[1],
+    _lib.check(_probe_lib().detrb_tma_im2col_probe(ctypes.c_void_p(x.data_ptr()), B, H, W, C, lower[0], lower[1], upper[0], upper[1],
                                                  stride, pixels, swz, c0, w, h, n, off_w, off_h, ctypes.c_void_p(out.data_ptr()),
                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
