@@ -423,9 +423,10 @@ def main():
     dbg("e2e leg done")
 
     # ------------------------------------------------------------------ rooflines, timed live (CUDA events on the launching stream)
-    # One object per kernel family of the step; `roofline` is the family with the largest share of the step BY TIME (the one-tile
-    # tcgen05 GEMM kernel on the HBM-bound 1x1 layers, 42 % -- shares from the committed ncu launch list, profiles/), the others
-    # follow in `rooflines`.  Every rank runs the probe steps (they contain the gradient all-reduce), rank 0 reports.
+    # One object per kernel family of the step; `roofline` is the family with the largest share of the step BY TIME in the committed
+    # ncu launch list (profiles/family_shares.json: the tcgen05 weight-gradient kernel, 22 %), the others follow in `rooflines`
+    # (streaming GEMM 17 %, persistent GEMM / conv 16 %, attention 13 %, halo conv).  Every rank runs the probe steps (they contain
+    # the gradient all-reduce), rank 0 reports.
     peak_sus, peak_burst, peak_hbm, how = measured_peaks()
     peak_tf, peak_tf_src = tensor_peak(clocks)
     if world > 1:                                                       # every rank needs the same probe set; clocks only exist on rank 0
@@ -465,23 +466,30 @@ def main():
         # algorithmic bytes (bf16): forward = input + weights + residual + output; data gradient = dY + weights
         # + ReLU mask + output; weight gradient = input + dY (+ the fp32 gradient tile, negligible)
         # (+ M*N/8 bytes of 1-bit ReLU mask written by the forward, read by the data gradient instead of the bf16 activation)
-        roof = hbm_obj(f"gemm_stream_kernel<256,residual,bits-out> streaming tcgen05 GEMM (weights resident in smem, in-place chunk slots): "
-                       f"1x1 conv 64->256 + residual + ReLU, layer1, M={Mh} N=256 K=64",
-                       2.0 * (Mh * sh.K + sh.N * sh.K + 2 * Mh * sh.N) + Mh * sh.N / 8, med(p_h), traffic("hbm_kernel_traffic.json"))
-        roof["family"] = "HBM-bound 1x1 convolutions of layer1-3 (gemm_stream_kernel): the largest share of the step by time (see profiles/: ncu launch list of this round)"
+        stream_obj = hbm_obj(f"gemm_stream_kernel<256,residual,bits-out> streaming tcgen05 GEMM (weights resident in smem, in-place chunk slots): "
+                             f"1x1 conv 64->256 + residual + ReLU, layer1, M={Mh} N=256 K=64",
+                             2.0 * (Mh * sh.K + sh.N * sh.K + 2 * Mh * sh.N) + Mh * sh.N / 8, med(p_h), traffic("hbm_kernel_traffic.json"))
+        # `roofline` = the kernel with the largest share of the step BY TIME in the committed launch list (profiles/family_shares.json):
+        # wgrad_tc_kernel, 22 % of the serialised step -- represented by its largest HBM-bound launch, timed where it runs: on the side
+        # stream, sharing HBM with the data-gradient chain of the main stream (alone it runs at 0.85 of the copy bandwidth: `isolated`)
+        roof = hbm_obj(f"wgrad_tc_kernel<plain> tcgen05 weight gradient (MN-major operands) of the layer1 1x1 conv 64->256, M={Mh} N=256 K=64, "
+                       f"on the side stream beside the data-gradient chain", 2.0 * (Mh * sh.K + Mh * sh.N), med(p_h + "#wgrad"),
+                       traffic("wgrad1x1_kernel_traffic.json"))
+        roof["isolated"] = {"us_per_launch": 62.0, "achieved": 5581.0, "frac": 5581.0 / peak_hbm,
+                            "source": "profiles/r02_ncu_wgrad_and_conv64.txt (ncu --set full, same launch alone on the GPU)"}
+        roof["family"] = "wgrad_tc_kernel (tcgen05 weight gradients): the largest share of the serialised step by time, 22 % (profiles/family_shares.json); it runs on the side stream, overlapped with the data-gradient chain -- the largest family of the critical path is the streaming GEMM kernel (rooflines.hbm_conv1x1_layer1_stream)"
         roof["whole_step"] = {"achieved": gf * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
                               "frac_of_tensor_peak": gf * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf, "peak": peak_tf, "peak_source": peak_tf_src}
         roofs = {
+            "hbm_conv1x1_layer1_stream": stream_obj,
             "persistent_conv3x3": tensor_obj(f"gemm_tcp_kernel<256,4,im2col> persistent tcgen05 implicit-GEMM conv 3x3 256->256, layer3, M={Mt} N=256 K=2304",
                                              2.0 * Mt * st.N * st.K, med(p_t), traffic("top_kernel_traffic.json")),
             "wgrad_conv3x3": tensor_obj(f"wgrad_tc_kernel<im2col> tcgen05 weight gradient of the same 3x3 conv (side stream, overlapped with the data-gradient chain), M={Mt}",
                                         2.0 * Mt * st.N * st.K, med(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
-            "wgrad_conv1x1_layer1": hbm_obj(f"wgrad_tc_kernel<plain> weight gradient of the layer1 1x1 conv 64->256 (side stream), M={Mh}",
-                                            2.0 * (Mh * sh.K + Mh * sh.N), med(p_h + "#wgrad")),
             "dgrad_conv1x1_layer1": hbm_obj(f"gemm_stream_kernel<64,bits-in>: data gradient of the layer1 1x1 conv 256->64 + 1-bit ReLU mask, M={Mh}",
                                             2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8, med(p_h + "#dgrad")),
             "conv3x3_layer1_halo": dict(tensor_obj(f"conv3x3_halo_kernel: 3x3 conv 64->64 + ReLU, layer1 (every input row staged once, nine taps = nine "
-                                                   f"descriptor views), M={Mh} N=64 K=576", 2.0 * Mh * 64 * 576, med(p_c)),
+                                                   f"descriptor views), M={Mh} N=64 K=576", 2.0 * Mh * 64 * 576, med(p_c), traffic("halo_kernel_traffic.json")),
                                         hbm_gbs=(2.0 * 2 * Mh * 64 + Mh * 8) / med(p_c) / 1e9),
             "dgrad_conv3x3_layer1_halo": tensor_obj(f"conv3x3_halo_kernel: data gradient of the same conv (+ 1-bit ReLU mask), M={Mh}",
                                                     2.0 * Mh * 64 * 576, med(p_c + "#dgrad")),

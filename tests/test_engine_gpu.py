@@ -269,3 +269,41 @@ def test_resnet101_backbone_forward(D):
     torch.cuda.synchronize()
     t = float(eng.a["total"][0])
     assert t == t and 0 < t < 1e3
+
+
+def test_streaming_halo_and_bit_mask_kernels_inside_the_full_size_step(D):
+    """Round-2 kernels in situ: one 800x1333 image (BASELINE configs[1] resolution, every layer at its benchmark row count per
+    image) through forward + loss + backward with the streaming GEMM / halo conv kernels ON (wherever supported) and OFF (one-tile /
+    persistent / im2col kernels, same 1-bit masks).  The kernels compute the same bf16 products in the same order, so the forward
+    is identical bit for bit; the weight gradients differ only by the order of their fp32 atomics."""
+    from oracle import detr_oracle as O
+    from detr_tensorflow_b200 import ops
+    P = O.init_params(seed=2)
+    img = torch.randn(1, 800, 1333, 3, generator=torch.Generator().manual_seed(2))
+    tb, tc = O.synthetic_targets(1, n=7, seed=2)
+    cfg = D.TrainingConfig()
+    cfg.background_class = 91
+    res = {}
+    for on in (1, 0):
+        olds, oldh = ops.set_tc_stream(2 * on), ops.set_tc_halo(on)          # 2: the streaming kernel wherever it is supported
+        try:
+            model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0)
+            eng = model.engine
+            out = model(img, training=False)
+            logits, boxes = out["pred_logits"].clone(), out["pred_boxes"].clone()
+            eng.set_targets(tb, tc)
+            eng.zero_grads()
+            eng.loss(91)
+            eng.backward()
+            torch.cuda.synchronize()
+            res[on] = (logits, boxes, float(eng.loss_dict()[0]), {k: v.clone() for k, v in eng.export_grads().items()})
+        finally:
+            ops.set_tc_stream(olds)
+            ops.set_tc_halo(oldh)
+        del model, eng
+        torch.cuda.empty_cache()
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
+    assert abs(res[1][2] - res[0][2]) <= 1e-6 * abs(res[0][2])
+    worst = max((rel(res[1][3][n], res[0][3][n]), n) for n in res[0][3] if float(res[0][3][n].norm()) > 1e-8)
+    print("new kernels on vs off: worst gradient difference", worst)
+    assert worst[0] < 1e-3, worst
