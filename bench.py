@@ -439,10 +439,22 @@ def main():
         eng.train_step(91, cfg.gradient_norm_clipping)
     torch.cuda.synchronize()
     times = {k: sorted(a.elapsed_time(b) for a, b in v) for k, v in eng.probe_events.items()}
+    # the weight gradients once more with the side stream off (same step, kernels serialised on the main stream): a kernel's own
+    # duration, which is what a roofline fraction describes -- beside the data-gradient chain the same launch shares HBM / SMs with
+    # another kernel and takes 1.5-1.7x as long (both figures are reported)
+    eng.probe_names = (p_t + "#wgrad", p_h + "#wgrad")
+    eng.probe_events = {}
+    saved_overlap, eng.overlap_wgrad = eng.overlap_wgrad, False
+    for _ in range(3):
+        eng.train_step(91, cfg.gradient_norm_clipping)
+    torch.cuda.synchronize()
+    eng.overlap_wgrad = saved_overlap
+    times_alone = {k: sorted(a.elapsed_time(b) for a, b in v) for k, v in eng.probe_events.items()}
     eng.probe_names = None
     roof, roofs = None, None
     if rank == 0:
         med = lambda k: times[k][len(times[k]) // 2] * 1e-3             # seconds
+        med_alone = lambda k: times_alone[k][len(times_alone[k]) // 2] * 1e-3
         gf = TRAIN_GFLOP_PER_IMAGE[args.backbone]
 
         def traffic(fname):
@@ -472,11 +484,12 @@ def main():
         # `roofline` = the kernel with the largest share of the step BY TIME in the committed launch list (profiles/family_shares.json):
         # wgrad_tc_kernel, 22 % of the serialised step -- represented by its largest HBM-bound launch, timed where it runs: on the side
         # stream, sharing HBM with the data-gradient chain of the main stream (alone it runs at 0.85 of the copy bandwidth: `isolated`)
-        roof = hbm_obj(f"wgrad_tc_kernel<plain> tcgen05 weight gradient (MN-major operands) of the layer1 1x1 conv 64->256, M={Mh} N=256 K=64, "
-                       f"on the side stream beside the data-gradient chain", 2.0 * (Mh * sh.K + Mh * sh.N), med(p_h + "#wgrad"),
-                       traffic("wgrad1x1_kernel_traffic.json"))
-        roof["isolated"] = {"us_per_launch": 62.0, "achieved": 5581.0, "frac": 5581.0 / peak_hbm,
-                            "source": "profiles/r02_ncu_wgrad_and_conv64.txt (ncu --set full, same launch alone on the GPU)"}
+        roof = hbm_obj(f"wgrad_tc_kernel<plain> tcgen05 weight gradient (MN-major operands) of the layer1 1x1 conv 64->256, M={Mh} N=256 K=64 "
+                       f"(timed inside a train step with the weight-gradient side stream off: the kernel alone on the GPU)",
+                       2.0 * (Mh * sh.K + Mh * sh.N), med_alone(p_h + "#wgrad"), traffic("wgrad1x1_kernel_traffic.json"))
+        roof["beside_data_gradient_chain"] = {"us_per_launch": med(p_h + "#wgrad") * 1e6,
+                                              "note": "the same launch as it runs in the timed step: on the side stream, concurrently with the data-gradient "
+                                                      "kernel of the main stream that reads the same dY (together they move ~690 MB in this time)"}
         roof["family"] = "wgrad_tc_kernel (tcgen05 weight gradients): the largest share of the serialised step by time, 22 % (profiles/family_shares.json); it runs on the side stream, overlapped with the data-gradient chain -- the largest family of the critical path is the streaming GEMM kernel (rooflines.hbm_conv1x1_layer1_stream)"
         roof["whole_step"] = {"achieved": gf * 1e9 * B * world * K / (ms / 1e3) / 1e12, "unit": "TFLOP/s (all GPUs)",
                               "frac_of_tensor_peak": gf * 1e9 * B * K / (ms / 1e3) / 1e12 / peak_tf, "peak": peak_tf, "peak_source": peak_tf_src}
@@ -484,8 +497,9 @@ def main():
             "hbm_conv1x1_layer1_stream": stream_obj,
             "persistent_conv3x3": tensor_obj(f"gemm_tcp_kernel<256,4,im2col> persistent tcgen05 implicit-GEMM conv 3x3 256->256, layer3, M={Mt} N=256 K=2304",
                                              2.0 * Mt * st.N * st.K, med(p_t), traffic("top_kernel_traffic.json")),
-            "wgrad_conv3x3": tensor_obj(f"wgrad_tc_kernel<im2col> tcgen05 weight gradient of the same 3x3 conv (side stream, overlapped with the data-gradient chain), M={Mt}",
-                                        2.0 * Mt * st.N * st.K, med(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
+            "wgrad_conv3x3": dict(tensor_obj(f"wgrad_tc_kernel<im2col> tcgen05 weight gradient of the same 3x3 conv, M={Mt} (side stream off: the kernel alone)",
+                                             2.0 * Mt * st.N * st.K, med_alone(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
+                                  us_beside_data_gradient_chain=med(p_t + "#wgrad") * 1e6),
             "dgrad_conv1x1_layer1": hbm_obj(f"gemm_stream_kernel<64,bits-in>: data gradient of the layer1 1x1 conv 256->64 + 1-bit ReLU mask, M={Mh}",
                                             2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8, med(p_h + "#dgrad")),
             "conv3x3_layer1_halo": dict(tensor_obj(f"conv3x3_halo_kernel: 3x3 conv 64->64 + ReLU, layer1 (every input row staged once, nine taps = nine "

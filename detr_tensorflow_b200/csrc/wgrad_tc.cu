@@ -43,7 +43,7 @@ template <bool IM2COL, bool SPLIT>
 __global__ void __launch_bounds__(WTHREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_y2, const __grid_constant__ CUtensorMap map_x2, const detrb_wgrad_t p,
-                const int pix_per_split, const int stem_mask)
+                const int pix_per_split, const int stem_mask, const int interleave)
 {
     constexpr int KT = WK;                                              // k columns of this CTA's dW tile (TMEM columns)
     constexpr int STG = WSTAGES;
@@ -59,9 +59,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * KT, n0 = blockIdx.y * WN;
-    const int m_begin = blockIdx.z * pix_per_split;
-    const int m_end = min(p.M, m_begin + pix_per_split);
-    const int nsteps1 = (m_end - m_begin + WP - 1) / WP;    // >= 1 by construction of the grid
+    // pixel blocks of this split: a contiguous range, or (interleave) every gridDim.z-th 64-pixel block -- then all CTAs together sweep
+    // the pixel range front to back like the data-gradient kernel that runs beside this one on the main stream and reads the same
+    // dY: whichever of the two comes second finds it in L2 (the reduction over pixels does not care about the order)
+    const int m_begin = interleave ? (int)blockIdx.z * WP : (int)blockIdx.z * pix_per_split;
+    const int m_step = interleave ? (int)gridDim.z * WP : WP;
+    const int m_end = interleave ? p.M : min(p.M, m_begin + pix_per_split);
+    const int nsteps1 = (m_end - m_begin + m_step - 1) / m_step;    // >= 1 by construction of the grid
     const int nsteps = SPLIT ? 3 * nsteps1 : nsteps1;
 
     // bias gradient (column sums of dY) fused: the k-tile-0 CTAs' otherwise idle epilogue warps add up the dY boxes of every stage
@@ -100,7 +104,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 const int part = SPLIT ? st / nsteps1 : 0;
                 const CUtensorMap *py = (SPLIT && part == 1) ? &map_y2 : &map_y;
                 const CUtensorMap *px = (SPLIT && part == 2) ? &map_x2 : &map_x;
-                const int m = m_begin + (st - part * nsteps1) * WP;
+                const int m = m_begin + (st - part * nsteps1) * m_step;
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), STG_BYTES);
                 const uint32_t dst = smem_base + stage * STG_BYTES;
@@ -293,14 +297,18 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     }
     dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
     const int stem_mask = p.k_mask ? 1 : 0;
+    // interleaved pixel blocks (env DETRB_WGRAD_INTERLEAVE=1): measured on the full step, no difference (651.2 / 651.5 vs 647.4 / 653.2
+    // img/s) -- the two kernels do not stay in lockstep -- so contiguous ranges remain the default
+    static int interleave = -1;
+    if (interleave < 0) { const char *e = getenv("DETRB_WGRAD_INTERLEAVE"); interleave = e ? atoi(e) : 0; }
     if (plain && !sp) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask);
+        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask, interleave);
     } else if (!sp) {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0);
+        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0, interleave);
     } else if (plain) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask);
+        DETRB_LAUNCH((wgrad_tc_kernel<false, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask, interleave);
     } else {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0);
+        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0, interleave);
     }
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;
