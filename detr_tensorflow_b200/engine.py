@@ -1160,7 +1160,22 @@ class Engine:
             self._lrs_host = key
 
     def set_enabled(self, backbone, transformers, nlayers=False):
-        self.group_enabled[:3] = torch.tensor([int(backbone), int(transformers), int(nlayers)], dtype=torch.uint8)
+        key = (int(bool(backbone)), int(bool(transformers)), int(bool(nlayers)))
+        if getattr(self, "_enabled_host", None) != key:        # (a host->device copy from pageable memory blocks the host)
+            self.group_enabled[:3] = torch.tensor(key, dtype=torch.uint8)
+            self._enabled_host = key
+
+    def fused_step(self, background_class, clipnorm):
+        """forward + losses + backward + gradient all-reduce + Adam for every enabled group + weight refresh on the staged batch
+        as ONE replayed launch sequence (capture_train_step): what training.fit runs when there is no gradient accumulation.  The
+        capture does not execute anything, so the caller must have run one step through grads_step / apply_group before (kernel
+        attribute set-up, NCCL communicator); group flags and learning rates are read from device memory at replay time."""
+        key = (self.plan_key, int(background_class), float(clipnorm), self.normalisers is not None, self.u8_input,
+               getattr(self, "input_method", None), self._distributed())
+        if getattr(self, "_fs_key", None) != key:
+            self._fs_replay = self.capture_train_step(background_class, clipnorm, warmup=0)
+            self._fs_key = key
+        self._fs_replay()
 
     def apply_group(self, name, grads_arena, clipnorm):
         """Adam apply for ONE group (the reference applies its three optimizers one after the other,

@@ -57,6 +57,28 @@ def run_train_step(model, images, t_bbox, t_class, optimizers, config):
     return m_outputs, total_loss, log, gradient_steps
 
 
+def run_train_and_apply_step(model, images, t_bbox, t_class, optimizers, config):
+    """run_train_step + aggregate_grad_and_apply for every group (training.py:9-25 + 53-54, optimizers.py:137-163 without
+    accumulation) as one replayed CUDA graph: the optimizer runs inside the graph, beside the last weight gradient of the
+    backward pass.  Used by fit when config.target_batch is None; same results as the two calls it replaces."""
+    eng = model.engine
+    t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
+    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device))
+    eng.set_global_normalisers(t_bbox_d)
+    eng.set_lrs(float(config.backbone_lr), float(config.transformers_lr), float(config.nlayers_lr))
+    eng.set_enabled(bool(config.train_backbone), bool(config.train_transformers), bool(getattr(config, "train_nlayers", False)))
+    eng.fused_step(int(config.background_class), float(config.gradient_norm_clipping))
+    m_outputs = eng.outputs()
+    total_loss, log = eng.loss_dict(snapshot=True)
+    log = dict(log)
+    for g in GROUPS:
+        log.update({f"{g}_lr": optimizers[f"{g}_optimizer"]._serialize_hyperparameter("learning_rate")})
+        if f"{g}_gradients" not in optimizers:
+            from .optimizers import _group_views
+            optimizers[f"{g}_gradients"] = _group_views(eng, g, eng.grads)
+    return m_outputs, total_loss, log
+
+
 def run_val_step(model, images, t_bbox, t_class, config):
     """training.py:28-32"""
     return _forward_loss(model, images, t_bbox, t_class, config, False, 1.0, False)
@@ -131,12 +153,23 @@ def fit(model, train_dt, optimizers, config, epoch_nb, class_names, on_step=None
     that is already finishing while the GPU works on the next one, instead of leaving the GPU idle until the host comes back."""
     t = None
     pending = None
+    eng = model.engine
+    # without gradient accumulation the step and the optimizer are one replayed graph (run_train_and_apply_step); the first step of
+    # a process goes through the two reference calls (it sets up every kernel the graph contains)
+    fused_ok = (config.target_batch is None and eng.device.type == "cuda" and getattr(config, "use_cuda_graph", True)
+                and getattr(config, "fused_optimizer_step", True))
     for epoch_step, (images, t_bbox, t_class) in enumerate(_Prefetcher(train_dt, model.engine.device)):
-        m_outputs, total_loss, log, gradient_steps = run_train_step(model, images, t_bbox, t_class, optimizers, config)
-        if config.log:
-            _train_log_hook(images, t_bbox, t_class, m_outputs, config, config.global_step, class_names, prefix="train/")
-        for name in gradient_steps:
-            aggregate_grad_and_apply(name, optimizers, gradient_steps[name]["gradients"], epoch_step, config)
+        if fused_ok and getattr(eng, "_split_step_done", False):
+            m_outputs, total_loss, log = run_train_and_apply_step(model, images, t_bbox, t_class, optimizers, config)
+            if config.log:
+                _train_log_hook(images, t_bbox, t_class, m_outputs, config, config.global_step, class_names, prefix="train/")
+        else:
+            m_outputs, total_loss, log, gradient_steps = run_train_step(model, images, t_bbox, t_class, optimizers, config)
+            if config.log:
+                _train_log_hook(images, t_bbox, t_class, m_outputs, config, config.global_step, class_names, prefix="train/")
+            for name in gradient_steps:
+                aggregate_grad_and_apply(name, optimizers, gradient_steps[name]["gradients"], epoch_step, config)
+            eng._split_step_done = True
         model.engine._ensure_weights()      # one refresh of the bf16 weight copies for all groups, enqueued before any host sync
         if on_step is not None:
             if pending is not None:

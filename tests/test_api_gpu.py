@@ -189,3 +189,38 @@ def test_checkpoint_roundtrip_and_resume_on_device(D, tmp_path):
     D.training.fit(model2, [(img, tb, tc)], opt2, cfg2, 0, None)
     torch.cuda.synchronize()
     assert rel(e2.params, e1.params) < 1e-6                       # identical up to the summation order of the gradient atomics
+
+
+def test_fit_fused_step_equals_the_two_reference_calls(D):
+    """training.fit without gradient accumulation replays ONE graph per step (run_train_and_apply_step: forward, losses, backward,
+    Adam of every enabled group, weight refresh); with config.fused_optimizer_step = False it makes the reference's two calls
+    (run_train_step + aggregate_grad_and_apply per group).  Same arithmetic: losses equal to rounding (weight gradients are summed
+    with fp32 atomics; after an optimizer step trajectories may differ by a flipped near-tie assignment, see
+    test_pipeline_gpu.py::test_uint8_frames_through_model_and_fit), the frozen group stays frozen, step counters advance alike."""
+    from oracle import detr_oracle as O
+    P = O.init_params(seed=5, num_encoder_layers=1, num_decoder_layers=2)
+    img = torch.randn(2, 96, 128, 3, generator=torch.Generator().manual_seed(5))
+    tb, tc = O.synthetic_targets(2, n=4, seed=5)
+    out = {}
+    for fused in (True, False):
+        cfg = D.TrainingConfig()
+        cfg.background_class, cfg.batch_size, cfg.target_batch = 91, 2, None
+        cfg.train_backbone, cfg.train_transformers = False, True            # the backbone group is computed but not applied
+        cfg.fused_optimizer_step = fused
+        model = D.get_detr_model(cfg, include_top=True, params=P, dropout=0.0, num_encoder_layers=1, num_decoder_layers=2)
+        opt = D.setup_optimizers(model, cfg)
+        seen, logs = [], []
+        D.training.fit(model, [(img, tb, tc)] * 4, opt, cfg, 0, None, on_step=lambda s, t, l: (seen.append(float(t)), logs.append(l)))
+        eng = model.engine
+        out[fused] = (seen, {k: v.clone() for k, v in eng.export_params().items()}, eng.steps[:3].cpu().tolist(), logs[-1])
+    a, b = out[True], out[False]
+    print("fused", a[0], "split", b[0])
+    assert len(a[0]) == 4 and abs(a[0][0] - b[0][0]) <= 5e-6 * abs(b[0][0])
+    assert all(abs(x - y) <= 5e-3 * abs(y) for x, y in zip(a[0], b[0])), (a[0], b[0])
+    assert a[2] == b[2] and a[2][0] == 0 and a[2][1] == 4                    # Adam iterations: backbone 0, transformers 4
+    for n in P:
+        if n.startswith("backbone/"):
+            assert torch.equal(a[1][n], b[1][n])                             # frozen group untouched in both paths
+    moved = max(float((a[1][n].float() - torch.as_tensor(P[n]).float().to(a[1][n].device)).abs().max()) for n in a[1] if not n.startswith("backbone/"))
+    assert moved > 0
+    assert set(a[3].keys()) == set(b[3].keys())                              # same log keys (losses + learning rates)
