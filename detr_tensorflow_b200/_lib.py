@@ -17,7 +17,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
 _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_maps.cu", "wgrad_tc.cu", "pipeline.cu", "attention_tc.cu", "conv_halo.cu"]
 _lib = None
-ABI_VERSION = 210          # detrb_version() of the library these ctypes structures / call sites were written for
+ABI_VERSION = 220          # detrb_version() of the library these ctypes structures / call sites were written for
 
 EXPORTS = [
     "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
@@ -58,7 +58,7 @@ class IgemmParams(Structure):
         ("mask_scale", c_float), ("relu", c_int), ("sigmoid", c_int), ("drop_p", c_float), ("seed", c_uint64),
         ("site", c_uint32), ("seed_ptr", c_void_p), ("C", c_void_p), ("ldc", c_int), ("Cf", c_void_p), ("ldcf", c_int),
         ("out_stride", c_int), ("SH", c_int), ("SW", c_int), ("accumulate", c_int), ("a_kb_rows", c_int),
-        ("split", c_int64), ("wsplit", c_int64), ("mask_bits", c_void_p), ("ldmb", c_int), ("out_bits", c_void_p), ("ldob", c_int),
+        ("split", c_int64), ("wsplit", c_int64), ("mask_bits", c_void_p), ("ldmb", c_int), ("out_bits", c_void_p), ("ldob", c_int), ("scratch", c_void_p),
     ]
 
 

@@ -25,6 +25,9 @@ bool detrb_gemm_tc_enabled();
 bool detrb_gemm_tc_conv_enabled();
 int detrb_gemm_tc_kind(const detrb_igemm_t &p);
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream);
+// elementwise.cu: stride-2 scatter of densely written parity-class / shortcut results (detrb_igemm_t.scratch)
+int detrb_scatter_s2(const bf16 *const src[4], bf16 *dst, int ldc, const uint8_t *mask_bits, int ldmb, int B, int H, int W, int C,
+                     int accumulate, cudaStream_t stream);
 // conv_halo.cu (3x3 / 64-channel convolution, every input pixel staged once)
 bool detrb_conv_halo_supported(const detrb_igemm_t &p);
 int detrb_conv_halo(const detrb_igemm_t &p, cudaStream_t stream);

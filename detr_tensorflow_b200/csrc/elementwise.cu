@@ -133,6 +133,41 @@ ln_bwd_kernel(const bf16 *dy, const bf16 *dy2, const bf16 *x, const float *gamma
     }
 }
 
+// ---------------------------------------------------------------- stride-2 scatter of densely written GEMM results
+// dst[b, y, x, :] (op)= mask(src_class(y & 1, x & 1)[b, y >> 1, x >> 1, :]); the four parity classes are compact [B, A_c, B_c, C] tensors
+// (A_c = (H - py + 1) / 2, B_c = (W - px + 1) / 2), a null class leaves its pixels untouched.  One thread per 8 channels of one pixel.
+__global__ void __launch_bounds__(256)
+scatter_s2_kernel(const bf16 *s0, const bf16 *s1, const bf16 *s2, const bf16 *s3, bf16 *dst, int ldc, const uint8_t *mask_bits, int ldmb,
+                  int H, int W, int C8, int accumulate)
+{
+    pdl_trigger();
+    pdl_wait();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * C8) return;
+    const int x = t / C8, c8 = t - x * C8, y = blockIdx.y, b = blockIdx.z;
+    const int py = y & 1, px = x & 1;
+    const bf16 *src = py ? (px ? s3 : s2) : (px ? s1 : s0);
+    if (!src) return;
+    const int Ac = (H - py + 1) >> 1, Bc = (W - px + 1) >> 1;
+    const size_t spix = ((size_t)b * Ac + (y >> 1)) * Bc + (x >> 1), dpix = ((size_t)b * H + y) * W + x;
+    uint4 u = *reinterpret_cast<const uint4 *>(src + spix * (size_t)(C8 * 8) + c8 * 8);
+    float v[8];
+    sp_unpack8(u, v);
+    bf16 *d = dst + dpix * ldc + c8 * 8;
+    if (mask_bits) {
+        const uint32_t m = mask_bits[dpix * ldmb + c8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = ((m >> i) & 1u) ? v[i] : 0.f;
+    }
+    if (accumulate) {
+        float o[8];
+        sp_unpack8(*reinterpret_cast<const uint4 *>(d), o);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] += o[i];
+    }
+    *reinterpret_cast<uint4 *>(d) = sp_pack8(v);
+}
+
 // ---------------------------------------------------------------- simple vector kernels
 __global__ void add_rowbcast_kernel(const bf16 *x, const bf16 *pos, bf16 *out, int64_t nvec, int64_t svec, long long split)
 {
@@ -497,5 +532,16 @@ extern "C" int detrb_dropout_mask(uint8_t *out, int M, int N, float drop_p, uint
     int64_t total = (int64_t)M * N;
     DETRB_LAUNCH(dropout_mask_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, out, M, N, drop_p, seed, site, seed_ptr);
     DETRB_CHECK_LAUNCH("dropout_mask_kernel");
+    return DETRB_OK;
+}
+
+int detrb_scatter_s2(const bf16 *const src[4], bf16 *dst, int ldc, const uint8_t *mask_bits, int ldmb, int B, int H, int W, int C,
+                     int accumulate, cudaStream_t stream)
+{
+    DETRB_REQUIRE(dst && C % 8 == 0 && ldc % 8 == 0 && B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "detrb_scatter_s2: bad args");
+    const int C8 = C / 8;
+    DETRB_LAUNCH(scatter_s2_kernel, dim3((unsigned)ceil_div(W * C8, 256), (unsigned)H, (unsigned)B), dim3(256), 0, stream, src[0], src[1], src[2],
+                 src[3], dst, ldc, mask_bits, ldmb, H, W, C8, accumulate);
+    DETRB_CHECK_LAUNCH("scatter_s2_kernel");
     return DETRB_OK;
 }

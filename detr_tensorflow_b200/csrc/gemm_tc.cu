@@ -1382,9 +1382,21 @@ static int dispatch_tc(const detrb_igemm_t &p, int bn, cudaStream_t stream, cons
 // Data gradient of a 3x3 / stride-2 / pad-1 convolution as four dense stride-1 sub-convolutions over dY, one per output
 // parity class (py, px): pixel (2a+py, 2b+px) only sees the taps kh with (py + 1 - kh) even -- {1} for py = 0, {2, 0} for
 // py = 1 (dY rows a, a+1) -- so no multiply-by-zero work is issued (the generic transposed gather wastes 75 %).
+// can the scatter go through the dense workspace (detrb_igemm_t.scratch) and one coalesced pass?
+static bool scratch_scatter_ok(const detrb_igemm_t &p)
+{
+    return p.scratch && !p.split && p.C && !p.Cf && !p.mask && !p.out_bits && !p.residual && !p.sigmoid && !(p.drop_p > 0.f) && !p.bias &&
+           !p.relu && p.mask_scale == 1.f && (((uintptr_t)p.scratch) & 15) == 0 && p.N % 8 == 0 && p.ldc % 8 == 0 && (((uintptr_t)p.C) & 15) == 0;
+}
+
 static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
 {
     static const int kmap[2][2] = {{1, -1}, {2, 0}};       // [parity][window offset] -> original tap index along that axis
+    // with a workspace: the four classes are written densely (fast TMA-store kernels) and scattered by one coalesced pass that also
+    // applies the bit mask; without: each class scatters its rows from the GEMM epilogue (16 bytes per thread and row)
+    const bool compact = scratch_scatter_ok(p) && !p.accumulate;
+    const bf16 *cls_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t soff = 0;
     for (int py = 0; py < 2; py++)
         for (int px = 0; px < 2; px++) {
             const int ny = 1 + py, nx = 1 + px;
@@ -1395,6 +1407,12 @@ static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
             q.OH = A; q.OW = Bc; q.M = p.batch * A * Bc; q.K = ny * nx * p.Cin;
             q.out_stride = 2; q.SH = p.OH; q.SW = p.OW;
             const size_t off = (size_t)py * p.OW + px;                         // first pixel of the class
+            if (compact) {
+                q.out_stride = 1; q.SH = q.SW = 0; q.mask_bits = nullptr; q.scratch = nullptr;
+                q.C = p.scratch + soff; q.ldc = p.N;
+                cls_out[py * 2 + px] = reinterpret_cast<const bf16 *>(q.C);
+                soff += (size_t)q.M * p.N;
+            } else
             if (q.C) q.C = q.C + off * q.ldc;
             if (q.Cf) q.Cf = q.Cf + off * q.ldcf;
             if (q.mask) q.mask = q.mask + off * q.ldm;
@@ -1411,13 +1429,33 @@ static int strided_dgrad_tc(const detrb_igemm_t &p, cudaStream_t stream)
             int rc = dispatch_tc<true>(q, 0, stream, &cls);
             if (rc) return rc;
         }
+    if (compact)
+        return detrb_scatter_s2(cls_out, reinterpret_cast<bf16 *>(p.C), p.ldc, p.mask_bits, p.ldmb, p.batch, p.OH, p.OW, p.N, 0, stream);
     return DETRB_OK;
+}
+
+// out_stride == 2 on a plain GEMM (the data gradient of a 1x1 / stride-2 shortcut, scatter-accumulated into the even pixels): with a
+// workspace the GEMM writes densely and one coalesced pass adds it to C
+static int strided_plain_tc(const detrb_igemm_t &p, cudaStream_t stream)
+{
+    detrb_igemm_t q = p;
+    q.out_stride = 1; q.SH = q.SW = 0; q.accumulate = 0; q.mask_bits = nullptr; q.scratch = nullptr;
+    q.C = p.scratch; q.ldc = p.N;
+    int rc = dispatch_tc<false>(q, 0, stream);
+    if (rc) return rc;
+    const bf16 *cls_out[4] = {reinterpret_cast<const bf16 *>(p.scratch), nullptr, nullptr, nullptr};
+    return detrb_scatter_s2(cls_out, reinterpret_cast<bf16 *>(p.C), p.ldc, p.mask_bits, p.ldmb, p.batch, p.SH, p.SW, p.N, p.accumulate, stream);
 }
 
 int detrb_gemm_tc(const detrb_igemm_t &p, cudaStream_t stream)
 {
     const int kind = detrb_gemm_tc_kind(p);
-    if (kind == 1) return dispatch_tc<false>(p, 0, stream);
+    if (kind == 1) {
+        if (p.out_stride == 2 && !p.a_kb_rows && scratch_scatter_ok(p) && p.OH == (p.SH + 1) / 2 && p.OW == (p.SW + 1) / 2 &&
+            p.M == p.batch * p.OH * p.OW)
+            return strided_plain_tc(p, stream);
+        return dispatch_tc<false>(p, 0, stream);
+    }
     if (kind == 2) {
         if (detrb_conv_halo_supported(p)) return detrb_conv_halo(p, stream);      // 3x3, 64 -> 64 channels: halo-reusing row kernel (conv_halo.cu)
         return dispatch_tc<true>(p, 0, stream);

@@ -541,6 +541,8 @@ class Engine:
         buf("g_y", max_elems)
         buf("g_1", max_elems)
         buf("g_2", max_elems)
+        if not self.paired:                      # dense workspace of the stride-2 scatter forms (detrb_igemm_t.scratch)
+            buf("g_s", max_elems + 64)
         if self.paired:
             def numel(shape):
                 n = 1
@@ -707,7 +709,8 @@ class Engine:
         self._before_write(out)
         self._probed(s.name + "#dgrad", lambda: ops.igemm(dy, s.Wd, M, s.Cin, s.taps * s.ldd, s.N, s.taps * s.ldd, g, mask_bits=mask_bits,
                                                           ldmb=s.Cin // 8, mask_scale=1.0, residual=residual, ldr=s.Cin, C=out, ldc=s.Cin,
-                                                          split=self.plane, wsplit=self.wplane))
+                                                          split=self.plane, wsplit=self.wplane,
+                                                          scratch=self.a.get("g_s") if stride > 1 else None))
 
     def _conv_wgrad(self, s, x, dy, ihw, ohw):
         B = self.B
@@ -1127,7 +1130,8 @@ class Engine:
                 self.launches += 1
                 self._before_write(g_in)
                 ops.igemm(g_out, cd.Wd, Mo, cd.Cin, cd.ldd, cd.N, cd.ldd, g, mask_bits=xbits, ldmb=cd.Cin // 8, mask_scale=1.0,
-                          C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True, split=self.plane, wsplit=self.wplane)
+                          C=g_in, ldc=cd.Cin, out_stride=st, SH=ihw[0], SW=ihw[1], accumulate=True, split=self.plane, wsplit=self.wplane,
+                          scratch=a.get("g_s"))
             g_out, g_in = g_in, g_out
             if blk["prefix"] == "backbone/layer3/0":
                 reached(1)

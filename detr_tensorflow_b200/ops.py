@@ -30,7 +30,7 @@ def plain_geom(M, K):
 
 def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mask=None, ldm=0, mask_scale=1.0,
           relu=False, sigmoid=False, drop_p=0.0, seed=0, site=0, seed_ptr=None, C=None, ldc=0, Cf=None, ldcf=0,
-          out_stride=1, SH=0, SW=0, accumulate=False, a_kb_rows=0, force_tc=None, split=0, wsplit=0, mask_bits=None, ldmb=0, out_bits=None, ldob=0):
+          out_stride=1, SH=0, SW=0, accumulate=False, a_kb_rows=0, force_tc=None, split=0, wsplit=0, mask_bits=None, ldmb=0, out_bits=None, ldob=0, scratch=None):
     p = IgemmParams()
     p.A, p.W = ptr(A), ptr(W)
     p.M, p.N, p.K, p.lda, p.ldw = M, N, K, lda, ldw
@@ -42,6 +42,7 @@ def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mas
     p.out_stride, p.SH, p.SW, p.accumulate, p.a_kb_rows = out_stride, SH, SW, int(accumulate), a_kb_rows
     p.split, p.wsplit = split, wsplit
     p.mask_bits, p.ldmb, p.out_bits, p.ldob = ptr(mask_bits), ldmb, ptr(out_bits), ldob
+    p.scratch = ptr(scratch)
     if force_tc is not None:
         check(_lib.lib().detrb_gemm_tc_force(byref(p), c_int(force_tc), _stream()))
     else:

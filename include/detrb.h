@@ -112,6 +112,12 @@ typedef struct {
      * N % 64 == 0, strides multiples of 8 bytes, 8-byte aligned bases; tcgen05 path only (DETRB_E_SHAPE otherwise). */
     const uint8_t *mask_bits; int ldmb;
     uint8_t *out_bits; int ldob;
+    /* optional workspace of at least M*N + 64 bf16 elements (16-byte aligned, plain bf16 only).  With it the two stride-2 scatter
+     * forms -- the data gradient of a 3x3 / stride-2 convolution (four parity-class sub-convolutions) and out_stride == 2 (the data
+     * gradient of a 1x1 / stride-2 shortcut, with or without accumulate) -- write their GEMM results densely through the fast
+     * TMA-store kernels and one coalesced pass scatters them (applies mask_bits, adds to C when accumulate); without it the
+     * results are scattered by the GEMM's own epilogue, row by row. */
+    detrb_bf16 *scratch;
 } detrb_igemm_t;
 
 int detrb_igemm(const detrb_igemm_t *p, detrb_stream_t stream);

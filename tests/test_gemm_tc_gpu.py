@@ -470,3 +470,48 @@ def test_conv3x3_halo_kernel(B, H, W):
     check("halo dgrad", dx[:M], refd, 1e-2, 2e-2)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(2, 30, 44, 64, 128), (1, 25, 43, 128, 256), (8, 200, 334, 128, 128), (8, 100, 167, 256, 256)])
+def test_stride2_scatter_through_the_dense_workspace(B, H, W, Ci, Co):
+    """detrb_igemm_t.scratch: the two stride-2 scatter forms of the backbone's backward pass -- the data gradient of a 3x3 / stride-2
+    convolution (four parity classes) and of a 1x1 / stride-2 shortcut (scatter-accumulate into the even pixels) -- written densely
+    by the fast kernels and scattered by one coalesced pass, against the same launches without workspace (results scattered by the
+    GEMM epilogue).  Identical arithmetic except one extra bf16 rounding of the shortcut term before it is added."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from detr_tensorflow_b200 import ops
+    M = B * H * W
+    oh, ow = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    Mo = B * oh * ow
+    g = torch.Generator().manual_seed(9)
+    dy = (torch.randn(Mo, Co, generator=g)).cuda().to(BF)
+    bits = torch.randint(0, 256, (M, Ci // 8), dtype=torch.uint8, generator=g).cuda()
+    scratch = torch.empty(M * Ci + 64, dtype=BF, device="cuda")
+    # 3x3 / stride 2 / pad 1 data gradient
+    w3 = (torch.randn(Ci, 9 * Co, generator=g) * (9 * Co) ** -0.5).cuda().to(BF)
+    g3 = dict(batch=B, IH=oh, IW=ow, Cin=Co, OH=H, OW=W, KH=3, KW=3, stride=2, pad=1, mode=1)
+    outs = []
+    for sc in (None, scratch):
+        o = torch.full((M + 1, Ci), 7.0, dtype=BF, device="cuda")
+        ops.igemm(dy, w3, M, Ci, 9 * Co, Co, 9 * Co, g3, mask_bits=bits, ldmb=Ci // 8, mask_scale=1.0, C=o, ldc=Ci, scratch=sc)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and float(outs[0][:M].float().abs().max()) > 0 and float((outs[0][M:].float() - 7.0).abs().max()) == 0
+    # 1x1 / stride-2 shortcut data gradient, accumulated into the even pixels
+    wd = (torch.randn(Ci, Co, generator=g) * Co ** -0.5).cuda().to(BF)
+    base = torch.randn(M + 1, Ci, generator=g).cuda().to(BF)
+    g1 = dict(batch=B, IH=oh, IW=ow, Cin=Co, OH=oh, OW=ow, KH=1, KW=1, stride=1, pad=0, mode=0)
+    outs = []
+    for sc in (None, scratch):
+        o = base.clone()
+        ops.igemm(dy, wd, Mo, Ci, Co, Co, Co, g1, mask_bits=bits, ldmb=Ci // 8, mask_scale=1.0, C=o, ldc=Ci, out_stride=2, SH=H, SW=W, accumulate=True,
+                  scratch=sc)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][M:], base[M:]) and torch.equal(outs[1][M:], base[M:])
+    odd = torch.ones(B, H, W, dtype=torch.bool, device="cuda")
+    odd[:, ::2, ::2] = False
+    assert torch.equal(outs[1][:M][odd.view(-1)], base[:M][odd.view(-1)])            # only the even pixels are touched
+    check("shortcut scatter", outs[1][:M], outs[0][:M], 1e-2, 2e-2)
+    assert not torch.equal(outs[1][:M], base[:M])
