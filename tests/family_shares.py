@@ -15,7 +15,7 @@ FAMILIES = [
     ("attention forward / backward (tcgen05)", r"attn_"),
     ("LayerNorm forward / backward", r"ln_(fwd|bwd)_kernel"),
     ("Adam + clipnorm + weight refresh", r"chunk_|adam_|prep_weights"),
-    ("pooling / input layout / fills", r"maxpool|image_|s2d|add_rowbcast|FillFunctor|elementwise"),
+    ("pooling / input layout / stride-2 scatter / fills", r"maxpool|image_|s2d|add_rowbcast|scatter_s2|FillFunctor|elementwise"),
     ("matcher + set loss", r"matcher_kernel|set_loss"),
     ("mma.sync GEMM / wgrad (unaligned heads)", r"igemm_kernel|wgrad_kernel"),
 ]
