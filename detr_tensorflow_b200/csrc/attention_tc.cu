@@ -19,6 +19,13 @@
 // (256 TMEM columns, 75 KB shared memory, <= 168 registers).
 #include "tc_common.cuh"
 
+// waits of the single-thread producer / MMA warps: relaxed polling (DETRB_ATTN_SPIN builds keep the plain spin for A/B runs)
+#ifdef DETRB_ATTN_SPIN
+#define MBAR_WAIT_CTRL(bar, parity) mbar_wait(bar, parity)
+#else
+#define MBAR_WAIT_CTRL(bar, parity) mbar_wait_relaxed(bar, parity, 32u)
+#endif
+
 namespace {
 
 constexpr int DH = 32;
@@ -113,7 +120,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             tma_load_2d(smem0 + OFF_Q, &map_q, q_full, h * DH, b * p.Lq + q0);
             for (int j = 0; j < nkt; j++) {
                 const int st = j % KVST;
-                mbar_wait(kv_empty(st), ((j / KVST) & 1) ^ 1);
+                MBAR_WAIT_CTRL(kv_empty(st), ((j / KVST) & 1) ^ 1);
                 mbar_expect_tx(kv_full(st), 2 * KT_BYTES);
                 const uint32_t dst = smem0 + OFF_KV + (uint32_t)st * (2 * KT_BYTES);
                 // rows beyond this batch's Lk keys belong to the next batch (or are zero-filled past the end of the tensor):
@@ -127,12 +134,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV, 0), IDESC_PV = idesc_f16(BQ, DH, 1);
-            mbar_wait(q_full, 0);
+            MBAR_WAIT_CTRL(q_full, 0);
             const uint64_t dq = desc_k_sw64(smem0 + OFF_Q);
             auto issue_s = [&](int j) {
                 const int st = j % KVST, sb = j & 1;
-                mbar_wait(kv_full(st), (j / KVST) & 1);
-                mbar_wait(s_empty(sb), ((j >> 1) & 1) ^ 1);              // the softmax warps have read S_{j-2} out of this buffer
+                MBAR_WAIT_CTRL(kv_full(st), (j / KVST) & 1);
+                MBAR_WAIT_CTRL(s_empty(sb), ((j >> 1) & 1) ^ 1);              // the softmax warps have read S_{j-2} out of this buffer
                 tc_fence_after();
                 const uint64_t dk = desc_k_sw64(smem0 + OFF_KV + (uint32_t)st * (2 * KT_BYTES));
 #pragma unroll
@@ -144,8 +151,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             for (int j = 0; j < nkt; j++) {
                 if (j + 1 < nkt) issue_s(j + 1);                         // scores of the next tile while the softmax works on this one
                 const int st = j % KVST, pb = j & 1;
-                mbar_wait(p_full(pb), (j >> 1) & 1);                     // P_j is in shared memory
-                mbar_wait(pv_empty(pb), ((j >> 1) & 1) ^ 1);             // PV_{j-2} has been read out of this buffer
+                MBAR_WAIT_CTRL(p_full(pb), (j >> 1) & 1);                     // P_j is in shared memory
+                MBAR_WAIT_CTRL(pv_empty(pb), ((j >> 1) & 1) ^ 1);             // PV_{j-2} has been read out of this buffer
                 tc_fence_after();
                 const uint64_t dp = desc_k_sw128(smem0 + OFF_P + (uint32_t)pb * P_BYTES);
                 const uint64_t dv = desc_mn_sw64(smem0 + OFF_KV + (uint32_t)st * (2 * KT_BYTES) + KT_BYTES);
@@ -367,7 +374,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             tma_load_2d(smem0 + DQ_OFF_DO, &map_do, q_full, h * DH, b * p.Lq + q0);
             for (int j = 0; j < nkt; j++) {
                 const int st = j % BSTG;
-                mbar_wait(kv_empty(st), ((j / BSTG) & 1) ^ 1);
+                MBAR_WAIT_CTRL(kv_empty(st), ((j / BSTG) & 1) ^ 1);
                 mbar_expect_tx(kv_full(st), 2 * TILE64);
                 const uint32_t dst = smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64);
                 tma_load_2d(dst, &map_k, kv_full(st), h * DH, b * p.Lk + j * BKV);
@@ -378,12 +385,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV, 0), IDESC_DQ = idesc_f16(BQ, DH, 1);
-            mbar_wait(q_full, 0);
+            MBAR_WAIT_CTRL(q_full, 0);
             const uint64_t dq_ = desc_k_sw64(smem0 + DQ_OFF_Q), ddo = desc_k_sw64(smem0 + DQ_OFF_DO);
             auto issue_sdp = [&](int j) {                                // S = Q K_j^T and dP = dO V_j^T (single-buffered in TMEM)
                 const int st = j % BSTG;
-                mbar_wait(kv_full(st), (j / BSTG) & 1);
-                mbar_wait(sdp_empty, (j & 1) ^ 1);                       // the row threads hold tile j-1 in registers
+                MBAR_WAIT_CTRL(kv_full(st), (j / BSTG) & 1);
+                MBAR_WAIT_CTRL(sdp_empty, (j & 1) ^ 1);                       // the row threads hold tile j-1 in registers
                 tc_fence_after();
                 const uint32_t kv = smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64);
                 const uint64_t dk = desc_k_sw64(kv), dv = desc_k_sw64(kv + TILE64);
@@ -397,7 +404,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int j = 0; j < nkt; j++) {
                 if (j + 1 < nkt) issue_sdp(j + 1);
                 const int st = j % BSTG, db = j & 1;
-                mbar_wait(ds_full(db), (j >> 1) & 1);
+                MBAR_WAIT_CTRL(ds_full(db), (j >> 1) & 1);
                 tc_fence_after();
                 const uint64_t dds = desc_k_sw128(smem0 + DQ_OFF_DS + (uint32_t)db * DS_BYTES);
                 const uint64_t dkm = desc_mn_sw64(smem0 + DQ_OFF_KV + (uint32_t)st * (2 * TILE64));
@@ -546,7 +553,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tma_load_2d(smem0 + DKV_OFF_V, &map_v, kv_full, h * DH, b * p.Lk + k0);
             for (int j = 0; j < nqt; j++) {
                 const int st = j % BSTG;
-                mbar_wait(q_empty(st), ((j / BSTG) & 1) ^ 1);
+                MBAR_WAIT_CTRL(q_empty(st), ((j / BSTG) & 1) ^ 1);
                 mbar_expect_tx(q_full(st), 2 * TILE64);
                 const uint32_t dst = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
                 tma_load_2d(dst, &map_q, q_full(st), h * DH, b * p.Lq + j * BKV);
@@ -557,12 +564,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t IDESC_S = idesc_f16(BQ, BKV, 0), IDESC_D = idesc_f16(BQ, DH, 1);
-            mbar_wait(kv_full, 0);
+            MBAR_WAIT_CTRL(kv_full, 0);
             const uint64_t dk = desc_k_sw64(smem0 + DKV_OFF_K), dv = desc_k_sw64(smem0 + DKV_OFF_V);
             auto issue_sdp = [&](int j) {                                // S^T = K Q_j^T and dP^T = V dO_j^T
                 const int st = j % BSTG;
-                mbar_wait(q_full(st), (j / BSTG) & 1);
-                mbar_wait(sdp_empty, (j & 1) ^ 1);
+                MBAR_WAIT_CTRL(q_full(st), (j / BSTG) & 1);
+                MBAR_WAIT_CTRL(sdp_empty, (j & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t qd = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
                 const uint64_t dq_ = desc_k_sw64(qd), ddo = desc_k_sw64(qd + TILE64);
@@ -576,7 +583,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int j = 0; j < nqt; j++) {
                 if (j + 1 < nqt) issue_sdp(j + 1);
                 const int st = j % BSTG;
-                mbar_wait(pds_full, j & 1);
+                MBAR_WAIT_CTRL(pds_full, j & 1);
                 tc_fence_after();
                 const uint32_t qd = smem0 + DKV_OFF_QDO + (uint32_t)st * (2 * TILE64);
                 const uint64_t dp_ = desc_k_sw128(smem0 + DKV_OFF_P), dds = desc_k_sw128(smem0 + DKV_OFF_DS);

@@ -24,6 +24,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n\t"
         "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
+// the same wait for the single-thread producer / MMA warps of kernels whose other warps are issue-bound (attention): the hardware may
+// suspend the thread for up to `hint_ns` inside try_wait, and a failed probe backs off with nanosleep -- the polling loop of
+// mbar_wait (try_wait + branch) otherwise competes for issue slots with the softmax warp on the same scheduler (ncu: 38 % of all
+// executed instructions of the attention forward kernel were polling)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+    while (true) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(4u * sleep_ns) : "memory");
+        if (ok) break;
+        __nanosleep(sleep_ns);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
