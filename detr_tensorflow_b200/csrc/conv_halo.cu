@@ -224,6 +224,224 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
 }
 
+// ================================================================================================ row-stationary variant
+// The kernel above issues 36 MMAs of 128 x 64 x 16 per output row: each fetches 4 KB of pixels + 2 KB of weights for 32 cycles of
+// tensor-pipe work, and at the ~64 B/clk the SM delivers operands that is 86 cycles per MMA (ncu + diag runs: MMA bound at 52 us).
+// Here an INPUT row is pushed through the tensor core once against all the taps that use it: input row r is tap row kh = 0 of output
+// row r+1, kh = 1 of output row r and kh = 2 of output row r-1, so one MMA of N = 192 with the weights stacked [W(2,kw); W(1,kw);
+// W(0,kw)] adds its contribution to THREE accumulators at once -- 12 MMAs (10 KB per 3x the work) instead of 36 per row.  The
+// accumulators form a ring of eight 64-column slots in tensor memory (output row i of the CTA lives in slot i % 8; a triple that
+// wraps around the ring is issued as two MMAs), every MMA accumulates, and a slot is zeroed by the epilogue warpgroup that drained
+// it (tcgen05.st) before the MMA warp may use it again.  Same accumulation order per output element as above (kh, kw, c): bit-exact.
+constexpr int NSLOT = 8;                            // accumulator ring (8 x 64 = all 512 TMEM columns)
+// input-row ring: a row is needed only while its own twelve MMAs run (seven 16 640-byte slots at 128-byte alignment were tried: wrong
+// results at full size -- the TMA write does want the 1024-byte alignment of the swizzle period -- and no faster)
+constexpr int NR2 = 5;
+constexpr int ROW_PITCH2 = ROW_BYTES;
+constexpr int RS2 = 4;                              // output staging tiles: two per epilogue warpgroup, released one store later
+constexpr int OFF_ROWS2 = W_BYTES, OFF_OUT2 = OFF_ROWS2 + NR2 * ROW_PITCH2, OFF_BAR2 = OFF_OUT2 + RS2 * 16384, OFF_BIAS2 = OFF_BAR2 + 256;
+constexpr int SMEM_BYTES2 = OFF_BIAS2 + HC * 4 + 1024;
+
+__device__ __forceinline__ void tmem_zero64(uint32_t taddr) {
+    const uint32_t z = 0u;
+#pragma unroll
+    for (int c = 0; c < 64; c += 16)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                     :: "r"(taddr + (uint32_t)c), "r"(z) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_halo192_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ CUtensorMap map_y, const detrb_igemm_t p, const HaloGeom geo, const int diag)
+{   // diag (developer switch DETRB_HALO_DIAG, wrong results, timing only): 1 = MMAs of kw 0 only, 2 = no epilogue arithmetic, 4 = N <= 64 per MMA
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem0 + OFF_BAR2;
+    auto row_full = [&](int s) { return bar0 + 8u * s; };
+    auto row_empty = [&](int s) { return bar0 + 8u * (NR2 + s); };
+    auto tmem_full = [&](int a) { return bar0 + 8u * (2 * NR2 + a); };
+    auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * NR2 + NSLOT + a); };
+    auto slot_free = [&](int i) { return bar0 + 8u * (2 * NR2 + 2 * NSLOT + i); };
+    const uint32_t w_full = bar0 + 8u * (2 * NR2 + 2 * NSLOT + RS2);
+    const uint32_t tmem_slot = w_full + 8u;
+    const uint32_t sbias = smem0 + OFF_BIAS2;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = geo.H;
+    const int u_begin = (int)((long long)blockIdx.x * geo.units / gridDim.x), u_end = (int)((long long)(blockIdx.x + 1) * geo.units / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_y);
+        for (int s = 0; s < NR2; s++) { mbar_init(row_full(s), 1); mbar_init(row_empty(s), 1); }
+        for (int a = 0; a < NSLOT; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 4); }
+        for (int i = 0; i < RS2; i++) mbar_init(slot_free(i), 1);
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)(NSLOT * HC)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== weights once (stacked per kw: kh = 2, 1, 0), then every input row of every run once =====================
+        if (elect_one()) {
+            mbar_expect_tx(w_full, W_BYTES);
+            for (int kw = 0; kw < 3; kw++)
+                for (int j = 0; j < 3; j++)                 // j = 2 - kh
+                    tma_load_2d(smem0 + (uint32_t)((kw * 3 + j) * W_TAP_BYTES), &map_w, w_full, geo.wtap[(2 - j) * 3 + kw] * HC, 0);
+            int seq = 0;
+            for (int u = u_begin; u < u_end;) {
+                const int strip = u / H, y0 = u - strip * H, y1 = min(H, y0 + (u_end - u));
+                const int b = strip / geo.nseg, x0 = (strip - b * geo.nseg) * TBM;
+                for (int r = max(0, y0 - 1); r <= min(H - 1, y1); r++, seq++) {
+                    const int slot = seq % NR2;
+                    mbar_wait(row_empty(slot), ((seq / NR2) & 1) ^ 1);
+                    mbar_expect_tx(row_full(slot), ROW_TX);
+                    tma_load_4d(smem0 + OFF_ROWS2 + (uint32_t)(slot * ROW_PITCH2), &map_x, row_full(slot), 0, x0 - 1, r, b);
+                }
+                u += y1 - y0;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one input row -> up to three accumulators =====================
+        if (elect_one()) {
+            mbar_wait(w_full, 0);
+            int seq = 0, oi_run = 0;                        // input rows consumed; index (within this CTA) of the run's first output row
+            for (int u = u_begin; u < u_end;) {
+                const int strip = u / H, y0 = u - strip * H, y1 = min(H, y0 + (u_end - u));
+                const int r_last = min(H - 1, y1);
+                for (int r = max(0, y0 - 1); r <= r_last; r++, seq++) {
+                    const int rslot = seq % NR2;
+                    mbar_wait(row_full(rslot), (seq / NR2) & 1);
+                    const int lo = max(r - 1, y0), hi = min(r + 1, y1 - 1);    // output rows this input row contributes to
+                    // an output row gets its first contribution from input row max(o - 1, 0): its slot must be drained and zeroed
+                    for (int o = lo; o <= hi; o++)
+                        if (r == max(o - 1, 0)) {
+                            const int oi = oi_run + (o - y0);
+                            mbar_wait(tmem_empty(oi % NSLOT), (oi / NSLOT) & 1);
+                        }
+                    tc_fence_after();
+                    const uint32_t row_addr = smem0 + OFF_ROWS2 + (uint32_t)(rslot * ROW_PITCH2);
+                    const int oi_lo = oi_run + (lo - y0), s_lo = oi_lo % NSLOT, nrows = hi - lo + 1;
+                    const int n1 = min(nrows, NSLOT - s_lo), n2 = nrows - n1;   // rows before / after the ring wraps
+                    const int j0 = lo - (r - 1);                                // first block of the stack [W(2,kw); W(1,kw); W(0,kw)]
+#pragma unroll
+                    for (int kw = 0; kw < 3; kw++) {
+                        if ((diag & 1) && kw) continue;
+                        const uint64_t da = make_smem_desc(row_addr + (uint32_t)(kw * 128));
+                        const uint32_t wb = smem0 + (uint32_t)((kw * 3 + j0) * W_TAP_BYTES);
+                        const uint64_t db1 = make_smem_desc(wb), db2 = make_smem_desc(wb + (uint32_t)(n1 * W_TAP_BYTES));
+#pragma unroll
+                        for (int k = 0; k < HC / 16; k++) {
+                            tc_mma_f16(tmem_base + (uint32_t)(s_lo * HC), da + (uint64_t)(k * 2), db1 + (uint64_t)(k * 2), make_idesc(TBM, (diag & 4) ? 64 : 64 * n1), 1u);
+                            if (n2 > 0) tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), make_idesc(TBM, 64 * n2), 1u);
+                        }
+                    }
+                    tc_commit(row_empty(rslot));                                // this input row is done with
+                    if (r - 1 >= y0) tc_commit(tmem_full((oi_run + (r - 1 - y0)) % NSLOT));        // output row r-1 is complete
+                    if (r == r_last && r <= y1 - 1) tc_commit(tmem_full((oi_run + (r - y0)) % NSLOT));   // bottom image row: row r too
+                }
+                oi_run += y1 - y0;
+                u += y1 - y0;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue: output row i of the CTA goes to warpgroup i % 2 (slots i % 8: each warpgroup owns four) =====================
+        const int wg = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const bool leader = (q == 0 && lane == 0);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int t = threadIdx.x - 128; t < HC; t += 256)
+            asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * (uint32_t)t), "f"(p.bias ? p.bias[t] : 0.f) : "memory");
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        // all accumulators start at zero
+        for (int a = wg; a < NSLOT; a += 2) {
+            tmem_zero64(lane_addr + (uint32_t)(a * HC));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(a));
+        }
+        const bool relu = p.relu != 0;
+        const bool mbits = p.mask_bits != nullptr, obits = p.out_bits != nullptr;
+        int prev_st = -1;
+        auto pixel = [&](int u, int &x0, int &y, int &b) -> long long {       // flat NHWC pixel index of this thread's row of unit u (-1: outside)
+            const int strip = u / H;
+            y = u - strip * H;
+            b = strip / geo.nseg;
+            x0 = (strip - b * geo.nseg) * TBM;
+            return (x0 + row < geo.W) ? ((long long)(b * H + y) * geo.W + x0 + row) : -1ll;
+        };
+        auto load_bits = [&](int u) -> uint2 {                                 // mask bits of this warpgroup's next row, one row ahead
+            int x0, y, b;
+            if (u >= u_end) return make_uint2(0u, 0u);
+            const long long m = pixel(u, x0, y, b);
+            return m >= 0 ? ld_bits8(p.mask_bits + (size_t)m * p.ldmb) : make_uint2(0u, 0u);
+        };
+        uint2 mb_nxt = mbits ? load_bits(u_begin + wg) : make_uint2(0u, 0u);
+        int oi = 0, nstore = 0;
+        for (int u = u_begin; u < u_end; u++, oi++) {
+            if ((oi & 1) != wg) continue;
+            int x0, y, b;
+            const long long m = pixel(u, x0, y, b);
+            uint2 mbc = mb_nxt, ob = make_uint2(0u, 0u);
+            if (mbits) mb_nxt = load_bits(u + 2);
+            const int a = oi % NSLOT;
+            mbar_wait(tmem_full(a), (oi / NSLOT) & 1);
+            tc_fence_after();
+            uint32_t acc_r[64];
+            tc_ld64(lane_addr + (uint32_t)(a * HC), acc_r);
+            const int st = 2 * (nstore & 1) + wg;                  // this warpgroup's two staging tiles alternate
+            const uint32_t sbuf = smem0 + OFF_OUT2 + (uint32_t)st * 16384u;
+            mbar_wait(slot_free(st), ((nstore >> 1) & 1) ^ 1);     // the store that last used this tile has read it
+            tc_wait_ld();
+            tmem_zero64(lane_addr + (uint32_t)(a * HC));           // drained: zero it and hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(a));
+            uint4 rr[8];
+            if (diag & 2) {}
+            else if (mbits) epi_chunk_math<false, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, sbuf + row_off, sw);
+            else if (obits) epi_chunk_math<false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, sbuf + row_off, sw);
+            else epi_chunk_math<false, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, sbuf + row_off, sw);
+            if (obits && m >= 0) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob) = ob;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+            if (leader) {
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             :: "l"(&map_y), "r"(sbuf), "r"(0), "r"(x0), "r"(y), "r"(b) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (prev_st >= 0) {                                   // the previous row's store has read its tile by now (or we wait for it)
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    mbar_arrive(slot_free(prev_st));
+                }
+                prev_st = st;
+            }
+            nstore++;
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(NSLOT * HC)) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -257,6 +475,7 @@ bool make_nhwc_map(CUtensorMap *map, const void *base, int B, int H, int W, int 
 int g_halo = 1;               // 0 off, 1 on                                                  (env DETRB_HALO)
 int g_halo_bo = 0;            // descriptor base-offset field for the shifted tap views: must stay 0 (see the kernel)   (env DETRB_HALO_BO, developer switch)
 int g_halo_diag = 0;          // timing-only switches (wrong results)                                                    (env DETRB_HALO_DIAG)
+int g_halo_192 = 1;           // row-stationary N = 192 variant (conv3x3_halo192_kernel)                                  (env DETRB_HALO_192)
 void read_env()
 {
     static bool done = false;
@@ -265,6 +484,7 @@ void read_env()
     if (const char *e = getenv("DETRB_HALO")) g_halo = atoi(e);
     if (const char *e = getenv("DETRB_HALO_BO")) g_halo_bo = atoi(e);
     if (const char *e = getenv("DETRB_HALO_DIAG")) g_halo_diag = atoi(e);
+    if (const char *e = getenv("DETRB_HALO_192")) g_halo_192 = atoi(e);
 }
 
 }  // namespace
@@ -298,6 +518,7 @@ int detrb_conv_halo(const detrb_igemm_t &p, cudaStream_t stream)
     static bool configured = false;
     static int num_sms = 148;
     if (!configured) {
+        DETRB_CUDA(cudaFuncSetAttribute(conv3x3_halo192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2));
         DETRB_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         int dev = 0;
         cudaGetDevice(&dev);
@@ -305,6 +526,11 @@ int detrb_conv_halo(const detrb_igemm_t &p, cudaStream_t stream)
         configured = true;
     }
     const int grid = geo.units < num_sms ? geo.units : num_sms;
+    if (g_halo_192) {
+        DETRB_LAUNCH(conv3x3_halo192_kernel, dim3(grid), dim3(NTHREADS), SMEM_BYTES2, stream, mx, mw, my, p, geo, g_halo_diag);
+        DETRB_CHECK_LAUNCH("conv3x3_halo192_kernel");
+        return DETRB_OK;
+    }
     DETRB_LAUNCH(conv3x3_halo_kernel, dim3(grid), dim3(NTHREADS), SMEM_BYTES, stream, mx, mw, my, p, geo, g_halo_bo, g_halo_diag);
     DETRB_CHECK_LAUNCH("conv3x3_halo_kernel");
     return DETRB_OK;
