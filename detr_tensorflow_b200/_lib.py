@@ -17,7 +17,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
 _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_maps.cu", "wgrad_tc.cu", "pipeline.cu", "attention_tc.cu", "conv_halo.cu"]
 _lib = None
-ABI_VERSION = 220          # detrb_version() of the library these ctypes structures / call sites were written for
+ABI_VERSION = 221          # detrb_version() of the library these ctypes structures / call sites were written for
 
 EXPORTS = [
     "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
@@ -95,7 +95,7 @@ class AttnBwdParams(Structure):
         ("lse", c_void_p), ("delta", c_void_p), ("dQ", c_void_p), ("dK", c_void_p), ("dV", c_void_p),
         ("lddq", c_int), ("lddk", c_int), ("lddv", c_int), ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int),
         ("scale", c_float), ("drop_p", c_float), ("seed", c_uint64), ("site", c_uint32), ("seed_ptr", c_void_p),
-        ("split", c_int64),
+        ("split", c_int64), ("parts", c_int),
     ]
 
 

@@ -611,22 +611,35 @@ extern "C" int detrb_attn_bwd(const detrb_attn_bwd_t *pp, detrb_stream_t stream_
     DETRB_REQUIRE(p.B > 0 && p.H > 0 && p.Lq > 0 && p.Lk > 0, "detrb_attn_bwd: empty problem");
     DETRB_REQUIRE(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 8 == 0 && p.lddo % 8 == 0,
                   "detrb_attn_bwd: strides must be multiples of 8");
+    DETRB_REQUIRE(p.parts >= 0 && p.parts <= 7, "detrb_attn_bwd: parts is a mask of 1 (delta) | 2 (dK/dV) | 4 (dQ)");
+    const int parts = p.parts ? p.parts : 7;
     int n = p.B * p.H * p.Lq;
-    DETRB_LAUNCH(attn_delta_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
-                                                            p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq, (long long)p.split);
-    DETRB_CHECK_LAUNCH("attn_delta_kernel");
+    if (parts & 1) {
+        DETRB_LAUNCH(attn_delta_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<const bf16 *>(p.O), reinterpret_cast<const bf16 *>(p.dO),
+                                                                p.ldo, p.lddo, p.delta, p.B, p.H, p.Lq, (long long)p.split);
+        DETRB_CHECK_LAUNCH("attn_delta_kernel");
+    }
     if (p.split) {
         const long long rq = (long long)p.B * p.H * p.Lq, rk = (long long)p.B * p.H * p.Lk;
-        DETRB_LAUNCH(attn_bwd_dkv_sp_kernel, dim3((unsigned)((rk + 7) / 8)), dim3(256), 0, stream, p);
-        DETRB_CHECK_LAUNCH("attn_bwd_dkv_sp_kernel");
-        DETRB_LAUNCH(attn_bwd_dq_sp_kernel, dim3((unsigned)((rq + 7) / 8)), dim3(256), 0, stream, p);
-        DETRB_CHECK_LAUNCH("attn_bwd_dq_sp_kernel");
+        if (parts & 2) {
+            DETRB_LAUNCH(attn_bwd_dkv_sp_kernel, dim3((unsigned)((rk + 7) / 8)), dim3(256), 0, stream, p);
+            DETRB_CHECK_LAUNCH("attn_bwd_dkv_sp_kernel");
+        }
+        if (parts & 4) {
+            DETRB_LAUNCH(attn_bwd_dq_sp_kernel, dim3((unsigned)((rq + 7) / 8)), dim3(256), 0, stream, p);
+            DETRB_CHECK_LAUNCH("attn_bwd_dq_sp_kernel");
+        }
         return DETRB_OK;
     }
+    if (!(parts & 6)) return DETRB_OK;
     if (detrb_attn_tc_enabled() && detrb_attn_bwd_tc_supported(p)) return detrb_attn_bwd_tc(p, stream);            // tcgen05 / TMA / TMEM
-    DETRB_LAUNCH(attn_bwd_dkv_kernel, dim3(dim3(ceil_div(p.Lk, TQ), p.H, p.B)), dim3(128), 0, stream, p);
-    DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-    DETRB_LAUNCH(attn_bwd_dq_kernel, dim3(dim3(ceil_div(p.Lq, TQ), p.H, p.B)), dim3(128), 0, stream, p);
-    DETRB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+    if (parts & 2) {
+        DETRB_LAUNCH(attn_bwd_dkv_kernel, dim3(dim3(ceil_div(p.Lk, TQ), p.H, p.B)), dim3(128), 0, stream, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+    }
+    if (parts & 4) {
+        DETRB_LAUNCH(attn_bwd_dq_kernel, dim3(dim3(ceil_div(p.Lq, TQ), p.H, p.B)), dim3(128), 0, stream, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dq_kernel");
+    }
     return DETRB_OK;
 }

@@ -762,9 +762,14 @@ int detrb_attn_bwd_tc(const detrb_attn_bwd_t &p, cudaStream_t stream)
         DETRB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));
         configured = true;
     }
-    DETRB_LAUNCH(attn_bwd_dkv_tc_kernel, dim3(ceil_div(p.Lk, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DKV, stream, q64, do64, k128, v128, p);
-    DETRB_CHECK_LAUNCH("attn_bwd_dkv_tc_kernel");
-    DETRB_LAUNCH(attn_bwd_dq_tc_kernel, dim3(ceil_div(p.Lq, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DQ, stream, q128, do128, k64, v64, p);
-    DETRB_CHECK_LAUNCH("attn_bwd_dq_tc_kernel");
+    const int parts = p.parts ? p.parts : 7;
+    if (parts & 2) {
+        DETRB_LAUNCH(attn_bwd_dkv_tc_kernel, dim3(ceil_div(p.Lk, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DKV, stream, q64, do64, k128, v128, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dkv_tc_kernel");
+    }
+    if (parts & 4) {
+        DETRB_LAUNCH(attn_bwd_dq_tc_kernel, dim3(ceil_div(p.Lq, BQ), p.H, p.B), dim3(NTHREADS), SMEM_DQ, stream, q128, do128, k64, v64, p);
+        DETRB_CHECK_LAUNCH("attn_bwd_dq_tc_kernel");
+    }
     return DETRB_OK;
 }

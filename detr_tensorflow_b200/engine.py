@@ -87,6 +87,7 @@ class Engine:
         # weight gradients run on a side stream, concurrently with the data-gradient chain (they only feed the optimizer)
         self.overlap_wgrad = self.device.type == "cuda" and not self.paired     # (parity precision: one stream, one arena)
         self.overlap_fwd = os.environ.get("DETRB_NO_FWD_FORK") is None        # forward-pass branches on the side stream
+        self.dec_fork = os.environ.get("DETRB_DEC_FORK", "1") != "0"           # decoder: value projection on a second side stream
         self.overlap_dmem = os.environ.get("DETRB_NO_DMEM_FORK") is None      # d(memory) accumulation on the side stream
         self._wstream = None
         self._pending = {}
@@ -496,14 +497,19 @@ class Engine:
         for l in range(self.ndec):
             for nm, shp in (("tq", (Mq, d)), ("qk", (Mq, 2 * d)), ("v", (Mq, d)), ("o", (Mq, d)), ("pre1", (Mq, d)),
                             ("t1", (Mq, d)), ("t1q", (Mq, d)), ("q2", (Mq, d)), ("k2", (M, d)), ("v2", (M, d)),
-                            ("o2", (Mq, d)), ("pre2", (Mq, d)), ("t2", (Mq, d)), ("h", (Mq, dff)), ("pre3", (Mq, d)),
-                            ("t3", (Mq, d))):
+                            ("o2", (Mq, d)), ("pre2", (Mq, d)), ("t2", (Mq, d)), ("h", (Mq, dff)), ("pre3", (Mq, d))):
                 buf(f"d{l}_{nm}", *shp)
             buf(f"d{l}_lse1", B * self.H * Q, dtype=F32)
             buf(f"d{l}_lse2", B * self.H * Q, dtype=F32)
-            for nm in ("mean1", "rstd1", "mean2", "rstd2", "mean3", "rstd3", "meanf", "rstdf"):
+            for nm in ("mean1", "rstd1", "mean2", "rstd2", "mean3", "rstd3"):
                 buf(f"d{l}_{nm}", Mq, dtype=F32)
         L = self.ndec
+        # the layer outputs t3 are rows of ONE buffer: the shared final norm (transformer.py:122-126) of all layers is one launch
+        # after the stack, and its backward one launch before it (d{l}_t3 below are row slices)
+        buf("t3_all", L * Mq, d)
+        buf("g_t3f", L * Mq, d)
+        buf("meanf", L * Mq, dtype=F32)
+        buf("rstdf", L * Mq, dtype=F32)
         buf("hs", L * Mq, d)
         buf("logits", L * Mq, self.C, dtype=F32)
         buf("hb1", L * Mq, d)
@@ -530,13 +536,15 @@ class Engine:
         buf("g_hs", L * Mq, d)
         buf("g_hb1", L * Mq, d)
         buf("g_hb2", L * Mq, d)
-        for nm, shp in (("gq_a", (Mq, d)), ("gq_b", (Mq, d)), ("gq_c", (Mq, d)), ("gq_d", (Mq, d)), ("gq_qk", (Mq, 2 * d)),
+        for nm, shp in (("gq_a", (Mq, d)), ("gq_b", (Mq, d)), ("gq_c", (Mq, d)), ("gq_d", (Mq, d)), ("gq_qkv", (Mq, 3 * d)),
                         ("gq_n0", (Mq, d)), ("gq_n1", (Mq, d)), ("gm_n0", (M, d)), ("gm_n1", (M, d)),
-                        ("gq_v", (Mq, d)), ("gq_h", (Mq, dff)), ("gq_q2", (Mq, d)), ("gm_k2", (M, d)), ("gm_v2", (M, d)),
+                        ("gq_h", (Mq, dff)), ("gq_q2", (Mq, d)), ("gm_k2", (M, d)), ("gm_v2", (M, d)),
                         ("g_mem", (M, d)), ("gm_a", (M, d)), ("gm_b", (M, d)), ("gm_c", (M, d)), ("gm_d", (M, d)),
-                        ("gm_qk", (M, 2 * d)), ("gm_v", (M, d)), ("gm_h", (M, dff))):
+                        ("gm_qkv", (M, 3 * d)), ("gm_h", (M, dff))):
             buf(nm, *shp)
         buf("delta", B * self.H * max(S, Q), dtype=F32)
+        buf("delta2", L * B * self.H * Q, dtype=F32)             # cross attention: per layer (its dK/dV kernel runs on the side stream)
+        buf("gq_d2", L * Mq, d)
         buf("g_x", max_elems)
         buf("g_y", max_elems)
         buf("g_1", max_elems)
@@ -558,6 +566,8 @@ class Engine:
             self.query_pos = a["query_pos"]
             self._store(self.query_pos, self.query_embed)
         self.pos = a["pos"]
+        for l in range(self.ndec):
+            a[f"d{l}_t3"] = a["t3_all"][l * Mq:(l + 1) * Mq]
         self._store(self.pos, self._pos_embedding(hh, ww))
         self.normalisers = None
 
@@ -617,7 +627,7 @@ class Engine:
         if not (self.overlap_wgrad and self._in_backward):
             return fn()
         if self._wstream is None:
-            self._wstream = torch.cuda.Stream()
+            self._wstream = self._side_stream()
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
@@ -630,21 +640,41 @@ class Engine:
             self._pending[self._key(t)] = done
         self._w_last = done
 
-    def _fork(self, fn):
-        """Run fn() on the side stream, ordered after everything enqueued on the main stream so far; returns the handle for
-        _join().  For branches of the forward pass whose inputs are ready and whose outputs are only needed later."""
+    # Stream priorities (kernel nodes of a captured graph keep the priority of the stream they were captured on).
+    # DETRB_STREAM_PRIO: 0 (default) = none, 1 = the main chain's thread blocks are placed first, 2 = the side streams' are.
+    # Measured on the full-size step (tests/time_step_env.py): 1 costs 0.4 ms -- starved weight gradients pile up behind the
+    # backward pass, where they run alone at low occupancy.
+    @staticmethod
+    def _prio_mode():
+        return int(os.environ.get("DETRB_STREAM_PRIO", "0"))
+
+    def _side_stream(self):
+        return torch.cuda.Stream(priority=-1 if self._prio_mode() == 2 else 0)
+
+    def _chain_stream(self):
+        return torch.cuda.Stream(priority=-1 if self._prio_mode() == 1 else 0)
+
+    def _fork(self, fn, lane=0):
+        """Run fn() on a side stream, ordered after everything enqueued on the main stream so far; returns the handle for
+        _join().  For branches of the forward pass whose inputs are ready and whose outputs are only needed later.
+        lane 1 is a second side stream for short branches that must not queue behind a long one on lane 0."""
         if not (self.overlap_wgrad and self.overlap_fwd):
             fn()
             return None
         if self._wstream is None:
-            self._wstream = torch.cuda.Stream()
+            self._wstream = self._side_stream()
+        side = self._wstream
+        if lane == 1:
+            if getattr(self, "_wstream2", None) is None:
+                self._wstream2 = self._side_stream()
+            side = self._wstream2
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
-        self._wstream.wait_event(ev)
-        with torch.cuda.stream(self._wstream):
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
             fn()
             done = torch.cuda.Event()
-            done.record(self._wstream)
+            done.record(side)
         return done
 
     @staticmethod
@@ -856,10 +886,17 @@ class Engine:
         for l, D in enumerate(self.dec):
             t = lambda n: a[f"d{l}_{n}"]
             W = D["sa"]["inp"]
-            ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d, split=self.plane)
-            self.launches += 1
+            vj = None
+            if self.dec_fork:                             # value projection beside the query/key projection (as in the encoder)
+                vj = self._fork(lambda: self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:]), lane=1)
+            if l == 0:                                    # (later layers: tq is the second output of the previous layer's LN3)
+                ops.add_rowbcast(tgt, self.query_pos, t("tq"), Mq, Q, d, split=self.plane)
+                self.launches += 1
             self._lin(t("tq"), W.Wf, Mq, 2 * d, d, d, out=t("qk"), bias=W.bias)
-            self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:])
+            if self.dec_fork:
+                self._join(vj)
+            else:
+                self._lin(tgt, W.Wf[2 * d:], Mq, d, d, d, out=t("v"), bias=W.bias[2 * d:])
             self.launches += 1
             ops.attn_fwd(t("qk"), t("qk")[:, d:], t("v"), 2 * d, 2 * d, d, t("o"), d, t("lse1"), B, Hh, Q, Q, scale,
                          **self._attn_drop(f"d{l}_attn1"))
@@ -878,12 +915,15 @@ class Engine:
             self._lin(t("t2"), D["l1"].Wf, Mq, dff, d, d, out=t("h"), bias=D["l1"].bias, relu=True, **self._drop(f"d{l}_dh"))
             self._lin(t("h"), D["l2"].Wf, Mq, d, dff, dff, out=t("pre3"), bias=D["l2"].bias, residual=t("t2"), ldr=d,
                       **self._drop(f"d{l}_do3"))
-            self._ln_fwd(t("pre3"), D["n3"], t("t3"), t("mean3"), t("rstd3"), Mq)
-            # shared final norm on every layer output (transformer.py:122-126)
-            self._ln_fwd(t("t3"), self.dec_norm, a["hs"][l * Mq:(l + 1) * Mq], t("meanf"), t("rstdf"), Mq)
+            if l + 1 < self.ndec:
+                self._ln_fwd(t("pre3"), D["n3"], t("t3"), t("mean3"), t("rstd3"), Mq, y2=a[f"d{l + 1}_tq"], pos=self.query_pos, S=Q)
+            else:
+                self._ln_fwd(t("pre3"), D["n3"], t("t3"), t("mean3"), t("rstd3"), Mq)
             tgt = t("t3")
-        # ---------------- heads (detr.py:185-188)
+        # shared final norm on every layer output (transformer.py:122-126): one launch over the six layers' rows
         LM = self.ndec * Mq
+        self._ln_fwd(a["t3_all"], self.dec_norm, a["hs"], a["meanf"], a["rstdf"], LM)
+        # ---------------- heads (detr.py:185-188)
         self._lin(a["hs"], self.h_cls.Wf, LM, self.C, d, d, Cf=a["logits"], ldcf=self.C, bias=self.h_cls.bias)
         self._lin(a["hs"], self.h_b0.Wf, LM, d, d, d, out=a["hb1"], bias=self.h_b0.bias, relu=True)
         self._lin(a["hb1"], self.h_b1.Wf, LM, d, d, d, out=a["hb2"], bias=self.h_b1.bias, relu=True)
@@ -992,6 +1032,8 @@ class Engine:
         self._lin_wgrad(self.h_cls, a["hs"], a["d_logits"], LM, ldy=self.ld_dl)
         self._lin(a["d_logits"], self.h_cls.Wd, LM, d, self.ld_dl, self.ld_dl, out=a["g_hs"], residual=a["g_hs"], ldr=d)
         # ---------------- decoder, last layer first
+        # final-norm branch of every layer at once: g_t3f[l] = LN_f'(g_hs[l])
+        self._ln_bwd(a["g_hs"], None, a["t3_all"], self.dec_norm, a["meanf"], a["rstdf"], a["g_t3f"], None, LM)
         mem, memp = self.mem, self.memp
         g_next = None                      # gradient wrt t3 coming from layer l+1 (None for the last layer)
         first_mem = True
@@ -999,10 +1041,8 @@ class Engine:
             D = self.dec[l]
             t = lambda n: a[f"d{l}_{n}"]
             tgt = a["tgt0"] if l == 0 else a[f"d{l - 1}_t3"]
-            # final-norm branch: d t3 += LN_f'(g_hs[l])
-            self._ln_bwd(a["g_hs"][l * Mq:(l + 1) * Mq], None, t("t3"), self.dec_norm, t("meanf"), t("rstdf"), a["gq_a"], None, Mq)
-            # LN3
-            self._ln_bwd(a["gq_a"], g_next, t("pre3"), D["n3"], t("mean3"), t("rstd3"), a["gq_b"], a["gq_c"], Mq, f"d{l}_do3")
+            # LN3 (d t3 = the final-norm branch + the gradient from layer l+1)
+            self._ln_bwd(a["g_t3f"][l * Mq:(l + 1) * Mq], g_next, t("pre3"), D["n3"], t("mean3"), t("rstd3"), a["gq_b"], a["gq_c"], Mq, f"d{l}_do3")
             # FFN: pre3 = t2 + drop(h W2 + b2), h = drop(relu(t2 W1 + b1))
             self._lin_wgrad(D["l2"], t("h"), a["gq_c"], Mq)
             self._lin(a["gq_c"], D["l2"].Wd, Mq, dff, d, d, out=a["gq_h"], mask=t("h"), ldm=dff, mask_scale=inv_keep)
@@ -1013,11 +1053,23 @@ class Engine:
             # cross attention: pre2 = t1 + drop(o2 Wo + bo)
             Wo, W = D["ca"]["out"], D["ca"]["inp"]
             self._lin_wgrad(Wo, t("o2"), a["gq_c"], Mq)
-            self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o2
+            nd = B * Hh * Q
+            dO2, delta2 = a["gq_d2"][l * Mq:(l + 1) * Mq], a["delta2"][l * nd:(l + 1) * nd]      # per layer: read on the side stream
+            self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=dO2)                                                  # d o2
             self.launches += 3
-            self._before_write(a["gq_q2"], a["gm_k2"], a["gm_v2"], a["delta"])
-            ops.attn_bwd(t("q2"), t("k2"), t("v2"), t("o2"), a["gq_d"], d, d, d, d, d, t("lse2"), a["delta"],
-                         a["gq_q2"], a["gm_k2"], a["gm_v2"], d, d, d, B, Hh, Q, S, scale, **self._attn_drop(f"d{l}_attn2"))
+            xargs = (t("q2"), t("k2"), t("v2"), t("o2"), dO2, d, d, d, d, d, t("lse2"), delta2,
+                     a["gq_q2"], a["gm_k2"], a["gm_v2"], d, d, d, B, Hh, Q, S, scale)
+            xkw = self._attn_drop(f"d{l}_attn2")
+            self._before_write(a["gq_q2"])
+            if self.dec_fork and self.overlap_wgrad:
+                # only dQ continues the decoder's chain; dK / dV (1050 keys) feed the weight gradients and d(memory), which
+                # live on the side stream anyway: the kernel goes there, in order with its consumers
+                ops.attn_bwd(*xargs, parts=1, **xkw)
+                self._on_wstream(lambda: ops.attn_bwd(*xargs, parts=2, **xkw), (dO2, delta2))
+                ops.attn_bwd(*xargs, parts=4, **xkw)
+            else:
+                self._before_write(a["gm_k2"], a["gm_v2"])
+                ops.attn_bwd(*xargs, **xkw)
             self._lin_wgrad(W, t("t1q"), a["gq_q2"], Mq, n_off=0, n_rows=d)
             self._lin_wgrad(W, memp, a["gm_k2"], M, n_off=d, n_rows=d)
             self._lin_wgrad(W, mem, a["gm_v2"], M, n_off=2 * d, n_rows=d)
@@ -1039,17 +1091,26 @@ class Engine:
             self._lin_wgrad(Wo, t("o"), a["gq_c"], Mq)
             self._lin(a["gq_c"], Wo.Wd, Mq, d, d, d, out=a["gq_d"])                                             # d o
             self.launches += 3
-            self._before_write(a["gq_qk"], a["gq_v"], a["delta"])
-            ops.attn_bwd(t("qk"), t("qk")[:, d:], t("v"), t("o"), a["gq_d"], 2 * d, 2 * d, d, d, d, t("lse1"), a["delta"],
-                         a["gq_qk"], a["gq_qk"][:, d:], a["gq_v"], 2 * d, 2 * d, d, B, Hh, Q, Q, scale,
-                         **self._attn_drop(f"d{l}_attn1"))
-            self._lin_wgrad(W, t("tq"), a["gq_qk"], Mq, n_off=0, n_rows=2 * d)
-            self._lin_wgrad(W, tgt, a["gq_v"], Mq, n_off=2 * d, n_rows=d)
+            # dq | dk | dv are the three column blocks of ONE [rows, 3d] buffer: the gradient wrt the layer input is a single
+            # GEMM over K = 3d against the whole in-projection
+            gqkv = a["gq_qkv"]
+            self._before_write(gqkv, a["delta"])
+            sargs = (t("qk"), t("qk")[:, d:], t("v"), t("o"), a["gq_d"], 2 * d, 2 * d, d, d, d, t("lse1"), a["delta"],
+                     gqkv, gqkv[:, d:], gqkv[:, 2 * d:], 3 * d, 3 * d, 3 * d, B, Hh, Q, Q, scale)
+            skw = self._attn_drop(f"d{l}_attn1")
+            if self.dec_fork:                             # dK/dV beside dQ (both short: 100 queries x 100 keys per head)
+                ops.attn_bwd(*sargs, parts=1, **skw)
+                kvj = self._fork(lambda: ops.attn_bwd(*sargs, parts=2, **skw), lane=1)
+                ops.attn_bwd(*sargs, parts=4, **skw)
+                self._join(kvj)
+            else:
+                ops.attn_bwd(*sargs, **skw)
+            self._lin_wgrad(W, t("tq"), gqkv, Mq, ldy=3 * d, n_off=0, n_rows=2 * d)
+            self._lin_wgrad(W, tgt, gqkv[:, 2 * d:], Mq, ldy=3 * d, n_off=2 * d, n_rows=d)
             if l > 0:
                 # d tgt = d_pre1 + dqk.Wqk (tq = tgt + query_pos) + dv.Wv   -> gradient wrt the previous layer's t3
-                self._lin(a["gq_qk"], W.Wd, Mq, d, 2 * d, W.ldd, out=a["gq_a"], residual=a["gq_b"], ldr=d)
                 g_next = a["gq_n0"] if (l & 1) else a["gq_n1"]       # ping-pong: read by layer l-1's LN3 backward
-                self._lin(a["gq_v"], W.Wd[:, :, 2 * d:], Mq, d, d, W.ldd, out=g_next, residual=a["gq_a"], ldr=d)
+                self._lin(gqkv, W.Wd, Mq, d, 3 * d, W.ldd, out=g_next, residual=a["gq_b"], ldr=d)
         self._mark("bwd_heads_decoder")
         # ---------------- encoder, last layer first.  g_mem = d y2 (last encoder layer output incl. its +pos use)
         self._join_wgrad()                                     # g_mem (and the decoder's weight gradients) complete
@@ -1069,16 +1130,16 @@ class Engine:
             self._lin_wgrad(Wo, e("o"), a["gm_b"], M)
             self._lin(a["gm_b"], Wo.Wd, M, d, d, d, out=a["gm_c"])                                             # d o
             self.launches += 3
-            self._before_write(a["gm_qk"], a["gm_v"], a["delta"])
+            gqkv = a["gm_qkv"]                                 # dq | dk | dv column blocks of one buffer (see the decoder)
+            self._before_write(gqkv, a["delta"])
             self._probed(f"e{l}_attn#bwd", lambda: ops.attn_bwd(
                 e("qk"), e("qk")[:, d:], e("v"), e("o"), a["gm_c"], 2 * d, 2 * d, d, d, d, e("lse"), a["delta"],
-                a["gm_qk"], a["gm_qk"][:, d:], a["gm_v"], 2 * d, 2 * d, d, B, Hh, S, S, scale, **self._attn_drop(f"e{l}_attn")))
-            self._lin_wgrad(W, xinp, a["gm_qk"], M, n_off=0, n_rows=2 * d)
-            self._lin_wgrad(W, xin, a["gm_v"], M, n_off=2 * d, n_rows=d)
-            # d x = d_pre1 + dqk.Wqk + dv.Wv   (xp = x + pos shares x's gradient)
-            self._lin(a["gm_qk"], W.Wd, M, d, 2 * d, W.ldd, out=a["gm_c"], residual=a["gm_a"], ldr=d)
+                gqkv, gqkv[:, d:], gqkv[:, 2 * d:], 3 * d, 3 * d, 3 * d, B, Hh, S, S, scale, **self._attn_drop(f"e{l}_attn")))
+            self._lin_wgrad(W, xinp, gqkv, M, ldy=3 * d, n_off=0, n_rows=2 * d)
+            self._lin_wgrad(W, xin, gqkv[:, 2 * d:], M, ldy=3 * d, n_off=2 * d, n_rows=d)
+            # d x = d_pre1 + [dq | dk | dv] . W_in   (xp = x + pos shares x's gradient): one GEMM over K = 3d
             g_y = a["gm_n0"] if (l & 1) else a["gm_n1"]
-            self._lin(a["gm_v"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=g_y, residual=a["gm_c"], ldr=d)
+            self._lin(gqkv, W.Wd, M, d, 3 * d, W.ldd, out=g_y, residual=a["gm_a"], ldr=d)
         self._mark("bwd_encoder")
         reached(0)
         # ---------------- input_proj
@@ -1313,7 +1374,7 @@ class Engine:
         n0 = self.launches
         if not dist_on:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._chain_stream()):
                 part1()
                 part2()
             self.launches_per_step = self.launches - n0
@@ -1324,7 +1385,7 @@ class Engine:
         import gc
         graphs = []
         pool = torch.cuda.graph_pool_handle()
-        cap = torch.cuda.Stream()
+        cap = self._chain_stream()
 
         def begin():
             g = torch.cuda.CUDAGraph()
@@ -1384,7 +1445,7 @@ class Engine:
         import gc
         graphs = []
         pool = torch.cuda.graph_pool_handle()
-        cap = torch.cuda.Stream()
+        cap = self._chain_stream()
 
         def begin():
             g = torch.cuda.CUDAGraph()
@@ -1444,7 +1505,7 @@ class Engine:
                 self._gs_graph = self._capture_bucketed(body)
             else:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                with torch.cuda.graph(g, stream=self._chain_stream(), capture_error_mode="thread_local"):
                     body()
                 self._gs_graph = g
             self._gs_key = key

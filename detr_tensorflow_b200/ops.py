@@ -106,13 +106,13 @@ def attn_fwd(Q, K, V, ldq, ldk, ldv, O, ldo, lse, B, H, Lq, Lk, scale, drop_p=0.
 
 
 def attn_bwd(Q, K, V, O, dO, ldq, ldk, ldv, ldo, lddo, lse, delta, dQ, dK, dV, lddq, lddk, lddv, B, H, Lq, Lk,
-             scale, drop_p=0.0, seed=0, site=0, seed_ptr=None, split=0):
+             scale, drop_p=0.0, seed=0, site=0, seed_ptr=None, split=0, parts=0):
     p = AttnBwdParams()
     p.Q, p.K, p.V, p.O, p.dO = ptr(Q), ptr(K), ptr(V), ptr(O), ptr(dO)
     p.ldq, p.ldk, p.ldv, p.ldo, p.lddo = ldq, ldk, ldv, ldo, lddo
     p.lse, p.delta, p.dQ, p.dK, p.dV = ptr(lse), ptr(delta), ptr(dQ), ptr(dK), ptr(dV)
     p.lddq, p.lddk, p.lddv, p.B, p.H, p.Lq, p.Lk = lddq, lddk, lddv, B, H, Lq, Lk
-    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr, p.split = scale, drop_p, seed, site, ptr(seed_ptr), split
+    p.scale, p.drop_p, p.seed, p.site, p.seed_ptr, p.split, p.parts = scale, drop_p, seed, site, ptr(seed_ptr), split, parts
     check(_lib.lib().detrb_attn_bwd(byref(p), _stream()))
 
 

@@ -188,6 +188,8 @@ typedef struct {
     float scale;
     float drop_p; uint64_t seed; uint32_t site; const uint64_t *seed_ptr;
     int64_t split;               /* parity precision: plane stride of the bf16 pairs of every bf16 operand (0 = plain bf16) */
+    int parts;                   /* 0 = everything; else a mask of the launches to enqueue: 1 = delta, 2 = dK/dV, 4 = dQ.  Lets a caller
+                                  * put the dK/dV kernel on another stream than the delta -> dQ chain (dK/dV and dQ both need delta) */
 } detrb_attn_bwd_t;
 int detrb_attn_bwd(const detrb_attn_bwd_t *p, detrb_stream_t stream);
 

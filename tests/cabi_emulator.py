@@ -347,9 +347,12 @@ class FakeLib:
         dO = RD(p.dO, B * Lq, H * 32, p.lddo, sp).view(B, Lq, -1)
         o, _ = self._attn_core(Q, K, V, p, B, H, Lq, Lk)
         gq, gk, gv = torch.autograd.grad(o, [Q, K, V], dO)
-        WR(p.dQ, B * Lq, H * 32, p.lddq, gq.reshape(B * Lq, -1), sp)
-        WR(p.dK, B * Lk, H * 32, p.lddk, gk.reshape(B * Lk, -1), sp)
-        WR(p.dV, B * Lk, H * 32, p.lddv, gv.reshape(B * Lk, -1), sp)
+        parts = int(p.parts) or 7                     # 1 = delta (no observable output here), 2 = dK/dV, 4 = dQ
+        if parts & 4:
+            WR(p.dQ, B * Lq, H * 32, p.lddq, gq.reshape(B * Lq, -1), sp)
+        if parts & 2:
+            WR(p.dK, B * Lk, H * 32, p.lddk, gk.reshape(B * Lk, -1), sp)
+            WR(p.dV, B * Lk, H * 32, p.lddv, gv.reshape(B * Lk, -1), sp)
         return 0
 
     # -- layer norm
