@@ -763,6 +763,279 @@ gemm_tcp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+// ================================================================================================ CTA-pair variant
+// gemm_pair_kernel: the persistent kernel above on a CTA PAIR (cluster of two SMs of one TPC, tcgen05 cta_group::2).  One pair owns a
+// 256 x BN tile: each CTA stages ITS 128 rows of A and ITS half (BN / 2 weight rows) of W, the leader CTA's single thread issues
+// 256 x BN x 16 MMAs that read both CTAs' shared memory and write both CTAs' tensor memory (128 lanes each).  Per SM the operand
+// traffic of one k-step is 4 KB (A) + BN / 2 rows of W instead of BN rows: 64 B/clk at BN = 256 where the single-CTA 128 x 256
+// tile needs 96 B/clk -- the shared-memory operand fetch (~64-70 B/clk measured) is what held that kernel at ~0.62 of the tensor
+// peak.  Barrier protocol (CUTLASS sm100 2-SM pipelines): the smem-full barriers live in the LEADER (both CTAs' TMA loads signal
+// them through the shared::cluster window, peer bit cleared; the leader's producer expects the bytes of both), smem-empty and
+// tmem-full are multicast to both CTAs by tcgen05.commit, tmem-empty is the leader's and takes the arrivals of both CTAs'
+// epilogue warps.  Epilogue: the straight-line chunk (bias / residual / ReLU / bit masks / dropout), per CTA as above.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;             // shared::cluster address of the same offset in CTA 0 of the pair
+
+template <int BN, int PST>
+struct PairLayout {
+    static constexpr int A_BYTES = TBM * TBK * 2;
+    static constexpr int B_BYTES = (BN / 2) * TBK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NCH = BN / 64;
+    static constexpr int NACC = 512 / BN;                                 // 2 (BN = 256) or 4 (BN = 128) accumulators: all of TMEM
+    static constexpr int OBUF = PST * STAGE_BYTES;                        // one [128 x 64] output staging tile per warpgroup
+    static constexpr int RING = OBUF + 2 * 16384;                         // residual ring (two slots)
+    static constexpr int TOTAL = 227 * 1024;
+    static constexpr int BAR_OFF = TOTAL - 1024 - 1024;
+    static constexpr int BIAS_OFF = BAR_OFF + 512;
+    static_assert(BAR_OFF - RING >= 2 * 16384, "pair GEMM: stages do not fit");
+};
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c, int w, int h, int n,
+                                                     uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 :: "r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA 0 of the pair (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int BN, int PST, bool IM2COL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS_P, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+                 const detrb_igemm_t p, const ConvAux aux, const int n_tiles_n, const int n_tiles)
+{
+    using L = PairLayout<BN, PST>;
+    constexpr int NACC = L::NACC, RS = 2;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + L::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (PST + s); };
+    auto tmem_full = [&](int a) { return bar_base + 8u * (2 * PST + a); };
+    auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * PST + NACC + a); };
+    auto resid_full = [&](int i) { return bar_base + 8u * (2 * PST + 2 * NACC + i); };
+    auto resid_empty = [&](int i) { return bar_base + 8u * (2 * PST + 2 * NACC + RS + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * PST + 2 * NACC + 2 * RS);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int nk = p.K / TBK;
+    const bool has_r = p.residual != nullptr;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        tma_prefetch_desc(&map_c);
+        if (has_r) tma_prefetch_desc(&map_r);
+        for (int s = 0; s < PST; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < NACC; a++) { mbar_init(tmem_full(a), 1); mbar_init(tmem_empty(a), 16); }
+        for (int i = 0; i < RS; i++) { mbar_init(resid_full(i), 1); mbar_init(resid_empty(i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    cluster_sync_all();                 // both CTAs' barriers initialised (the peer signals the leader's), TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== A / W producer (both CTAs: own 128 rows of A, own half of W) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / n_tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (tile % n_tiles_n) * BN + (int)rank * (BN / 2);
+                int w0 = 0, h0 = 0, img = 0;
+                if (IM2COL) {
+                    const int ohw = p.OH * p.OW;
+                    img = m0 / ohw;
+                    const int rem = m0 - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                    const int st = p.mode == 0 ? p.stride : 1;
+                    w0 = ox * st - aux.pad; h0 = oy * st - aux.pad;
+                }
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+                    const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+                    if (IM2COL) {
+                        const int k0 = kb * TBK, tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
+                        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                        tma_load_im2col_pair(a_dst, &map_a, full_bar(stage), c0, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                        tma_load_2d_pair(a_dst + L::A_BYTES, &map_b, full_bar(stage), aux.wtap[tap] * p.Cin + c0, n0);
+                    } else {
+                        tma_load_2d_pair(a_dst, &map_a, full_bar(stage), kb * TBK, m0);
+                        tma_load_2d_pair(a_dst + L::A_BYTES, &map_b, full_bar(stage), kb * TBK, n0);
+                    }
+                    if (++stage == PST) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(2 * TBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs, it++) {
+                const int acc = it % NACC;
+                mbar_wait(tmem_empty(acc), ((it / NACC) & 1) ^ 1);        // the epilogue warps of BOTH CTAs have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nk; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * L::STAGE_BYTES;
+                    const uint64_t da = make_smem_desc(a_addr), db = make_smem_desc(a_addr + L::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; k++)
+                        tc_mma_f16_pair(d_addr, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    tc_commit_pair(empty_bar(stage));
+                    if (++stage == PST) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(tmem_full(acc));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== residual producer (one ring slot per 64-column chunk of this CTA's 128 rows) =====================
+        if (lane == 0 && has_r) {
+            int g = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int m0 = (tile / n_tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (tile % n_tiles_n) * BN;
+                for (int cb = 0; cb < L::NCH; cb++, g++) {
+                    const int slot = g % RS;
+                    mbar_wait(resid_empty(slot), ((g / RS) & 1) ^ 1);
+                    mbar_expect_tx(resid_full(slot), 16384u);
+                    tma_load_2d(smem_base + L::RING + (uint32_t)slot * 16384u, &map_r, resid_full(slot), n0 + cb * 64, m0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue: chunk g goes to warpgroup g % 2 =====================
+        const int wg = (warp - 4) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+        const bool leader = (q == 0 && lane == 0);
+        const uint32_t obuf = smem_base + L::OBUF + (uint32_t)wg * 16384u;
+        const uint32_t sbias = smem_base + L::BIAS_OFF + (uint32_t)wg * 256u;
+        const uint32_t thresh = dropout_thresh16(p.drop_p);
+        const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+        const uint64_t seed = p.seed ^ ((p.drop_p > 0.f && p.seed_ptr) ? *p.seed_ptr : 0ull);
+        int it = 0, g = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs, it++) {
+            const int m0 = (tile / n_tiles_n) * (2 * TBM) + (int)rank * TBM, n0 = (tile % n_tiles_n) * BN;
+            const int acc = it % NACC;
+            const int m = m0 + row;
+            uint2 mb_cur[L::NCH];
+#pragma unroll
+            for (int i = 0; i < L::NCH; i++) mb_cur[i] = make_uint2(0u, 0u);
+            if (p.mask_bits && m < p.M) {
+                const uint8_t *mp = p.mask_bits + (size_t)m * p.ldmb + (n0 >> 3);
+#pragma unroll
+                for (int i = 0; i < L::NCH; i++) mb_cur[i] = ld_bits8(mp + 8 * i);
+            }
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            mbar_wait(tmem_full(acc), (it / NACC) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < L::NCH; cb++, g++) {
+                if ((g & 1) != wg) continue;
+                const int nb = n0 + cb * 64;
+                int slot = 0;
+                uint32_t rbuf = 0;
+                if (has_r) {
+                    slot = g % RS;
+                    mbar_wait(resid_full(slot), (g / RS) & 1);
+                    rbuf = smem_base + L::RING + (uint32_t)slot * 16384u;
+                }
+                if (q < 2) {                                    // this chunk's 64 bias values -> smem (visible after the barrier below)
+                    const int t = q * 32 + lane;
+                    const float b = (p.bias && nb + t < p.N) ? p.bias[nb + t] : 0.f;
+                    asm volatile("st.shared.f32 [%0], %1;" :: "r"(sbias + 4u * t), "f"(b) : "memory");
+                }
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the last store has read the staging tile
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+                uint2 mbc = mb_cur[0], ob = make_uint2(0u, 0u);
+#pragma unroll
+                for (int i = 1; i < L::NCH; i++) if (cb == i) mbc = mb_cur[i];
+                uint32_t acc_r[64];
+                tc_ld64(t_addr + (uint32_t)(cb * 64), acc_r);
+                uint4 rr[8];
+                if (has_r) lds_row8(rr, rbuf + row_off, sw);
+                tc_wait_ld();
+                const bool relu = p.relu != 0;
+                if (p.drop_p > 0.f) {
+                    EpiDrop dr;
+                    dr.rowhash = dropout_rowhash(seed, p.site, (uint32_t)m); dr.thresh = thresh; dr.col0 = (uint32_t)nb; dr.scale = drop_scale;
+                    if (has_r) epi_chunk_math<true, false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw, dr);
+                    else epi_chunk_math<false, false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw, dr);
+                } else if (has_r) {
+                    if (p.mask_bits) epi_chunk_math<true, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, obuf + row_off, sw);
+                    else if (p.out_bits) epi_chunk_math<true, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                    else epi_chunk_math<true, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                } else {
+                    if (p.mask_bits) epi_chunk_math<false, true, false>(acc_r, rr, sbias, relu, mbc, p.mask_scale, ob, obuf + row_off, sw);
+                    else if (p.out_bits) epi_chunk_math<false, false, true>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                    else epi_chunk_math<false, false, false>(acc_r, rr, sbias, relu, mbc, 1.f, ob, obuf + row_off, sw);
+                }
+                if (p.out_bits && m < p.M) *reinterpret_cast<uint2 *>(p.out_bits + (size_t)m * p.ldob + (nb >> 3)) = ob;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + wg) : "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 :: "l"(&map_c), "r"(obuf), "r"(nb), "r"(m0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (has_r && lane == 0) mbar_arrive(resid_empty(slot));
+            }
+            // this warp is done with the accumulator of this tile: one arrival on the LEADER's barrier (16 = 8 warps x 2 CTAs)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tmem_empty(acc));
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                 // no CTA of the pair leaves (or frees TMEM) while the other may still signal it or read its smem
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ================================================================================================ streaming variant
 // The HBM-bound 1x1 layers of layer1 / layer2 (M = 133600 .. 534400 rows, K and N in 64 .. 512): 2-8 flops per byte, the job is
 // to keep the memory system full.  One persistent CTA per SM owns a fixed column range of BN <= 256 columns and streams 128-row
@@ -1039,6 +1312,8 @@ static int g_r_early = 1;            // early residual fetch: 0 never, 1 policy 
 static int g_deep_small = 1;         // one stage per k-block for K <= 256 on latency-bound grids           (env DETRB_DEEP_SMALL)
 static int g_one_stage = 1;          // one-stage kernel for K = 64                                          (env DETRB_ONE_STAGE)
 static int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
+static int g_tc_pair = 0;            // CTA-pair kernel: 0 off, 1 for 256-wide tiles, 2 for 128- and 256-wide tiles   (env DETRB_PAIR)
+static int g_tc_pair_forced = -1;    // detrb_set_tc_pair() overrides the environment
 static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
@@ -1120,6 +1395,39 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         int rs = slot ? (PL::RING_BYTES / slot) & ~1 : 0;
         if (rs > MAXRS) rs = MAXRS;
         if (slot && rs < 2) DETRB_FAIL(DETRB_E_SHAPE, "persistent gemm_tc: no room for the residual / mask ring");
+        if constexpr (BN >= 128 && OB == 1) {
+            // CTA-pair kernel (cta_group::2): 256 x BN tiles, the straight-line epilogue only
+            static int pair_mode = -1;                     // env DETRB_PAIR: 0 off, 1 BN = 256, 2 BN = 128 and 256
+            if (pair_mode < 0) { const char *e = getenv("DETRB_PAIR"); pair_mode = e ? atoi(e) : g_tc_pair; }
+            const int mode = g_tc_pair_forced >= 0 ? g_tc_pair_forced : pair_mode;
+            if (mode >= (BN == 256 ? 1 : 2) && !p.mask && !p.sigmoid && p.N % BN == 0 && p.K % TBK == 0 && !p.a_kb_rows && p.M > TBM) {
+                constexpr int QST = BN == 256 ? 5 : 6;
+                using QL = PairLayout<BN, QST>;
+                static bool qconfigured = false;
+                static int max_pairs = 74;
+                if (!qconfigured) {
+                    DETRB_CUDA(cudaFuncSetAttribute((gemm_pair_kernel<BN, QST, IM2COL>), cudaFuncAttributeMaxDynamicSharedMemorySize, QL::TOTAL));
+                    cudaLaunchConfig_t qc = {};
+                    qc.gridDim = dim3(2 * 74); qc.blockDim = dim3(NTHREADS_P); qc.dynamicSmemBytes = QL::TOTAL;
+                    cudaLaunchAttribute qa[1];
+                    qa[0].id = cudaLaunchAttributeClusterDimension;
+                    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                    qc.attrs = qa; qc.numAttrs = 1;
+                    int nc = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nc, (gemm_pair_kernel<BN, QST, IM2COL>), &qc) == cudaSuccess && nc > 0) max_pairs = nc;
+                    else (void)cudaGetLastError();
+                    qconfigured = true;
+                }
+                CUtensorMap mbh;
+                if (!make_map(&mbh, p.W, (uint64_t)p.N, w_cols, (uint64_t)p.ldw, BN / 2))
+                    DETRB_FAIL(DETRB_E_CUDA, "gemm_tc pair: cuTensorMapEncodeTiled(W half) failed (N=%d K=%d ldw=%d)", p.N, p.K, p.ldw);
+                const int qtn = p.N / BN, qtiles = qtn * ceil_div(p.M, 2 * TBM);
+                const int pairs = qtiles < max_pairs ? qtiles : max_pairs;
+                DETRB_LAUNCH((gemm_pair_kernel<BN, QST, IM2COL>), dim3(2 * pairs), dim3(NTHREADS_P), QL::TOTAL, stream, ma, mbh, mc, mr, p, aux, qtn, qtiles);
+                DETRB_CHECK_LAUNCH("gemm_pair_kernel");
+                return DETRB_OK;
+            }
+        }
         const int ntn = ceil_div(p.N, BN), ntiles = ntn * ceil_div(p.M, TBM);
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
         DETRB_LAUNCH((gemm_tcp_kernel<BN, STAGES, IM2COL, OB>), dim3(grid_p), dim3(NTHREADS_P), PL::TOTAL, stream, ma, mb, mc, mr, mm, p, aux, ntn, ntiles, rs);
@@ -1285,6 +1593,7 @@ extern "C" int detrb_set_tc_persistent(int enable)
     g_tc_persistent = enable;
     return old;
 }
+extern "C" int detrb_set_tc_pair(int mode) { int old = g_tc_pair_forced; g_tc_pair_forced = mode; return old; }
 extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
 static int g_tc_conv_enabled = 1;
 extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }

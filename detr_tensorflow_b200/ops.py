@@ -75,6 +75,11 @@ def set_tc_stream(enable):
     return _lib.lib().detrb_set_tc_stream(c_int(int(enable)))
 
 
+def set_tc_pair(mode):
+    """CTA-pair persistent GEMM (cta_group::2): 0 off, 1 256-wide tiles, 2 128- and 256-wide tiles, -1 environment; returns the old mode."""
+    return int(_lib.lib().detrb_set_tc_pair(c_int(mode)))
+
+
 def set_tc_halo(enable):
     return _lib.lib().detrb_set_tc_halo(c_int(int(enable)))
 

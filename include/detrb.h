@@ -130,6 +130,10 @@ int detrb_set_tc_tma_epilogue(int enable);
 int detrb_set_tc_persistent(int enable);     /* persistent tile loop (one CTA per SM, epilogue overlapped with the next main loop) */   /* coalesced TMA-load/TMA-store epilogue of the tcgen05 kernel (default on) */   /* gathered convolutions (TMA im2col) on the tcgen05 kernel too (default on when tc is on) */
 int detrb_set_tc_stream(int enable);         /* streaming kernel for the HBM-bound 1x1 layers (weights resident in shared memory): 0 off, 1 auto, 2 wherever supported */
 int detrb_set_tc_halo(int enable);           /* halo-reusing row kernel for 3x3 / stride 1 / 64 -> 64 channel convolutions (conv_halo.cu): 0 off, 1 on */
+/* CTA-pair persistent GEMM (gemm_pair_kernel: tcgen05 cta_group::2, 256 x BN tiles shared by the two SMs of a TPC).
+ * mode 0 = off, 1 = for the 256-wide tiles, 2 = for the 128- and 256-wide tiles, -1 = follow the environment (DETRB_PAIR).
+ * Returns the previous mode.  Results are bit-identical to the single-CTA persistent kernel (same products, same order). */
+int detrb_set_tc_pair(int mode);
 int detrb_gemm_tc_force(const detrb_igemm_t *p, int bn, detrb_stream_t stream);
 
 /* Weight gradient  dW[N,K] (+)= rowscale[n] * sum_m dY[m,n] * gather(A)[m,k]   (fp32 atomics)

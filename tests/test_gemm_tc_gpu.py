@@ -515,3 +515,83 @@ def test_stride2_scatter_through_the_dense_workspace(B, H, W, Ci, Co):
     assert torch.equal(outs[1][:M][odd.view(-1)], base[:M][odd.view(-1)])            # only the even pixels are touched
     check("shortcut scatter", outs[1][:M], outs[0][:M], 1e-2, 2e-2)
     assert not torch.equal(outs[1][:M], base[:M])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["plain256", "resid_bits256", "maskbits256", "dropout256", "plain128", "conv256", "conv256_dgrad", "conv128",
+                                  "tail256"])
+def test_gemm_pair_kernel(case):
+    """gemm_pair_kernel (tcgen05 cta_group::2: one 256 x BN tile per CTA pair, each CTA stages its 128 rows of A and its half of W):
+    bit for bit against the single-CTA persistent kernel (same products, same accumulation order, same epilogue), plus fp32 PyTorch.
+    Odd counts of 128-row tiles (the peer CTA of the last pair entirely past M), residual ring, 1-bit masks in / out, dropout,
+    im2col operands (3x3 convolution forward and data gradient), 128- and 256-wide tiles."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from detr_tensorflow_b200 import ops
+    kw, geom, ref = {}, None, None
+    if case in ("plain256", "resid_bits256", "maskbits256", "dropout256", "plain128", "tail256"):
+        M, N, K = {"plain256": (33600, 256, 1024), "resid_bits256": (33600, 512, 512), "maskbits256": (20000, 256, 2048),
+                   "dropout256": (8400, 256, 2048), "plain128": (33600, 128, 1152), "tail256": (129, 256, 1024)}[case]
+        A = rnd(M, K, seed=1).to(BF)
+        W = rnd(N, K, scale=K ** -0.5, seed=2).to(BF)
+        bias = rnd(N, seed=3)
+        geom = ops.plain_geom(M, K)
+        kw = dict(bias=bias, relu=case in ("plain256", "resid_bits256", "plain128", "tail256"))
+        ref = A.float() @ W.float().t() + bias
+        if case == "resid_bits256":
+            R = rnd(M, N, seed=4).to(BF)
+            kw.update(residual=R, ldr=N)
+            ref = ref + R.float()
+        if kw["relu"]:
+            ref = F.relu(ref)
+        if case == "maskbits256":
+            mb = torch.randint(0, 256, (M, N // 8), dtype=torch.uint8, generator=torch.Generator().manual_seed(7)).cuda()
+            kw.update(mask_bits=mb, ldmb=N // 8, mask_scale=1.25)
+            ref = ref * _bits_to_bool(mb, N) * 1.25
+        if case == "dropout256":
+            R = rnd(M, N, seed=4).to(BF)
+            kw.update(residual=R, ldr=N, drop_p=0.1, seed=1234, site=5)
+            ref = None
+        lda, ldw = K, K
+    else:
+        B, H, Wd, Cc = {"conv256": (8, 50, 84, 256), "conv256_dgrad": (3, 50, 84, 256), "conv128": (2, 100, 167, 128)}[case]
+        mode = 1 if case == "conv256_dgrad" else 0
+        x = rnd(B, H, Wd, Cc, seed=1).to(BF)
+        w = rnd(Cc, 3, 3, Cc, scale=(9 * Cc) ** -0.5, seed=2).to(BF)
+        M, N, K = B * H * Wd, Cc, 9 * Cc
+        A, W, lda, ldw = x, w, Cc, K
+        geom = conv_geom(B, H, Wd, Cc, H, Wd, 3, 3, 1, 1, mode=mode)
+        if mode == 0:
+            bias = rnd(Cc, seed=3)
+            kw = dict(bias=bias, relu=True)
+            ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias=bias, padding=1).permute(0, 2, 3, 1)).reshape(M, N)
+        else:
+            W = w.reshape(Cc, 9, Cc).permute(2, 1, 0).contiguous()
+            xt = torch.zeros(B, Cc, H, Wd, device="cuda", requires_grad=True)
+            o = F.conv2d(xt, w.float().permute(0, 3, 1, 2), padding=1)
+            gx, = torch.autograd.grad(o, [xt], x.float().permute(0, 3, 1, 2))
+            ref = gx.permute(0, 2, 3, 1).reshape(M, N)
+    want_bits = case == "resid_bits256"
+    res = {}
+    oldp = ops.set_tc_persistent(2)
+    try:
+        for pair in (2, 0):
+            old = ops.set_tc_pair(pair)
+            try:
+                y = torch.full((M + 1, N), 7.0, dtype=BF, device="cuda")
+                ob = torch.full((M + 1, N // 8), 0x5A, dtype=torch.uint8, device="cuda")
+                extra = dict(out_bits=ob, ldob=N // 8) if want_bits else {}
+                ops.igemm(A, W, M, N, K, lda, ldw, geom, C=y, ldc=N, **kw, **extra)
+                torch.cuda.synchronize()
+            finally:
+                ops.set_tc_pair(old)
+            res[pair] = (y, ob)
+    finally:
+        ops.set_tc_persistent(oldp)
+    y, ob = res[2]
+    assert float((y[M:].float() - 7.0).abs().max()) == 0 and int((ob[M:] != 0x5A).sum()) == 0
+    if ref is not None:
+        check(case, y[:M], ref, 1e-2, 3e-2)
+    if want_bits:
+        assert torch.equal(_bits_to_bool(ob[:M], N), y[:M].float() > 0)
+    assert torch.equal(res[2][0], res[0][0]) and torch.equal(res[2][1], res[0][1])
