@@ -1488,6 +1488,11 @@ int stream_pick(const detrb_igemm_t &p)
     if (g_tc_stream >= 2) return bn;
     // auto: the long HBM-bound streams (at least four tiles per CTA); shorter problems stay on the latency-oriented kernels
     const long tiles = (long)ceil_div(p.M, TBM) * (p.N / bn);
+    // K = 256 with many column ranges (layer3's 256 -> 1024 convs, the encoder's FFN1): every range re-reads all of A, and the
+    // persistent kernel with 128-wide tiles measured faster (43.5 vs 54.7 us on the layer3 shape)      (env DETRB_K256_TCP=0: old policy)
+    static int k256_tcp = -1;
+    if (k256_tcp < 0) { const char *e = getenv("DETRB_K256_TCP"); k256_tcp = e ? atoi(e) : 1; }
+    if (k256_tcp && p.K == 256 && p.N / bn >= (k256_tcp >= 2 ? 8 : 8) && (k256_tcp >= 2 || p.N == 1024)) return 0;
     return tiles >= 4 * 148 ? bn : 0;
 }
 
@@ -1631,6 +1636,7 @@ static int dispatch_tcp(const detrb_igemm_t &p, int bn, cudaStream_t stream, con
         // on the one-tile kernel, whose 4 co-resident CTAs give the epilogue 16 warps per SM
         if (nk >= g_tcp_min_nk256 && p.N % 256 == 0 && !both && mt * (p.N / 256) >= g_tcp_min_tiles256) pick = 256;
         else if (nk > 4 && p.N >= 128 && mt * ceil_div(p.N, 128) >= g_tcp_min_tiles) pick = 128;
+        else if (nk == 4 && p.N >= 1024 && p.N % 128 == 0 && !p.mask && mt * (p.N / 128) >= 4 * 148) pick = 128;    // see stream_pick
         else if (nk == 4 && p.N == 64 && !p.residual && !p.mask && mt >= 4 * 148) pick = 64;
     }
     if (!pick) return DETRB_OK;
