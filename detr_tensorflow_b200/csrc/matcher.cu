@@ -14,6 +14,7 @@ namespace {
 
 constexpr int MAXQ = 128;     // queries per image supported (reference: 100)
 constexpr int MAXT = 100;     // wire format holds at most 99 targets (data/processing.py:49)
+constexpr int MAXC = 128;     // classes staged in shared memory (more: read from global memory)
 
 struct Cand { double v; int it; int un; };
 
@@ -53,6 +54,7 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
     int *col4row = remaining + MAXQ;                             // [MAXT]
     int *SC = col4row + MAXT;                                    // [MAXQ]
     int *SR = SC + MAXQ;                                         // [MAXT]
+    float *sL = reinterpret_cast<float *>(SR + MAXT);            // [Q][C] logits of this problem (C <= MAXC)
     __shared__ int s_bad;
 
     const int p = blockIdx.x, b = p % B;
@@ -66,6 +68,21 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
     if (n > MAXT - 1) n = MAXT - 1;
     if (n > Q) n = Q;
     if (tid == 0) s_bad = 0;
+    // ---- the problem's logits -> shared memory in one coalesced sweep (every later read -- softmax statistics, the class
+    // probabilities of the cost matrix -- would otherwise be a dependent global round trip on a kernel that is pure latency)
+    const bool staged = C <= MAXC;
+    if (staged) {
+        if (ldl == C && ((reinterpret_cast<uintptr_t>(lg) & 15) == 0) && ((Q * C) & 3) == 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(lg);
+            float4 *dst = reinterpret_cast<float4 *>(sL);
+            for (int i = tid; i < (Q * C) >> 2; i += 128) dst[i] = src[i];
+        } else {
+            for (int i = tid; i < Q * C; i += 128) { const int q = i / C; sL[i] = lg[(size_t)q * ldl + (i - q * C)]; }
+        }
+        __syncthreads();
+    }
+    const float *lgs = staged ? sL : lg;
+    const int lds = staged ? C : ldl;
 
     // ---- stage boxes / targets
     for (int i = tid; i < Q; i += 128) {
@@ -84,10 +101,10 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
     // ---- softmax statistics per query (tf.nn.softmax, hungarian_matching.py:176)
     for (int q = warp; q < Q; q += 4) {
         float mx = -INFINITY;
-        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[(size_t)q * ldl + c]);
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lgs[(size_t)q * lds + c]);
         mx = warp_max(mx);
         float sm = 0.f;
-        for (int c = lane; c < C; c += 32) sm += expf(lg[(size_t)q * ldl + c] - mx);
+        for (int c = lane; c < C; c += 32) sm += expf(lgs[(size_t)q * lds + c] - mx);
         sm = warp_sum(sm);
         if (lane == 0) { smax[q] = mx; ssum[q] = sm; }
     }
@@ -97,7 +114,7 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
         int t = e / Q, q = e - t * Q;
         int cls = sTc[t];
         float prob = 0.f;
-        if (cls >= 0 && cls < C) prob = __fdiv_rn(expf(lg[(size_t)q * ldl + cls] - smax[q]), ssum[q]);
+        if (cls >= 0 && cls < C) prob = __fdiv_rn(expf(lgs[(size_t)q * lds + cls] - smax[q]), ssum[q]);
         float c = detrb_match_cost(sP + q * 4, sPxy + q * 4, sT + t * 4, sTxy + t * 4, prob, fc, fb, fg);
         costT[t * Q + q] = c;
         if (cost_out) cost_out[((size_t)p * Q + q) * 100 + t] = c;
@@ -125,17 +142,43 @@ matcher_kernel(const float *logits, int ldl, const float *boxes, const float *t_
             const double ui = u[i];
             const float *crow = costT + i * nc;
             Cand best; best.v = INFINITY; best.it = -1; best.un = 0;
-            for (int it = lane; it < num_remaining; it += 32) {
-                int j = remaining[it];
-                double r = minVal + (double)crow[j] - ui - v[j];
-                if (r < spc[j]) { path[j] = i; spc[j] = r; }
-                Cand c; c.v = spc[j]; c.it = it; c.un = (row4col[j] == -1);
-                if (detrb_lsap_better(c.v, c.it, c.un, best.v, best.it, best.un)) best = c;
-            }
+            // (fixed trip count, guarded: the four column visits of a lane are independent until the final compare, and unrolled
+            //  their shared-memory loads and fp64 chains overlap -- this loop is the latency of the whole kernel)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                Cand other = cand_shfl_xor(best, o);
-                if (detrb_lsap_better(other.v, other.it, other.un, best.v, best.it, best.un)) best = other;
+            for (int k = 0; k < MAXQ / 32; k++) {
+                const int it = lane + 32 * k;
+                const bool ok = it < num_remaining;
+                const int j = ok ? remaining[it] : 0;
+                const double r = minVal + (double)crow[j] - ui - v[j];
+                double sj = spc[j];
+                if (ok && r < sj) { path[j] = i; spc[j] = r; sj = r; }
+                const int un = (row4col[j] == -1);
+                if (ok && detrb_lsap_better(sj, it, un, best.v, best.it, best.un)) { best.v = sj; best.it = it; best.un = un; }
+            }
+            // the winner under detrb_lsap_better, without a shuffle tree over (double, int, int) triples: two 32-bit warp minima over the
+            // order-preserving integer image of the value, then one warp maximum over a key that encodes the tie rule (among equal
+            // values the LAST unassigned position, else the FIRST)
+            {
+                const double bv = best.v + 0.0;                                        // (-0.0 -> +0.0: equal values, equal images)
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(bv);
+                const unsigned long long img = bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+                const unsigned hi = best.it >= 0 ? (unsigned)(img >> 32) : 0xFFFFFFFFu, lo = (unsigned)img;
+                const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+                const bool in_hi = best.it >= 0 && hi == mhi;
+                const unsigned mlo = __reduce_min_sync(0xffffffffu, in_hi ? lo : 0xFFFFFFFFu);
+                const bool mine = in_hi && lo == mlo;
+                const unsigned key = mine ? (best.un ? (0x20000u + (unsigned)best.it) : (0x10000u + (0xFFFFu - (unsigned)best.it))) : 0u;
+                const unsigned mk = __reduce_max_sync(0xffffffffu, key);
+                Cand w;
+                if (mk == 0u) { w.v = INFINITY; w.it = -1; w.un = 0; }
+                else {
+                    w.un = mk >= 0x20000u;
+                    w.it = w.un ? (int)(mk - 0x20000u) : (int)(0xFFFFu - (mk - 0x10000u));
+                    const unsigned long long wimg = ((unsigned long long)mhi << 32) | mlo;
+                    const unsigned long long wbits = (wimg >> 63) ? (wimg ^ 0x8000000000000000ull) : ~wimg;
+                    w.v = __longlong_as_double((long long)wbits);
+                }
+                best = w;
             }
             minVal = best.v;
             if (best.it < 0 || minVal == INFINITY) { bad = 2; break; }     // infeasible
@@ -321,6 +364,7 @@ __global__ void set_loss_finalize_kernel(const float *sums, const float *t_bbox,
     *total = bad ? __int_as_float(0x7fc00000) : tot * loss_scale;
 }
 
+static_assert(MAXQ % 32 == 0, "the LSAP scan visits MAXQ / 32 columns per lane");
 constexpr size_t matcher_smem_bytes()
 {
     return sizeof(double) * (MAXQ + MAXQ + MAXT) + sizeof(float) * (MAXT * MAXQ + MAXQ * 8 + MAXT * 8 + MAXQ * 2) +
@@ -339,12 +383,14 @@ extern "C" int detrb_matcher(const float *logits, int ldl, const float *boxes, c
     DETRB_REQUIRE(P > 0 && B > 0 && P % B == 0, "detrb_matcher: P=%d must be a positive multiple of B=%d", P, B);
     DETRB_REQUIRE(Q > 0 && Q <= MAXQ, "detrb_matcher: Q=%d out of range (1..%d)", Q, MAXQ);
     DETRB_REQUIRE(C > 0 && ldl >= C, "detrb_matcher: C=%d ldl=%d", C, ldl);
-    constexpr size_t smem = matcher_smem_bytes();
+    // + the staged logits [Q][C] (C <= MAXC; 36.8 KB at 100 x 92: two CTAs per SM, 256 problems in one wave)
+    const size_t smem = matcher_smem_bytes() + (C <= MAXC ? sizeof(float) * (size_t)Q * C : 0);
     static bool configured[64] = {false};          // the opt-in is per device
     int dev = 0;
     DETRB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        DETRB_CUDA(cudaFuncSetAttribute(matcher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DETRB_CUDA(cudaFuncSetAttribute(matcher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(matcher_smem_bytes() + sizeof(float) * MAXQ * MAXC)));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     DETRB_LAUNCH(matcher_kernel, dim3(P), dim3(128), smem, (cudaStream_t)stream, logits, ldl, boxes, t_bbox, t_class, B, Q, C,
