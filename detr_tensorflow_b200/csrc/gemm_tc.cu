@@ -1488,11 +1488,12 @@ int stream_pick(const detrb_igemm_t &p)
     if (g_tc_stream >= 2) return bn;
     // auto: the long HBM-bound streams (at least four tiles per CTA); shorter problems stay on the latency-oriented kernels
     const long tiles = (long)ceil_div(p.M, TBM) * (p.N / bn);
-    // K = 256 with many column ranges (layer3's 256 -> 1024 convs, the encoder's FFN1): every range re-reads all of A, and the
-    // persistent kernel with 128-wide tiles measured faster (43.5 vs 54.7 us on the layer3 shape)      (env DETRB_K256_TCP=0: old policy)
+    // (K = 256 with eight column ranges -- layer3's 256 -> 1024 convs: the persistent kernel with 128-wide tiles beat this kernel
+    //  while its A ring was 5 stages, 43.5 vs 54.7 us; with a whole-tile ring of 4 (launch_stream) this kernel takes 38 us.
+    //  env DETRB_K256_TCP=1 sends the shape to the persistent kernel)
     static int k256_tcp = -1;
-    if (k256_tcp < 0) { const char *e = getenv("DETRB_K256_TCP"); k256_tcp = e ? atoi(e) : 1; }
-    if (k256_tcp && p.K == 256 && p.N / bn >= (k256_tcp >= 2 ? 8 : 8) && (k256_tcp >= 2 || p.N == 1024)) return 0;
+    if (k256_tcp < 0) { const char *e = getenv("DETRB_K256_TCP"); k256_tcp = e ? atoi(e) : 0; }
+    if (k256_tcp && p.K == 256 && p.N / bn >= 8 && (k256_tcp >= 2 || p.N == 1024)) return 0;
     return tiles >= 4 * 148 ? bn : 0;
 }
 
@@ -1524,6 +1525,11 @@ int launch_stream(const detrb_igemm_t &p, cudaStream_t stream)
     int nst = g_stream_nst ? g_stream_nst : (2 * nk > 4 ? 2 * nk : 4);
     if (nst > ST_MAX_NST) nst = ST_MAX_NST;
     if (nst > units - 4) nst = units - 4;
+    // a ring that is not a whole number of tiles measured much slower (K = 256, N = 1024: 5 stages 52 us, 4 stages 37 us): round
+    // down to a multiple of the k-blocks per tile, the freed stages become chunk slots          (env DETRB_STREAM_WHOLE=0: off)
+    static int whole = -1;
+    if (whole < 0) { const char *e = getenv("DETRB_STREAM_WHOLE"); whole = e ? atoi(e) : 1; }
+    if (whole && !g_stream_nst && nst > nk && nst % nk) nst -= nst % nk;
     int rs = g_stream_rs ? g_stream_rs : units - nst;
     if (rs > units - nst) rs = units - nst;
     rs &= ~1;

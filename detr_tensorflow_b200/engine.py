@@ -623,36 +623,55 @@ class Engine:
     def _key(t):
         return t.untyped_storage().data_ptr()
 
-    def _on_wstream(self, fn, reads):
+    def _on_wstream(self, fn, reads, low=False):
         if not (self.overlap_wgrad and self._in_backward):
             return fn()
         if self._wstream is None:
             self._wstream = self._side_stream()
+        side = self._wstream
+        if low and self._low_stream() is not None:
+            side = self._lstream
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
-        self._wstream.wait_event(ev)                 # operands produced by everything enqueued so far
-        with torch.cuda.stream(self._wstream):
+        side.wait_event(ev)                          # operands produced by everything enqueued so far
+        with torch.cuda.stream(side):
             fn()
             done = torch.cuda.Event()
-            done.record(self._wstream)
+            done.record(side)
         for t in reads:
             self._pending[self._key(t)] = done
-        self._w_last = done
+        if side is self._wstream:
+            self._w_last = done
+        else:
+            self._l_last = done
 
     # Stream priorities (kernel nodes of a captured graph keep the priority of the stream they were captured on).
     # DETRB_STREAM_PRIO: 0 (default) = none, 1 = the main chain's thread blocks are placed first, 2 = the side streams' are.
     # Measured on the full-size step (tests/time_step_env.py): 1 costs 0.4 ms -- starved weight gradients pile up behind the
     # backward pass, where they run alone at low occupancy.
+    # DETRB_LOWPRIO (default 1): a third, LOWER-priority stream for the bulk work that shadows the decoder -- all layers'
+    # cross-attention K/V projections of the memory in the forward pass; the cross-attention dK/dV kernel, its weight gradients and
+    # the d(memory) accumulation in the backward pass -- 8400-row kernels that otherwise take the SM slots the decoder's 7..64-CTA
+    # kernels are waiting for (the decoder is a latency chain; this work is only needed layers later).
     @staticmethod
     def _prio_mode():
         return int(os.environ.get("DETRB_STREAM_PRIO", "0"))
 
+    @staticmethod
+    def _lowprio():
+        return os.environ.get("DETRB_LOWPRIO", "1") != "0"
+
     def _side_stream(self):
-        return torch.cuda.Stream(priority=-1 if self._prio_mode() == 2 else 0)
+        return torch.cuda.Stream(priority=-1 if (self._prio_mode() == 2 or self._lowprio()) else 0)
 
     def _chain_stream(self):
-        return torch.cuda.Stream(priority=-1 if self._prio_mode() == 1 else 0)
+        return torch.cuda.Stream(priority=-1 if (self._prio_mode() == 1 or self._lowprio()) else 0)
+
+    def _low_stream(self):
+        if getattr(self, "_lstream", None) is None:
+            self._lstream = torch.cuda.Stream(priority=0) if self._lowprio() else None
+        return self._lstream
 
     def _fork(self, fn, lane=0):
         """Run fn() on a side stream, ordered after everything enqueued on the main stream so far; returns the handle for
@@ -668,6 +687,8 @@ class Engine:
             if getattr(self, "_wstream2", None) is None:
                 self._wstream2 = self._side_stream()
             side = self._wstream2
+        elif lane == 2 and self._low_stream() is not None:
+            side = self._lstream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         side.wait_event(ev)
@@ -697,6 +718,9 @@ class Engine:
         if self._w_last is not None:
             torch.cuda.current_stream().wait_event(self._w_last)
         self._w_last = None
+        if getattr(self, "_l_last", None) is not None:
+            torch.cuda.current_stream().wait_event(self._l_last)
+        self._l_last = None
         self._pending.clear()
 
     def _lin(self, A, W, M, N, K, ldw, out=None, ldc=None, lda=None, **kw):
@@ -749,12 +773,12 @@ class Engine:
         self._on_wstream(lambda: self._probed(s.name + "#wgrad", lambda: ops.wgrad(
             x, s.Cin, dy, s.N, B * ohw[0] * ohw[1], s.N, s.K, g, s.grad, s.K, rowscale=s.fold, dbias=s.bias_grad, split=self.plane)), (x, dy))
 
-    def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None):
+    def _lin_wgrad(self, s, x, dy, M, ldy=None, n_off=0, n_rows=None, lda=None, low=False):
         """dW[n_off:n_off+n_rows] += dy^T x ; dbias likewise"""
         n_rows = n_rows or s.N
         self.launches += 1
         self._on_wstream(lambda: ops.wgrad(x, lda or s.K, dy, ldy or n_rows, M, n_rows, s.K, ops.plain_geom(M, s.K),
-                                           s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:], split=self.plane), (x, dy))
+                                           s.grad[n_off * s.K:], s.K, dbias=s.bias_grad[n_off:], split=self.plane), (x, dy), low=low)
 
     def _ln_fwd(self, x, n, y, mean, rstd, M, y2=None, pos=None, S=1):
         self.launches += 1
@@ -882,7 +906,7 @@ class Engine:
             def kv(l=l, Wc=Wc):
                 self._lin(memp, Wc.Wf[d:], M, d, d, d, out=a[f"d{l}_k2"], bias=Wc.bias[d:])
                 self._lin(mem, Wc.Wf[2 * d:], M, d, d, d, out=a[f"d{l}_v2"], bias=Wc.bias[2 * d:])
-            kv_ready.append(self._fork(kv))
+            kv_ready.append(self._fork(kv, lane=2))
         for l, D in enumerate(self.dec):
             t = lambda n: a[f"d{l}_{n}"]
             W = D["sa"]["inp"]
@@ -1065,21 +1089,21 @@ class Engine:
                 # only dQ continues the decoder's chain; dK / dV (1050 keys) feed the weight gradients and d(memory), which
                 # live on the side stream anyway: the kernel goes there, in order with its consumers
                 ops.attn_bwd(*xargs, parts=1, **xkw)
-                self._on_wstream(lambda: ops.attn_bwd(*xargs, parts=2, **xkw), (dO2, delta2))
+                self._on_wstream(lambda: ops.attn_bwd(*xargs, parts=2, **xkw), (dO2, delta2), low=True)
                 ops.attn_bwd(*xargs, parts=4, **xkw)
             else:
                 self._before_write(a["gm_k2"], a["gm_v2"])
                 ops.attn_bwd(*xargs, **xkw)
             self._lin_wgrad(W, t("t1q"), a["gq_q2"], Mq, n_off=0, n_rows=d)
-            self._lin_wgrad(W, memp, a["gm_k2"], M, n_off=d, n_rows=d)
-            self._lin_wgrad(W, mem, a["gm_v2"], M, n_off=2 * d, n_rows=d)
+            self._lin_wgrad(W, memp, a["gm_k2"], M, n_off=d, n_rows=d, low=True)          # (in order with the dK/dV kernel that feeds them)
+            self._lin_wgrad(W, mem, a["gm_v2"], M, n_off=2 * d, n_rows=d, low=True)
             # d memory accumulates over decoder layers (memory feeds every cross attention)
             # (side stream, in order with each other; only the encoder's backward needs g_mem -- joined there)
             def dmem(W=W, first=first_mem):
                 self._lin(a["gm_k2"], W.Wd[:, :, d:], M, d, d, W.ldd, out=a["g_mem"], residual=None if first else a["g_mem"], ldr=d)
                 self._lin(a["gm_v2"], W.Wd[:, :, 2 * d:], M, d, d, W.ldd, out=a["g_mem"], residual=a["g_mem"], ldr=d)
             if self.overlap_dmem:
-                self._on_wstream(dmem, (a["gm_k2"], a["gm_v2"]))
+                self._on_wstream(dmem, (a["gm_k2"], a["gm_v2"]), low=True)
             else:
                 dmem()
             first_mem = False
