@@ -224,7 +224,166 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     }
 }
 
+// ================================================================================================ narrow variant (N <= 64)
+// Layers with at most 64 output channels (the stem, layer1's 256 -> 64 and 3x3 64 -> 64 convs: the largest pixel counts of the network)
+// waste half of the 128-row UMMA of the kernel above (dY is the M operand there), and its k-tiles each re-read dY.  Here the roles
+// are swapped and one CTA owns ALL of K:   D_a[128 k-columns x 64 out channels] += X_a^T[128 x 16 px] . dY[16 px x 64]   for the
+// NA = ceil(K / 128) accumulators a (64 TMEM columns each).  Per 64-pixel stage: ONE dY box and K / 64 gathered boxes (nine taps of the
+// 3x3: 80 KB), every MMA does useful work (M = 128, N = 64), dY is read once.  CTAs split the pixel range, fp32 red.add merge; in
+// the epilogue a warp's lanes hold consecutive k of one output channel: coalesced reductions.
+constexpr int NARROW_MAX_BOXES = 9;
+constexpr uint32_t WIDESC_NARROW = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+template <bool IM2COL>
+__global__ void __launch_bounds__(WTHREADS)
+wgrad_narrow_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, const detrb_wgrad_t p,
+                    const int pix_per_split, const int stem_mask, const int nstages, const int tmem_cols)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int nb = p.K / 64, na = (nb + 1) / 2;                        // gathered boxes per stage, accumulators
+    const uint32_t stage_bytes = (uint32_t)(1 + nb) * BOX_BYTES;
+    const uint32_t bar_base = smem_base + (uint32_t)nstages * stage_bytes + BOX_BYTES;      // (+ one box: the odd last accumulator's upper half reads past the stage)
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * 8;
+    const uint32_t tmem_slot = bar_base + 8u * 9;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_begin = (int)blockIdx.x * pix_per_split;
+    const int m_end = min(p.M, m_begin + pix_per_split);
+    const int nsteps = (m_end - m_begin + WP - 1) / WP;                // >= 1 by construction of the grid
+    const bool do_bias = p.dbias != nullptr;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_y);
+        tma_prefetch_desc(&map_x);
+        for (int s = 0; s < nstages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_bias ? 5 : 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int ohw = p.OH * p.OW;
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                const int m = m_begin + st * WP;
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                mbar_expect_tx(full_bar(stage), stage_bytes);
+                const uint32_t dst = smem_base + (uint32_t)stage * stage_bytes;
+                tma_load_2d(dst, &map_y, full_bar(stage), 0, m);                              // dY[m .. m+64, 0 .. 64)
+                if (IM2COL) {
+                    const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
+                    const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
+                    for (int j = 0; j < nb; j++) {
+                        const int k = j * 64, tap = k / p.Cin, cc = k - tap * p.Cin;
+                        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                        tma_load_im2col(dst + (uint32_t)(1 + j) * BOX_BYTES, &map_x, full_bar(stage), cc, w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                    }
+                } else {
+                    const int sl = p.a_kb_rows;                                              // sliding-window A: block j is j * sl rows further down
+                    for (int j = 0; j < nb; j++)
+                        tma_load_2d(dst + (uint32_t)(1 + j) * BOX_BYTES, &map_x, full_bar(stage), sl ? 0 : j * 64, m + j * sl);
+                }
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+                const uint64_t dy = make_desc_mn(base);
+#pragma unroll
+                for (int ks = 0; ks < WP / 16; ks++) {        // 16 pixels = 2 swizzle atoms = 2048 B further down every box
+                    const uint64_t off = (uint64_t)(ks * (2048 >> 4));
+                    for (int a = 0; a < na; a++)
+                        tc_mma_f16(tmem_base + (uint32_t)(a * 64), make_desc_mn(base + (uint32_t)(1 + 2 * a) * BOX_BYTES) + off, dy + off,
+                                   WIDESC_NARROW, (st | ks) != 0);
+                }
+                tc_commit(empty_bar(stage));
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        const int te = threadIdx.x - 64;                                 // 0 .. 127
+        if (do_bias) {
+            // thread -> channel pair (2cp, 2cp+1) and one quarter of the stage's 64 pixel rows; dY box: pixel row r at r * 128 B, its
+            // 16-byte chunk c (8 channels) at chunk c ^ (r % 8)
+            const int cp = te & 31, quarter = te >> 5;
+            const uint32_t chunk = (uint32_t)(cp >> 2), within = (uint32_t)(cp & 3) * 4u;
+            float s0 = 0.f, s1 = 0.f;
+            int stage = 0; uint32_t phase = 0;
+            for (int st = 0; st < nsteps; st++) {
+                mbar_wait(full_bar(stage), phase);
+                const uint32_t base = smem_base + (uint32_t)stage * stage_bytes + within;
+#pragma unroll 8
+                for (int r = quarter * 16; r < quarter * 16 + 16; r++) {
+                    uint32_t u;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(base + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+                    const float2 f = unpack_bf16x2(u);
+                    s0 += f.x; s1 += f.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar(stage));
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+            const int c0 = 2 * cp;
+            if (c0 < p.N) atomicAdd(p.dbias + c0, s0 * (p.rowscale ? p.rowscale[c0] : 1.f));
+            if (c0 + 1 < p.N) atomicAdd(p.dbias + c0 + 1, s1 * (p.rowscale ? p.rowscale[c0 + 1] : 1.f));
+        }
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        for (int a = 0; a < na; a++) {
+            const int k = a * 128 + q * 32 + lane;                   // this thread's TMEM lane = one k column of dW
+            bool k_ok = k < p.K;
+            if (stem_mask) {
+                const int ch = k & 15, tb = (k >> 4) & 3, ta = k >> 6;
+                const int ry = ch / 6, rx = (ch / 3) & 1, kh = 2 * ta + ry - 1, kw = 2 * tb + rx - 1;
+                k_ok = k_ok && ch < 12 && kh >= 0 && kh <= 6 && kw >= 0 && kw <= 6;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t r[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c0), r);
+                tc_wait_ld();
+                if (!k_ok) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int n = c0 + i;
+                    if (n < p.N) atomicAdd(p.dW + (size_t)n * p.ldw + k, __uint_as_float(r[i]) * (p.rowscale ? p.rowscale[n] : 1.f));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)tmem_cols) : "memory");
+    }
+}
+
 }  // namespace
+
 
 bool detrb_wgrad_tc_supported(const detrb_wgrad_t &p)
 {
@@ -277,6 +436,34 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         }
     }
     if (!sp) { my2 = my; mx2 = mx; }
+    static int narrow_on = -1;                       // env DETRB_WGRAD_NARROW=0: the general kernel everywhere
+    if (narrow_on < 0) { const char *e = getenv("DETRB_WGRAD_NARROW"); narrow_on = e ? atoi(e) : 1; }
+    // mode 1: the plain operands only (K = 256: layer1's 256 -> 64 convs, the stem); mode 2: also the gathered 3x3 (measured SLOWER
+    // than the general kernel, 117 vs 100 us: nine im2col boxes per stage leave room for two stages only and the loop runs at TMA
+    // latency -- the fix is the halo scheme of conv_halo.cu, whole rows staged once, taps as shifted views; not built)
+    if (narrow_on && (plain ? p.K >= 128 : narrow_on >= 2) && !sp && p.N <= 64 && p.K % 64 == 0 && p.K / 64 <= NARROW_MAX_BOXES && p.M >= 148 * WP) {
+        const int nb = p.K / 64, na = (nb + 1) / 2;
+        const int stage_bytes = (1 + nb) * BOX_BYTES;
+        int nstages = (227 * 1024 - 2048 - 1024 - BOX_BYTES) / stage_bytes;
+        if (nstages > 4) nstages = 4;
+        const int tmem_cols = na * 64 <= 64 ? 64 : na * 64 <= 128 ? 128 : na * 64 <= 256 ? 256 : 512;
+        const size_t smem = (size_t)nstages * stage_bytes + BOX_BYTES + 256 + 1024;
+        static bool nconfigured = false;
+        if (!nconfigured) {
+            DETRB_CUDA(cudaFuncSetAttribute((wgrad_narrow_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DETRB_CUDA(cudaFuncSetAttribute((wgrad_narrow_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            nconfigured = true;
+        }
+        int nsplit = 148;
+        int pps = ceil_div(ceil_div(p.M, nsplit), WP) * WP;
+        nsplit = ceil_div(p.M, pps);
+        if (nstages >= 2) {
+            if (plain) DETRB_LAUNCH((wgrad_narrow_kernel<false>), dim3(nsplit), dim3(WTHREADS), smem, stream, my, mx, p, pps, p.k_mask ? 1 : 0, nstages, tmem_cols);
+            else DETRB_LAUNCH((wgrad_narrow_kernel<true>), dim3(nsplit), dim3(WTHREADS), smem, stream, my, mx, p, pps, 0, nstages, tmem_cols);
+            DETRB_CHECK_LAUNCH("wgrad_narrow_kernel");
+            return DETRB_OK;
+        }
+    }
     const int kt = WK;
     const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
     // one wave of 2 CTAs per SM (fewer fp32 atomics per gradient element) -- rounded DOWN: 36 tiles x 9 splits = 324 CTAs on 296

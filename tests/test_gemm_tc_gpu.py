@@ -195,7 +195,10 @@ def test_conv_tc_forward_and_dgrad(ops, cin, cout, k, stride, pad, H, W, bn):
 # ------------------------------------------------------------------------------------------------ tcgen05 weight gradient
 @pytest.mark.parametrize("cin,cout,k,stride,pad,H,W", [(64, 64, 1, 1, 0, 13, 19), (64, 64, 3, 1, 1, 13, 19), (128, 128, 3, 2, 1, 13, 19),
                                                        (256, 512, 1, 2, 0, 13, 19), (64, 256, 1, 1, 0, 9, 11), (256, 256, 3, 1, 1, 50, 84),
-                                                       (256, 92, 1, 1, 0, 30, 40), (2048, 256, 1, 1, 0, 25, 42)])
+                                                       (256, 92, 1, 1, 0, 30, 40), (2048, 256, 1, 1, 0, 25, 42),
+                                                       # >= 148 x 64 pixels and <= 64 output channels: wgrad_narrow_kernel (one CTA owns all of K)
+                                                       (64, 64, 3, 1, 1, 100, 167), (256, 64, 1, 1, 0, 90, 131), (64, 48, 3, 1, 1, 77, 99),
+                                                       (128, 64, 1, 1, 0, 80, 80), (64, 64, 1, 1, 0, 200, 334)])
 def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
     B = 2
     oh, ow = _out(H, k, stride, pad), _out(W, k, stride, pad)
@@ -225,7 +228,7 @@ def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
 
 
 # ------------------------------------------------------------------------------------------------ stem as a sliding-window GEMM
-@pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224)])
+@pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224), (400, 667)])
 def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
     """The production stem: zero-padded space-to-depth image [B, HP, WP, 16] read as a GEMM operand whose rows are overlapping
     128-byte windows (detrb_igemm_t.a_kb_rows = WP, lda = 16) == 7x7 / stride 2 / pad 3 convolution (resnet_backbone.py:11-12,
