@@ -8,10 +8,10 @@ import sys
 
 FAMILIES = [
     ("gemm_stream_kernel (streaming tcgen05 GEMM: HBM-bound 1x1 convs of layer1-3, stem, FFN1)", r"gemm_stream_kernel"),
-    ("conv3x3_halo_kernel (halo-reusing 3x3 / 64-channel conv, forward + data gradient)", r"conv3x3_halo_kernel"),
-    ("gemm_tcp_kernel (persistent tcgen05 GEMM / conv: tensor-bound shapes)", r"gemm_tcp_kernel"),
+    ("conv3x3_halo_kernel (halo-reusing 3x3 / 64-channel conv, forward + data gradient)", r"conv3x3_halo"),
+    ("gemm_tcp_kernel (persistent tcgen05 GEMM / conv: tensor-bound shapes)", r"gemm_tcp_kernel|gemm_pair_kernel"),
     ("gemm_tc_kernel (one-tile tcgen05 GEMM / conv: small transformer linears, strided convs and data gradients)", r"gemm_tc_kernel"),
-    ("wgrad_tc_kernel (tcgen05 weight gradients, side stream)", r"wgrad_tc_kernel"),
+    ("wgrad_tc_kernel (tcgen05 weight gradients, side stream)", r"wgrad_tc_kernel|wgrad_narrow_kernel"),
     ("attention forward / backward (tcgen05)", r"attn_"),
     ("LayerNorm forward / backward", r"ln_(fwd|bwd)_kernel"),
     ("Adam + clipnorm + weight refresh", r"chunk_|adam_|prep_weights"),
