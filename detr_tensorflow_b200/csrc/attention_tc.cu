@@ -704,7 +704,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
 }  // namespace
 
-static int g_attn_tc = 1;
+static thread_local int g_attn_tc = 1;
 extern "C" int detrb_set_tc_attn(int enable) { int old = g_attn_tc; g_attn_tc = enable; return old; }
 bool detrb_attn_tc_enabled() { return g_attn_tc != 0; }
 
@@ -725,7 +725,7 @@ int detrb_attn_fwd_tc(const detrb_attn_fwd_t &p, cudaStream_t stream)
         !detrb_make_tiled_map(&mk, p.K, (uint64_t)p.B * p.Lk, cols, (uint64_t)p.ldk, BKV, DH, 64) ||
         !detrb_make_tiled_map(&mv, p.V, (uint64_t)p.B * p.Lk, cols, (uint64_t)p.ldv, BKV, DH, 64))
         DETRB_FAIL(DETRB_E_CUDA, "attn_fwd_tc: cuTensorMapEncodeTiled failed (B=%d H=%d Lq=%d Lk=%d)", p.B, p.H, p.Lq, p.Lk);
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
         configured = true;
@@ -756,7 +756,7 @@ int detrb_attn_bwd_tc(const detrb_attn_bwd_t &p, cudaStream_t stream)
         !detrb_make_tiled_map(&q64, p.Q, rq, cols, (uint64_t)p.ldq, BKV, DH, 64) || !detrb_make_tiled_map(&do64, p.dO, rq, cols, (uint64_t)p.lddo, BKV, DH, 64) ||
         !detrb_make_tiled_map(&k128, p.K, rk, cols, (uint64_t)p.ldk, BQ, DH, 64) || !detrb_make_tiled_map(&v128, p.V, rk, cols, (uint64_t)p.ldv, BQ, DH, 64))
         DETRB_FAIL(DETRB_E_CUDA, "attn_bwd_tc: cuTensorMapEncodeTiled failed (B=%d H=%d Lq=%d Lk=%d)", p.B, p.H, p.Lq, p.Lk);
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ));
         DETRB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DKV));

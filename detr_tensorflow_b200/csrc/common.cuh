@@ -19,6 +19,20 @@ void detrb_set_error(const char *fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute opt-ins (dynamic shared memory above 48 KB) belong to a DEVICE, not to the process: one flag per device
+// ordinal, so that a process driving several GPUs configures each of them.  slot() is the current device's flag (a scratch flag,
+// i.e. "configure every time", outside 0..63 or when the runtime cannot name the device).
+struct detrb_per_device_flag {
+    bool done[64] = {};
+    bool scratch = false;
+    bool &slot()
+    {
+        int d = -1;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) { scratch = false; return scratch; }
+        return done[d];
+    }
+};
+
 // gemm_tc.cu (tcgen05 / TMA / TMEM path)
 bool detrb_gemm_tc_supported(const detrb_igemm_t &p);
 bool detrb_gemm_tc_enabled();

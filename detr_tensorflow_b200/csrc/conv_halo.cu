@@ -472,13 +472,13 @@ bool make_nhwc_map(CUtensorMap *map, const void *base, int B, int H, int W, int 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int g_halo = 1;               // 0 off, 1 on                                                  (env DETRB_HALO)
+thread_local int g_halo = 1;          // 0 off, 1 on                                                  (env DETRB_HALO)
 int g_halo_bo = 0;            // descriptor base-offset field for the shifted tap views: must stay 0 (see the kernel)   (env DETRB_HALO_BO, developer switch)
 int g_halo_diag = 0;          // timing-only switches (wrong results)                                                    (env DETRB_HALO_DIAG)
 int g_halo_192 = 1;           // row-stationary N = 192 variant (conv3x3_halo192_kernel)                                  (env DETRB_HALO_192)
 void read_env()
 {
-    static bool done = false;
+    static thread_local bool done = false;     // per thread: g_halo is (the developer switches below are process-wide, re-reading them is idempotent)
     if (done) return;
     done = true;
     if (const char *e = getenv("DETRB_HALO")) g_halo = atoi(e);
@@ -515,7 +515,7 @@ int detrb_conv_halo(const detrb_igemm_t &p, cudaStream_t stream)
     geo.units = geo.B * geo.nseg * geo.H;
     // forward: tap (kh, kw) pairs with weight tap kh*3+kw; data gradient (mode 1, stride 1): the flipped kernel
     for (int i = 0; i < 9; i++) geo.wtap[i] = p.mode == 1 ? 8 - i : i;
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     static int num_sms = 148;
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute(conv3x3_halo192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES2));

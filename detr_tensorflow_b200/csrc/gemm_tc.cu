@@ -1307,13 +1307,13 @@ bool make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, 
     return r == CUDA_SUCCESS;
 }
 
-static int g_tma_epilogue = 1;
+static thread_local int g_tma_epilogue = 1;          // (the public switches are thread-local: detrb_bind installs a handle's values)
 static int g_r_early = 1;            // early residual fetch: 0 never, 1 policy (launch_tc), 2 always      (env DETRB_R_EARLY)
 static int g_deep_small = 1;         // one stage per k-block for K <= 256 on latency-bound grids           (env DETRB_DEEP_SMALL)
 static int g_one_stage = 1;          // one-stage kernel for K = 64                                          (env DETRB_ONE_STAGE)
-static int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
+static thread_local int g_tc_persistent = 1;      // 1: auto policy (dispatch_tcp)
 static int g_tc_pair = 0;            // CTA-pair kernel: 0 off, 1 for 256-wide tiles, 2 for 128- and 256-wide tiles   (env DETRB_PAIR)
-static int g_tc_pair_forced = -1;    // detrb_set_tc_pair() overrides the environment
+static thread_local int g_tc_pair_forced = -1;    // detrb_set_tc_pair() overrides the environment
 static long g_tcp_min_tiles = 64, g_tcp_min_tiles256 = 100, g_tcp_min_nk256 = 12;     // auto policy thresholds (env DETRB_TCP_MIN_TILES / DETRB_TCP_MIN_NK256)
 
 struct ConvClass { ConvAux aux; int upper_w, upper_h, w_cols; };
@@ -1379,7 +1379,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
     }
     if constexpr (PERSIST) {
         using PL = PLayout<BN, STAGES, OB>;
-        static bool pconfigured = false;
+        static detrb_per_device_flag pconfigured_dev; bool &pconfigured = pconfigured_dev.slot();      // the opt-in is per device
         static int num_sms = 148;
         if (!pconfigured) {
             DETRB_CUDA(cudaFuncSetAttribute((gemm_tcp_kernel<BN, STAGES, IM2COL, OB>), cudaFuncAttributeMaxDynamicSharedMemorySize, PL::TOTAL));
@@ -1403,7 +1403,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
             if (mode >= (BN == 256 ? 1 : 2) && !p.mask && !p.sigmoid && p.N % BN == 0 && p.K % TBK == 0 && !p.a_kb_rows && p.M > TBM) {
                 constexpr int QST = BN == 256 ? 5 : 6;
                 using QL = PairLayout<BN, QST>;
-                static bool qconfigured = false;
+                static detrb_per_device_flag qconfigured_dev; bool &qconfigured = qconfigured_dev.slot();      // the opt-in is per device
                 static int max_pairs = 74;
                 if (!qconfigured) {
                     DETRB_CUDA(cudaFuncSetAttribute((gemm_pair_kernel<BN, QST, IM2COL>), cudaFuncAttributeMaxDynamicSharedMemorySize, QL::TOTAL));
@@ -1435,7 +1435,7 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
         return DETRB_OK;
     } else {
     using L = SmemLayout<BN, STAGES>;
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES, IM2COL, SPLIT, BITS_T>), cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
@@ -1458,14 +1458,14 @@ int launch_tc(const detrb_igemm_t &p, cudaStream_t stream, const ConvClass *cls 
 }
 
 // streaming kernel: plain GEMM, bf16 TMA output, weights of one column range resident in shared memory
-static int g_tc_stream = 1;          // 0 off, 1 auto (stream_pick), 2 wherever supported (tests)      (env DETRB_STREAM)
+static thread_local int g_tc_stream = 1;          // 0 off, 1 auto (stream_pick), 2 wherever supported (tests)      (env DETRB_STREAM)
 static int g_stream_nst = 0, g_stream_rs = 0;      // overrides (env DETRB_STREAM_NST / DETRB_STREAM_RS), 0 = policy
 static int g_stream_diag = 0, g_stream_bn = 0;     // developer switches (env DETRB_STREAM_DIAG / DETRB_STREAM_BN)
 
 // column width per CTA (0: not a streaming shape)
 int stream_pick(const detrb_igemm_t &p)
 {
-    static bool env_read = false;
+    static thread_local bool env_read = false;     // per thread: g_tc_stream is
     if (!env_read) {
         env_read = true;
         if (const char *e = getenv("DETRB_STREAM")) g_tc_stream = atoi(e);
@@ -1510,7 +1510,7 @@ int launch_stream(const detrb_igemm_t &p, cudaStream_t stream)
     mr = mc;
     if (p.residual && !make_map(&mr, p.residual, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldr, TBM))
         DETRB_FAIL(DETRB_E_CUDA, "gemm_stream: cuTensorMapEncodeTiled(residual) failed");
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     static int num_sms = 148;
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute((gemm_stream_kernel<BN, HAS_R, MBITS, OBITS>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1594,7 +1594,7 @@ int detrb_gemm_tc_kind(const detrb_igemm_t &p)
 
 bool detrb_gemm_tc_supported(const detrb_igemm_t &p) { return detrb_gemm_tc_kind(p) != 0; }
 
-static int g_tc_enabled = 1;      // validated on B200 (tests/test_gemm_tc_gpu.py): default on
+static thread_local int g_tc_enabled = 1;      // validated on B200 (tests/test_gemm_tc_gpu.py): default on
 extern "C" int detrb_set_tc(int enable) { int old = g_tc_enabled; g_tc_enabled = enable; return old; }
 bool detrb_gemm_tc_enabled() { return g_tc_enabled != 0; }
 
@@ -1606,7 +1606,7 @@ extern "C" int detrb_set_tc_persistent(int enable)
 }
 extern "C" int detrb_set_tc_pair(int mode) { int old = g_tc_pair_forced; g_tc_pair_forced = mode; return old; }
 extern "C" int detrb_set_tc_tma_epilogue(int enable) { int old = g_tma_epilogue; g_tma_epilogue = enable; return old; }
-static int g_tc_conv_enabled = 1;
+static thread_local int g_tc_conv_enabled = 1;
 extern "C" int detrb_set_tc_conv(int enable) { int old = g_tc_conv_enabled; g_tc_conv_enabled = enable; return old; }
 bool detrb_gemm_tc_conv_enabled() { return g_tc_conv_enabled != 0; }
 

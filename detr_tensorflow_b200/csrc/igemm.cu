@@ -232,7 +232,7 @@ template <int BN, bool STEM>
 int launch(const detrb_igemm_t &p, cudaStream_t stream)
 {
     constexpr int smem = STAGES * (BM + BN) * LDS * (int)sizeof(bf16);
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;

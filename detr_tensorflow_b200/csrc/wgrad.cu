@@ -200,7 +200,7 @@ extern "C" int detrb_wgrad(const detrb_wgrad_t *pp, detrb_stream_t stream_)
     int pix_per_split = ceil_div(ceil_div(p.M, splits), BP) * BP;
     splits = ceil_div(p.M, pix_per_split);
     constexpr int smem = STAGES * 2 * BP * LDT * (int)sizeof(bf16);
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         DETRB_CUDA(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

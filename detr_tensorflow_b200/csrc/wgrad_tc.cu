@@ -448,7 +448,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
         if (nstages > 4) nstages = 4;
         const int tmem_cols = na * 64 <= 64 ? 64 : na * 64 <= 128 ? 128 : na * 64 <= 256 ? 256 : 512;
         const size_t smem = (size_t)nstages * stage_bytes + BOX_BYTES + 256 + 1024;
-        static bool nconfigured = false;
+        static detrb_per_device_flag nconfigured_dev; bool &nconfigured = nconfigured_dev.slot();      // the opt-in is per device
         if (!nconfigured) {
             DETRB_CUDA(cudaFuncSetAttribute((wgrad_narrow_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             DETRB_CUDA(cudaFuncSetAttribute((wgrad_narrow_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -474,7 +474,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     if (splits < 1) splits = 1;
     int pix_per_split = ceil_div(ceil_div(p.M, splits), WP) * WP;
     splits = ceil_div(p.M, pix_per_split);
-    static bool configured = false;
+    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
     if (!configured) {
         DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
         DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
@@ -501,7 +501,7 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
     return DETRB_OK;
 }
 
-static int g_wgrad_tc_enabled = 1;     // validated on B200 (tests/test_gemm_tc_gpu.py::test_wgrad_tc)
+static thread_local int g_wgrad_tc_enabled = 1;     // validated on B200 (tests/test_gemm_tc_gpu.py::test_wgrad_tc)
 extern "C" int detrb_set_tc_wgrad(int enable) { int old = g_wgrad_tc_enabled; g_wgrad_tc_enabled = enable; return old; }
 bool detrb_wgrad_tc_enabled() { return g_wgrad_tc_enabled != 0; }
 

@@ -66,7 +66,13 @@ class Engine:
         self.lib = _lib.lib()
         if self.device.type != "cuda" and not getattr(_lib, "_EMULATED", False):
             raise RuntimeError("detr_tensorflow_b200 has no CPU path: a B200 (sm_100a) device is required")
+        self.handle = None
         if self.device.type == "cuda":
+            # one handle per GPU / rank: fails unless the device is compute capability 10.x (there is no fallback path), then makes
+            # the device and the handle's kernel-policy switches current for this thread (include/detrb.h, "Handles")
+            index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.handle = ops.Handle(index)
+            self.handle.bind()
             _lib.check(self.lib.detrb_check_device())
         self.backbone_name = backbone
         self.nb_class = nb_class                    # fine-tuning heads (detr.py:94-114): C = nb_class, 'nlayers' group

@@ -49,6 +49,46 @@ def igemm(A, W, M, N, K, lda, ldw, geom, *, bias=None, residual=None, ldr=0, mas
         check(_lib.lib().detrb_igemm(byref(p), _stream()))
 
 
+OPTIONS = {"pdl": 0, "tc": 1, "tc_conv": 2, "tc_tma_epilogue": 3, "tc_persistent": 4, "tc_stream": 5, "tc_halo": 6, "tc_pair": 7,
+           "tc_wgrad": 8, "tc_attn": 9}          # DETRB_OPT_* of include/detrb.h
+
+
+class Handle:
+    """detrb_handle_t (include/detrb.h, "Handles"): the device a step runs on + the kernel-policy switches, one per GPU / rank.
+    `bind()` makes it current for the calling thread (cudaSetDevice + the thread-local switches)."""
+
+    def __init__(self, device_index):
+        L = _lib.lib()
+        self._h = c_void_p()
+        check(L.detrb_create(c_int(int(device_index)), byref(self._h)))
+
+    @property
+    def device_index(self):
+        return int(_lib.lib().detrb_handle_device(self._h))
+
+    def set(self, option, value):
+        check(_lib.lib().detrb_handle_set(self._h, c_int(OPTIONS[option]), c_int(int(value))))
+
+    def get(self, option):
+        v = c_int()
+        check(_lib.lib().detrb_handle_get(self._h, c_int(OPTIONS[option]), byref(v)))
+        return v.value
+
+    def bind(self):
+        check(_lib.lib().detrb_bind(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib().detrb_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def set_tc(enable):
     """route plain GEMMs through the tcgen05/TMA/TMEM kernel (gemm_tc.cu); returns the previous setting"""
     return _lib.lib().detrb_set_tc(c_int(int(enable)))

@@ -55,6 +55,45 @@ int detrb_check_device(void);
 int detrb_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------
+ * Handles (one handle per GPU / rank).  The reference keeps its per-model state in the Keras model object
+ * (networks/detr.py:116-204); below the Python mirror that state is (a) the device the step runs on and (b) the kernel-policy
+ * switches.  A handle owns both; it owns NO device memory (buffers, workspaces and weights stay with the caller, as above).
+ *
+ *   detrb_create(device, &h)   checks that `device` exists and is compute capability 10.x (DETRB_E_ARCH otherwise: there is no
+ *                              fallback path), records it and gives the handle the creating thread's current policy (the defaults below,
+ *                              or what the DETRB_* environment variables say, unless the thread called detrb_set_* before).
+ *   detrb_handle_set / _get    change / read ONE switch of the handle (nothing else is touched; unknown option: DETRB_E_BADARG).
+ *   detrb_bind(h)              makes h current for the CALLING THREAD: cudaSetDevice(h's device) and h's switches become the
+ *                              thread's switches.  Every detrb_* compute call of that thread then runs under them.
+ *   detrb_destroy(h)           frees the host object (NULL is accepted).
+ *
+ * The switches are thread-local: the detrb_set_* functions of this header change the calling thread's current value (a thread
+ * that never bound a handle runs the defaults, initialised from the DETRB_* environment variables), so two threads that bound two
+ * handles -- two GPUs driven from one process -- do not see each other's settings.  A handle is thread-compatible (one thread
+ * at a time); detrb_last_error() is the calling thread's message, so it is also "the handle's" last error.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct detrb_handle detrb_handle_t;
+enum {
+    DETRB_OPT_PDL = 0,             /* detrb_set_pdl            default 1 */
+    DETRB_OPT_TC = 1,              /* detrb_set_tc             default 1 */
+    DETRB_OPT_TC_CONV = 2,         /* detrb_set_tc_conv        default 1 */
+    DETRB_OPT_TC_TMA_EPILOGUE = 3, /* detrb_set_tc_tma_epilogue default 1 */
+    DETRB_OPT_TC_PERSISTENT = 4,   /* detrb_set_tc_persistent  default 1 (auto policy) */
+    DETRB_OPT_TC_STREAM = 5,       /* detrb_set_tc_stream      default 1 (auto policy) */
+    DETRB_OPT_TC_HALO = 6,         /* detrb_set_tc_halo        default 1 */
+    DETRB_OPT_TC_PAIR = 7,         /* detrb_set_tc_pair        default -1 (follow DETRB_PAIR, else off) */
+    DETRB_OPT_TC_WGRAD = 8,        /* detrb_set_tc_wgrad       default 1 */
+    DETRB_OPT_TC_ATTN = 9,         /* detrb_set_tc_attn        default 1 */
+    DETRB_OPT_COUNT = 10
+};
+int detrb_create(int device, detrb_handle_t **out);
+int detrb_destroy(detrb_handle_t *h);
+int detrb_handle_device(const detrb_handle_t *h);                       /* the device ordinal, or DETRB_E_BADARG */
+int detrb_handle_set(detrb_handle_t *h, int option, int value);
+int detrb_handle_get(const detrb_handle_t *h, int option, int *value);
+int detrb_bind(const detrb_handle_t *h);
+
+/* ------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / linear layer:  C[M,N] = epilogue( gather(A)[M,K] * W[N,K]^T )
  * Replaces tf Conv2D+ZeroPadding2D+FrozenBatchNorm2D+ReLU(+residual) (networks/resnet_backbone.py:
  * 20-26, 116-136; custom_layers.py:21-24), Conv2D input_proj (detr.py:44), Linear

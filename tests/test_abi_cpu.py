@@ -99,3 +99,28 @@ def test_every_call_site_passes_the_declared_number_of_arguments():
         if name.startswith("detrb_") and name in protos:
             n = len(inspect.signature(fn).parameters) - 1          # minus self
             assert n == protos[name], f"cabi_emulator.FakeLib.{name}: {n} parameters, header declares {protos[name]}"
+
+
+def test_handle_entry_points_fail_cleanly_without_a_gpu():
+    """detrb_create on a box without a B200 returns an error code and a message (no fallback, no crash); the handle functions
+    reject NULL; detrb_destroy(NULL) is a no-op.  (The per-thread switch behaviour is a -m gpu test: tests/test_api_gpu.py.)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from detr_tensorflow_b200 import _lib
+    L = ctypes.CDLL(_lib.build())
+    L.detrb_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    rc = L.detrb_create(ctypes.c_int(0), ctypes.byref(h))
+    assert rc < 0 and not h.value and L.detrb_last_error()
+    assert L.detrb_create(ctypes.c_int(0), None) == -1
+    assert L.detrb_destroy(None) == 0
+    v = ctypes.c_int()
+    assert L.detrb_handle_set(None, ctypes.c_int(0), ctypes.c_int(1)) == -1
+    assert L.detrb_handle_get(None, ctypes.c_int(0), ctypes.byref(v)) == -1
+    assert L.detrb_bind(None) == -1 and b"live handle" in L.detrb_last_error()
+    # the option table of the Python wrapper mirrors the header's enum
+    from detr_tensorflow_b200 import ops
+    enum = dict((k.lower(), int(n)) for k, n in re.findall(r"DETRB_OPT_([A-Z_]+) = (\d+)", _header()))
+    count = enum.pop("count")
+    assert ops.OPTIONS == enum and count == len(enum)

@@ -224,3 +224,58 @@ def test_fit_fused_step_equals_the_two_reference_calls(D):
     moved = max(float((a[1][n].float() - torch.as_tensor(P[n]).float().to(a[1][n].device)).abs().max()) for n in a[1] if not n.startswith("backbone/"))
     assert moved > 0
     assert set(a[3].keys()) == set(b[3].keys())                              # same log keys (losses + learning rates)
+
+
+def test_handles_own_the_device_and_a_per_thread_kernel_policy(D):
+    """include/detrb.h "Handles": detrb_create checks the device, a handle carries its own switches, detrb_bind installs them for
+    the calling thread only -- a thread that bound a handle with the tcgen05 GEMM switched off runs the mma.sync kernel and gets
+    the same product, while the main thread's switches (and a second handle) stay untouched."""
+    import threading
+    from detr_tensorflow_b200 import _lib, ops
+    with pytest.raises(_lib.DetrbError):
+        ops.Handle(torch.cuda.device_count() + 3)
+    before = {k: None for k in ("tc", "tc_stream", "tc_halo")}
+    for k in before:                                    # the main thread's current values (read through the setters)
+        f = getattr(ops, "set_" + k)
+        before[k] = f(1)
+        f(before[k])
+    h1, h2 = ops.Handle(0), ops.Handle(0)
+    assert h1.device_index == 0 and h1.get("tc") == before["tc"] and h1.get("tc_pair") == -1
+    h1.set("tc", 0)
+    h1.set("tc_stream", 0)
+    assert h2.get("tc") == before["tc"] and h2.get("tc_stream") == before["tc_stream"]          # handles are independent
+    with pytest.raises(KeyError):
+        h1.set("no_such_option", 1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 384, 128, 256
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    ref = A.float() @ W.float().t()
+    out, seen = {}, {}
+
+    def worker():
+        h1.bind()
+        seen["tc"] = ops.set_tc(0)                      # previous value of THIS thread = the handle's
+        seen["stream"] = ops.set_tc_stream(0)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), C=C, ldc=N)
+        s.synchronize()
+        out["worker"] = C
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert seen == {"tc": 0, "stream": 0}
+    assert ops.set_tc(before["tc"]) == before["tc"] and ops.set_tc_stream(before["tc_stream"]) == before["tc_stream"]   # main thread untouched
+    C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.igemm(A, W, M, N, K, K, K, ops.plain_geom(M, K), C=C, ldc=N)
+    torch.cuda.synchronize()
+    assert rel(C, ref) < 4e-3 and rel(out["worker"], ref) < 4e-3
+    h2.bind()                                           # binding a default handle leaves this thread on the defaults
+    assert ops.set_tc(before["tc"]) == before["tc"]
+    h1.close()
+    h2.close()
+    eng = D.get_detr_model(_cfg(D, 1, None), include_top=True, num_encoder_layers=1, num_decoder_layers=1).engine
+    assert eng.handle is not None and eng.handle.device_index == torch.cuda.current_device()
