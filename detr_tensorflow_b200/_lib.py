@@ -17,7 +17,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.environ.get("DETRB_SO") or os.path.join(_HERE, "libdetrb.so")
 _SOURCES = ["abi.cu", "igemm.cu", "wgrad.cu", "attention.cu", "elementwise.cu", "matcher.cu", "optim.cu", "gemm_tc.cu", "tma_maps.cu", "wgrad_tc.cu", "pipeline.cu", "attention_tc.cu", "conv_halo.cu", "handle.cu"]
 _lib = None
-ABI_VERSION = 222          # detrb_version() of the library these ctypes structures / call sites were written for
+ABI_VERSION = 223          # detrb_version() of the library these ctypes structures / call sites were written for
 
 EXPORTS = [
     "detrb_version", "detrb_last_error", "detrb_check_device", "detrb_set_pdl", "detrb_igemm", "detrb_wgrad", "detrb_attn_fwd",
@@ -25,7 +25,7 @@ EXPORTS = [
     "detrb_image_to_nhwc4", "detrb_image_to_s2d16", "detrb_f32_to_bf16", "detrb_colsum", "detrb_maxpool_fwd", "detrb_maxpool_bwd",
     "detrb_matcher", "detrb_set_loss", "detrb_adam_clipnorm", "detrb_prep_weight", "detrb_dropout_mask",
     "detrb_set_tc", "detrb_set_tc_conv", "detrb_set_tc_tma_epilogue", "detrb_set_tc_persistent", "detrb_gemm_tc_force", "detrb_prep_weights_multi", "detrb_adam_clipnorm_chunked", "detrb_set_tc_wgrad", "detrb_wgrad_tc_force",
-    "detrb_create", "detrb_destroy", "detrb_handle_device", "detrb_handle_set", "detrb_handle_get", "detrb_bind",
+    "detrb_create", "detrb_destroy", "detrb_handle_device", "detrb_handle_set", "detrb_handle_get", "detrb_bind", "detrb_set_wgrad_tile",
     "detrb_attn_dropout_mask", "detrb_normalize_u8", "detrb_image_u8_to_s2d16", "detrb_postprocess", "detrb_accumulate", "detrb_set_tc_attn", "detrb_map_match", "detrb_resize_affine_u8", "detrb_set_tc_stream", "detrb_set_tc_halo", "detrb_set_tc_pair",
 ]
 

@@ -12,7 +12,7 @@ void detrb_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-extern "C" int detrb_version(void) { return 222; }   // 0.2.2.2: handles (detrb_create / detrb_bind), thread-local policy switches;  0.2.2.1: detrb_attn_bwd_t.parts;  0.2.2: detrb_igemm_t.scratch;  0.2.1: 1-bit ReLU masks (mask_bits / out_bits), detrb_resize_affine_u8;  0.2.0: parity-precision planes, detrb_accumulate, set_loss status
+extern "C" int detrb_version(void) { return 223; }   // 0.2.2.3: detrb_set_wgrad_tile;  0.2.2.2: handles (detrb_create / detrb_bind), thread-local policy switches;  0.2.2.1: detrb_attn_bwd_t.parts;  0.2.2: detrb_igemm_t.scratch;  0.2.1: 1-bit ReLU masks (mask_bits / out_bits), detrb_resize_affine_u8;  0.2.0: parity-precision planes, detrb_accumulate, set_loss status
 // (bump on EVERY change of a struct or prototype in include/detrb.h: _lib.py refuses to load a library of another version)
 
 extern "C" const char *detrb_last_error(void) { return g_err; }

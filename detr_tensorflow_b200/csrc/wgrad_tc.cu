@@ -17,11 +17,15 @@ namespace {
 constexpr int WN = 128;                 // dW rows per CTA (output channels)  = UMMA M
 constexpr int WK = 128;                 // dW cols per CTA (tap*Cin + c)      = UMMA N
 constexpr int WP = 64;                  // pixels per pipeline stage (4 UMMAs of K = 16)
-constexpr int WSTAGES = 3;
 constexpr int BOX_BYTES = WP * 128;     // one [64 pixels x 64 channels] bf16 box
-constexpr int WSTAGE_BYTES = 4 * BOX_BYTES;
-constexpr int WSMEM = WSTAGES * WSTAGE_BYTES + 256 + 1024;
 constexpr int WTHREADS = 192;
+// Tile variants <NA, KT>: NA accumulators of 128 output channels x KT k-columns per CTA.  <1,128> is the base tile (32 KB per
+// 64-pixel stage, two CTAs per SM).  On the deep layers the base tile is bound by the L2 -> shared-memory path (64 FLOP per
+// staged byte: ~15 TB/s for ~830 TFLOP/s, tests/time_wgrad_shapes.py); the wider tiles stage fewer bytes per FLOP -- <1,256> and
+// <2,128> 85 FLOP/B (48 KB stages), <2,256> 128 FLOP/B (64 KB stages, all 512 TMEM columns) -- on one CTA per SM.
+__host__ __device__ constexpr int wgrad_stage_bytes(int na, int kt) { return (2 * na + kt / 64) * BOX_BYTES; }
+__host__ __device__ constexpr int wgrad_stages(int na, int kt) { return na * kt == 128 ? 3 : na * kt == 256 ? 4 : 3; }
+__host__ __device__ constexpr int wgrad_smem(int na, int kt) { return wgrad_stages(na, kt) * wgrad_stage_bytes(na, kt) + 256 + 1024; }
 
 // MN-major 128B-swizzled operand: 64-element (128 B) rows, one per K index (pixel); 8-pixel swizzle atoms 1024 B apart
 // (SBO); the next 64-channel block of the MN dimension lives one box further (LBO = BOX_BYTES).
@@ -35,19 +39,21 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     return d;
 }
 // kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t WIDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WK >> 3) << 17) | ((uint32_t)(WN >> 4) << 24);
+__host__ __device__ constexpr uint32_t wgrad_idesc(int kt) { return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kt >> 3) << 17) | ((uint32_t)(WN >> 4) << 24); }
 
 // SPLIT (parity precision, include/detrb.h): dY and A are bf16 pairs (lo planes through map_y2 / map_x2); the pixel range is
 // walked three times -- dY_hi^T A_hi, dY_lo^T A_hi, dY_hi^T A_lo -- into the same TMEM accumulator.
-template <bool IM2COL, bool SPLIT>
+template <bool IM2COL, bool SPLIT, int NA, int KT>
 __global__ void __launch_bounds__(WTHREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_y2, const __grid_constant__ CUtensorMap map_x2, const detrb_wgrad_t p,
                 const int pix_per_split, const int stem_mask, const int interleave)
 {
-    constexpr int KT = WK;                                              // k columns of this CTA's dW tile (TMEM columns)
-    constexpr int STG = WSTAGES;
-    constexpr int STG_BYTES = WSTAGE_BYTES;
+    constexpr int NBY = 2 * NA, NBX = KT / 64;                          // dY / gathered boxes per stage
+    constexpr int STG = wgrad_stages(NA, KT);
+    constexpr int STG_BYTES = wgrad_stage_bytes(NA, KT);
+    constexpr int TCOLS = NA * KT;                                      // TMEM columns: accumulator a at column a * KT
+    constexpr uint32_t IDESC = wgrad_idesc(KT);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STG * STG_BYTES;
@@ -58,7 +64,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = blockIdx.x * KT, n0 = blockIdx.y * WN;
+    const int k0 = blockIdx.x * KT, n0 = blockIdx.y * (WN * NA);
     // pixel blocks of this split: a contiguous range, or (interleave) every gridDim.z-th 64-pixel block -- then all CTAs together sweep
     // the pixel range front to back like the data-gradient kernel that runs beside this one on the main stream and reads the same
     // dY: whichever of the two comes second finds it in L2 (the reduction over pixels does not care about the order)
@@ -79,7 +85,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)KT) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"((uint32_t)TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_trigger();
@@ -91,12 +97,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
-            // the two 64-wide k blocks of this tile: (tap, channel offset)
-            int tap[2], cc[2];
+            // the 64-wide k blocks of this tile: (tap, channel offset); blocks past K (a partial last tile) gather tap 0 -- their
+            // columns are dropped in the epilogue
+            int tap[NBX], cc[NBX];
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
+            for (int j = 0; j < NBX; j++) {
                 const int k = k0 + j * 64;
-                tap[j] = k / p.Cin; cc[j] = k - tap[j] * p.Cin;
+                tap[j] = k < p.K ? k / p.Cin : 0; cc[j] = k < p.K ? k - tap[j] * p.Cin : 0;
             }
             const int ohw = p.OH * p.OW;
             int stage = 0; uint32_t phase = 0;
@@ -108,21 +115,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(full_bar(stage), STG_BYTES);
                 const uint32_t dst = smem_base + stage * STG_BYTES;
-                tma_load_2d(dst, py, full_bar(stage), n0, m);                             // dY[m.., n0 .. n0+64)
-                tma_load_2d(dst + BOX_BYTES, py, full_bar(stage), n0 + 64, m);
+#pragma unroll
+                for (int j = 0; j < NBY; j++)
+                    tma_load_2d(dst + j * BOX_BYTES, py, full_bar(stage), n0 + 64 * j, m);       // dY[m.., n0 + 64 j ..): zero fill past N
                 if (IM2COL) {
                     const int img = m / ohw, rem = m - img * ohw, oy = rem / p.OW, ox = rem - oy * p.OW;
                     const int w0 = ox * p.stride - p.pad, h0 = oy * p.stride - p.pad;
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
+                    for (int j = 0; j < NBX; j++) {
                         const int kh = tap[j] / p.KW, kw = tap[j] - kh * p.KW;
-                        tma_load_im2col(dst + (2 + j) * BOX_BYTES, px, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
+                        tma_load_im2col(dst + (NBY + j) * BOX_BYTES, px, full_bar(stage), cc[j], w0, h0, img, (uint16_t)kw, (uint16_t)kh);
                     }
                 } else {
                     // sliding-window A (a_kb_rows > 0): 64-column block j is the 64-element run j * a_kb_rows rows further down
                     const int kb = k0 / 64, sl = p.a_kb_rows;
-                    tma_load_2d(dst + 2 * BOX_BYTES, px, full_bar(stage), sl ? 0 : k0, m + kb * sl);
-                    tma_load_2d(dst + 3 * BOX_BYTES, px, full_bar(stage), sl ? 0 : k0 + 64, m + (kb + 1) * sl);
+#pragma unroll
+                    for (int j = 0; j < NBX; j++)
+                        tma_load_2d(dst + (NBY + j) * BOX_BYTES, px, full_bar(stage), sl ? 0 : k0 + 64 * j, m + (kb + j) * sl);
                 }
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
@@ -135,11 +144,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 const uint32_t base = smem_base + stage * STG_BYTES;
-                const uint64_t da = make_desc_mn(base);
-                const uint64_t db = make_desc_mn(base + 2 * BOX_BYTES);
+                const uint64_t db = make_desc_mn(base + NBY * BOX_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < WP / 16; ks++)      // 16 pixels = 2 swizzle atoms = 2048 B further down the box
-                    tc_mma_f16(tmem_base, da + (uint64_t)(ks * (2048 >> 4)), db + (uint64_t)(ks * (2048 >> 4)), WIDESC, (st | ks) != 0);
+#pragma unroll
+                    for (int a = 0; a < NA; a++)          // accumulator a: output channels n0 + 128 a .. (dY boxes 2a, 2a + 1)
+                        tc_mma_f16(tmem_base + (uint32_t)(a * KT), make_desc_mn(base + a * 2 * BOX_BYTES) + (uint64_t)(ks * (2048 >> 4)),
+                                   db + (uint64_t)(ks * (2048 >> 4)), IDESC, (st | ks) != 0);
                 tc_commit(empty_bar(stage));
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
@@ -152,39 +163,48 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
             // row r at r*128 B, its 16-byte chunk c (8 channels) at chunk c ^ (r % 8) (128-byte swizzle)
             const int te = threadIdx.x - 64, cp = te & 63, half = te >> 6;
             const uint32_t box_off = (uint32_t)(cp >> 5) * BOX_BYTES, chunk = (uint32_t)((cp & 31) >> 2), within = (uint32_t)(cp & 3) * 4u;
-            float s0 = 0.f, s1 = 0.f;
+            float s0[NA], s1[NA];
+#pragma unroll
+            for (int a = 0; a < NA; a++) { s0[a] = 0.f; s1[a] = 0.f; }
             int stage = 0; uint32_t phase = 0;
             for (int st = 0; st < nsteps; st++) {
                 mbar_wait(full_bar(stage), phase);
                 const uint32_t base = smem_base + stage * STG_BYTES + box_off + within;
                 const bool count = !SPLIT || st < 2 * nsteps1;            // the third pass stages dY_hi again
+#pragma unroll
+                for (int a = 0; a < NA; a++) {
 #pragma unroll 8
-                for (int r = half * 32; count && r < half * 32 + 32; r++) {
-                    uint32_t u;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(base + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
-                    const float2 f = unpack_bf16x2(u);
-                    s0 += f.x; s1 += f.y;
+                    for (int r = half * 32; count && r < half * 32 + 32; r++) {
+                        uint32_t u;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(base + (uint32_t)(a * 2 * BOX_BYTES) + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+                        const float2 f = unpack_bf16x2(u);
+                        s0[a] += f.x; s1[a] += f.y;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_bar(stage));            // this warp is done reading the stage
                 if (++stage == STG) { stage = 0; phase ^= 1; }
             }
-            const int nb = n0 + 2 * cp;
-            if (nb < p.N) atomicAdd(p.dbias + nb, s0 * (p.rowscale ? p.rowscale[nb] : 1.f));
-            if (nb + 1 < p.N) atomicAdd(p.dbias + nb + 1, s1 * (p.rowscale ? p.rowscale[nb + 1] : 1.f));
+#pragma unroll
+            for (int a = 0; a < NA; a++) {
+                const int nb = n0 + a * WN + 2 * cp;
+                if (nb < p.N) atomicAdd(p.dbias + nb, s0[a] * (p.rowscale ? p.rowscale[nb] : 1.f));
+                if (nb + 1 < p.N) atomicAdd(p.dbias + nb + 1, s1[a] * (p.rowscale ? p.rowscale[nb + 1] : 1.f));
+            }
         }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;
-        const int n = n0 + q * 32 + lane;
-        const bool row_ok = n < p.N;
-        const float sc = (row_ok && p.rowscale) ? p.rowscale[n] : 1.f;
-        float *drow = p.dW + (size_t)(row_ok ? n : 0) * p.ldw;
         const bool vec_ok = (p.ldw % 4 == 0) && (((uintptr_t)p.dW & 15) == 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < KT; c0 += 16) {
+        for (int ac = 0; ac < NA * KT; ac += 16) {
+            const int a = ac / KT, c0 = ac - a * KT;
+            const int n = n0 + a * WN + q * 32 + lane;
+            const bool row_ok = n < p.N;
+            const float sc = (row_ok && p.rowscale) ? p.rowscale[n] : 1.f;
+            float *drow = p.dW + (size_t)(row_ok ? n : 0) * p.ldw;
             uint32_t r[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ac, r);
             tc_wait_ld();
             if (!row_ok) continue;
 #pragma unroll
@@ -220,7 +240,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)KT) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
     }
 }
 
@@ -406,6 +426,21 @@ bool detrb_wgrad_tc_profitable(const detrb_wgrad_t &p)
     return p.M >= 16384 || (p.M >= min_m && (long)p.N * p.K >= min_nk);
 }
 
+static int g_wgrad_tile = 0;            // developer switch, see detrb_wgrad_tc (detrb_set_wgrad_tile / env DETRB_WGRAD_TILE)
+extern "C" int detrb_set_wgrad_tile(int mode) { int old = g_wgrad_tile; g_wgrad_tile = mode; return old; }
+
+// which tile for which layer (tests/time_wgrad_shapes.py on B200, isolated launches)
+static void wgrad_tile_policy(const detrb_wgrad_t &p, int *na, int *kt)
+{
+    // profiles/r02_wgrad_tiles.log: launched alone the 128 x 256 tile is 5-15 % faster on the backbone's deep layers (layer2 3x3,
+    // layer3 / layer4 1x1, layer3 3x3), the 256-channel tiles (NA = 2) are slower everywhere.  Inside the train step, where the
+    // weight gradients share the GPU with the data-gradient chain of the main stream, the wide tile changes nothing (11.46 / 11.45 ms
+    // base tile vs 11.48 / 11.48 ms, profiles/r02_wgrad_tile_step_ab.log): the base tile (two CTAs per SM) stays the policy, the
+    // wide tiles stay selectable (detrb_set_wgrad_tile, tests/test_gemm_tc_gpu.py::test_wgrad_tc_wide_tiles)
+    (void)p;
+    *na = 1; *kt = WK;
+}
+
 int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
 {
     const bool plain = p.KH == 1 && p.KW == 1 && p.stride == 1 && p.pad == 0;
@@ -464,39 +499,60 @@ int detrb_wgrad_tc(const detrb_wgrad_t &p, cudaStream_t stream)
             return DETRB_OK;
         }
     }
-    const int kt = WK;
-    const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN);
-    // one wave of 2 CTAs per SM (fewer fp32 atomics per gradient element) -- rounded DOWN: 36 tiles x 9 splits = 324 CTAs on 296
-    // slots ran a second, nearly empty wave (ncu, round 2: SMs active 56 % of the 3x3 256->256 kernel's duration)
-    int splits = (148 * 2) / tiles;
+    // tile variant <NA, KT> (see the top of the file).  g_wgrad_tile: 0 = policy, 1 = base tile everywhere, 2 / 3 / 4 = <1,256> / <2,128> /
+    // <2,256> wherever the shape allows (tests, tuning runs; env DETRB_WGRAD_TILE presets it)
+    static bool env_read = false;
+    if (!env_read) { env_read = true; if (const char *e = getenv("DETRB_WGRAD_TILE")) g_wgrad_tile = atoi(e); }
+    int na = 1, kt = WK;
+    if (!sp && !p.a_kb_rows && !p.k_mask) {
+        const bool wide_k = p.K >= 256, wide_n = p.N >= 256;
+        if (g_wgrad_tile == 0) wgrad_tile_policy(p, &na, &kt);
+        else if (g_wgrad_tile == 2 && wide_k) kt = 256;
+        else if (g_wgrad_tile == 3 && wide_n) na = 2;
+        else if (g_wgrad_tile == 4) { if (wide_k) kt = 256; if (wide_n) na = 2; }
+    }
+    const int tiles = ceil_div(p.K, kt) * ceil_div(p.N, WN * na);
+    // one wave: 2 CTAs per SM of the base tile, 1 CTA per SM of the wider ones (fewer fp32 atomics per gradient element) -- rounded
+    // DOWN: 36 tiles x 9 splits = 324 CTAs on 296 slots ran a second, nearly empty wave (ncu, round 2: SMs active 56 % of the 3x3
+    // 256->256 kernel's duration)
+    int splits = (na * kt == 128 ? 148 * 2 : 148) / tiles;
     const int max_splits = ceil_div(p.M, WP * 4);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int pix_per_split = ceil_div(ceil_div(p.M, splits), WP) * WP;
     splits = ceil_div(p.M, pix_per_split);
-    static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      // the opt-in is per device
-    if (!configured) {
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM));
-        configured = true;
-    }
-    dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN), splits);
+    dim3 grid(ceil_div(p.K, kt), ceil_div(p.N, WN * na), splits);
     const int stem_mask = p.k_mask ? 1 : 0;
     // interleaved pixel blocks (env DETRB_WGRAD_INTERLEAVE=1): measured on the full step, no difference (651.2 / 651.5 vs 647.4 / 653.2
     // img/s) -- the two kernels do not stay in lockstep -- so contiguous ranges remain the default
     static int interleave = -1;
     if (interleave < 0) { const char *e = getenv("DETRB_WGRAD_INTERLEAVE"); interleave = e ? atoi(e) : 0; }
-    if (plain && !sp) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask, interleave);
-    } else if (!sp) {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, false>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0, interleave);
+#define DETRB_WGRAD_LAUNCH(IM2COL_, SPLIT_, NA_, KT_, MASK_)                                                                            \
+    do {                                                                                                                                \
+        static detrb_per_device_flag configured_dev; bool &configured = configured_dev.slot();      /* the opt-in is per device */     \
+        if (!configured) {                                                                                                              \
+            DETRB_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<IM2COL_, SPLIT_, NA_, KT_>), cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                            wgrad_smem(NA_, KT_)));                                                                     \
+            configured = true;                                                                                                          \
+        }                                                                                                                               \
+        DETRB_LAUNCH((wgrad_tc_kernel<IM2COL_, SPLIT_, NA_, KT_>), dim3(grid), dim3(WTHREADS), wgrad_smem(NA_, KT_), stream, my, mx, my2, mx2, \
+                     p, pix_per_split, MASK_, interleave);                                                                              \
+    } while (0)
+    if (sp) {
+        if (plain) DETRB_WGRAD_LAUNCH(false, true, 1, 128, stem_mask);
+        else DETRB_WGRAD_LAUNCH(true, true, 1, 128, 0);
     } else if (plain) {
-        DETRB_LAUNCH((wgrad_tc_kernel<false, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, stem_mask, interleave);
+        if (na == 1 && kt == 128) DETRB_WGRAD_LAUNCH(false, false, 1, 128, stem_mask);
+        else if (na == 1) DETRB_WGRAD_LAUNCH(false, false, 1, 256, 0);
+        else if (kt == 128) DETRB_WGRAD_LAUNCH(false, false, 2, 128, 0);
+        else DETRB_WGRAD_LAUNCH(false, false, 2, 256, 0);
     } else {
-        DETRB_LAUNCH((wgrad_tc_kernel<true, true>), dim3(grid), dim3(WTHREADS), WSMEM, stream, my, mx, my2, mx2, p, pix_per_split, 0, interleave);
+        if (na == 1 && kt == 128) DETRB_WGRAD_LAUNCH(true, false, 1, 128, 0);
+        else if (na == 1) DETRB_WGRAD_LAUNCH(true, false, 1, 256, 0);
+        else if (kt == 128) DETRB_WGRAD_LAUNCH(true, false, 2, 128, 0);
+        else DETRB_WGRAD_LAUNCH(true, false, 2, 256, 0);
     }
+#undef DETRB_WGRAD_LAUNCH
     DETRB_CHECK_LAUNCH("wgrad_tc_kernel");
     return DETRB_OK;
 }

@@ -98,6 +98,11 @@ def set_tc_wgrad(enable):
     return _lib.lib().detrb_set_tc_wgrad(c_int(int(enable)))
 
 
+def set_wgrad_tile(mode):
+    """tile of the tcgen05 weight-gradient kernel: 0 policy, 1 128x128, 2 128x256, 3 256x128, 4 256x256; returns the previous mode"""
+    return int(_lib.lib().detrb_set_wgrad_tile(c_int(int(mode))))
+
+
 def set_tc_attn(enable):
     """attention forward on the tcgen05 kernel (attention_tc.cu); returns the previous setting"""
     return _lib.lib().detrb_set_tc_attn(c_int(int(enable)))

@@ -198,6 +198,11 @@ typedef struct {
 int detrb_wgrad(const detrb_wgrad_t *p, detrb_stream_t stream);
 /* tcgen05 weight-gradient kernel (wgrad_tc.cu; MN-major operands straight from TMA): switch + forced entry for tests */
 int detrb_set_tc_wgrad(int enable);
+/* tile of the tcgen05 weight-gradient kernel (process-wide developer switch for tests and tuning runs): 0 = the built-in policy,
+ * 1 = 128 x 128 everywhere, 2 / 3 / 4 = 128 x 256 / 256 x 128 / 256 x 256 (out channels x k columns) wherever the shape allows.
+ * All tiles compute the same sums (the split of the pixel range, hence the fp32 rounding of the merge, differs).  Returns the
+ * previous mode. */
+int detrb_set_wgrad_tile(int mode);
 int detrb_wgrad_tc_force(const detrb_wgrad_t *p, detrb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -227,6 +227,44 @@ def test_wgrad_tc(ops, cin, cout, k, stride, pad, H, W):
     check("wgrad tc vs mma.sync", dW_b, dW_a, 1e-2, tol)
 
 
+@pytest.mark.parametrize("tile", [2, 3, 4])
+@pytest.mark.parametrize("cin,cout,k,stride,pad,H,W", [(256, 256, 3, 1, 1, 50, 84), (128, 128, 3, 1, 1, 31, 45), (256, 512, 1, 2, 0, 26, 38),
+                                                       (1024, 256, 1, 1, 0, 25, 42), (256, 1024, 1, 1, 0, 25, 42), (512, 512, 3, 2, 1, 25, 42),
+                                                       (192, 320, 3, 1, 1, 17, 23), (128, 512, 1, 1, 0, 50, 67)])
+def test_wgrad_tc_wide_tiles(ops, tile, cin, cout, k, stride, pad, H, W):
+    """The wider tiles of the tcgen05 weight-gradient kernel (wgrad_tc_kernel<NA, KT>: 128 x 256, 256 x 128, 256 x 256 out channels x
+    k columns, one CTA per SM) against torch and against the base 128 x 128 tile; shapes with partial last tiles in both directions
+    (K = 1152 / 1728 with KT = 256, N = 320 with NA = 2) and the fused bias gradient of the second accumulator."""
+    B = 2
+    oh, ow = _out(H, k, stride, pad), _out(W, k, stride, pad)
+    M, K = B * oh * ow, k * k * cin
+    x = rnd(B, H, W, cin, seed=1).to(BF)
+    dy = rnd(M, cout, seed=2).to(BF)
+    scale = rnd(cout, seed=3).abs() + 0.5
+    g = conv_geom(B, H, W, cin, oh, ow, k, k, stride, pad)
+    res = {}
+    for mode in (1, tile):
+        old = ops.set_wgrad_tile(mode)
+        try:
+            dW = torch.zeros(cout, K, dtype=F32, device="cuda")
+            db = torch.zeros(cout, dtype=F32, device="cuda")
+            ops.wgrad(x, cin, dy, cout, M, cout, K, g, dW, K, rowscale=scale, dbias=db, force_tc=True)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_wgrad_tile(old)
+        res[mode] = (dW, db)
+    xt = x.float().permute(0, 3, 1, 2)
+    wt = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
+    o = F.conv2d(xt, wt, stride=stride, padding=pad)
+    gw, = torch.autograd.grad(o, [wt], dy.float().view(B, oh, ow, cout).permute(0, 3, 1, 2))
+    ref = gw.permute(0, 2, 3, 1).reshape(cout, K) * scale[:, None]
+    ref_b = dy.float().sum(0) * scale
+    tol = 1e-2 * float(ref.abs().max())
+    check("wide tile vs torch", res[tile][0], ref, 1e-2, tol)
+    check("wide tile vs base tile", res[tile][0], res[1][0], 1e-3, 1e-3 * float(ref.abs().max()))
+    check("wide tile bias gradient", res[tile][1], ref_b, 2e-3, 2e-3 * float(ref_b.abs().max()) + 1e-3)
+
+
 # ------------------------------------------------------------------------------------------------ stem as a sliding-window GEMM
 @pytest.mark.parametrize("H,W", [(37, 45), (64, 96), (160, 224), (400, 667)])
 def test_stem_sliding_window_gemm_pool_and_wgrad(ops, H, W):
