@@ -442,7 +442,7 @@ def main():
     # the weight gradients once more with the side stream off (same step, kernels serialised on the main stream): a kernel's own
     # duration, which is what a roofline fraction describes -- beside the data-gradient chain the same launch shares HBM / SMs with
     # another kernel and takes 1.5-1.7x as long (both figures are reported)
-    eng.probe_names = (p_t + "#wgrad", p_h + "#wgrad")
+    eng.probe_names = (p_t + "#wgrad", p_h + "#wgrad", p_h + "#dgrad", p_c + "#dgrad")
     eng.probe_events = {}
     saved_overlap, eng.overlap_wgrad = eng.overlap_wgrad, False
     for _ in range(3):
@@ -501,17 +501,29 @@ def main():
                                              2.0 * Mt * st.N * st.K, med_alone(p_t + "#wgrad"), traffic("wgrad_kernel_traffic.json")),
                                   us_beside_data_gradient_chain=med(p_t + "#wgrad") * 1e6),
             "dgrad_conv1x1_layer1": hbm_obj(f"gemm_stream_kernel<64,bits-in>: data gradient of the layer1 1x1 conv 256->64 + 1-bit ReLU mask, M={Mh}",
-                                            2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8, med(p_h + "#dgrad")),
+                                            2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8, med(p_h + "#dgrad"), traffic("stream_dgrad_kernel_traffic.json")),
             "conv3x3_layer1_halo": dict(tensor_obj(f"conv3x3_halo_kernel: 3x3 conv 64->64 + ReLU, layer1 (every input row staged once, nine taps = nine "
                                                    f"descriptor views), M={Mh} N=64 K=576", 2.0 * Mh * 64 * 576, med(p_c), traffic("halo_kernel_traffic.json")),
                                         hbm_gbs=(2.0 * 2 * Mh * 64 + Mh * 8) / med(p_c) / 1e9),
             "dgrad_conv3x3_layer1_halo": tensor_obj(f"conv3x3_halo_kernel: data gradient of the same conv (+ 1-bit ReLU mask), M={Mh}",
-                                                    2.0 * Mh * 64 * 576, med(p_c + "#dgrad")),
+                                                    2.0 * Mh * 64 * 576, med(p_c + "#dgrad"), traffic("halo_dgrad_kernel_traffic.json")),
             "attention_fwd": tensor_obj(f"encoder self-attention forward, B={B} H=8 S={S} dh=32 (QK^T + PV flops; {B * 8 * S * S / 1e6:.1f} M exponentials)",
-                                        4.0 * B * 8 * S * S * 32, med("e2_attn#fwd")),
+                                        4.0 * B * 8 * S * S * 32, med("e2_attn#fwd"), traffic("attn_fwd_kernel_traffic.json")),
             "attention_bwd": tensor_obj(f"encoder self-attention backward (delta + dK/dV + dQ kernels), B={B} H=8 S={S} dh=32",
-                                        14.0 * B * 8 * S * S * 32, med("e2_attn#bwd")),
+                                        14.0 * B * 8 * S * S * 32, med("e2_attn#bwd"), traffic("attn_bwd_kernel_traffic.json")),
         }
+        # the two data-gradient launches above are timed where they run: beside the weight-gradient kernels of the side stream, which
+        # read the same dY (HBM and SMs are shared: 1.5-2x the kernel's own duration).  The kernel's own figure -- the same step with
+        # the side stream off, what ncu sees for the isolated launch (profiles/r02_ncu_dgrad_kernels.txt) -- is reported next to it
+        for key, probe, byts in (("dgrad_conv1x1_layer1", p_h + "#dgrad", 2.0 * (Mh * sh.N + sh.N * sh.K + Mh * sh.K) + Mh * sh.K / 8),
+                                 ("dgrad_conv3x3_layer1_halo", p_c + "#dgrad", None)):
+            if probe in times_alone and times_alone[probe]:
+                ta = med_alone(probe)
+                roofs[key]["alone"] = {"us_per_launch": ta * 1e6, "note": "side stream off: the kernel alone on the GPU"}
+                if byts is not None:
+                    roofs[key]["alone"].update(achieved=byts / ta / 1e9, frac=byts / ta / 1e9 / peak_hbm)
+                else:
+                    roofs[key]["alone"].update(achieved=roofs[key]["flops_per_launch"] / ta / 1e12, frac=roofs[key]["flops_per_launch"] / ta / 1e12 / peak_tf)
         shares = os.path.join(ROOT, "profiles", "family_shares.json")
         if os.path.exists(shares):
             roof["family_shares_of_step"] = json.load(open(shares))

@@ -13,3 +13,5 @@ PY
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-300
 timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_final.csv python tests/profile_step.py > gpurun_out/profile_step_final.log 2>&1
 python tests/summarize_launches.py gpurun_out/launches_final.csv 70 > gpurun_out/launches_final_summary.txt; head -4 gpurun_out/launches_final_summary.txt
+timeout 300 python bench.py --backbone resnet101 --batch 4 --no-cpu-baseline --no-matcher-bench > gpurun_out/bench_final_r101.json 2> gpurun_out/bench_final_r101.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_final_r101.json')); print('R101 B=4', round(d['value'],1), 'e2e', round(d['e2e']['value'],1))" || tail -3 gpurun_out/bench_final_r101.err
