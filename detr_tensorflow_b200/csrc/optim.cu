@@ -151,11 +151,17 @@ prep_weights_multi_kernel(const detrb_prep_desc_t *descs, int nslots, long long 
     pdl_wait();         // predecessor complete, its writes visible
     __shared__ float tile[PT][PT + 1];
     const int t = blockIdx.x;
-    int lo = 0, hi = nslots - 1;                       // last slot whose tile_begin <= t
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
-    }
+    // this tile's slot = the last one whose tile_begin <= t (tile_begin ascends from 0): counted by the whole block with one load per
+    // thread -- a binary search is seven DEPENDENT global loads at the start of a block that lives for ~3 us
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < nslots; i += 256) cnt += descs[i].tile_begin <= t ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    const int lo = s_cnt - 1;
     const detrb_prep_desc_t d = descs[lo];
     const int local = t - d.tile_begin;
     const int ct = (d.Cin + PT - 1) / PT, nt = (d.N + PT - 1) / PT;

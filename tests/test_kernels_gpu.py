@@ -368,6 +368,29 @@ def test_maxpool_fwd_bwd(ops):
     assert rel < 0.05, rel
 
 
+@pytest.mark.parametrize("H,W", [(21, 27), (64, 90), (7, 8)])
+def test_maxpool_fwd_argmax_tie_rule(ops, H, W):
+    """The packed bf16x2 forward (maxpool_fwd_bf16_kernel) against a torch restatement of the rule the backward pass relies on: taps
+    scanned in row-major order, padding absent, the FIRST maximum wins (strict >), a maximum that is not positive is stored as tap
+    15 -- on inputs full of ties (values quantised to quarters, exact zeros after the ReLU)."""
+    B, C = 2, 64
+    oh, ow = _out(H, 3, 2, 1), _out(W, 3, 2, 1)
+    g = torch.Generator().manual_seed(9)
+    for x in (torch.round(F.relu(torch.randn(B, H, W, C, generator=g)) * 4) / 4, F.relu(torch.randn(B, H, W, C, generator=g) - 0.8),
+              torch.randn(B, H, W, C, generator=g)):
+        xb = dev(x.to(BF))
+        y = torch.zeros(B, oh, ow, C, dtype=BF, device="cuda")
+        arg = torch.full((B, oh, ow, C), 99, dtype=torch.uint8, device="cuda")
+        ops.maxpool_fwd(xb, y, arg, B, H, W, C, oh, ow)
+        torch.cuda.synchronize()
+        xp = F.pad(xb.float().cpu().permute(0, 3, 1, 2), (1, 1, 1, 1), value=float("-inf"))
+        patches = F.unfold(xp, 3, stride=2).view(B, C, 9, oh, ow)
+        mx, ref_arg = patches.max(dim=2).values, patches.argmax(dim=2)         # argmax: index of the first maximal value
+        ref_arg[~(mx > 0)] = 15
+        assert torch.equal(y.float().cpu(), mx.permute(0, 2, 3, 1))
+        assert torch.equal(arg.cpu().long(), ref_arg.permute(0, 2, 3, 1))
+
+
 # ------------------------------------------------------------------------------------------------ matcher / loss
 def _run_matcher(ops, logits, boxes, t_bbox, t_class, want_cost=True):
     P, Q, C = logits.shape
