@@ -1230,14 +1230,28 @@ class Engine:
         self.launches += 1
         self._before_write(g_in)
         HP, WP = self.hw_pad
-        ops.maxpool_bwd(g_out, a["pool_arg"], g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
-                        XH=HP, XW=WP, split=self.plane)
         stem = self.slots["backbone/conv1"]
         self.launches += 1
         x, Ms = a["s2d"], self.M_stem
         before_stem = self._w_last if self._w_last is not None else True
-        self._on_wstream(lambda: ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
-                                           rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True, split=self.plane), (x, g_in))
+        pool_arg = a["pool_arg"]
+
+        def pool_and_stem():
+            ops.maxpool_bwd(g_out, pool_arg, g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
+                            XH=HP, XW=WP, split=self.plane)
+            ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
+                      rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True, split=self.plane)
+        # the max-pool backward feeds nothing but the stem's weight gradient.  DETRB_POOL_BWD_SIDE=1 sends both to the side stream, so
+        # that the optimizer step of everything else (optimizer_step, defer_tail) starts beside the pooling kernel instead of behind
+        # it: measured, no difference (11.42 vs 11.43 ms/step, profiles/r02_pool_bwd_side_ab.log) -- pooling, stem weight gradient
+        # and Adam are all HBM-bound, their sum is what the tail costs either way -- so the pooling kernel stays on the main stream
+        if os.environ.get("DETRB_POOL_BWD_SIDE") != "1":
+            ops.maxpool_bwd(g_out, pool_arg, g_in, B, self.hw_stem[0], self.hw_stem[1], 64, self.hw_pool[0], self.hw_pool[1],
+                            XH=HP, XW=WP, split=self.plane)
+            self._on_wstream(lambda: ops.wgrad(x, 16, g_in, stem.N, Ms, stem.N, stem.K, ops.plain_geom(Ms, stem.K), stem.grad, stem.K,
+                                               rowscale=stem.fold, dbias=stem.bias_grad, a_kb_rows=WP, k_mask=True, split=self.plane), (x, g_in))
+        else:
+            self._on_wstream(pool_and_stem, (x, g_in, g_out, pool_arg))
         self._in_backward = False
         if defer_tail and boundary is None and self._w_last is not None and hasattr(self.lib, "detrb_adam_clipnorm_chunked"):
             self._tail = before_stem                               # joined by optimizer_step()
