@@ -1424,6 +1424,8 @@ class Engine:
             self.launches_per_step = self.launches - n0
             self._graph = graph
             return graph.replay
+        # (One graph with the bucket all-reduces captured inside it was tried once more at the end of round 2 -- torch 2.11 / NCCL 2.28,
+        #  two B200s: the capture completes, the first replay never returns -- a hang, killed by the test's timeout.  The cut stays.)
         # data parallel: the backward pass is cut at the gradient-bucket boundaries into consecutive graphs; bucket k's eager
         # all-reduce is enqueued between graph k and graph k+1 and runs (on NCCL's stream) while graph k+1 computes
         import gc
