@@ -329,6 +329,16 @@ set_loss_kernel(const float *logits, int ldl, const float *boxes, const float *t
     }
 }
 
+// clears the loss accumulators.  A kernel, not cudaMemsetAsync: a memset node between two kernels breaks the programmatic-dependent-
+// launch chain of the stream (the kernel behind it starts with the full launch latency: 13 us between matcher and loss in the
+// step's timeline, tests/trace_step.py)
+__global__ void zero_sums_kernel(float *sums, int n)
+{
+    pdl_trigger();
+    pdl_wait();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sums[i] = 0.f;
+}
+
 __global__ void set_loss_finalize_kernel(const float *sums, const float *t_bbox, int L, int B, int Q,
                                          const float *normalisers, float loss_scale,
                                          float *losses, float *total, const int32_t *status, int nstatus)
@@ -411,7 +421,8 @@ extern "C" int detrb_set_loss(const float *logits, int ldl, const float *boxes, 
     DETRB_REQUIRE(L > 0 && B > 0 && Q > 0 && C > 0 && C <= 128 && ldl >= C, "detrb_set_loss: bad sizes");
     DETRB_REQUIRE(!d_logits || (ld_dl >= C && ld_dl <= 128), "detrb_set_loss: ld_dl=%d", ld_dl);
     DETRB_REQUIRE(!d_boxpre || (ld_db >= 4 && ld_db <= 64), "detrb_set_loss: ld_db=%d", ld_db);
-    DETRB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 8 * L, stream));
+    DETRB_LAUNCH(zero_sums_kernel, dim3(1), dim3(64), 0, stream, sums, 8 * L);
+    DETRB_CHECK_LAUNCH("zero_sums_kernel");
     int rows = L * B * Q;
     DETRB_LAUNCH(set_loss_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, logits, ldl, boxes, t_bbox, t_class, match, L, B, Q, C, background_class,
                                                            normalisers, loss_scale, sums, (bf16 *)d_logits, ld_dl, (bf16 *)d_boxpre, ld_db, (long long)split);

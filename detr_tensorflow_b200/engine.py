@@ -984,7 +984,7 @@ class Engine:
         """get_losses (loss.py:22-34): matcher + set criterion for all decoder layers; fills d_logits/d_boxpre."""
         a, L, B, Q = self.a, self.ndec, self.B, self.Q
         self.match()
-        self.launches += 2
+        self.launches += 3              # clear of the accumulators, loss, finalize
         ops.set_loss(a["logits"], self.C, a["boxes"], a["t_bbox"], a["t_class"], a["match"], L, B, Q, self.C,
                      background_class, self.normalisers, loss_scale, a["loss_sums"], a["losses"], a["total"],
                      a["d_logits"] if with_grad else None, self.ld_dl, a["d_boxpre"] if with_grad else None, 32,
@@ -1025,6 +1025,14 @@ class Engine:
     # ------------------------------------------------------------------------------------------ backward
     def zero_grads(self):
         self.grads.zero_()
+
+    def loss_and_zero_grads(self, background_class, loss_scale=1.0):
+        """The set loss with its gradient, then the clear of the gradient arena (166 MB).  (The clear BESIDE the matcher on a side
+        stream -- the arena is not touched between the previous optimizer step and the first weight gradient -- was measured: no
+        difference, 11.42 vs 11.42 ms/step, profiles/r02_zero_grads_fork_ab.log; the extra cross-stream edges cost what the 24 us
+        kernel costs.)"""
+        self.loss(background_class, loss_scale=loss_scale, with_grad=True)
+        self.zero_grads()
 
     def grad_buckets(self):
         """[lo, hi) ranges of the flat gradient arena in the order the backward pass completes them: transformer + heads
@@ -1372,8 +1380,7 @@ class Engine:
         self._ensure_weights()
         self.seed_dev.add_(1)                   # fresh dropout masks every step, also under graph replay
         self._forward_impl()
-        self.loss(background_class, loss_scale=loss_scale, with_grad=True)
-        self.zero_grads()
+        self.loss_and_zero_grads(background_class, loss_scale)
         if self._distributed():
             works = []
             self.backward(train_backbone=train_backbone, boundary=lambda k: works.append(self.allreduce_bucket(k)))
@@ -1398,8 +1405,7 @@ class Engine:
             self.training = True
             self.seed_dev.add_(1)
             self._forward_impl()
-            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
-            self.zero_grads()
+            self.loss_and_zero_grads(background_class, loss_scale)
             self.backward(train_backbone=train_backbone, defer_tail=not self._distributed())
 
         def part2():
@@ -1449,8 +1455,7 @@ class Engine:
             self.training = True
             self.seed_dev.add_(1)
             self._forward_impl()
-            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
-            self.zero_grads()
+            self.loss_and_zero_grads(background_class, loss_scale)
             self.backward(train_backbone=train_backbone, boundary=cut)      # graphs 0..2 end at the bucket boundaries
             part2()                                                           # graph 3: optimizer
             graphs[-1].capture_end()
@@ -1524,8 +1529,7 @@ class Engine:
             self.training = True
             self.seed_dev.add_(1)
             self._forward_impl()
-            self.loss(background_class, loss_scale=loss_scale, with_grad=True)
-            self.zero_grads()
+            self.loss_and_zero_grads(background_class, loss_scale)
             self.backward(train_backbone=True, boundary=boundary)
         self._ensure_weights()                             # a per-group apply (apply_group) since the last forward pass
         dist_on = self._distributed()
