@@ -815,8 +815,28 @@ class Engine:
         self.input_lut = device_lut(normalized_method, self.device)
         self.input_method = normalized_method
 
-    def _stage_images(self, images):
+    def _stage_images(self, images, direct=False):
+        """images -> the engine's resident input.  direct (training.fit / run_train_step: `images` is a contiguous tensor on this
+        device): the space-to-depth conversion that opens the forward pass runs NOW, reading `images` where it lies, and the replayed
+        launch sequence starts behind it (s2d_staged: _forward_impl skips the conversion) -- instead of a 100 MB device-to-device copy
+        into the resident image buffer in front of every step (env DETRB_STAGE_S2D=0: the copy)."""
         a = self.a
+        self.s2d_staged = False
+        if (direct and images.device == self.device and images.is_contiguous() and tuple(images.shape) == tuple(a["images"].shape)
+                and images.dtype in (torch.uint8, F32) and os.environ.get("DETRB_STAGE_S2D", "1") != "0"):
+            B = self.B
+            HP, WP = self.hw_pad
+            if images.dtype == torch.uint8:
+                if getattr(self, "input_lut", None) is None:
+                    self.set_input_normalisation("torch_resnet")
+                ops.image_u8_to_s2d16(images, self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP,
+                                      split=self.plane)
+            else:
+                ops.image_to_s2d16(images, a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP, split=self.plane)
+            self.launches += 1
+            self.u8_input = images.dtype == torch.uint8
+            self.s2d_staged = True
+            return
         if images.dtype == torch.uint8:
             if getattr(self, "input_lut", None) is None:
                 self.set_input_normalisation("torch_resnet")
@@ -844,12 +864,15 @@ class Engine:
         # ---------------- backbone (resnet_backbone.py:20-32)
         # stem: space-to-depth(2) turns the 7x7/s2 conv into a dense 4x4/s1 conv over 16-channel pixels = a sliding-window GEMM
         HP, WP = self.hw_pad
-        if self.u8_input:                     # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
+        if getattr(self, "s2d_staged", False):
+            pass                              # a["s2d"] was filled from the caller's batch by _stage_images(direct=True)
+        elif self.u8_input:                   # data/processing.py:6-23 fused into the layout change (no fp32 image in HBM)
             ops.image_u8_to_s2d16(a["images_u8"], self.input_lut[0], self.input_lut[1], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP,
                                   split=self.plane)
+            self.launches += 1
         else:
             ops.image_to_s2d16(a["images"], a["s2d"], B, self.H0, self.W0, 2, 2, HP, WP, split=self.plane)
-        self.launches += 1
+            self.launches += 1
         stem = self.slots["backbone/conv1"]
         # one plain GEMM [B*HP*WP, 256] x [64, 256]^T whose A rows are overlapping 128-byte windows of the padded image
         self.launches += 1
@@ -1288,7 +1311,7 @@ class Engine:
         capture does not execute anything, so the caller must have run one step through grads_step / apply_group before (kernel
         attribute set-up, NCCL communicator); group flags and learning rates are read from device memory at replay time."""
         key = (self.plan_key, int(background_class), float(clipnorm), self.normalisers is not None, self.u8_input,
-               getattr(self, "input_method", None), self._distributed())
+               getattr(self, "input_method", None), self._distributed(), getattr(self, "s2d_staged", False))
         if getattr(self, "_fs_key", None) != key:
             self._fs_replay = self.capture_train_step(background_class, clipnorm, warmup=0)
             self._fs_key = key
@@ -1481,11 +1504,11 @@ class Engine:
         return replay
 
     # ------------------------------------------------------------------------------------------ graph-replayed gradient step
-    def stage_inputs(self, images, t_bbox, t_class):
-        """host/device inputs -> the engine's resident buffers (async copies on the current stream)"""
+    def stage_inputs(self, images, t_bbox, t_class, direct=False):
+        """host/device inputs -> the engine's resident buffers (async copies on the current stream; direct: see _stage_images)"""
         B, H, W, _ = images.shape
         self._plan(B, H, W)
-        self._stage_images(images)
+        self._stage_images(images, direct=direct)
         self.set_targets(t_bbox, t_class)
 
     def _capture_bucketed(self, body):
@@ -1542,7 +1565,7 @@ class Engine:
                 w.wait()
             return
         key = (self.plan_key, int(background_class), float(loss_scale), self.normalisers is not None, self.u8_input,
-               getattr(self, "input_method", None), dist_on)
+               getattr(self, "input_method", None), dist_on, getattr(self, "s2d_staged", False))
         if getattr(self, "_gs_key", None) != key:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

@@ -45,7 +45,7 @@ def run_train_step(model, images, t_bbox, t_class, optimizers, config):
     eng = model.engine
     gradient_aggregate = int(config.target_batch // config.batch_size) if config.target_batch is not None else 1
     t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
-    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device))
+    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device), direct=True)
     eng.set_global_normalisers(t_bbox_d)
     # the reference traces this function once (@tf.function, training.py:9); here the launch sequence of
     # forward + losses + backward + gradient all-reduce is captured once per input shape as a CUDA graph and replayed
@@ -63,7 +63,7 @@ def run_train_and_apply_step(model, images, t_bbox, t_class, optimizers, config)
     backward pass.  Used by fit when config.target_batch is None; same results as the two calls it replaces."""
     eng = model.engine
     t_bbox_d = _dev(t_bbox, torch.float32, eng.device)
-    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device))
+    eng.stage_inputs(_dev_img(images, config, eng), t_bbox_d, _dev(t_class, torch.int64, eng.device), direct=True)
     eng.set_global_normalisers(t_bbox_d)
     eng.set_lrs(float(config.backbone_lr), float(config.transformers_lr), float(config.nlayers_lr))
     eng.set_enabled(bool(config.train_backbone), bool(config.train_transformers), bool(getattr(config, "train_nlayers", False)))
@@ -86,8 +86,8 @@ def run_val_step(model, images, t_bbox, t_class, config):
 
 class _Prefetcher:
     """Overlaps the host->device copy of batch i+1 with the compute of batch i: batches are copied on a side stream into two
-    alternating device staging sets; run_train_step then stages them with a device-to-device copy (0.1 ms instead of ~2 ms of
-    PCIe time on the critical path for a 100 MB fp32 batch).  The reference feeds from tf.data, which prefetches the same way."""
+    alternating device staging sets; run_train_step then reads the images where they lie (Engine._stage_images(direct=True): the
+    step's opening layout kernel runs from the staging set, no PCIe time and no extra copy on the critical path).  The reference feeds from tf.data, which prefetches the same way."""
 
     def __init__(self, iterable, device):
         self.it, self.device = iter(iterable), device
