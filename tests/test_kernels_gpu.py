@@ -391,6 +391,33 @@ def test_maxpool_fwd_argmax_tie_rule(ops, H, W):
         assert torch.equal(arg.cpu().long(), ref_arg.permute(0, 2, 3, 1))
 
 
+@pytest.mark.parametrize("H,W", [(21, 27), (64, 90), (7, 8)])
+def test_maxpool_bwd_equals_sequential_fp32_scatter(ops, H, W):
+    """The packed backward (maxpool_bwd_bf16_kernel): every window's gradient goes to the position its stored tap names (tap 15:
+    nowhere), contributions to one input pixel are added in fp32 in window order (oy, then ox) and rounded to bf16 once -- checked
+    bit for bit against numpy's sequential scatter-add, on tie-rich inputs (several windows often name the same pixel)."""
+    B, C = 2, 64
+    oh, ow = _out(H, 3, 2, 1), _out(W, 3, 2, 1)
+    g = torch.Generator().manual_seed(11)
+    x = dev((torch.round(F.relu(torch.randn(B, H, W, C, generator=g)) * 2) / 2).to(BF))
+    y = torch.zeros(B, oh, ow, C, dtype=BF, device="cuda")
+    arg = torch.zeros(B, oh, ow, C, dtype=torch.uint8, device="cuda")
+    ops.maxpool_fwd(x, y, arg, B, H, W, C, oh, ow)
+    dy = dev(torch.randn(B, oh, ow, C, generator=g).to(BF))
+    dx = torch.full((B, H, W, C), 7.0, dtype=BF, device="cuda")
+    ops.maxpool_bwd(dy, arg, dx, B, H, W, C, oh, ow)
+    torch.cuda.synchronize()
+    a = arg.cpu().numpy().astype(np.int64)
+    bb, oy, ox, cc = np.meshgrid(np.arange(B), np.arange(oh), np.arange(ow), np.arange(C), indexing="ij")
+    keep = a != 15
+    iy, ix = 2 * oy - 1 + a // 3, 2 * ox - 1 + a % 3
+    assert keep.any() and (~keep).any()
+    assert ((iy[keep] >= 0) & (iy[keep] < H) & (ix[keep] >= 0) & (ix[keep] < W)).all()
+    ref = np.zeros((B, H, W, C), dtype=np.float32)
+    np.add.at(ref, (bb[keep], iy[keep], ix[keep], cc[keep]), dy.float().cpu().numpy()[keep])      # unbuffered: sequential, C order
+    assert torch.equal(dx.cpu(), torch.from_numpy(ref).to(BF))
+
+
 # ------------------------------------------------------------------------------------------------ matcher / loss
 def _run_matcher(ops, logits, boxes, t_bbox, t_class, want_cost=True):
     P, Q, C = logits.shape
