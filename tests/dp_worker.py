@@ -52,6 +52,16 @@ total, grads = run(img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], Tru
 t = torch.tensor([total])
 dist.all_reduce(t)
 _, grads_b = run(img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], True, bucketed=True)
+# the same step through the PUBLIC API (training.run_train_step: stage_inputs(direct=True) -> grads_step with the bucketed
+# all-reduces, global normalisers), dropout 0 so that the training-mode forward equals the one above
+model = D.get_detr_model(cfg, include_top=True, num_encoder_layers=NE, num_decoder_layers=ND, device="cpu", params=P, dropout=0.0)
+cfg.batch_size, cfg.target_batch = 1, None
+cfg.train_backbone = cfg.train_transformers = True
+opt = D.setup_optimizers(model, cfg)
+_, total_api, log_api, _ = D.training.run_train_step(model, img[rank:rank + 1], tb[rank:rank + 1], tc[rank:rank + 1], opt, cfg)
+assert model.engine.s2d_staged                   # the batch was read where it lies, not copied into the resident image buffer
+grads_api = model.engine.export_grads()
 if rank == 0:
-    torch.save({"total_global": float(t), "grads": grads, "grads_bucketed": grads_b}, f"{outdir}/dp_rank0.pt")
+    torch.save({"total_global": float(t), "grads": grads, "grads_bucketed": grads_b, "grads_api": grads_api,
+                "total_api": float(total_api)}, f"{outdir}/dp_rank0.pt")
 dist.destroy_process_group()

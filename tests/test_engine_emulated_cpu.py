@@ -413,6 +413,9 @@ def test_data_parallel_two_ranks_gloo(tmp_path):
             assert rel(a, b) < 2e-3, (k, rel(a, b))
         # three overlapped bucket all-reduces (Engine.grad_buckets) == the one flat all-reduce, bit for bit
         assert torch.equal(dp["grads_bucketed"][k], a), k
+        # ... and so does the public API (training.run_train_step under torch.distributed: direct staging, bucketed grads_step)
+        assert torch.equal(dp["grads_api"][k], a), k
+    assert abs(dp["total_api"] - single["total"]) < 1e-4 * abs(single["total"])      # logged loss = the GLOBAL loss on every rank
 
 
 def test_finetune_heads_nlayers_group(emu):
